@@ -1,0 +1,202 @@
+/* lattice_b200.h -- C ABI of the B200-native beam-FEM hot path for pyLatticeDSO.
+ *
+ * The reference (Tcadart/pyLatticeDSO) has no FFI layer: its hot path is three
+ * Python callables that delegate to FEniCSx/PETSc.  Each
+ * entry point below names the reference interface (file:line under the
+ * pyLatticeDSO checkout) whose arithmetic it replaces.  INTEGRATION.md shows
+ * the ctypes stub a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every data pointer is a DEVICE pointer (e.g. torch.Tensor.data_ptr());
+ *     the caller owns all buffers; the library allocates only inside lat_ctx
+ *     (workspace, freed by lat_ctx_destroy) and reports sizes by two-call
+ *     queries; FP64 values, int32 indices, int64 sizes.
+ *   - per-node DOF order [ux,uy,uz,rx,ry,rz]; global DOF = 6*node + d
+ *     (pyLatticeDesign/point.py:68).
+ *   - BSR: 6x6 blocks, block rows sorted, column indices sorted inside a row,
+ *     block values row-major, 36 doubles per block.
+ *   - return value: 0 ok; <0 argument error; >0 CUDA/NCCL error (see
+ *     lat_last_error).  PCG non-convergence is NOT an error: it is reported in
+ *     lat_pcg_result.info exactly like conjugate_gradient_solver.py:73,98,103,108.
+ *   - one ctx <-> one device <-> one stream; a ctx is not thread-safe; work is
+ *     enqueued on the ctx stream and only the calls documented as "syncs"
+ *     wait for it.
+ */
+#ifndef LATTICE_B200_H
+#define LATTICE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lat_ctx lat_ctx;
+
+#define LAT_OK 0
+#define LAT_ERR_ARG (-1)
+#define LAT_ERR_STATE (-2)
+#define LAT_ERR_UNSUPPORTED (-3)
+
+/* assembly modes */
+#define LAT_ASM_GATHER 0 /* deterministic: one thread per BSR block gathers its elements */
+#define LAT_ASM_ATOMIC 1 /* one thread per element, warp-aggregated FP64 atomics          */
+
+/* preconditioners */
+#define LAT_PC_NONE 0
+#define LAT_PC_JACOBI 1
+#define LAT_PC_BLOCK6 2
+
+int lat_version(void);
+
+/* stream: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or 0 for
+ * the legacy default stream. */
+int lat_ctx_create(int device, void* stream, lat_ctx** out);
+int lat_ctx_destroy(lat_ctx* ctx);
+const char* lat_last_error(lat_ctx* ctx);
+/* blocks until everything enqueued on the ctx stream is done */
+int lat_ctx_sync(lat_ctx* ctx);
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
+int64_t lat_launch_count(lat_ctx* ctx);
+
+/* ---- A1: 12x12 Timoshenko element stiffness ---------------------------------
+ * Replaces the FFCx element kernel generated from SimulationBase.define_K_form
+ * (pyLatticeSim/simulation_base.py:141-156,190-197,220-225) with the local frame
+ * of BeamModel.calculate_local_coordinate_system (beam_model.py:197-216) and the
+ * section constants of Material.compute_mechanical_properties
+ * (material_definition.py:142-156).  drad != 0 returns dK_e/dr instead
+ * (material_definition.py:207-223).
+ * Ke: [n_elem][12][12] row-major, element DOFs [w1,th1,w2,th2] in global axes. */
+int lat_elem_stiffness(lat_ctx* ctx, const double* x, const double* y, const double* z,
+                       const int32_t* en0, const int32_t* en1, const double* rad,
+                       int64_t n_elem, double young, double nu, double kappa,
+                       int drad, double* Ke);
+
+/* ---- A3: sparsity pattern ----------------------------------------------------
+ * Replaces dolfinx create_matrix / PETSc preallocation behind
+ * fem_petsc.assemble_matrix (simulation_base.py:480-481, schur_complement.py:69-71).
+ * Builds the 6x6 block graph (node adjacency + self) by counting sort on the
+ * row node followed by a segmented per-row sort/unique and scans.
+ * Call 1: lat_bsr_pattern_build  -> *nnzb (kept inside ctx)       [syncs]
+ * Call 2: lat_bsr_pattern_export -> rowptr[n_nodes+1], colidx[nnzb],
+ *         elem_block[n_elem*4] = BSR block index of the (n0,n0),(n0,n1),(n1,n0),
+ *         (n1,n1) quadrants of every element (the scatter map; may be NULL). */
+int lat_bsr_pattern_build(lat_ctx* ctx, const int32_t* en0, const int32_t* en1,
+                          int64_t n_elem, int64_t n_nodes, int64_t* nnzb);
+int lat_bsr_pattern_export(lat_ctx* ctx, int32_t* rowptr, int32_t* colidx, int32_t* elem_block);
+
+/* Scalar CSR structure of a BSR pattern: indptr[6n+1], indices[36 nnzb].
+ * Bit-exact with scipy.sparse.coo_matrix((v,(i,j))).tocsr() + sum_duplicates +
+ * sort_indices fed with all 144 entries of every element (oracle.assemble_csr). */
+int lat_csr_structure(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx,
+                      int64_t n_nodes, int32_t* indptr, int32_t* indices);
+/* BSR block values -> CSR value order (same structure as lat_csr_structure) */
+int lat_bsr_to_csr_values(lat_ctx* ctx, const int32_t* rowptr, int64_t n_nodes,
+                          const double* bsr_vals, double* csr_vals);
+
+/* ---- A1+A3: fused element generation + global assembly ---------------------
+ * K = sum_e P_e^T K_e P_e into BSR values (fem_petsc.assemble_matrix without bcs,
+ * simulation_base.py:480, schur_complement.py:69-71).  Requires the pattern of
+ * the same mesh to be resident in ctx (lat_bsr_pattern_build).  vals[nnzb*36]
+ * is overwritten.  drad != 0 assembles sum_e chain_e * dK_e/dr (chain may be NULL). */
+int lat_assemble_bsr(lat_ctx* ctx, const double* x, const double* y, const double* z,
+                     const int32_t* en0, const int32_t* en1, const double* rad,
+                     const double* chain, int64_t n_elem, int64_t n_nodes,
+                     double young, double nu, double kappa, int mode, int drad,
+                     double* vals);
+
+/* ---- A4: Dirichlet elimination ------------------------------------------------
+ * fem_petsc.assemble_matrix(bcs) + apply_lifting + set_bc (simulation_base.py:480-492):
+ *   vals_bc = rows/cols of constrained DOFs zeroed, unit diagonal (may alias vals);
+ *   b = f - K[:,c] g on free rows, b[c] = g[c].
+ * fixed: uint8[6n] (non-zero = constrained), g,f,b: double[6n]. */
+int lat_apply_dirichlet(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx,
+                        int64_t n_nodes, const double* vals, const uint8_t* fixed,
+                        const double* g, const double* f, double* vals_bc, double* b);
+
+/* ---- A10: y = K x (reactions R = K_unconstrained u, simulation_base.py:582-645) */
+int lat_bsr_spmv(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx,
+                 const double* vals, int64_t n_nodes, const double* x, double* y);
+
+/* ---- A5/A6: preconditioned conjugate gradients -------------------------------
+ * Replaces KSP preonly+LU (simulation_base.py:502-511) and restates
+ * conjugate_gradient_solver (pyLatticeSim/conjugate_gradient_solver.py:15-122).
+ * reference_semantics = 1 reproduces that function's iteration exactly: x0 = 0,
+ * alpha = min(rz/pAp, alpha_max) (:78-79), p <- z every restart_every iterations
+ * (:89-90), stop when |r| <= tol |b| (:97) or |p| < mintol (|x| + 1e-12) (:102),
+ * info 0/1/2 (:73,98,103,108).  reference_semantics = 0 is textbook PCG with the
+ * single test |r| <= tol |b|. */
+typedef struct {
+  double tol;
+  double mintol;
+  double alpha_max;
+  int64_t restart_every;
+  int32_t maxiter;
+  int32_t precond;
+  int32_t reference_semantics;
+  int32_t check_every; /* iterations between host polls of the device status (0 = default 32) */
+} lat_pcg_opts;
+
+typedef struct {
+  int32_t iters;
+  int32_t info;      /* 0 converged, 1 maxiter, 2 alpha < 1e-6 seen (reference flag) */
+  double relres;     /* |r| / |b| at exit (recurrence residual) */
+  double norm_b;
+  double solve_ms;   /* device time of the iteration loop (CUDA events on the ctx stream) */
+  int64_t launches;  /* kernels launched by this call */
+} lat_pcg_result;
+
+/* x is overwritten (x0 = 0).  [syncs] */
+int lat_pcg_bsr(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, const double* vals,
+                int64_t n_nodes, const double* b, double* x, const lat_pcg_opts* opts,
+                lat_pcg_result* result);
+
+/* ---- A11: compliance sensitivity ----------------------------------------------
+ * g[group[e]] -= chain_e * u_e^T (dK_e/dr)(r_e) u_e   (LatticeOpti.calculate_gradient
+ * compliance branch, lattice_opti.py:746-841, sign of :719 included; element form
+ * of lattice_sim.py:1020-1054 with material_definition.py:163-231).
+ * u: [6 n_nodes]; lambda: second vector for adjoint objectives (NULL -> lambda = u,
+ * lattice_opti.py:843-902 uses lambda^T dS u); group: int32[n_elem] (<0 = skip);
+ * chain: NULL -> 1.  g[n_groups] is overwritten.  q_elem (optional) receives the
+ * per-element contribution. */
+int lat_compliance_grad(lat_ctx* ctx, const double* x, const double* y, const double* z,
+                        const int32_t* en0, const int32_t* en1, const double* rad,
+                        const double* chain, const int32_t* group, int64_t n_elem,
+                        double young, double nu, double kappa, const double* u,
+                        const double* lambda, int64_t n_groups, double* g, double* q_elem);
+
+/* ---- A7: batched per-cell Schur complement -----------------------------------
+ * SchurComplement.calculate_schur_complement (schur_complement.py:75-147) via
+ * get_schur_complement (utils_schur.py:22-53) for a batch of cells that share one
+ * local mesh topology (same local connectivity, per-cell coordinates and radii):
+ *   S_c = K_BB - K_BI K_II^-1 K_IB.
+ * Local numbering: the first n_bnd_nodes local nodes are the boundary nodes in
+ * cell.node_in_order_simulation order (cell.py:611-680); the remaining
+ * n_loc_nodes - n_bnd_nodes are interior.
+ *   xyz:  [n_cells][n_loc_nodes][3]   len0/len1: int32[n_loc_elem] local connectivity
+ *   rad:  [n_cells][n_loc_elem]
+ *   S:    [n_cells][6 n_bnd][6 n_bnd] row-major (C order like the reference ndarray)
+ * drad_chain != NULL additionally writes dS/dr_g for n_grad radius groups:
+ *   elem_group int32[n_loc_elem] (<0 none), drad_chain[n_loc_elem] = d rad_e / d r_group,
+ *   dS: [n_cells][n_grad][6 n_bnd][6 n_bnd]  (analytic; replaces the central FD of
+ *   lattice_sim.py:1020-1054). */
+int lat_schur_batch(lat_ctx* ctx, const double* xyz, const int32_t* len0, const int32_t* len1,
+                    const double* rad, int64_t n_cells, int32_t n_loc_nodes, int32_t n_bnd_nodes,
+                    int32_t n_loc_elem, double young, double nu, double kappa, double* S,
+                    const int32_t* elem_group, const double* drad_chain, int32_t n_grad, double* dS);
+
+/* ---- A8: DDM interface operator ------------------------------------------------
+ * y = sum_c B_c S_c B_c^T x  (LatticeSim.calculate_reaction_force_global ->
+ * update_reaction_force_each_cell -> solve_sub_problem, lattice_sim.py:1180-1252,
+ * cell.py:684-750).  S: [n_cells][nb][nb] (or one shared matrix when s_stride = 0),
+ * gidx: int32[n_cells][nb] global free-DOF index of each local boundary DOF or -1
+ * (fixed DOF: contributes u_fixed[c][k] instead of x, output dropped);
+ * u_fixed may be NULL (= 0).  y[n_free] is overwritten. */
+int lat_ddm_matvec(lat_ctx* ctx, const double* S, int64_t s_stride, const int32_t* gidx,
+                   const double* u_fixed, int64_t n_cells, int32_t nb, int64_t n_free,
+                   const double* x, double* y);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LATTICE_B200_H */

@@ -1,0 +1,163 @@
+"""Device pipeline of the full-lattice beam FEM and the drop-in replacement of
+``pyLatticeSim.utils_simulation.solve_FEM_FenicsX`` (utils_simulation.py:21-56).
+
+    mesh (host SoA) --H2D--> element generation + BSR assembly --> Dirichlet
+    elimination --> Jacobi / 6x6 block-Jacobi PCG --> reactions --D2H--> Points
+
+All numerics run in ``liblattice_b200.so`` (CUDA, sm_100a); this module only
+moves arrays and mirrors the reference's write-back onto ``Point`` objects
+(full_scale_lattice_simulation.py:77-120).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import lib as L
+from .mesh import NDOF, BeamMesh, bc_arrays_from_lattice, flatten_lattice
+
+KAPPA = 0.9  # material_definition.py:45
+
+# pyLatticeDesign/materials/*.json (E, nu) -- data consumed as-is
+MATERIALS = {"VeroClear": (1013.0, 0.3)}
+
+
+def material_constants(lattice):
+    """(E, nu) of ``lattice.material_name`` (beam_model.py:190-193 -> materials.py:9-52)."""
+    name = getattr(lattice, "material_name", "VeroClear")
+    if name in MATERIALS:
+        return MATERIALS[name]
+    try:  # fall back to the reference's own loader when it is importable
+        from pyLatticeDesign.materials import MatProperties
+        m = MatProperties(name)
+        return float(m.young_modulus), float(m.poisson_ratio)
+    except Exception as e:  # pragma: no cover
+        raise KeyError(f"unknown material {name!r}") from e
+
+
+class BeamFEM:
+    """Assembled beam-FEM operator resident on one GPU."""
+
+    def __init__(self, mesh: BeamMesh, young: float, nu: float, kappa: float = KAPPA, ctx: L.Context | None = None,
+                 pinned: bool = False):
+        import torch
+        self.torch = torch
+        self.ctx = ctx or L.Context()
+        self.mesh = mesh
+        self.young, self.nu, self.kappa = float(young), float(nu), float(kappa)
+        dev = self.ctx.device
+        self.h2d_bytes = 0
+
+        def up(a, dtype):
+            t = torch.from_numpy(np.ascontiguousarray(a, dtype=dtype))
+            if pinned:
+                t = t.pin_memory()
+            self.h2d_bytes += t.numel() * t.element_size()
+            return t.to(dev, non_blocking=pinned)
+
+        self.x = up(mesh.x, np.float64)
+        self.y = up(mesh.y, np.float64)
+        self.z = up(mesh.z, np.float64)
+        self.en0 = up(mesh.en0, np.int32)
+        self.en1 = up(mesh.en1, np.int32)
+        self.rad = up(mesh.rad, np.float64)
+        self.n_nodes = mesh.n_nodes
+        self.n_elems = mesh.n_elems
+        self.n_dof = mesh.n_dof
+        self.rowptr = self.colidx = self.vals = self.vals_bc = None
+
+    # -- pattern + assembly ---------------------------------------------------
+    def build_pattern(self):
+        self.rowptr, self.colidx = self.ctx.bsr_pattern(self.en0, self.en1, self.n_nodes)
+        self.nnzb = int(self.colidx.numel())
+        return self.rowptr, self.colidx
+
+    def assemble(self, mode=L.ASM_GATHER, out=None):
+        if self.rowptr is None:
+            self.build_pattern()
+        self.vals = self.ctx.assemble_bsr(self.x, self.y, self.z, self.en0, self.en1, self.rad, self.n_nodes,
+                                          self.nnzb, self.young, self.nu, self.kappa, mode=mode, out=out)
+        return self.vals
+
+    def set_radii(self, rad):
+        """Update element radii (device copy) -- geometry/pattern unchanged."""
+        t = self.torch.from_numpy(np.ascontiguousarray(rad, dtype=np.float64))
+        self.rad.copy_(t)
+        self.vals = None
+
+    # -- solve ------------------------------------------------------------------
+    def solve(self, fixed, g, f, tol=1e-8, maxiter=200000, precond=L.PC_BLOCK6, keep_unconstrained=True,
+              want_reactions=True, **pcg_kw):
+        """Static solve K u = f with u[c] = g.  Returns (u, reactions, info) as device tensors/dict.
+
+        BC algebra of simulation_base.py:480-499; the sparse LU of :502-511 is replaced
+        by PCG to ``tol`` relative residual."""
+        torch = self.torch
+        if self.vals is None:
+            self.assemble()
+        dev = self.ctx.device
+        fixed_d = torch.as_tensor(np.ascontiguousarray(fixed, dtype=np.uint8)).to(dev) if not torch.is_tensor(fixed) else fixed
+        g_d = torch.as_tensor(np.ascontiguousarray(g, dtype=np.float64)).to(dev) if not torch.is_tensor(g) else g
+        f_d = torch.as_tensor(np.ascontiguousarray(f, dtype=np.float64)).to(dev) if not torch.is_tensor(f) else f
+        keep = keep_unconstrained or want_reactions
+        self.vals_bc, b = self.ctx.apply_dirichlet(self.rowptr, self.colidx, self.vals, fixed_d, g_d, f_d,
+                                                   inplace=not keep)
+        u, info = self.ctx.pcg(self.rowptr, self.colidx, self.vals_bc, b, tol=tol, maxiter=maxiter,
+                               precond=precond, **pcg_kw)
+        R = None
+        if want_reactions:
+            R = self.ctx.spmv(self.rowptr, self.colidx, self.vals, u)   # R = K_unconstrained u
+        if not keep:
+            self.vals = None
+        return u, R, info
+
+    def compliance_gradient(self, u, group, n_groups, chain=None, lam=None):
+        torch = self.torch
+        dev = self.ctx.device
+        grp = torch.as_tensor(np.ascontiguousarray(group, dtype=np.int32)).to(dev) if not torch.is_tensor(group) else group
+        ch = None
+        if chain is not None:
+            ch = torch.as_tensor(np.ascontiguousarray(chain, dtype=np.float64)).to(dev) if not torch.is_tensor(chain) else chain
+        return self.ctx.compliance_grad(self.x, self.y, self.z, self.en0, self.en1, self.rad, grp, n_groups, u,
+                                        self.young, self.nu, self.kappa, chain=ch, lam=lam)
+
+
+class FEMResult:
+    """What ``solve_FEM_FenicsX`` returns as its second value, reduced to what callers read."""
+
+    def __init__(self, fem: BeamFEM, u, reactions, info, fixed):
+        self.fem = fem
+        self.u = u
+        self.reactions = reactions
+        self.info = info
+        self.fixed = fixed
+
+
+def solve_FEM_B200(lattice, elements_per_strut="gmsh", tol=1e-10, maxiter=500000, precond=L.PC_BLOCK6,
+                   dedup_point_loads=False, ctx=None):
+    """Drop-in for ``solve_FEM_FenicsX(lattice) -> (xsol, simulationModel)``
+    (utils_simulation.py:21-56).
+
+    Leaves ``Point.displacement_vector`` on every lattice node and
+    ``Point.reaction_force_vector`` on nodes with a fixed DOF
+    (full_scale_lattice_simulation.py:77-120), then returns
+    ``lattice.get_global_displacement()[0]`` (utils_simulation.py:55-56).
+    """
+    E, nu = material_constants(lattice)
+    mesh = flatten_lattice(lattice, None, elements_per_strut)
+    fixed, g, f = bc_arrays_from_lattice(lattice, mesh, dedup_point_loads=dedup_point_loads)
+    fem = BeamFEM(mesh, E, nu, ctx=ctx)
+    u, R, info = fem.solve(fixed, g, f, tol=tol, maxiter=maxiter, precond=precond)
+    u_h = u.cpu().numpy().reshape(-1, NDOF)
+    R_h = R.cpu().numpy().reshape(-1, NDOF)
+    for k, p in enumerate(mesh.meta["points"]):
+        p.displacement_vector[:] = [float(v) for v in u_h[k]]
+    # Reactions: same loop as full_scale_lattice_simulation.py:111-120 -- one set_reaction_force per
+    # (cell, node) pair, and Point.set_reaction_force ACCUMULATES (point.py:372-385), so a clamped node
+    # shared by k cells ends up with k times K.u, exactly like the reference.
+    loc = {int(i): k for k, i in enumerate(mesh.point_index)}
+    for cell in lattice.cells:
+        for node in cell.points_cell:
+            if 1 in node.fixed_DOF:
+                node.set_reaction_force([float(v) for v in R_h[loc[node.index]]])
+    xsol, _ = lattice.get_global_displacement()
+    return xsol, FEMResult(fem, u, R, info, fixed)

@@ -1,0 +1,236 @@
+"""ctypes binding of ``liblattice_b200.so`` (the C ABI declared in
+``include/lattice_b200.h``).  torch tensors are used only as device buffers:
+every call passes ``tensor.data_ptr()``.
+
+There is NO CPU fallback: :func:`load` raises if the shared library is missing
+and :class:`Context` raises if no CUDA device is usable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "liblattice_b200.so")
+SOURCES = ["lattice_core.cu", "lattice_solver.cu", "lattice_schur.cu"]
+HEADERS = [os.path.join(_HERE, "csrc", "common.cuh"), os.path.join(_ROOT, "include", "lattice_b200.h")]
+
+ASM_GATHER, ASM_ATOMIC = 0, 1
+PC_NONE, PC_JACOBI, PC_BLOCK6 = 0, 1, 2
+
+EXPORTS = [
+    "lat_version", "lat_ctx_create", "lat_ctx_destroy", "lat_last_error", "lat_ctx_sync", "lat_launch_count",
+    "lat_elem_stiffness", "lat_bsr_pattern_build", "lat_bsr_pattern_export", "lat_csr_structure",
+    "lat_bsr_to_csr_values", "lat_assemble_bsr", "lat_apply_dirichlet", "lat_bsr_spmv", "lat_pcg_bsr",
+    "lat_compliance_grad", "lat_schur_batch", "lat_ddm_matvec",
+]
+
+
+class LatticeB200Error(RuntimeError):
+    pass
+
+
+class PcgOpts(C.Structure):
+    _fields_ = [("tol", C.c_double), ("mintol", C.c_double), ("alpha_max", C.c_double),
+                ("restart_every", C.c_int64), ("maxiter", C.c_int32), ("precond", C.c_int32),
+                ("reference_semantics", C.c_int32), ("check_every", C.c_int32)]
+
+
+class PcgResult(C.Structure):
+    _fields_ = [("iters", C.c_int32), ("info", C.c_int32), ("relres", C.c_double), ("norm_b", C.c_double),
+                ("solve_ms", C.c_double), ("launches", C.c_int64)]
+
+
+def nvcc_command(out=LIB_PATH):
+    src = [os.path.join(_HERE, "csrc", s) for s in SOURCES]
+    return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+            "-shared", "-Xcompiler", "-fPIC", "-I", os.path.join(_ROOT, "include"), "-o", out] + src
+
+
+def build(force=False, verbose=False):
+    """Compile the CUDA library for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    src = [os.path.join(_HERE, "csrc", s) for s in SOURCES] + HEADERS
+    if not force and os.path.exists(LIB_PATH):
+        t = os.path.getmtime(LIB_PATH)
+        if all(os.path.getmtime(s) <= t for s in src):
+            return LIB_PATH
+    cmd = nvcc_command()
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise LatticeB200Error("nvcc failed:\n" + r.stdout + r.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load():
+    """dlopen the library and declare the prototypes. Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LatticeB200Error(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(the CUDA path is the only path; there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    lib.lat_version.restype = C.c_int
+    lib.lat_ctx_create.argtypes = [C.c_int, vp, C.POINTER(vp)]
+    lib.lat_ctx_destroy.argtypes = [vp]
+    lib.lat_last_error.argtypes = [vp]
+    lib.lat_last_error.restype = C.c_char_p
+    lib.lat_ctx_sync.argtypes = [vp]
+    lib.lat_launch_count.argtypes = [vp]
+    lib.lat_launch_count.restype = i64
+    lib.lat_elem_stiffness.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, C.c_int, vp]
+    lib.lat_bsr_pattern_build.argtypes = [vp, vp, vp, i64, i64, C.POINTER(i64)]
+    lib.lat_bsr_pattern_export.argtypes = [vp, vp, vp, vp]
+    lib.lat_csr_structure.argtypes = [vp, vp, vp, i64, vp, vp]
+    lib.lat_bsr_to_csr_values.argtypes = [vp, vp, i64, vp, vp]
+    lib.lat_assemble_bsr.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, dbl, dbl, dbl, C.c_int, C.c_int, vp]
+    lib.lat_apply_dirichlet.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
+    lib.lat_bsr_spmv.argtypes = [vp, vp, vp, vp, i64, vp, vp]
+    lib.lat_pcg_bsr.argtypes = [vp, vp, vp, vp, i64, vp, vp, C.POINTER(PcgOpts), C.POINTER(PcgResult)]
+    lib.lat_compliance_grad.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, vp, vp, i64, vp, vp]
+    lib.lat_schur_batch.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, i32, dbl, dbl, dbl, vp, vp, vp, i32, vp]
+    lib.lat_ddm_matvec.argtypes = [vp, vp, i64, vp, vp, i64, i32, i64, vp, vp]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if name not in ("lat_last_error", "lat_launch_count"):
+            fn.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+class Context:
+    """One library context = one GPU + one CUDA stream (torch's current stream)."""
+
+    def __init__(self, device=None):
+        import torch
+        self.lib = load()
+        if not torch.cuda.is_available():
+            raise LatticeB200Error("no CUDA device available: pylatticedso_b200 has no CPU fallback")
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        torch.cuda.set_device(self.device)
+        self.stream = torch.cuda.current_stream(self.device)
+        h = C.c_void_p()
+        rc = self.lib.lat_ctx_create(self.device.index, C.c_void_p(self.stream.cuda_stream), C.byref(h))
+        if rc != 0:
+            raise LatticeB200Error(f"lat_ctx_create failed with code {rc}")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lat_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != 0:
+            msg = self.lib.lat_last_error(self.h)
+            raise LatticeB200Error(f"[{rc}] {msg.decode() if msg else 'unknown error'}")
+
+    def sync(self):
+        self.check(self.lib.lat_ctx_sync(self.h))
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.lat_launch_count(self.h))
+
+    # -- thin typed wrappers (device tensors in, device tensors out) ----------
+    def elem_stiffness(self, x, y, z, en0, en1, rad, young, nu, kappa=0.9, drad=False):
+        import torch
+        ne = en0.numel()
+        Ke = torch.empty((ne, 12, 12), dtype=torch.float64, device=self.device)
+        self.check(self.lib.lat_elem_stiffness(self.h, _ptr(x), _ptr(y), _ptr(z), _ptr(en0), _ptr(en1), _ptr(rad),
+                                               ne, young, nu, kappa, int(drad), _ptr(Ke)))
+        return Ke
+
+    def bsr_pattern(self, en0, en1, n_nodes, want_elem_block=False):
+        import torch
+        nnzb = C.c_int64(0)
+        self.check(self.lib.lat_bsr_pattern_build(self.h, _ptr(en0), _ptr(en1), en0.numel(), n_nodes, C.byref(nnzb)))
+        rowptr = torch.empty(n_nodes + 1, dtype=torch.int32, device=self.device)
+        colidx = torch.empty(nnzb.value, dtype=torch.int32, device=self.device)
+        eb = torch.empty((en0.numel(), 4), dtype=torch.int32, device=self.device) if want_elem_block else None
+        self.check(self.lib.lat_bsr_pattern_export(self.h, _ptr(rowptr), _ptr(colidx), _ptr(eb)))
+        return (rowptr, colidx, eb) if want_elem_block else (rowptr, colidx)
+
+    def csr_structure(self, rowptr, colidx):
+        import torch
+        n_nodes = rowptr.numel() - 1
+        indptr = torch.empty(6 * n_nodes + 1, dtype=torch.int32, device=self.device)
+        indices = torch.empty(36 * colidx.numel(), dtype=torch.int32, device=self.device)
+        self.check(self.lib.lat_csr_structure(self.h, _ptr(rowptr), _ptr(colidx), n_nodes, _ptr(indptr), _ptr(indices)))
+        return indptr, indices
+
+    def bsr_to_csr_values(self, rowptr, vals):
+        import torch
+        out = torch.empty_like(vals)
+        self.check(self.lib.lat_bsr_to_csr_values(self.h, _ptr(rowptr), rowptr.numel() - 1, _ptr(vals), _ptr(out)))
+        return out
+
+    def assemble_bsr(self, x, y, z, en0, en1, rad, n_nodes, nnzb, young, nu, kappa=0.9, mode=ASM_GATHER,
+                     drad=False, chain=None, out=None):
+        import torch
+        vals = out if out is not None else torch.empty(nnzb * 36, dtype=torch.float64, device=self.device)
+        self.check(self.lib.lat_assemble_bsr(self.h, _ptr(x), _ptr(y), _ptr(z), _ptr(en0), _ptr(en1), _ptr(rad),
+                                             _ptr(chain), en0.numel(), n_nodes, young, nu, kappa, mode, int(drad),
+                                             _ptr(vals)))
+        return vals
+
+    def apply_dirichlet(self, rowptr, colidx, vals, fixed, g, f, inplace=False, want_matrix=True):
+        import torch
+        n_nodes = rowptr.numel() - 1
+        b = torch.empty(6 * n_nodes, dtype=torch.float64, device=self.device)
+        vbc = (vals if inplace else torch.empty_like(vals)) if want_matrix else None
+        self.check(self.lib.lat_apply_dirichlet(self.h, _ptr(rowptr), _ptr(colidx), n_nodes, _ptr(vals), _ptr(fixed),
+                                                _ptr(g), _ptr(f), _ptr(vbc), _ptr(b)))
+        return vbc, b
+
+    def spmv(self, rowptr, colidx, vals, x, out=None):
+        import torch
+        y = out if out is not None else torch.empty_like(x)
+        self.check(self.lib.lat_bsr_spmv(self.h, _ptr(rowptr), _ptr(colidx), _ptr(vals), rowptr.numel() - 1, _ptr(x), _ptr(y)))
+        return y
+
+    def pcg(self, rowptr, colidx, vals, b, x=None, tol=1e-8, maxiter=10000, precond=PC_JACOBI,
+            reference_semantics=False, mintol=0.0, alpha_max=0.0, restart_every=0, check_every=0):
+        import torch
+        if x is None:
+            x = torch.empty_like(b)
+        o = PcgOpts(tol, mintol, alpha_max, restart_every, maxiter, precond, int(reference_semantics), check_every)
+        r = PcgResult()
+        self.check(self.lib.lat_pcg_bsr(self.h, _ptr(rowptr), _ptr(colidx), _ptr(vals), rowptr.numel() - 1, _ptr(b),
+                                        _ptr(x), C.byref(o), C.byref(r)))
+        return x, dict(iters=r.iters, info=r.info, relres=r.relres, norm_b=r.norm_b, solve_ms=r.solve_ms,
+                       launches=r.launches)
+
+    def compliance_grad(self, x, y, z, en0, en1, rad, group, n_groups, u, young, nu, kappa=0.9, chain=None,
+                        lam=None, want_elem=False):
+        import torch
+        g = torch.empty(n_groups, dtype=torch.float64, device=self.device)
+        q = torch.empty(en0.numel(), dtype=torch.float64, device=self.device) if want_elem else None
+        self.check(self.lib.lat_compliance_grad(self.h, _ptr(x), _ptr(y), _ptr(z), _ptr(en0), _ptr(en1), _ptr(rad),
+                                                _ptr(chain), _ptr(group), en0.numel(), young, nu, kappa, _ptr(u),
+                                                _ptr(lam), n_groups, _ptr(g), _ptr(q)))
+        return (g, q) if want_elem else g

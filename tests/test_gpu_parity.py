@@ -1,0 +1,242 @@
+"""GPU: the CUDA path (through the C ABI) against the CPU oracle and the committed fixtures."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import E_MOD, NU, load_golden, mesh_from_npz
+from oracle import lattice_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(ctx, a, dtype):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).to(ctx.device)
+
+
+def upload(ctx, m):
+    return (dev(ctx, m.x, np.float64), dev(ctx, m.y, np.float64), dev(ctx, m.z, np.float64),
+            dev(ctx, m.en0, np.int32), dev(ctx, m.en1, np.int32), dev(ctx, m.rad, np.float64))
+
+
+def bsr_to_scipy(rowptr, colidx, vals, n_nodes):
+    return sp.bsr_matrix((vals.reshape(-1, 6, 6), colidx, rowptr), shape=(6 * n_nodes, 6 * n_nodes)).tocsr()
+
+
+def random_mesh(seed=0, n_nodes=200, n_elem=700):
+    from pylatticedso_b200.mesh import BeamMesh
+    rng = np.random.default_rng(seed)
+    xyz = rng.standard_normal((n_nodes, 3))
+    en0 = rng.integers(0, n_nodes, n_elem)
+    en1 = (en0 + rng.integers(1, n_nodes, n_elem)) % n_nodes
+    en0[:5] = en0[5:10]; en1[:5] = en1[5:10]        # duplicated struts
+    en0[10], en1[10] = en1[11], en0[11]             # same strut, opposite orientation
+    # axis-aligned and frame-rule tie cases
+    xyz[0] = [0, 0, 0]; xyz[1] = [1, 0, 0]; xyz[2] = [0, 1, 0]; xyz[3] = [0, 0, 1]; xyz[4] = [1, 1, 0]; xyz[5] = [1, 1, 1]
+    en0[20:25] = 0; en1[20:25] = [1, 2, 3, 4, 5]
+    rad = rng.uniform(0.01, 0.1, n_elem)
+    return BeamMesh(x=xyz[:, 0].copy(), y=xyz[:, 1].copy(), z=xyz[:, 2].copy(), en0=en0.astype(np.int32),
+                    en1=en1.astype(np.int32), rad=rad, beam_of_elem=np.arange(n_elem), chain=np.ones(n_elem),
+                    n_points=n_nodes, point_index=np.arange(n_nodes))
+
+
+@pytest.mark.parametrize("drad", [False, True])
+def test_element_stiffness_matches_oracle_1e12(ctx, drad):
+    m = random_mesh()
+    x, y, z, en0, en1, rad = upload(ctx, m)
+    Ke = ctx.elem_stiffness(x, y, z, en0, en1, rad, E_MOD, NU, drad=drad).cpu().numpy()
+    ref = orc.element_stiffness(m.xyz[m.en0], m.xyz[m.en1], m.rad, E_MOD, NU, drad=drad)
+    scale = np.abs(ref).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(Ke - ref) / scale).max() < 1e-12      # north_star: stiffness values within 1e-12 relative
+
+
+def test_element_stiffness_empty_and_ragged(ctx):
+    import torch
+    m = random_mesh(n_elem=33)                            # one full warp + 1
+    x, y, z, en0, en1, rad = upload(ctx, m)
+    Ke = ctx.elem_stiffness(x, y, z, en0, en1, rad, E_MOD, NU).cpu().numpy()
+    ref = orc.element_stiffness(m.xyz[m.en0], m.xyz[m.en1], m.rad, E_MOD, NU)
+    assert np.abs(Ke - ref).max() < 1e-12 * np.abs(ref).max()
+    e = torch.empty(0, dtype=torch.int32, device=ctx.device)
+    assert ctx.elem_stiffness(x, y, z, e, e, rad[:0], E_MOD, NU).shape[0] == 0
+
+
+@pytest.mark.parametrize("which", ["random", "bcc", "octet_m2"])
+def test_pattern_is_bit_exact_with_scipy_csr(ctx, which):
+    from pylatticedso_b200 import mesh as M
+    if which == "random":
+        m = random_mesh(1)
+    elif which == "bcc":
+        m = M.mesh_from_synthetic(M.synthetic_lattice("BCC", (4, 3, 5), [0.05]), 1)
+    else:
+        m = M.mesh_from_synthetic(M.synthetic_lattice("Octet", (3, 3, 2), [0.03]), 2)
+    x, y, z, en0, en1, rad = upload(ctx, m)
+    rowptr, colidx, eb = ctx.bsr_pattern(en0, en1, m.n_nodes, want_elem_block=True)
+    indptr, indices = ctx.csr_structure(rowptr, colidx)
+    K = orc.assemble_csr(m.xyz, np.stack([m.en0, m.en1], 1), m.rad, E_MOD, NU)
+    assert K.indptr.dtype == np.int32
+    assert np.array_equal(indptr.cpu().numpy(), K.indptr)          # bit-exact CSR structure
+    assert np.array_equal(indices.cpu().numpy(), K.indices)
+    # closed form: blocks = nodes + 2 * (distinct struts)
+    pairs = {(min(a, b), max(a, b)) for a, b in zip(m.en0.tolist(), m.en1.tolist())}
+    assert colidx.numel() == m.n_nodes + 2 * len(pairs)
+    # scatter map points at the right blocks
+    rp, ci, ebh = rowptr.cpu().numpy(), colidx.cpu().numpy(), eb.cpu().numpy()
+    rows = np.repeat(np.arange(m.n_nodes), np.diff(rp))
+    for q, (ra, ca) in enumerate(((m.en0, m.en0), (m.en0, m.en1), (m.en1, m.en0), (m.en1, m.en1))):
+        assert np.array_equal(rows[ebh[:, q]], ra) and np.array_equal(ci[ebh[:, q]], ca)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("drad", [False, True])
+def test_assembly_matches_oracle(ctx, mode, drad):
+    m = random_mesh(2)
+    m.chain = np.random.default_rng(3).uniform(1.0, 1.5, m.n_elems)
+    x, y, z, en0, en1, rad = upload(ctx, m)
+    rowptr, colidx = ctx.bsr_pattern(en0, en1, m.n_nodes)
+    chain = dev(ctx, m.chain, np.float64) if drad else None
+    vals = ctx.assemble_bsr(x, y, z, en0, en1, rad, m.n_nodes, colidx.numel(), E_MOD, NU, mode=mode, drad=drad,
+                            chain=chain)
+    en = np.stack([m.en0, m.en1], 1)
+    if drad:
+        Ke = orc.element_stiffness(m.xyz[m.en0], m.xyz[m.en1], m.rad, E_MOD, NU, drad=True) * m.chain[:, None, None]
+        dofs = (en[:, :, None] * 6 + np.arange(6)[None, None, :]).reshape(-1, 12)
+        K = sp.coo_matrix((Ke.ravel(), (np.repeat(dofs, 12, 1).ravel(), np.tile(dofs, (1, 12)).ravel())),
+                          shape=(m.n_dof, m.n_dof)).tocsr()
+    else:
+        K = orc.assemble_csr(m.xyz, en, m.rad, E_MOD, NU)
+    csr_vals = ctx.bsr_to_csr_values(rowptr, vals).cpu().numpy()
+    Kd = K.toarray()
+    A = bsr_to_scipy(rowptr.cpu().numpy(), colidx.cpu().numpy(), vals.cpu().numpy(), m.n_nodes).toarray()
+    assert np.abs(A - Kd).max() < 1e-12 * np.abs(Kd).max()
+    if not drad:
+        assert np.abs(csr_vals - K.data).max() < 1e-12 * np.abs(K.data).max()   # same order as scipy's CSR data
+
+
+def test_gather_assembly_is_deterministic_and_symmetric(ctx):
+    from pylatticedso_b200 import mesh as M
+    m = M.mesh_from_synthetic(M.synthetic_lattice("Octet", (4, 4, 4), [0.03]), 1)
+    x, y, z, en0, en1, rad = upload(ctx, m)
+    rowptr, colidx = ctx.bsr_pattern(en0, en1, m.n_nodes)
+    v1 = ctx.assemble_bsr(x, y, z, en0, en1, rad, m.n_nodes, colidx.numel(), E_MOD, NU).cpu().numpy()
+    rowptr2, colidx2 = ctx.bsr_pattern(en0, en1, m.n_nodes)
+    v2 = ctx.assemble_bsr(x, y, z, en0, en1, rad, m.n_nodes, colidx.numel(), E_MOD, NU).cpu().numpy()
+    assert np.array_equal(v1, v2)                               # bit-reproducible
+    A = bsr_to_scipy(rowptr.cpu().numpy(), colidx.cpu().numpy(), v1, m.n_nodes)
+    assert abs(A - A.T).max() < 1e-12 * abs(A).max()
+    # rigid translation is in the null space of the unconstrained operator
+    t = np.tile([1.0, 2.0, -0.5, 0, 0, 0], m.n_nodes)
+    assert np.abs(A @ t).max() < 1e-9 * abs(A).max()
+
+
+def test_dirichlet_spmv_and_reactions(ctx):
+    from pylatticedso_b200 import mesh as M
+    m = M.mesh_from_synthetic(M.synthetic_lattice("BCC", (3, 3, 3), [0.05]), 2)
+    fixed, g, f = M.compression_bc(m)
+    f = f.copy(); f[6 * 40 + 1] = 0.3                      # a point load on a free DOF
+    x, y, z, en0, en1, rad = upload(ctx, m)
+    rowptr, colidx = ctx.bsr_pattern(en0, en1, m.n_nodes)
+    vals = ctx.assemble_bsr(x, y, z, en0, en1, rad, m.n_nodes, colidx.numel(), E_MOD, NU)
+    vbc, b = ctx.apply_dirichlet(rowptr, colidx, vals, dev(ctx, fixed, np.uint8), dev(ctx, g, np.float64), dev(ctx, f, np.float64))
+    K = orc.assemble_csr(m.xyz, np.stack([m.en0, m.en1], 1), m.rad, E_MOD, NU)
+    Kbc, bo = orc.apply_dirichlet(K, fixed, g, f)
+    A = bsr_to_scipy(rowptr.cpu().numpy(), colidx.cpu().numpy(), vbc.cpu().numpy(), m.n_nodes)
+    assert abs(A - Kbc).max() < 1e-12 * abs(Kbc).max()
+    assert np.abs(b.cpu().numpy() - bo).max() < 1e-12 * np.abs(bo).max()
+    v = np.random.default_rng(0).standard_normal(m.n_dof)
+    yv = ctx.spmv(rowptr, colidx, vals, dev(ctx, v, np.float64)).cpu().numpy()
+    assert np.abs(yv - K @ v).max() < 1e-12 * np.abs(K @ v).max()
+
+
+@pytest.mark.parametrize("precond", [0, 1, 2])
+def test_pcg_solves_to_tolerance(ctx, precond):
+    from pylatticedso_b200 import mesh as M
+    m = M.mesh_from_synthetic(M.synthetic_lattice("BCC", (3, 3, 3), [0.05]), 1)
+    fixed, g, f = M.compression_bc(m)
+    x, y, z, en0, en1, rad = upload(ctx, m)
+    rowptr, colidx = ctx.bsr_pattern(en0, en1, m.n_nodes)
+    vals = ctx.assemble_bsr(x, y, z, en0, en1, rad, m.n_nodes, colidx.numel(), E_MOD, NU)
+    vbc, b = ctx.apply_dirichlet(rowptr, colidx, vals, dev(ctx, fixed, np.uint8), dev(ctx, g, np.float64), dev(ctx, f, np.float64))
+    u, info = ctx.pcg(rowptr, colidx, vbc, b, tol=1e-12, maxiter=20000, precond=precond)
+    K = orc.assemble_csr(m.xyz, np.stack([m.en0, m.en1], 1), m.rad, E_MOD, NU)
+    uo, Ro = orc.solve_static(K, fixed.astype(bool), g, f)
+    assert info["info"] == 0 and info["relres"] <= 1e-12
+    assert np.abs(u.cpu().numpy() - uo).max() < 1e-8 * np.abs(uo).max()   # north_star: displacements 1e-8
+    # deterministic: same iterate bit for bit on a second run
+    u2, info2 = ctx.pcg(rowptr, colidx, vbc, b, tol=1e-12, maxiter=20000, precond=precond)
+    assert info2["iters"] == info["iters"] and np.array_equal(u.cpu().numpy(), u2.cpu().numpy())
+
+
+@pytest.mark.parametrize("name", ["well_default", "well_ddm", "ill_clamp", "ill_restart"])
+def test_pcg_reference_semantics_match_reference_solver(ctx, name):
+    """Same iteration as the reference's conjugate_gradient_solver (outputs frozen in pcg_reference.npz):
+    dense SPD test matrices are padded to a multiple of 6 and fed as one BSR matrix."""
+    G = load_golden("pcg_reference.npz")
+    A = G["A_well"] if name.startswith("well") else G["A_ill"]
+    n = A.shape[0]
+    assert n % 6 == 0
+    nb = n // 6
+    rowptr = np.arange(0, nb * nb + 1, nb, dtype=np.int32)
+    colidx = np.tile(np.arange(nb, dtype=np.int32), nb)
+    vals = A.reshape(nb, 6, nb, 6).transpose(0, 2, 1, 3).reshape(-1)
+    maxiter, tol, mintol, restart, amax = G[f"{name}_params"]
+    jac = bool(G[f"{name}_jacobi"])
+    x, info = ctx.pcg(dev(ctx, rowptr, np.int32), dev(ctx, colidx, np.int32), dev(ctx, vals, np.float64),
+                      dev(ctx, G[f"{name}_b"], np.float64), tol=float(tol), maxiter=int(maxiter),
+                      precond=1 if jac else 0, reference_semantics=True, mintol=float(mintol),
+                      alpha_max=float(amax), restart_every=int(restart), check_every=4)
+    assert info["info"] == int(G[f"{name}_info"])
+    assert info["iters"] == int(G[f"{name}_iters"])
+    xr = G[f"{name}_x"]
+    assert np.abs(x.cpu().numpy() - xr).max() < 1e-9 * np.abs(xr).max()
+
+
+@pytest.mark.parametrize("case", ["disp", "force"])
+def test_full_fem_matches_reference_ddm_in_the_loop(ctx, case):
+    """3x2x2 penalised BCC lattice on the reference gmsh subdivision (10 656 DOF): assemble + eliminate
+    + block-Jacobi PCG on the GPU vs the reference's own solve_DDM boundary displacements."""
+    from pylatticedso_b200.fem import BeamFEM
+    G = load_golden(f"ddm_loop_{case}.npz")
+    m = mesh_from_npz(G)
+    fem = BeamFEM(m, E_MOD, NU, ctx=ctx)
+    u, R, info = fem.solve(G["fixed"], G["g"], G["f"], tol=1e-12, maxiter=400000, precond=2)
+    assert info["info"] == 0
+    up = u.cpu().numpy().reshape(-1, 6)[: m.n_points]
+    ref = G["u_points_reference_ddm"]
+    sel = G["point_on_cell_boundary"]
+    assert np.abs(up[sel] - ref[sel]).max() / np.abs(ref).max() < 1e-8
+    K = orc.assemble_csr(m.xyz, np.stack([m.en0, m.en1], 1), m.rad, E_MOD, NU)
+    uo, Ro = orc.solve_static(K, G["fixed"].astype(bool), G["g"], G["f"])
+    c = G["fixed"].astype(bool)
+    assert np.abs(R.cpu().numpy()[c] - Ro[c]).max() < 1e-8 * np.abs(Ro[c]).max()   # reactions 1e-8
+
+
+def test_compliance_gradient_matches_reference_and_oracle(ctx):
+    from pylatticedso_b200.fem import BeamFEM
+    G = load_golden("grad_loop_bcc311.npz")
+    m = mesh_from_npz(G)
+    fem = BeamFEM(m, E_MOD, NU, ctx=ctx)
+    u, R, info = fem.solve(G["fixed"], G["g"], G["f"], tol=1e-13, maxiter=400000, precond=2)
+    comp = float((dev(ctx, G["f"], np.float64) * u).sum())
+    assert abs(comp - float(G["compliance_reference"])) < 1e-8 * abs(comp)
+    g = fem.compliance_gradient(u, G["group"], 3, chain=m.chain).cpu().numpy()
+    ref = G["gradient_reference_fd"]
+    assert np.abs(g - G["gradient_oracle_analytic"]).max() < 1e-6 * np.abs(ref).max()
+    assert np.abs(g - ref).max() < 5e-6 * np.abs(ref).max()      # reference FD noise ~2e-6 |g|_inf
+    # adjoint form with lambda = u is the same number; per-element output sums to the groups
+    g2, q = fem.ctx.compliance_grad(fem.x, fem.y, fem.z, fem.en0, fem.en1, fem.rad, dev(ctx, G["group"], np.int32),
+                                    3, u, E_MOD, NU, chain=dev(ctx, m.chain, np.float64), lam=u, want_elem=True)
+    assert np.allclose(g2.cpu().numpy(), g, rtol=1e-12)
+    qs = np.zeros(3); np.add.at(qs, G["group"], q.cpu().numpy())
+    assert np.allclose(qs, g, rtol=1e-10)
+
+
+def test_bad_arguments_are_errors_not_crashes(ctx):
+    import torch
+    from pylatticedso_b200.lib import LatticeB200Error
+    en0 = torch.tensor([0, 1, 5], dtype=torch.int32, device=ctx.device)
+    en1 = torch.tensor([1, 1, 2], dtype=torch.int32, device=ctx.device)   # degenerate + out of range
+    with pytest.raises(LatticeB200Error):
+        ctx.bsr_pattern(en0, en1, 3)
+    with pytest.raises(LatticeB200Error):
+        ctx.check(ctx.lib.lat_bsr_spmv(ctx.h, None, None, None, 3, None, None))

@@ -1,0 +1,82 @@
+"""CPU: host-side flattening and the vectorised generator against the reference numbering."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from pylatticedso_b200 import mesh as M
+from pylatticedso_b200 import refshim
+
+
+@pytest.mark.parametrize("name", ["bcc_322", "octet_322", "octet_223_graded", "bcc_345"])
+def test_synthetic_lattice_reproduces_reference_numbering(name):
+    G = load_golden(f"numbering_{name}.npz")
+    grad = None
+    if float(G["grad_param_z"]) != 0.0:
+        grad = ("linear", [False, False, True], [0.0, 0.0, float(G["grad_param_z"])])
+    lat = M.synthetic_lattice(str(G["geom"]), tuple(G["n_cells"]), list(G["radii"]), grad_radius=grad)
+    assert np.array_equal(lat.pxyz, G["pxyz"])          # node.index order + coordinates, bit exact
+    assert np.array_equal(lat.b_p1, G["b_p1"]) and np.array_equal(lat.b_p2, G["b_p2"])
+    assert np.array_equal(lat.b_rad, G["b_rad"])        # shared struts keep the first cell's radius
+    assert np.array_equal(lat.b_cell, G["b_cell"])
+    assert np.array_equal(lat.cell_radii, G["cell_radii"])
+
+
+def test_node_and_strut_counts_match_closed_forms():
+    for n in (3, 5):
+        b = M.synthetic_lattice("BCC", (n, n, n), [0.05])
+        assert b.pxyz.shape[0] == (n + 1) ** 3 + n ** 3 and b.b_p1.shape[0] == 8 * n ** 3
+        o = M.synthetic_lattice("Octet", (n, n, n), [0.03])
+        assert o.pxyz.shape[0] == (n + 1) ** 3 + 3 * n * n * (n + 1)
+        assert o.b_p1.shape[0] == 12 * n * n * (n + 1) + 12 * n ** 3
+
+
+def test_subdivision_layout():
+    lat = M.synthetic_lattice("BCC", (2, 1, 1), [0.05])
+    m = M.mesh_from_synthetic(lat, 3)
+    nb = lat.b_p1.shape[0]
+    assert m.n_elems == 3 * nb and m.n_nodes == lat.pxyz.shape[0] + 2 * nb
+    # element chain of beam 0: p1 -> i0 -> i1 -> p2, interior nodes appended beam-major
+    npnt = lat.pxyz.shape[0]
+    assert list(m.en0[:3]) == [lat.b_p1[0], npnt, npnt + 1] and list(m.en1[:3]) == [npnt, npnt + 1, lat.b_p2[0]]
+    a, c = lat.pxyz[lat.b_p1[0]], lat.pxyz[lat.b_p2[0]]
+    assert np.allclose(m.xyz[npnt], a + (c - a) / 3)
+    assert M.gmsh_segments(np.array([0.8660254]), 0.05)[0] == 18   # BCC half diagonal, h = 0.05
+    assert M.gmsh_segments(np.array([0.01]), 0.05)[0] == 1
+
+
+def test_compression_bc_counts():
+    lat = M.synthetic_lattice("BCC", (5, 5, 5), [0.05])
+    m = M.mesh_from_synthetic(lat, 1)
+    fixed, g, f = M.compression_bc(m)
+    assert int(fixed.sum()) == 252                       # SURVEY.md section 8d, C1 [probed on the reference]
+    assert m.n_nodes == 341 and m.n_elems == 1000 and m.n_dof == 2046
+    assert (g[fixed == 1] != 0).sum() == 36 and not f.any()
+
+
+@pytest.mark.skipif(not refshim.have_reference(), reason="needs a pyLatticeDSO checkout")
+def test_flatten_object_graph_matches_generator_and_oracle():
+    import contextlib
+    import io
+    from oracle import lattice_oracle as orc
+    ls = refshim.import_reference()
+    cfg = {"geometry": {"cell_size": {"x": 1, "y": 1, "z": 1}, "number_of_cells": {"x": 2, "y": 3, "z": 2},
+                        "radii": [0.04], "geom_types": ["Octet"]},
+           "simulation_parameters": {"enable": False, "material": "VeroClear", "periodicity": False},
+           "boundary_conditions": {"Displacement": {"Fixed": {"Surface": ["Zmin"], "DOF": ["X", "Y", "Z", "RX", "RY", "RZ"],
+                                                              "Value": [0, 0, 0, 0, 0, 0]},
+                                                    "Load": {"Surface": ["Zmax"], "DOF": ["Z"], "Value": [-0.01]}}}}
+    refshim.set_inline_presets({"t": cfg})
+    with contextlib.redirect_stdout(io.StringIO()):
+        lat = ls.LatticeSim("t")
+    syn = M.synthetic_lattice("Octet", (2, 3, 2), [0.04])
+    for m_ in (1, 2, "gmsh"):
+        a = M.flatten_lattice(lat, None, m_)
+        b = M.mesh_from_synthetic(syn, m_)
+        o = orc.flatten_lattice(lat, None, m_)
+        for k in ("x", "y", "z", "en0", "en1", "rad"):
+            assert np.array_equal(getattr(a, k), getattr(b, k)), (m_, k)
+        assert np.array_equal(a.xyz, o["xyz"]) and np.array_equal(a.en0, o["en"][:, 0]) and np.array_equal(a.rad, o["rad"])
+    a = M.flatten_lattice(lat, None, 1)
+    fixed, g, f = M.bc_arrays_from_lattice(lat, a)
+    fs, gs, fs_ = M.compression_bc(M.mesh_from_synthetic(syn, 1))
+    assert np.array_equal(fixed, fs) and np.array_equal(g, gs) and np.array_equal(f, fs_)

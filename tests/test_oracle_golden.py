@@ -1,0 +1,84 @@
+"""CPU: the oracle against every known-answer fixture."""
+import numpy as np
+import pytest
+
+from conftest import E_MOD, NU, load_golden, mesh_from_npz
+from oracle import lattice_oracle as orc
+
+
+@pytest.mark.parametrize("geom,tol", [("BCC", 1e-12), ("Hybrid1", 5e-12), ("Hybrid4", 1e-12)])
+def test_oracle_reproduces_reference_schur_goldens(geom, tol):
+    """30 Schur matrices stored by the reference (real dolfinx/PETSc runs)."""
+    G = load_golden(f"schur_{geom}.npz")
+    SM = G["schur_matrices"]
+    assert SM.shape[0] == 10
+    for i in range(SM.shape[0]):
+        m = mesh_from_npz(G, f"c{i}_")
+        K = orc.assemble_csr(m.xyz, np.stack([m.en0, m.en1], 1), m.rad, E_MOD, NU)
+        S = orc.schur_complement(K, G[f"c{i}_bnd"])
+        err = np.abs(S - SM[i]).max() / np.abs(SM[i]).max()
+        assert err < tol, (geom, i, err)
+
+
+def test_element_matrix_properties():
+    rng = np.random.default_rng(0)
+    x1 = rng.standard_normal((50, 3))
+    x2 = x1 + rng.standard_normal((50, 3))
+    # include axis-aligned and tie cases of the frame rule
+    x1[:4] = 0.0
+    x2[0] = [1, 0, 0]; x2[1] = [0, 1, 0]; x2[2] = [0, 0, 1]; x2[3] = [1, 1, 0]
+    r = rng.uniform(0.01, 0.1, 50)
+    K = orc.element_stiffness(x1, x2, r, E_MOD, NU)
+    assert np.abs(K - K.transpose(0, 2, 1)).max() < 1e-9 * np.abs(K).max()
+    for k in range(50):
+        w = np.linalg.eigvalsh(K[k])
+        assert (w > -1e-9 * w.max()).all()
+        assert (np.abs(w) > 1e-9 * w.max()).sum() == 6      # rank 6: six rigid-body modes
+    # derivative against central differences
+    h = 1e-6
+    dK = orc.element_stiffness(x1, x2, r, E_MOD, NU, drad=True)
+    fd = (orc.element_stiffness(x1, x2, r + h, E_MOD, NU) - orc.element_stiffness(x1, x2, r - h, E_MOD, NU)) / (2 * h)
+    assert np.abs(dK - fd).max() < 1e-6 * np.abs(dK).max()
+
+
+@pytest.mark.parametrize("case", ["disp", "force"])
+def test_oracle_fem_matches_reference_ddm_in_the_loop(case):
+    """Reference's own solve_DDM (fed with oracle Schur matrices) vs the oracle's full FEM."""
+    G = load_golden(f"ddm_loop_{case}.npz")
+    m = mesh_from_npz(G)
+    K = orc.assemble_csr(m.xyz, np.stack([m.en0, m.en1], 1), m.rad, E_MOD, NU)
+    u, R = orc.solve_static(K, G["fixed"].astype(bool), G["g"], G["f"])
+    up = u.reshape(-1, 6)[: m.n_points]
+    ref = G["u_points_reference_ddm"]
+    sel = G["point_on_cell_boundary"]
+    assert np.abs(up[sel] - ref[sel]).max() / np.abs(ref).max() < 1e-9
+    # global equilibrium of the reactions
+    free = ~G["fixed"].astype(bool)
+    assert np.abs((R - G["f"])[free]).max() < 1e-8 * np.abs(R).max()
+
+
+def test_oracle_gradient_matches_reference_optimiser_in_the_loop():
+    G = load_golden("grad_loop_bcc311.npz")
+    m = mesh_from_npz(G)
+    en = np.stack([m.en0, m.en1], 1)
+    K = orc.assemble_csr(m.xyz, en, m.rad, E_MOD, NU)
+    u, _ = orc.solve_static(K, G["fixed"].astype(bool), G["g"], G["f"])
+    assert abs(float(G["f"] @ u) - float(G["compliance_reference"])) < 1e-8 * abs(float(G["compliance_reference"]))
+    g = orc.compliance_gradient(m.xyz, en, m.rad, u, G["group"], 3, E_MOD, NU, chain=m.chain)
+    ref = G["gradient_reference_fd"]
+    # the reference gradient is a central FD of Schur matrices (lattice_sim.py:1020-1054, h = 1e-6):
+    # its own noise is ~2e-6 |g|_inf, so 1e-6-level agreement is only meaningful relative to |g|_inf
+    assert np.abs(g - ref).max() < 5e-6 * np.abs(ref).max()
+    assert np.abs(g - G["gradient_oracle_analytic"]).max() < 1e-12 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("name", ["well_default", "well_ddm", "ill_clamp", "ill_restart"])
+def test_oracle_pcg_is_the_reference_pcg(name):
+    G = load_golden("pcg_reference.npz")
+    A = G["A_well"] if name.startswith("well") else G["A_ill"]
+    maxiter, tol, mintol, restart, amax = G[f"{name}_params"]
+    Minv = np.diag(1.0 / np.diag(A)) if bool(G[f"{name}_jacobi"]) else None
+    x, info, it = orc.reference_pcg(A, G[f"{name}_b"], Minv, maxiter=int(maxiter), tol=tol, mintol=mintol,
+                                    restart_every=int(restart), alpha_max=amax)
+    assert info == int(G[f"{name}_info"]) and it == int(G[f"{name}_iters"])
+    assert np.array_equal(x, G[f"{name}_x"])
