@@ -114,6 +114,10 @@ int lat_apply_dirichlet(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
                         int64_t n_nodes, const double* vals, const uint8_t* fixed,
                         const double* g, const double* f, double* vals_bc, double* b);
 
+/* u[c] = g[c] on constrained DOFs (fem_petsc.set_bc, simulation_base.py:492): makes the imposed
+ * values exact after an iterative solve. */
+int lat_set_dirichlet_values(lat_ctx* ctx, const uint8_t* fixed, const double* g, int64_t n_dof, double* u);
+
 /* ---- A10: y = K x (reactions R = K_unconstrained u, simulation_base.py:582-645) */
 int lat_bsr_spmv(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx,
                  const double* vals, int64_t n_nodes, const double* x, double* y);
@@ -135,6 +139,9 @@ typedef struct {
   int32_t precond;
   int32_t reference_semantics;
   int32_t check_every; /* iterations between host polls of the device status (0 = default 32) */
+  int32_t profile_iters; /* >0: the first profile_iters iterations are launched outside the CUDA graph
+                            with CUDA events around each kernel (fills spmv_ms / update_ms) */
+  int32_t reserved;
 } lat_pcg_opts;
 
 typedef struct {
@@ -144,6 +151,10 @@ typedef struct {
   double norm_b;
   double solve_ms;   /* device time of the iteration loop (CUDA events on the ctx stream) */
   int64_t launches;  /* kernels launched by this call */
+  double spmv_ms;    /* mean duration of the fused SpMV kernel over the profiled iterations (0 if none) */
+  double update_ms;  /* mean duration of the update kernel over the profiled iterations */
+  int32_t profiled;  /* iterations actually profiled */
+  int32_t reserved;
 } lat_pcg_result;
 
 /* x is overwritten (x0 = 0).  [syncs] */

@@ -305,7 +305,9 @@ __global__ void k_sort_rows(int64_t n_nodes, const int32_t* __restrict__ adjptr,
     adj_other[j + 1] = ko;
     adj_el[j + 1] = ke;
   }
-  int cnt = 1;  // self
+  // a node without any element keeps an EMPTY row (like scipy's COO->CSR of the element
+  // triplets, and like dolfinx, whose mesh does not contain unconnected gmsh points)
+  int cnt = (hi > lo) ? 1 : 0;  // self
   for (int i = lo; i < hi; ++i)
     if (i == lo || adj_other[i] != adj_other[i - 1]) ++cnt;
   nb[n] = cnt;
@@ -319,6 +321,7 @@ __global__ void k_fill_cols(int64_t n_nodes, const int32_t* __restrict__ adjptr,
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= n_nodes) return;
   const int lo = adjptr[n], hi = adjptr[n + 1];
+  if (hi == lo) { diagpos[n] = -1; return; }
   int w = rowptr[n];
   bool self_done = false;
   int i = lo;
@@ -661,6 +664,19 @@ __global__ void k_mask_vec(const uint8_t* __restrict__ fixed, const double* __re
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   out[i] = fixed[i] ? g[i] : 0.0;
+}
+
+__global__ void k_set_bc(const uint8_t* __restrict__ fixed, const double* __restrict__ g, int64_t n, double* __restrict__ u) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && fixed[i]) u[i] = g[i];
+}
+
+extern "C" int lat_set_dirichlet_values(lat_ctx* ctx, const uint8_t* fixed, const double* g, int64_t n_dof, double* u) {
+  if (!ctx) return LAT_ERR_ARG;
+  LAT_CHECK_ARG(ctx, fixed && g && u && n_dof > 0);
+  LAT_CUDA(ctx, cudaSetDevice(ctx->device));
+  LAT_LAUNCH(ctx, k_set_bc, (unsigned)ceil_div(n_dof, 256), 256, 0, fixed, g, n_dof, u);
+  return LAT_OK;
 }
 
 int lat_spmv_internal(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, const double* vals,

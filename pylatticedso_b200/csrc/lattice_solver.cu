@@ -5,6 +5,8 @@
 // idle).  DOF index 6*node + r is therefore consecutive across lanes 0..29, so
 // all vector traffic is coalesced, and the 6 lanes of a group read one 288 B
 // block of the matrix as 6 x 48 B (three 16 B loads per lane).
+#include <vector>
+
 #include "common.cuh"
 
 static constexpr int SPMV_BLOCK = 256;                        // 8 warps
@@ -338,10 +340,42 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
   }
 
   int rc = LAT_OK;
-  const int nbatch = (int)ceil_div(o->maxiter > 0 ? o->maxiter : 0, check);
+  // optional per-kernel timing of the first iterations (outside the graph, events between kernels)
+  int nprof = o->profile_iters > 0 ? o->profile_iters : 0;
+  if (nprof > o->maxiter) nprof = o->maxiter;
+  if (nprof > 256) nprof = 256;
+  double spmv_ms = 0.0, update_ms = 0.0;
+  if (nprof > 0) {
+    std::vector<cudaEvent_t> evs(3 * nprof);
+    for (auto& e : evs) cudaEventCreate(&e);
+    for (int it = 0; it < nprof; ++it) {
+      cudaEventRecord(evs[3 * it], ctx->stream);
+      k_pcg_spmv<0><<<grid, SPMV_BLOCK, 0, ctx->stream>>>(rowptr, colidx, vals, n_nodes, z, pa, pb, Ap, sc, partials, prm);
+      cudaEventRecord(evs[3 * it + 1], ctx->stream);
+      k_pcg_update<PC><<<grid, SPMV_BLOCK, 0, ctx->stream>>>(n_nodes, dinv, x, r, z, pa, pb, Ap, sc, partials, prm);
+      cudaEventRecord(evs[3 * it + 2], ctx->stream);
+      ctx->launches += 2;
+    }
+    ce = cudaStreamSynchronize(ctx->stream);
+    if (ce == cudaSuccess) {
+      for (int it = 0; it < nprof; ++it) {
+        float a = 0.f, b2 = 0.f;
+        cudaEventElapsedTime(&a, evs[3 * it], evs[3 * it + 1]);
+        cudaEventElapsedTime(&b2, evs[3 * it + 1], evs[3 * it + 2]);
+        spmv_ms += a;
+        update_ms += b2;
+      }
+      spmv_ms /= nprof;
+      update_ms /= nprof;
+    }
+    for (auto& e : evs) cudaEventDestroy(e);
+    if (ce != cudaSuccess) rc = lat_cuda_fail(ctx, ce, "PCG profiled iterations", __FILE__, __LINE__);
+  }
+  const int remaining = o->maxiter - nprof;
+  const int nbatch = (int)ceil_div(remaining > 0 ? remaining : 0, check);
   PcgScalars* hs = ctx->h_scal;
   int launched = 0, checked = 0;
-  bool finished = (o->maxiter <= 0);
+  bool finished = (remaining <= 0);
   // software pipeline of depth 2: batch i+1 is enqueued before the status of batch i is read;
   // kernels of a batch enqueued after convergence exit immediately (sc->done), so x is frozen
   // at the converged iterate exactly like the `break` of the reference loop.
@@ -379,6 +413,10 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
   res->info = hs[0].done && !hs[0].breakdown ? 0 : (hs[0].breakdown ? 3 : (hs[0].info_flag2 ? 2 : 1));
   res->solve_ms = ms;
   res->launches = ctx->launches - launches0;
+  res->spmv_ms = spmv_ms;
+  res->update_ms = update_ms;
+  res->profiled = nprof;
+  res->reserved = 0;
   return LAT_OK;
 }
 

@@ -103,6 +103,7 @@ class BeamFEM:
                                                    inplace=not keep)
         u, info = self.ctx.pcg(self.rowptr, self.colidx, self.vals_bc, b, tol=tol, maxiter=maxiter,
                                precond=precond, **pcg_kw)
+        self.ctx.set_dirichlet_values(fixed_d, g_d, u)
         R = None
         if want_reactions:
             R = self.ctx.spmv(self.rowptr, self.colidx, self.vals, u)   # R = K_unconstrained u

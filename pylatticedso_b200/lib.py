@@ -24,7 +24,7 @@ PC_NONE, PC_JACOBI, PC_BLOCK6 = 0, 1, 2
 EXPORTS = [
     "lat_version", "lat_ctx_create", "lat_ctx_destroy", "lat_last_error", "lat_ctx_sync", "lat_launch_count",
     "lat_elem_stiffness", "lat_bsr_pattern_build", "lat_bsr_pattern_export", "lat_csr_structure",
-    "lat_bsr_to_csr_values", "lat_assemble_bsr", "lat_apply_dirichlet", "lat_bsr_spmv", "lat_pcg_bsr",
+    "lat_bsr_to_csr_values", "lat_assemble_bsr", "lat_apply_dirichlet", "lat_set_dirichlet_values", "lat_bsr_spmv", "lat_pcg_bsr",
     "lat_compliance_grad", "lat_schur_batch", "lat_ddm_matvec",
 ]
 
@@ -36,12 +36,14 @@ class LatticeB200Error(RuntimeError):
 class PcgOpts(C.Structure):
     _fields_ = [("tol", C.c_double), ("mintol", C.c_double), ("alpha_max", C.c_double),
                 ("restart_every", C.c_int64), ("maxiter", C.c_int32), ("precond", C.c_int32),
-                ("reference_semantics", C.c_int32), ("check_every", C.c_int32)]
+                ("reference_semantics", C.c_int32), ("check_every", C.c_int32),
+                ("profile_iters", C.c_int32), ("reserved", C.c_int32)]
 
 
 class PcgResult(C.Structure):
     _fields_ = [("iters", C.c_int32), ("info", C.c_int32), ("relres", C.c_double), ("norm_b", C.c_double),
-                ("solve_ms", C.c_double), ("launches", C.c_int64)]
+                ("solve_ms", C.c_double), ("launches", C.c_int64), ("spmv_ms", C.c_double),
+                ("update_ms", C.c_double), ("profiled", C.c_int32), ("reserved", C.c_int32)]
 
 
 def nvcc_command(out=LIB_PATH):
@@ -95,6 +97,7 @@ def load():
     lib.lat_bsr_to_csr_values.argtypes = [vp, vp, i64, vp, vp]
     lib.lat_assemble_bsr.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, dbl, dbl, dbl, C.c_int, C.c_int, vp]
     lib.lat_apply_dirichlet.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
+    lib.lat_set_dirichlet_values.argtypes = [vp, vp, vp, i64, vp]
     lib.lat_bsr_spmv.argtypes = [vp, vp, vp, vp, i64, vp, vp]
     lib.lat_pcg_bsr.argtypes = [vp, vp, vp, vp, i64, vp, vp, C.POINTER(PcgOpts), C.POINTER(PcgResult)]
     lib.lat_compliance_grad.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, vp, vp, i64, vp, vp]
@@ -207,6 +210,10 @@ class Context:
                                                 _ptr(g), _ptr(f), _ptr(vbc), _ptr(b)))
         return vbc, b
 
+    def set_dirichlet_values(self, fixed, g, u):
+        self.check(self.lib.lat_set_dirichlet_values(self.h, _ptr(fixed), _ptr(g), u.numel(), _ptr(u)))
+        return u
+
     def spmv(self, rowptr, colidx, vals, x, out=None):
         import torch
         y = out if out is not None else torch.empty_like(x)
@@ -214,16 +221,18 @@ class Context:
         return y
 
     def pcg(self, rowptr, colidx, vals, b, x=None, tol=1e-8, maxiter=10000, precond=PC_JACOBI,
-            reference_semantics=False, mintol=0.0, alpha_max=0.0, restart_every=0, check_every=0):
+            reference_semantics=False, mintol=0.0, alpha_max=0.0, restart_every=0, check_every=0,
+            profile_iters=0):
         import torch
         if x is None:
             x = torch.empty_like(b)
-        o = PcgOpts(tol, mintol, alpha_max, restart_every, maxiter, precond, int(reference_semantics), check_every)
+        o = PcgOpts(tol, mintol, alpha_max, restart_every, maxiter, precond, int(reference_semantics), check_every,
+                    profile_iters, 0)
         r = PcgResult()
         self.check(self.lib.lat_pcg_bsr(self.h, _ptr(rowptr), _ptr(colidx), _ptr(vals), rowptr.numel() - 1, _ptr(b),
                                         _ptr(x), C.byref(o), C.byref(r)))
         return x, dict(iters=r.iters, info=r.info, relres=r.relres, norm_b=r.norm_b, solve_ms=r.solve_ms,
-                       launches=r.launches)
+                       launches=r.launches, spmv_ms=r.spmv_ms, update_ms=r.update_ms, profiled=r.profiled)
 
     def compliance_grad(self, x, y, z, en0, en1, rad, group, n_groups, u, young, nu, kappa=0.9, chain=None,
                         lam=None, want_elem=False):

@@ -23,7 +23,7 @@ def test_bcc20_m2_compression_full_size(ctx):
     # true residual of the constrained system, recomputed with the plain SpMV
     fx = torch.from_numpy(fixed).to(ctx.device).bool()
     r = R - torch.from_numpy(f).to(ctx.device)
-    assert float(r[~fx].norm()) <= 2e-8 * float(R[fx].norm())
+    assert float(r[~fx].norm()) <= 2e-8 * info["norm_b"]     # true residual vs the recurrence's 1e-8 |b|
     assert float((u[fx] - torch.from_numpy(g).to(ctx.device)[fx]).abs().max()) < 1e-14
     # global equilibrium: the reactions balance (no external load)
     Rn = R.reshape(-1, 6)
