@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 beam-FEM hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): BCC 20x20x20 lattice, r = 0.05, 2 elements per
+strut (81 261 nodes / 128 000 elements / 487 566 DOF), uniaxial compression
+(clamp Zmin, u_z = -0.01 on Zmax), VeroClear.  One STEP = one pass of the hot
+path: fused element generation + BSR assembly -> Dirichlet elimination ->
+6x6 block-Jacobi PCG to 1e-8 relative residual -> reactions.
+
+value  = PCG DOF-iterations / s = n_dof * iterations / device time of the WHOLE step
+         (assembly, elimination and reactions included), inputs resident in HBM.
+e2e    = the same quantity through the host-facing API (host numpy buffers in pinned
+         memory -> H2D of the mesh and BCs, pattern reuse, step, D2H of u and R).
+roofline = the dominant kernel (k_pcg_spmv: fused p-update + BSR SpMV + dots),
+         timed live with CUDA events on the library stream during the timed steps.
+
+Multi-GPU (N > 1): weak scaling, one process per GPU; the lattice is extended to
+(20 N) x 20 x 20 cells and cut into N x-slabs (see pylatticedso_b200/distributed.py).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+E_MOD, NU, KAPPA = 1013.0, 0.3, 0.9
+METRIC = "pcg_dof_iters_per_s"
+UNIT = "DOF-iterations/s"
+WORKLOAD = "BCC 20x20x20, r=0.05, 2 elements/strut (487566 DOF), uniaxial compression, block-Jacobi PCG to 1e-8"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            c = [v.strip() for v in row.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(n_slabs=1):
+    from pylatticedso_b200 import mesh as M
+    lat = M.synthetic_lattice("BCC", (20 * n_slabs, 20, 20), [0.05])
+    mesh = M.mesh_from_synthetic(lat, 2)
+    fixed, g, f = M.compression_bc(mesh)
+    return lat, mesh, fixed, g, f
+
+
+def spmv_bytes(n_nodes, nnzb):
+    """Algorithmic bytes of one k_pcg_spmv launch: matrix 288 B + column index 4 B per
+    block; per block row 4 B rowptr, 48 B z + 48 B p_old read, 48 B p_new + 48 B Ap written."""
+    return nnzb * 292 + n_nodes * (4 + 4 * 48)
+
+
+def iteration_bytes(n_nodes, nnzb, block_jacobi=True):
+    """SpMV (292 nb + 100)/6 B/DOF + 96 B/DOF (+48 B/DOF for 6x6 block-Jacobi)."""
+    return nnzb * 292 + n_nodes * 100 + 6 * n_nodes * (96 + (48 if block_jacobi else 0))
+
+
+# --------------------------------------------------------------------------- reference arm / CPU baseline
+def cpu_reference_run(steps, warmup, pcg_iters=1500, quiet=True):
+    """The reference's CPU path for this workload, restated (oracle port): numpy element
+    matrices + scipy COO->CSR assembly + Dirichlet elimination + the reference's PCG
+    (conjugate_gradient_solver.py semantics) with a Jacobi preconditioner on scipy's CSR
+    SpMV, `pcg_iters` iterations per step (bounded sample)."""
+    from oracle import lattice_oracle as orc
+    import scipy.sparse as sp
+    _, mesh, fixed, g, f = build_workload(1)
+    en = np.stack([mesh.en0, mesh.en1], 1)
+    xyz = mesh.xyz
+    times, asm_times = [], []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        K = orc.assemble_csr(xyz, en, mesh.rad, E_MOD, NU)
+        t1 = time.perf_counter()
+        Kbc, b = orc.apply_dirichlet(K, fixed, g, f)
+        Minv = sp.diags(1.0 / Kbc.diagonal())
+        x, info, it = orc.reference_pcg(Kbc, b, Minv, maxiter=pcg_iters, tol=1e-8, mintol=0.0,
+                                        restart_every=10 ** 9, alpha_max=1e300)
+        t2 = time.perf_counter()
+        if s >= warmup:
+            times.append(t2 - t0)
+            asm_times.append(t1 - t0)
+    T = float(np.sum(times))
+    val = mesh.n_dof * pcg_iters * steps / T
+    return dict(value=val, ms_per_step=1e3 * T / steps, asm_elems_per_s=mesh.n_elems * steps / float(np.sum(asm_times)),
+                n_dof=mesh.n_dof, iters=pcg_iters)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    try:
+        from threadpoolctl import threadpool_limits
+        limits = threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        limits = None
+    steps, warmup = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
+    r = cpu_reference_run(steps, warmup)
+    sample = (f"{steps} step(s): numpy/scipy assembly of the full 128000-element mesh + {r['iters']} Jacobi-PCG "
+              f"iterations each (scipy CSR SpMV is single-threaded)")
+    line = {
+        "metric": METRIC, "value": r["value"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU restatement of the reference path (dolfinx/PETSc are not installable here)"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores_available": os.cpu_count(),
+                         "assembly_elements_per_s": r["asm_elems_per_s"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from pylatticedso_b200 import lib as L
+    from pylatticedso_b200.fem import BeamFEM
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L.build()
+    ctx = L.Context(local)
+    dev = ctx.device
+    hbm_peak, peak_src = measured_peaks()
+
+    distributed = world > 1
+    if distributed:
+        from pylatticedso_b200 import distributed as D
+        prob = D.build_slab_problem(ctx, rank, world, cells_per_rank=20)
+        n_dof_global, n_elem_global = prob.n_dof_global, prob.n_elem_global
+    else:
+        lat, mesh, fixed, g, f = build_workload(1)
+        n_dof_global, n_elem_global = mesh.n_dof, mesh.n_elems
+
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    if not distributed:
+        host = {k: pin(v) for k, v in dict(x=mesh.x, y=mesh.y, z=mesh.z, en0=mesh.en0, en1=mesh.en1, rad=mesh.rad,
+                                           fixed=fixed, g=g, f=f).items()}
+        fem = BeamFEM(mesh, E_MOD, NU, KAPPA, ctx=ctx)
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record(); fem.build_pattern(); t1.record(); torch.cuda.synchronize()
+        pattern_ms = t0.elapsed_time(t1)
+        fixed_d, g_d, f_d = (host[k].to(dev) for k in ("fixed", "g", "f"))
+        vals = torch.empty(fem.nnzb * 36, dtype=torch.float64, device=dev)
+        vals_bc = torch.empty_like(vals)
+        n_nodes, nnzb = fem.n_nodes, fem.nnzb
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # > 126 MB L2
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def step(profile):
+        """One pass of the hot path with device-resident inputs. Returns per-phase events + PCG info."""
+        e = [ev() for _ in range(4)]
+        e[0].record()
+        ctx.assemble_bsr(fem.x, fem.y, fem.z, fem.en0, fem.en1, fem.rad, n_nodes, nnzb, E_MOD, NU, KAPPA, out=vals)
+        e[1].record()
+        ctx.check(ctx.lib.lat_apply_dirichlet(ctx.h, L._ptr(fem.rowptr), L._ptr(fem.colidx), n_nodes, L._ptr(vals),
+                                              L._ptr(fixed_d), L._ptr(g_d), L._ptr(f_d), L._ptr(vals_bc), L._ptr(b_d)))
+        e[2].record()
+        u, info = ctx.pcg(fem.rowptr, fem.colidx, vals_bc, b_d, x=u_d, tol=1e-8, maxiter=200000,
+                          precond=L.PC_BLOCK6, profile_iters=profile)
+        ctx.set_dirichlet_values(fixed_d, g_d, u)
+        ctx.spmv(fem.rowptr, fem.colidx, vals, u, out=R_d)
+        e[3].record()
+        return e, info
+
+    if distributed:
+        res = D.bench_steps(prob, args, flush)
+    else:
+        b_d = torch.empty(fem.n_dof, dtype=torch.float64, device=dev)
+        u_d = torch.empty_like(b_d)
+        R_d = torch.empty_like(b_d)
+        for _ in range(args.warmup):
+            step(0)
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        sampler.start()
+        launches0 = ctx.launches
+        tot_ms = asm_ms = solve_ms = 0.0
+        iters = 0
+        spmv_ms, upd_ms, nprof = [], [], 0
+        for _ in range(args.steps):
+            flush.fill_(1.0)            # evict the previous step's matrix from L2 (untimed)
+            torch.cuda.synchronize()
+            e, info = step(64)
+            torch.cuda.synchronize()
+            tot_ms += e[0].elapsed_time(e[3])
+            asm_ms += e[0].elapsed_time(e[1])
+            solve_ms += info["solve_ms"]
+            iters += info["iters"]
+            assert info["info"] == 0, f"PCG did not converge: {info}"
+            spmv_ms.append(info["spmv_ms"]); upd_ms.append(info["update_ms"]); nprof += info["profiled"]
+        launches = ctx.launches - launches0
+        clocks = sampler.stop()
+        # ---- end-to-end through the host-facing API: pinned host buffers -> H2D -> step -> D2H
+        h2d = sum(t.numel() * t.element_size() for t in host.values())
+        u_host = torch.empty(fem.n_dof, dtype=torch.float64).pin_memory()
+        R_host = torch.empty(fem.n_dof, dtype=torch.float64).pin_memory()
+        d2h = 2 * fem.n_dof * 8
+        e2e_ms, e2e_iters = 0.0, 0
+        for s in range(1 + args.steps):
+            flush.fill_(1.0)
+            torch.cuda.synchronize()
+            a, b_ = ev(), ev()
+            a.record()
+            for k, dst in (("x", fem.x), ("y", fem.y), ("z", fem.z), ("en0", fem.en0), ("en1", fem.en1), ("rad", fem.rad),
+                           ("fixed", fixed_d), ("g", g_d), ("f", f_d)):
+                dst.copy_(host[k], non_blocking=True)
+            _, info = step(0)
+            u_host.copy_(u_d, non_blocking=True)
+            R_host.copy_(R_d, non_blocking=True)
+            b_.record()
+            torch.cuda.synchronize()
+            if s >= 1:
+                e2e_ms += a.elapsed_time(b_)
+                e2e_iters += info["iters"]
+        res = dict(tot_ms=tot_ms, asm_ms=asm_ms, solve_ms=solve_ms, iters=iters, launches=launches, clocks=clocks,
+                   spmv_ms=float(np.mean(spmv_ms)), update_ms=float(np.mean(upd_ms)), nprof=nprof,
+                   e2e_ms=e2e_ms, e2e_iters=e2e_iters, h2d=h2d, d2h=d2h, pattern_ms=pattern_ms,
+                   n_nodes=n_nodes, nnzb=nnzb)
+
+    # max over ranks of the timed region
+    tot_ms = res["tot_ms"]
+    if world > 1:
+        t = torch.tensor([res["tot_ms"], res["e2e_ms"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tot_ms, res["e2e_ms"] = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = n_dof_global * res["iters"] / (tot_ms * 1e-3)
+    e2e_val = n_dof_global * res["e2e_iters"] / (res["e2e_ms"] * 1e-3)
+    nn, nz = res["n_nodes"], res["nnzb"]
+    ach = spmv_bytes(nn, nz) / (res["spmv_ms"] * 1e-3) / 1e9
+    it_bytes = iteration_bytes(nn, nz, True)
+    it_gbs = it_bytes * res["iters"] / (res["solve_ms"] * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD if world == 1 else f"BCC {20 * world}x20x20 in {world} x-slabs of 20 cell layers (weak scaling of: {WORKLOAD})",
+                   "n_dof": n_dof_global, "n_elements": n_elem_global, "precond": "block-jacobi-6x6", "tol": 1e-8,
+                   "iterations_per_step": res["iters"] / args.steps,
+                   "l2": "L2 flushed (256 MB write) between steps; within a step the 98 MB matrix is re-streamed "
+                         "every PCG iteration with evict-first loads (working set ~ L2 size, see DESIGN.md)",
+                   "parallelism": "single" if world == 1 else f"slab{world}"},
+        "assembly": {"value": n_elem_global * args.steps / (res["asm_ms"] * 1e-3), "unit": "elements/s",
+                     "ms": res["asm_ms"] / args.steps, "mode": "gather (deterministic, fused element generation)",
+                     "pattern_build_ms_one_off": res.get("pattern_ms")},
+        "pcg": {"solve_ms_per_step": res["solve_ms"] / args.steps, "iteration_GBps_survey_bytes": it_gbs,
+                "iteration_frac_of_hbm": it_gbs / hbm_peak, "update_kernel_ms": res["update_ms"]},
+        "roofline": {"kernel": "k_pcg_spmv (fused p = z + beta p, BSR 6x6 SpMV, p.Ap, p.p)", "bound": "hbm",
+                     "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                     "peak_source": peak_src, "bytes_per_launch": spmv_bytes(nn, nz),
+                     "avg_launch_ms": res["spmv_ms"], "launches_timed": res["nprof"]},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": res["h2d"], "d2h_bytes_per_step": res["d2h"],
+                "ms_per_step": res["e2e_ms"] / args.steps},
+        "gpu_launches": res["launches"],
+        "clocks": res["clocks"],
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        c = cpu_reference_run(1, 0, pcg_iters=1000)
+        line["cpu_baseline"] = {"value": c["value"], "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": "1 step: numpy/scipy assembly of the full mesh + 1000 Jacobi-PCG iterations "
+                                          "(oracle port; scipy SpMV is single-threaded)",
+                                "host_cores_available": os.cpu_count(),
+                                "assembly_elements_per_s": c["asm_elems_per_s"]}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
