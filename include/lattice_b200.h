@@ -141,7 +141,7 @@ typedef struct {
   int32_t check_every; /* iterations between host polls of the device status (0 = default 32) */
   int32_t profile_iters; /* >0: the first profile_iters iterations are launched outside the CUDA graph
                             with CUDA events around each kernel (fills spmv_ms / update_ms) */
-  int32_t reserved;
+  int32_t reserved;      /* bit 1: use the experimental TMA-staged (cp.async.bulk) SpMV kernel (A/B testing) */
 } lat_pcg_opts;
 
 typedef struct {

@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_bsr_spmv(const int32_t* __restri
 
 int lat_spmv_internal(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, const double* vals,
                       int64_t n_nodes, const double* x, double* y) {
+  // one-shot products (lifting, reactions) use the direct-load kernel: no partition / host sync needed
   LAT_LAUNCH(ctx, k_bsr_spmv, (unsigned)ceil_div(n_nodes, ROWS_PER_CTA), SPMV_BLOCK, 0, rowptr, colidx, vals,
              n_nodes, x, y);
   return LAT_OK;
@@ -284,6 +285,204 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_pcg_update(int64_t n_nodes, cons
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// TMA-staged SpMV (sm_90+ bulk async copy, used on sm_100a)
+// ---------------------------------------------------------------------------
+// A CTA owns a contiguous range of block rows whose matrix blocks form ONE contiguous
+// byte range of `vals` (<= cap_blocks * 288 B).  One elected thread arms an mbarrier
+// and issues cp.async.bulk (global -> shared) for the whole range; the other threads
+// meanwhile fetch the column indices.  With 4 CTAs resident per SM, ~200 KB of matrix
+// per SM are in flight while other CTAs compute, so HBM latency is covered by
+// CTA-level parallelism instead of per-thread dependent loads (the v1 kernel issued
+// rowptr -> colidx -> vals -> vector loads back to back in every thread).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// row partition: CTA i covers rows [cta_row0[i], cta_row0[i+1]) = the rows whose first block index
+// falls in [i*T, (i+1)*T)  ->  at most T + max_row_len - 1 blocks per CTA.
+__global__ void k_spmv_partition(const int32_t* __restrict__ rowptr, int64_t n_nodes, int T, int G,
+                                 int32_t* __restrict__ cta_row0, int32_t* __restrict__ max_nb) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= G) {
+    const int64_t target = i * (int64_t)T;
+    int64_t lo = 0, hi = n_nodes;  // first row r with rowptr[r] >= target
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (rowptr[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    cta_row0[i] = (i == G) ? (int32_t)n_nodes : (int32_t)lo;
+  }
+  // longest row (grid-stride)
+  int m = 0;
+  for (int64_t r = i; r < n_nodes; r += (int64_t)gridDim.x * blockDim.x) m = max(m, rowptr[r + 1] - rowptr[r]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(max_nb, m);
+}
+
+static constexpr int TMA_T = 160;  // target blocks per CTA (46 KB of matrix)
+
+// MODE 0: y = A x.   MODE 1: PCG kernel 1 (p_new = z + beta p_old; Ap; p.Ap, p.p)
+template <int MODE>
+__global__ void __launch_bounds__(SPMV_BLOCK, 4)
+k_spmv_tma(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const double* __restrict__ vals,
+           int64_t n_nodes, const int32_t* __restrict__ cta_row0, int cap_blocks, const double* __restrict__ xz,
+           double* __restrict__ pa, double* __restrict__ pb, double* __restrict__ y, PcgScalars* __restrict__ sc,
+           double* __restrict__ partials, PcgParams prm) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t s_bar;
+  double* s_vals = reinterpret_cast<double*>(smem_raw);
+  int32_t* s_col = reinterpret_cast<int32_t*>(smem_raw + (size_t)cap_blocks * 288);
+  int k = 0;
+  double beta = 0.0;
+  const double* __restrict__ p_old = nullptr;
+  double* __restrict__ p_new = nullptr;
+  if (MODE == 1) {
+    if (sc->done || sc->iters >= prm.maxiter) return;
+    k = sc->iters;
+    beta = sc->beta;
+    p_old = (k & 1) ? pb : pa;
+    p_new = (k & 1) ? pa : pb;
+  }
+  const int r0 = cta_row0[blockIdx.x], r1 = cta_row0[blockIdx.x + 1];
+  const int b0 = rowptr[r0], b1 = rowptr[r1];
+  const int nblk = b1 - b0;
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar, 1);
+    if (nblk > 0) {
+      const uint32_t bytes = (uint32_t)nblk * 288u;
+      mbar_expect_tx(&s_bar, bytes);
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(vals + (int64_t)b0 * 36);
+      unsigned char* dst = smem_raw;
+      for (uint32_t off = 0; off < bytes; off += 32768u) {
+        const uint32_t n = min(32768u, bytes - off);
+        bulk_g2s(dst + off, src + off, n, &s_bar);
+      }
+    }
+  }
+  for (int i = threadIdx.x; i < nblk; i += SPMV_BLOCK) s_col[i] = __ldg(colidx + b0 + i);
+  __syncthreads();
+  if (nblk > 0) mbar_wait(&s_bar, 0);
+
+  const int lane = threadIdx.x & 31;
+  const int g = lane / 6, r = lane - g * 6;
+  double dot_pAp = 0.0, dot_pp = 0.0;
+  for (int base = r0 + (threadIdx.x >> 5) * ROWS_PER_WARP; base < r1; base += ROWS_PER_CTA) {
+    const int n = base + g;
+    if (g < ROWS_PER_WARP && n < r1) {
+      const int lo = rowptr[n] - b0, hi = rowptr[n + 1] - b0;
+      double acc = 0.0;
+#pragma unroll 2
+      for (int j = lo; j < hi; ++j) {
+        const int c = s_col[j];
+        const double2* vp = reinterpret_cast<const double2*>(s_vals + j * 36 + r * 6);
+        const double2 a0 = vp[0], a1 = vp[1], a2 = vp[2];
+        double2 x0, x1, x2;
+        if (MODE == 1) {
+          const double2* zp = reinterpret_cast<const double2*>(xz + (int64_t)c * 6);
+          const double2* pp = reinterpret_cast<const double2*>(p_old + (int64_t)c * 6);
+          const double2 z0 = zp[0], z1 = zp[1], z2 = zp[2];
+          const double2 q0 = pp[0], q1 = pp[1], q2 = pp[2];
+          x0.x = fma(beta, q0.x, z0.x); x0.y = fma(beta, q0.y, z0.y);
+          x1.x = fma(beta, q1.x, z1.x); x1.y = fma(beta, q1.y, z1.y);
+          x2.x = fma(beta, q2.x, z2.x); x2.y = fma(beta, q2.y, z2.y);
+        } else {
+          const double2* xp = reinterpret_cast<const double2*>(xz + (int64_t)c * 6);
+          x0 = __ldg(xp); x1 = __ldg(xp + 1); x2 = __ldg(xp + 2);
+        }
+        acc = dot6(a0, a1, a2, x0, x1, x2, acc);
+      }
+      const int64_t i = (int64_t)n * 6 + r;
+      if (MODE == 1) {
+        const double pv = fma(beta, p_old[i], xz[i]);
+        p_new[i] = pv;
+        dot_pAp = fma(pv, acc, dot_pAp);
+        dot_pp = fma(pv, pv, dot_pp);
+      }
+      y[i] = acc;
+    }
+  }
+  if (MODE == 1) {
+    double v[2] = {dot_pAp, dot_pp}, out[2];
+    if (grid_reduce<2, SPMV_BLOCK>(v, partials, &sc->counter[1], out)) {
+      sc->pAp = out[0];
+      sc->pp = out[1];
+    }
+  }
+}
+
+struct SpmvPlan {
+  bool tma = false;
+  int grid = 0, cap_blocks = 0, smem = 0;
+  int32_t* cta_row0 = nullptr;
+};
+
+// Builds (or reuses) the row partition of a BSR matrix for the TMA kernels.  [syncs once per new matrix]
+static int spmv_plan(lat_ctx* ctx, const int32_t* rowptr, int64_t n_nodes, SpmvPlan* plan) {
+  plan->tma = false;
+  int32_t* meta = lat_buf<int32_t>(ctx, "spmv_meta", 8);
+  if (!meta) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+  int32_t nnzb32 = 0;
+  LAT_CUDA(ctx, cudaMemsetAsync(meta, 0, 8 * sizeof(int32_t), ctx->stream));
+  LAT_CUDA(ctx, cudaMemcpyAsync(&nnzb32, rowptr + n_nodes, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const int64_t nnzb = nnzb32;
+  if (nnzb <= 0) return LAT_OK;
+  const int G = (int)ceil_div(nnzb, TMA_T);
+  int32_t* cta_row0 = lat_buf<int32_t>(ctx, "spmv_cta_row0", (size_t)G + 2);
+  if (!cta_row0) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+  const int64_t work = n_nodes > G + 1 ? n_nodes : G + 1;
+  int64_t pg = ceil_div(work, 256);
+  if (pg > 4096) pg = 4096;
+  if (pg * 256 < G + 1) pg = ceil_div(G + 1, 256);
+  LAT_LAUNCH(ctx, k_spmv_partition, (unsigned)pg, 256, 0, rowptr, n_nodes, TMA_T, G, cta_row0, meta);
+  int32_t max_nb = 0;
+  LAT_CUDA(ctx, cudaMemcpyAsync(&max_nb, meta, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const int cap = TMA_T + max_nb;
+  const int smem = ((cap * 292 + 15) / 16) * 16;
+  if (smem > 200 * 1024) return LAT_OK;  // pathological row length: keep the direct-load kernels
+  static bool attr_done = false;
+  if (!attr_done || true) {
+    LAT_CUDA(ctx, cudaFuncSetAttribute(k_spmv_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    LAT_CUDA(ctx, cudaFuncSetAttribute(k_spmv_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  plan->tma = true;
+  plan->grid = G;
+  plan->cap_blocks = cap;
+  plan->smem = smem;
+  plan->cta_row0 = cta_row0;
+  return LAT_OK;
+}
+
 // ---------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------
@@ -292,13 +491,22 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
                    int64_t n_nodes, const double* b, double* x, const lat_pcg_opts* o, lat_pcg_result* res) {
   const int64_t n = 6 * n_nodes;
   const unsigned grid = (unsigned)ceil_div(n_nodes, ROWS_PER_CTA);
+  // The TMA-staged SpMV is opt-in (bit 1 of `reserved`): on B200 it measured 5-10 % SLOWER than the
+  // direct-load kernel (tools/ab_spmv.py, profiles/r01_spmv_ab.txt) because the kernel is bound by
+  // L2->SM traffic of the vector gathers, not by HBM latency.
+  SpmvPlan plan;
+  if (o->reserved & 2) {
+    const int prc = spmv_plan(ctx, rowptr, n_nodes, &plan);
+    if (prc) return prc;
+  }
+  const size_t max_grid = (plan.tma && (unsigned)plan.grid > grid) ? (size_t)plan.grid : (size_t)grid;
   double* r = lat_buf<double>(ctx, "pcg_r", n);
   double* z = lat_buf<double>(ctx, "pcg_z", n);
   double* pa = lat_buf<double>(ctx, "pcg_pa", n);
   double* pb = lat_buf<double>(ctx, "pcg_pb", n);
   double* Ap = lat_buf<double>(ctx, "pcg_Ap", n);
   double* dinv = lat_buf<double>(ctx, "pcg_dinv", PC == LAT_PC_BLOCK6 ? 36 * n_nodes : n);
-  double* partials = lat_buf<double>(ctx, "pcg_partials", (size_t)4 * grid + 8);
+  double* partials = lat_buf<double>(ctx, "pcg_partials", (size_t)4 * max_grid + 8);
   PcgScalars* sc = lat_buf<PcgScalars>(ctx, "pcg_scalars", 1);
   if (!r || !z || !pa || !pb || !Ap || !dinv || !partials || !sc)
     return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
@@ -313,6 +521,13 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
   int check = o->check_every > 0 ? o->check_every : 32;
   if (check > o->maxiter) check = o->maxiter > 0 ? o->maxiter : 1;
 
+  auto launch_spmv = [&](cudaStream_t st) {
+    if (plan.tma)
+      k_spmv_tma<1><<<plan.grid, SPMV_BLOCK, plan.smem, st>>>(rowptr, colidx, vals, n_nodes, plan.cta_row0,
+                                                             plan.cap_blocks, z, pa, pb, Ap, sc, partials, prm);
+    else
+      k_pcg_spmv<0><<<grid, SPMV_BLOCK, 0, st>>>(rowptr, colidx, vals, n_nodes, z, pa, pb, Ap, sc, partials, prm);
+  };
   LAT_CUDA(ctx, cudaMemsetAsync(sc, 0, sizeof(PcgScalars), ctx->stream));
   if (PC != LAT_PC_NONE)
     LAT_LAUNCH(ctx, k_precond_setup, (unsigned)ceil_div(n_nodes, 128), 128, 0, rowptr, colidx, vals, n_nodes, PC, dinv);
@@ -327,7 +542,7 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
   cudaError_t ce = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
   if (ce == cudaSuccess) {
     for (int it = 0; it < check; ++it) {
-      k_pcg_spmv<0><<<grid, SPMV_BLOCK, 0, cap>>>(rowptr, colidx, vals, n_nodes, z, pa, pb, Ap, sc, partials, prm);
+      launch_spmv(cap);
       k_pcg_update<PC><<<grid, SPMV_BLOCK, 0, cap>>>(n_nodes, dinv, x, r, z, pa, pb, Ap, sc, partials, prm);
     }
     ce = cudaStreamEndCapture(cap, &graph);
@@ -350,7 +565,7 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
     for (auto& e : evs) cudaEventCreate(&e);
     for (int it = 0; it < nprof; ++it) {
       cudaEventRecord(evs[3 * it], ctx->stream);
-      k_pcg_spmv<0><<<grid, SPMV_BLOCK, 0, ctx->stream>>>(rowptr, colidx, vals, n_nodes, z, pa, pb, Ap, sc, partials, prm);
+      launch_spmv(ctx->stream);
       cudaEventRecord(evs[3 * it + 1], ctx->stream);
       k_pcg_update<PC><<<grid, SPMV_BLOCK, 0, ctx->stream>>>(n_nodes, dinv, x, r, z, pa, pb, Ap, sc, partials, prm);
       cudaEventRecord(evs[3 * it + 2], ctx->stream);

@@ -1,0 +1,123 @@
+// Standalone micro-benchmark used to choose the SpMV thread mapping (not part of the library).
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o spmv_bench spmv_bench.cu
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <algorithm>
+#define CK(x) do{cudaError_t e=(x); if(e!=cudaSuccess){printf("CUDA %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1);} }while(0)
+
+__global__ void k_read(const double2* __restrict__ v, size_t n2, double* out) {
+  double s = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+    double2 a = __ldcs(v + i); s += a.x + a.y;
+  }
+  if (s == 123.456) out[0] = s;
+}
+
+// V0/V1/V2: 6 lanes per row, 5 rows per warp (library v1 mapping)
+template <int MODE>
+__global__ void __launch_bounds__(256) k_v1(const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                                             const double* __restrict__ vals, int n_nodes, const double* __restrict__ x,
+                                             const double* __restrict__ x2, double* __restrict__ y, double* __restrict__ y2) {
+  const int lane = threadIdx.x & 31, g = lane / 6, r = lane - g * 6;
+  const long warp = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long n = warp * 5 + g;
+  if (g >= 5 || n >= n_nodes) return;
+  const int lo = rowptr[n], hi = rowptr[n + 1];
+  double acc = 0;
+#pragma unroll 4
+  for (int j = lo; j < hi; ++j) {
+    const double2* vp = reinterpret_cast<const double2*>(vals + (long)j * 36 + r * 6);
+    const double2 a0 = __ldcs(vp), a1 = __ldcs(vp + 1), a2 = __ldcs(vp + 2);
+    if (MODE == 0) { acc += a0.x + a0.y + a1.x + a1.y + a2.x + a2.y; continue; }
+    const int c = __ldg(colidx + j);
+    const double2* xp = reinterpret_cast<const double2*>(x + (long)c * 6);
+    double2 x0 = __ldg(xp), x1 = __ldg(xp + 1), x2v = __ldg(xp + 2);
+    if (MODE == 2) {
+      const double2* qp = reinterpret_cast<const double2*>(x2 + (long)c * 6);
+      double2 q0 = __ldg(qp), q1 = __ldg(qp + 1), q2 = __ldg(qp + 2);
+      x0.x += 0.5 * q0.x; x0.y += 0.5 * q0.y; x1.x += 0.5 * q1.x; x1.y += 0.5 * q1.y; x2v.x += 0.5 * q2.x; x2v.y += 0.5 * q2.y;
+    }
+    acc += a0.x * x0.x + a0.y * x0.y + a1.x * x1.x + a1.y * x1.y + a2.x * x2v.x + a2.y * x2v.y;
+  }
+  y[n * 6 + r] = acc;
+  if (MODE == 2) y2[n * 6 + r] = acc * 0.5;
+}
+
+// V3: warp streams its rows' blocks flat: lane l loads double2 #l of an 18-double2 block pair layout.
+// Each warp handles ROWS consecutive rows; the blocks of those rows are contiguous -> the warp reads
+// them with perfectly coalesced 512 B requests (32 lanes x 16 B), multiplies by the gathered x and
+// does a segmented reduction: 3 lanes per matrix row-of-block, blocks summed per row via smem atomics-free pass.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_flat(const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                                               const double* __restrict__ vals, int n_nodes, const double* __restrict__ x,
+                                               const double* __restrict__ x2, double* __restrict__ y, double* __restrict__ y2) {
+  // CTA handles 64 rows; per-row accumulators in shared memory (6 doubles each)
+  __shared__ double s_y[64 * 6];
+  __shared__ int s_rp[65];
+  const int row0 = blockIdx.x * 64;
+  const int nrow = min(64, n_nodes - row0);
+  for (int i = threadIdx.x; i <= nrow; i += 256) s_rp[i] = rowptr[row0 + i];
+  for (int i = threadIdx.x; i < 64 * 6; i += 256) s_y[i] = 0.0;
+  __syncthreads();
+  const int b0 = s_rp[0], b1 = s_rp[nrow];
+  const long q0 = (long)b0 * 18, q1 = (long)b1 * 18;  // double2 units
+  const double2* v2 = reinterpret_cast<const double2*>(vals);
+  for (long q = q0 + threadIdx.x; q < q1; q += 256) {
+    const double2 a = __ldcs(v2 + q);
+    const int blk = (int)(q / 18), w = (int)(q - (long)blk * 18);   // w: 0..17 -> row w/3, col pair w%3
+    const int rr = w / 3, cp = w - rr * 3;
+    double v;
+    if (MODE == 0) v = a.x + a.y;
+    else {
+      const int c = __ldg(colidx + blk);
+      const double2 xv = __ldg(reinterpret_cast<const double2*>(x + (long)c * 6) + cp);
+      v = a.x * xv.x + a.y * xv.y;
+      if (MODE == 2) { const double2 qv = __ldg(reinterpret_cast<const double2*>(x2 + (long)c * 6) + cp); v += 0.5 * (a.x * qv.x + a.y * qv.y); }
+    }
+    // find row of blk by binary search in s_rp
+    int lo = 0, hi = nrow;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_rp[mid] <= blk) lo = mid; else hi = mid; }
+    atomicAdd(&s_y[lo * 6 + rr], v);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nrow * 6; i += 256) { y[(long)row0 * 6 + i] = s_y[i]; if (MODE == 2) y2[(long)row0 * 6 + i] = 0.5 * s_y[i]; }
+}
+
+int main(int argc, char** argv) {
+  int N = argc > 1 ? atoi(argv[1]) : 440000; int NB = argc > 2 ? atoi(argv[2]) : 9;
+  std::vector<int> rp(N + 1), ci; rp[0] = 0;
+  for (int i = 0; i < N; ++i) {
+    std::vector<int> c;
+    for (int k = 0; k < NB; ++k) { long o = (long)i + (k - NB / 2) * 997L; o = ((o % N) + N) % N; c.push_back((int)o); }
+    std::sort(c.begin(), c.end()); c.erase(std::unique(c.begin(), c.end()), c.end());
+    for (int v : c) ci.push_back(v); rp[i + 1] = (int)ci.size();
+  }
+  size_t nnzb = ci.size();
+  double *vals, *x, *x2, *y, *y2; int *drp, *dci;
+  CK(cudaMalloc(&vals, nnzb * 288)); CK(cudaMalloc(&x, N * 48)); CK(cudaMalloc(&x2, N * 48)); CK(cudaMalloc(&y, N * 48)); CK(cudaMalloc(&y2, N * 48));
+  CK(cudaMalloc(&drp, (N + 1) * 4)); CK(cudaMalloc(&dci, nnzb * 4));
+  CK(cudaMemset(vals, 0, nnzb * 288)); CK(cudaMemset(x, 0, N * 48)); CK(cudaMemset(x2, 0, N * 48));
+  CK(cudaMemcpy(drp, rp.data(), (N + 1) * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dci, ci.data(), nnzb * 4, cudaMemcpyHostToDevice));
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double mb = nnzb * 292.0 / 1e6;
+  printf("N=%d nnzb=%zu matrix=%.1f MB\n", N, nnzb, mb);
+  auto timeit = [&](const char* name, auto fn, double bytes) {
+    for (int i = 0; i < 3; ++i) fn();
+    cudaEventRecord(e0); for (int i = 0; i < 20; ++i) fn(); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+    float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 20;
+    printf("%-28s %8.1f us  %7.0f GB/s\n", name, ms * 1e3, bytes / ms / 1e6);
+  };
+  double bytes_m = nnzb * 288.0, bytes_1 = nnzb * 292.0 + N * 100.0, bytes_2 = nnzb * 292.0 + N * (4 + 4 * 48.0);
+  timeit("read-only stream", [&] { k_read<<<148 * 16, 256>>>((const double2*)vals, nnzb * 18, y); }, bytes_m);
+  int grid = (N + 39) / 40;
+  timeit("v1 matrix only", [&] { k_v1<0><<<grid, 256>>>(drp, dci, vals, N, x, x2, y, y2); }, bytes_m);
+  timeit("v1 spmv", [&] { k_v1<1><<<grid, 256>>>(drp, dci, vals, N, x, x2, y, y2); }, bytes_1);
+  timeit("v1 pcg-like (2 gathers)", [&] { k_v1<2><<<grid, 256>>>(drp, dci, vals, N, x, x2, y, y2); }, bytes_2);
+  int gridf = (N + 63) / 64;
+  timeit("flat matrix only", [&] { k_flat<0><<<gridf, 256>>>(drp, dci, vals, N, x, x2, y, y2); }, bytes_m);
+  timeit("flat spmv", [&] { k_flat<1><<<gridf, 256>>>(drp, dci, vals, N, x, x2, y, y2); }, bytes_1);
+  timeit("flat pcg-like", [&] { k_flat<2><<<gridf, 256>>>(drp, dci, vals, N, x, x2, y, y2); }, bytes_2);
+  return 0;
+}
