@@ -204,4 +204,24 @@ __device__ __forceinline__ void elem_block_accum(const ElemCoef& e, int re, int 
   }
 }
 
+// Single entry (i, j), 0 <= i, j < 6, of the 6x6 block (row node end re, column node end ce).
+__device__ __forceinline__ double elem_block_entry(const ElemCoef& e, int re, int ce, int i, int j) {
+  const double sA = (re == ce) ? 1.0 : -1.0;
+  const bool rw = i < 3, cw = j < 3;
+  const int a = rw ? i : i - 3, b = cw ? j : j - 3;
+  const double ta = (a == 0) ? e.tx : (a == 1 ? e.ty : e.tz);
+  const double tb = (b == 0) ? e.tx : (b == 1 ? e.ty : e.tz);
+  const double d = (a == b) ? 1.0 : 0.0;
+  if (rw && cw) return sA * (e.aI * d + e.aT * ta * tb);
+  if (!rw && !cw) return (e.bI + sA * e.dI) * d + (sA * e.dT - e.bI) * ta * tb;
+  double sk = 0.0;
+  if (a != b) {
+    const int k = 3 - a - b;
+    const double tk = (k == 0) ? e.tx : (k == 1 ? e.ty : e.tz);
+    sk = ((b - a + 3) % 3 == 1) ? -tk : tk;  // [t]x entry (a, b)
+  }
+  if (rw) return ((re == 0) ? -e.c : e.c) * sk;
+  return ((ce == 0) ? e.c : -e.c) * sk;
+}
+
 #endif  // __CUDACC__

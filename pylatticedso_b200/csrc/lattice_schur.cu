@@ -1,17 +1,299 @@
-// lattice_schur.cu -- batched per-cell Schur complements and the DDM interface operator.  sm_100a.
+// lattice_schur.cu -- batched per-cell Schur complements (dense partial Cholesky, one CTA per
+// cell) and the DDM interface operator (batched S_c GEMV with gather/scatter).  sm_100a.
 #include "common.cuh"
+
+static constexpr int SCHUR_BLOCK = 256;
+static constexpr int SCHUR_MAX_NB = 96;   // boundary DOFs per cell (BCC 48, Octet 84)
+static constexpr int GRAD_PER_THREAD = (SCHUR_MAX_NB * SCHUR_MAX_NB + SCHUR_BLOCK - 1) / SCHUR_BLOCK;
+
+// position of local node l in the factorisation order: interior nodes first, boundary nodes last
+__device__ __forceinline__ int node_pos(int l, int nn, int nbn) { return l >= nbn ? l - nbn : nn - nbn + l; }
+
+// The six strain 12-vectors of an element (oracle.strain_vectors; simulation_base.py:141-156) --
+// only needed for the rank-6 form of dK_e used by the sensitivity contraction.
+__device__ void strain_vectors_dev(const double* xa, const double* xb, double* B /*[6][12]*/, double* Lout) {
+  double d[3] = {xb[0] - xa[0], xb[1] - xa[1], xb[2] - xa[2]};
+  const double L = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), iL = 1.0 / L;
+  double t[3] = {d[0] * iL, d[1] * iL, d[2] * iL};
+  // frame rule of beam_model.py:199-216
+  double e1[3] = {1, 0, 0};
+  if (fabs(t[1]) < fabs(t[0])) { e1[0] = 0; e1[1] = 1; }
+  const double te1 = t[0] * e1[0] + t[1] * e1[1] + t[2] * e1[2];
+  double e2[3] = {e1[0], e1[1], e1[2]};
+  if (fabs(t[2]) < fabs(te1)) { e2[0] = 0; e2[1] = 0; e2[2] = 1; }
+  double a1[3] = {t[1] * e2[2] - t[2] * e2[1], t[2] * e2[0] - t[0] * e2[2], t[0] * e2[1] - t[1] * e2[0]};
+  double n1 = 1.0 / sqrt(a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2]);
+  a1[0] *= n1; a1[1] *= n1; a1[2] *= n1;
+  double a2[3] = {t[1] * a1[2] - t[2] * a1[1], t[2] * a1[0] - t[0] * a1[2], t[0] * a1[1] - t[1] * a1[0]};
+  double n2 = 1.0 / sqrt(a2[0] * a2[0] + a2[1] * a2[1] + a2[2] * a2[2]);
+  a2[0] *= n2; a2[1] *= n2; a2[2] *= n2;
+  for (int i = 0; i < 72; ++i) B[i] = 0.0;
+  for (int k = 0; k < 3; ++k) {
+    B[0 * 12 + k] = -t[k] * iL;  B[0 * 12 + 6 + k] = t[k] * iL;
+    B[1 * 12 + k] = -a1[k] * iL; B[1 * 12 + 6 + k] = a1[k] * iL; B[1 * 12 + 3 + k] = -0.5 * a2[k]; B[1 * 12 + 9 + k] = -0.5 * a2[k];
+    B[2 * 12 + k] = -a2[k] * iL; B[2 * 12 + 6 + k] = a2[k] * iL; B[2 * 12 + 3 + k] = 0.5 * a1[k];  B[2 * 12 + 9 + k] = 0.5 * a1[k];
+    B[3 * 12 + 3 + k] = -t[k] * iL;  B[3 * 12 + 9 + k] = t[k] * iL;
+    B[4 * 12 + 3 + k] = -a1[k] * iL; B[4 * 12 + 9 + k] = a1[k] * iL;
+    B[5 * 12 + 3 + k] = -a2[k] * iL; B[5 * 12 + 9 + k] = a2[k] * iL;
+  }
+  *Lout = L;
+}
+
+// One CTA per cell (grid-stride over cells).  A = dense cell stiffness in factorisation order
+// (interior DOFs first), lower triangle used.  Partial right-looking Cholesky over the nI interior
+// pivots; the rows of column k that are exactly zero are skipped (the cell graph is a set of strut
+// chains joined at a few nodes, so most of the column is structurally zero), which keeps the cost
+// proportional to the fill, not to n^3.  The trailing nB x nB block is then the Schur complement.
+template <bool SMEM>
+__global__ void __launch_bounds__(SCHUR_BLOCK) k_schur_dense(
+    const double* __restrict__ xyz, const int32_t* __restrict__ len0, const int32_t* __restrict__ len1,
+    const double* __restrict__ rad, int64_t n_cells, int nn, int nbn, int ne, double young, double nu, double kappa,
+    double* __restrict__ S, double* __restrict__ ws, const int32_t* __restrict__ elem_group,
+    const double* __restrict__ drad_chain, int n_grad, double* __restrict__ dS) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const int n = 6 * nn, nB = 6 * nbn, nI = n - nB;
+  const int ld = n | 1;  // odd leading dimension: column walks are bank-conflict free
+  // shared layout
+  size_t off = 0;
+  double* A = SMEM ? reinterpret_cast<double*>(sm_raw) : (ws + (size_t)blockIdx.x * n * ld);
+  if (SMEM) off += (size_t)n * ld * sizeof(double);
+  ElemCoef* s_coef = reinterpret_cast<ElemCoef*>(sm_raw + off); off += (size_t)ne * sizeof(ElemCoef);
+  double* s_diag = reinterpret_cast<double*>(sm_raw + off); off += (size_t)n * sizeof(double);
+  double* s_v = reinterpret_cast<double*>(sm_raw + off); off += (size_t)6 * SCHUR_MAX_NB * sizeof(double);
+  double* s_B = reinterpret_cast<double*>(sm_raw + off); off += 80 * sizeof(double);  // 72 strain entries + L + weights
+  int32_t* s_list = reinterpret_cast<int32_t*>(sm_raw + off); off += (size_t)n * sizeof(int32_t);
+  int32_t* s_e0 = reinterpret_cast<int32_t*>(sm_raw + off); off += (size_t)ne * sizeof(int32_t);
+  int32_t* s_e1 = reinterpret_cast<int32_t*>(sm_raw + off); off += (size_t)ne * sizeof(int32_t);
+  __shared__ int s_cnt;
+  __shared__ int s_bad;
+  const int tid = threadIdx.x;
+
+  for (int e = tid; e < ne; e += SCHUR_BLOCK) { s_e0[e] = len0[e]; s_e1[e] = len1[e]; }
+
+  for (int64_t c = blockIdx.x; c < n_cells; c += gridDim.x) {
+    const double* cx = xyz + c * (int64_t)nn * 3;
+    const double* cr = rad + c * (int64_t)ne;
+    __syncthreads();
+    if (tid == 0) { s_cnt = 0; s_bad = 0; }
+    for (int e = tid; e < ne; e += SCHUR_BLOCK) {
+      const int a = s_e0[e], b = s_e1[e];
+      s_coef[e] = elem_coef(cx[a * 3], cx[a * 3 + 1], cx[a * 3 + 2], cx[b * 3], cx[b * 3 + 1], cx[b * 3 + 2], cr[e],
+                            young, nu, kappa, false);
+    }
+    for (int i = tid; i < n * ld; i += SCHUR_BLOCK) A[i] = 0.0;
+    __syncthreads();
+    // ---- assembly: work item = (row node a, entry k of a 6x6 block); fixed element order -> deterministic
+    for (int w = tid; w < nn * 36; w += SCHUR_BLOCK) {
+      const int a = w / 36, k = w - a * 36, i = k / 6, j = k - i * 6;
+      const int ra = node_pos(a, nn, nbn) * 6 + i;
+      double diag = 0.0;
+      for (int e = 0; e < ne; ++e) {
+        const int e0 = s_e0[e], e1 = s_e1[e];
+        if (e0 == a) {
+          diag += elem_block_entry(s_coef[e], 0, 0, i, j);
+          A[ra * ld + node_pos(e1, nn, nbn) * 6 + j] += elem_block_entry(s_coef[e], 0, 1, i, j);
+        } else if (e1 == a) {
+          diag += elem_block_entry(s_coef[e], 1, 1, i, j);
+          A[ra * ld + node_pos(e0, nn, nbn) * 6 + j] += elem_block_entry(s_coef[e], 1, 0, i, j);
+        }
+      }
+      A[ra * ld + node_pos(a, nn, nbn) * 6 + j] += diag;
+    }
+    // ---- partial Cholesky over the interior pivots
+    for (int k = 0; k < nI; ++k) {
+      __syncthreads();
+      const double p = A[k * ld + k];
+      if (!(p > 0.0)) { if (tid == 0) s_bad = 1; }
+      const double inv = rsqrt(p);
+      const double invr = inv * (1.5 - 0.5 * p * inv * inv);  // one Newton step on rsqrt -> full FP64 accuracy
+      for (int i = k + 1 + tid; i < n; i += SCHUR_BLOCK) {
+        const double v = A[i * ld + k];
+        if (v != 0.0) {
+          A[i * ld + k] = v * invr;
+          s_list[atomicAdd(&s_cnt, 1)] = i;
+        }
+      }
+      if (tid == 0) s_diag[k] = p * invr;  // sqrt(p)
+      __syncthreads();
+      const int m = s_cnt;
+      for (int q = tid; q < m * m; q += SCHUR_BLOCK) {
+        const int ii = q / m, jj = q - ii * m;
+        const int i = s_list[ii], j = s_list[jj];
+        if (i >= j) A[i * ld + j] -= A[i * ld + k] * A[j * ld + k];
+      }
+      __syncthreads();
+      if (tid == 0) s_cnt = 0;
+    }
+    __syncthreads();
+    const bool bad = s_bad != 0;
+    // ---- S = trailing block (lower triangle mirrored), row-major [nB][nB]
+    double* Sc = S + c * (int64_t)nB * nB;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int q = tid; q < nB * nB; q += SCHUR_BLOCK) {
+      const int bi = q / nB, bj = q - bi * nB;
+      const int hi = bi > bj ? bi : bj, lo = bi > bj ? bj : bi;
+      Sc[q] = bad ? qnan : A[(nI + hi) * ld + nI + lo];
+    }
+    if (dS == nullptr || n_grad <= 0) continue;
+    // ---- sensitivities: dS_g = E^T dK_g E with E = [-X; I], X = K_II^-1 K_IB.
+    // rows nI.. of A hold Y^T = K_BI L^-T; back-substitute in place to X^T = Y^T L^-1.
+    __syncthreads();
+    for (int b = tid; b < nB; b += SCHUR_BLOCK) {
+      double* row = A + (size_t)(nI + b) * ld;
+      for (int k = nI - 1; k >= 0; --k) {
+        double v = row[k];
+        for (int i = k + 1; i < nI; ++i) v -= A[i * ld + k] * row[i];
+        row[k] = v / s_diag[k];
+      }
+    }
+    __syncthreads();
+    for (int gsel = 0; gsel < n_grad; ++gsel) {
+      double acc[GRAD_PER_THREAD];
+#pragma unroll
+      for (int u = 0; u < GRAD_PER_THREAD; ++u) acc[u] = 0.0;
+      for (int e = 0; e < ne; ++e) {
+        if (elem_group[e] != gsel) continue;  // uniform across the CTA
+        const int a = s_e0[e], b = s_e1[e];
+        if (tid == 0) {
+          double L;
+          strain_vectors_dev(cx + a * 3, cx + b * 3, s_B, &L);
+          const double r = cr[e];
+          const double PI = 3.14159265358979323846, G = young / (2.0 * (1.0 + nu));
+          const double dSr = 2.0 * PI * r, dIr = PI * r * r * r, ch = drad_chain ? drad_chain[e] : 1.0;
+          const double wES = young * dSr, wGS = G * kappa * dSr, wGJ = G * 2.0 * dIr, wEI = young * dIr;
+          s_B[72] = ch * L * wES; s_B[73] = ch * L * wGS; s_B[74] = ch * L * wGS;
+          s_B[75] = ch * L * wGJ; s_B[76] = ch * L * wEI; s_B[77] = ch * L * wEI;
+        }
+        __syncthreads();
+        // v_i[b] = sum_d B_i[d] * E[dof_d][b]
+        const int pa = node_pos(a, nn, nbn) * 6, pb = node_pos(b, nn, nbn) * 6;
+        for (int w = tid; w < 6 * nB; w += SCHUR_BLOCK) {
+          const int i = w / nB, bb = w - i * nB;
+          double v = 0.0;
+#pragma unroll
+          for (int d = 0; d < 12; ++d) {
+            const int q = (d < 6 ? pa + d : pb + d - 6);
+            const double Eqb = (q < nI) ? -A[(size_t)(nI + bb) * ld + q] : ((q - nI == bb) ? 1.0 : 0.0);
+            v = fma(s_B[i * 12 + d], Eqb, v);
+          }
+          s_v[i * SCHUR_MAX_NB + bb] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < GRAD_PER_THREAD; ++u) {
+          const int q = tid + u * SCHUR_BLOCK;
+          if (q < nB * nB) {
+            const int b1 = q / nB, b2 = q - b1 * nB;
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) s = fma(s_B[72 + i] * s_v[i * SCHUR_MAX_NB + b1], s_v[i * SCHUR_MAX_NB + b2], s);
+            acc[u] += s;
+          }
+        }
+        __syncthreads();
+      }
+      double* dSc = dS + (c * (int64_t)n_grad + gsel) * (int64_t)nB * nB;
+#pragma unroll
+      for (int u = 0; u < GRAD_PER_THREAD; ++u) {
+        const int q = tid + u * SCHUR_BLOCK;
+        if (q < nB * nB) dSc[q] = bad ? qnan : acc[u];
+      }
+    }
+  }
+}
 
 extern "C" int lat_schur_batch(lat_ctx* ctx, const double* xyz, const int32_t* len0, const int32_t* len1,
                                const double* rad, int64_t n_cells, int32_t n_loc_nodes, int32_t n_bnd_nodes,
                                int32_t n_loc_elem, double young, double nu, double kappa, double* S,
                                const int32_t* elem_group, const double* drad_chain, int32_t n_grad, double* dS) {
   if (!ctx) return LAT_ERR_ARG;
-  return lat_fail(ctx, LAT_ERR_UNSUPPORTED, "lat_schur_batch not built yet", __FILE__, __LINE__);
+  LAT_CHECK_ARG(ctx, xyz && len0 && len1 && rad && S);
+  LAT_CHECK_ARG(ctx, n_cells >= 0 && n_loc_nodes > 0 && n_bnd_nodes > 0 && n_bnd_nodes <= n_loc_nodes && n_loc_elem > 0);
+  LAT_CHECK_ARG(ctx, 6 * n_bnd_nodes <= SCHUR_MAX_NB);
+  LAT_CHECK_ARG(ctx, dS == nullptr || (elem_group != nullptr && n_grad > 0));
+  if (n_cells == 0) return LAT_OK;
+  LAT_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int n = 6 * n_loc_nodes, ld = n | 1;
+  const size_t aux = (size_t)n_loc_elem * sizeof(ElemCoef) + (size_t)n * 8 + 6 * SCHUR_MAX_NB * 8 + 80 * 8 + (size_t)n * 4 +
+                     2 * (size_t)n_loc_elem * 4 + 64;
+  const size_t a_bytes = (size_t)n * ld * sizeof(double);
+  const bool in_smem = a_bytes + aux <= 220 * 1024;
+  const size_t smem = in_smem ? a_bytes + aux : aux;
+  if (smem > 220 * 1024) return lat_fail(ctx, LAT_ERR_UNSUPPORTED, "cell mesh too large for lat_schur_batch", __FILE__, __LINE__);
+  int per_sm = in_smem ? (int)((220 * 1024) / (smem + 1024)) : 2;
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 8) per_sm = 8;
+  int64_t grid = (int64_t)ctx->sm_count * per_sm;
+  if (grid > n_cells) grid = n_cells;
+  if (in_smem) {
+    LAT_CUDA(ctx, cudaFuncSetAttribute(k_schur_dense<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LAT_LAUNCH(ctx, k_schur_dense<true>, (unsigned)grid, SCHUR_BLOCK, smem, xyz, len0, len1, rad, n_cells, n_loc_nodes,
+               n_bnd_nodes, n_loc_elem, young, nu, kappa, S, nullptr, elem_group, drad_chain, n_grad, dS);
+  } else {
+    double* ws = lat_buf<double>(ctx, "schur_ws", (size_t)grid * n * ld);
+    if (!ws) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+    LAT_CUDA(ctx, cudaFuncSetAttribute(k_schur_dense<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LAT_LAUNCH(ctx, k_schur_dense<false>, (unsigned)grid, SCHUR_BLOCK, smem, xyz, len0, len1, rad, n_cells, n_loc_nodes,
+               n_bnd_nodes, n_loc_elem, young, nu, kappa, S, ws, elem_group, drad_chain, n_grad, dS);
+  }
+  return LAT_OK;
+}
+
+// ===========================================================================
+// A8: DDM interface operator  y = sum_c B_c S_c B_c^T x
+// ===========================================================================
+// One warp per cell.  The warp gathers the cell's boundary displacements (lane j holds
+// u_c[j], u_c[j+32], u_c[j+64]), streams S_c row by row with coalesced loads, reduces each
+// row product with shuffles, and scatter-adds the 6 n_bnd results into y with FP64 atomics.
+__global__ void __launch_bounds__(256) k_ddm_matvec(const double* __restrict__ S, int64_t s_stride,
+                                                    const int32_t* __restrict__ gidx, const double* __restrict__ u_fixed,
+                                                    int64_t n_cells, int nb, const double* __restrict__ x,
+                                                    double* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= n_cells) return;
+  const int32_t* gi = gidx + c * nb;
+  const double* Sc = S + c * s_stride;
+  double xr[3];
+  int gl[3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const int j = lane + 32 * q;
+    gl[q] = -2;
+    xr[q] = 0.0;
+    if (j < nb) {
+      gl[q] = gi[j];
+      xr[q] = gl[q] >= 0 ? x[gl[q]] : (u_fixed ? u_fixed[c * nb + j] : 0.0);
+    }
+  }
+  double yr[3] = {0.0, 0.0, 0.0};
+  for (int i = 0; i < nb; ++i) {
+    const double* row = Sc + (int64_t)i * nb;
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int j = lane + 32 * q;
+      if (j < nb) s = fma(row[j], xr[q], s);
+    }
+    s = warp_sum(s);
+    if (lane == (i & 31)) {
+      if (i < 32) yr[0] = s; else if (i < 64) yr[1] = s; else yr[2] = s;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 3; ++q)
+    if (gl[q] >= 0) atomicAdd(&y[gl[q]], yr[q]);
 }
 
 extern "C" int lat_ddm_matvec(lat_ctx* ctx, const double* S, int64_t s_stride, const int32_t* gidx,
                               const double* u_fixed, int64_t n_cells, int32_t nb, int64_t n_free,
                               const double* x, double* y) {
   if (!ctx) return LAT_ERR_ARG;
-  return lat_fail(ctx, LAT_ERR_UNSUPPORTED, "lat_ddm_matvec not built yet", __FILE__, __LINE__);
+  LAT_CHECK_ARG(ctx, S && gidx && x && y && n_cells >= 0 && nb > 0 && nb <= SCHUR_MAX_NB && n_free > 0);
+  LAT_CHECK_ARG(ctx, s_stride == 0 || s_stride >= (int64_t)nb * nb);
+  LAT_CUDA(ctx, cudaSetDevice(ctx->device));
+  LAT_CUDA(ctx, cudaMemsetAsync(y, 0, n_free * sizeof(double), ctx->stream));
+  if (n_cells == 0) return LAT_OK;
+  LAT_LAUNCH(ctx, k_ddm_matvec, (unsigned)ceil_div(n_cells, 8), 256, 0, S, s_stride, gidx, u_fixed, n_cells, nb, x, y);
+  return LAT_OK;
 }

@@ -243,3 +243,28 @@ class Context:
                                                 _ptr(chain), _ptr(group), en0.numel(), young, nu, kappa, _ptr(u),
                                                 _ptr(lam), n_groups, _ptr(g), _ptr(q)))
         return (g, q) if want_elem else g
+
+    def schur_batch(self, xyz, len0, len1, rad, n_bnd_nodes, young, nu, kappa=0.9, elem_group=None, chain=None,
+                    n_grad=0):
+        """xyz [n_cells, n_loc_nodes, 3], rad [n_cells, n_loc_elem] -> S [n_cells, nB, nB] (and dS)."""
+        import torch
+        n_cells, nn = int(xyz.shape[0]), int(xyz.shape[1])
+        ne = int(len0.numel())
+        nB = 6 * n_bnd_nodes
+        S = torch.empty((n_cells, nB, nB), dtype=torch.float64, device=self.device)
+        dS = torch.empty((n_cells, n_grad, nB, nB), dtype=torch.float64, device=self.device) if n_grad > 0 else None
+        self.check(self.lib.lat_schur_batch(self.h, _ptr(xyz), _ptr(len0), _ptr(len1), _ptr(rad), n_cells, nn,
+                                            n_bnd_nodes, ne, young, nu, kappa, _ptr(S), _ptr(elem_group), _ptr(chain),
+                                            n_grad, _ptr(dS)))
+        return (S, dS) if n_grad > 0 else S
+
+    def ddm_matvec(self, S, gidx, x, n_free=None, u_fixed=None, out=None):
+        """y = sum_c B_c S_c B_c^T x.  S: [n_cells, nb, nb] or [nb, nb] (shared by all cells)."""
+        import torch
+        n_cells, nb = int(gidx.shape[0]), int(gidx.shape[1])
+        stride = 0 if S.dim() == 2 else nb * nb
+        n_free = int(x.numel()) if n_free is None else n_free
+        y = out if out is not None else torch.empty(n_free, dtype=torch.float64, device=self.device)
+        self.check(self.lib.lat_ddm_matvec(self.h, _ptr(S), stride, _ptr(gidx), _ptr(u_fixed), n_cells, nb, n_free,
+                                           _ptr(x), _ptr(y)))
+        return y

@@ -1,0 +1,116 @@
+"""Per-cell Schur complements on the GPU: drop-in for
+``pyLatticeSim.utils_schur.get_schur_complement`` (utils_schur.py:22-53) and the
+batched form that feeds ``LatticeSim.calculate_schur_complement_cells``
+(lattice_sim.py:846-919) and the npz dataset schema (utils_schur.py:55-72).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import lib as L
+from .fem import KAPPA, material_constants
+from .mesh import BeamMesh, flatten_lattice, mesh_from_synthetic
+
+
+def local_cell_mesh(mesh: BeamMesh, boundary_nodes):
+    """Renumber a one-cell mesh for ``lat_schur_batch``: the boundary nodes first, in the given
+    order (``cell.node_in_order_simulation``), then the interior nodes with the strut-interior
+    (degree-2) nodes before the interior joints -- the order in which the partial Cholesky
+    produces the least fill.  Returns (perm_old_to_new, xyz_local[nn,3], len0, len1)."""
+    nn = mesh.n_nodes
+    boundary_nodes = np.asarray(boundary_nodes, dtype=np.int64)
+    is_b = np.zeros(nn, dtype=bool)
+    is_b[boundary_nodes] = True
+    deg = np.bincount(np.concatenate([mesh.en0, mesh.en1]), minlength=nn)
+    interior = np.flatnonzero(~is_b)
+    chain = interior[(interior >= mesh.n_points)]          # strut-interior nodes, already beam-major
+    joints = interior[(interior < mesh.n_points)]
+    joints = joints[np.argsort(deg[joints], kind="stable")]
+    order = np.concatenate([boundary_nodes, chain, joints])
+    perm = np.empty(nn, dtype=np.int64)
+    perm[order] = np.arange(nn)
+    xyz = mesh.xyz[order]
+    return perm, xyz, perm[mesh.en0].astype(np.int32), perm[mesh.en1].astype(np.int32)
+
+
+def get_schur_complement(lattice, cell_index=None, elements_per_strut="gmsh", ctx=None):
+    """Drop-in for ``get_schur_complement(lattice, cell_index) -> ndarray[nB, nB]`` (C order;
+    boundary DOF order = 6 DOFs of each node of ``cell.node_in_order_simulation``)."""
+    import torch
+    if cell_index is None and lattice.get_number_cells() > 1:
+        raise ValueError("The lattice must contain only one cell for Schur complement calculation or specify a "
+                         "cell_index.")                       # utils_schur.py:35-36
+    cell = lattice.cells[0] if cell_index is None else lattice.cells[cell_index]
+    cell.define_node_order_to_simulate()                      # utils_schur.py:39
+    mesh = flatten_lattice(lattice, cell.index, elements_per_strut)
+    loc = {int(i): k for k, i in enumerate(mesh.point_index)}
+    bnd = np.array([loc[p.index] for p in cell.node_in_order_simulation], dtype=np.int64)
+    E, nu = material_constants(lattice)
+    ctx = ctx or L.Context()
+    perm, xyz, l0, l1 = local_cell_mesh(mesh, bnd)
+    dev = ctx.device
+    S = ctx.schur_batch(torch.from_numpy(xyz[None]).to(dev), torch.from_numpy(l0).to(dev), torch.from_numpy(l1).to(dev),
+                        torch.from_numpy(mesh.rad[None].copy()).to(dev), len(bnd), E, nu, KAPPA)
+    out = S[0].cpu().numpy()
+    if not np.isfinite(out).all():
+        raise RuntimeError("Schur complement: interior stiffness block is not positive definite")
+    return out
+
+
+class CellBatch:
+    """Topology shared by a batch of cells + per-cell coordinates/radii resident on the GPU."""
+
+    def __init__(self, ctx, xyz, len0, len1, rad, n_bnd_nodes, young, nu, kappa=KAPPA, elem_group=None, chain=None,
+                 n_grad=0):
+        import torch
+        self.ctx = ctx
+        dev = ctx.device
+        t = lambda a, d: torch.from_numpy(np.ascontiguousarray(a, dtype=d)).to(dev)
+        self.xyz, self.len0, self.len1, self.rad = t(xyz, np.float64), t(len0, np.int32), t(len1, np.int32), t(rad, np.float64)
+        self.n_bnd_nodes = int(n_bnd_nodes)
+        self.young, self.nu, self.kappa = young, nu, kappa
+        self.elem_group = None if elem_group is None else t(elem_group, np.int32)
+        self.chain = None if chain is None else t(chain, np.float64)
+        self.n_grad = int(n_grad)
+
+    def schur(self, with_gradients=False):
+        if with_gradients:
+            return self.ctx.schur_batch(self.xyz, self.len0, self.len1, self.rad, self.n_bnd_nodes, self.young, self.nu,
+                                        self.kappa, self.elem_group, self.chain, self.n_grad)
+        return self.ctx.schur_batch(self.xyz, self.len0, self.len1, self.rad, self.n_bnd_nodes, self.young, self.nu,
+                                    self.kappa)
+
+
+def bcc_cell_order_nodes(pxyz, box):
+    """``Cell.define_node_order_to_simulate`` (cell.py:611-680) for arrays: nodes on the cell box, each
+    assigned to the first face of (Xmin, Xmax, Ymin, Ymax, Zmin, Zmax) it lies on, sorted in-plane."""
+    x0, x1, y0, y1, z0, z1 = box
+    tol = 1e-9
+    faces = [np.abs(pxyz[:, 0] - x0) <= tol, np.abs(pxyz[:, 0] - x1) <= tol, np.abs(pxyz[:, 1] - y0) <= tol,
+             np.abs(pxyz[:, 1] - y1) <= tol, np.abs(pxyz[:, 2] - z0) <= tol, np.abs(pxyz[:, 2] - z1) <= tol]
+    taken = np.zeros(pxyz.shape[0], dtype=bool)
+    order = []
+    keys = [(1, 2, 0), (1, 2, 0), (0, 2, 1), (0, 2, 1), (0, 1, 2), (0, 1, 2)]
+    for f, key in zip(faces, keys):
+        idx = np.flatnonzero(f & ~taken)
+        taken[idx] = True
+        srt = np.lexsort((pxyz[idx, key[2]], pxyz[idx, key[1]], pxyz[idx, key[0]]))
+        order.extend(idx[srt].tolist())
+    return np.array(order, dtype=np.int64)
+
+
+def synthetic_cell_batch(ctx, geom, radii, elements_per_strut, young, nu, cell_size=1.0, with_gradients=False):
+    """One unit cell of ``geom`` per entry of ``radii`` (shape [n_cells]) -- BASELINE config 4."""
+    from .mesh import synthetic_lattice
+    lat = synthetic_lattice(geom, (1, 1, 1), [1.0], cell_size=(cell_size,) * 3)
+    mesh = mesh_from_synthetic(lat, elements_per_strut)
+    bnd = bcc_cell_order_nodes(lat.pxyz, (0, cell_size, 0, cell_size, 0, cell_size))
+    perm, xyz, l0, l1 = local_cell_mesh(mesh, bnd)
+    radii = np.asarray(radii, dtype=np.float64)
+    n_cells = radii.shape[0]
+    xyz_b = np.broadcast_to(xyz[None], (n_cells,) + xyz.shape).copy()
+    rad_b = np.repeat(radii[:, None], mesh.n_elems, axis=1)
+    grp = np.zeros(mesh.n_elems, dtype=np.int32) if with_gradients else None
+    ch = np.ones(mesh.n_elems) if with_gradients else None
+    return CellBatch(ctx, xyz_b, l0, l1, rad_b, len(bnd), young, nu, elem_group=grp, chain=ch,
+                     n_grad=1 if with_gradients else 0), bnd

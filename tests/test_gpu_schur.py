@@ -1,0 +1,87 @@
+"""GPU: batched per-cell Schur complements and the DDM interface operator."""
+import numpy as np
+import pytest
+
+from conftest import E_MOD, NU, load_golden, mesh_from_npz
+from oracle import lattice_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def t(ctx, a, d):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=d)).to(ctx.device)
+
+
+@pytest.mark.parametrize("geom,tol", [("BCC", 1e-11), ("Hybrid1", 1e-11), ("Hybrid4", 1e-11)])
+def test_schur_batch_reproduces_reference_goldens(ctx, geom, tol):
+    """The 30 Schur matrices stored by the reference (dolfinx/PETSc) through lat_schur_batch."""
+    from pylatticedso_b200.schur import local_cell_mesh
+    G = load_golden(f"schur_{geom}.npz")
+    SM = G["schur_matrices"]
+    for i in range(SM.shape[0]):
+        m = mesh_from_npz(G, f"c{i}_")
+        bnd_nodes = G[f"c{i}_bnd"][::6] // 6
+        perm, xyz, l0, l1 = local_cell_mesh(m, bnd_nodes)
+        S = ctx.schur_batch(t(ctx, xyz[None], np.float64), t(ctx, l0, np.int32), t(ctx, l1, np.int32),
+                            t(ctx, m.rad[None], np.float64), len(bnd_nodes), E_MOD, NU)[0].cpu().numpy()
+        err = np.abs(S - SM[i]).max() / np.abs(SM[i]).max()
+        assert err < tol, (geom, i, err)
+        assert np.array_equal(S, S.T)
+
+
+def test_schur_batch_many_cells_and_gradients(ctx):
+    """Config-4 style batch: one BCC cell per radius, n_I = 6 (m=1) and n_I = 102-like (m=3) meshes,
+    against the oracle; analytic dS/dr against a central difference of the oracle."""
+    from pylatticedso_b200.schur import synthetic_cell_batch
+    from pylatticedso_b200 import mesh as M
+    rng = np.random.default_rng(44)
+    radii = 0.02 + 0.06 * rng.random(300)
+    for m_ in (1, 3):
+        batch, bnd = synthetic_cell_batch(ctx, "BCC", radii, m_, E_MOD, NU, with_gradients=True)
+        S, dS = batch.schur(with_gradients=True)
+        S, dS = S.cpu().numpy(), dS.cpu().numpy()
+        lat = M.synthetic_lattice("BCC", (1, 1, 1), [1.0])
+        mesh = M.mesh_from_synthetic(lat, m_)
+        en = np.stack([mesh.en0, mesh.en1], 1)
+        bd = (bnd[:, None] * 6 + np.arange(6)[None, :]).ravel()
+        for c in (0, 17, 299):
+            f = lambda r: orc.schur_complement(orc.assemble_csr(mesh.xyz, en, np.full(mesh.n_elems, r), E_MOD, NU), bd)
+            So = f(radii[c])
+            assert np.abs(S[c] - So).max() < 1e-11 * np.abs(So).max()
+            h = 1e-6
+            fd = (f(radii[c] + h) - f(radii[c] - h)) / (2 * h)
+            assert np.abs(dS[c, 0] - fd).max() < 1e-6 * np.abs(fd).max()
+        # S is symmetric positive semi-definite with exactly the 6 rigid-body modes in its null space
+        w = np.linalg.eigvalsh(S[5])
+        assert w.min() > -1e-9 * w.max() and (np.abs(w) < 1e-9 * w.max()).sum() == 6
+
+
+def test_ddm_matvec_matches_assembled_interface_operator(ctx):
+    """y = sum_c B_c S_c B_c^T x against a dense numpy restatement of lattice_sim.py:1180-1252."""
+    rng = np.random.default_rng(3)
+    n_cells, nb, n_free = 50, 48, 400
+    S = rng.standard_normal((n_cells, nb, nb)); S = S + S.transpose(0, 2, 1)
+    gidx = np.full((n_cells, nb), -1, dtype=np.int32)
+    for c in range(n_cells):
+        pick = rng.choice(n_free, size=40, replace=False)
+        gidx[c, rng.choice(nb, size=40, replace=False)] = pick
+    x = rng.standard_normal(n_free)
+    ufix = rng.standard_normal((n_cells, nb)) * (gidx < 0)
+    for uf in (None, ufix):
+        y = ctx.ddm_matvec(t(ctx, S, np.float64), t(ctx, gidx, np.int32), t(ctx, x, np.float64), n_free,
+                           None if uf is None else t(ctx, uf, np.float64)).cpu().numpy()
+        ref = np.zeros(n_free)
+        for c in range(n_cells):
+            u = np.where(gidx[c] >= 0, x[np.maximum(gidx[c], 0)], 0.0 if uf is None else uf[c])
+            r = S[c] @ u
+            np.add.at(ref, gidx[c][gidx[c] >= 0], r[gidx[c] >= 0])
+        assert np.abs(y - ref).max() < 1e-12 * np.abs(ref).max()
+    # shared S for all cells (uniform lattice: one cached Schur matrix, lattice_sim.py:857-883)
+    y = ctx.ddm_matvec(t(ctx, S[0], np.float64), t(ctx, gidx, np.int32), t(ctx, x, np.float64), n_free).cpu().numpy()
+    ref = np.zeros(n_free)
+    for c in range(n_cells):
+        u = np.where(gidx[c] >= 0, x[np.maximum(gidx[c], 0)], 0.0)
+        r = S[0] @ u
+        np.add.at(ref, gidx[c][gidx[c] >= 0], r[gidx[c] >= 0])
+    assert np.abs(y - ref).max() < 1e-12 * np.abs(ref).max()
