@@ -199,108 +199,141 @@ def run_b200(args):
     hbm_peak, peak_src = measured_peaks()
 
     distributed = world > 1
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    lat, mesh, fixed, g, f = build_workload(world)
+    n_dof_global, n_elem_global = mesh.n_dof, mesh.n_elems
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # > 126 MB L2
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
     if distributed:
         from pylatticedso_b200 import distributed as D
-        prob = D.build_slab_problem(ctx, rank, world, cells_per_rank=20)
-        n_dof_global, n_elem_global = prob.n_dof_global, prob.n_elem_global
-    else:
-        lat, mesh, fixed, g, f = build_workload(1)
-        n_dof_global, n_elem_global = mesh.n_dof, mesh.n_elems
+        ctx.comm_create(rank, world)
+        dfem = D.DistributedFEM(ctx, mesh, E_MOD, NU, rank, world, KAPPA)
+        dfem.set_bc(fixed, g, f)
+        lm = dfem.lmesh
+        host = {k: pin(v) for k, v in dict(x=lm.x, y=lm.y, z=lm.z, en0=lm.en0, en1=lm.en1, rad=lm.rad,
+                                           fixed=fixed[dfem.dofs], g=g[dfem.dofs], f=f[dfem.dofs]).items()}
+        vals = torch.empty(dfem.nnzb * 36, dtype=torch.float64, device=dev)
+        vals_bc = torch.empty_like(vals)
+        b_d = torch.empty(6 * dfem.n_local, dtype=torch.float64, device=dev)
+        u_d = torch.empty_like(b_d)
+        n_nodes, nnzb = dfem.n_owned, dfem.nnzb_owned
 
-    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-    if not distributed:
+        def step(profile):
+            e = [ev() for _ in range(2)]
+            e[0].record()
+            dfem.assemble(out=vals)
+            e[1].record()
+            u, R, info = dfem.solve(tol=1e-8, maxiter=200000, precond=L.PC_BLOCK6, vals_bc=vals_bc, b=b_d, u=u_d)
+            e.append(ev()); e[2].record()
+            return [e[0], e[1], e[1], e[2]], info, (u, R)
+
+        dev_targets = (("x", dfem.x), ("y", dfem.y), ("z", dfem.z), ("en0", dfem.en0), ("en1", dfem.en1),
+                       ("rad", dfem.rad), ("fixed", dfem.fixed_d), ("g", dfem.g_d), ("f", dfem.f_d))
+        n_out = 6 * dfem.n_local
+        pattern_ms = None
+    else:
         host = {k: pin(v) for k, v in dict(x=mesh.x, y=mesh.y, z=mesh.z, en0=mesh.en0, en1=mesh.en1, rad=mesh.rad,
                                            fixed=fixed, g=g, f=f).items()}
         fem = BeamFEM(mesh, E_MOD, NU, KAPPA, ctx=ctx)
-        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0 = ev(); t1 = ev()
         t0.record(); fem.build_pattern(); t1.record(); torch.cuda.synchronize()
         pattern_ms = t0.elapsed_time(t1)
         fixed_d, g_d, f_d = (host[k].to(dev) for k in ("fixed", "g", "f"))
         vals = torch.empty(fem.nnzb * 36, dtype=torch.float64, device=dev)
         vals_bc = torch.empty_like(vals)
         n_nodes, nnzb = fem.n_nodes, fem.nnzb
-    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # > 126 MB L2
-
-    def ev():
-        return torch.cuda.Event(enable_timing=True)
-
-    def step(profile):
-        """One pass of the hot path with device-resident inputs. Returns per-phase events + PCG info."""
-        e = [ev() for _ in range(4)]
-        e[0].record()
-        ctx.assemble_bsr(fem.x, fem.y, fem.z, fem.en0, fem.en1, fem.rad, n_nodes, nnzb, E_MOD, NU, KAPPA, out=vals)
-        e[1].record()
-        ctx.check(ctx.lib.lat_apply_dirichlet(ctx.h, L._ptr(fem.rowptr), L._ptr(fem.colidx), n_nodes, L._ptr(vals),
-                                              L._ptr(fixed_d), L._ptr(g_d), L._ptr(f_d), L._ptr(vals_bc), L._ptr(b_d)))
-        e[2].record()
-        u, info = ctx.pcg(fem.rowptr, fem.colidx, vals_bc, b_d, x=u_d, tol=1e-8, maxiter=200000,
-                          precond=L.PC_BLOCK6, profile_iters=profile)
-        ctx.set_dirichlet_values(fixed_d, g_d, u)
-        ctx.spmv(fem.rowptr, fem.colidx, vals, u, out=R_d)
-        e[3].record()
-        return e, info
-
-    if distributed:
-        res = D.bench_steps(prob, args, flush)
-    else:
         b_d = torch.empty(fem.n_dof, dtype=torch.float64, device=dev)
         u_d = torch.empty_like(b_d)
         R_d = torch.empty_like(b_d)
-        for _ in range(args.warmup):
-            step(0)
+
+        def step(profile):
+            """One pass of the hot path with device-resident inputs. Returns per-phase events + PCG info."""
+            e = [ev() for _ in range(4)]
+            e[0].record()
+            ctx.assemble_bsr(fem.x, fem.y, fem.z, fem.en0, fem.en1, fem.rad, n_nodes, nnzb, E_MOD, NU, KAPPA, out=vals)
+            e[1].record()
+            ctx.check(ctx.lib.lat_apply_dirichlet(ctx.h, L._ptr(fem.rowptr), L._ptr(fem.colidx), n_nodes, L._ptr(vals),
+                                                  L._ptr(fixed_d), L._ptr(g_d), L._ptr(f_d), L._ptr(vals_bc), L._ptr(b_d)))
+            e[2].record()
+            u, info = ctx.pcg(fem.rowptr, fem.colidx, vals_bc, b_d, x=u_d, tol=1e-8, maxiter=200000,
+                              precond=L.PC_BLOCK6, profile_iters=profile)
+            ctx.set_dirichlet_values(fixed_d, g_d, u)
+            ctx.spmv(fem.rowptr, fem.colidx, vals, u, out=R_d)
+            e[3].record()
+            return e, info, (u_d, R_d)
+
+        dev_targets = (("x", fem.x), ("y", fem.y), ("z", fem.z), ("en0", fem.en0), ("en1", fem.en1), ("rad", fem.rad),
+                       ("fixed", fixed_d), ("g", g_d), ("f", f_d))
+        n_out = fem.n_dof
+
+    def barrier():
         torch.cuda.synchronize()
-        sampler = ClockSampler(local)
-        sampler.start()
-        launches0 = ctx.launches
-        tot_ms = asm_ms = solve_ms = 0.0
-        iters = 0
-        spmv_ms, upd_ms, nprof = [], [], 0
-        for _ in range(args.steps):
-            flush.fill_(1.0)            # evict the previous step's matrix from L2 (untimed)
+        if distributed:
+            dist.barrier()
             torch.cuda.synchronize()
-            e, info = step(64)
-            torch.cuda.synchronize()
-            tot_ms += e[0].elapsed_time(e[3])
-            asm_ms += e[0].elapsed_time(e[1])
-            solve_ms += info["solve_ms"]
-            iters += info["iters"]
-            assert info["info"] == 0, f"PCG did not converge: {info}"
-            spmv_ms.append(info["spmv_ms"]); upd_ms.append(info["update_ms"]); nprof += info["profiled"]
-        launches = ctx.launches - launches0
-        clocks = sampler.stop()
-        # ---- end-to-end through the host-facing API: pinned host buffers -> H2D -> step -> D2H
-        h2d = sum(t.numel() * t.element_size() for t in host.values())
-        u_host = torch.empty(fem.n_dof, dtype=torch.float64).pin_memory()
-        R_host = torch.empty(fem.n_dof, dtype=torch.float64).pin_memory()
-        d2h = 2 * fem.n_dof * 8
-        e2e_ms, e2e_iters = 0.0, 0
-        for s in range(1 + args.steps):
-            flush.fill_(1.0)
-            torch.cuda.synchronize()
-            a, b_ = ev(), ev()
-            a.record()
-            for k, dst in (("x", fem.x), ("y", fem.y), ("z", fem.z), ("en0", fem.en0), ("en1", fem.en1), ("rad", fem.rad),
-                           ("fixed", fixed_d), ("g", g_d), ("f", f_d)):
-                dst.copy_(host[k], non_blocking=True)
-            _, info = step(0)
-            u_host.copy_(u_d, non_blocking=True)
-            R_host.copy_(R_d, non_blocking=True)
-            b_.record()
-            torch.cuda.synchronize()
-            if s >= 1:
-                e2e_ms += a.elapsed_time(b_)
-                e2e_iters += info["iters"]
-        res = dict(tot_ms=tot_ms, asm_ms=asm_ms, solve_ms=solve_ms, iters=iters, launches=launches, clocks=clocks,
-                   spmv_ms=float(np.mean(spmv_ms)), update_ms=float(np.mean(upd_ms)), nprof=nprof,
-                   e2e_ms=e2e_ms, e2e_iters=e2e_iters, h2d=h2d, d2h=d2h, pattern_ms=pattern_ms,
-                   n_nodes=n_nodes, nnzb=nnzb)
+
+    for _ in range(args.warmup):
+        step(0)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ctx.launches
+    tot_ms = asm_ms = solve_ms = 0.0
+    iters = 0
+    spmv_ms, upd_ms, nprof = [], [], 0
+    for _ in range(args.steps):
+        flush.fill_(1.0)            # evict the previous step's matrix from L2 (untimed)
+        barrier()
+        e, info, _ = step(64)
+        barrier()
+        tot_ms += e[0].elapsed_time(e[3])
+        asm_ms += e[0].elapsed_time(e[1])
+        solve_ms += info["solve_ms"]
+        iters += info["iters"]
+        assert info["info"] == 0, f"PCG did not converge: {info}"
+        spmv_ms.append(info.get("spmv_ms", 0.0)); upd_ms.append(info.get("update_ms", 0.0)); nprof += info.get("profiled", 0)
+    launches = ctx.launches - launches0
+    clocks = sampler.stop()
+    # ---- end-to-end through the host-facing API: pinned host buffers -> H2D -> step -> D2H
+    h2d = sum(t.numel() * t.element_size() for t in host.values())
+    u_host = torch.empty(n_out, dtype=torch.float64).pin_memory()
+    R_host = torch.empty(n_out, dtype=torch.float64).pin_memory()
+    d2h = 2 * n_out * 8
+    e2e_ms, e2e_iters = 0.0, 0
+    for s_ in range(1 + args.steps):
+        flush.fill_(1.0)
+        barrier()
+        a, b_ = ev(), ev()
+        a.record()
+        for k, dst in dev_targets:
+            dst.copy_(host[k], non_blocking=True)
+        _, info, (uu, RR) = step(0)
+        u_host.copy_(uu, non_blocking=True)
+        R_host.copy_(RR, non_blocking=True)
+        b_.record()
+        barrier()
+        if s_ >= 1:
+            e2e_ms += a.elapsed_time(b_)
+            e2e_iters += info["iters"]
+    res = dict(tot_ms=tot_ms, asm_ms=asm_ms, solve_ms=solve_ms, iters=iters, launches=launches, clocks=clocks,
+               spmv_ms=float(np.mean(spmv_ms)), update_ms=float(np.mean(upd_ms)), nprof=nprof,
+               e2e_ms=e2e_ms, e2e_iters=e2e_iters, h2d=h2d, d2h=d2h, pattern_ms=pattern_ms,
+               n_nodes=n_nodes, nnzb=nnzb)
 
     # max over ranks of the timed region
     tot_ms = res["tot_ms"]
     if world > 1:
-        t = torch.tensor([res["tot_ms"], res["e2e_ms"]], dtype=torch.float64, device=dev)
+        t = torch.tensor([res["tot_ms"], res["e2e_ms"], res["asm_ms"], res["solve_ms"]], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        tot_ms, res["e2e_ms"] = float(t[0]), float(t[1])
+        tot_ms, res["e2e_ms"], res["asm_ms"], res["solve_ms"] = (float(v) for v in t)
+        t2 = torch.tensor([res["h2d"], res["d2h"], res["launches"], res["n_nodes"], res["nnzb"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(t2, op=dist.ReduceOp.SUM)
+        res["h2d"], res["d2h"], res["launches"] = int(t2[0]), int(t2[1]), int(t2[2])
+        res["n_nodes_all"], res["nnzb_all"] = int(t2[3]), int(t2[4])
+        ctx.comm_destroy()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -309,8 +342,12 @@ def run_b200(args):
     value = n_dof_global * res["iters"] / (tot_ms * 1e-3)
     e2e_val = n_dof_global * res["e2e_iters"] / (res["e2e_ms"] * 1e-3)
     nn, nz = res["n_nodes"], res["nnzb"]
-    ach = spmv_bytes(nn, nz) / (res["spmv_ms"] * 1e-3) / 1e9
-    it_bytes = iteration_bytes(nn, nz, True)
+    if world == 1:
+        ach = spmv_bytes(nn, nz) / (res["spmv_ms"] * 1e-3) / 1e9
+        it_bytes = iteration_bytes(nn, nz, True)
+    else:
+        ach = None
+        it_bytes = iteration_bytes(res["n_nodes_all"], res["nnzb_all"], True)
     it_gbs = it_bytes * res["iters"] / (res["solve_ms"] * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -326,11 +363,12 @@ def run_b200(args):
                      "ms": res["asm_ms"] / args.steps, "mode": "gather (deterministic, fused element generation)",
                      "pattern_build_ms_one_off": res.get("pattern_ms")},
         "pcg": {"solve_ms_per_step": res["solve_ms"] / args.steps, "iteration_GBps_survey_bytes": it_gbs,
-                "iteration_frac_of_hbm": it_gbs / hbm_peak, "update_kernel_ms": res["update_ms"]},
+                "iteration_frac_of_hbm": it_gbs / (hbm_peak * world), "update_kernel_ms": res["update_ms"]},
         "roofline": {"kernel": "k_pcg_spmv (fused p = z + beta p, BSR 6x6 SpMV, p.Ap, p.p)", "bound": "hbm",
-                     "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                     "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": (ach / hbm_peak) if ach else None, "traffic": None,
                      "peak_source": peak_src, "bytes_per_launch": spmv_bytes(nn, nz),
-                     "avg_launch_ms": res["spmv_ms"], "launches_timed": res["nprof"]},
+                     "avg_launch_ms": res["spmv_ms"], "launches_timed": res["nprof"],
+                     "note": None if world == 1 else "per-kernel timing is taken at N=1 only; see pcg.iteration_frac_of_hbm"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": res["h2d"], "d2h_bytes_per_step": res["d2h"],
                 "ms_per_step": res["e2e_ms"] / args.steps},
         "gpu_launches": res["launches"],

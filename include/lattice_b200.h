@@ -162,6 +162,34 @@ int lat_pcg_bsr(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, cons
                 int64_t n_nodes, const double* b, double* x, const lat_pcg_opts* opts,
                 lat_pcg_result* result);
 
+/* ---- (e) multi-GPU: slab partition, NCCL over NVLink ---------------------------------------
+ * The reference is single-process (MPI.COMM_SELF, utils_simulation.py:39); this is the new exchange
+ * step of the sharded PCG.  One process per GPU.  Each rank holds the block rows of the nodes it
+ * OWNS (n_owned, complete rows) over a local column space [owned nodes | ghost nodes]; ghost nodes are
+ * ordered by owner rank (the order of `peer`), then by global node id, so a received halo lands
+ * contiguously.  Per PCG iteration: one halo exchange of z (ncclSend/ncclRecv with the <= 2 slab
+ * neighbours) and two all-reduces of 2 and 4 doubles (p.Ap, p.p | r.z, r.r, x.x, restart norm). */
+typedef struct {
+  int32_t n_neighbors;
+  int32_t pad;
+  const int32_t* peer;       /* HOST  [n_neighbors] ranks */
+  const int32_t* send_count; /* HOST  [n_neighbors] owned nodes sent to each peer */
+  const int32_t* recv_count; /* HOST  [n_neighbors] ghost nodes received from each peer */
+  const int32_t* send_idx;   /* DEVICE int32[sum send_count] local ids of the owned nodes to send, peer-major */
+  int64_t n_owned, n_local;  /* nodes */
+} lat_halo;
+
+/* rank 0 creates the 128-byte NCCL id; the host layer broadcasts it (torch.distributed / MPI / file) */
+int lat_nccl_unique_id(void* id128);
+int lat_comm_create(lat_ctx* ctx, const void* id128, int nranks, int rank); /* collective */
+int lat_comm_destroy(lat_ctx* ctx);
+int lat_allreduce_sum(lat_ctx* ctx, double* buf, int64_t n);               /* in place, on the ctx stream */
+int lat_halo_exchange(lat_ctx* ctx, const lat_halo* halo, double* vec);     /* vec: [6 n_local] */
+/* b: [6 n_owned] (at least), x: [6 n_local] (ghost part is NOT updated: call lat_halo_exchange) [syncs] */
+int lat_pcg_bsr_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, const double* vals,
+                     const lat_halo* halo, const double* b, double* x, const lat_pcg_opts* opts,
+                     lat_pcg_result* result);
+
 /* ---- A11: compliance sensitivity ----------------------------------------------
  * g[group[e]] -= chain_e * u_e^T (dK_e/dr)(r_e) u_e   (LatticeOpti.calculate_gradient
  * compliance branch, lattice_opti.py:746-841, sign of :719 included; element form

@@ -18,6 +18,7 @@ struct PcgScalars {
   double rz_old, pAp, pp, rr, xx, bb, beta, alpha_last;
   int32_t done, info_flag2, iters, breakdown;
   unsigned int counter[4];  // last-block-done tickets (one per kernel family)
+  double sums[4];           // local partial sums awaiting the all-reduce (multi-GPU path)
 };
 
 struct lat_ctx {
@@ -33,6 +34,9 @@ struct lat_ctx {
   PcgScalars* h_scal = nullptr;  // 2 slots
   int64_t* h_i64 = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  // multi-GPU
+  void* nccl_comm = nullptr;
+  int nranks = 1, rank = 0;
 };
 
 int lat_fail(lat_ctx* ctx, int code, const char* what, const char* file, int line);

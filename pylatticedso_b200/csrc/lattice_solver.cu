@@ -5,6 +5,8 @@
 // idle).  DOF index 6*node + r is therefore consecutive across lanes 0..29, so
 // all vector traffic is coalesced, and the 6 lanes of a group read one 288 B
 // block of the matrix as 6 x 48 B (three 16 B loads per lane).
+#include <cstdio>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -141,7 +143,67 @@ struct PcgParams {
   double tol, mintol, alpha_max;
   int64_t restart_every;
   int32_t maxiter, reference;
+  int32_t dist, pad;  // dist = 1: kernels only store LOCAL sums; the host all-reduces and runs k_pcg_finalize_*
 };
+
+// Stop tests, beta and bookkeeping of one iteration from the GLOBAL sums (single thread).
+__device__ __forceinline__ void pcg_finish_iteration(PcgScalars* sc, const PcgParams& prm, double rz_new, double rr,
+                                                     double xx, double pnorm) {
+  const int k = sc->iters;
+  const double pAp = sc->pAp;
+  double alpha = sc->rz_old / pAp;
+  if (prm.reference && prm.alpha_max > 0.0) alpha = fmin(alpha, prm.alpha_max);
+  const bool restart = prm.reference && prm.restart_every > 0 && k > 0 && (k % prm.restart_every) == 0;
+  const double pp = restart ? pnorm : sc->pp;
+  sc->rr = rr;
+  sc->xx = xx;
+  sc->alpha_last = alpha;
+  sc->iters = k + 1;
+  int done = 0;
+  if (prm.reference) {
+    // :97  residual_norm <= tol * norm_b      :102  direction_norm < mintol * (solution_norm + 1e-12)
+    if (sqrt(rr) <= prm.tol * sqrt(sc->bb)) done = 1;
+    else if (prm.mintol > 0.0 && sqrt(pp) < prm.mintol * (sqrt(xx) + 1e-12)) done = 1;
+    else if (alpha < 1e-6) sc->info_flag2 = 1;  // :107-109
+  } else {
+    if (rr <= prm.tol * prm.tol * sc->bb) done = 1;
+    else if (!(pAp > 0.0) || !(rr == rr)) { done = 1; sc->breakdown = 1; }
+  }
+  sc->beta = rz_new / sc->rz_old;
+  sc->rz_old = rz_new;
+  if (done) sc->done = 1;
+}
+
+__device__ __forceinline__ void pcg_finish_init(PcgScalars* sc, double rz, double bb) {
+  sc->rz_old = rz;
+  sc->bb = bb;
+  sc->rr = bb;
+  sc->beta = 0.0;
+  sc->pAp = 0.0; sc->pp = 0.0; sc->xx = 0.0; sc->alpha_last = 0.0;
+  sc->iters = 0; sc->info_flag2 = 0; sc->breakdown = 0;
+  sc->done = (bb == 0.0) ? 1 : 0;   // b == 0 -> x = 0
+}
+
+__global__ void k_pcg_finalize_init(PcgScalars* sc) { pcg_finish_init(sc, sc->sums[0], sc->sums[1]); }
+__global__ void k_pcg_finalize_update(PcgScalars* sc, PcgParams prm) {
+  if (sc->done || sc->iters >= prm.maxiter) return;
+  pcg_finish_iteration(sc, prm, sc->sums[0], sc->sums[1], sc->sums[2], sc->sums[3]);
+}
+// ghost entries of the search direction: p_new = z + beta p_old on [first, last)
+__global__ void k_pcg_ghost_p(int64_t first, int64_t last, const double* __restrict__ z, double* __restrict__ pa,
+                              double* __restrict__ pb, const PcgScalars* __restrict__ sc, PcgParams prm) {
+  if (sc->done || sc->iters >= prm.maxiter) return;
+  const int k = sc->iters;
+  const double beta = sc->beta;
+  const double* p_old = (k & 1) ? pb : pa;
+  double* p_new = (k & 1) ? pa : pb;
+  const int64_t i = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < last) p_new[i] = fma(beta, p_old[i], z[i]);
+}
+__global__ void k_pack_halo(const int32_t* __restrict__ idx, int64_t n, const double* __restrict__ v, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * 6) out[i] = v[(int64_t)idx[i / 6] * 6 + (i % 6)];
+}
 
 // init: x = 0, r = b, z = M^-1 r, p[0] = z; rz_old = r.z, bb = b.b
 template <int PC>
@@ -149,7 +211,8 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_pcg_init(int64_t n_nodes, const 
                                                          const double* __restrict__ dinv, double* __restrict__ x,
                                                          double* __restrict__ r, double* __restrict__ z,
                                                          double* __restrict__ p0, double* __restrict__ p1,
-                                                         PcgScalars* __restrict__ sc, double* __restrict__ partials) {
+                                                         PcgScalars* __restrict__ sc, double* __restrict__ partials,
+                                                         int dist) {
   const int lane = threadIdx.x & 31;
   const int g = lane / 6, rr_ = lane - g * 6;
   const int64_t warp = (int64_t)blockIdx.x * (SPMV_BLOCK / 32) + (threadIdx.x >> 5);
@@ -161,13 +224,8 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_pcg_init(int64_t n_nodes, const 
   if (active) { x[i] = 0.0; r[i] = bv; z[i] = zv; p0[i] = zv; p1[i] = zv; }
   double v[2] = {bv * zv, bv * bv}, out[2];
   if (grid_reduce<2, SPMV_BLOCK>(v, partials, &sc->counter[0], out)) {
-    sc->rz_old = out[0];
-    sc->bb = out[1];
-    sc->rr = out[1];
-    sc->beta = 0.0;
-    sc->pAp = 0.0; sc->pp = 0.0; sc->xx = 0.0; sc->alpha_last = 0.0;
-    sc->iters = 0; sc->info_flag2 = 0; sc->breakdown = 0;
-    sc->done = (out[1] == 0.0) ? 1 : 0;   // b == 0 -> x = 0
+    if (dist) { sc->sums[0] = out[0]; sc->sums[1] = out[1]; }
+    else pcg_finish_init(sc, out[0], out[1]);
   }
 }
 
@@ -263,28 +321,10 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_pcg_update(int64_t n_nodes, cons
   if (active) z[i] = zv;
   double v[4] = {rv * zv, rv * rv, xv * xv, pnorm}, out[4];
   if (grid_reduce<4, SPMV_BLOCK>(v, partials, &sc->counter[2], out)) {
-    const double rz_new = out[0], rr = out[1], xx = out[2];
-    const double pp = restart ? out[3] : sc->pp;
-    sc->rr = rr;
-    sc->xx = xx;
-    sc->alpha_last = alpha;
-    sc->iters = k + 1;
-    int done = 0;
-    if (prm.reference) {
-      // :97  residual_norm <= tol * norm_b      :102  direction_norm < mintol * (solution_norm + 1e-12)
-      if (sqrt(rr) <= prm.tol * sqrt(sc->bb)) done = 1;
-      else if (prm.mintol > 0.0 && sqrt(pp) < prm.mintol * (sqrt(xx) + 1e-12)) done = 1;
-      else if (alpha < 1e-6) sc->info_flag2 = 1;  // :107-109
-    } else {
-      if (rr <= prm.tol * prm.tol * sc->bb) done = 1;
-      else if (!(pAp > 0.0) || !(rr == rr)) { done = 1; sc->breakdown = 1; }
-    }
-    sc->beta = rz_new / sc->rz_old;
-    sc->rz_old = rz_new;
-    if (done) sc->done = 1;
+    if (prm.dist) { sc->sums[0] = out[0]; sc->sums[1] = out[1]; sc->sums[2] = out[2]; sc->sums[3] = out[3]; }
+    else pcg_finish_iteration(sc, prm, out[0], out[1], out[2], out[3]);
   }
 }
-
 
 // ---------------------------------------------------------------------------
 // TMA-staged SpMV (sm_90+ bulk async copy, used on sm_100a)
@@ -518,6 +558,8 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
   prm.restart_every = o->restart_every;
   prm.maxiter = o->maxiter;
   prm.reference = o->reference_semantics;
+  prm.dist = 0;
+  prm.pad = 0;
   int check = o->check_every > 0 ? o->check_every : 32;
   if (check > o->maxiter) check = o->maxiter > 0 ? o->maxiter : 1;
 
@@ -532,7 +574,7 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
   if (PC != LAT_PC_NONE)
     LAT_LAUNCH(ctx, k_precond_setup, (unsigned)ceil_div(n_nodes, 128), 128, 0, rowptr, colidx, vals, n_nodes, PC, dinv);
   LAT_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-  LAT_LAUNCH(ctx, k_pcg_init<PC>, grid, SPMV_BLOCK, 0, n_nodes, b, dinv, x, r, z, pa, pb, sc, partials);
+  LAT_LAUNCH(ctx, k_pcg_init<PC>, grid, SPMV_BLOCK, 0, n_nodes, b, dinv, x, r, z, pa, pb, sc, partials, 0);
 
   // one CUDA graph = `check` iterations (2 kernels each); relaunched until the device reports done
   cudaGraph_t graph = nullptr;
@@ -646,6 +688,235 @@ extern "C" int lat_pcg_bsr(lat_ctx* ctx, const int32_t* rowptr, const int32_t* c
     case LAT_PC_NONE: return pcg_run<LAT_PC_NONE>(ctx, rowptr, colidx, vals, n_nodes, b, x, opts, result);
     case LAT_PC_JACOBI: return pcg_run<LAT_PC_JACOBI>(ctx, rowptr, colidx, vals, n_nodes, b, x, opts, result);
     case LAT_PC_BLOCK6: return pcg_run<LAT_PC_BLOCK6>(ctx, rowptr, colidx, vals, n_nodes, b, x, opts, result);
+    default: return lat_fail(ctx, LAT_ERR_ARG, "unknown preconditioner", __FILE__, __LINE__);
+  }
+}
+
+
+// ===========================================================================
+// multi-GPU: NCCL (dlopen'ed -- the library torch already loaded), halo exchange, distributed PCG
+// ===========================================================================
+#include <dlfcn.h>
+
+namespace {
+struct NcclUniqueId { char internal[128]; };
+typedef int (*fn_GetUniqueId)(NcclUniqueId*);
+typedef int (*fn_CommInitRank)(void**, int, NcclUniqueId, int);
+typedef int (*fn_CommDestroy)(void*);
+typedef int (*fn_AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_SendRecv)(void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_Send)(const void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_Group)(void);
+typedef const char* (*fn_ErrStr)(int);
+struct NcclApi {
+  void* h = nullptr;
+  fn_GetUniqueId GetUniqueId = nullptr;
+  fn_CommInitRank CommInitRank = nullptr;
+  fn_CommDestroy CommDestroy = nullptr;
+  fn_AllReduce AllReduce = nullptr;
+  fn_Send Send = nullptr;
+  fn_SendRecv Recv = nullptr;
+  fn_Group GroupStart = nullptr, GroupEnd = nullptr;
+  fn_ErrStr ErrStr = nullptr;
+  bool ok = false;
+} g_nccl;
+const int NCCL_FLOAT64 = 8, NCCL_SUM = 0;
+
+bool nccl_load() {
+  if (g_nccl.ok) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    g_nccl.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.h) break;
+  }
+  if (!g_nccl.h) return false;
+  g_nccl.GetUniqueId = (fn_GetUniqueId)dlsym(g_nccl.h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (fn_CommInitRank)dlsym(g_nccl.h, "ncclCommInitRank");
+  g_nccl.CommDestroy = (fn_CommDestroy)dlsym(g_nccl.h, "ncclCommDestroy");
+  g_nccl.AllReduce = (fn_AllReduce)dlsym(g_nccl.h, "ncclAllReduce");
+  g_nccl.Send = (fn_Send)dlsym(g_nccl.h, "ncclSend");
+  g_nccl.Recv = (fn_SendRecv)dlsym(g_nccl.h, "ncclRecv");
+  g_nccl.GroupStart = (fn_Group)dlsym(g_nccl.h, "ncclGroupStart");
+  g_nccl.GroupEnd = (fn_Group)dlsym(g_nccl.h, "ncclGroupEnd");
+  g_nccl.ErrStr = (fn_ErrStr)dlsym(g_nccl.h, "ncclGetErrorString");
+  g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.AllReduce && g_nccl.Send &&
+              g_nccl.Recv && g_nccl.GroupStart && g_nccl.GroupEnd;
+  return g_nccl.ok;
+}
+
+int nccl_fail(lat_ctx* ctx, int rc, const char* what, int line) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "lattice_b200: NCCL error %d (%s) in %s (line %d)", rc,
+           g_nccl.ErrStr ? g_nccl.ErrStr(rc) : "?", what, line);
+  ctx->err = buf;
+  return 1000 + rc;
+}
+#define LAT_NCCL(ctx, call)                                   \
+  do {                                                        \
+    int _r = (call);                                          \
+    if (_r != 0) return nccl_fail((ctx), _r, #call, __LINE__); \
+  } while (0)
+}  // namespace
+
+extern "C" int lat_nccl_unique_id(void* id128) {
+  if (!id128) return LAT_ERR_ARG;
+  if (!nccl_load()) return LAT_ERR_UNSUPPORTED;
+  NcclUniqueId id;
+  const int rc = g_nccl.GetUniqueId(&id);
+  if (rc != 0) return 1000 + rc;
+  memcpy(id128, &id, sizeof id);
+  return LAT_OK;
+}
+
+extern "C" int lat_comm_create(lat_ctx* ctx, const void* id128, int nranks, int rank) {
+  if (!ctx) return LAT_ERR_ARG;
+  LAT_CHECK_ARG(ctx, id128 && nranks >= 1 && rank >= 0 && rank < nranks);
+  if (!nccl_load()) return lat_fail(ctx, LAT_ERR_UNSUPPORTED, "libnccl.so.2 not found", __FILE__, __LINE__);
+  LAT_CUDA(ctx, cudaSetDevice(ctx->device));
+  NcclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  void* comm = nullptr;
+  LAT_NCCL(ctx, g_nccl.CommInitRank(&comm, nranks, id, rank));
+  ctx->nccl_comm = comm;
+  ctx->nranks = nranks;
+  ctx->rank = rank;
+  return LAT_OK;
+}
+
+extern "C" int lat_comm_destroy(lat_ctx* ctx) {
+  if (!ctx) return LAT_ERR_ARG;
+  if (ctx->nccl_comm) {
+    cudaStreamSynchronize(ctx->stream);
+    g_nccl.CommDestroy(ctx->nccl_comm);
+    ctx->nccl_comm = nullptr;
+  }
+  return LAT_OK;
+}
+
+extern "C" int lat_allreduce_sum(lat_ctx* ctx, double* buf, int64_t n) {
+  if (!ctx) return LAT_ERR_ARG;
+  LAT_CHECK_ARG(ctx, buf && n > 0);
+  if (ctx->nranks == 1 || !ctx->nccl_comm) return LAT_OK;
+  LAT_NCCL(ctx, g_nccl.AllReduce(buf, buf, (size_t)n, NCCL_FLOAT64, NCCL_SUM, ctx->nccl_comm, ctx->stream));
+  return LAT_OK;
+}
+
+static int halo_exchange(lat_ctx* ctx, const lat_halo* h, double* vec) {
+  if (ctx->nranks == 1 || h->n_neighbors == 0) return LAT_OK;
+  int64_t tot_send = 0;
+  for (int i = 0; i < h->n_neighbors; ++i) tot_send += h->send_count[i];
+  double* sendbuf = lat_buf<double>(ctx, "halo_send", (size_t)tot_send * 6 + 8);
+  if (!sendbuf) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+  if (tot_send > 0)
+    LAT_LAUNCH(ctx, k_pack_halo, (unsigned)ceil_div(tot_send * 6, 256), 256, 0, h->send_idx, tot_send, vec, sendbuf);
+  LAT_NCCL(ctx, g_nccl.GroupStart());
+  int64_t so = 0, ro = 0;
+  for (int i = 0; i < h->n_neighbors; ++i) {
+    if (h->send_count[i] > 0)
+      LAT_NCCL(ctx, g_nccl.Send(sendbuf + so * 6, (size_t)h->send_count[i] * 6, NCCL_FLOAT64, h->peer[i], ctx->nccl_comm, ctx->stream));
+    if (h->recv_count[i] > 0)
+      LAT_NCCL(ctx, g_nccl.Recv(vec + (h->n_owned + ro) * 6, (size_t)h->recv_count[i] * 6, NCCL_FLOAT64, h->peer[i], ctx->nccl_comm, ctx->stream));
+    so += h->send_count[i];
+    ro += h->recv_count[i];
+  }
+  LAT_NCCL(ctx, g_nccl.GroupEnd());
+  return LAT_OK;
+}
+
+extern "C" int lat_halo_exchange(lat_ctx* ctx, const lat_halo* halo, double* vec) {
+  if (!ctx) return LAT_ERR_ARG;
+  LAT_CHECK_ARG(ctx, halo && vec);
+  LAT_CHECK_ARG(ctx, ctx->nranks == 1 || ctx->nccl_comm != nullptr);
+  LAT_CUDA(ctx, cudaSetDevice(ctx->device));
+  return halo_exchange(ctx, halo, vec);
+}
+
+template <int PC>
+static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, const double* vals,
+                        const lat_halo* h, const double* b, double* x, const lat_pcg_opts* o, lat_pcg_result* res) {
+  const int64_t n_own = h->n_owned, n_loc = h->n_local;
+  const int64_t n = 6 * n_loc;
+  const unsigned grid = (unsigned)ceil_div(n_own, ROWS_PER_CTA);
+  double* r = lat_buf<double>(ctx, "pcg_r", n);
+  double* z = lat_buf<double>(ctx, "pcg_z", n);
+  double* pa = lat_buf<double>(ctx, "pcg_pa", n);
+  double* pb = lat_buf<double>(ctx, "pcg_pb", n);
+  double* Ap = lat_buf<double>(ctx, "pcg_Ap", n);
+  double* dinv = lat_buf<double>(ctx, "pcg_dinv", PC == LAT_PC_BLOCK6 ? 36 * n_own : 6 * n_own);
+  double* partials = lat_buf<double>(ctx, "pcg_partials", (size_t)4 * grid + 8);
+  PcgScalars* sc = lat_buf<PcgScalars>(ctx, "pcg_scalars", 1);
+  if (!r || !z || !pa || !pb || !Ap || !dinv || !partials || !sc)
+    return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+  const int64_t launches0 = ctx->launches;
+  PcgParams prm;
+  prm.tol = o->tol; prm.mintol = o->mintol; prm.alpha_max = o->alpha_max; prm.restart_every = o->restart_every;
+  prm.maxiter = o->maxiter; prm.reference = o->reference_semantics; prm.dist = 1; prm.pad = 0;
+  int check = o->check_every > 0 ? o->check_every : 32;
+  const int64_t g0 = 6 * n_own, g1 = 6 * n_loc;  // ghost DOF range
+  const unsigned ggrid = (unsigned)ceil_div(g1 - g0 > 0 ? g1 - g0 : 1, 256);
+
+  LAT_CUDA(ctx, cudaMemsetAsync(sc, 0, sizeof(PcgScalars), ctx->stream));
+  LAT_CUDA(ctx, cudaMemsetAsync(z, 0, n * sizeof(double), ctx->stream));
+  LAT_CUDA(ctx, cudaMemsetAsync(pa, 0, n * sizeof(double), ctx->stream));
+  LAT_CUDA(ctx, cudaMemsetAsync(pb, 0, n * sizeof(double), ctx->stream));
+  if (PC != LAT_PC_NONE)
+    LAT_LAUNCH(ctx, k_precond_setup, (unsigned)ceil_div(n_own, 128), 128, 0, rowptr, colidx, vals, n_own, PC, dinv);
+  LAT_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+  LAT_LAUNCH(ctx, k_pcg_init<PC>, grid, SPMV_BLOCK, 0, n_own, b, dinv, x, r, z, pa, pb, sc, partials, 1);
+  int rc = lat_allreduce_sum(ctx, sc->sums, 2);
+  if (rc) return rc;
+  LAT_LAUNCH(ctx, k_pcg_finalize_init, 1, 1, 0, sc);
+  rc = halo_exchange(ctx, h, z);
+  if (rc) return rc;
+  PcgScalars* hs = ctx->h_scal;
+  int it = 0;
+  bool finished = o->maxiter <= 0;
+  while (!finished) {
+    const int batch = (o->maxiter - it) < check ? (o->maxiter - it) : check;
+    for (int q = 0; q < batch; ++q) {
+      LAT_LAUNCH(ctx, k_pcg_spmv<0>, grid, SPMV_BLOCK, 0, rowptr, colidx, vals, n_own, z, pa, pb, Ap, sc, partials, prm);
+      if (g1 > g0) LAT_LAUNCH(ctx, k_pcg_ghost_p, ggrid, 256, 0, g0, g1, z, pa, pb, sc, prm);
+      rc = lat_allreduce_sum(ctx, &sc->pAp, 2);  // pAp, pp are adjacent
+      if (rc) return rc;
+      LAT_LAUNCH(ctx, k_pcg_update<PC>, grid, SPMV_BLOCK, 0, n_own, dinv, x, r, z, pa, pb, Ap, sc, partials, prm);
+      rc = lat_allreduce_sum(ctx, sc->sums, 4);
+      if (rc) return rc;
+      LAT_LAUNCH(ctx, k_pcg_finalize_update, 1, 1, 0, sc, prm);
+      rc = halo_exchange(ctx, h, z);
+      if (rc) return rc;
+    }
+    it += batch;
+    LAT_CUDA(ctx, cudaMemcpyAsync(&hs[0], sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, ctx->stream));
+    LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (hs[0].done || hs[0].iters >= o->maxiter || it >= o->maxiter) finished = true;
+  }
+  LAT_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+  LAT_CUDA(ctx, cudaMemcpyAsync(&hs[0], sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, ctx->stream));
+  LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+  res->iters = hs[0].iters;
+  res->norm_b = sqrt(hs[0].bb);
+  res->relres = hs[0].bb > 0.0 ? sqrt(hs[0].rr / hs[0].bb) : 0.0;
+  res->info = hs[0].done && !hs[0].breakdown ? 0 : (hs[0].breakdown ? 3 : (hs[0].info_flag2 ? 2 : 1));
+  res->solve_ms = ms;
+  res->launches = ctx->launches - launches0;
+  res->spmv_ms = 0.0; res->update_ms = 0.0; res->profiled = 0; res->reserved = 0;
+  return LAT_OK;
+}
+
+extern "C" int lat_pcg_bsr_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, const double* vals,
+                                const lat_halo* halo, const double* b, double* x, const lat_pcg_opts* opts,
+                                lat_pcg_result* result) {
+  if (!ctx) return LAT_ERR_ARG;
+  LAT_CHECK_ARG(ctx, rowptr && colidx && vals && halo && b && x && opts && result);
+  LAT_CHECK_ARG(ctx, halo->n_owned > 0 && halo->n_local >= halo->n_owned && opts->maxiter >= 0);
+  LAT_CHECK_ARG(ctx, ctx->nranks == 1 || ctx->nccl_comm != nullptr);
+  LAT_CUDA(ctx, cudaSetDevice(ctx->device));
+  switch (opts->precond) {
+    case LAT_PC_NONE: return pcg_run_dist<LAT_PC_NONE>(ctx, rowptr, colidx, vals, halo, b, x, opts, result);
+    case LAT_PC_JACOBI: return pcg_run_dist<LAT_PC_JACOBI>(ctx, rowptr, colidx, vals, halo, b, x, opts, result);
+    case LAT_PC_BLOCK6: return pcg_run_dist<LAT_PC_BLOCK6>(ctx, rowptr, colidx, vals, halo, b, x, opts, result);
     default: return lat_fail(ctx, LAT_ERR_ARG, "unknown preconditioner", __FILE__, __LINE__);
   }
 }

@@ -1,0 +1,199 @@
+"""Multi-GPU sharding of the full-lattice solve: 1-D slab partition by x (cells are numbered
+i-major in the reference, ``pyLatticeDesign/lattice.py:448-453``, so a slab of consecutive
+x-layers is a contiguous cell-index range), one process per GPU.
+
+Host side (numpy, this file): which nodes a rank owns, which neighbours' nodes it needs as
+ghosts, local renumbering [owned | ghosts by owner rank, then global id], send lists.  Both
+sides of every exchange derive their lists from the same global connectivity, so no
+communication is needed to set the halos up.
+
+Device side (``liblattice_b200.so``): complete block rows of the owned nodes are assembled
+locally from the elements that touch them (a one-strut-deep overlap instead of exchanging
+partial rows); PCG exchanges the ghost part of z with ncclSend/ncclRecv and all-reduces the dot
+products (``lat_pcg_bsr_dist``).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from .mesh import NDOF, BeamMesh
+
+
+@dataclass
+class SlabPartition:
+    rank: int
+    world: int
+    owned: np.ndarray        # global node ids owned by this rank (ascending)
+    ghosts: np.ndarray       # global node ids of the ghosts, ordered by owner rank then global id
+    ghost_owner: np.ndarray  # owner rank of each ghost
+    local_elems: np.ndarray  # global element ids assembled on this rank (ascending)
+    peers: list              # neighbour ranks (ascending)
+    send_lists: list         # per peer: LOCAL ids (owned) to send, ordered by global id
+    recv_counts: list        # per peer: number of ghosts owned by that peer
+    g2l: dict | None = None
+
+    @property
+    def n_owned(self):
+        return int(self.owned.shape[0])
+
+    @property
+    def n_local(self):
+        return int(self.owned.shape[0] + self.ghosts.shape[0])
+
+    @property
+    def local_nodes(self):
+        return np.concatenate([self.owned, self.ghosts])
+
+
+def node_owner_by_x(x, bounds):
+    """Owner rank of each node from its x coordinate: rank p owns bounds[p] <= x < bounds[p+1]
+    (the last rank also owns x == bounds[-1])."""
+    r = np.searchsorted(bounds, x, side="right") - 1
+    return np.clip(r, 0, len(bounds) - 2).astype(np.int32)
+
+
+def slab_bounds(x_min, x_max, world, n_layers=None, cell=1.0):
+    """Slab boundaries on cell-layer planes: n_layers cells split as evenly as possible."""
+    if n_layers is None:
+        n_layers = int(round((x_max - x_min) / cell))
+    cuts = [x_min + cell * ((n_layers * p) // world) for p in range(world)] + [x_max]
+    return np.array(cuts, dtype=np.float64)
+
+
+def partition_slab(mesh: BeamMesh, rank: int, world: int, bounds=None, owner=None) -> SlabPartition:
+    if owner is None:
+        if bounds is None:
+            bounds = slab_bounds(float(mesh.x.min()), float(mesh.x.max()), world)
+        owner = node_owner_by_x(mesh.x, bounds)
+    o0, o1 = owner[mesh.en0], owner[mesh.en1]
+    mine = (o0 == rank) | (o1 == rank)
+    local_elems = np.flatnonzero(mine)
+    owned = np.flatnonzero(owner == rank)
+    ends = np.concatenate([mesh.en0[local_elems], mesh.en1[local_elems]])
+    ghosts = np.unique(ends[owner[ends] != rank])
+    gown = owner[ghosts]
+    order = np.lexsort((ghosts, gown))
+    ghosts, gown = ghosts[order], gown[order]
+    peers = sorted(set(gown.tolist()))
+    # what I must send to peer q: my owned nodes that are element-neighbours of a node owned by q
+    e_cross0 = (o0 == rank) & (o1 != rank)
+    e_cross1 = (o1 == rank) & (o0 != rank)
+    send_pairs = np.concatenate([np.stack([mesh.en0[e_cross0], o1[e_cross0]], 1),
+                                 np.stack([mesh.en1[e_cross1], o0[e_cross1]], 1)], axis=0)
+    peers = sorted(set(peers) | set(send_pairs[:, 1].tolist()))
+    g2l_owned = {int(g): k for k, g in enumerate(owned)}
+    send_lists, recv_counts = [], []
+    for q in peers:
+        nodes = np.unique(send_pairs[send_pairs[:, 1] == q, 0])
+        send_lists.append(np.array([g2l_owned[int(g)] for g in nodes], dtype=np.int32))
+        recv_counts.append(int((gown == q).sum()))
+    return SlabPartition(rank, world, owned, ghosts, gown, local_elems, peers, send_lists, recv_counts)
+
+
+def local_mesh(mesh: BeamMesh, part: SlabPartition) -> BeamMesh:
+    """Sub-mesh of a rank in local numbering [owned | ghosts]."""
+    nodes = part.local_nodes
+    g2l = np.full(mesh.n_nodes, -1, dtype=np.int64)
+    g2l[nodes] = np.arange(nodes.shape[0])
+    e = part.local_elems
+    return BeamMesh(x=mesh.x[nodes].copy(), y=mesh.y[nodes].copy(), z=mesh.z[nodes].copy(),
+                    en0=g2l[mesh.en0[e]].astype(np.int32), en1=g2l[mesh.en1[e]].astype(np.int32),
+                    rad=mesh.rad[e].copy(), beam_of_elem=mesh.beam_of_elem[e].copy(), chain=mesh.chain[e].copy(),
+                    n_points=int((nodes < mesh.n_points).sum()), point_index=nodes[nodes < mesh.n_points],
+                    cell_of_elem=None if mesh.cell_of_elem is None else mesh.cell_of_elem[e].copy(),
+                    meta={"global_nodes": nodes})
+
+
+def local_dofs(part: SlabPartition):
+    nodes = part.local_nodes
+    return (nodes[:, None] * NDOF + np.arange(NDOF)[None, :]).ravel()
+
+
+class DistributedFEM:
+    """Slab-sharded assemble + solve.  Every rank passes the same GLOBAL mesh and BC arrays (cheap,
+    vectorised) and keeps only its slab on the GPU."""
+
+    def __init__(self, ctx, mesh: BeamMesh, young, nu, rank, world, kappa=0.9, bounds=None):
+        import torch
+        from . import lib as L
+        self.torch, self.L = torch, L
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self.part = partition_slab(mesh, rank, world, bounds)
+        self.lmesh = local_mesh(mesh, self.part)
+        self.young, self.nu, self.kappa = young, nu, kappa
+        dev = ctx.device
+        t = lambda a, d: torch.from_numpy(np.ascontiguousarray(a, dtype=d)).to(dev)
+        m = self.lmesh
+        self.x, self.y, self.z = t(m.x, np.float64), t(m.y, np.float64), t(m.z, np.float64)
+        self.en0, self.en1, self.rad = t(m.en0, np.int32), t(m.en1, np.int32), t(m.rad, np.float64)
+        self.n_owned, self.n_local = self.part.n_owned, self.part.n_local
+        send = np.concatenate(self.part.send_lists) if self.part.send_lists else np.zeros(0, np.int32)
+        self.send_idx = t(send, np.int32)
+        self.halo = ctx.make_halo(self.part.peers, [len(s) for s in self.part.send_lists], self.part.recv_counts,
+                                  self.send_idx, self.n_owned, self.n_local)
+        self.dofs = local_dofs(self.part)
+        self.n_dof_global = mesh.n_dof
+        self.n_elem_global = mesh.n_elems
+        # pattern over the local mesh; only the first n_owned block rows are complete and used
+        self.rowptr, self.colidx = ctx.bsr_pattern(self.en0, self.en1, self.n_local)
+        self.nnzb = int(self.colidx.numel())
+        self.nnzb_owned = int(self.rowptr[self.n_owned].item())
+        self.vals = None
+
+    def set_bc(self, fixed, g, f):
+        t = lambda a, d: self.torch.from_numpy(np.ascontiguousarray(a[self.dofs], dtype=d)).to(self.ctx.device)
+        self.fixed_d, self.g_d, self.f_d = t(fixed, np.uint8), t(g, np.float64), t(f, np.float64)
+
+    def assemble(self, out=None):
+        self.vals = self.ctx.assemble_bsr(self.x, self.y, self.z, self.en0, self.en1, self.rad, self.n_local, self.nnzb,
+                                          self.young, self.nu, self.kappa, out=out)
+        return self.vals
+
+    def solve(self, tol=1e-8, maxiter=200000, precond=2, vals_bc=None, b=None, u=None, check_every=0):
+        """Returns (u_local [6 n_local] incl. ghosts, reactions on owned rows, info)."""
+        torch, ctx = self.torch, self.ctx
+        if self.vals is None:
+            self.assemble()
+        if vals_bc is None:
+            vals_bc = torch.empty_like(self.vals)
+        if b is None:
+            b = torch.empty(6 * self.n_local, dtype=torch.float64, device=ctx.device)
+        if u is None:
+            u = torch.empty(6 * self.n_local, dtype=torch.float64, device=ctx.device)
+        L = self.L
+        ctx.check(ctx.lib.lat_apply_dirichlet(ctx.h, L._ptr(self.rowptr), L._ptr(self.colidx), self.n_local,
+                                              L._ptr(self.vals), L._ptr(self.fixed_d), L._ptr(self.g_d),
+                                              L._ptr(self.f_d), L._ptr(vals_bc), L._ptr(b)))
+        u, info = ctx.pcg_dist(self.rowptr, self.colidx, vals_bc, self.halo, b, u, tol=tol, maxiter=maxiter,
+                               precond=precond, check_every=check_every)
+        ctx.set_dirichlet_values(self.fixed_d, self.g_d, u)
+        ctx.halo_exchange(self.halo, u)
+        R = ctx.spmv(self.rowptr, self.colidx, self.vals, u)     # rows >= n_owned are partial: ignore
+        return u, R, info
+
+    def gather_owned(self, vec_local):
+        """All-gather the owned part of a local vector into a global numpy vector (test / write-back helper)."""
+        import torch.distributed as dist
+        torch = self.torch
+        own = vec_local[: 6 * self.n_owned].contiguous()
+        counts = torch.tensor([own.numel()], device=own.device)
+        allc = [torch.zeros_like(counts) for _ in range(self.world)]
+        dist.all_gather(allc, counts)
+        mx = int(max(int(c) for c in allc))
+        pad = torch.zeros(mx, dtype=own.dtype, device=own.device)
+        pad[: own.numel()] = own
+        bufs = [torch.zeros_like(pad) for _ in range(self.world)]
+        dist.all_gather(bufs, pad)
+        ids = torch.from_numpy(self.part.owned).to(own.device)
+        idpad = torch.full((mx // 6,), -1, dtype=torch.int64, device=own.device)
+        idpad[: ids.numel()] = ids
+        idb = [torch.zeros_like(idpad) for _ in range(self.world)]
+        dist.all_gather(idb, idpad)
+        out = np.zeros(self.n_dof_global)
+        for q in range(self.world):
+            k = int(allc[q]) // 6
+            gi = idb[q][:k].cpu().numpy()
+            out.reshape(-1, 6)[gi] = bufs[q][: 6 * k].cpu().numpy().reshape(-1, 6)
+        return out

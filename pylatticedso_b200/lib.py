@@ -26,6 +26,8 @@ EXPORTS = [
     "lat_elem_stiffness", "lat_bsr_pattern_build", "lat_bsr_pattern_export", "lat_csr_structure",
     "lat_bsr_to_csr_values", "lat_assemble_bsr", "lat_apply_dirichlet", "lat_set_dirichlet_values", "lat_bsr_spmv", "lat_pcg_bsr",
     "lat_compliance_grad", "lat_schur_batch", "lat_ddm_matvec",
+    "lat_nccl_unique_id", "lat_comm_create", "lat_comm_destroy", "lat_allreduce_sum", "lat_halo_exchange",
+    "lat_pcg_bsr_dist",
 ]
 
 
@@ -46,10 +48,16 @@ class PcgResult(C.Structure):
                 ("update_ms", C.c_double), ("profiled", C.c_int32), ("reserved", C.c_int32)]
 
 
+class Halo(C.Structure):
+    _fields_ = [("n_neighbors", C.c_int32), ("pad", C.c_int32), ("peer", C.POINTER(C.c_int32)),
+                ("send_count", C.POINTER(C.c_int32)), ("recv_count", C.POINTER(C.c_int32)),
+                ("send_idx", C.c_void_p), ("n_owned", C.c_int64), ("n_local", C.c_int64)]
+
+
 def nvcc_command(out=LIB_PATH):
     src = [os.path.join(_HERE, "csrc", s) for s in SOURCES]
     return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-            "-shared", "-Xcompiler", "-fPIC", "-I", os.path.join(_ROOT, "include"), "-o", out] + src
+            "-shared", "-Xcompiler", "-fPIC", "-I", os.path.join(_ROOT, "include"), "-o", out] + src + ["-ldl"]
 
 
 def build(force=False, verbose=False):
@@ -103,6 +111,12 @@ def load():
     lib.lat_compliance_grad.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, vp, vp, i64, vp, vp]
     lib.lat_schur_batch.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, i32, dbl, dbl, dbl, vp, vp, vp, i32, vp]
     lib.lat_ddm_matvec.argtypes = [vp, vp, i64, vp, vp, i64, i32, i64, vp, vp]
+    lib.lat_nccl_unique_id.argtypes = [vp]
+    lib.lat_comm_create.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.lat_comm_destroy.argtypes = [vp]
+    lib.lat_allreduce_sum.argtypes = [vp, vp, i64]
+    lib.lat_halo_exchange.argtypes = [vp, C.POINTER(Halo), vp]
+    lib.lat_pcg_bsr_dist.argtypes = [vp, vp, vp, vp, C.POINTER(Halo), vp, vp, C.POINTER(PcgOpts), C.POINTER(PcgResult)]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("lat_last_error", "lat_launch_count"):
@@ -268,3 +282,52 @@ class Context:
         self.check(self.lib.lat_ddm_matvec(self.h, _ptr(S), stride, _ptr(gidx), _ptr(u_fixed), n_cells, nb, n_free,
                                            _ptr(x), _ptr(y)))
         return y
+
+    # -- multi-GPU ---------------------------------------------------------------
+    def comm_create(self, rank, world):
+        """Create the library's NCCL communicator; the 128-byte id travels through torch.distributed."""
+        import torch
+        import torch.distributed as dist
+        buf = (C.c_char * 128)()
+        if rank == 0:
+            rc = self.lib.lat_nccl_unique_id(buf)
+            if rc != 0:
+                raise LatticeB200Error(f"lat_nccl_unique_id failed with code {rc}")
+        t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        if dist.get_backend() == "nccl":
+            t = t.to(self.device)
+        dist.broadcast(t, src=0)
+        raw = bytes(t.cpu().numpy().tobytes())
+        idbuf = C.create_string_buffer(raw, 128)
+        self.check(self.lib.lat_comm_create(self.h, idbuf, world, rank))
+        self.rank, self.world = rank, world
+
+    def comm_destroy(self):
+        self.lib.lat_comm_destroy(self.h)
+
+    def make_halo(self, peers, send_counts, recv_counts, send_idx_dev, n_owned, n_local):
+        n = len(peers)
+        arr = lambda v: (C.c_int32 * max(1, n))(*[int(q) for q in v])
+        keep = (arr(peers), arr(send_counts), arr(recv_counts), send_idx_dev)
+        h = Halo(n, 0, C.cast(keep[0], C.POINTER(C.c_int32)), C.cast(keep[1], C.POINTER(C.c_int32)),
+                 C.cast(keep[2], C.POINTER(C.c_int32)), C.c_void_p(send_idx_dev.data_ptr() if send_idx_dev is not None and send_idx_dev.numel() else 0),
+                 int(n_owned), int(n_local))
+        h._keep = keep
+        return h
+
+    def halo_exchange(self, halo, vec):
+        self.check(self.lib.lat_halo_exchange(self.h, C.byref(halo), _ptr(vec)))
+        return vec
+
+    def allreduce_sum(self, t):
+        self.check(self.lib.lat_allreduce_sum(self.h, _ptr(t), t.numel()))
+        return t
+
+    def pcg_dist(self, rowptr, colidx, vals, halo, b, x, tol=1e-8, maxiter=10000, precond=PC_JACOBI,
+                 reference_semantics=False, mintol=0.0, alpha_max=0.0, restart_every=0, check_every=0):
+        o = PcgOpts(tol, mintol, alpha_max, restart_every, maxiter, precond, int(reference_semantics), check_every, 0, 0)
+        r = PcgResult()
+        self.check(self.lib.lat_pcg_bsr_dist(self.h, _ptr(rowptr), _ptr(colidx), _ptr(vals), C.byref(halo), _ptr(b),
+                                             _ptr(x), C.byref(o), C.byref(r)))
+        return x, dict(iters=r.iters, info=r.info, relres=r.relres, norm_b=r.norm_b, solve_ms=r.solve_ms,
+                       launches=r.launches)

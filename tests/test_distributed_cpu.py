@@ -1,0 +1,105 @@
+"""CPU (gloo, world_size 2): the host-side slab partition / halo logic of the multi-GPU path.
+The device exchange (ncclSend/ncclRecv) is replaced by torch.distributed gloo send/recv and the
+local operators are assembled with the CPU oracle, so the index logic is what is tested."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import E_MOD, NU, ROOT
+
+
+def _exchange(part, vec_nodes6):
+    """gloo version of lat_halo_exchange: vec_nodes6 [n_local, 6]."""
+    reqs, recv_bufs = [], []
+    ro = 0
+    for q, sl, rc in zip(part.peers, part.send_lists, part.recv_counts):
+        if len(sl):
+            reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(vec_nodes6[sl])), dst=q))
+        if rc:
+            buf = torch.empty((rc, 6), dtype=torch.float64)
+            reqs.append(dist.irecv(buf, src=q))
+            recv_bufs.append((ro, rc, buf))
+        ro += rc
+    for r in reqs:
+        r.wait()
+    for ro, rc, buf in recv_bufs:
+        vec_nodes6[part.n_owned + ro: part.n_owned + ro + rc] = buf.numpy()
+
+
+def _worker(rank, world, port, geom, ncell, m_, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from pylatticedso_b200 import mesh as M
+        from pylatticedso_b200 import distributed as D
+        from oracle import lattice_oracle as orc
+        lat = M.synthetic_lattice(geom, ncell, [0.04])
+        mesh = M.mesh_from_synthetic(lat, m_)
+        part = D.partition_slab(mesh, rank, world)
+        lm = D.local_mesh(mesh, part)
+        # every node is owned exactly once
+        cnt = torch.zeros(mesh.n_nodes, dtype=torch.int64)
+        cnt[torch.from_numpy(part.owned)] = 1
+        dist.all_reduce(cnt)
+        assert bool((cnt == 1).all())
+        # complete rows: every element touching an owned node is local
+        touched = np.isin(mesh.en0, part.owned) | np.isin(mesh.en1, part.owned)
+        assert np.array_equal(np.flatnonzero(touched), part.local_elems)
+        # ghost section ordered by owner then global id, contiguous per peer
+        assert np.all(np.diff(part.ghost_owner) >= 0)
+        for qq in part.peers:
+            g = part.ghosts[part.ghost_owner == qq]
+            assert np.all(np.diff(g) > 0)
+        # distributed SpMV == global SpMV on the owned rows
+        Kg = orc.assemble_csr(mesh.xyz, np.stack([mesh.en0, mesh.en1], 1), mesh.rad, E_MOD, NU)
+        Kl = orc.assemble_csr(lm.xyz, np.stack([lm.en0, lm.en1], 1), lm.rad, E_MOD, NU)
+        rng = np.random.default_rng(5)
+        xg = rng.standard_normal(mesh.n_dof)
+        xl = np.zeros((part.n_local, 6))
+        xl[: part.n_owned] = xg.reshape(-1, 6)[part.owned]          # ghosts unknown until exchanged
+        _exchange(part, xl)
+        assert np.array_equal(xl[part.n_owned:], xg.reshape(-1, 6)[part.ghosts])
+        yl = (Kl @ xl.ravel()).reshape(-1, 6)[: part.n_owned]
+        yg = (Kg @ xg).reshape(-1, 6)[part.owned]
+        assert np.abs(yl - yg).max() < 1e-12 * np.abs(yg).max()
+        # dot products over owned DOFs all-reduce to the global dot
+        d = torch.tensor([float((xl[: part.n_owned] ** 2).sum())], dtype=torch.float64)
+        dist.all_reduce(d)
+        assert abs(float(d) - float(xg @ xg)) < 1e-10 * float(xg @ xg)
+        q.put((rank, "ok", part.n_owned, len(part.ghosts)))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, "FAIL: " + traceback.format_exc(), 0, 0))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("geom,ncell,m_", [("BCC", (4, 2, 2), 2), ("Octet", (4, 2, 3), 1), ("BCC", (5, 2, 2), 1)])
+def test_slab_partition_two_ranks_gloo(geom, ncell, m_):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + hash((geom, ncell, m_))) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, geom, ncell, m_, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for r in res:
+        assert r[1] == "ok", r[1]
+    assert sum(r[2] for r in res) > 0 and all(r[3] > 0 for r in res)
+
+
+def test_slab_bounds_and_owner():
+    from pylatticedso_b200 import distributed as D
+    b = D.slab_bounds(0.0, 100.0, 8)
+    assert list(np.diff(b)) == [12, 13, 12, 13, 12, 13, 12, 13] or sum(np.diff(b)) == 100
+    o = D.node_owner_by_x(np.array([0.0, 11.99, 12.0, 99.9, 100.0]), b)
+    assert list(o) == [0, 0, 1, 7, 7]

@@ -1,0 +1,53 @@
+"""Multi-GPU parity check (run under torchrun, one rank per GPU):
+   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tools/dist_check.py
+The slab-sharded assemble + PCG (NCCL halo exchange, all-reduced dots) must reproduce the CPU
+oracle's displacements and reactions to 1e-8."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pylatticedso_b200 import lib as L, mesh as M, distributed as D  # noqa: E402
+from oracle import lattice_oracle as orc  # noqa: E402
+
+E, NU = 1013.0, 0.3
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = L.Context(local)
+    ctx.comm_create(rank, world)
+    ok = True
+    for geom, n, m_, r in (("BCC", (2 * world, 3, 3), 2, 0.05), ("Octet", (2 * world + 1, 2, 3), 1, 0.03)):
+        lat = M.synthetic_lattice(geom, n, [r])
+        mesh = M.mesh_from_synthetic(lat, m_)
+        fixed, g, f = M.compression_bc(mesh)
+        f = f.copy(); f[6 * 7 + 0] = 0.01
+        dfem = D.DistributedFEM(ctx, mesh, E, NU, rank, world)
+        dfem.set_bc(fixed, g, f)
+        u, R, info = dfem.solve(tol=1e-13, maxiter=100000, precond=L.PC_BLOCK6, check_every=16)
+        ug = dfem.gather_owned(u)
+        Rg = dfem.gather_owned(R)
+        if rank == 0:
+            K = orc.assemble_csr(mesh.xyz, np.stack([mesh.en0, mesh.en1], 1), mesh.rad, E, NU)
+            uo, Ro = orc.solve_static(K, fixed.astype(bool), g, f)
+            eu = np.abs(ug - uo).max() / np.abs(uo).max()
+            er = np.abs(Rg - Ro).max() / np.abs(Ro).max()
+            print(f"[dist_check] {geom}{n} m={m_} world={world} n_dof={mesh.n_dof} iters={info['iters']} info={info['info']} "
+                  f"relres={info['relres']:.1e} |u-uo|/|uo|={eu:.2e} |R-Ro|/|Ro|={er:.2e}", flush=True)
+            ok = ok and info["info"] == 0 and eu < 1e-8 and er < 1e-8
+    ctx.comm_destroy()
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("[dist_check] PASS" if ok else "[dist_check] FAIL", flush=True)
+        sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
