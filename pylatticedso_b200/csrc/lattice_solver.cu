@@ -801,15 +801,8 @@ extern "C" int lat_allreduce_sum(lat_ctx* ctx, double* buf, int64_t n) {
   return LAT_OK;
 }
 
-static int halo_exchange(lat_ctx* ctx, const lat_halo* h, double* vec) {
-  if (ctx->nranks == 1 || h->n_neighbors == 0) return LAT_OK;
-  int64_t tot_send = 0;
-  for (int i = 0; i < h->n_neighbors; ++i) tot_send += h->send_count[i];
-  double* sendbuf = lat_buf<double>(ctx, "halo_send", (size_t)tot_send * 6 + 8);
-  if (!sendbuf) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
-  if (tot_send > 0)
-    LAT_LAUNCH(ctx, k_pack_halo, (unsigned)ceil_div(tot_send * 6, 256), 256, 0, h->send_idx, tot_send, vec, sendbuf);
-  LAT_NCCL(ctx, g_nccl.GroupStart());
+// sends/receives of one halo exchange; must be called between ncclGroupStart/End
+static int halo_comm(lat_ctx* ctx, const lat_halo* h, double* vec, double* sendbuf) {
   int64_t so = 0, ro = 0;
   for (int i = 0; i < h->n_neighbors; ++i) {
     if (h->send_count[i] > 0)
@@ -819,6 +812,28 @@ static int halo_exchange(lat_ctx* ctx, const lat_halo* h, double* vec) {
     so += h->send_count[i];
     ro += h->recv_count[i];
   }
+  return LAT_OK;
+}
+
+static int halo_pack(lat_ctx* ctx, const lat_halo* h, const double* vec, double** sendbuf_out) {
+  int64_t tot_send = 0;
+  for (int i = 0; i < h->n_neighbors; ++i) tot_send += h->send_count[i];
+  double* sendbuf = lat_buf<double>(ctx, "halo_send", (size_t)tot_send * 6 + 8);
+  if (!sendbuf) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+  if (tot_send > 0)
+    LAT_LAUNCH(ctx, k_pack_halo, (unsigned)ceil_div(tot_send * 6, 256), 256, 0, h->send_idx, tot_send, vec, sendbuf);
+  *sendbuf_out = sendbuf;
+  return LAT_OK;
+}
+
+static int halo_exchange(lat_ctx* ctx, const lat_halo* h, double* vec) {
+  if (ctx->nranks == 1 || h->n_neighbors == 0) return LAT_OK;
+  double* sendbuf = nullptr;
+  int rc = halo_pack(ctx, h, vec, &sendbuf);
+  if (rc) return rc;
+  LAT_NCCL(ctx, g_nccl.GroupStart());
+  rc = halo_comm(ctx, h, vec, sendbuf);
+  if (rc) { g_nccl.GroupEnd(); return rc; }
   LAT_NCCL(ctx, g_nccl.GroupEnd());
   return LAT_OK;
 }
@@ -869,27 +884,86 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
   rc = halo_exchange(ctx, h, z);
   if (rc) return rc;
   PcgScalars* hs = ctx->h_scal;
+  const bool multi = ctx->nranks > 1 && ctx->nccl_comm != nullptr;
+  // one PCG iteration: 5 kernels + (multi-GPU) 2 NCCL launches: all-reduce(p.Ap, p.p), then
+  // {all-reduce(r.z, r.r, x.x, |p|^2) + halo exchange of z} fused in one NCCL group.
+  auto one_iteration = [&]() -> int {
+    LAT_LAUNCH(ctx, k_pcg_spmv<0>, grid, SPMV_BLOCK, 0, rowptr, colidx, vals, n_own, z, pa, pb, Ap, sc, partials, prm);
+    if (g1 > g0) LAT_LAUNCH(ctx, k_pcg_ghost_p, ggrid, 256, 0, g0, g1, z, pa, pb, sc, prm);
+    int rc2 = lat_allreduce_sum(ctx, &sc->pAp, 2);  // pAp, pp are adjacent
+    if (rc2) return rc2;
+    LAT_LAUNCH(ctx, k_pcg_update<PC>, grid, SPMV_BLOCK, 0, n_own, dinv, x, r, z, pa, pb, Ap, sc, partials, prm);
+    if (multi) {
+      double* sendbuf = nullptr;
+      rc2 = halo_pack(ctx, h, z, &sendbuf);
+      if (rc2) return rc2;
+      LAT_NCCL(ctx, g_nccl.GroupStart());
+      LAT_NCCL(ctx, g_nccl.AllReduce(sc->sums, sc->sums, 4, NCCL_FLOAT64, NCCL_SUM, ctx->nccl_comm, ctx->stream));
+      rc2 = halo_comm(ctx, h, z, sendbuf);
+      if (rc2) { g_nccl.GroupEnd(); return rc2; }
+      LAT_NCCL(ctx, g_nccl.GroupEnd());
+    }
+    LAT_LAUNCH(ctx, k_pcg_finalize_update, 1, 1, 0, sc, prm);
+    return LAT_OK;
+  };
+  // make sure the halo send buffer exists before any capture (allocation is not capturable)
+  {
+    double* sb = nullptr;
+    int64_t tot_send = 0;
+    for (int i = 0; i < h->n_neighbors; ++i) tot_send += h->send_count[i];
+    sb = lat_buf<double>(ctx, "halo_send", (size_t)tot_send * 6 + 8);
+    if (!sb) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+  }
+  // capture `check` iterations (kernels AND NCCL operations) into one CUDA graph: the host then issues
+  // one graph launch per batch instead of ~8 launches per iteration.
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  bool use_graph = (o->reserved & 4) == 0 && o->maxiter >= check;
+  if (use_graph) {
+    const int64_t l0 = ctx->launches;
+    cudaError_t ce = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+    int crc = LAT_OK;
+    if (ce == cudaSuccess) {
+      for (int q = 0; q < check && crc == LAT_OK; ++q) crc = one_iteration();
+      ce = cudaStreamEndCapture(ctx->stream, &graph);
+    }
+    ctx->launches = l0;
+    if (ce != cudaSuccess || crc != LAT_OK || graph == nullptr) {
+      cudaGetLastError();
+      if (graph) cudaGraphDestroy(graph);
+      graph = nullptr;
+      use_graph = false;
+    } else if (cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) {
+      cudaGetLastError();
+      cudaGraphDestroy(graph);
+      graph = nullptr;
+      use_graph = false;
+    }
+  }
   int it = 0;
   bool finished = o->maxiter <= 0;
   while (!finished) {
     const int batch = (o->maxiter - it) < check ? (o->maxiter - it) : check;
-    for (int q = 0; q < batch; ++q) {
-      LAT_LAUNCH(ctx, k_pcg_spmv<0>, grid, SPMV_BLOCK, 0, rowptr, colidx, vals, n_own, z, pa, pb, Ap, sc, partials, prm);
-      if (g1 > g0) LAT_LAUNCH(ctx, k_pcg_ghost_p, ggrid, 256, 0, g0, g1, z, pa, pb, sc, prm);
-      rc = lat_allreduce_sum(ctx, &sc->pAp, 2);  // pAp, pp are adjacent
-      if (rc) return rc;
-      LAT_LAUNCH(ctx, k_pcg_update<PC>, grid, SPMV_BLOCK, 0, n_own, dinv, x, r, z, pa, pb, Ap, sc, partials, prm);
-      rc = lat_allreduce_sum(ctx, sc->sums, 4);
-      if (rc) return rc;
-      LAT_LAUNCH(ctx, k_pcg_finalize_update, 1, 1, 0, sc, prm);
-      rc = halo_exchange(ctx, h, z);
-      if (rc) return rc;
+    if (use_graph && batch == check) {
+      cudaError_t ce = cudaGraphLaunch(gexec, ctx->stream);
+      if (ce != cudaSuccess) { rc = lat_cuda_fail(ctx, ce, "cudaGraphLaunch", __FILE__, __LINE__); break; }
+      ctx->launches += (int64_t)check * (g1 > g0 ? 5 : 4);
+    } else {
+      for (int q = 0; q < batch; ++q) {
+        rc = one_iteration();
+        if (rc) break;
+      }
+      if (rc) break;
     }
     it += batch;
-    LAT_CUDA(ctx, cudaMemcpyAsync(&hs[0], sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, ctx->stream));
-    LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaMemcpyAsync(&hs[0], sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+    if (ce != cudaSuccess) { rc = lat_cuda_fail(ctx, ce, "distributed PCG iteration", __FILE__, __LINE__); break; }
     if (hs[0].done || hs[0].iters >= o->maxiter || it >= o->maxiter) finished = true;
   }
+  if (gexec) cudaGraphExecDestroy(gexec);
+  if (graph) cudaGraphDestroy(graph);
+  if (rc) return rc;
   LAT_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
   LAT_CUDA(ctx, cudaMemcpyAsync(&hs[0], sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, ctx->stream));
   LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
