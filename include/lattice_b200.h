@@ -129,7 +129,8 @@ int lat_bsr_spmv(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx,
  * alpha = min(rz/pAp, alpha_max) (:78-79), p <- z every restart_every iterations
  * (:89-90), stop when |r| <= tol |b| (:97) or |p| < mintol (|x| + 1e-12) (:102),
  * info 0/1/2 (:73,98,103,108).  reference_semantics = 0 is textbook PCG with the
- * single test |r| <= tol |b|. */
+ * single test |r| <= tol |b|, run in the Chronopoulos-Gear arrangement (one gather, one
+ * reduction per iteration; same Krylov iterates in exact arithmetic). */
 typedef struct {
   double tol;
   double mintol;
@@ -141,7 +142,8 @@ typedef struct {
   int32_t check_every; /* iterations between host polls of the device status (0 = default 32) */
   int32_t profile_iters; /* >0: the first profile_iters iterations are launched outside the CUDA graph
                             with CUDA events around each kernel (fills spmv_ms / update_ms) */
-  int32_t reserved;      /* bit 1: use the experimental TMA-staged (cp.async.bulk) SpMV kernel (A/B testing) */
+  int32_t reserved;      /* bit 1: experimental TMA-staged SpMV kernel; bit 2: no CUDA graph in the multi-GPU path;
+                            bit 3: classic two-reduction recurrences instead of Chronopoulos-Gear (textbook mode) */
 } lat_pcg_opts;
 
 typedef struct {

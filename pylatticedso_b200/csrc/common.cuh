@@ -19,6 +19,8 @@ struct PcgScalars {
   int32_t done, info_flag2, iters, breakdown;
   unsigned int counter[4];  // last-block-done tickets (one per kernel family)
   double sums[4];           // local partial sums awaiting the all-reduce (multi-GPU path)
+  double gamma, alpha;      // Chronopoulos-Gear variant: (r,u) and the current step length
+  int32_t first, pad;
 };
 
 struct lat_ctx {

@@ -327,6 +327,120 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_pcg_update(int64_t n_nodes, cons
 }
 
 // ---------------------------------------------------------------------------
+// Chronopoulos-Gear PCG (default for the textbook mode): ONE gather and ONE global reduction per
+// iteration.   u = M^-1 r,  w = A u,  gamma = (r,u),  delta = (w,u)
+//   beta = gamma/gamma_old,  alpha = gamma / (delta - beta*gamma/alpha_old)
+//   p = u + beta p,  s = w + beta s,  x += alpha p,  r -= alpha s
+// Kernel A (k_cg_spmv): w = A u with the three dots and, in the last block, the scalar recurrences
+// and the stop test.  Kernel B (k_cg_update): the five vector updates and the preconditioner, no
+// reduction at all.  Mathematically the same Krylov iteration as classic PCG; the classic two-reduction
+// form (k_pcg_spmv / k_pcg_update) is kept for reference_semantics = 1, whose clamp / restart rules
+// are defined on the classic recurrences.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void cg_finish(PcgScalars* sc, const PcgParams& prm, double gamma, double delta, double rr) {
+  sc->rr = rr;
+  if (sc->first) {  // set-up pass: w0 = A u0
+    sc->first = 0;
+    sc->bb = rr;    // r0 = b
+    sc->beta = 0.0;
+    sc->gamma = gamma;
+    sc->alpha = gamma / delta;
+    if (rr == 0.0) sc->done = 1;
+    else if (!(delta > 0.0)) { sc->done = 1; sc->breakdown = 1; }
+    return;
+  }
+  sc->iters += 1;
+  if (rr <= prm.tol * prm.tol * sc->bb) { sc->done = 1; return; }
+  const double beta = gamma / sc->gamma;
+  const double denom = delta - beta * gamma / sc->alpha;
+  if (!(denom > 0.0) || !(rr == rr)) { sc->done = 1; sc->breakdown = 1; return; }
+  sc->beta = beta;
+  sc->alpha = gamma / denom;
+  sc->gamma = gamma;
+}
+
+__global__ void k_cg_finalize(PcgScalars* sc, PcgParams prm) {
+  if (sc->done || sc->iters >= prm.maxiter) return;
+  cg_finish(sc, prm, sc->sums[0], sc->sums[1], sc->sums[2]);
+}
+
+__global__ void __launch_bounds__(SPMV_BLOCK) k_cg_spmv(const int32_t* __restrict__ rowptr,
+                                                        const int32_t* __restrict__ colidx,
+                                                        const double* __restrict__ vals, int64_t n_nodes,
+                                                        const double* __restrict__ u, const double* __restrict__ r,
+                                                        double* __restrict__ w, PcgScalars* __restrict__ sc,
+                                                        double* __restrict__ partials, PcgParams prm) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane / 6, rr_ = lane - g * 6;
+  const int64_t warp = (int64_t)blockIdx.x * (SPMV_BLOCK / 32) + (threadIdx.x >> 5);
+  const int64_t n = warp * ROWS_PER_WARP + g;
+  const bool active = g < ROWS_PER_WARP && n < n_nodes;
+  // independent loads first: the row extent and the own-row entries do not depend on the status word
+  int lo = 0, hi = 0;
+  double uo = 0.0, ro = 0.0;
+  const int64_t i = n * 6 + rr_;
+  if (active) { lo = __ldg(rowptr + n); hi = __ldg(rowptr + n + 1); uo = u[i]; ro = r[i]; }
+  if (sc->done || sc->iters >= prm.maxiter) return;
+  double acc = 0.0;
+#pragma unroll 4
+  for (int j = lo; j < hi; ++j) {
+    const int c = __ldg(colidx + j);
+    const double2* vp = reinterpret_cast<const double2*>(vals + (int64_t)j * 36 + rr_ * 6);
+    const double2* xp = reinterpret_cast<const double2*>(u + (int64_t)c * 6);
+    const double2 a0 = __ldcs(vp), a1 = __ldcs(vp + 1), a2 = __ldcs(vp + 2);
+    const double2 x0 = xp[0], x1 = xp[1], x2 = xp[2];
+    acc = dot6(a0, a1, a2, x0, x1, x2, acc);
+  }
+  if (active) w[i] = acc;
+  double v[3] = {ro * uo, acc * uo, ro * ro}, out[3];
+  if (grid_reduce<3, SPMV_BLOCK>(v, partials, &sc->counter[1], out)) {
+    if (prm.dist) { sc->sums[0] = out[0]; sc->sums[1] = out[1]; sc->sums[2] = out[2]; }
+    else cg_finish(sc, prm, out[0], out[1], out[2]);
+  }
+}
+
+template <int PC>
+__global__ void __launch_bounds__(SPMV_BLOCK) k_cg_update(int64_t n_nodes, const double* __restrict__ dinv,
+                                                          double* __restrict__ x, double* __restrict__ r,
+                                                          double* __restrict__ u, const double* __restrict__ w,
+                                                          double* __restrict__ p, double* __restrict__ s,
+                                                          const PcgScalars* __restrict__ sc, PcgParams prm) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane / 6, rr_ = lane - g * 6;
+  const int64_t warp = (int64_t)blockIdx.x * (SPMV_BLOCK / 32) + (threadIdx.x >> 5);
+  const int64_t n = warp * ROWS_PER_WARP + g;
+  const bool active = g < ROWS_PER_WARP && n < n_nodes;
+  const int64_t i = n * 6 + rr_;
+  double uv = 0.0, wv = 0.0, pv = 0.0, sv = 0.0, xv = 0.0, rv = 0.0;
+  if (active) { uv = u[i]; wv = w[i]; pv = p[i]; sv = s[i]; xv = x[i]; rv = r[i]; }
+  if (sc->done || sc->iters >= prm.maxiter) return;
+  const double alpha = sc->alpha, beta = sc->beta;
+  pv = fma(beta, pv, uv);
+  sv = fma(beta, sv, wv);
+  xv = fma(alpha, pv, xv);
+  rv = fma(-alpha, sv, rv);
+  const double zn = apply_precond<PC>(dinv, n, g, rr_, active, rv);
+  if (active) { p[i] = pv; s[i] = sv; x[i] = xv; r[i] = rv; u[i] = zn; }
+}
+
+// init for the CG variant: x = 0, r = b, u = M^-1 b, p = s = 0
+template <int PC>
+__global__ void __launch_bounds__(SPMV_BLOCK) k_cg_init(int64_t n_nodes, const double* __restrict__ b,
+                                                        const double* __restrict__ dinv, double* __restrict__ x,
+                                                        double* __restrict__ r, double* __restrict__ u,
+                                                        double* __restrict__ p, double* __restrict__ s) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane / 6, rr_ = lane - g * 6;
+  const int64_t warp = (int64_t)blockIdx.x * (SPMV_BLOCK / 32) + (threadIdx.x >> 5);
+  const int64_t n = warp * ROWS_PER_WARP + g;
+  const bool active = g < ROWS_PER_WARP && n < n_nodes;
+  const int64_t i = n * 6 + rr_;
+  const double bv = active ? b[i] : 0.0;
+  const double zv = apply_precond<PC>(dinv, n, g, rr_, active, bv);
+  if (active) { x[i] = 0.0; r[i] = bv; u[i] = zv; p[i] = 0.0; s[i] = 0.0; }
+}
+
+// ---------------------------------------------------------------------------
 // TMA-staged SpMV (sm_90+ bulk async copy, used on sm_100a)
 // ---------------------------------------------------------------------------
 // A CTA owns a contiguous range of block rows whose matrix blocks form ONE contiguous
@@ -563,18 +677,41 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
   int check = o->check_every > 0 ? o->check_every : 32;
   if (check > o->maxiter) check = o->maxiter > 0 ? o->maxiter : 1;
 
+  // bit 3 of `reserved` forces the classic two-reduction recurrences in the textbook mode
+  const bool cgv = !o->reference_semantics && !(o->reserved & 8) && !plan.tma;
   auto launch_spmv = [&](cudaStream_t st) {
-    if (plan.tma)
+    if (cgv)
+      k_cg_spmv<<<grid, SPMV_BLOCK, 0, st>>>(rowptr, colidx, vals, n_nodes, z, r, Ap, sc, partials, prm);
+    else if (plan.tma)
       k_spmv_tma<1><<<plan.grid, SPMV_BLOCK, plan.smem, st>>>(rowptr, colidx, vals, n_nodes, plan.cta_row0,
                                                              plan.cap_blocks, z, pa, pb, Ap, sc, partials, prm);
     else
       k_pcg_spmv<0><<<grid, SPMV_BLOCK, 0, st>>>(rowptr, colidx, vals, n_nodes, z, pa, pb, Ap, sc, partials, prm);
   };
+  auto launch_update = [&](cudaStream_t st) {
+    if (cgv)
+      k_cg_update<PC><<<grid, SPMV_BLOCK, 0, st>>>(n_nodes, dinv, x, r, z, Ap, pa, pb, sc, prm);
+    else
+      k_pcg_update<PC><<<grid, SPMV_BLOCK, 0, st>>>(n_nodes, dinv, x, r, z, pa, pb, Ap, sc, partials, prm);
+  };
+  // one iteration = (spmv, update) in the classic form, (update, spmv) in the Chronopoulos-Gear form
+  auto launch_iteration = [&](cudaStream_t st) {
+    if (cgv) { launch_update(st); launch_spmv(st); }
+    else { launch_spmv(st); launch_update(st); }
+  };
   LAT_CUDA(ctx, cudaMemsetAsync(sc, 0, sizeof(PcgScalars), ctx->stream));
   if (PC != LAT_PC_NONE)
     LAT_LAUNCH(ctx, k_precond_setup, (unsigned)ceil_div(n_nodes, 128), 128, 0, rowptr, colidx, vals, n_nodes, PC, dinv);
   LAT_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-  LAT_LAUNCH(ctx, k_pcg_init<PC>, grid, SPMV_BLOCK, 0, n_nodes, b, dinv, x, r, z, pa, pb, sc, partials, 0);
+  if (cgv) {
+    const int32_t one = 1;
+    LAT_CUDA(ctx, cudaMemcpyAsync(&sc->first, &one, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    LAT_LAUNCH(ctx, k_cg_init<PC>, grid, SPMV_BLOCK, 0, n_nodes, b, dinv, x, r, z, pa, pb);
+    launch_spmv(ctx->stream);  // set-up pass: w0 = A u0, gamma0, delta0, |b|^2
+    ctx->launches++;
+  } else {
+    LAT_LAUNCH(ctx, k_pcg_init<PC>, grid, SPMV_BLOCK, 0, n_nodes, b, dinv, x, r, z, pa, pb, sc, partials, 0);
+  }
 
   // one CUDA graph = `check` iterations (2 kernels each); relaunched until the device reports done
   cudaGraph_t graph = nullptr;
@@ -583,10 +720,7 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
   LAT_CUDA(ctx, cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
   cudaError_t ce = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
   if (ce == cudaSuccess) {
-    for (int it = 0; it < check; ++it) {
-      launch_spmv(cap);
-      k_pcg_update<PC><<<grid, SPMV_BLOCK, 0, cap>>>(n_nodes, dinv, x, r, z, pa, pb, Ap, sc, partials, prm);
-    }
+    for (int it = 0; it < check; ++it) launch_iteration(cap);
     ce = cudaStreamEndCapture(cap, &graph);
   }
   if (ce == cudaSuccess) ce = cudaGraphInstantiate(&gexec, graph, 0);
@@ -603,22 +737,39 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
   if (nprof > 256) nprof = 256;
   double spmv_ms = 0.0, update_ms = 0.0;
   if (nprof > 0) {
-    std::vector<cudaEvent_t> evs(3 * nprof);
+    std::vector<cudaEvent_t> evs(3 * nprof), evs_end(nprof);
     for (auto& e : evs) cudaEventCreate(&e);
+    for (auto& e : evs_end) cudaEventCreate(&e);
     for (int it = 0; it < nprof; ++it) {
-      cudaEventRecord(evs[3 * it], ctx->stream);
-      launch_spmv(ctx->stream);
-      cudaEventRecord(evs[3 * it + 1], ctx->stream);
-      k_pcg_update<PC><<<grid, SPMV_BLOCK, 0, ctx->stream>>>(n_nodes, dinv, x, r, z, pa, pb, Ap, sc, partials, prm);
-      cudaEventRecord(evs[3 * it + 2], ctx->stream);
+      // events bracket each kernel; slot 0->1 is always the SpMV kernel, 1->2 / 2->0' the update kernel
+      if (cgv) {
+        cudaEventRecord(evs[3 * it + 1], ctx->stream);
+        launch_update(ctx->stream);
+        cudaEventRecord(evs[3 * it + 2], ctx->stream);
+        cudaEventRecord(evs[3 * it], ctx->stream);
+        launch_spmv(ctx->stream);
+        // the closing event of the SpMV is recorded into a reused slot below
+      } else {
+        cudaEventRecord(evs[3 * it], ctx->stream);
+        launch_spmv(ctx->stream);
+        cudaEventRecord(evs[3 * it + 1], ctx->stream);
+        launch_update(ctx->stream);
+        cudaEventRecord(evs[3 * it + 2], ctx->stream);
+      }
+      if (cgv) cudaEventRecord(evs_end[it], ctx->stream);
       ctx->launches += 2;
     }
     ce = cudaStreamSynchronize(ctx->stream);
     if (ce == cudaSuccess) {
       for (int it = 0; it < nprof; ++it) {
         float a = 0.f, b2 = 0.f;
-        cudaEventElapsedTime(&a, evs[3 * it], evs[3 * it + 1]);
-        cudaEventElapsedTime(&b2, evs[3 * it + 1], evs[3 * it + 2]);
+        if (cgv) {
+          cudaEventElapsedTime(&a, evs[3 * it], evs_end[it]);            // SpMV kernel
+          cudaEventElapsedTime(&b2, evs[3 * it + 1], evs[3 * it + 2]);   // update kernel
+        } else {
+          cudaEventElapsedTime(&a, evs[3 * it], evs[3 * it + 1]);
+          cudaEventElapsedTime(&b2, evs[3 * it + 1], evs[3 * it + 2]);
+        }
         spmv_ms += a;
         update_ms += b2;
       }
@@ -626,6 +777,7 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
       update_ms /= nprof;
     }
     for (auto& e : evs) cudaEventDestroy(e);
+    for (auto& e : evs_end) cudaEventDestroy(e);
     if (ce != cudaSuccess) rc = lat_cuda_fail(ctx, ce, "PCG profiled iterations", __FILE__, __LINE__);
   }
   const int remaining = o->maxiter - nprof;

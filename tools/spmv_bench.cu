@@ -85,11 +85,87 @@ __global__ void __launch_bounds__(256) k_flat(const int* __restrict__ rowptr, co
   for (int i = threadIdx.x; i < nrow * 6; i += 256) { y[(long)row0 * 6 + i] = s_y[i]; if (MODE == 2) y2[(long)row0 * 6 + i] = 0.5 * s_y[i]; }
 }
 
+// Chunked variant: CH blocks of a row are loaded back to back (clamped indices, zero weights past the end)
+// before any is consumed -> CH*6 independent 16 B loads in flight per lane even for 3-block rows.
+template <int CH, int DOTS>
+__global__ void __launch_bounds__(256) k_chunk(const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                                                const double* __restrict__ vals, int n_nodes, const double* __restrict__ x,
+                                                const double* __restrict__ rr, double* __restrict__ y, double* __restrict__ part) {
+  const int lane = threadIdx.x & 31, g = lane / 6, r = lane - g * 6;
+  const long warp = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long n = warp * 5 + g;
+  const bool active = g < 5 && n < n_nodes;
+  double acc = 0, d0 = 0, d1 = 0, d2 = 0;
+  if (active) {
+    const int lo = rowptr[n], hi = rowptr[n + 1];
+    for (int j = lo; j < hi; j += CH) {
+      double2 a[CH][3], xv[CH][3];
+#pragma unroll
+      for (int k = 0; k < CH; ++k) {
+        const int jj = min(j + k, hi - 1);
+        const int c = __ldg(colidx + jj);
+        const double2* vp = reinterpret_cast<const double2*>(vals + (long)jj * 36 + r * 6);
+        const double2* xp = reinterpret_cast<const double2*>(x + (long)c * 6);
+        a[k][0] = __ldcs(vp); a[k][1] = __ldcs(vp + 1); a[k][2] = __ldcs(vp + 2);
+        xv[k][0] = __ldg(xp); xv[k][1] = __ldg(xp + 1); xv[k][2] = __ldg(xp + 2);
+      }
+#pragma unroll
+      for (int k = 0; k < CH; ++k) {
+        double t = a[k][0].x * xv[k][0].x + a[k][0].y * xv[k][0].y + a[k][1].x * xv[k][1].x + a[k][1].y * xv[k][1].y +
+                   a[k][2].x * xv[k][2].x + a[k][2].y * xv[k][2].y;
+        acc += (j + k < hi) ? t : 0.0;
+      }
+    }
+    const long i = n * 6 + r;
+    y[i] = acc;
+    if (DOTS) { const double u = x[i], rv = rr[i]; d0 = rv * u; d1 = acc * u; d2 = rv * rv; }
+  }
+  if (DOTS) {
+    // block reduction + partials (no last-block pass here: measures the cheap part of the epilogue)
+    __shared__ double sp[3][8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { d0 += __shfl_xor_sync(~0u, d0, o); d1 += __shfl_xor_sync(~0u, d1, o); d2 += __shfl_xor_sync(~0u, d2, o); }
+    if (lane == 0) { sp[0][threadIdx.x >> 5] = d0; sp[1][threadIdx.x >> 5] = d1; sp[2][threadIdx.x >> 5] = d2; }
+    __syncthreads();
+    if (threadIdx.x < 3) { double s2 = 0; for (int k = 0; k < 8; ++k) s2 += sp[threadIdx.x][k]; part[threadIdx.x * gridDim.x + blockIdx.x] = s2; }
+  }
+}
+
+// Persistent variant: grid = SMs x k CTAs; each CTA owns a contiguous range of rows (equal nnz), warps walk it
+// in tiles of 5 rows.  MODE as above.
+template <int MODE, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_persist(const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                                                      const double* __restrict__ vals, int n_nodes, const int* __restrict__ cta_row0,
+                                                      const double* __restrict__ x, const double* __restrict__ x2,
+                                                      double* __restrict__ y, double* __restrict__ y2) {
+  const int lane = threadIdx.x & 31, g = lane / 6, r = lane - g * 6;
+  const int r0 = cta_row0[blockIdx.x], r1 = cta_row0[blockIdx.x + 1];
+  for (int base = r0 + (threadIdx.x >> 5) * 5; base < r1; base += (THREADS / 32) * 5) {
+    const int n = base + g;
+    if (g >= 5 || n >= r1) continue;
+    const int lo = rowptr[n], hi = rowptr[n + 1];
+    double acc = 0;
+#pragma unroll 4
+    for (int j = lo; j < hi; ++j) {
+      const double2* vp = reinterpret_cast<const double2*>(vals + (long)j * 36 + r * 6);
+      const double2 a0 = __ldcs(vp), a1 = __ldcs(vp + 1), a2 = __ldcs(vp + 2);
+      if (MODE == 0) { acc += a0.x + a0.y + a1.x + a1.y + a2.x + a2.y; continue; }
+      const int c = __ldg(colidx + j);
+      const double2* xp = reinterpret_cast<const double2*>(x + (long)c * 6);
+      double2 x0 = __ldg(xp), x1 = __ldg(xp + 1), x2v = __ldg(xp + 2);
+      acc += a0.x * x0.x + a0.y * x0.y + a1.x * x1.x + a1.y * x1.y + a2.x * x2v.x + a2.y * x2v.y;
+    }
+    y[(long)n * 6 + r] = acc;
+  }
+}
+
 int main(int argc, char** argv) {
   int N = argc > 1 ? atoi(argv[1]) : 440000; int NB = argc > 2 ? atoi(argv[2]) : 9;
   std::vector<int> rp(N + 1), ci; rp[0] = 0;
+  const bool lattice_like = NB < 0;   // NB < 0: BCC m=2 like structure: first 21% rows have 9 blocks, the rest 3
   for (int i = 0; i < N; ++i) {
     std::vector<int> c;
+    if (lattice_like) NB = (i < (int)(0.2124 * N)) ? 9 : 3;
     for (int k = 0; k < NB; ++k) { long o = (long)i + (k - NB / 2) * 997L; o = ((o % N) + N) % N; c.push_back((int)o); }
     std::sort(c.begin(), c.end()); c.erase(std::unique(c.begin(), c.end()), c.end());
     for (int v : c) ci.push_back(v); rp[i + 1] = (int)ci.size();
@@ -119,5 +195,34 @@ int main(int argc, char** argv) {
   timeit("flat matrix only", [&] { k_flat<0><<<gridf, 256>>>(drp, dci, vals, N, x, x2, y, y2); }, bytes_m);
   timeit("flat spmv", [&] { k_flat<1><<<gridf, 256>>>(drp, dci, vals, N, x, x2, y, y2); }, bytes_1);
   timeit("flat pcg-like", [&] { k_flat<2><<<gridf, 256>>>(drp, dci, vals, N, x, x2, y, y2); }, bytes_2);
+  double* part; CK(cudaMalloc(&part, 3 * (grid + 1) * 8));
+  double bytes_c = nnzb * 292.0 + N * (4 + 3 * 48.0);
+  timeit("chunk2 spmv", [&] { k_chunk<2, 0><<<grid, 256>>>(drp, dci, vals, N, x, x2, y, part); }, bytes_1);
+  timeit("chunk3 spmv", [&] { k_chunk<3, 0><<<grid, 256>>>(drp, dci, vals, N, x, x2, y, part); }, bytes_1);
+  timeit("chunk4 spmv", [&] { k_chunk<4, 0><<<grid, 256>>>(drp, dci, vals, N, x, x2, y, part); }, bytes_1);
+  timeit("chunk3 spmv + 3 dots", [&] { k_chunk<3, 1><<<grid, 256>>>(drp, dci, vals, N, x, x2, y, part); }, bytes_c);
+  timeit("chunk4 spmv + 3 dots", [&] { k_chunk<4, 1><<<grid, 256>>>(drp, dci, vals, N, x, x2, y, part); }, bytes_c);
+  if (argc > 3) return 0;
+  // persistent variants
+  for (int k : {2, 4}) {
+    for (int threads : {256, 512}) {
+      int G = 148 * k;
+      std::vector<int> c0(G + 1);
+      for (int i = 0; i <= G; ++i) {
+        long target = (long)nnzb * i / G;
+        int r = (int)(std::lower_bound(rp.begin(), rp.end(), (int)target) - rp.begin());
+        c0[i] = i == G ? N : std::min(r, N);
+      }
+      int* dc0; CK(cudaMalloc(&dc0, (G + 1) * 4)); CK(cudaMemcpy(dc0, c0.data(), (G + 1) * 4, cudaMemcpyHostToDevice));
+      char nm[64];
+      snprintf(nm, 64, "persist k=%d t=%d matrix", k, threads);
+      if (threads == 256) timeit(nm, [&] { k_persist<0, 256><<<G, 256>>>(drp, dci, vals, N, dc0, x, x2, y, y2); }, bytes_m);
+      else timeit(nm, [&] { k_persist<0, 512><<<G, 512>>>(drp, dci, vals, N, dc0, x, x2, y, y2); }, bytes_m);
+      snprintf(nm, 64, "persist k=%d t=%d spmv", k, threads);
+      if (threads == 256) timeit(nm, [&] { k_persist<1, 256><<<G, 256>>>(drp, dci, vals, N, dc0, x, x2, y, y2); }, bytes_1);
+      else timeit(nm, [&] { k_persist<1, 512><<<G, 512>>>(drp, dci, vals, N, dc0, x, x2, y, y2); }, bytes_1);
+      cudaFree(dc0);
+    }
+  }
   return 0;
 }
