@@ -83,10 +83,12 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// Deterministic grid reduction of NV values: every block writes its partial sums,
-// the last block to finish (ticket counter) adds the partials in a fixed order.
-// Returns true in thread 0 of that last block, with the totals in out[].
-// partials: [NV][gridDim.x].  All threads of the block must call this.
+// Deterministic grid reduction of NV values: every block writes its partial sums, the last block
+// to finish (ticket counter) adds the partials in a fixed order.  Returns true in thread 0 of that
+// last block, with the totals in out[].  partials: [NV][gridDim.x].  All threads must call this.
+// Cost note (profiles/r01_fence_ab.txt): the gpu-scope release before the ticket keeps every CTA
+// resident ~1.5 us longer; kernels on the critical path of the PCG iteration therefore use
+// block_partials() + a separate one-CTA reduce kernel instead.
 template <int NV, int BLOCK>
 __device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* partials, unsigned int* ticket,
                                             double (&out)[NV]) {
@@ -106,14 +108,16 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* partials, u
       for (int k = 0; k < BLOCK / 32; ++k) s += s_part[i][k];
       partials[(size_t)i * gridDim.x + blockIdx.x] = s;
     }
-    __threadfence();
-    unsigned int t = atomicAdd(ticket, 1u);
+    // RELEASE ticket: orders this thread's partial stores before the increment (MEMBAR.ALL.GPU +
+    // ATOMG) without the CCTL.IVALL L1 invalidate that __threadfence() adds on sm_100
+    unsigned int t;
+    asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(ticket) : "memory");
     s_last = (t == gridDim.x - 1);
   }
   __syncthreads();
   if (!s_last) return false;
-  // last block: fixed-order tree over the partials (independent of arrival order)
-  __threadfence();
+  // last block only: acquire, then a fixed-order tree over the partials (independent of arrival order)
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     double s = 0.0;
@@ -134,6 +138,48 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* partials, u
     return true;
   }
   return false;
+}
+
+// Block-level half of the reduction only: partials[i][blockIdx.x] = sum over the CTA of v[i].
+// Plain stores, no ordering needed -- the consumer is a later kernel.
+template <int NV, int BLOCK>
+__device__ __forceinline__ void block_partials(double (&v)[NV], double* partials) {
+  __shared__ double s_bp[NV][BLOCK / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double w = warp_sum(v[i]);
+    if (lane == 0) s_bp[i][wid] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < BLOCK / 32; ++k) s += s_bp[threadIdx.x][k];
+    partials[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = s;
+  }
+}
+
+// Fixed-order sum of partials[NV][n_part] by ONE CTA of BLOCK threads; totals valid in thread 0.
+template <int NV, int BLOCK>
+__device__ __forceinline__ void sum_partials(const double* __restrict__ partials, int n_part, double (&out)[NV]) {
+  __shared__ double s_sp[NV][BLOCK / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double s = 0.0;
+    for (int k = threadIdx.x; k < n_part; k += BLOCK) s += partials[(size_t)i * n_part + k];
+    s = warp_sum(s);
+    if (lane == 0) s_sp[i][wid] = s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double s = 0.0;
+    if (threadIdx.x == 0)
+      for (int k = 0; k < BLOCK / 32; ++k) s += s_sp[i][k];
+    out[i] = s;
+  }
 }
 
 // Coefficients that define the 12x12 stiffness of one element in global axes.

@@ -392,8 +392,17 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_cg_spmv(const int32_t* __restric
     acc = dot6(a0, a1, a2, x0, x1, x2, acc);
   }
   if (active) w[i] = acc;
-  double v[3] = {ro * uo, acc * uo, ro * ro}, out[3];
-  if (grid_reduce<3, SPMV_BLOCK>(v, partials, &sc->counter[1], out)) {
+  double v[3] = {ro * uo, acc * uo, ro * ro};
+  block_partials<3, SPMV_BLOCK>(v, partials);
+}
+
+// One CTA: fixed-order sum of the per-CTA partials, then the scalar recurrences / stop test.
+__global__ void __launch_bounds__(1024) k_cg_reduce(const double* __restrict__ partials, int n_part,
+                                                    PcgScalars* __restrict__ sc, PcgParams prm) {
+  if (sc->done || sc->iters >= prm.maxiter) return;
+  double out[3];
+  sum_partials<3, 1024>(partials, n_part, out);
+  if (threadIdx.x == 0) {
     if (prm.dist) { sc->sums[0] = out[0]; sc->sums[1] = out[1]; sc->sums[2] = out[2]; }
     else cg_finish(sc, prm, out[0], out[1], out[2]);
   }
@@ -695,8 +704,11 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
       k_pcg_update<PC><<<grid, SPMV_BLOCK, 0, st>>>(n_nodes, dinv, x, r, z, pa, pb, Ap, sc, partials, prm);
   };
   // one iteration = (spmv, update) in the classic form, (update, spmv) in the Chronopoulos-Gear form
+  auto launch_reduce = [&](cudaStream_t st) {
+    if (cgv) k_cg_reduce<<<1, 1024, 0, st>>>(partials, (int)grid, sc, prm);
+  };
   auto launch_iteration = [&](cudaStream_t st) {
-    if (cgv) { launch_update(st); launch_spmv(st); }
+    if (cgv) { launch_update(st); launch_spmv(st); launch_reduce(st); }
     else { launch_spmv(st); launch_update(st); }
   };
   LAT_CUDA(ctx, cudaMemsetAsync(sc, 0, sizeof(PcgScalars), ctx->stream));
@@ -708,7 +720,8 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
     LAT_CUDA(ctx, cudaMemcpyAsync(&sc->first, &one, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     LAT_LAUNCH(ctx, k_cg_init<PC>, grid, SPMV_BLOCK, 0, n_nodes, b, dinv, x, r, z, pa, pb);
     launch_spmv(ctx->stream);  // set-up pass: w0 = A u0, gamma0, delta0, |b|^2
-    ctx->launches++;
+    launch_reduce(ctx->stream);
+    ctx->launches += 2;
   } else {
     LAT_LAUNCH(ctx, k_pcg_init<PC>, grid, SPMV_BLOCK, 0, n_nodes, b, dinv, x, r, z, pa, pb, sc, partials, 0);
   }
@@ -748,7 +761,9 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
         cudaEventRecord(evs[3 * it + 2], ctx->stream);
         cudaEventRecord(evs[3 * it], ctx->stream);
         launch_spmv(ctx->stream);
-        // the closing event of the SpMV is recorded into a reused slot below
+        cudaEventRecord(evs_end[it], ctx->stream);   // closes the SpMV kernel; the reduce kernel is timed apart
+        launch_reduce(ctx->stream);
+        ++ctx->launches;
       } else {
         cudaEventRecord(evs[3 * it], ctx->stream);
         launch_spmv(ctx->stream);
@@ -756,7 +771,6 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
         launch_update(ctx->stream);
         cudaEventRecord(evs[3 * it + 2], ctx->stream);
       }
-      if (cgv) cudaEventRecord(evs_end[it], ctx->stream);
       ctx->launches += 2;
     }
     ce = cudaStreamSynchronize(ctx->stream);
@@ -792,7 +806,7 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
     while (launched < nbatch && launched - checked < 2) {
       ce = cudaGraphLaunch(gexec, ctx->stream);
       if (ce != cudaSuccess) { rc = lat_cuda_fail(ctx, ce, "cudaGraphLaunch", __FILE__, __LINE__); break; }
-      ctx->launches += 2 * check;
+      ctx->launches += (cgv ? 3 : 2) * check;
       cudaMemcpyAsync(&hs[launched & 1], sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, ctx->stream);
       cudaEventRecord(ctx->ev[2 + (launched & 1)], ctx->stream);
       ++launched;

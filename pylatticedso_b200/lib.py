@@ -236,12 +236,12 @@ class Context:
 
     def pcg(self, rowptr, colidx, vals, b, x=None, tol=1e-8, maxiter=10000, precond=PC_JACOBI,
             reference_semantics=False, mintol=0.0, alpha_max=0.0, restart_every=0, check_every=0,
-            profile_iters=0, tma_spmv=False, classic=False):
+            profile_iters=0, tma_spmv=False, classic=False, debug=0):
         import torch
         if x is None:
             x = torch.empty_like(b)
         o = PcgOpts(tol, mintol, alpha_max, restart_every, maxiter, precond, int(reference_semantics), check_every,
-                    profile_iters, (2 if tma_spmv else 0) | (8 if classic else 0))
+                    profile_iters, (2 if tma_spmv else 0) | (8 if classic else 0) | (debug << 8))
         r = PcgResult()
         self.check(self.lib.lat_pcg_bsr(self.h, _ptr(rowptr), _ptr(colidx), _ptr(vals), rowptr.numel() - 1, _ptr(b),
                                         _ptr(x), C.byref(o), C.byref(r)))

@@ -161,8 +161,18 @@ __global__ void __launch_bounds__(THREADS) k_persist(const int* __restrict__ row
 
 int main(int argc, char** argv) {
   int N = argc > 1 ? atoi(argv[1]) : 440000; int NB = argc > 2 ? atoi(argv[2]) : 9;
-  std::vector<int> rp(N + 1), ci; rp[0] = 0;
-  const bool lattice_like = NB < 0;   // NB < 0: BCC m=2 like structure: first 21% rows have 9 blocks, the rest 3
+  std::vector<int> rp, ci;
+  bool from_file = false;
+  if (argc > 1 && atoi(argv[1]) == 0) {   // argv[1] = pattern file: int32 N, int32 nnzb, rowptr[N+1], colidx[nnzb]
+    FILE* f = fopen(argv[1], "rb"); if (!f) { printf("cannot open %s\n", argv[1]); return 1; }
+    int hdr[2]; if (fread(hdr, 4, 2, f) != 2) return 1; N = hdr[0];
+    rp.resize(N + 1); ci.resize(hdr[1]);
+    if (fread(rp.data(), 4, N + 1, f) != (size_t)N + 1 || fread(ci.data(), 4, hdr[1], f) != (size_t)hdr[1]) return 1;
+    fclose(f); from_file = true;
+  }
+  if (!from_file) { rp.assign(N + 1, 0); }
+  const bool lattice_like = NB < 0;
+  if (!from_file)   // NB < 0: BCC m=2 like structure: first 21% rows have 9 blocks, the rest 3
   for (int i = 0; i < N; ++i) {
     std::vector<int> c;
     if (lattice_like) NB = (i < (int)(0.2124 * N)) ? 9 : 3;
