@@ -13,7 +13,7 @@ value  = PCG DOF-iterations / s = n_dof * iterations / device time of the WHOLE 
          (assembly, elimination and reactions included), inputs resident in HBM.
 e2e    = the same quantity through the host-facing API (host numpy buffers in pinned
          memory -> H2D of the mesh and BCs, pattern reuse, step, D2H of u and R).
-roofline = the dominant kernel (k_pcg_spmv: fused p-update + BSR SpMV + dots),
+roofline = the dominant kernel (k_cg_spmv: BSR SpMV fused with the three CG dot products),
          timed live with CUDA events on the library stream during the timed steps.
 
 Multi-GPU (N > 1): weak scaling, one process per GPU; the lattice is extended to
@@ -111,9 +111,10 @@ def build_workload(n_slabs=1):
 
 
 def spmv_bytes(n_nodes, nnzb):
-    """Algorithmic bytes of one k_pcg_spmv launch: matrix 288 B + column index 4 B per
-    block; per block row 4 B rowptr, 48 B z + 48 B p_old read, 48 B p_new + 48 B Ap written."""
-    return nnzb * 292 + n_nodes * (4 + 4 * 48)
+    """Algorithmic bytes of one k_cg_spmv launch: matrix 288 B + column index 4 B per
+    block; per block row 4 B rowptr, 48 B u (the gathered vector, counted once) + 48 B r read,
+    48 B w = A u written."""
+    return nnzb * 292 + n_nodes * (4 + 3 * 48)
 
 
 def iteration_bytes(n_nodes, nnzb, block_jacobi=True):
@@ -364,7 +365,7 @@ def run_b200(args):
                      "pattern_build_ms_one_off": res.get("pattern_ms")},
         "pcg": {"solve_ms_per_step": res["solve_ms"] / args.steps, "iteration_GBps_survey_bytes": it_gbs,
                 "iteration_frac_of_hbm": it_gbs / (hbm_peak * world), "update_kernel_ms": res["update_ms"]},
-        "roofline": {"kernel": "k_pcg_spmv (fused p = z + beta p, BSR 6x6 SpMV, p.Ap, p.p)", "bound": "hbm",
+        "roofline": {"kernel": "k_cg_spmv (BSR 6x6 SpMV w = A u fused with the partial sums of (r,u), (w,u), (r,r))", "bound": "hbm",
                      "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": (ach / hbm_peak) if ach else None, "traffic": None,
                      "peak_source": peak_src, "bytes_per_launch": spmv_bytes(nn, nz),
                      "avg_launch_ms": res["spmv_ms"], "launches_timed": res["nprof"],

@@ -170,7 +170,7 @@ int lat_pcg_bsr(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, cons
  * OWNS (n_owned, complete rows) over a local column space [owned nodes | ghost nodes]; ghost nodes are
  * ordered by owner rank (the order of `peer`), then by global node id, so a received halo lands
  * contiguously.  Per PCG iteration: one halo exchange of z (ncclSend/ncclRecv with the <= 2 slab
- * neighbours) and two all-reduces of 2 and 4 doubles (p.Ap, p.p | r.z, r.r, x.x, restart norm). */
+ * neighbours) of u = M^-1 r and ONE all-reduce of 3 doubles ((r,u), (Au,u), (r,r); Chronopoulos-Gear form). */
 typedef struct {
   int32_t n_neighbors;
   int32_t pad;

@@ -1015,76 +1015,66 @@ extern "C" int lat_halo_exchange(lat_ctx* ctx, const lat_halo* halo, double* vec
 template <int PC>
 static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, const double* vals,
                         const lat_halo* h, const double* b, double* x, const lat_pcg_opts* o, lat_pcg_result* res) {
+  // Chronopoulos-Gear arrangement: per iteration ONE halo exchange (u) and ONE all-reduce (3 doubles).
   const int64_t n_own = h->n_owned, n_loc = h->n_local;
   const int64_t n = 6 * n_loc;
   const unsigned grid = (unsigned)ceil_div(n_own, ROWS_PER_CTA);
   double* r = lat_buf<double>(ctx, "pcg_r", n);
-  double* z = lat_buf<double>(ctx, "pcg_z", n);
-  double* pa = lat_buf<double>(ctx, "pcg_pa", n);
-  double* pb = lat_buf<double>(ctx, "pcg_pb", n);
-  double* Ap = lat_buf<double>(ctx, "pcg_Ap", n);
+  double* u = lat_buf<double>(ctx, "pcg_z", n);
+  double* p = lat_buf<double>(ctx, "pcg_pa", n);
+  double* sv = lat_buf<double>(ctx, "pcg_pb", n);
+  double* w = lat_buf<double>(ctx, "pcg_Ap", n);
   double* dinv = lat_buf<double>(ctx, "pcg_dinv", PC == LAT_PC_BLOCK6 ? 36 * n_own : 6 * n_own);
   double* partials = lat_buf<double>(ctx, "pcg_partials", (size_t)4 * grid + 8);
   PcgScalars* sc = lat_buf<PcgScalars>(ctx, "pcg_scalars", 1);
-  if (!r || !z || !pa || !pb || !Ap || !dinv || !partials || !sc)
+  if (!r || !u || !p || !sv || !w || !dinv || !partials || !sc)
     return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+  if (o->reference_semantics)
+    return lat_fail(ctx, LAT_ERR_UNSUPPORTED, "reference_semantics is single-GPU only", __FILE__, __LINE__);
   const int64_t launches0 = ctx->launches;
   PcgParams prm;
-  prm.tol = o->tol; prm.mintol = o->mintol; prm.alpha_max = o->alpha_max; prm.restart_every = o->restart_every;
-  prm.maxiter = o->maxiter; prm.reference = o->reference_semantics; prm.dist = 1; prm.pad = 0;
+  prm.tol = o->tol; prm.mintol = 0.0; prm.alpha_max = 0.0; prm.restart_every = 0;
+  prm.maxiter = o->maxiter; prm.reference = 0; prm.dist = 1; prm.pad = 0;
   int check = o->check_every > 0 ? o->check_every : 32;
-  const int64_t g0 = 6 * n_own, g1 = 6 * n_loc;  // ghost DOF range
-  const unsigned ggrid = (unsigned)ceil_div(g1 - g0 > 0 ? g1 - g0 : 1, 256);
-
+  const bool multi = ctx->nranks > 1 && ctx->nccl_comm != nullptr;
+  {  // the halo send buffer must exist before any stream capture (allocation is not capturable)
+    int64_t tot_send = 0;
+    for (int i = 0; i < h->n_neighbors; ++i) tot_send += h->send_count[i];
+    if (!lat_buf<double>(ctx, "halo_send", (size_t)tot_send * 6 + 8))
+      return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+  }
   LAT_CUDA(ctx, cudaMemsetAsync(sc, 0, sizeof(PcgScalars), ctx->stream));
-  LAT_CUDA(ctx, cudaMemsetAsync(z, 0, n * sizeof(double), ctx->stream));
-  LAT_CUDA(ctx, cudaMemsetAsync(pa, 0, n * sizeof(double), ctx->stream));
-  LAT_CUDA(ctx, cudaMemsetAsync(pb, 0, n * sizeof(double), ctx->stream));
+  const int32_t one = 1;
+  LAT_CUDA(ctx, cudaMemcpyAsync(&sc->first, &one, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  LAT_CUDA(ctx, cudaMemsetAsync(u, 0, n * sizeof(double), ctx->stream));
   if (PC != LAT_PC_NONE)
     LAT_LAUNCH(ctx, k_precond_setup, (unsigned)ceil_div(n_own, 128), 128, 0, rowptr, colidx, vals, n_own, PC, dinv);
   LAT_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-  LAT_LAUNCH(ctx, k_pcg_init<PC>, grid, SPMV_BLOCK, 0, n_own, b, dinv, x, r, z, pa, pb, sc, partials, 1);
-  int rc = lat_allreduce_sum(ctx, sc->sums, 2);
-  if (rc) return rc;
-  LAT_LAUNCH(ctx, k_pcg_finalize_init, 1, 1, 0, sc);
-  rc = halo_exchange(ctx, h, z);
-  if (rc) return rc;
-  PcgScalars* hs = ctx->h_scal;
-  const bool multi = ctx->nranks > 1 && ctx->nccl_comm != nullptr;
-  // one PCG iteration: 5 kernels + (multi-GPU) 2 NCCL launches: all-reduce(p.Ap, p.p), then
-  // {all-reduce(r.z, r.r, x.x, |p|^2) + halo exchange of z} fused in one NCCL group.
-  auto one_iteration = [&]() -> int {
-    LAT_LAUNCH(ctx, k_pcg_spmv<0>, grid, SPMV_BLOCK, 0, rowptr, colidx, vals, n_own, z, pa, pb, Ap, sc, partials, prm);
-    if (g1 > g0) LAT_LAUNCH(ctx, k_pcg_ghost_p, ggrid, 256, 0, g0, g1, z, pa, pb, sc, prm);
-    int rc2 = lat_allreduce_sum(ctx, &sc->pAp, 2);  // pAp, pp are adjacent
+  LAT_LAUNCH(ctx, k_cg_init<PC>, grid, SPMV_BLOCK, 0, n_own, b, dinv, x, r, u, p, sv);
+
+  // halo(u) -> w = A u, partial dots -> local sums -> all-reduce -> scalar recurrences / stop test
+  auto spmv_and_reduce = [&]() -> int {
+    int rc2 = multi ? halo_exchange(ctx, h, u) : LAT_OK;
     if (rc2) return rc2;
-    LAT_LAUNCH(ctx, k_pcg_update<PC>, grid, SPMV_BLOCK, 0, n_own, dinv, x, r, z, pa, pb, Ap, sc, partials, prm);
-    if (multi) {
-      double* sendbuf = nullptr;
-      rc2 = halo_pack(ctx, h, z, &sendbuf);
-      if (rc2) return rc2;
-      LAT_NCCL(ctx, g_nccl.GroupStart());
-      LAT_NCCL(ctx, g_nccl.AllReduce(sc->sums, sc->sums, 4, NCCL_FLOAT64, NCCL_SUM, ctx->nccl_comm, ctx->stream));
-      rc2 = halo_comm(ctx, h, z, sendbuf);
-      if (rc2) { g_nccl.GroupEnd(); return rc2; }
-      LAT_NCCL(ctx, g_nccl.GroupEnd());
-    }
-    LAT_LAUNCH(ctx, k_pcg_finalize_update, 1, 1, 0, sc, prm);
+    LAT_LAUNCH(ctx, k_cg_spmv, grid, SPMV_BLOCK, 0, rowptr, colidx, vals, n_own, u, r, w, sc, partials, prm);
+    LAT_LAUNCH(ctx, k_cg_reduce, 1, 1024, 0, partials, (int)grid, sc, prm);
+    rc2 = lat_allreduce_sum(ctx, sc->sums, 3);
+    if (rc2) return rc2;
+    LAT_LAUNCH(ctx, k_cg_finalize, 1, 1, 0, sc, prm);
     return LAT_OK;
   };
-  // make sure the halo send buffer exists before any capture (allocation is not capturable)
-  {
-    double* sb = nullptr;
-    int64_t tot_send = 0;
-    for (int i = 0; i < h->n_neighbors; ++i) tot_send += h->send_count[i];
-    sb = lat_buf<double>(ctx, "halo_send", (size_t)tot_send * 6 + 8);
-    if (!sb) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
-  }
-  // capture `check` iterations (kernels AND NCCL operations) into one CUDA graph: the host then issues
-  // one graph launch per batch instead of ~8 launches per iteration.
+  auto one_iteration = [&]() -> int {
+    LAT_LAUNCH(ctx, k_cg_update<PC>, grid, SPMV_BLOCK, 0, n_own, dinv, x, r, u, w, p, sv, sc, prm);
+    return spmv_and_reduce();
+  };
+  int rc = spmv_and_reduce();  // set-up pass
+  if (rc) return rc;
+
+  // `check` iterations (kernels AND NCCL operations) are captured into one CUDA graph
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
   bool use_graph = (o->reserved & 4) == 0 && o->maxiter >= check;
+  int64_t per_iter = 0;
   if (use_graph) {
     const int64_t l0 = ctx->launches;
     cudaError_t ce = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
@@ -1093,6 +1083,7 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
       for (int q = 0; q < check && crc == LAT_OK; ++q) crc = one_iteration();
       ce = cudaStreamEndCapture(ctx->stream, &graph);
     }
+    per_iter = (ctx->launches - l0) / check;
     ctx->launches = l0;
     if (ce != cudaSuccess || crc != LAT_OK || graph == nullptr) {
       cudaGetLastError();
@@ -1106,6 +1097,7 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
       use_graph = false;
     }
   }
+  PcgScalars* hs = ctx->h_scal;
   int it = 0;
   bool finished = o->maxiter <= 0;
   while (!finished) {
@@ -1113,7 +1105,7 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
     if (use_graph && batch == check) {
       cudaError_t ce = cudaGraphLaunch(gexec, ctx->stream);
       if (ce != cudaSuccess) { rc = lat_cuda_fail(ctx, ce, "cudaGraphLaunch", __FILE__, __LINE__); break; }
-      ctx->launches += (int64_t)check * (g1 > g0 ? 5 : 4);
+      ctx->launches += per_iter * check;
     } else {
       for (int q = 0; q < batch; ++q) {
         rc = one_iteration();
@@ -1138,7 +1130,7 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
   res->iters = hs[0].iters;
   res->norm_b = sqrt(hs[0].bb);
   res->relres = hs[0].bb > 0.0 ? sqrt(hs[0].rr / hs[0].bb) : 0.0;
-  res->info = hs[0].done && !hs[0].breakdown ? 0 : (hs[0].breakdown ? 3 : (hs[0].info_flag2 ? 2 : 1));
+  res->info = hs[0].done && !hs[0].breakdown ? 0 : (hs[0].breakdown ? 3 : 1);
   res->solve_ms = ms;
   res->launches = ctx->launches - launches0;
   res->spmv_ms = 0.0; res->update_ms = 0.0; res->profiled = 0; res->reserved = 0;
