@@ -213,6 +213,14 @@ def run_b200(args):
         ctx.comm_create(rank, world)
         dfem = D.DistributedFEM(ctx, mesh, E_MOD, NU, rank, world, KAPPA)
         dfem.set_bc(fixed, g, f)
+        comm_mode = "nccl"
+        if not args.nccl:
+            try:
+                dfem.enable_p2p()
+                comm_mode = "nvlink-peer-memory"
+            except Exception as e_:  # still a GPU path: NCCL send/recv + all-reduce
+                if rank == 0:
+                    print(f"bench.py: peer-memory path unavailable ({e_}); using NCCL", file=sys.stderr)
         lm = dfem.lmesh
         host = {k: pin(v) for k, v in dict(x=lm.x, y=lm.y, z=lm.z, en0=lm.en0, en1=lm.en1, rad=lm.rad,
                                            fixed=fixed[dfem.dofs], g=g[dfem.dofs], f=f[dfem.dofs]).items()}
@@ -359,7 +367,8 @@ def run_b200(args):
                    "iterations_per_step": res["iters"] / args.steps,
                    "l2": "L2 flushed (256 MB write) between steps; within a step the 98 MB matrix is re-streamed "
                          "every PCG iteration with evict-first loads (working set ~ L2 size, see DESIGN.md)",
-                   "parallelism": "single" if world == 1 else f"slab{world}"},
+                   "parallelism": "single" if world == 1 else f"slab{world}",
+                   "exchange": None if world == 1 else comm_mode},
         "assembly": {"value": n_elem_global * args.steps / (res["asm_ms"] * 1e-3), "unit": "elements/s",
                      "ms": res["asm_ms"] / args.steps, "mode": "gather (deterministic, fused element generation)",
                      "pattern_build_ms_one_off": res.get("pattern_ms")},
@@ -394,6 +403,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl", action="store_true", help="multi-GPU: NCCL halo/all-reduce instead of NVLink peer memory")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

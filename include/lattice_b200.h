@@ -143,7 +143,8 @@ typedef struct {
   int32_t profile_iters; /* >0: the first profile_iters iterations are launched outside the CUDA graph
                             with CUDA events around each kernel (fills spmv_ms / update_ms) */
   int32_t reserved;      /* bit 1: experimental TMA-staged SpMV kernel; bit 2: no CUDA graph in the multi-GPU path;
-                            bit 3: classic two-reduction recurrences instead of Chronopoulos-Gear (textbook mode) */
+                            bit 3: classic two-reduction recurrences instead of Chronopoulos-Gear (textbook mode);
+                            bit 4 (lat_pcg_bsr_dist): NVLink peer-memory halo/all-reduce instead of NCCL */
 } lat_pcg_opts;
 
 typedef struct {
@@ -191,6 +192,18 @@ int lat_halo_exchange(lat_ctx* ctx, const lat_halo* halo, double* vec);     /* v
 int lat_pcg_bsr_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, const double* vals,
                      const lat_halo* halo, const double* b, double* x, const lat_pcg_opts* opts,
                      lat_pcg_result* result);
+
+/* NVLink peer-memory path (no NCCL inside the iteration): each rank creates one arena (mailboxes, halo
+ * flags and the ghosted vector u), the host layer all-gathers the 64-byte CUDA IPC handles, every rank
+ * maps all arenas.  lat_pcg_bsr_dist with bit 4 of opts.reserved then pushes halos with st.global on the
+ * mapped peer pointers and all-reduces the 3 CG sums through the mailboxes inside its own kernels
+ * (k_p2p_push, k_cg_spmv_p2p, k_p2p_reduce); info = 4 reports a peer time-out.
+ *   nb_rank[k], nb_dst_node0[k]: neighbour k (same order as lat_halo.peer) and the first node index, in
+ *   THAT rank's local numbering, of the ghost segment this rank fills. */
+int lat_p2p_arena_create(lat_ctx* ctx, int64_t n_local, void* handle64);
+int lat_p2p_attach(lat_ctx* ctx, const void* handles /*[nranks][64]*/, int nranks, int rank, int n_neighbors,
+                   const int32_t* nb_rank, const int64_t* nb_dst_node0);
+int lat_p2p_destroy(lat_ctx* ctx);
 
 /* ---- A11: compliance sensitivity ----------------------------------------------
  * g[group[e]] -= chain_e * u_e^T (dK_e/dr)(r_e) u_e   (LatticeOpti.calculate_gradient

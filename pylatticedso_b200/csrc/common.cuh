@@ -21,6 +21,7 @@ struct PcgScalars {
   double sums[4];           // local partial sums awaiting the all-reduce (multi-GPU path)
   double gamma, alpha;      // Chronopoulos-Gear variant: (r,u) and the current step length
   int32_t first, pad;
+  int32_t seq, p2p_timeout; // peer-memory path: sequence number of the last completed reduction
 };
 
 struct lat_ctx {
@@ -39,6 +40,8 @@ struct lat_ctx {
   // multi-GPU
   void* nccl_comm = nullptr;
   int nranks = 1, rank = 0;
+  // NVLink peer-memory path (lat_p2p_*): one arena per rank, mapped into every rank
+  struct P2P* p2p = nullptr;
 };
 
 int lat_fail(lat_ctx* ctx, int code, const char* what, const char* file, int line);

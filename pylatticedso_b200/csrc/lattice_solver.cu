@@ -144,6 +144,7 @@ struct PcgParams {
   int64_t restart_every;
   int32_t maxiter, reference;
   int32_t dist, pad;  // dist = 1: kernels only store LOCAL sums; the host all-reduces and runs k_pcg_finalize_*
+  unsigned long long seq_base;  // peer-memory path: (solve epoch << 32), so flags of earlier solves never match
 };
 
 // Stop tests, beta and bookkeeping of one iteration from the GLOBAL sums (single thread).
@@ -396,12 +397,13 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_cg_spmv(const int32_t* __restric
   block_partials<3, SPMV_BLOCK>(v, partials);
 }
 
+static constexpr int CG_REDUCE_BLOCK = 512;
 // One CTA: fixed-order sum of the per-CTA partials, then the scalar recurrences / stop test.
-__global__ void __launch_bounds__(1024) k_cg_reduce(const double* __restrict__ partials, int n_part,
-                                                    PcgScalars* __restrict__ sc, PcgParams prm) {
-  if (sc->done || sc->iters >= prm.maxiter) return;
+__global__ void __launch_bounds__(CG_REDUCE_BLOCK) k_cg_reduce(const double* __restrict__ partials, int n_part,
+                                                               PcgScalars* __restrict__ sc, PcgParams prm) {
   double out[3];
-  sum_partials<3, 1024>(partials, n_part, out);
+  sum_partials<3, CG_REDUCE_BLOCK>(partials, n_part, out);   // issued before the (dependent) status check
+  if (sc->done || sc->iters >= prm.maxiter) return;
   if (threadIdx.x == 0) {
     if (prm.dist) { sc->sums[0] = out[0]; sc->sums[1] = out[1]; sc->sums[2] = out[2]; }
     else cg_finish(sc, prm, out[0], out[1], out[2]);
@@ -683,6 +685,7 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
   prm.reference = o->reference_semantics;
   prm.dist = 0;
   prm.pad = 0;
+  prm.seq_base = 0;
   int check = o->check_every > 0 ? o->check_every : 32;
   if (check > o->maxiter) check = o->maxiter > 0 ? o->maxiter : 1;
 
@@ -705,7 +708,7 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
   };
   // one iteration = (spmv, update) in the classic form, (update, spmv) in the Chronopoulos-Gear form
   auto launch_reduce = [&](cudaStream_t st) {
-    if (cgv) k_cg_reduce<<<1, 1024, 0, st>>>(partials, (int)grid, sc, prm);
+    if (cgv) k_cg_reduce<<<1, CG_REDUCE_BLOCK, 0, st>>>(partials, (int)grid, sc, prm);
   };
   auto launch_iteration = [&](cudaStream_t st) {
     if (cgv) { launch_update(st); launch_spmv(st); launch_reduce(st); }
@@ -1012,6 +1015,246 @@ extern "C" int lat_halo_exchange(lat_ctx* ctx, const lat_halo* halo, double* vec
   return halo_exchange(ctx, halo, vec);
 }
 
+// ===========================================================================
+// NVLink peer-memory path: halo push and all-reduce INSIDE our own kernels
+// ===========================================================================
+// Every rank owns one cudaMalloc'ed arena, IPC-mapped into all ranks of the node:
+//   [ mailbox: 2 parities x MAXR x {v0,v1,v2,seq} | halo flags: MAXR x uint64 | u: 6 n_local doubles ]
+// * halo:  k_p2p_push stores the owned boundary entries of u straight into the neighbour's ghost section
+//          (st.global on the mapped peer pointer), then publishes the sequence number with a system-scope
+//          release; the neighbour's SpMV kernel acquires it before gathering.
+// * all-reduce: k_p2p_reduce sums the per-CTA partials, writes the 3 local sums into EVERY rank's mailbox
+//          (slot = my rank), releases the sequence number, then spins (bounded) until all slots carry it and
+//          adds them in rank order -- identical bits on every rank, no NCCL launch, ~2-3 us over NVSwitch.
+// All spins are bounded; a timeout sets breakdown = 2 and stops the solve instead of hanging the GPU.
+static constexpr int P2P_MAXR = 16;
+struct P2PMail { double v[3]; unsigned long long seq; };
+struct P2PArenaHdr {
+  P2PMail mail[2][P2P_MAXR];
+  unsigned long long halo_flag[P2P_MAXR];   // indexed by SOURCE rank
+  unsigned long long pad[16];
+};
+struct P2P {
+  int nranks = 1, rank = 0;
+  unsigned long long epoch = 0;
+  unsigned char* arena = nullptr;           // my arena (device pointer)
+  size_t arena_bytes = 0;
+  int64_t n_local = 0;
+  unsigned char* peer[P2P_MAXR] = {nullptr};  // mapped arenas of all ranks (peer[rank] == arena)
+  // per neighbour (halo order): destination ghost offset (nodes) inside the peer's u
+  int n_nb = 0;
+  int nb_rank[P2P_MAXR];
+  int64_t nb_dst_off[P2P_MAXR];
+  bool attached = false;
+  // device copies for kernels
+  unsigned char** d_peer = nullptr;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Push the owned boundary entries of u into the ghost sections of the neighbours, then publish `seq`.
+// send_idx: local node ids, neighbour-major; nb_first[k]..nb_first[k+1]: range of neighbour k.
+struct P2PPushArgs {
+  int n_nb;
+  int nb_rank[4];
+  int nb_first[5];
+  int64_t nb_dst_node0[4];   // first destination node (peer local numbering) of my segment
+  int my_rank;
+};
+__global__ void k_p2p_push(const int32_t* __restrict__ send_idx, const double* __restrict__ u,
+                           unsigned char* const* __restrict__ peers, P2PPushArgs a, size_t u_off,
+                           const PcgScalars* __restrict__ sc, PcgParams prm, unsigned int* __restrict__ cta_done) {
+  if (sc->done || sc->iters >= prm.maxiter) return;
+  const unsigned long long seq = prm.seq_base + (unsigned long long)sc->seq + 1ull;  // sequence of the upcoming SpMV
+  const int total = a.nb_first[a.n_nb];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total * 6; i += gridDim.x * blockDim.x) {
+    const int e = i / 6, d = i - e * 6;
+    int k = 0;
+    while (k + 1 < a.n_nb && e >= a.nb_first[k + 1]) ++k;
+    double* dst = reinterpret_cast<double*>(peers[a.nb_rank[k]] + u_off);
+    dst[(a.nb_dst_node0[k] + (e - a.nb_first[k])) * 6 + d] = u[(int64_t)send_idx[e] * 6 + d];
+  }
+  // last CTA to finish publishes the flags: every thread fences its own peer stores at system scope,
+  // the CTA barrier + ticket chain makes them happen-before the release of the flag
+  __shared__ bool s_last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned int t = atomicAdd(cta_done, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence_system();
+    for (int k = 0; k < a.n_nb; ++k) {
+      P2PArenaHdr* hdr = reinterpret_cast<P2PArenaHdr*>(peers[a.nb_rank[k]]);
+      st_release_sys(&hdr->halo_flag[a.my_rank], seq);
+    }
+    *cta_done = 0u;
+  }
+}
+
+// Block-level wait for the halos of sequence `seq` from all neighbours (thread 0 spins, bounded).
+__device__ __forceinline__ bool p2p_wait_halo(const P2PArenaHdr* hdr, int n_nb, const int* nb_rank, unsigned long long seq) {
+  __shared__ int s_ok;
+  if (threadIdx.x == 0) {
+    int ok = 1;
+    for (int k = 0; k < n_nb; ++k) {
+      long long spins = 0;
+      while (ld_acquire_sys(&hdr->halo_flag[nb_rank[k]]) < seq) {
+        if (++spins > (1ll << 24)) { ok = 0; break; }
+        __nanosleep(20);
+      }
+    }
+    s_ok = ok;
+  }
+  __syncthreads();
+  return s_ok != 0;
+}
+
+struct P2PWaitArgs { int n_nb; int nb_rank[4]; };
+
+// SpMV of the peer-memory path: identical to k_cg_spmv after waiting for the neighbours' halos.
+__global__ void __launch_bounds__(SPMV_BLOCK) k_cg_spmv_p2p(const int32_t* __restrict__ rowptr,
+                                                            const int32_t* __restrict__ colidx,
+                                                            const double* __restrict__ vals, int64_t n_nodes,
+                                                            const double* __restrict__ u, const double* __restrict__ r,
+                                                            double* __restrict__ w, PcgScalars* __restrict__ sc,
+                                                            double* __restrict__ partials, PcgParams prm,
+                                                            const P2PArenaHdr* __restrict__ hdr, P2PWaitArgs wa) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane / 6, rr_ = lane - g * 6;
+  const int64_t warp = (int64_t)blockIdx.x * (SPMV_BLOCK / 32) + (threadIdx.x >> 5);
+  const int64_t n = warp * ROWS_PER_WARP + g;
+  const bool active = g < ROWS_PER_WARP && n < n_nodes;
+  int lo = 0, hi = 0;
+  double uo = 0.0, ro = 0.0;
+  const int64_t i = n * 6 + rr_;
+  if (active) { lo = __ldg(rowptr + n); hi = __ldg(rowptr + n + 1); uo = u[i]; ro = r[i]; }
+  if (sc->done || sc->iters >= prm.maxiter) return;
+  const bool ok = p2p_wait_halo(hdr, wa.n_nb, wa.nb_rank, prm.seq_base + (unsigned long long)sc->seq + 1ull);
+  if (!ok) {
+    if (threadIdx.x == 0) sc->p2p_timeout = 1;
+  }
+  double acc = 0.0;
+#pragma unroll 4
+  for (int j = lo; j < hi; ++j) {
+    const int c = __ldg(colidx + j);
+    const double2* vp = reinterpret_cast<const double2*>(vals + (int64_t)j * 36 + rr_ * 6);
+    const double2* xp = reinterpret_cast<const double2*>(u + (int64_t)c * 6);
+    const double2 a0 = __ldcs(vp), a1 = __ldcs(vp + 1), a2 = __ldcs(vp + 2);
+    const double2 x0 = xp[0], x1 = xp[1], x2 = xp[2];
+    acc = dot6(a0, a1, a2, x0, x1, x2, acc);
+  }
+  if (active) w[i] = acc;
+  double v[3] = {ro * uo, acc * uo, ro * ro};
+  block_partials<3, SPMV_BLOCK>(v, partials);
+}
+
+// One CTA: local sums -> every rank's mailbox -> wait for all -> rank-ordered total -> recurrences.
+__global__ void __launch_bounds__(1024) k_p2p_reduce(const double* __restrict__ partials, int n_part,
+                                                     PcgScalars* __restrict__ sc, PcgParams prm,
+                                                     unsigned char* const* __restrict__ peers, int nranks, int my_rank) {
+  if (sc->done || sc->iters >= prm.maxiter) return;
+  double out[3];
+  sum_partials<3, 1024>(partials, n_part, out);
+  if (threadIdx.x != 0) return;
+  const unsigned long long seq = prm.seq_base + (unsigned long long)sc->seq + 1ull;
+  const int par = (int)(seq & 1ull);
+  for (int q = 0; q < nranks; ++q) {
+    P2PArenaHdr* hdr = reinterpret_cast<P2PArenaHdr*>(peers[q]);
+    P2PMail* m = &hdr->mail[par][my_rank];
+    m->v[0] = out[0]; m->v[1] = out[1]; m->v[2] = out[2];
+  }
+  __threadfence_system();
+  for (int q = 0; q < nranks; ++q) {
+    P2PArenaHdr* hdr = reinterpret_cast<P2PArenaHdr*>(peers[q]);
+    st_release_sys(&hdr->mail[par][my_rank].seq, seq);
+  }
+  const P2PArenaHdr* mine = reinterpret_cast<const P2PArenaHdr*>(peers[my_rank]);
+  double tot[3] = {0.0, 0.0, 0.0};
+  bool ok = !sc->p2p_timeout;
+  for (int q = 0; q < nranks && ok; ++q) {
+    long long spins = 0;
+    while (ld_acquire_sys(&mine->mail[par][q].seq) < seq) {
+      if (++spins > (1ll << 24)) { ok = false; break; }
+      __nanosleep(20);
+    }
+    const volatile double* vv = mine->mail[par][q].v;
+    tot[0] += vv[0]; tot[1] += vv[1]; tot[2] += vv[2];
+  }
+  sc->seq = sc->seq + 1;
+  if (!ok) { sc->done = 1; sc->breakdown = 2; return; }
+  cg_finish(sc, prm, tot[0], tot[1], tot[2]);
+}
+
+extern "C" int lat_p2p_arena_create(lat_ctx* ctx, int64_t n_local, void* handle64) {
+  if (!ctx) return LAT_ERR_ARG;
+  LAT_CHECK_ARG(ctx, n_local > 0 && handle64);
+  LAT_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->p2p) ctx->p2p = new P2P();
+  P2P* p = ctx->p2p;
+  if (p->attached) return lat_fail(ctx, LAT_ERR_STATE, "p2p arena already attached: destroy the comm first", __FILE__, __LINE__);
+  if (p->arena) { cudaFree(p->arena); p->arena = nullptr; }
+  p->arena_bytes = sizeof(P2PArenaHdr) + (size_t)n_local * 6 * sizeof(double) + 256;
+  LAT_CUDA(ctx, cudaMalloc(&p->arena, p->arena_bytes));
+  LAT_CUDA(ctx, cudaMemset(p->arena, 0, p->arena_bytes));
+  p->n_local = n_local;
+  cudaIpcMemHandle_t h;
+  LAT_CUDA(ctx, cudaIpcGetMemHandle(&h, p->arena));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(handle64, &h, 64);
+  return LAT_OK;
+}
+
+extern "C" int lat_p2p_attach(lat_ctx* ctx, const void* handles, int nranks, int rank, int n_neighbors,
+                              const int32_t* nb_rank, const int64_t* nb_dst_node0) {
+  if (!ctx) return LAT_ERR_ARG;
+  LAT_CHECK_ARG(ctx, handles && nranks >= 1 && nranks <= P2P_MAXR && rank >= 0 && rank < nranks);
+  LAT_CHECK_ARG(ctx, n_neighbors >= 0 && n_neighbors <= 4 && (n_neighbors == 0 || (nb_rank && nb_dst_node0)));
+  P2P* p = ctx->p2p;
+  if (!p || !p->arena) return lat_fail(ctx, LAT_ERR_STATE, "call lat_p2p_arena_create first", __FILE__, __LINE__);
+  LAT_CUDA(ctx, cudaSetDevice(ctx->device));
+  p->nranks = nranks;
+  p->rank = rank;
+  for (int q = 0; q < nranks; ++q) {
+    if (q == rank) { p->peer[q] = p->arena; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, reinterpret_cast<const unsigned char*>(handles) + 64 * q, 64);
+    void* ptr = nullptr;
+    LAT_CUDA(ctx, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    p->peer[q] = reinterpret_cast<unsigned char*>(ptr);
+  }
+  p->n_nb = n_neighbors;
+  for (int k = 0; k < n_neighbors; ++k) { p->nb_rank[k] = nb_rank[k]; p->nb_dst_off[k] = nb_dst_node0[k]; }
+  if (!p->d_peer) LAT_CUDA(ctx, cudaMalloc(&p->d_peer, P2P_MAXR * sizeof(unsigned char*)));
+  LAT_CUDA(ctx, cudaMemcpy(p->d_peer, p->peer, P2P_MAXR * sizeof(unsigned char*), cudaMemcpyHostToDevice));
+  p->attached = true;
+  return LAT_OK;
+}
+
+extern "C" int lat_p2p_destroy(lat_ctx* ctx) {
+  if (!ctx || !ctx->p2p) return LAT_OK;
+  P2P* p = ctx->p2p;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int q = 0; q < p->nranks; ++q)
+    if (q != p->rank && p->peer[q]) cudaIpcCloseMemHandle(p->peer[q]);
+  if (p->d_peer) cudaFree(p->d_peer);
+  if (p->arena) cudaFree(p->arena);
+  delete p;
+  ctx->p2p = nullptr;
+  return LAT_OK;
+}
+
 template <int PC>
 static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, const double* vals,
                         const lat_halo* h, const double* b, double* x, const lat_pcg_opts* o, lat_pcg_result* res) {
@@ -1019,24 +1262,54 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
   const int64_t n_own = h->n_owned, n_loc = h->n_local;
   const int64_t n = 6 * n_loc;
   const unsigned grid = (unsigned)ceil_div(n_own, ROWS_PER_CTA);
+  // bit 4 of `reserved`: halo push + all-reduce through NVLink peer memory inside our kernels (no NCCL)
+  P2P* pp = ctx->p2p;
+  const bool p2p = (o->reserved & 16) && pp && pp->attached && pp->nranks == ctx->nranks && pp->n_local == n_loc &&
+                   pp->n_nb == h->n_neighbors;
+  if ((o->reserved & 16) && !p2p)
+    return lat_fail(ctx, LAT_ERR_STATE, "peer-memory path requested but no matching arena is attached", __FILE__, __LINE__);
   double* r = lat_buf<double>(ctx, "pcg_r", n);
-  double* u = lat_buf<double>(ctx, "pcg_z", n);
+  double* u = p2p ? reinterpret_cast<double*>(pp->arena + sizeof(P2PArenaHdr)) : lat_buf<double>(ctx, "pcg_z", n);
   double* p = lat_buf<double>(ctx, "pcg_pa", n);
   double* sv = lat_buf<double>(ctx, "pcg_pb", n);
   double* w = lat_buf<double>(ctx, "pcg_Ap", n);
   double* dinv = lat_buf<double>(ctx, "pcg_dinv", PC == LAT_PC_BLOCK6 ? 36 * n_own : 6 * n_own);
   double* partials = lat_buf<double>(ctx, "pcg_partials", (size_t)4 * grid + 8);
   PcgScalars* sc = lat_buf<PcgScalars>(ctx, "pcg_scalars", 1);
-  if (!r || !u || !p || !sv || !w || !dinv || !partials || !sc)
+  unsigned int* cta_done = lat_buf<unsigned int>(ctx, "p2p_cta_done", 4);
+  if (!r || !u || !p || !sv || !w || !dinv || !partials || !sc || !cta_done)
     return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
   if (o->reference_semantics)
     return lat_fail(ctx, LAT_ERR_UNSUPPORTED, "reference_semantics is single-GPU only", __FILE__, __LINE__);
   const int64_t launches0 = ctx->launches;
   PcgParams prm;
   prm.tol = o->tol; prm.mintol = 0.0; prm.alpha_max = 0.0; prm.restart_every = 0;
-  prm.maxiter = o->maxiter; prm.reference = 0; prm.dist = 1; prm.pad = 0;
+  prm.maxiter = o->maxiter; prm.reference = 0; prm.dist = 1; prm.pad = 0; prm.seq_base = 0;
   int check = o->check_every > 0 ? o->check_every : 32;
   const bool multi = ctx->nranks > 1 && ctx->nccl_comm != nullptr;
+  P2PPushArgs pa;
+  P2PWaitArgs wa;
+  memset(&pa, 0, sizeof pa);
+  memset(&wa, 0, sizeof wa);
+  int push_total = 0;
+  if (p2p) {
+    pp->epoch += 1;
+    prm.seq_base = pp->epoch << 32;
+    pa.n_nb = wa.n_nb = h->n_neighbors;
+    pa.my_rank = pp->rank;
+    for (int k = 0; k < h->n_neighbors; ++k) {
+      if (h->peer[k] != pp->nb_rank[k])
+        return lat_fail(ctx, LAT_ERR_STATE, "halo neighbour order differs from the attached arena", __FILE__, __LINE__);
+      pa.nb_rank[k] = wa.nb_rank[k] = h->peer[k];
+      pa.nb_first[k] = push_total;
+      pa.nb_dst_node0[k] = pp->nb_dst_off[k];
+      push_total += h->send_count[k];
+    }
+    pa.nb_first[h->n_neighbors] = push_total;
+    LAT_CUDA(ctx, cudaMemsetAsync(cta_done, 0, 4 * sizeof(unsigned int), ctx->stream));
+  }
+  const size_t u_off = sizeof(P2PArenaHdr);
+  const P2PArenaHdr* my_hdr = p2p ? reinterpret_cast<const P2PArenaHdr*>(pp->arena) : nullptr;
   {  // the halo send buffer must exist before any stream capture (allocation is not capturable)
     int64_t tot_send = 0;
     for (int i = 0; i < h->n_neighbors; ++i) tot_send += h->send_count[i];
@@ -1054,10 +1327,18 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
 
   // halo(u) -> w = A u, partial dots -> local sums -> all-reduce -> scalar recurrences / stop test
   auto spmv_and_reduce = [&]() -> int {
+    if (p2p) {
+      if (push_total > 0)
+        LAT_LAUNCH(ctx, k_p2p_push, (unsigned)ceil_div((int64_t)push_total * 6, 256), 256, 0, h->send_idx, u, pp->d_peer, pa,
+                   u_off, sc, prm, cta_done);
+      LAT_LAUNCH(ctx, k_cg_spmv_p2p, grid, SPMV_BLOCK, 0, rowptr, colidx, vals, n_own, u, r, w, sc, partials, prm, my_hdr, wa);
+      LAT_LAUNCH(ctx, k_p2p_reduce, 1, 1024, 0, partials, (int)grid, sc, prm, pp->d_peer, pp->nranks, pp->rank);
+      return LAT_OK;
+    }
     int rc2 = multi ? halo_exchange(ctx, h, u) : LAT_OK;
     if (rc2) return rc2;
     LAT_LAUNCH(ctx, k_cg_spmv, grid, SPMV_BLOCK, 0, rowptr, colidx, vals, n_own, u, r, w, sc, partials, prm);
-    LAT_LAUNCH(ctx, k_cg_reduce, 1, 1024, 0, partials, (int)grid, sc, prm);
+    LAT_LAUNCH(ctx, k_cg_reduce, 1, CG_REDUCE_BLOCK, 0, partials, (int)grid, sc, prm);
     rc2 = lat_allreduce_sum(ctx, sc->sums, 3);
     if (rc2) return rc2;
     LAT_LAUNCH(ctx, k_cg_finalize, 1, 1, 0, sc, prm);
@@ -1130,7 +1411,7 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
   res->iters = hs[0].iters;
   res->norm_b = sqrt(hs[0].bb);
   res->relres = hs[0].bb > 0.0 ? sqrt(hs[0].rr / hs[0].bb) : 0.0;
-  res->info = hs[0].done && !hs[0].breakdown ? 0 : (hs[0].breakdown ? 3 : 1);
+  res->info = hs[0].done && !hs[0].breakdown ? 0 : (hs[0].breakdown == 2 ? 4 : (hs[0].breakdown ? 3 : 1));
   res->solve_ms = ms;
   res->launches = ctx->launches - launches0;
   res->spmv_ms = 0.0; res->update_ms = 0.0; res->profiled = 0; res->reserved = 0;

@@ -151,6 +151,26 @@ class DistributedFEM:
                                           self.young, self.nu, self.kappa, out=out)
         return self.vals
 
+    def enable_p2p(self):
+        """Switch the iteration's halo exchange / all-reduce from NCCL to NVLink peer memory written by our
+        own kernels.  Every rank tells its neighbours where their data lands: the first local node index of
+        the ghost segment owned by each peer."""
+        import torch.distributed as dist
+        torch = self.torch
+        # my ghost segments: peer q's data starts at n_owned + sum(recv_counts of earlier peers)
+        off, seg0 = self.n_owned, {}
+        for q, rc in zip(self.part.peers, self.part.recv_counts):
+            seg0[q] = off
+            off += rc
+        table = torch.full((self.world,), -1, dtype=torch.int64, device=self.ctx.device)
+        for q, v in seg0.items():
+            table[q] = v
+        allt = [torch.zeros_like(table) for _ in range(self.world)]
+        dist.all_gather(allt, table)          # allt[q][me] = where MY data lands on rank q
+        dst0 = [int(allt[q][self.rank]) for q in self.part.peers]
+        self.ctx.p2p_setup(self.n_local, self.part.peers, dst0)
+        self.p2p = True
+
     def solve(self, tol=1e-8, maxiter=200000, precond=2, vals_bc=None, b=None, u=None, check_every=0):
         """Returns (u_local [6 n_local] incl. ghosts, reactions on owned rows, info)."""
         torch, ctx = self.torch, self.ctx
@@ -167,7 +187,7 @@ class DistributedFEM:
                                               L._ptr(self.vals), L._ptr(self.fixed_d), L._ptr(self.g_d),
                                               L._ptr(self.f_d), L._ptr(vals_bc), L._ptr(b)))
         u, info = ctx.pcg_dist(self.rowptr, self.colidx, vals_bc, self.halo, b, u, tol=tol, maxiter=maxiter,
-                               precond=precond, check_every=check_every)
+                               precond=precond, check_every=check_every, p2p=getattr(self, "p2p", False))
         ctx.set_dirichlet_values(self.fixed_d, self.g_d, u)
         ctx.halo_exchange(self.halo, u)
         R = ctx.spmv(self.rowptr, self.colidx, self.vals, u)     # rows >= n_owned are partial: ignore

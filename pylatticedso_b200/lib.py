@@ -27,7 +27,7 @@ EXPORTS = [
     "lat_bsr_to_csr_values", "lat_assemble_bsr", "lat_apply_dirichlet", "lat_set_dirichlet_values", "lat_bsr_spmv", "lat_pcg_bsr",
     "lat_compliance_grad", "lat_schur_batch", "lat_ddm_matvec",
     "lat_nccl_unique_id", "lat_comm_create", "lat_comm_destroy", "lat_allreduce_sum", "lat_halo_exchange",
-    "lat_pcg_bsr_dist",
+    "lat_pcg_bsr_dist", "lat_p2p_arena_create", "lat_p2p_attach", "lat_p2p_destroy",
 ]
 
 
@@ -116,6 +116,9 @@ def load():
     lib.lat_comm_destroy.argtypes = [vp]
     lib.lat_allreduce_sum.argtypes = [vp, vp, i64]
     lib.lat_halo_exchange.argtypes = [vp, C.POINTER(Halo), vp]
+    lib.lat_p2p_arena_create.argtypes = [vp, i64, vp]
+    lib.lat_p2p_attach.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]
+    lib.lat_p2p_destroy.argtypes = [vp]
     lib.lat_pcg_bsr_dist.argtypes = [vp, vp, vp, vp, C.POINTER(Halo), vp, vp, C.POINTER(PcgOpts), C.POINTER(PcgResult)]
     for name in EXPORTS:
         fn = getattr(lib, name)
@@ -323,9 +326,33 @@ class Context:
         self.check(self.lib.lat_allreduce_sum(self.h, _ptr(t), t.numel()))
         return t
 
+    def p2p_setup(self, n_local, peers, dst_node0):
+        """Create this rank's peer-memory arena, all-gather the IPC handles and map every rank's arena."""
+        import torch
+        import torch.distributed as dist
+        buf = (C.c_char * 64)()
+        self.check(self.lib.lat_p2p_arena_create(self.h, int(n_local), buf))
+        mine = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        if dist.get_backend() == "nccl":
+            mine = mine.to(self.device)
+        allh = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(allh, mine)
+        raw = b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh)
+        n = len(peers)
+        nb = (C.c_int32 * max(1, n))(*[int(q) for q in peers])
+        d0 = (C.c_int64 * max(1, n))(*[int(q) for q in dst_node0])
+        self.check(self.lib.lat_p2p_attach(self.h, C.create_string_buffer(raw, len(raw)), self.world, self.rank, n, nb, d0))
+        self.p2p_ready = True
+
+    def p2p_destroy(self):
+        self.lib.lat_p2p_destroy(self.h)
+        self.p2p_ready = False
+
     def pcg_dist(self, rowptr, colidx, vals, halo, b, x, tol=1e-8, maxiter=10000, precond=PC_JACOBI,
-                 reference_semantics=False, mintol=0.0, alpha_max=0.0, restart_every=0, check_every=0):
-        o = PcgOpts(tol, mintol, alpha_max, restart_every, maxiter, precond, int(reference_semantics), check_every, 0, 0)
+                 reference_semantics=False, mintol=0.0, alpha_max=0.0, restart_every=0, check_every=0, p2p=False,
+                 no_graph=False):
+        o = PcgOpts(tol, mintol, alpha_max, restart_every, maxiter, precond, int(reference_semantics), check_every, 0,
+                    (16 if p2p else 0) | (4 if no_graph else 0))
         r = PcgResult()
         self.check(self.lib.lat_pcg_bsr_dist(self.h, _ptr(rowptr), _ptr(colidx), _ptr(vals), C.byref(halo), _ptr(b),
                                              _ptr(x), C.byref(o), C.byref(r)))

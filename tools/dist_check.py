@@ -30,17 +30,24 @@ def main():
         f = f.copy(); f[6 * 7 + 0] = 0.01
         dfem = D.DistributedFEM(ctx, mesh, E, NU, rank, world)
         dfem.set_bc(fixed, g, f)
-        u, R, info = dfem.solve(tol=1e-13, maxiter=100000, precond=L.PC_BLOCK6, check_every=16)
-        ug = dfem.gather_owned(u)
-        Rg = dfem.gather_owned(R)
         if rank == 0:
             K = orc.assemble_csr(mesh.xyz, np.stack([mesh.en0, mesh.en1], 1), mesh.rad, E, NU)
             uo, Ro = orc.solve_static(K, fixed.astype(bool), g, f)
-            eu = np.abs(ug - uo).max() / np.abs(uo).max()
-            er = np.abs(Rg - Ro).max() / np.abs(Ro).max()
-            print(f"[dist_check] {geom}{n} m={m_} world={world} n_dof={mesh.n_dof} iters={info['iters']} info={info['info']} "
-                  f"relres={info['relres']:.1e} |u-uo|/|uo|={eu:.2e} |R-Ro|/|Ro|={er:.2e}", flush=True)
-            ok = ok and info["info"] == 0 and eu < 1e-8 and er < 1e-8
+        for mode in ("nccl", "p2p"):
+            if mode == "p2p":
+                dfem.enable_p2p()
+            for rep in range(2 if mode == "p2p" else 1):      # second p2p solve: flags of the first must not match
+                u, R, info = dfem.solve(tol=1e-13, maxiter=100000, precond=L.PC_BLOCK6, check_every=16)
+            ug = dfem.gather_owned(u)
+            Rg = dfem.gather_owned(R)
+            if rank == 0:
+                eu = np.abs(ug - uo).max() / np.abs(uo).max()
+                er = np.abs(Rg - Ro).max() / np.abs(Ro).max()
+                print(f"[dist_check] {mode} {geom}{n} m={m_} world={world} n_dof={mesh.n_dof} iters={info['iters']} "
+                      f"info={info['info']} relres={info['relres']:.1e} solve_ms={info['solve_ms']:.2f} |u-uo|/|uo|={eu:.2e} "
+                      f"|R-Ro|/|Ro|={er:.2e}", flush=True)
+                ok = ok and info["info"] == 0 and eu < 1e-8 and er < 1e-8
+        ctx.p2p_destroy()
     ctx.comm_destroy()
     dist.barrier()
     dist.destroy_process_group()
