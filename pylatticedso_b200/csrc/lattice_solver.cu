@@ -1020,9 +1020,9 @@ extern "C" int lat_halo_exchange(lat_ctx* ctx, const lat_halo* halo, double* vec
 // ===========================================================================
 // Every rank owns one cudaMalloc'ed arena, IPC-mapped into all ranks of the node:
 //   [ mailbox: 2 parities x MAXR x {v0,v1,v2,seq} | halo flags: MAXR x uint64 | u: 6 n_local doubles ]
-// * halo:  k_p2p_push stores the owned boundary entries of u straight into the neighbour's ghost section
+// * halo:  k_p2p_halo (one CTA) stores the owned boundary entries of u straight into the neighbour's ghost section
 //          (st.global on the mapped peer pointer), then publishes the sequence number with a system-scope
-//          release; the neighbour's SpMV kernel acquires it before gathering.
+//          release and waits for the neighbours' flags; the SpMV kernel that follows is the plain one.
 // * all-reduce: k_p2p_reduce sums the per-CTA partials, writes the 3 local sums into EVERY rank's mailbox
 //          (slot = my rank), releases the sequence number, then spins (bounded) until all slots carry it and
 //          adds them in rank order -- identical bits on every rank, no NCCL launch, ~2-3 us over NVSwitch.
@@ -1068,95 +1068,38 @@ struct P2PPushArgs {
   int64_t nb_dst_node0[4];   // first destination node (peer local numbering) of my segment
   int my_rank;
 };
-__global__ void k_p2p_push(const int32_t* __restrict__ send_idx, const double* __restrict__ u,
-                           unsigned char* const* __restrict__ peers, P2PPushArgs a, size_t u_off,
-                           const PcgScalars* __restrict__ sc, PcgParams prm, unsigned int* __restrict__ cta_done) {
+// ONE CTA: push the owned boundary entries of u into the neighbours' ghost sections, publish `seq`, then
+// wait (bounded) until every neighbour has published the same `seq` into OUR arena.  The SpMV that follows
+// is the plain k_cg_spmv: the kernel boundary orders it after this wait and starts with a clean L1.
+__global__ void __launch_bounds__(1024) k_p2p_halo(const int32_t* __restrict__ send_idx, const double* __restrict__ u,
+                                                   unsigned char* const* __restrict__ peers, P2PPushArgs a, size_t u_off,
+                                                   PcgScalars* __restrict__ sc, PcgParams prm) {
   if (sc->done || sc->iters >= prm.maxiter) return;
   const unsigned long long seq = prm.seq_base + (unsigned long long)sc->seq + 1ull;  // sequence of the upcoming SpMV
   const int total = a.nb_first[a.n_nb];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total * 6; i += gridDim.x * blockDim.x) {
+  for (int i = threadIdx.x; i < total * 6; i += blockDim.x) {
     const int e = i / 6, d = i - e * 6;
     int k = 0;
     while (k + 1 < a.n_nb && e >= a.nb_first[k + 1]) ++k;
     double* dst = reinterpret_cast<double*>(peers[a.nb_rank[k]] + u_off);
     dst[(a.nb_dst_node0[k] + (e - a.nb_first[k])) * 6 + d] = u[(int64_t)send_idx[e] * 6 + d];
   }
-  // last CTA to finish publishes the flags: every thread fences its own peer stores at system scope,
-  // the CTA barrier + ticket chain makes them happen-before the release of the flag
-  __shared__ bool s_last;
-  __threadfence_system();
-  __syncthreads();
+  __threadfence_system();   // every thread: its peer stores are performed at system scope ...
+  __syncthreads();          // ... before thread 0 releases the flags
   if (threadIdx.x == 0) {
-    __threadfence_system();
-    const unsigned int t = atomicAdd(cta_done, 1u);
-    s_last = (t == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (s_last && threadIdx.x == 0) {
-    __threadfence_system();
     for (int k = 0; k < a.n_nb; ++k) {
       P2PArenaHdr* hdr = reinterpret_cast<P2PArenaHdr*>(peers[a.nb_rank[k]]);
       st_release_sys(&hdr->halo_flag[a.my_rank], seq);
     }
-    *cta_done = 0u;
-  }
-}
-
-// Block-level wait for the halos of sequence `seq` from all neighbours (thread 0 spins, bounded).
-__device__ __forceinline__ bool p2p_wait_halo(const P2PArenaHdr* hdr, int n_nb, const int* nb_rank, unsigned long long seq) {
-  __shared__ int s_ok;
-  if (threadIdx.x == 0) {
-    int ok = 1;
-    for (int k = 0; k < n_nb; ++k) {
+    const P2PArenaHdr* mine = reinterpret_cast<const P2PArenaHdr*>(peers[a.my_rank]);
+    for (int k = 0; k < a.n_nb; ++k) {
       long long spins = 0;
-      while (ld_acquire_sys(&hdr->halo_flag[nb_rank[k]]) < seq) {
-        if (++spins > (1ll << 24)) { ok = 0; break; }
+      while (ld_acquire_sys(&mine->halo_flag[a.nb_rank[k]]) < seq) {
+        if (++spins > (1ll << 24)) { sc->p2p_timeout = 1; break; }
         __nanosleep(20);
       }
     }
-    s_ok = ok;
   }
-  __syncthreads();
-  return s_ok != 0;
-}
-
-struct P2PWaitArgs { int n_nb; int nb_rank[4]; };
-
-// SpMV of the peer-memory path: identical to k_cg_spmv after waiting for the neighbours' halos.
-__global__ void __launch_bounds__(SPMV_BLOCK) k_cg_spmv_p2p(const int32_t* __restrict__ rowptr,
-                                                            const int32_t* __restrict__ colidx,
-                                                            const double* __restrict__ vals, int64_t n_nodes,
-                                                            const double* __restrict__ u, const double* __restrict__ r,
-                                                            double* __restrict__ w, PcgScalars* __restrict__ sc,
-                                                            double* __restrict__ partials, PcgParams prm,
-                                                            const P2PArenaHdr* __restrict__ hdr, P2PWaitArgs wa) {
-  const int lane = threadIdx.x & 31;
-  const int g = lane / 6, rr_ = lane - g * 6;
-  const int64_t warp = (int64_t)blockIdx.x * (SPMV_BLOCK / 32) + (threadIdx.x >> 5);
-  const int64_t n = warp * ROWS_PER_WARP + g;
-  const bool active = g < ROWS_PER_WARP && n < n_nodes;
-  int lo = 0, hi = 0;
-  double uo = 0.0, ro = 0.0;
-  const int64_t i = n * 6 + rr_;
-  if (active) { lo = __ldg(rowptr + n); hi = __ldg(rowptr + n + 1); uo = u[i]; ro = r[i]; }
-  if (sc->done || sc->iters >= prm.maxiter) return;
-  const bool ok = p2p_wait_halo(hdr, wa.n_nb, wa.nb_rank, prm.seq_base + (unsigned long long)sc->seq + 1ull);
-  if (!ok) {
-    if (threadIdx.x == 0) sc->p2p_timeout = 1;
-  }
-  double acc = 0.0;
-#pragma unroll 4
-  for (int j = lo; j < hi; ++j) {
-    const int c = __ldg(colidx + j);
-    const double2* vp = reinterpret_cast<const double2*>(vals + (int64_t)j * 36 + rr_ * 6);
-    const double2* xp = reinterpret_cast<const double2*>(u + (int64_t)c * 6);
-    const double2 a0 = __ldcs(vp), a1 = __ldcs(vp + 1), a2 = __ldcs(vp + 2);
-    const double2 x0 = xp[0], x1 = xp[1], x2 = xp[2];
-    acc = dot6(a0, a1, a2, x0, x1, x2, acc);
-  }
-  if (active) w[i] = acc;
-  double v[3] = {ro * uo, acc * uo, ro * ro};
-  block_partials<3, SPMV_BLOCK>(v, partials);
 }
 
 // One CTA: local sums -> every rank's mailbox -> wait for all -> rank-ordered total -> recurrences.
@@ -1276,8 +1219,7 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
   double* dinv = lat_buf<double>(ctx, "pcg_dinv", PC == LAT_PC_BLOCK6 ? 36 * n_own : 6 * n_own);
   double* partials = lat_buf<double>(ctx, "pcg_partials", (size_t)4 * grid + 8);
   PcgScalars* sc = lat_buf<PcgScalars>(ctx, "pcg_scalars", 1);
-  unsigned int* cta_done = lat_buf<unsigned int>(ctx, "p2p_cta_done", 4);
-  if (!r || !u || !p || !sv || !w || !dinv || !partials || !sc || !cta_done)
+  if (!r || !u || !p || !sv || !w || !dinv || !partials || !sc)
     return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
   if (o->reference_semantics)
     return lat_fail(ctx, LAT_ERR_UNSUPPORTED, "reference_semantics is single-GPU only", __FILE__, __LINE__);
@@ -1288,28 +1230,24 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
   int check = o->check_every > 0 ? o->check_every : 32;
   const bool multi = ctx->nranks > 1 && ctx->nccl_comm != nullptr;
   P2PPushArgs pa;
-  P2PWaitArgs wa;
   memset(&pa, 0, sizeof pa);
-  memset(&wa, 0, sizeof wa);
   int push_total = 0;
   if (p2p) {
     pp->epoch += 1;
     prm.seq_base = pp->epoch << 32;
-    pa.n_nb = wa.n_nb = h->n_neighbors;
+    pa.n_nb = h->n_neighbors;
     pa.my_rank = pp->rank;
     for (int k = 0; k < h->n_neighbors; ++k) {
       if (h->peer[k] != pp->nb_rank[k])
         return lat_fail(ctx, LAT_ERR_STATE, "halo neighbour order differs from the attached arena", __FILE__, __LINE__);
-      pa.nb_rank[k] = wa.nb_rank[k] = h->peer[k];
+      pa.nb_rank[k] = h->peer[k];
       pa.nb_first[k] = push_total;
       pa.nb_dst_node0[k] = pp->nb_dst_off[k];
       push_total += h->send_count[k];
     }
     pa.nb_first[h->n_neighbors] = push_total;
-    LAT_CUDA(ctx, cudaMemsetAsync(cta_done, 0, 4 * sizeof(unsigned int), ctx->stream));
   }
   const size_t u_off = sizeof(P2PArenaHdr);
-  const P2PArenaHdr* my_hdr = p2p ? reinterpret_cast<const P2PArenaHdr*>(pp->arena) : nullptr;
   {  // the halo send buffer must exist before any stream capture (allocation is not capturable)
     int64_t tot_send = 0;
     for (int i = 0; i < h->n_neighbors; ++i) tot_send += h->send_count[i];
@@ -1319,7 +1257,10 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
   LAT_CUDA(ctx, cudaMemsetAsync(sc, 0, sizeof(PcgScalars), ctx->stream));
   const int32_t one = 1;
   LAT_CUDA(ctx, cudaMemcpyAsync(&sc->first, &one, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-  LAT_CUDA(ctx, cudaMemsetAsync(u, 0, n * sizeof(double), ctx->stream));
+  // Only the OWNED part of u is initialised here.  In the peer-memory path a neighbour that is ahead may
+  // already have pushed its first halo of this solve into our ghost section: zeroing it would lose data
+  // (observed: 1634 instead of 1246 iterations and a wrong iterate on the first solve).
+  if (!p2p) LAT_CUDA(ctx, cudaMemsetAsync(u, 0, n * sizeof(double), ctx->stream));
   if (PC != LAT_PC_NONE)
     LAT_LAUNCH(ctx, k_precond_setup, (unsigned)ceil_div(n_own, 128), 128, 0, rowptr, colidx, vals, n_own, PC, dinv);
   LAT_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -1328,10 +1269,9 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
   // halo(u) -> w = A u, partial dots -> local sums -> all-reduce -> scalar recurrences / stop test
   auto spmv_and_reduce = [&]() -> int {
     if (p2p) {
-      if (push_total > 0)
-        LAT_LAUNCH(ctx, k_p2p_push, (unsigned)ceil_div((int64_t)push_total * 6, 256), 256, 0, h->send_idx, u, pp->d_peer, pa,
-                   u_off, sc, prm, cta_done);
-      LAT_LAUNCH(ctx, k_cg_spmv_p2p, grid, SPMV_BLOCK, 0, rowptr, colidx, vals, n_own, u, r, w, sc, partials, prm, my_hdr, wa);
+      if (h->n_neighbors > 0)
+        LAT_LAUNCH(ctx, k_p2p_halo, 1, 1024, 0, h->send_idx, u, pp->d_peer, pa, u_off, sc, prm);
+      LAT_LAUNCH(ctx, k_cg_spmv, grid, SPMV_BLOCK, 0, rowptr, colidx, vals, n_own, u, r, w, sc, partials, prm);
       LAT_LAUNCH(ctx, k_p2p_reduce, 1, 1024, 0, partials, (int)grid, sc, prm, pp->d_peer, pp->nranks, pp->rank);
       return LAT_OK;
     }
