@@ -157,7 +157,8 @@ typedef struct {
   double spmv_ms;    /* mean duration of the fused SpMV kernel over the profiled iterations (0 if none) */
   double update_ms;  /* mean duration of the update kernel over the profiled iterations */
   int32_t profiled;  /* iterations actually profiled */
-  int32_t reserved;
+  int32_t reserved;  /* restarts triggered by the true-residual safeguard */
+  double true_relres; /* |b - A x| / |b| recomputed after convergence (textbook mode; -1 if not measured) */
 } lat_pcg_result;
 
 /* x is overwritten (x0 = 0).  [syncs] */

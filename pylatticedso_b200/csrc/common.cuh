@@ -22,6 +22,8 @@ struct PcgScalars {
   double gamma, alpha;      // Chronopoulos-Gear variant: (r,u) and the current step length
   int32_t first, pad;
   int32_t seq, p2p_timeout; // peer-memory path: sequence number of the last completed reduction
+  double true_rr;           // |b - A x|^2 measured by the safeguard
+  int32_t restarts, pad2;
 };
 
 struct lat_ctx {

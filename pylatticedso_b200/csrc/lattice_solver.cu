@@ -341,8 +341,9 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_pcg_update(int64_t n_nodes, cons
 __device__ __forceinline__ void cg_finish(PcgScalars* sc, const PcgParams& prm, double gamma, double delta, double rr) {
   sc->rr = rr;
   if (sc->first) {  // set-up pass: w0 = A u0
+    if (sc->first == 1) sc->bb = rr;   // r0 = b (first == 2: restart from x, |b| is kept)
+    else if (rr <= prm.tol * prm.tol * sc->bb) { sc->first = 0; sc->done = 1; return; }
     sc->first = 0;
-    sc->bb = rr;    // r0 = b
     sc->beta = 0.0;
     sc->gamma = gamma;
     sc->alpha = gamma / delta;
@@ -449,6 +450,46 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_cg_init(int64_t n_nodes, const d
   const double bv = active ? b[i] : 0.0;
   const double zv = apply_precond<PC>(dinv, n, g, rr_, active, bv);
   if (active) { x[i] = 0.0; r[i] = bv; u[i] = zv; p[i] = 0.0; s[i] = 0.0; }
+}
+
+// ---------------------------------------------------------------------------
+// True-residual safeguard of the Chronopoulos-Gear form.  The recurrences r -= alpha s, s = w + beta s
+// can drift from b - A x (and a lost halo would break them silently), so a converged solve is verified:
+// r_true = b - A x; if |r_true| > 2 tol |b| the iteration restarts from x with r = r_true (at most twice).
+// ---------------------------------------------------------------------------
+template <int PC>
+__global__ void __launch_bounds__(SPMV_BLOCK) k_cg_restart(int64_t n_nodes, const double* __restrict__ b,
+                                                           const double* __restrict__ Ax, const double* __restrict__ dinv,
+                                                           double* __restrict__ r, double* __restrict__ u,
+                                                           double* __restrict__ p, double* __restrict__ s,
+                                                           double* __restrict__ partials) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane / 6, rr_ = lane - g * 6;
+  const int64_t warp = (int64_t)blockIdx.x * (SPMV_BLOCK / 32) + (threadIdx.x >> 5);
+  const int64_t n = warp * ROWS_PER_WARP + g;
+  const bool active = g < ROWS_PER_WARP && n < n_nodes;
+  const int64_t i = n * 6 + rr_;
+  const double rv = active ? b[i] - Ax[i] : 0.0;
+  const double zv = apply_precond<PC>(dinv, n, g, rr_, active, rv);
+  if (active) { r[i] = rv; u[i] = zv; p[i] = 0.0; s[i] = 0.0; }
+  double v[1] = {rv * rv};
+  block_partials<1, SPMV_BLOCK>(v, partials);
+}
+
+// One CTA: |r_true|^2 (local, or local part awaiting an all-reduce when `dist`) and the accept/restart decision.
+__global__ void __launch_bounds__(CG_REDUCE_BLOCK) k_cg_true_residual(const double* __restrict__ partials, int n_part,
+                                                                      PcgScalars* __restrict__ sc, PcgParams prm, int decide) {
+  double out[1];
+  if (decide == 0 || decide == 2) sum_partials<1, CG_REDUCE_BLOCK>(partials, n_part, out);
+  if (threadIdx.x != 0) return;
+  if (decide == 0) { sc->sums[3] = out[0]; return; }           // dist: local sum only, all-reduced by the host
+  const double rr = (decide == 2) ? out[0] : sc->sums[3];
+  sc->true_rr = rr;
+  if (rr > 4.0 * prm.tol * prm.tol * sc->bb && sc->restarts < 2 && sc->iters < prm.maxiter) {  // |r_true| > 2 tol |b|
+    sc->done = 0;
+    sc->first = 2;
+    sc->restarts += 1;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -800,30 +841,55 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
   const int remaining = o->maxiter - nprof;
   const int nbatch = (int)ceil_div(remaining > 0 ? remaining : 0, check);
   PcgScalars* hs = ctx->h_scal;
-  int launched = 0, checked = 0;
-  bool finished = (remaining <= 0);
   // software pipeline of depth 2: batch i+1 is enqueued before the status of batch i is read;
   // kernels of a batch enqueued after convergence exit immediately (sc->done), so x is frozen
   // at the converged iterate exactly like the `break` of the reference loop.
-  while (!finished && rc == LAT_OK) {
-    while (launched < nbatch && launched - checked < 2) {
-      ce = cudaGraphLaunch(gexec, ctx->stream);
-      if (ce != cudaSuccess) { rc = lat_cuda_fail(ctx, ce, "cudaGraphLaunch", __FILE__, __LINE__); break; }
-      ctx->launches += (cgv ? 3 : 2) * check;
-      cudaMemcpyAsync(&hs[launched & 1], sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, ctx->stream);
-      cudaEventRecord(ctx->ev[2 + (launched & 1)], ctx->stream);
-      ++launched;
+  auto run_batches = [&](int64_t budget) -> int {
+    const int nb = (int)ceil_div(budget > 0 ? budget : 0, check);
+    int launched = 0, checked = 0;
+    bool finished = (nb <= 0);
+    while (!finished) {
+      while (launched < nb && launched - checked < 2) {
+        ce = cudaGraphLaunch(gexec, ctx->stream);
+        if (ce != cudaSuccess) return lat_cuda_fail(ctx, ce, "cudaGraphLaunch", __FILE__, __LINE__);
+        ctx->launches += (cgv ? 3 : 2) * check;
+        cudaMemcpyAsync(&hs[launched & 1], sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaEventRecord(ctx->ev[2 + (launched & 1)], ctx->stream);
+        ++launched;
+      }
+      const int sl = checked & 1;
+      ce = cudaEventSynchronize(ctx->ev[2 + sl]);
+      if (ce != cudaSuccess) return lat_cuda_fail(ctx, ce, "PCG iteration", __FILE__, __LINE__);
+      ++checked;
+      if (hs[sl].done || hs[sl].iters >= o->maxiter || checked == nb) finished = true;
     }
-    if (rc != LAT_OK) break;
-    const int s = checked & 1;
-    ce = cudaEventSynchronize(ctx->ev[2 + s]);
-    if (ce != cudaSuccess) { rc = lat_cuda_fail(ctx, ce, "PCG iteration", __FILE__, __LINE__); break; }
-    ++checked;
-    if (hs[s].done || hs[s].iters >= o->maxiter || checked == nbatch) finished = true;
+    cudaMemcpyAsync(&hs[0], sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, ctx->stream);
+    ce = cudaStreamSynchronize(ctx->stream);
+    if (ce != cudaSuccess) return lat_cuda_fail(ctx, ce, "PCG sync", __FILE__, __LINE__);
+    return LAT_OK;
+  };
+  if (rc == LAT_OK) rc = run_batches(remaining);
+  // true-residual safeguard of the Chronopoulos-Gear form (see k_cg_restart)
+  double true_rr = -1.0;
+  while (rc == LAT_OK && cgv && hs[0].done && !hs[0].breakdown && hs[0].bb > 0.0) {
+    rc = lat_spmv_internal(ctx, rowptr, colidx, vals, n_nodes, x, Ap);
+    if (rc) break;
+    k_cg_restart<PC><<<grid, SPMV_BLOCK, 0, ctx->stream>>>(n_nodes, b, Ap, dinv, r, z, pa, pb, partials);
+    k_cg_true_residual<<<1, CG_REDUCE_BLOCK, 0, ctx->stream>>>(partials, (int)grid, sc, prm, 2);
+    ctx->launches += 2;
+    cudaMemcpyAsync(&hs[0], sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, ctx->stream);
+    ce = cudaStreamSynchronize(ctx->stream);
+    if (ce != cudaSuccess) { rc = lat_cuda_fail(ctx, ce, "PCG residual check", __FILE__, __LINE__); break; }
+    true_rr = hs[0].true_rr;
+    if (hs[0].done) break;       // accepted
+    // restart from x: set-up pass, then iterate on the remaining budget
+    launch_spmv(ctx->stream);
+    launch_reduce(ctx->stream);
+    ctx->launches += 2;
+    rc = run_batches((int64_t)o->maxiter - hs[0].iters);
   }
   if (rc == LAT_OK) {
     cudaEventRecord(ctx->ev[1], ctx->stream);
-    cudaMemcpyAsync(&hs[0], sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, ctx->stream);
     ce = cudaStreamSynchronize(ctx->stream);
     if (ce != cudaSuccess) rc = lat_cuda_fail(ctx, ce, "PCG final sync", __FILE__, __LINE__);
   }
@@ -842,7 +908,8 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
   res->spmv_ms = spmv_ms;
   res->update_ms = update_ms;
   res->profiled = nprof;
-  res->reserved = 0;
+  res->reserved = hs[0].restarts;
+  res->true_relres = (true_rr >= 0.0 && hs[0].bb > 0.0) ? sqrt(true_rr / hs[0].bb) : -1.0;
   return LAT_OK;
 }
 
@@ -1319,26 +1386,50 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
     }
   }
   PcgScalars* hs = ctx->h_scal;
-  int it = 0;
-  bool finished = o->maxiter <= 0;
-  while (!finished) {
-    const int batch = (o->maxiter - it) < check ? (o->maxiter - it) : check;
-    if (use_graph && batch == check) {
-      cudaError_t ce = cudaGraphLaunch(gexec, ctx->stream);
-      if (ce != cudaSuccess) { rc = lat_cuda_fail(ctx, ce, "cudaGraphLaunch", __FILE__, __LINE__); break; }
-      ctx->launches += per_iter * check;
-    } else {
-      for (int q = 0; q < batch; ++q) {
-        rc = one_iteration();
-        if (rc) break;
+  auto run_batches = [&](int64_t budget) -> int {
+    int64_t it = 0;
+    bool finished = budget <= 0;
+    while (!finished) {
+      const int batch = (int)((budget - it) < check ? (budget - it) : check);
+      if (use_graph && batch == check) {
+        cudaError_t ce = cudaGraphLaunch(gexec, ctx->stream);
+        if (ce != cudaSuccess) return lat_cuda_fail(ctx, ce, "cudaGraphLaunch", __FILE__, __LINE__);
+        ctx->launches += per_iter * check;
+      } else {
+        for (int q = 0; q < batch; ++q) {
+          const int rc3 = one_iteration();
+          if (rc3) return rc3;
+        }
       }
-      if (rc) break;
+      it += batch;
+      cudaMemcpyAsync(&hs[0], sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, ctx->stream);
+      cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+      if (ce != cudaSuccess) return lat_cuda_fail(ctx, ce, "distributed PCG iteration", __FILE__, __LINE__);
+      if (hs[0].done || hs[0].iters >= o->maxiter || it >= budget) finished = true;
     }
-    it += batch;
+    return LAT_OK;
+  };
+  rc = run_batches(o->maxiter);
+  // true-residual safeguard (see k_cg_restart): x needs its ghosts, |r_true|^2 is all-reduced
+  double true_rr = -1.0;
+  while (rc == LAT_OK && hs[0].done && !hs[0].breakdown && hs[0].bb > 0.0) {
+    if (multi) { rc = halo_exchange(ctx, h, x); if (rc) break; }
+    rc = lat_spmv_internal(ctx, rowptr, colidx, vals, n_own, x, w);
+    if (rc) break;
+    k_cg_restart<PC><<<grid, SPMV_BLOCK, 0, ctx->stream>>>(n_own, b, w, dinv, r, u, p, sv, partials);
+    k_cg_true_residual<<<1, CG_REDUCE_BLOCK, 0, ctx->stream>>>(partials, (int)grid, sc, prm, 0);
+    rc = lat_allreduce_sum(ctx, sc->sums + 3, 1);
+    if (rc) break;
+    k_cg_true_residual<<<1, CG_REDUCE_BLOCK, 0, ctx->stream>>>(partials, (int)grid, sc, prm, 1);
+    ctx->launches += 3;
     cudaMemcpyAsync(&hs[0], sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t ce = cudaStreamSynchronize(ctx->stream);
-    if (ce != cudaSuccess) { rc = lat_cuda_fail(ctx, ce, "distributed PCG iteration", __FILE__, __LINE__); break; }
-    if (hs[0].done || hs[0].iters >= o->maxiter || it >= o->maxiter) finished = true;
+    if (ce != cudaSuccess) { rc = lat_cuda_fail(ctx, ce, "distributed PCG residual check", __FILE__, __LINE__); break; }
+    true_rr = hs[0].true_rr;
+    if (hs[0].done) break;
+    rc = spmv_and_reduce();   // restart from x: set-up pass
+    if (rc) break;
+    rc = run_batches((int64_t)o->maxiter - hs[0].iters);
   }
   if (gexec) cudaGraphExecDestroy(gexec);
   if (graph) cudaGraphDestroy(graph);
@@ -1354,7 +1445,8 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
   res->info = hs[0].done && !hs[0].breakdown ? 0 : (hs[0].breakdown == 2 ? 4 : (hs[0].breakdown ? 3 : 1));
   res->solve_ms = ms;
   res->launches = ctx->launches - launches0;
-  res->spmv_ms = 0.0; res->update_ms = 0.0; res->profiled = 0; res->reserved = 0;
+  res->spmv_ms = 0.0; res->update_ms = 0.0; res->profiled = 0; res->reserved = hs[0].restarts;
+  res->true_relres = (true_rr >= 0.0 && hs[0].bb > 0.0) ? sqrt(true_rr / hs[0].bb) : -1.0;
   return LAT_OK;
 }
 

@@ -45,7 +45,8 @@ class PcgOpts(C.Structure):
 class PcgResult(C.Structure):
     _fields_ = [("iters", C.c_int32), ("info", C.c_int32), ("relres", C.c_double), ("norm_b", C.c_double),
                 ("solve_ms", C.c_double), ("launches", C.c_int64), ("spmv_ms", C.c_double),
-                ("update_ms", C.c_double), ("profiled", C.c_int32), ("reserved", C.c_int32)]
+                ("update_ms", C.c_double), ("profiled", C.c_int32), ("reserved", C.c_int32),
+                ("true_relres", C.c_double)]
 
 
 class Halo(C.Structure):
@@ -249,7 +250,8 @@ class Context:
         self.check(self.lib.lat_pcg_bsr(self.h, _ptr(rowptr), _ptr(colidx), _ptr(vals), rowptr.numel() - 1, _ptr(b),
                                         _ptr(x), C.byref(o), C.byref(r)))
         return x, dict(iters=r.iters, info=r.info, relres=r.relres, norm_b=r.norm_b, solve_ms=r.solve_ms,
-                       launches=r.launches, spmv_ms=r.spmv_ms, update_ms=r.update_ms, profiled=r.profiled)
+                       launches=r.launches, spmv_ms=r.spmv_ms, update_ms=r.update_ms, profiled=r.profiled,
+                       true_relres=r.true_relres, restarts=r.reserved)
 
     def compliance_grad(self, x, y, z, en0, en1, rad, group, n_groups, u, young, nu, kappa=0.9, chain=None,
                         lam=None, want_elem=False):
@@ -357,4 +359,4 @@ class Context:
         self.check(self.lib.lat_pcg_bsr_dist(self.h, _ptr(rowptr), _ptr(colidx), _ptr(vals), C.byref(halo), _ptr(b),
                                              _ptr(x), C.byref(o), C.byref(r)))
         return x, dict(iters=r.iters, info=r.info, relres=r.relres, norm_b=r.norm_b, solve_ms=r.solve_ms,
-                       launches=r.launches)
+                       launches=r.launches, true_relres=r.true_relres, restarts=r.reserved)

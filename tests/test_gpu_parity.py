@@ -235,6 +235,27 @@ def test_compliance_gradient_matches_reference_and_oracle(ctx):
     assert np.allclose(qs, g, rtol=1e-10)
 
 
+def test_cg_true_residual_safeguard(ctx):
+    """The Chronopoulos-Gear recurrences are verified against b - A x after convergence; the reported true
+    residual must honour the tolerance (restarting from x if it does not)."""
+    from pylatticedso_b200 import mesh as M
+    m = M.mesh_from_synthetic(M.synthetic_lattice("BCC", (6, 6, 6), [0.02]), 3)     # slender struts: cond ~1e9
+    fixed, g, f = M.compression_bc(m)
+    x, y, z, en0, en1, rad = upload(ctx, m)
+    rowptr, colidx = ctx.bsr_pattern(en0, en1, m.n_nodes)
+    vals = ctx.assemble_bsr(x, y, z, en0, en1, rad, m.n_nodes, colidx.numel(), E_MOD, NU)
+    vbc, b = ctx.apply_dirichlet(rowptr, colidx, vals, dev(ctx, fixed, np.uint8), dev(ctx, g, np.float64), dev(ctx, f, np.float64))
+    for tol in (1e-8, 1e-12):
+        u, info = ctx.pcg(rowptr, colidx, vbc, b, tol=tol, maxiter=200000, precond=2)
+        r = ctx.spmv(rowptr, colidx, vbc, u) - b
+        true = float(r.norm()) / info["norm_b"]
+        assert info["info"] == 0 and info["true_relres"] >= 0
+        assert abs(info["true_relres"] - true) <= 1e-3 * true + 1e-16       # the safeguard measures what it says
+        assert true <= 2.0 * tol or info["restarts"] == 2                  # accepted, or restart budget spent
+        uc, ic = ctx.pcg(rowptr, colidx, vbc, b, tol=tol, maxiter=200000, precond=2, classic=True)
+        assert float((u - uc).abs().max()) <= 1e3 * tol * float(uc.abs().max())
+
+
 def test_bad_arguments_are_errors_not_crashes(ctx):
     import torch
     from pylatticedso_b200.lib import LatticeB200Error
