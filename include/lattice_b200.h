@@ -251,6 +251,18 @@ int lat_ddm_matvec(lat_ctx* ctx, const double* S, int64_t s_stride, const int32_
                    const double* u_fixed, int64_t n_cells, int32_t nb, int64_t n_free,
                    const double* x, double* y);
 
+/* ---- A9: assembled interface operator -------------------------------------------------------
+ * K_G = sum_c P_c^T S_c P_c as BSR over the interface (cell-boundary) nodes: what
+ * LatticeSim.build_preconditioner + Cell.build_local_preconditioner (lattice_sim.py:1351-1415,
+ * cell.py:783-827) assemble as COO triplets for SuperLU.  cell_nodes: int32[n_cells][n_bnd_nodes]
+ * interface node index (Point.index_boundary) of each local boundary node in
+ * cell.node_in_order_simulation order (-1 = absent).  The pattern (rowptr, colidx, nnzb) must contain
+ * every (node, node) pair of every cell: build it with lat_bsr_pattern_build on the node pairs.
+ * vals[nnzb*36] is overwritten.  FP64 atomics: summation order is not fixed.  [syncs] */
+int lat_assemble_cells_bsr(lat_ctx* ctx, const double* S, int64_t s_stride, const int32_t* cell_nodes,
+                           int64_t n_cells, int32_t n_bnd_nodes, const int32_t* rowptr, const int32_t* colidx,
+                           int64_t nnzb, double* vals);
+
 #ifdef __cplusplus
 }
 #endif

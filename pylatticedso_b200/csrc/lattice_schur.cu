@@ -297,3 +297,64 @@ extern "C" int lat_ddm_matvec(lat_ctx* ctx, const double* S, int64_t s_stride, c
   LAT_LAUNCH(ctx, k_ddm_matvec, (unsigned)ceil_div(n_cells, 8), 256, 0, S, s_stride, gidx, u_fixed, n_cells, nb, x, y);
   return LAT_OK;
 }
+
+
+// ===========================================================================
+// A9: assembled interface operator  K_G = sum_c P_c^T S_c P_c  as BSR(6x6)
+// ===========================================================================
+// LatticeSim.build_preconditioner / Cell.build_local_preconditioner (lattice_sim.py:1351-1415,
+// cell.py:783-827) assemble the same matrix as COO triplets on the free DOFs and hand it to SuperLU.
+// Here it is assembled on ALL interface DOFs (6 per boundary node, Dirichlet rows eliminated afterwards
+// with lat_apply_dirichlet) so that the BSR PCG can solve the interface problem directly.
+// One warp per (cell, row node a): for every column node b the 6x6 block of S_c is scatter-added
+// (FP64 RED) into the BSR block (node_a, node_b) located by binary search.
+__global__ void __launch_bounds__(256) k_assemble_cells(const double* __restrict__ S, int64_t s_stride,
+                                                        const int32_t* __restrict__ cell_nodes, int64_t n_cells, int nbn,
+                                                        const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                                        double* __restrict__ vals, int32_t* __restrict__ missing) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= n_cells * nbn) return;
+  const int64_t c = wid / nbn;
+  const int a = (int)(wid - c * nbn);
+  const int nb = 6 * nbn;
+  const int32_t* cn = cell_nodes + c * nbn;
+  const int na = cn[a];
+  if (na < 0) return;
+  const double* Sc = S + c * s_stride;
+  const int lo = rowptr[na], hi = rowptr[na + 1];
+  for (int b = 0; b < nbn; ++b) {
+    const int nbk = cn[b];
+    if (nbk < 0) continue;
+    int l = lo, h = hi;
+    while (l < h) { const int mid = (l + h) >> 1; if (colidx[mid] < nbk) l = mid + 1; else h = mid; }
+    if (l >= hi || colidx[l] != nbk) { if (lane == 0) atomicAdd(missing, 1); continue; }
+    double* dst = vals + (int64_t)l * 36;
+    for (int k = lane; k < 36; k += 32) {
+      const int i = k / 6, j = k - i * 6;
+      atomicAdd(dst + k, Sc[(int64_t)(a * 6 + i) * nb + b * 6 + j]);
+    }
+  }
+}
+
+extern "C" int lat_assemble_cells_bsr(lat_ctx* ctx, const double* S, int64_t s_stride, const int32_t* cell_nodes,
+                                      int64_t n_cells, int32_t n_bnd_nodes, const int32_t* rowptr, const int32_t* colidx,
+                                      int64_t nnzb, double* vals) {
+  if (!ctx) return LAT_ERR_ARG;
+  LAT_CHECK_ARG(ctx, S && cell_nodes && rowptr && colidx && vals && n_cells >= 0 && n_bnd_nodes > 0 && nnzb > 0);
+  LAT_CHECK_ARG(ctx, 6 * n_bnd_nodes <= SCHUR_MAX_NB);
+  LAT_CHECK_ARG(ctx, s_stride == 0 || s_stride >= (int64_t)36 * n_bnd_nodes * n_bnd_nodes);
+  LAT_CUDA(ctx, cudaSetDevice(ctx->device));
+  int32_t* missing = lat_buf<int32_t>(ctx, "cells_missing", 4);
+  if (!missing) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+  LAT_CUDA(ctx, cudaMemsetAsync(missing, 0, 4 * sizeof(int32_t), ctx->stream));
+  LAT_CUDA(ctx, cudaMemsetAsync(vals, 0, (size_t)nnzb * 36 * sizeof(double), ctx->stream));
+  if (n_cells == 0) return LAT_OK;
+  LAT_LAUNCH(ctx, k_assemble_cells, (unsigned)ceil_div(n_cells * n_bnd_nodes, 8), 256, 0, S, s_stride, cell_nodes, n_cells,
+             (int)n_bnd_nodes, rowptr, colidx, vals, missing);
+  int32_t h = 0;
+  LAT_CUDA(ctx, cudaMemcpyAsync(&h, missing, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h != 0) return lat_fail(ctx, LAT_ERR_ARG, "pattern does not contain every (node, node) pair of the cells", __FILE__, __LINE__);
+  return LAT_OK;
+}

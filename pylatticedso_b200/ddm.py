@@ -1,0 +1,104 @@
+"""Domain-decomposition (static condensation) solve on the GPU: the device counterpart of
+``LatticeSim.solve_DDM`` (lattice_sim.py:1111-1176).
+
+    per-cell Schur complements (lat_schur_batch)            -- SchurComplement, schur_complement.py:75-147
+ -> interface operator K_G = sum_c P_c^T S_c P_c as BSR     -- build_preconditioner, lattice_sim.py:1351-1415
+ -> Dirichlet elimination + block-Jacobi PCG on K_G         -- replaces CG on the Python operator
+                                                               calculate_reaction_force_global (:1180-1252)
+ -> reactions R = K_G u                                     -- update_reaction_force_each_cell (:1204-1223)
+
+The reference iterates on the free interface DOFs with a Python loop over all cells per CG iteration and
+preconditions with a SuperLU factorisation of the same assembled matrix; here the assembled matrix itself is
+solved.  ``lat_ddm_matvec`` (the matrix-free operator) remains available through ``Context.ddm_matvec``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import lib as L
+from .mesh import NDOF
+
+
+def cell_pair_elements(cell_nodes):
+    """All unordered node pairs of every cell as virtual 2-node elements (pattern input)."""
+    cn = np.asarray(cell_nodes, dtype=np.int64)
+    nbn = cn.shape[1]
+    ia, ib = np.triu_indices(nbn, k=1)
+    a, b = cn[:, ia].ravel(), cn[:, ib].ravel()
+    ok = (a >= 0) & (b >= 0) & (a != b)
+    return a[ok].astype(np.int32), b[ok].astype(np.int32)
+
+
+class InterfaceProblem:
+    """Assembled interface system of a decomposed lattice, resident on one GPU."""
+
+    def __init__(self, ctx: L.Context, cell_nodes, n_interface_nodes, S):
+        """cell_nodes: int [n_cells, n_bnd_nodes] interface node index of each local boundary node
+        (``Point.index_boundary`` in ``cell.node_in_order_simulation`` order); S: device tensor
+        [n_cells, nb, nb] or [nb, nb] (one Schur matrix shared by identical cells)."""
+        import torch
+        self.torch, self.ctx = torch, ctx
+        dev = ctx.device
+        self.n_nodes = int(n_interface_nodes)
+        self.cell_nodes = torch.from_numpy(np.ascontiguousarray(cell_nodes, dtype=np.int32)).to(dev)
+        e0, e1 = cell_pair_elements(cell_nodes)
+        self.rowptr, self.colidx = ctx.bsr_pattern(torch.from_numpy(e0).to(dev), torch.from_numpy(e1).to(dev), self.n_nodes)
+        self.S = S
+        self.vals = ctx.assemble_cells_bsr(S, self.cell_nodes, self.rowptr, self.colidx)
+
+    def solve(self, fixed, g, f, tol=1e-10, maxiter=200000, precond=L.PC_BLOCK6):
+        torch, ctx = self.torch, self.ctx
+        dev = ctx.device
+        t = lambda a, d: torch.from_numpy(np.ascontiguousarray(a, dtype=d)).to(dev)
+        fd, gd, fv = t(fixed, np.uint8), t(g, np.float64), t(f, np.float64)
+        vbc, b = ctx.apply_dirichlet(self.rowptr, self.colidx, self.vals, fd, gd, fv)
+        u, info = ctx.pcg(self.rowptr, self.colidx, vbc, b, tol=tol, maxiter=maxiter, precond=precond)
+        ctx.set_dirichlet_values(fd, gd, u)
+        R = ctx.spmv(self.rowptr, self.colidx, self.vals, u)
+        return u, R, info, b
+
+    def matvec_free(self, x_free, gidx, u_fixed=None):
+        """The reference's interface operator on the FREE-DOF vector (lattice_sim.py:1180-1252)."""
+        return self.ctx.ddm_matvec(self.S, gidx, x_free, u_fixed=u_fixed)
+
+
+def solve_DDM_B200(lattice, tol=1e-10, maxiter=200000, ctx=None):
+    """Drop-in for ``LatticeSim.solve_DDM()`` -> (xsol, info, global_displacement_index, b).
+
+    Needs ``cell.schur_complement`` on every cell (``calculate_schur_complement_cells``, which calls the
+    patched ``get_schur_complement``).  Leaves displacements and reactions on the boundary ``Point``s."""
+    import torch
+    ctx = ctx or L.Context()
+    cells = list(lattice.cells)
+    for c in cells:
+        if c.node_in_order_simulation is None:
+            c.define_node_order_to_simulate()
+    nbn = max(len(c.node_in_order_simulation) for c in cells)
+    n_int = int(lattice.max_index_boundary) + 1
+    cell_nodes = np.full((len(cells), nbn), -1, dtype=np.int32)
+    S = np.zeros((len(cells), 6 * nbn, 6 * nbn))
+    pts = {}
+    for k, c in enumerate(cells):
+        nb = len(c.node_in_order_simulation)
+        for a, p in enumerate(c.node_in_order_simulation):
+            cell_nodes[k, a] = p.index_boundary
+            pts[p.index_boundary] = p
+        S[k, : 6 * nb, : 6 * nb] = np.asarray(c.schur_complement)
+    fixed = np.zeros(6 * n_int, dtype=np.uint8)
+    g = np.zeros(6 * n_int)
+    f = np.zeros(6 * n_int)
+    for ib, p in pts.items():
+        for d in range(NDOF):
+            if p.fixed_DOF[d]:
+                fixed[6 * ib + d] = 1
+                g[6 * ib + d] = p.displacement_vector[d]
+            f[6 * ib + d] = float(p.applied_force[d])   # DDM applies every component once (lattice_sim.py:567-632)
+    prob = InterfaceProblem(ctx, cell_nodes, n_int, torch.from_numpy(S).to(ctx.device))
+    u, R, info, b = prob.solve(fixed, g, f, tol=tol, maxiter=maxiter)
+    uh, Rh = u.cpu().numpy().reshape(-1, 6), R.cpu().numpy().reshape(-1, 6)
+    for ib, p in pts.items():
+        p.displacement_vector[:] = [float(v) for v in uh[ib]]
+        p.reaction_force_vector = [float(v) for v in Rh[ib]]
+    xsol, idx = lattice.get_global_displacement()
+    free = fixed.reshape(-1) == 0
+    return xsol, info["info"], lattice.global_displacement_index, b.cpu().numpy()[free]

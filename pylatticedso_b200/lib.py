@@ -27,7 +27,7 @@ EXPORTS = [
     "lat_bsr_to_csr_values", "lat_assemble_bsr", "lat_apply_dirichlet", "lat_set_dirichlet_values", "lat_bsr_spmv", "lat_pcg_bsr",
     "lat_compliance_grad", "lat_schur_batch", "lat_ddm_matvec",
     "lat_nccl_unique_id", "lat_comm_create", "lat_comm_destroy", "lat_allreduce_sum", "lat_halo_exchange",
-    "lat_pcg_bsr_dist", "lat_p2p_arena_create", "lat_p2p_attach", "lat_p2p_destroy",
+    "lat_pcg_bsr_dist", "lat_p2p_arena_create", "lat_p2p_attach", "lat_p2p_destroy", "lat_assemble_cells_bsr",
 ]
 
 
@@ -112,6 +112,7 @@ def load():
     lib.lat_compliance_grad.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, vp, vp, i64, vp, vp]
     lib.lat_schur_batch.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, i32, dbl, dbl, dbl, vp, vp, vp, i32, vp]
     lib.lat_ddm_matvec.argtypes = [vp, vp, i64, vp, vp, i64, i32, i64, vp, vp]
+    lib.lat_assemble_cells_bsr.argtypes = [vp, vp, i64, vp, i64, i32, vp, vp, i64, vp]
     lib.lat_nccl_unique_id.argtypes = [vp]
     lib.lat_comm_create.argtypes = [vp, vp, C.c_int, C.c_int]
     lib.lat_comm_destroy.argtypes = [vp]
@@ -287,6 +288,16 @@ class Context:
         self.check(self.lib.lat_ddm_matvec(self.h, _ptr(S), stride, _ptr(gidx), _ptr(u_fixed), n_cells, nb, n_free,
                                            _ptr(x), _ptr(y)))
         return y
+
+    def assemble_cells_bsr(self, S, cell_nodes, rowptr, colidx):
+        """K_G = sum_c P_c^T S_c P_c.  S: [n_cells, nb, nb] or [nb, nb] (shared)."""
+        import torch
+        n_cells, nbn = int(cell_nodes.shape[0]), int(cell_nodes.shape[1])
+        stride = 0 if S.dim() == 2 else 36 * nbn * nbn
+        vals = torch.empty(colidx.numel() * 36, dtype=torch.float64, device=self.device)
+        self.check(self.lib.lat_assemble_cells_bsr(self.h, _ptr(S), stride, _ptr(cell_nodes), n_cells, nbn, _ptr(rowptr),
+                                                   _ptr(colidx), colidx.numel(), _ptr(vals)))
+        return vals
 
     # -- multi-GPU ---------------------------------------------------------------
     def comm_create(self, rank, world):

@@ -85,3 +85,49 @@ def test_ddm_matvec_matches_assembled_interface_operator(ctx):
         r = S[0] @ u
         np.add.at(ref, gidx[c][gidx[c] >= 0], r[gidx[c] >= 0])
     assert np.abs(y - ref).max() < 1e-12 * np.abs(ref).max()
+
+
+def test_ddm_interface_solve_equals_full_fem(ctx):
+    """Static condensation is exact: per-cell Schur (lat_schur_batch) -> assembled interface operator
+    (lat_assemble_cells_bsr) -> PCG must reproduce the full-lattice FEM displacements on the cell corners,
+    and the matrix-free operator (lat_ddm_matvec) must equal the assembled one."""
+    import torch
+    from pylatticedso_b200 import mesh as M
+    from pylatticedso_b200.ddm import InterfaceProblem
+    from pylatticedso_b200.fem import BeamFEM
+    from pylatticedso_b200.schur import bcc_cell_order_nodes, synthetic_cell_batch
+    n = (3, 2, 2)
+    lat = M.synthetic_lattice("BCC", n, [0.05])
+    mesh = M.mesh_from_synthetic(lat, 3)
+    fixed, g, f = M.compression_bc(mesh)
+    f = f.copy()
+    fem = BeamFEM(mesh, E_MOD, NU, ctx=ctx)
+    u, R, info = fem.solve(fixed, g, f, tol=1e-13, maxiter=200000)
+    u_pts = u.cpu().numpy().reshape(-1, 6)[: mesh.n_points]
+    # interface = the cell corners; every cell is a translate of the unit cell
+    key = {tuple(np.round(p, 9)): k for k, p in enumerate(lat.pxyz)}
+    corner = np.array([k for k, p in enumerate(lat.pxyz) if np.allclose(p, np.round(p))])
+    g2i = -np.ones(lat.pxyz.shape[0], dtype=np.int64); g2i[corner] = np.arange(corner.size)
+    unit = M.synthetic_lattice("BCC", (1, 1, 1), [1.0])
+    order = bcc_cell_order_nodes(unit.pxyz, (0, 1, 0, 1, 0, 1))
+    cells = []
+    for i in range(n[0]):
+        for j in range(n[1]):
+            for k in range(n[2]):
+                cells.append([g2i[key[tuple(np.round(unit.pxyz[o] + np.array([i, j, k]), 9))]] for o in order])
+    cell_nodes = np.array(cells, dtype=np.int32)
+    batch, _ = synthetic_cell_batch(ctx, "BCC", np.array([0.05]), 3, E_MOD, NU)
+    S = batch.schur()[0]
+    prob = InterfaceProblem(ctx, cell_nodes, corner.size, S)
+    dof = (corner[:, None] * 6 + np.arange(6)[None, :]).ravel()
+    ui, Ri, infoi, b = prob.solve(fixed[dof], g[dof], f[dof], tol=1e-13)
+    assert infoi["info"] == 0
+    ref = u_pts[corner]
+    assert np.abs(ui.cpu().numpy().reshape(-1, 6) - ref).max() < 1e-8 * np.abs(ref).max()
+    # matrix-free operator == assembled operator on a random vector (all DOFs free)
+    rng = np.random.default_rng(0)
+    x = torch.from_numpy(rng.standard_normal(6 * corner.size)).to(ctx.device)
+    gidx = torch.from_numpy((cell_nodes[:, :, None] * 6 + np.arange(6)[None, None, :]).reshape(len(cells), -1).astype(np.int32)).to(ctx.device)
+    y1 = ctx.ddm_matvec(S, gidx, x)
+    y2 = ctx.spmv(prob.rowptr, prob.colidx, prob.vals, x)
+    assert float((y1 - y2).abs().max()) < 1e-11 * float(y2.abs().max())
