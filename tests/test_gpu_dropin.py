@@ -1,0 +1,60 @@
+"""GPU: the drop-in layer (flatten -> C ABI -> write-back onto the objects) on stand-in lattice objects."""
+import numpy as np
+import pytest
+
+from conftest import E_MOD, NU
+from fake_lattice import FakeLattice
+from oracle import lattice_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def test_solve_fem_dropin_writes_back_like_the_reference(ctx):
+    from pylatticedso_b200 import mesh as M
+    from pylatticedso_b200.fem import solve_FEM_B200
+    lat = FakeLattice("BCC", (3, 2, 2), 0.05)
+    lat.compression()
+    xsol, model = solve_FEM_B200(lat, elements_per_strut=2, tol=1e-12, ctx=ctx)
+    assert model.info["info"] == 0
+    mesh = M.mesh_from_synthetic(lat.syn, 2)
+    fixed, g, f = M.compression_bc(mesh)
+    K = orc.assemble_csr(mesh.xyz, np.stack([mesh.en0, mesh.en1], 1), mesh.rad, E_MOD, NU)
+    uo, Ro = orc.solve_static(K, fixed.astype(bool), g, f)
+    uo, Ro = uo.reshape(-1, 6), Ro.reshape(-1, 6)
+    for p in lat.points:
+        assert np.abs(np.array(p.displacement_vector) - uo[p.index]).max() < 1e-8 * np.abs(uo).max()
+        if any(p.fixed_DOF):
+            k = sum(1 for c in lat.cells if p in c.points_cell)   # reactions accumulate once per containing cell
+            assert np.abs(np.array(p.reaction_force_vector) - k * Ro[p.index]).max() < 1e-8 * np.abs(Ro).max() * k
+    xs, idx = lat.get_global_displacement()
+    assert np.array_equal(xsol, xs) and len(idx) == len(xs)
+
+
+def test_get_schur_complement_dropin(ctx):
+    from pylatticedso_b200.schur import get_schur_complement
+    from pylatticedso_b200.mesh import flatten_lattice, cell_boundary_dofs
+    lat = FakeLattice("BCC", (2, 1, 1), 0.04)
+    with pytest.raises(ValueError):
+        get_schur_complement(lat, None, elements_per_strut=3, ctx=ctx)      # utils_schur.py:35-36
+    S = get_schur_complement(lat, 1, elements_per_strut=3, ctx=ctx)
+    mesh = flatten_lattice(lat, 1, 3)
+    bnd = cell_boundary_dofs(lat.cells[1], mesh)
+    K = orc.assemble_csr(mesh.xyz, np.stack([mesh.en0, mesh.en1], 1), mesh.rad, E_MOD, NU)
+    So = orc.schur_complement(K, bnd)
+    assert S.shape == (48, 48) and np.abs(S - So).max() < 1e-11 * np.abs(So).max()
+
+
+def test_solve_ddm_dropin_matches_fem(ctx):
+    from pylatticedso_b200.ddm import solve_DDM_B200
+    from pylatticedso_b200.fem import solve_FEM_B200
+    from pylatticedso_b200.schur import get_schur_complement
+    a = FakeLattice("BCC", (2, 2, 2), 0.05); a.compression()
+    b = FakeLattice("BCC", (2, 2, 2), 0.05); b.compression()
+    x_fem, _ = solve_FEM_B200(a, elements_per_strut=2, tol=1e-13, ctx=ctx)
+    S = get_schur_complement(b, 0, elements_per_strut=2, ctx=ctx)            # identical cells share one matrix
+    for c in b.cells:
+        c.schur_complement = S
+    x_ddm, info, idx, rhs = solve_DDM_B200(b, tol=1e-13, ctx=ctx)
+    assert info == 0 and x_ddm.shape == x_fem.shape
+    # compare_FEM_DDM.py:37-38
+    assert np.linalg.norm(x_fem - x_ddm) / np.linalg.norm(x_fem) < 1e-8
