@@ -1135,36 +1135,45 @@ struct P2PPushArgs {
   int64_t nb_dst_node0[4];   // first destination node (peer local numbering) of my segment
   int my_rank;
 };
-// ONE CTA: push the owned boundary entries of u into the neighbours' ghost sections, publish `seq`, then
-// wait (bounded) until every neighbour has published the same `seq` into OUR arena.  The SpMV that follows
-// is the plain k_cg_spmv: the kernel boundary orders it after this wait and starts with a clean L1.
-__global__ void __launch_bounds__(1024) k_p2p_halo(const int32_t* __restrict__ send_idx, const double* __restrict__ u,
-                                                   unsigned char* const* __restrict__ peers, P2PPushArgs a, size_t u_off,
-                                                   PcgScalars* __restrict__ sc, PcgParams prm) {
+// Push the owned boundary entries of u into the neighbours' ghost sections (grid-stride over the send
+// list, st.global on the IPC-mapped peer pointers); the LAST CTA to finish publishes `seq` to every
+// neighbour and then waits (bounded) until every neighbour has published the same `seq` into OUR arena.
+// The SpMV that follows is the plain k_cg_spmv: the kernel boundary orders it after this wait and
+// starts with a clean L1.
+__global__ void __launch_bounds__(256) k_p2p_halo(const int32_t* __restrict__ send_idx, const double* __restrict__ u,
+                                                  unsigned char* const* __restrict__ peers, P2PPushArgs a, size_t u_off,
+                                                  PcgScalars* __restrict__ sc, PcgParams prm, unsigned int* __restrict__ ticket) {
   if (sc->done || sc->iters >= prm.maxiter) return;
   const unsigned long long seq = prm.seq_base + (unsigned long long)sc->seq + 1ull;  // sequence of the upcoming SpMV
   const int total = a.nb_first[a.n_nb];
-  for (int i = threadIdx.x; i < total * 6; i += blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total * 6; i += gridDim.x * blockDim.x) {
     const int e = i / 6, d = i - e * 6;
     int k = 0;
     while (k + 1 < a.n_nb && e >= a.nb_first[k + 1]) ++k;
     double* dst = reinterpret_cast<double*>(peers[a.nb_rank[k]] + u_off);
     dst[(a.nb_dst_node0[k] + (e - a.nb_first[k])) * 6 + d] = u[(int64_t)send_idx[e] * 6 + d];
   }
+  __shared__ bool s_last;
   __threadfence_system();   // every thread: its peer stores are performed at system scope ...
-  __syncthreads();          // ... before thread 0 releases the flags
+  __syncthreads();          // ... before thread 0 takes the ticket
   if (threadIdx.x == 0) {
-    for (int k = 0; k < a.n_nb; ++k) {
-      P2PArenaHdr* hdr = reinterpret_cast<P2PArenaHdr*>(peers[a.nb_rank[k]]);
-      st_release_sys(&hdr->halo_flag[a.my_rank], seq);
-    }
-    const P2PArenaHdr* mine = reinterpret_cast<const P2PArenaHdr*>(peers[a.my_rank]);
-    for (int k = 0; k < a.n_nb; ++k) {
-      long long spins = 0;
-      while (ld_acquire_sys(&mine->halo_flag[a.nb_rank[k]]) < seq) {
-        if (++spins > (1ll << 24)) { sc->p2p_timeout = 1; break; }
-        __nanosleep(20);
-      }
+    const unsigned int t = atomicAdd(ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence_system();
+  *ticket = 0u;
+  for (int k = 0; k < a.n_nb; ++k) {
+    P2PArenaHdr* hdr = reinterpret_cast<P2PArenaHdr*>(peers[a.nb_rank[k]]);
+    st_release_sys(&hdr->halo_flag[a.my_rank], seq);
+  }
+  const P2PArenaHdr* mine = reinterpret_cast<const P2PArenaHdr*>(peers[a.my_rank]);
+  for (int k = 0; k < a.n_nb; ++k) {
+    long long spins = 0;
+    while (ld_acquire_sys(&mine->halo_flag[a.nb_rank[k]]) < seq) {
+      if (++spins > (1ll << 24)) { sc->p2p_timeout = 1; break; }
+      __nanosleep(20);
     }
   }
 }
@@ -1315,6 +1324,12 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
     pa.nb_first[h->n_neighbors] = push_total;
   }
   const size_t u_off = sizeof(P2PArenaHdr);
+  unsigned halo_grid = (unsigned)ceil_div((int64_t)push_total * 6, 256 * 8);   // ~8 entries per thread
+  if (halo_grid < 1) halo_grid = 1;
+  if (halo_grid > 64) halo_grid = 64;
+  unsigned int* halo_ticket = lat_buf<unsigned int>(ctx, "p2p_ticket", 4);
+  if (!halo_ticket) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+  if (p2p) LAT_CUDA(ctx, cudaMemsetAsync(halo_ticket, 0, 4 * sizeof(unsigned int), ctx->stream));
   {  // the halo send buffer must exist before any stream capture (allocation is not capturable)
     int64_t tot_send = 0;
     for (int i = 0; i < h->n_neighbors; ++i) tot_send += h->send_count[i];
@@ -1337,7 +1352,7 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
   auto spmv_and_reduce = [&]() -> int {
     if (p2p) {
       if (h->n_neighbors > 0)
-        LAT_LAUNCH(ctx, k_p2p_halo, 1, 1024, 0, h->send_idx, u, pp->d_peer, pa, u_off, sc, prm);
+        LAT_LAUNCH(ctx, k_p2p_halo, halo_grid, 256, 0, h->send_idx, u, pp->d_peer, pa, u_off, sc, prm, halo_ticket);
       LAT_LAUNCH(ctx, k_cg_spmv, grid, SPMV_BLOCK, 0, rowptr, colidx, vals, n_own, u, r, w, sc, partials, prm);
       LAT_LAUNCH(ctx, k_p2p_reduce, 1, 1024, 0, partials, (int)grid, sc, prm, pp->d_peer, pp->nranks, pp->rank);
       return LAT_OK;
