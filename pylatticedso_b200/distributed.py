@@ -193,6 +193,22 @@ class DistributedFEM:
         R = ctx.spmv(self.rowptr, self.colidx, self.vals, u)     # rows >= n_owned are partial: ignore
         return u, R, info
 
+    def compliance_gradient(self, u_local, group_global, n_groups, chain_global=None):
+        """g[p] = -sum_e chain_e u_e^T dK_e/dr u_e over ALL elements of the lattice (lattice_opti.py:746-841).
+        Every element is counted on exactly one rank (the owner of its first node); the per-rank partial
+        gradients are summed with one all-reduce.  ``u_local`` must carry valid ghosts (``solve`` returns it so)."""
+        torch = self.torch
+        e = self.part.local_elems
+        owner_first = self.lmesh.en0 < self.n_owned            # first node owned by this rank
+        grp = np.where(owner_first, np.asarray(group_global)[e], -1).astype(np.int32)
+        dev = self.ctx.device
+        ch = None
+        if chain_global is not None:
+            ch = torch.from_numpy(np.ascontiguousarray(np.asarray(chain_global)[e], dtype=np.float64)).to(dev)
+        g = self.ctx.compliance_grad(self.x, self.y, self.z, self.en0, self.en1, self.rad, torch.from_numpy(grp).to(dev),
+                                     n_groups, u_local, self.young, self.nu, self.kappa, chain=ch)
+        return self.ctx.allreduce_sum(g)
+
     def gather_owned(self, vec_local):
         """All-gather the owned part of a local vector into a global numpy vector (test / write-back helper)."""
         import torch.distributed as dist

@@ -47,6 +47,14 @@ def main():
                       f"info={info['info']} relres={info['relres']:.1e} solve_ms={info['solve_ms']:.2f} |u-uo|/|uo|={eu:.2e} "
                       f"|R-Ro|/|Ro|={er:.2e}", flush=True)
                 ok = ok and info["info"] == 0 and eu < 1e-8 and er < 1e-8
+        # sharded compliance gradient w.r.t. per-cell radii == oracle's
+        ncell = int(mesh.cell_of_elem.max()) + 1
+        gd = dfem.compliance_gradient(u, mesh.cell_of_elem, ncell).cpu().numpy()
+        if rank == 0:
+            go = orc.compliance_gradient(mesh.xyz, np.stack([mesh.en0, mesh.en1], 1), mesh.rad, uo, mesh.cell_of_elem, ncell, E, NU)
+            eg = np.abs(gd - go).max() / np.abs(go).max()
+            print(f"[dist_check] gradient {geom}{n} world={world} n_groups={ncell} |g-go|/|go|={eg:.2e}", flush=True)
+            ok = ok and eg < 1e-6
         ctx.p2p_destroy()
     ctx.comm_destroy()
     dist.barrier()
