@@ -131,6 +131,41 @@ __global__ void __launch_bounds__(256) k_chunk(const int* __restrict__ rowptr, c
   }
 }
 
+// Clone of the library's k_cg_spmv with switches: STATUS (dependent status-word check), MINB (min CTAs/SM),
+// LATE (own-row loads after the loop instead of before).
+template <int STATUS, int MINB, int LATE>
+__global__ void __launch_bounds__(256, MINB) k_cgclone(const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                                                        const double* __restrict__ vals, int n_nodes, const double* __restrict__ u,
+                                                        const double* __restrict__ r, double* __restrict__ w,
+                                                        const int* __restrict__ status, double* __restrict__ part) {
+  __shared__ double sp[3][8];
+  const int lane = threadIdx.x & 31, g = lane / 6, rr_ = lane - g * 6;
+  const long warp = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long n = warp * 5 + g;
+  const bool active = g < 5 && n < n_nodes;
+  int lo = 0, hi = 0; double uo = 0, ro = 0;
+  const long i = n * 6 + rr_;
+  if (active) { lo = __ldg(rowptr + n); hi = __ldg(rowptr + n + 1); if (!LATE) { uo = u[i]; ro = r[i]; } }
+  if (STATUS) { if (status[0] || status[1] >= 1000000) return; }
+  double acc = 0;
+#pragma unroll 4
+  for (int j = lo; j < hi; ++j) {
+    const int c = __ldg(colidx + j);
+    const double2* vp = reinterpret_cast<const double2*>(vals + (long)j * 36 + rr_ * 6);
+    const double2* xp = reinterpret_cast<const double2*>(u + (long)c * 6);
+    const double2 a0 = __ldcs(vp), a1 = __ldcs(vp + 1), a2 = __ldcs(vp + 2);
+    const double2 x0 = xp[0], x1 = xp[1], x2 = xp[2];
+    acc += a0.x * x0.x + a0.y * x0.y + a1.x * x1.x + a1.y * x1.y + a2.x * x2.x + a2.y * x2.y;
+  }
+  if (active) { w[i] = acc; if (LATE) { uo = u[i]; ro = r[i]; } }
+  double d0 = ro * uo, d1 = acc * uo, d2 = ro * ro;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { d0 += __shfl_xor_sync(~0u, d0, o); d1 += __shfl_xor_sync(~0u, d1, o); d2 += __shfl_xor_sync(~0u, d2, o); }
+  if (lane == 0) { sp[0][threadIdx.x >> 5] = d0; sp[1][threadIdx.x >> 5] = d1; sp[2][threadIdx.x >> 5] = d2; }
+  __syncthreads();
+  if (threadIdx.x < 3) { double s2 = 0; for (int k = 0; k < 8; ++k) s2 += sp[threadIdx.x][k]; part[threadIdx.x * gridDim.x + blockIdx.x] = s2; }
+}
+
 // Persistent variant: grid = SMs x k CTAs; each CTA owns a contiguous range of rows (equal nnz), warps walk it
 // in tiles of 5 rows.  MODE as above.
 template <int MODE, int THREADS>
@@ -212,6 +247,13 @@ int main(int argc, char** argv) {
   timeit("chunk4 spmv", [&] { k_chunk<4, 0><<<grid, 256>>>(drp, dci, vals, N, x, x2, y, part); }, bytes_1);
   timeit("chunk3 spmv + 3 dots", [&] { k_chunk<3, 1><<<grid, 256>>>(drp, dci, vals, N, x, x2, y, part); }, bytes_c);
   timeit("chunk4 spmv + 3 dots", [&] { k_chunk<4, 1><<<grid, 256>>>(drp, dci, vals, N, x, x2, y, part); }, bytes_c);
+  int* dstat; CK(cudaMalloc(&dstat, 16)); CK(cudaMemset(dstat, 0, 16));
+  timeit("cgclone status=1 minb=1 early", [&] { k_cgclone<1, 1, 0><<<grid, 256>>>(drp, dci, vals, N, x, x2, y, dstat, part); }, bytes_c);
+  timeit("cgclone status=0 minb=1 early", [&] { k_cgclone<0, 1, 0><<<grid, 256>>>(drp, dci, vals, N, x, x2, y, dstat, part); }, bytes_c);
+  timeit("cgclone status=1 minb=6 early", [&] { k_cgclone<1, 6, 0><<<grid, 256>>>(drp, dci, vals, N, x, x2, y, dstat, part); }, bytes_c);
+  timeit("cgclone status=1 minb=8 early", [&] { k_cgclone<1, 8, 0><<<grid, 256>>>(drp, dci, vals, N, x, x2, y, dstat, part); }, bytes_c);
+  timeit("cgclone status=1 minb=1 late", [&] { k_cgclone<1, 1, 1><<<grid, 256>>>(drp, dci, vals, N, x, x2, y, dstat, part); }, bytes_c);
+  timeit("cgclone status=1 minb=6 late", [&] { k_cgclone<1, 6, 1><<<grid, 256>>>(drp, dci, vals, N, x, x2, y, dstat, part); }, bytes_c);
   if (argc > 3) return 0;
   // persistent variants
   for (int k : {2, 4}) {
