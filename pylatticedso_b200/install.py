@@ -22,6 +22,9 @@ def patch_reference(elements_per_strut="gmsh"):
     def _schur(lattice, cell_index=None):
         return schur.get_schur_complement(lattice, cell_index, elements_per_strut=elements_per_strut)
 
+    # conjugate_gradient_solver is NOT rebound blindly: the reference passes scipy LinearOperators wrapping its
+    # Python cell loop (lattice_sim.py:1148-1160); the device version (pylatticedso_b200.pcg) takes a BsrOperator.
+    # The DDM path is replaced as a whole by ddm.solve_DDM_B200 instead.
     for modname, attr, fn in (("pyLatticeSim.utils_simulation", "solve_FEM_FenicsX", _solve),
                               ("pyLatticeOpti.lattice_opti", "solve_FEM_FenicsX", _solve),
                               ("pyLatticeSim.utils_schur", "get_schur_complement", _schur),

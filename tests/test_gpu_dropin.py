@@ -58,3 +58,28 @@ def test_solve_ddm_dropin_matches_fem(ctx):
     assert info == 0 and x_ddm.shape == x_fem.shape
     # compare_FEM_DDM.py:37-38
     assert np.linalg.norm(x_fem - x_ddm) / np.linalg.norm(x_fem) < 1e-8
+
+
+@pytest.mark.parametrize("name", ["well_default", "ill_clamp"])
+def test_conjugate_gradient_solver_dropin(ctx, name):
+    """Same call as the reference's conjugate_gradient_solver(A, b, M, maxiter, tol, mintol, restart_every,
+    alpha_max) -> (x, info), on a device operator; outputs frozen from the reference's own solver."""
+    import torch
+    from conftest import load_golden
+    from pylatticedso_b200.pcg import BsrOperator, Jacobi, conjugate_gradient_solver
+    G = load_golden("pcg_reference.npz")
+    A = G["A_well"] if name.startswith("well") else G["A_ill"]
+    nb = A.shape[0] // 6
+    t = lambda a, d: torch.from_numpy(np.ascontiguousarray(a, dtype=d)).to(ctx.device)
+    op = BsrOperator(ctx, t(np.arange(0, nb * nb + 1, nb), np.int32), t(np.tile(np.arange(nb), nb), np.int32),
+                     t(A.reshape(nb, 6, nb, 6).transpose(0, 2, 1, 3).reshape(-1), np.float64))
+    maxiter, tol, mintol, restart, amax = G[f"{name}_params"]
+    seen = []
+    x, info = conjugate_gradient_solver(op, G[f"{name}_b"], M=Jacobi if bool(G[f"{name}_jacobi"]) else None,
+                                        maxiter=int(maxiter), tol=tol, mintol=mintol, restart_every=int(restart),
+                                        alpha_max=amax, callback=seen.append)
+    assert info == int(G[f"{name}_info"]) and len(seen) == 1
+    assert np.abs(x - G[f"{name}_x"]).max() < 1e-9 * np.abs(G[f"{name}_x"]).max()
+    assert np.abs(op @ x - A @ x).max() < 1e-12 * np.abs(A @ x).max()
+    with pytest.raises(TypeError):
+        conjugate_gradient_solver(A, G[f"{name}_b"])          # a host matrix is not accepted: no CPU fallback
