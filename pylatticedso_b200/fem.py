@@ -162,3 +162,37 @@ def solve_FEM_B200(lattice, elements_per_strut="gmsh", tol=1e-10, maxiter=500000
                 node.set_reaction_force([float(v) for v in R_h[loc[node.index]]])
     xsol, _ = lattice.get_global_displacement()
     return xsol, FEMResult(fem, u, R, info, fixed)
+
+
+def compliance_gradient_lattice(lattice, model: FEMResult, optimization_type="unit_cell"):
+    """dC/d(param) in the parameter order of ``LatticeOpti.calculate_gradient`` (lattice_opti.py:752-761:
+    ``cell.index * n_geom + j`` for ``unit_cell``, ``j`` for hybrid ``constant``), sign of :719 included.
+
+    The reference evaluates  -sum_c u_c^T (dS_c/dr_j) u_c  with one Schur matrix per cell built from
+    ``cell.beams_cell`` -- a strut shared by k cells therefore contributes to the parameter of EACH of its
+    cells (cell.py:914-915 changes it from every owner).  The element form used here reproduces that by
+    giving every (cell, strut) incidence its own pass of ``lat_compliance_grad``.
+    """
+    import torch
+    fem = model.fem
+    mesh = fem.mesh
+    n_geom = len(getattr(lattice, "geom_types", [0])) if hasattr(lattice, "geom_types") else 1
+    cells = list(lattice.cells)
+    n_params = len(cells) * n_geom if optimization_type == "unit_cell" else n_geom
+    # (beam.index -> list of parameter ids), one entry per owning cell
+    owners = {}
+    for c in cells:
+        for b in c.beams_cell:
+            j = int(getattr(b, "type_beam", 0))
+            pid = c.index * n_geom + j if optimization_type == "unit_cell" else j
+            owners.setdefault(b.index, []).append(pid)
+    depth = max(len(v) for v in owners.values())
+    grad = torch.zeros(n_params, dtype=torch.float64, device=fem.ctx.device)
+    chain = torch.from_numpy(np.ascontiguousarray(mesh.chain, dtype=np.float64)).to(fem.ctx.device)
+    for layer in range(depth):
+        table = {bi: (v[layer] if layer < len(v) else -1) for bi, v in owners.items()}
+        grp = np.array([table.get(int(bi), -1) for bi in mesh.beam_of_elem], dtype=np.int32)
+        grad += fem.ctx.compliance_grad(fem.x, fem.y, fem.z, fem.en0, fem.en1, fem.rad,
+                                        torch.from_numpy(grp).to(fem.ctx.device), n_params, model.u, fem.young, fem.nu,
+                                        fem.kappa, chain=chain)
+    return grad.cpu().numpy()

@@ -83,3 +83,23 @@ def test_conjugate_gradient_solver_dropin(ctx, name):
     assert np.abs(op @ x - A @ x).max() < 1e-12 * np.abs(A @ x).max()
     with pytest.raises(TypeError):
         conjugate_gradient_solver(A, G[f"{name}_b"])          # a host matrix is not accepted: no CPU fallback
+
+
+def test_compliance_gradient_lattice_parameter_order(ctx):
+    """Parameter order cell.index * n_geom + j (lattice_opti.py:758-761) and the value against the oracle."""
+    from pylatticedso_b200 import mesh as M
+    from pylatticedso_b200.fem import compliance_gradient_lattice, solve_FEM_B200
+    lat = FakeLattice("BCC", (3, 1, 1), 0.05)
+    for p in lat.points:                          # clamp Xmin, tip load on Xmax (dedup: every load once)
+        if p.x == 0.0:
+            p.fixed_DOF = [True] * 6
+        elif p.x == 3.0:
+            p.applied_force[2] = -0.025
+    xsol, model = solve_FEM_B200(lat, elements_per_strut=3, tol=1e-13, dedup_point_loads=True, ctx=ctx)
+    g = compliance_gradient_lattice(lat, model)
+    mesh = model.fem.mesh
+    en = np.stack([mesh.en0, mesh.en1], 1)
+    go = orc.compliance_gradient(mesh.xyz, en, mesh.rad, model.u.cpu().numpy(), lat.syn.b_cell[mesh.beam_of_elem], 3,
+                                 E_MOD, NU, chain=mesh.chain)
+    assert g.shape == (3,) and np.abs(g - go).max() < 1e-9 * np.abs(go).max()
+    assert (g < 0).all() and abs(g[0]) > abs(g[1]) > abs(g[2])     # thicker struts near the clamp help most
