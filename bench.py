@@ -299,7 +299,7 @@ def run_b200(args):
     for _ in range(args.steps):
         flush.fill_(1.0)            # evict the previous step's matrix from L2 (untimed)
         barrier()
-        e, info, _ = step(64)
+        e, info, _ = step(32)
         barrier()
         tot_ms += e[0].elapsed_time(e[3])
         asm_ms += e[0].elapsed_time(e[1])

@@ -216,6 +216,30 @@ def make_grad_loop(ls):
         ls.get_schur_complement = orig
 
 
+def make_c1_parity(ls):
+    """BASELINE configs[0] in parity mode: BCC 5x5x5, r = 0.05, joint penalisation on, reference gmsh
+    subdivision (h = 0.05): 2 992 beams -> 18 992 elements / 18 333 nodes / 109 998 DOF, uniaxial compression.
+    Mesh and BCs come from the reference object graph; the stored solution is the oracle's direct solve."""
+    bc = {"Displacement": {
+        "Fixed": {"Surface": ["Zmin"], "DOF": ["X", "Y", "Z", "RX", "RY", "RZ"], "Value": [0, 0, 0, 0, 0, 0]},
+        "Load": {"Surface": ["Zmax"], "DOF": ["Z"], "Value": [-0.01]}}}
+    refshim.set_inline_presets({"c1": base_cfg("BCC", (5, 5, 5), [0.05], True, False, {"boundary_conditions": bc})})
+    with quiet():
+        lat = ls.LatticeSim("c1")
+    mesh = M.flatten_lattice(lat, None, "gmsh")
+    fixed, g, f = M.bc_arrays_from_lattice(lat, mesh)
+    K = orc.assemble_csr(mesh.xyz, np.stack([mesh.en0, mesh.en1], 1), mesh.rad, E_MOD, NU)
+    u, R = orc.solve_static(K, fixed.astype(bool), g, f)
+    npnt = mesh.n_points
+    print(f"c1_parity: beams={len(lat.beams)} nodes={mesh.n_nodes} elements={mesh.n_elems} dof={mesh.n_dof} "
+          f"fixed={int(fixed.sum())} |u|max={np.abs(u).max():.4e}")
+    arr = mesh_arrays(mesh)
+    arr["rad"] = arr["rad"].astype(np.float64)
+    np.savez_compressed(os.path.join(HERE, "c1_parity_bcc555.npz"), fixed=np.packbits(fixed), g_nonzero_idx=np.flatnonzero(g),
+                        g_nonzero_val=g[np.flatnonzero(g)], u_points_oracle=u.reshape(-1, 6)[:npnt],
+                        reactions_points_oracle=R.reshape(-1, 6)[:npnt], n_dof=np.int64(mesh.n_dof), **arr)
+
+
 def make_pcg(ls):
     import importlib
     cgm = importlib.import_module("pyLatticeSim.conjugate_gradient_solver")
@@ -254,6 +278,7 @@ def main():
     make_numbering(ls)
     make_ddm_loop(ls)
     make_grad_loop(ls)
+    make_c1_parity(ls)
     make_pcg(ls)
     tot = sum(os.path.getsize(os.path.join(HERE, f)) for f in os.listdir(HERE) if f.endswith(".npz"))
     print(f"total fixture size {tot / 1e6:.2f} MB")

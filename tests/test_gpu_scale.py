@@ -76,3 +76,27 @@ def test_octet40_graded_gradient_full_size(ctx):
     # atomic and gather assembly agree
     va = ctx.assemble_bsr(x, y, z, en0, en1, rad, m.n_nodes, colidx.numel(), E_MOD, NU, mode=L.ASM_ATOMIC)
     assert float((va - vals).abs().max()) < 1e-12 * float(vals.abs().max())
+
+
+def test_config0_bcc5_parity_mode_against_oracle(ctx):
+    """BASELINE configs[0]: BCC 5^3 with joint penalisation on the reference's gmsh subdivision
+    (18 333 nodes / 18 992 elements / 109 998 DOF, mesh and BCs dumped from the reference object graph):
+    displacements and reactions at the lattice points against the oracle's direct solve, 1e-8."""
+    from conftest import load_golden, mesh_from_npz
+    from pylatticedso_b200.fem import BeamFEM
+    G = load_golden("c1_parity_bcc555.npz")
+    m = mesh_from_npz(G)
+    assert (m.n_nodes, m.n_elems, m.n_dof) == (18333, 18992, 109998)
+    n = int(G["n_dof"])
+    fixed = np.unpackbits(G["fixed"])[:n].astype(np.uint8)
+    assert int(fixed.sum()) == 252
+    g = np.zeros(n); g[G["g_nonzero_idx"]] = G["g_nonzero_val"]
+    fem = BeamFEM(m, E_MOD, NU, ctx=ctx)
+    u, R, info = fem.solve(fixed, g, np.zeros(n), tol=1e-13, maxiter=2000000, precond=2)
+    assert info["info"] == 0
+    up = u.cpu().numpy().reshape(-1, 6)[: m.n_points]
+    Rp = R.cpu().numpy().reshape(-1, 6)[: m.n_points]
+    uo, Ro = G["u_points_oracle"], G["reactions_points_oracle"]
+    assert np.abs(up - uo).max() < 1e-8 * np.abs(uo).max()
+    fx = fixed.reshape(-1, 6)[: m.n_points].astype(bool)
+    assert np.abs(Rp[fx] - Ro[fx]).max() < 1e-8 * np.abs(Ro[fx]).max()
