@@ -111,6 +111,23 @@ class BeamFEM:
             self.vals = None
         return u, R, info
 
+    def adjoint_gradient(self, u, dJdu, fixed, group, n_groups, chain=None, tol=1e-10, maxiter=200000,
+                         precond=L.PC_BLOCK6):
+        """dJ/d(param) for an objective J(u) with dJ/du = ``dJdu`` (zero on constrained DOFs):
+        solve K lambda = dJ/du with the SAME constrained operator, then g[p] = -sum_e lambda_e^T dK_e/dr u_e.
+        (LatticeOpti's displacement objectives: adjoint S lambda = dJ/du and lambda^T dS u,
+        lattice_opti.py:843-902,1487-1648.)  Requires a previous ``solve`` (uses its eliminated matrix)."""
+        torch = self.torch
+        if self.vals_bc is None:
+            raise RuntimeError("adjoint_gradient needs the constrained operator of a previous solve()")
+        dev = self.ctx.device
+        fd = torch.as_tensor(np.ascontiguousarray(fixed, dtype=np.uint8)).to(dev) if not torch.is_tensor(fixed) else fixed
+        q = torch.as_tensor(np.ascontiguousarray(dJdu, dtype=np.float64)).to(dev) if not torch.is_tensor(dJdu) else dJdu.clone()
+        q = torch.where(fd.bool(), torch.zeros_like(q), q)
+        lam, info = self.ctx.pcg(self.rowptr, self.colidx, self.vals_bc, q, tol=tol, maxiter=maxiter, precond=precond)
+        g = self.compliance_gradient(u, group, n_groups, chain=chain, lam=lam)
+        return g, lam, info
+
     def compliance_gradient(self, u, group, n_groups, chain=None, lam=None):
         torch = self.torch
         dev = self.ctx.device

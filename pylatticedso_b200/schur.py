@@ -114,3 +114,28 @@ def synthetic_cell_batch(ctx, geom, radii, elements_per_strut, young, nu, cell_s
     ch = np.ones(mesh.n_elems) if with_gradients else None
     return CellBatch(ctx, xyz_b, l0, l1, rad_b, len(bnd), young, nu, elem_group=grp, chain=ch,
                      n_grad=1 if with_gradients else 0), bnd
+
+
+def save_schur_dataset(path, radius_values, schur_matrices):
+    """Write a batch of Schur complements in the reference's dataset schema (utils_schur.py:55-72:
+    ``radius_values`` [n, n_geom], ``schur_matrices`` [n, nB, nB]) so that
+    ``load_schur_complement_dataset`` (utils_schur.py:93-129), the preconditioner approximations
+    (lattice_sim.py:1312-1329) and the greedy reduced basis can consume GPU-computed batches."""
+    import torch
+    S = schur_matrices.cpu().numpy() if torch.is_tensor(schur_matrices) else np.asarray(schur_matrices)
+    rv = np.asarray(radius_values, dtype=np.float64)
+    if rv.ndim == 1:
+        rv = rv[:, None]
+    if rv.shape[0] != S.shape[0]:
+        raise ValueError("radius_values and schur_matrices must have the same leading dimension")
+    np.savez(path, radius_values=rv, schur_matrices=S)
+    return path
+
+
+def load_schur_dataset(path):
+    """{tuple(radii): S} exactly like ``load_schur_complement_dataset`` (utils_schur.py:108-124)."""
+    data = np.load(path, allow_pickle=True)
+    rv, S = data["radius_values"], data["schur_matrices"]
+    if np.ndim(rv[0]) == 0 or np.ndim(rv) == 1:
+        return {tuple(np.atleast_1d(rv)): S}
+    return {tuple(r): m for r, m in zip(rv, S)}

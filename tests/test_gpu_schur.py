@@ -131,3 +131,23 @@ def test_ddm_interface_solve_equals_full_fem(ctx):
     y1 = ctx.ddm_matvec(S, gidx, x)
     y2 = ctx.spmv(prob.rowptr, prob.colidx, prob.vals, x)
     assert float((y1 - y2).abs().max()) < 1e-11 * float(y2.abs().max())
+
+
+def test_schur_dataset_roundtrip_in_reference_schema(ctx, tmp_path):
+    """A GPU batch written in the reference's npz schema reproduces the reference's own stored dataset."""
+    from pylatticedso_b200.schur import local_cell_mesh, load_schur_dataset, save_schur_dataset
+    G = load_golden("schur_Hybrid4.npz")
+    S_all = []
+    for i in range(10):
+        m = mesh_from_npz(G, f"c{i}_")
+        bnd_nodes = G[f"c{i}_bnd"][::6] // 6
+        perm, xyz, l0, l1 = local_cell_mesh(m, bnd_nodes)
+        S_all.append(ctx.schur_batch(t(ctx, xyz[None], np.float64), t(ctx, l0, np.int32), t(ctx, l1, np.int32),
+                                     t(ctx, m.rad[None], np.float64), len(bnd_nodes), E_MOD, NU)[0])
+    import torch
+    p = save_schur_dataset(str(tmp_path / "Schur_complement_Hybrid4.npz"), G["radius_values"], torch.stack(S_all))
+    d = load_schur_dataset(p)
+    assert len(d) == 10
+    for i, r in enumerate(G["radius_values"]):
+        ref = G["schur_matrices"][i]
+        assert np.abs(d[tuple(r)] - ref).max() < 1e-11 * np.abs(ref).max()
