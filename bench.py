@@ -243,7 +243,8 @@ def run_b200(args):
             e[0].record()
             dfem.assemble(out=vals)
             e[1].record()
-            u, R, info = dfem.solve(tol=1e-8, maxiter=200000, precond=L.PC_BLOCK6, vals_bc=vals_bc, b=b_d, u=u_d)
+            u, R, info = dfem.solve(tol=1e-8, maxiter=200000, precond=L.PC_BLOCK6, vals_bc=vals_bc, b=b_d, u=u_d,
+                                    profile_iters=profile)
             e.append(ev()); e[2].record()
             return [e[0], e[1], e[1], e[2]], info, (u, R)
 
@@ -359,12 +360,9 @@ def run_b200(args):
     value = n_dof_global * res["iters"] / (tot_ms * 1e-3)
     e2e_val = n_dof_global * res["e2e_iters"] / (res["e2e_ms"] * 1e-3)
     nn, nz = res["n_nodes"], res["nnzb"]
-    if world == 1:
-        ach = spmv_bytes(nn, nz) / (res["spmv_ms"] * 1e-3) / 1e9
-        it_bytes = iteration_bytes(nn, nz, True)
-    else:
-        ach = None
-        it_bytes = iteration_bytes(res["n_nodes_all"], res["nnzb_all"], True)
+    # rank 0's own kernel: its launch processes rank 0's rows (nn, nz are rank-local for N > 1)
+    ach = spmv_bytes(nn, nz) / (res["spmv_ms"] * 1e-3) / 1e9 if res["spmv_ms"] > 0 else None
+    it_bytes = iteration_bytes(nn, nz, True) if world == 1 else iteration_bytes(res["n_nodes_all"], res["nnzb_all"], True)
     it_gbs = it_bytes * res["iters"] / (res["solve_ms"] * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -389,7 +387,8 @@ def run_b200(args):
                                        "(profiles/r01_ncu_full_v3_cg_kernels.csv)",
                      "peak_source": peak_src, "bytes_per_launch": spmv_bytes(nn, nz),
                      "avg_launch_ms": res["spmv_ms"], "launches_timed": res["nprof"],
-                     "note": None if world == 1 else "per-kernel timing is taken at N=1 only; see pcg.iteration_frac_of_hbm"},
+                     "note": None if world == 1 else "rank 0's kernel over rank 0's slab (per-GPU peak); see pcg.iteration_frac_of_hbm "
+                                                     "for the whole job against the aggregate peak"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": res["h2d"], "d2h_bytes_per_step": res["d2h"],
                 "ms_per_step": res["e2e_ms"] / args.steps},
         "gpu_launches": res["launches"],

@@ -171,7 +171,7 @@ class DistributedFEM:
         self.ctx.p2p_setup(self.n_local, self.part.peers, dst0)
         self.p2p = True
 
-    def solve(self, tol=1e-8, maxiter=200000, precond=2, vals_bc=None, b=None, u=None, check_every=0):
+    def solve(self, tol=1e-8, maxiter=200000, precond=2, vals_bc=None, b=None, u=None, check_every=0, profile_iters=0):
         """Returns (u_local [6 n_local] incl. ghosts, reactions on owned rows, info)."""
         torch, ctx = self.torch, self.ctx
         if self.vals is None:
@@ -187,7 +187,8 @@ class DistributedFEM:
                                               L._ptr(self.vals), L._ptr(self.fixed_d), L._ptr(self.g_d),
                                               L._ptr(self.f_d), L._ptr(vals_bc), L._ptr(b)))
         u, info = ctx.pcg_dist(self.rowptr, self.colidx, vals_bc, self.halo, b, u, tol=tol, maxiter=maxiter,
-                               precond=precond, check_every=check_every, p2p=getattr(self, "p2p", False))
+                               precond=precond, check_every=check_every, p2p=getattr(self, "p2p", False),
+                               profile_iters=profile_iters)
         ctx.set_dirichlet_values(self.fixed_d, self.g_d, u)
         ctx.halo_exchange(self.halo, u)
         R = ctx.spmv(self.rowptr, self.colidx, self.vals, u)     # rows >= n_owned are partial: ignore
