@@ -6,6 +6,7 @@
 // all vector traffic is coalesced, and the 6 lanes of a group read one 288 B
 // block of the matrix as 6 x 48 B (three 16 B loads per lane).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -1090,15 +1091,18 @@ extern "C" int lat_halo_exchange(lat_ctx* ctx, const lat_halo* halo, double* vec
 // * halo:  k_p2p_halo (one CTA) stores the owned boundary entries of u straight into the neighbour's ghost section
 //          (st.global on the mapped peer pointer), then publishes the sequence number with a system-scope
 //          release and waits for the neighbours' flags; the SpMV kernel that follows is the plain one.
-// * all-reduce: k_p2p_reduce sums the per-CTA partials, writes the 3 local sums into EVERY rank's mailbox
-//          (slot = my rank), releases the sequence number, then spins (bounded) until all slots carry it and
-//          adds them in rank order -- identical bits on every rank, no NCCL launch, ~2-3 us over NVSwitch.
+// * all-reduce: k_p2p_reduce sums the per-CTA partials and writes the 3 local sums into EVERY rank's mailbox
+//          (slot = my rank) as 8-byte {32 data bits | 32 flag bits} words (one NVLink hop, no fence / flag
+//          round trip), polls its own mailbox until every word carries this sequence's flag and adds the
+//          contributions in rank order -- identical bits on every rank, no NCCL launch.
 // All spins are bounded; a timeout sets breakdown = 2 and stops the solve instead of hanging the GPU.
 static constexpr int P2P_MAXR = 16;
-struct P2PMail { double v[3]; unsigned long long seq; };
+static constexpr int P2P_SLOTS = 32;          // halo flag slots per source rank (one per pushing CTA, wrapped)
+// "LL" mailbox word (as in NCCL's low-latency protocol): 32 data bits + 32 flag bits in ONE 8-byte store, which
+// is atomic, so no fence / separate flag round trip is needed: a double travels as two such words.
 struct P2PArenaHdr {
-  P2PMail mail[2][P2P_MAXR];
-  unsigned long long halo_flag[P2P_MAXR];   // indexed by SOURCE rank
+  unsigned long long mail[2][P2P_MAXR][6];                  // [parity][source rank][3 doubles x {lo, hi}]
+  unsigned long long halo_flag[P2P_MAXR][P2P_SLOTS];        // [source rank][slot]
   unsigned long long pad[16];
 };
 struct P2P {
@@ -1135,14 +1139,20 @@ struct P2PPushArgs {
   int64_t nb_dst_node0[4];   // first destination node (peer local numbering) of my segment
   int my_rank;
 };
-// Push the owned boundary entries of u into the neighbours' ghost sections (grid-stride over the send
-// list, st.global on the IPC-mapped peer pointers); the LAST CTA to finish publishes `seq` to every
-// neighbour and then waits (bounded) until every neighbour has published the same `seq` into OUR arena.
-// The SpMV that follows is the plain k_cg_spmv: the kernel boundary orders it after this wait and
-// starts with a clean L1.
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Push the owned boundary entries of u into the neighbours' ghost sections (grid-stride over the send list,
+// st.global on the IPC-mapped peer pointers).  Every CTA then publishes `seq` into ITS flag slots of every
+// neighbour's arena with one release store each (no local ticket, no second phase), and finally waits
+// (bounded) until all slots of all neighbours in OUR arena carry `seq`.  The SpMV that follows is the plain
+// k_cg_spmv: the kernel boundary orders it after this wait and starts with a clean L1.
 __global__ void __launch_bounds__(256) k_p2p_halo(const int32_t* __restrict__ send_idx, const double* __restrict__ u,
                                                   unsigned char* const* __restrict__ peers, P2PPushArgs a, size_t u_off,
-                                                  PcgScalars* __restrict__ sc, PcgParams prm, unsigned int* __restrict__ ticket) {
+                                                  PcgScalars* __restrict__ sc, PcgParams prm) {
   if (sc->done || sc->iters >= prm.maxiter) return;
   const unsigned long long seq = prm.seq_base + (unsigned long long)sc->seq + 1ull;  // sequence of the upcoming SpMV
   const int total = a.nb_first[a.n_nb];
@@ -1153,27 +1163,28 @@ __global__ void __launch_bounds__(256) k_p2p_halo(const int32_t* __restrict__ se
     double* dst = reinterpret_cast<double*>(peers[a.nb_rank[k]] + u_off);
     dst[(a.nb_dst_node0[k] + (e - a.nb_first[k])) * 6 + d] = u[(int64_t)send_idx[e] * 6 + d];
   }
-  __shared__ bool s_last;
-  __threadfence_system();   // every thread: its peer stores are performed at system scope ...
-  __syncthreads();          // ... before thread 0 takes the ticket
-  if (threadIdx.x == 0) {
-    const unsigned int t = atomicAdd(ticket, 1u);
-    s_last = (t == gridDim.x - 1);
+  __syncthreads();   // the CTA's peer stores happen-before thread 0's release stores (cumulativity)
+  // ONE system-scope fence, then relaxed flag stores spread over the lanes of warp 0 (a release store per
+  // slot would serialise one fence + NVLink round trip per slot: measured 83 instead of 67 us per iteration)
+  if (threadIdx.x < 32) {
+    if (threadIdx.x == 0) __threadfence_system();
+    __syncwarp();
+    for (int k = 0; k < a.n_nb; ++k) {
+      P2PArenaHdr* hdr = reinterpret_cast<P2PArenaHdr*>(peers[a.nb_rank[k]]);
+      const int sl = blockIdx.x + (int)threadIdx.x * gridDim.x;
+      if (sl < P2P_SLOTS)
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(&hdr->halo_flag[a.my_rank][sl]), "l"(seq) : "memory");
+    }
   }
-  __syncthreads();
-  if (!s_last || threadIdx.x != 0) return;
-  __threadfence_system();
-  *ticket = 0u;
-  for (int k = 0; k < a.n_nb; ++k) {
-    P2PArenaHdr* hdr = reinterpret_cast<P2PArenaHdr*>(peers[a.nb_rank[k]]);
-    st_release_sys(&hdr->halo_flag[a.my_rank], seq);
-  }
-  const P2PArenaHdr* mine = reinterpret_cast<const P2PArenaHdr*>(peers[a.my_rank]);
-  for (int k = 0; k < a.n_nb; ++k) {
-    long long spins = 0;
-    while (ld_acquire_sys(&mine->halo_flag[a.nb_rank[k]]) < seq) {
-      if (++spins > (1ll << 24)) { sc->p2p_timeout = 1; break; }
-      __nanosleep(20);
+  // wait for the neighbours: lane l of warp 0 polls slot l of every neighbour
+  if (threadIdx.x < P2P_SLOTS) {
+    const P2PArenaHdr* mine = reinterpret_cast<const P2PArenaHdr*>(peers[a.my_rank]);
+    for (int k = 0; k < a.n_nb; ++k) {
+      long long spins = 0;
+      while (ld_acquire_sys(&mine->halo_flag[a.nb_rank[k]][threadIdx.x]) < seq) {
+        if (++spins > (1ll << 24)) { sc->p2p_timeout = 1; break; }
+        __nanosleep(20);
+      }
     }
   }
 }
@@ -1183,35 +1194,52 @@ __global__ void __launch_bounds__(1024) k_p2p_reduce(const double* __restrict__ 
                                                      PcgScalars* __restrict__ sc, PcgParams prm,
                                                      unsigned char* const* __restrict__ peers, int nranks, int my_rank) {
   if (sc->done || sc->iters >= prm.maxiter) return;
+  __shared__ double s_loc[3];
+  __shared__ double s_tot[P2P_MAXR][3];
+  __shared__ int s_ok;
   double out[3];
   sum_partials<3, 1024>(partials, n_part, out);
-  if (threadIdx.x != 0) return;
   const unsigned long long seq = prm.seq_base + (unsigned long long)sc->seq + 1ull;
+  // 32-bit flag in the upper half of each word: 12 bits of the solve epoch + 20 bits of the iteration
+  // counter, never 0 (the arena starts zeroed) and never equal to what the previous solves left behind
+  const unsigned long long flag = ((((seq >> 32) & 0xfffull) << 20) | ((seq & 0xfffffull) + 1ull) | 0x80000000ull) << 32;
   const int par = (int)(seq & 1ull);
-  for (int q = 0; q < nranks; ++q) {
+  if (threadIdx.x == 0) { s_loc[0] = out[0]; s_loc[1] = out[1]; s_loc[2] = out[2]; s_ok = 1; }
+  __syncthreads();
+  // thread (q, w): word w (0..5) of my 3 sums into rank q's mailbox -- nranks * 6 independent 8-byte stores
+  if (threadIdx.x < nranks * 6) {
+    const int q = threadIdx.x / 6, w = threadIdx.x - q * 6;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(s_loc[w >> 1]);
+    const unsigned long long half = (w & 1) ? (bits >> 32) : (bits & 0xffffffffull);
     P2PArenaHdr* hdr = reinterpret_cast<P2PArenaHdr*>(peers[q]);
-    P2PMail* m = &hdr->mail[par][my_rank];
-    m->v[0] = out[0]; m->v[1] = out[1]; m->v[2] = out[2];
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(&hdr->mail[par][my_rank][w]), "l"(flag | half) : "memory");
   }
-  __threadfence_system();
-  for (int q = 0; q < nranks; ++q) {
-    P2PArenaHdr* hdr = reinterpret_cast<P2PArenaHdr*>(peers[q]);
-    st_release_sys(&hdr->mail[par][my_rank].seq, seq);
-  }
-  const P2PArenaHdr* mine = reinterpret_cast<const P2PArenaHdr*>(peers[my_rank]);
-  double tot[3] = {0.0, 0.0, 0.0};
-  bool ok = !sc->p2p_timeout;
-  for (int q = 0; q < nranks && ok; ++q) {
+  // thread (q, w) polls word w of rank q's contribution in MY mailbox until it carries this sequence's flag
+  unsigned long long word = 0;
+  if (threadIdx.x < nranks * 6) {
+    const int q = threadIdx.x / 6, w = threadIdx.x - q * 6;
+    const P2PArenaHdr* mine = reinterpret_cast<const P2PArenaHdr*>(peers[my_rank]);
     long long spins = 0;
-    while (ld_acquire_sys(&mine->mail[par][q].seq) < seq) {
-      if (++spins > (1ll << 24)) { ok = false; break; }
+    for (;;) {
+      word = ld_relaxed_sys(&mine->mail[par][q][w]);
+      if ((word & 0xffffffff00000000ull) == flag) break;
+      if (++spins > (1ll << 24)) { s_ok = 0; break; }
       __nanosleep(20);
     }
-    const volatile double* vv = mine->mail[par][q].v;
-    tot[0] += vv[0]; tot[1] += vv[1]; tot[2] += vv[2];
   }
+  // reassemble the doubles: lanes (q, 2k) and (q, 2k+1) hold lo / hi of sum k of rank q
+  const unsigned long long other = __shfl_down_sync(0xffffffffu, word, 1);
+  if (threadIdx.x < nranks * 6 && (threadIdx.x % 6) % 2 == 0) {
+    const int q = threadIdx.x / 6, w = threadIdx.x - q * 6;
+    const unsigned long long bits = (word & 0xffffffffull) | ((other & 0xffffffffull) << 32);
+    s_tot[q][w >> 1] = __longlong_as_double((long long)bits);
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  double tot[3] = {0.0, 0.0, 0.0};
+  for (int q = 0; q < nranks; ++q) { tot[0] += s_tot[q][0]; tot[1] += s_tot[q][1]; tot[2] += s_tot[q][2]; }   // rank order
   sc->seq = sc->seq + 1;
-  if (!ok) { sc->done = 1; sc->breakdown = 2; return; }
+  if (!s_ok || sc->p2p_timeout) { sc->done = 1; sc->breakdown = 2; return; }
   cg_finish(sc, prm, tot[0], tot[1], tot[2]);
 }
 
@@ -1326,10 +1354,7 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
   const size_t u_off = sizeof(P2PArenaHdr);
   unsigned halo_grid = (unsigned)ceil_div((int64_t)push_total * 6, 256 * 8);   // ~8 entries per thread
   if (halo_grid < 1) halo_grid = 1;
-  if (halo_grid > 64) halo_grid = 64;
-  unsigned int* halo_ticket = lat_buf<unsigned int>(ctx, "p2p_ticket", 4);
-  if (!halo_ticket) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
-  if (p2p) LAT_CUDA(ctx, cudaMemsetAsync(halo_ticket, 0, 4 * sizeof(unsigned int), ctx->stream));
+  if (halo_grid > (unsigned)P2P_SLOTS) halo_grid = P2P_SLOTS;
   {  // the halo send buffer must exist before any stream capture (allocation is not capturable)
     int64_t tot_send = 0;
     for (int i = 0; i < h->n_neighbors; ++i) tot_send += h->send_count[i];
@@ -1350,23 +1375,37 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
 
   // halo(u) -> w = A u, partial dots -> local sums -> all-reduce -> scalar recurrences / stop test
   cudaEvent_t prof_ev[2] = {nullptr, nullptr};
+  cudaEvent_t tr_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  double tr_ms[4] = {0.0, 0.0, 0.0, 0.0};
+  const bool trace = getenv("LAT_P2P_TRACE") != nullptr;
   bool prof_on = false;
   double prof_ms = 0.0;
   int prof_n = 0;
   auto spmv_and_reduce = [&]() -> int {
     if (p2p) {
+      if (prof_on && trace) cudaEventRecord(tr_ev[1], ctx->stream);
       if (h->n_neighbors > 0)
-        LAT_LAUNCH(ctx, k_p2p_halo, halo_grid, 256, 0, h->send_idx, u, pp->d_peer, pa, u_off, sc, prm, halo_ticket);
+        LAT_LAUNCH(ctx, k_p2p_halo, halo_grid, 256, 0, h->send_idx, u, pp->d_peer, pa, u_off, sc, prm);
+      if (prof_on && trace) cudaEventRecord(tr_ev[2], ctx->stream);
       if (prof_on) cudaEventRecord(prof_ev[0], ctx->stream);
       LAT_LAUNCH(ctx, k_cg_spmv, grid, SPMV_BLOCK, 0, rowptr, colidx, vals, n_own, u, r, w, sc, partials, prm);
       if (prof_on) cudaEventRecord(prof_ev[1], ctx->stream);
       LAT_LAUNCH(ctx, k_p2p_reduce, 1, 1024, 0, partials, (int)grid, sc, prm, pp->d_peer, pp->nranks, pp->rank);
+      if (prof_on && trace) cudaEventRecord(tr_ev[4], ctx->stream);
       if (prof_on) {
         cudaEventSynchronize(prof_ev[1]);
         float ms1 = 0.f;
         cudaEventElapsedTime(&ms1, prof_ev[0], prof_ev[1]);
         prof_ms += ms1;
         ++prof_n;
+        if (trace) {
+          cudaEventSynchronize(tr_ev[4]);
+          float a = 0.f, b2 = 0.f, c2 = 0.f;
+          cudaEventElapsedTime(&a, tr_ev[0], tr_ev[1]);   // update kernel
+          cudaEventElapsedTime(&b2, tr_ev[1], tr_ev[2]);  // halo push + wait
+          cudaEventElapsedTime(&c2, prof_ev[1], tr_ev[4]); // reduce + mailbox all-reduce
+          tr_ms[0] += a; tr_ms[1] += b2; tr_ms[2] += ms1; tr_ms[3] += c2;
+        }
       }
       return LAT_OK;
     }
@@ -1380,6 +1419,7 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
     return LAT_OK;
   };
   auto one_iteration = [&]() -> int {
+    if (prof_on && trace) cudaEventRecord(tr_ev[0], ctx->stream);
     LAT_LAUNCH(ctx, k_cg_update<PC>, grid, SPMV_BLOCK, 0, n_own, dinv, x, r, u, w, p, sv, sc, prm);
     return spmv_and_reduce();
   };
@@ -1444,11 +1484,16 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
   if (nprof > 0) {
     cudaEventCreate(&prof_ev[0]);
     cudaEventCreate(&prof_ev[1]);
+    for (auto& e : tr_ev) cudaEventCreate(&e);
     prof_on = true;
     for (int q = 0; q < nprof && rc == LAT_OK; ++q) rc = one_iteration();
     prof_on = false;
     cudaEventDestroy(prof_ev[0]);
     cudaEventDestroy(prof_ev[1]);
+    for (auto& e : tr_ev) cudaEventDestroy(e);
+    if (trace && prof_n > 0)
+      fprintf(stderr, "[lat p2p trace] rank %d: update %.1f us | halo push+wait %.1f us | spmv %.1f us | reduce+allreduce %.1f us (mean of %d)\n",
+              ctx->rank, 1e3 * tr_ms[0] / prof_n, 1e3 * tr_ms[1] / prof_n, 1e3 * tr_ms[2] / prof_n, 1e3 * tr_ms[3] / prof_n, prof_n);
     if (rc) return rc;
   }
   rc = run_batches((int64_t)o->maxiter - nprof);
