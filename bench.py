@@ -377,7 +377,7 @@ def run_b200(args):
                    "parallelism": "single" if world == 1 else f"slab{world}",
                    "exchange": None if world == 1 else comm_mode},
         "assembly": {"value": n_elem_global * args.steps / (res["asm_ms"] * 1e-3), "unit": "elements/s",
-                     "ms": res["asm_ms"] / args.steps, "mode": "gather (deterministic, fused element generation)",
+                     "ms": res["asm_ms"] / args.steps, "mode": "rows (deterministic, fused element generation, 256-bit stores)",
                      "pattern_build_ms_one_off": res.get("pattern_ms")},
         "pcg": {"solve_ms_per_step": res["solve_ms"] / args.steps, "iteration_GBps_survey_bytes": it_gbs,
                 "iteration_frac_of_hbm": it_gbs / (hbm_peak * world), "update_kernel_ms": res["update_ms"]},

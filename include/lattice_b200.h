@@ -41,6 +41,7 @@ typedef struct lat_ctx lat_ctx;
 /* assembly modes */
 #define LAT_ASM_GATHER 0 /* deterministic: one thread per BSR block gathers its elements */
 #define LAT_ASM_ATOMIC 1 /* one thread per element, warp-aggregated FP64 atomics          */
+#define LAT_ASM_ROWS 2   /* deterministic: one thread per block row, 256-bit stores; fastest, the host default */
 
 /* preconditioners */
 #define LAT_PC_NONE 0

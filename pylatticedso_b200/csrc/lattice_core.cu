@@ -537,6 +537,74 @@ __global__ void __launch_bounds__(ASM_BLOCK) k_assemble_gather(
   }
 }
 
+// Row mode: one thread per block ROW.  The thread walks the node's incidence list (sorted by neighbour, then
+// element); each incident element's coefficients are generated ONCE per end (twice per element instead of the
+// four times of the block-per-thread kernel), the off-diagonal quadrant is stored straight from registers
+// (32-byte stores into the row's contiguous 288 B blocks) and the diagonal quadrant is accumulated in
+// registers and written last.  No idle lanes while one lane sums a joint's 8-14 diagonal contributions,
+// no atomics, fixed summation order (bit-reproducible).
+// sm_100a has 256-bit global accesses (STG.E.256): nine per 288 B block instead of eighteen 128-bit ones.  A row
+// thread's stores are scattered across lanes (one line per lane), so the LSU cost is per instruction, not per byte.
+__device__ __forceinline__ void st256(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void ld256(const double* p, double& a, double& b, double& c, double& d) {
+  asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void store_block(double* __restrict__ dst, const double (&q)[36], bool accumulate) {
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    double a = q[4 * k], b = q[4 * k + 1], c = q[4 * k + 2], d = q[4 * k + 3];
+    if (accumulate) {
+      double oa, ob, oc, od;
+      ld256(dst + 4 * k, oa, ob, oc, od);
+      a += oa; b += ob; c += oc; d += od;
+    }
+    st256(dst + 4 * k, a, b, c, d);
+  }
+}
+
+__global__ void __launch_bounds__(128) k_assemble_rows(
+    const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+    const int32_t* __restrict__ en0, const int32_t* __restrict__ en1,
+    const double* __restrict__ rad, const double* __restrict__ chain,
+    const int32_t* __restrict__ adjptr, const int32_t* __restrict__ adj_other, const int32_t* __restrict__ adj_el,
+    const int32_t* __restrict__ rowptr, int64_t n_nodes, double young, double nu, double kappa,
+    int drad, double* __restrict__ vals) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_nodes) return;
+  const int lo = adjptr[n], hi = adjptr[n + 1];
+  if (hi == lo) return;                      // unconnected node: empty row
+  int w = rowptr[n];                         // next block to write in this row
+  int wdiag = -1;
+  double dacc[36];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) dacc[k] = 0.0;
+  int prev = -1;
+  for (int i = lo; i < hi; ++i) {
+    const int other = adj_other[i];
+    const int ee = adj_el[i];
+    const int e = ee >> 1, end = ee & 1;
+    const int a = en0[e], c = en1[e];
+    const ElemCoef co = elem_coef(x[a], y[a], z[a], x[c], y[c], z[c], rad[e], young, nu, kappa, drad != 0);
+    const double wt = (drad && chain) ? chain[e] : 1.0;
+    elem_block_accum(co, end, end, wt, dacc);
+    double q[36];
+#pragma unroll
+    for (int k = 0; k < 36; ++k) q[k] = 0.0;
+    elem_block_accum(co, end, end ^ 1, wt, q);
+    const bool dup = (other == prev);        // second strut between the same two nodes: add to the same block
+    if (!dup) {
+      if (wdiag < 0 && other > (int)n) { wdiag = w; ++w; }   // the diagonal block sits here in column order
+      ++w;
+    }
+    store_block(vals + (int64_t)(w - 1) * 36, q, dup);
+    prev = other;
+  }
+  if (wdiag < 0) wdiag = w;                  // all neighbours have smaller indices
+  store_block(vals + (int64_t)wdiag * 36, dacc, false);
+}
+
 // Atomic mode: one thread per element, 4 quadrants scatter-added with FP64 RED.
 // The two diagonal quadrants are warp-aggregated first: lanes whose quadrant
 // targets the same BSR block (consecutive elements of a strut, struts of one
@@ -600,12 +668,19 @@ extern "C" int lat_assemble_bsr(lat_ctx* ctx, const double* x, const double* y, 
                                 double nu, double kappa, int mode, int drad, double* vals) {
   if (!ctx) return LAT_ERR_ARG;
   LAT_CHECK_ARG(ctx, x && y && z && en0 && en1 && rad && vals);
-  LAT_CHECK_ARG(ctx, mode == LAT_ASM_GATHER || mode == LAT_ASM_ATOMIC);
+  LAT_CHECK_ARG(ctx, mode == LAT_ASM_GATHER || mode == LAT_ASM_ATOMIC || mode == LAT_ASM_ROWS);
   if (ctx->pat_nnzb < 0 || ctx->pat_nelem != n_elem || ctx->pat_nnodes != n_nodes)
     return lat_fail(ctx, LAT_ERR_STATE, "resident pattern does not match this mesh: call lat_bsr_pattern_build", __FILE__, __LINE__);
   LAT_CUDA(ctx, cudaSetDevice(ctx->device));
   const int64_t nz = ctx->pat_nnzb;
-  if (mode == LAT_ASM_GATHER) {
+  // the row kernel uses 256-bit stores; a misaligned values array takes the (bit-identical) gather kernel
+  if (mode == LAT_ASM_ROWS && (reinterpret_cast<uintptr_t>(vals) & 31) != 0) mode = LAT_ASM_GATHER;
+  if (mode == LAT_ASM_ROWS) {
+    LAT_LAUNCH(ctx, k_assemble_rows, (unsigned)ceil_div(n_nodes, 128), 128, 0, x, y, z, en0, en1, rad, chain,
+               (const int32_t*)ctx->bufs["pat_adjptr"].p, (const int32_t*)ctx->bufs["pat_adj_other"].p,
+               (const int32_t*)ctx->bufs["pat_adj_el"].p, (const int32_t*)ctx->bufs["pat_rowptr"].p, n_nodes, young, nu,
+               kappa, drad, vals);
+  } else if (mode == LAT_ASM_GATHER) {
     LAT_LAUNCH(ctx, k_assemble_gather, (unsigned)ceil_div(nz, ASM_BLOCK), ASM_BLOCK, 0, x, y, z, en0, en1, rad,
                chain, (const int32_t*)ctx->bufs["pat_blk_lo"].p, (const int32_t*)ctx->bufs["pat_blk_hi"].p,
                (const int32_t*)ctx->bufs["pat_blockrow"].p, (const int32_t*)ctx->bufs["pat_colidx"].p,

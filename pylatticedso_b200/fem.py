@@ -71,7 +71,7 @@ class BeamFEM:
         self.nnzb = int(self.colidx.numel())
         return self.rowptr, self.colidx
 
-    def assemble(self, mode=L.ASM_GATHER, out=None):
+    def assemble(self, mode=L.ASM_ROWS, out=None):
         if self.rowptr is None:
             self.build_pattern()
         self.vals = self.ctx.assemble_bsr(self.x, self.y, self.z, self.en0, self.en1, self.rad, self.n_nodes,

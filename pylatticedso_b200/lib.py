@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "liblattice_b200.so")
 SOURCES = ["lattice_core.cu", "lattice_solver.cu", "lattice_schur.cu"]
 HEADERS = [os.path.join(_HERE, "csrc", "common.cuh"), os.path.join(_ROOT, "include", "lattice_b200.h")]
 
-ASM_GATHER, ASM_ATOMIC = 0, 1
+ASM_GATHER, ASM_ATOMIC, ASM_ROWS = 0, 1, 2
 PC_NONE, PC_JACOBI, PC_BLOCK6 = 0, 1, 2
 
 EXPORTS = [
@@ -211,7 +211,7 @@ class Context:
         self.check(self.lib.lat_bsr_to_csr_values(self.h, _ptr(rowptr), rowptr.numel() - 1, _ptr(vals), _ptr(out)))
         return out
 
-    def assemble_bsr(self, x, y, z, en0, en1, rad, n_nodes, nnzb, young, nu, kappa=0.9, mode=ASM_GATHER,
+    def assemble_bsr(self, x, y, z, en0, en1, rad, n_nodes, nnzb, young, nu, kappa=0.9, mode=ASM_ROWS,
                      drad=False, chain=None, out=None):
         import torch
         vals = out if out is not None else torch.empty(nnzb * 36, dtype=torch.float64, device=self.device)

@@ -88,7 +88,7 @@ def test_pattern_is_bit_exact_with_scipy_csr(ctx, which):
         assert np.array_equal(rows[ebh[:, q]], ra) and np.array_equal(ci[ebh[:, q]], ca)
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("drad", [False, True])
 def test_assembly_matches_oracle(ctx, mode, drad):
     m = random_mesh(2)

@@ -36,6 +36,9 @@ for geom, n, m_, r in (("BCC", 60, 1, 0.05), ("Octet", 40, 1, 0.03)):
     ms = timeit(lambda: ctx.assemble_bsr(x, y, z, en0, en1, rad, N, nnzb, E, NU, out=vals))
     line("k_assemble_gather (fused)", cfg, Ecount, "elements", ms, Ecount * 1216)
     print(f"{'':34s} {'  actual HBM write 288 B/block':28s} {nnzb*288/ms/1e6:8.0f} GB/s  frac={nnzb*288/ms/1e6/peak:5.2f}")
+    ms = timeit(lambda: ctx.assemble_bsr(x, y, z, en0, en1, rad, N, nnzb, E, NU, mode=L.ASM_ROWS, out=vals))
+    line("k_assemble_rows (fused)", cfg, Ecount, "elements", ms, Ecount * 1216)
+    print(f"{'':34s} {'  actual HBM write 288 B/block':28s} {nnzb*288/ms/1e6:8.0f} GB/s  frac={nnzb*288/ms/1e6/peak:5.2f}")
     ms = timeit(lambda: ctx.assemble_bsr(x, y, z, en0, en1, rad, N, nnzb, E, NU, mode=L.ASM_ATOMIC, out=vals))
     line("k_assemble_atomic", cfg, Ecount, "elements", ms, Ecount * 1216)
     ctx.assemble_bsr(x, y, z, en0, en1, rad, N, nnzb, E, NU, out=vals)
