@@ -167,6 +167,26 @@ int lat_pcg_bsr(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, cons
                 int64_t n_nodes, const double* b, double* x, const lat_pcg_opts* opts,
                 lat_pcg_result* result);
 
+/* ---- matrix-free operator (B200 design choice, no reference counterpart) ---------------------
+ * The same linear system as lat_assemble_bsr + lat_apply_dirichlet + lat_pcg_bsr, but K is never
+ * stored: every product regenerates the element action from the geometry (beam_model.py:197-216 and
+ * material_definition.py:147 restated as f = a*d + b*t(t.d) + c*(t x d) per 3-vector, see
+ * csrc/matfree.cuh).  About a tenth of the HBM bytes of the assembled product and no 15 GB matrix at
+ * octet 100^3; iterates agree with the assembled path to rounding (tests/test_gpu_matfree.py).
+ *   lat_matfree_setup  needs the resident pattern of the same mesh (lat_bsr_pattern_build); `fixed` is the
+ *                      uint8[6 n_nodes] Dirichlet mask (NULL: none).  Call again when radii / mask change.
+ *   lat_matfree_apply  y = A u;  eliminated = 1: A = P K P + (I - P) (what the solver iterates on),
+ *                      eliminated = 0: the raw stiffness K (reactions R = K u - f).
+ *   lat_matfree_rhs    b = P (f - K g) + (I - P) g: the lifting of lat_apply_dirichlet (f may be NULL).
+ *   lat_pcg_matfree    Chronopoulos-Gear PCG on A; opts as lat_pcg_bsr, reference_semantics must be 0
+ *                      (LAT_ERR_UNSUPPORTED otherwise).  [syncs] */
+int lat_matfree_setup(lat_ctx* ctx, const double* x, const double* y, const double* z, const int32_t* en0,
+                      const int32_t* en1, const double* rad, int64_t n_elem, int64_t n_nodes, double young,
+                      double nu, double kappa, const uint8_t* fixed);
+int lat_matfree_apply(lat_ctx* ctx, const double* u, double* y, int eliminated);
+int lat_matfree_rhs(lat_ctx* ctx, const double* g, const double* f, double* b);
+int lat_pcg_matfree(lat_ctx* ctx, const double* b, double* x, const lat_pcg_opts* opts, lat_pcg_result* result);
+
 /* ---- (e) multi-GPU: slab partition, NCCL over NVLink ---------------------------------------
  * The reference is single-process (MPI.COMM_SELF, utils_simulation.py:39); this is the new exchange
  * step of the sharded PCG.  One process per GPU.  Each rank holds the block rows of the nodes it
@@ -194,6 +214,11 @@ int lat_halo_exchange(lat_ctx* ctx, const lat_halo* halo, double* vec);     /* v
 int lat_pcg_bsr_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, const double* vals,
                      const lat_halo* halo, const double* b, double* x, const lat_pcg_opts* opts,
                      lat_pcg_result* result);
+/* Matrix-free twin: the operator was set up (lat_matfree_setup) over the LOCAL mesh (n_local nodes, ghosts
+ * included); products run on the owned rows, ghosts of u arrive through the same NCCL / peer-memory halo
+ * (bit 4 of opts.reserved).  b: [6 n_owned] at least, x: [6 n_local].  [syncs] */
+int lat_pcg_matfree_dist(lat_ctx* ctx, const lat_halo* halo, const double* b, double* x, const lat_pcg_opts* opts,
+                         lat_pcg_result* result);
 
 /* NVLink peer-memory path (no NCCL inside the iteration): each rank creates one arena (mailboxes, halo
  * flags and the ghosted vector u), the host layer all-gathers the 64-byte CUDA IPC handles, every rank

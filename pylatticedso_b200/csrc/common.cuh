@@ -35,6 +35,9 @@ struct lat_ctx {
   std::map<std::string, DevBuf> bufs;
   // resident sparsity pattern (lat_bsr_pattern_build)
   int64_t pat_nelem = -1, pat_nnodes = -1, pat_nnzb = -1;
+  // resident matrix-free operator (lat_matfree_setup): material constants; arrays live in bufs "mf_*"
+  int64_t mf_nnodes = -1, mf_nelem = -1;
+  double mf_young = 0.0, mf_nu = 0.0, mf_kappa = 0.0;
   // pinned host staging
   PcgScalars* h_scal = nullptr;  // 2 slots
   int64_t* h_i64 = nullptr;

@@ -375,6 +375,7 @@ extern "C" int lat_bsr_pattern_build(lat_ctx* ctx, const int32_t* en0, const int
   LAT_CHECK_ARG(ctx, n_nodes < (int64_t)1 << 30 && n_elem < (int64_t)1 << 30);
   LAT_CUDA(ctx, cudaSetDevice(ctx->device));
   ctx->pat_nnzb = -1;
+  ctx->mf_nnodes = -1;   // a resident matrix-free operator refers to the old incidence lists
   int32_t* deg = lat_buf<int32_t>(ctx, "pat_deg", n_nodes + 1);
   int32_t* adjptr = lat_buf<int32_t>(ctx, "pat_adjptr", n_nodes + 1);
   int32_t* cursor = lat_buf<int32_t>(ctx, "pat_cursor", n_nodes + 1);

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "matfree.cuh"
 
 static constexpr int SPMV_BLOCK = 256;                        // 8 warps
 static constexpr int ROWS_PER_WARP = 5;
@@ -75,31 +76,19 @@ extern "C" int lat_bsr_spmv(lat_ctx* ctx, const int32_t* rowptr, const int32_t* 
 // ---------------------------------------------------------------------------
 // dinv layout: Jacobi -> [6n] reciprocal diagonal; block-Jacobi -> [n][21] packed upper triangle of the
 // (symmetric) inverse of the diagonal block.
-__global__ void k_precond_setup(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
-                                const double* __restrict__ vals, int64_t n_nodes, int precond,
-                                double* __restrict__ dinv) {
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= n_nodes) return;
-  int d = -1;
-  for (int j = rowptr[n]; j < rowptr[n + 1]; ++j)
-    if (colidx[j] == n) { d = j; break; }
+// Invert one diagonal block and store it in the dinv layout above.
+__device__ __forceinline__ void precond_store(double (&a)[6][6], int64_t n, int precond, double* __restrict__ dinv) {
   if (precond == LAT_PC_JACOBI) {
 #pragma unroll
-    for (int r = 0; r < 6; ++r) {
-      const double v = d >= 0 ? vals[(int64_t)d * 36 + r * 7] : 1.0;
-      dinv[n * 6 + r] = (v > 0.0) ? 1.0 / v : 1.0;
-    }
+    for (int r = 0; r < 6; ++r) dinv[n * 6 + r] = (a[r][r] > 0.0) ? 1.0 / a[r][r] : 1.0;
     return;
   }
   // 6x6 SPD inverse by Gauss-Jordan without pivoting
-  double a[6][6], inv[6][6];
+  double inv[6][6];
 #pragma unroll
   for (int i = 0; i < 6; ++i)
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      a[i][k] = d >= 0 ? vals[(int64_t)d * 36 + i * 6 + k] : (i == k ? 1.0 : 0.0);
-      inv[i][k] = (i == k) ? 1.0 : 0.0;
-    }
+    for (int k = 0; k < 6; ++k) inv[i][k] = (i == k) ? 1.0 : 0.0;
   bool ok = true;
 #pragma unroll
   for (int p = 0; p < 6; ++p) {
@@ -125,21 +114,66 @@ __global__ void k_precond_setup(const int32_t* __restrict__ rowptr, const int32_
       dinv[n * 21 + (i * (11 - i)) / 2 + k] = ok ? 0.5 * (inv[i][k] + inv[k][i]) : (i == k ? 1.0 : 0.0);
 }
 
+__global__ void k_precond_setup(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                const double* __restrict__ vals, int64_t n_nodes, int precond,
+                                double* __restrict__ dinv) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_nodes) return;
+  int d = -1;
+  for (int j = rowptr[n]; j < rowptr[n + 1]; ++j)
+    if (colidx[j] == n) { d = j; break; }
+  double a[6][6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a[i][k] = d >= 0 ? vals[(int64_t)d * 36 + i * 6 + k] : (i == k ? 1.0 : 0.0);
+  precond_store(a, n, precond, dinv);
+}
+
+// matrix-free operator: the diagonal blocks are regenerated from the geometry
+__global__ void k_mf_precond(MfOp op, int64_t n_nodes, int precond, double* __restrict__ dinv) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_nodes) return;
+  double a[6][6];
+  mf_diag_block(op, n, a);
+  precond_store(a, n, precond, dinv);
+}
+
+// The preconditioner entries of the lane's row can be fetched BEFORE the residual is known: doing so
+// explicitly puts them in the same memory round trip as the vector loads (nvcc only hoisted half of them).
+template <int PC>
+struct PrecondRow {
+  double d[PC == LAT_PC_BLOCK6 ? 6 : 1];
+};
+template <int PC>
+__device__ __forceinline__ PrecondRow<PC> load_precond(const double* __restrict__ dinv, int64_t n, int r, bool active) {
+  PrecondRow<PC> p;
+  if (PC == LAT_PC_JACOBI) p.d[0] = active ? __ldg(dinv + n * 6 + r) : 0.0;
+  if (PC == LAT_PC_BLOCK6) {
+    const double* blk = dinv + n * 21;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const int i = r < k ? r : k, j = r < k ? k : r;
+      p.d[k] = active ? __ldg(blk + (i * (11 - i)) / 2 + j) : 0.0;
+    }
+  }
+  return p;
+}
 // z_r = (M^-1 r)_r for the lane's DOF; rv = the lane's residual entry.  All 32 lanes must call.
+template <int PC>
+__device__ __forceinline__ double apply_precond(const PrecondRow<PC>& p, int g, double rv) {
+  if (PC == LAT_PC_NONE) return rv;
+  if (PC == LAT_PC_JACOBI) return p.d[0] * rv;
+  double z = 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) z = fma(p.d[k], __shfl_sync(0xffffffffu, rv, g * 6 + k), z);
+  return z;
+}
 template <int PC>
 __device__ __forceinline__ double apply_precond(const double* __restrict__ dinv, int64_t n, int g, int r,
                                                 bool active, double rv) {
-  if (PC == LAT_PC_NONE) return rv;
-  if (PC == LAT_PC_JACOBI) return active ? dinv[n * 6 + r] * rv : 0.0;
-  double z = 0.0;
-  const double* blk = dinv + n * 21;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    const double rk = __shfl_sync(0xffffffffu, rv, g * 6 + k);
-    const int i = r < k ? r : k, j = r < k ? k : r;
-    if (active) z = fma(blk[(i * (11 - i)) / 2 + j], rk, z);
-  }
-  return z;
+  const PrecondRow<PC> p = load_precond<PC>(dinv, n, r, active);
+  return apply_precond<PC>(p, g, rv);
 }
 
 // ---------------------------------------------------------------------------
@@ -404,6 +438,34 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_cg_spmv(const int32_t* __restric
   block_partials<3, SPMV_BLOCK>(v, partials);
 }
 
+// Matrix-free twin of k_cg_spmv: w = A u regenerated from the geometry (matfree.cuh, one thread per node),
+// same three dots.
+__global__ void __launch_bounds__(MF_BLOCK, 9) k_cg_spmv_mf(MfOp op, int64_t n_nodes, const double* __restrict__ u,
+                                                         const double* __restrict__ r, double* __restrict__ w,
+                                                         PcgScalars* __restrict__ sc, double* __restrict__ partials,
+                                                         PcgParams prm) {
+  const int64_t n = (int64_t)blockIdx.x * MF_BLOCK + threadIdx.x;
+  const bool active = n < n_nodes;
+  MfU rr;
+  rr.a = rr.b = rr.c = make_double2(0.0, 0.0);
+  if (active) rr = mf_load_u(r, n);
+  if (sc->done || sc->iters >= prm.maxiter) return;
+  double v[3] = {0.0, 0.0, 0.0};
+  if (active) {
+    double uo[6], f[6];
+    mf_node_product<true>(op, n, u, uo, f);
+    mf_store6(w, n, f);
+    const double ro[6] = {rr.a.x, rr.a.y, rr.b.x, rr.b.y, rr.c.x, rr.c.y};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      v[0] = fma(ro[k], uo[k], v[0]);
+      v[1] = fma(f[k], uo[k], v[1]);
+      v[2] = fma(ro[k], ro[k], v[2]);
+    }
+  }
+  block_partials<3, MF_BLOCK>(v, partials);
+}
+
 static constexpr int CG_REDUCE_BLOCK = 512;
 // One CTA: fixed-order sum of the per-CTA partials, then the scalar recurrences / stop test.
 __global__ void __launch_bounds__(CG_REDUCE_BLOCK) k_cg_reduce(const double* __restrict__ partials, int n_part,
@@ -431,13 +493,15 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_cg_update(int64_t n_nodes, const
   const int64_t i = n * 6 + rr_;
   double uv = 0.0, wv = 0.0, pv = 0.0, sv = 0.0, xv = 0.0, rv = 0.0;
   if (active) { uv = u[i]; wv = w[i]; pv = p[i]; sv = s[i]; xv = x[i]; rv = r[i]; }
-  if (sc->done || sc->iters >= prm.maxiter) return;
+  const PrecondRow<PC> pr = load_precond<PC>(dinv, n, rr_, active);   // same round trip as the vectors
+  const int done = sc->done, iters = sc->iters;
   const double alpha = sc->alpha, beta = sc->beta;
+  if (done || iters >= prm.maxiter) return;
   pv = fma(beta, pv, uv);
   sv = fma(beta, sv, wv);
   xv = fma(alpha, pv, xv);
   rv = fma(-alpha, sv, rv);
-  const double zn = apply_precond<PC>(dinv, n, g, rr_, active, rv);
+  const double zn = apply_precond<PC>(pr, g, rv);
   if (active) { p[i] = pv; s[i] = sv; x[i] = xv; r[i] = rv; u[i] = zn; }
 }
 
@@ -700,14 +764,16 @@ static int spmv_plan(lat_ctx* ctx, const int32_t* rowptr, int64_t n_nodes, SpmvP
 // ---------------------------------------------------------------------------
 template <int PC>
 static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, const double* vals,
-                   int64_t n_nodes, const double* b, double* x, const lat_pcg_opts* o, lat_pcg_result* res) {
+                   int64_t n_nodes, const double* b, double* x, const lat_pcg_opts* o, lat_pcg_result* res,
+                   const MfOp* mf = nullptr) {
   const int64_t n = 6 * n_nodes;
   const unsigned grid = (unsigned)ceil_div(n_nodes, ROWS_PER_CTA);
+  const unsigned mf_grid = (unsigned)ceil_div(n_nodes, MF_BLOCK);   // matrix-free product: one thread per node
   // The TMA-staged SpMV is opt-in (bit 1 of `reserved`): on B200 it measured 5-10 % SLOWER than the
   // direct-load kernel (tools/ab_spmv.py, profiles/r01_spmv_ab.txt) because the kernel is bound by
   // L2->SM traffic of the vector gathers, not by HBM latency.
   SpmvPlan plan;
-  if (o->reserved & 2) {
+  if ((o->reserved & 2) && !mf) {
     const int prc = spmv_plan(ctx, rowptr, n_nodes, &plan);
     if (prc) return prc;
   }
@@ -737,9 +803,11 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
   if (check > o->maxiter) check = o->maxiter > 0 ? o->maxiter : 1;
 
   // bit 3 of `reserved` forces the classic two-reduction recurrences in the textbook mode
-  const bool cgv = !o->reference_semantics && !(o->reserved & 8) && !plan.tma;
+  const bool cgv = mf || (!o->reference_semantics && !(o->reserved & 8) && !plan.tma);
   auto launch_spmv = [&](cudaStream_t st) {
-    if (cgv)
+    if (mf)
+      k_cg_spmv_mf<<<mf_grid, MF_BLOCK, 0, st>>>(*mf, n_nodes, z, r, Ap, sc, partials, prm);
+    else if (cgv)
       k_cg_spmv<<<grid, SPMV_BLOCK, 0, st>>>(rowptr, colidx, vals, n_nodes, z, r, Ap, sc, partials, prm);
     else if (plan.tma)
       k_spmv_tma<1><<<plan.grid, SPMV_BLOCK, plan.smem, st>>>(rowptr, colidx, vals, n_nodes, plan.cta_row0,
@@ -755,15 +823,17 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
   };
   // one iteration = (spmv, update) in the classic form, (update, spmv) in the Chronopoulos-Gear form
   auto launch_reduce = [&](cudaStream_t st) {
-    if (cgv) k_cg_reduce<<<1, CG_REDUCE_BLOCK, 0, st>>>(partials, (int)grid, sc, prm);
+    if (cgv) k_cg_reduce<<<1, CG_REDUCE_BLOCK, 0, st>>>(partials, (int)(mf ? mf_grid : grid), sc, prm);
   };
   auto launch_iteration = [&](cudaStream_t st) {
     if (cgv) { launch_update(st); launch_spmv(st); launch_reduce(st); }
     else { launch_spmv(st); launch_update(st); }
   };
   LAT_CUDA(ctx, cudaMemsetAsync(sc, 0, sizeof(PcgScalars), ctx->stream));
-  if (PC != LAT_PC_NONE)
-    LAT_LAUNCH(ctx, k_precond_setup, (unsigned)ceil_div(n_nodes, 128), 128, 0, rowptr, colidx, vals, n_nodes, PC, dinv);
+  if (PC != LAT_PC_NONE) {
+    if (mf) LAT_LAUNCH(ctx, k_mf_precond, (unsigned)ceil_div(n_nodes, 128), 128, 0, *mf, n_nodes, PC, dinv);
+    else LAT_LAUNCH(ctx, k_precond_setup, (unsigned)ceil_div(n_nodes, 128), 128, 0, rowptr, colidx, vals, n_nodes, PC, dinv);
+  }
   LAT_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
   if (cgv) {
     const int32_t one = 1;
@@ -878,7 +948,8 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
   // true-residual safeguard of the Chronopoulos-Gear form (see k_cg_restart)
   double true_rr = -1.0;
   while (rc == LAT_OK && cgv && hs[0].done && !hs[0].breakdown && hs[0].bb > 0.0) {
-    rc = lat_spmv_internal(ctx, rowptr, colidx, vals, n_nodes, x, Ap);
+    if (mf) { k_mf_apply<true><<<mf_grid, MF_BLOCK, 0, ctx->stream>>>(*mf, n_nodes, x, Ap); ++ctx->launches; }
+    else rc = lat_spmv_internal(ctx, rowptr, colidx, vals, n_nodes, x, Ap);
     if (rc) break;
     k_cg_restart<PC><<<grid, SPMV_BLOCK, 0, ctx->stream>>>(n_nodes, b, Ap, dinv, r, z, pa, pb, partials);
     k_cg_true_residual<<<1, CG_REDUCE_BLOCK, 0, ctx->stream>>>(partials, (int)grid, sc, prm, 2);
@@ -930,6 +1001,89 @@ extern "C" int lat_pcg_bsr(lat_ctx* ctx, const int32_t* rowptr, const int32_t* c
     case LAT_PC_NONE: return pcg_run<LAT_PC_NONE>(ctx, rowptr, colidx, vals, n_nodes, b, x, opts, result);
     case LAT_PC_JACOBI: return pcg_run<LAT_PC_JACOBI>(ctx, rowptr, colidx, vals, n_nodes, b, x, opts, result);
     case LAT_PC_BLOCK6: return pcg_run<LAT_PC_BLOCK6>(ctx, rowptr, colidx, vals, n_nodes, b, x, opts, result);
+    default: return lat_fail(ctx, LAT_ERR_ARG, "unknown preconditioner", __FILE__, __LINE__);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// matrix-free operator (matfree.cuh): resident set-up, products, PCG
+// ---------------------------------------------------------------------------
+static int mf_get(lat_ctx* ctx, MfOp* op) {
+  if (ctx->mf_nnodes < 0)
+    return lat_fail(ctx, LAT_ERR_STATE, "no resident matrix-free operator: call lat_matfree_setup", __FILE__, __LINE__);
+  const double G = ctx->mf_young / (2.0 * (1.0 + ctx->mf_nu));
+  op->adjptr = (const int32_t*)ctx->bufs["pat_adjptr"].p;
+  op->inc = (const MfInc*)ctx->bufs["mf_inc"].p;
+  op->node4 = (const double*)ctx->bufs["mf_node4"].p;
+  op->E = ctx->mf_young;
+  op->Gk = G * ctx->mf_kappa;
+  op->G2mE = 2.0 * G - ctx->mf_young;
+  op->inv4pi = 1.0 / (4.0 * 3.14159265358979323846);
+  return LAT_OK;
+}
+
+extern "C" int lat_matfree_setup(lat_ctx* ctx, const double* x, const double* y, const double* z,
+                                 const int32_t* en0, const int32_t* en1, const double* rad, int64_t n_elem,
+                                 int64_t n_nodes, double young, double nu, double kappa, const uint8_t* fixed) {
+  if (!ctx) return LAT_ERR_ARG;
+  LAT_CHECK_ARG(ctx, x && y && z && en0 && en1 && rad && n_elem > 0 && n_nodes > 0);
+  if (ctx->pat_nnzb < 0 || ctx->pat_nelem != n_elem || ctx->pat_nnodes != n_nodes)
+    return lat_fail(ctx, LAT_ERR_STATE, "resident pattern does not match this mesh: call lat_bsr_pattern_build", __FILE__, __LINE__);
+  LAT_CUDA(ctx, cudaSetDevice(ctx->device));
+  MfInc* inc = lat_buf<MfInc>(ctx, "mf_inc", (size_t)2 * n_elem);
+  double* node4 = lat_buf<double>(ctx, "mf_node4", (size_t)4 * n_nodes);
+  if (!inc || !node4) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+  LAT_LAUNCH(ctx, k_mf_setup_inc, (unsigned)ceil_div(2 * n_elem, 256), 256, 0, (const int32_t*)ctx->bufs["pat_adj_other"].p,
+             (const int32_t*)ctx->bufs["pat_adj_el"].p, x, y, z, en0, en1, rad, 2 * n_elem, inc);
+  LAT_LAUNCH(ctx, k_mf_setup_nodes, (unsigned)ceil_div(n_nodes, 256), 256, 0, x, y, z, fixed, n_nodes, node4);
+  ctx->mf_nnodes = n_nodes;
+  ctx->mf_nelem = n_elem;
+  ctx->mf_young = young;
+  ctx->mf_nu = nu;
+  ctx->mf_kappa = kappa;
+  return LAT_OK;
+}
+
+extern "C" int lat_matfree_apply(lat_ctx* ctx, const double* u, double* y, int eliminated) {
+  if (!ctx) return LAT_ERR_ARG;
+  LAT_CHECK_ARG(ctx, u && y && u != y);
+  LAT_CHECK_ARG(ctx, ((reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(y)) & 31) == 0);   // 256-bit accesses
+  MfOp op;
+  if (int rc = mf_get(ctx, &op)) return rc;
+  LAT_CUDA(ctx, cudaSetDevice(ctx->device));
+  const unsigned grid = (unsigned)ceil_div(ctx->mf_nnodes, MF_BLOCK);
+  if (eliminated) LAT_LAUNCH(ctx, k_mf_apply<true>, grid, MF_BLOCK, 0, op, ctx->mf_nnodes, u, y);
+  else LAT_LAUNCH(ctx, k_mf_apply<false>, grid, MF_BLOCK, 0, op, ctx->mf_nnodes, u, y);
+  return LAT_OK;
+}
+
+extern "C" int lat_matfree_rhs(lat_ctx* ctx, const double* g, const double* f, double* b) {
+  if (!ctx) return LAT_ERR_ARG;
+  LAT_CHECK_ARG(ctx, g && b && g != b);
+  LAT_CHECK_ARG(ctx, ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(b)) & 31) == 0);
+  MfOp op;
+  if (int rc = mf_get(ctx, &op)) return rc;
+  LAT_CUDA(ctx, cudaSetDevice(ctx->device));
+  LAT_LAUNCH(ctx, k_mf_rhs, (unsigned)ceil_div(ctx->mf_nnodes, MF_BLOCK), MF_BLOCK, 0, op, ctx->mf_nnodes, g, f, b);
+  return LAT_OK;
+}
+
+extern "C" int lat_pcg_matfree(lat_ctx* ctx, const double* b, double* x, const lat_pcg_opts* opts,
+                               lat_pcg_result* result) {
+  if (!ctx) return LAT_ERR_ARG;
+  LAT_CHECK_ARG(ctx, b && x && opts && result);
+  LAT_CHECK_ARG(ctx, opts->maxiter >= 0 && opts->tol >= 0.0);
+  LAT_CHECK_ARG(ctx, (reinterpret_cast<uintptr_t>(x) & 31) == 0);
+  if (opts->reference_semantics)
+    return lat_fail(ctx, LAT_ERR_UNSUPPORTED, "the reference clamp/restart rules are defined on the assembled path (lat_pcg_bsr)", __FILE__, __LINE__);
+  MfOp op;
+  if (int rc = mf_get(ctx, &op)) return rc;
+  LAT_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t nn = ctx->mf_nnodes;
+  switch (opts->precond) {
+    case LAT_PC_NONE: return pcg_run<LAT_PC_NONE>(ctx, nullptr, nullptr, nullptr, nn, b, x, opts, result, &op);
+    case LAT_PC_JACOBI: return pcg_run<LAT_PC_JACOBI>(ctx, nullptr, nullptr, nullptr, nn, b, x, opts, result, &op);
+    case LAT_PC_BLOCK6: return pcg_run<LAT_PC_BLOCK6>(ctx, nullptr, nullptr, nullptr, nn, b, x, opts, result, &op);
     default: return lat_fail(ctx, LAT_ERR_ARG, "unknown preconditioner", __FILE__, __LINE__);
   }
 }
@@ -1110,6 +1264,7 @@ struct P2PArenaHdr {
   unsigned long long halo_flag[P2P_MAXR][P2P_SLOTS];        // [source rank][slot]
   unsigned long long pad[16];
 };
+static_assert(sizeof(P2PArenaHdr) % 32 == 0, "u behind the header is read with 256-bit loads");
 struct P2P {
   int nranks = 1, rank = 0;
   unsigned long long epoch = 0;
@@ -1309,11 +1464,14 @@ extern "C" int lat_p2p_destroy(lat_ctx* ctx) {
 
 template <int PC>
 static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, const double* vals,
-                        const lat_halo* h, const double* b, double* x, const lat_pcg_opts* o, lat_pcg_result* res) {
+                        const lat_halo* h, const double* b, double* x, const lat_pcg_opts* o, lat_pcg_result* res,
+                        const MfOp* mf = nullptr) {
   // Chronopoulos-Gear arrangement: per iteration ONE halo exchange (u) and ONE all-reduce (3 doubles).
   const int64_t n_own = h->n_owned, n_loc = h->n_local;
   const int64_t n = 6 * n_loc;
   const unsigned grid = (unsigned)ceil_div(n_own, ROWS_PER_CTA);
+  const unsigned mf_grid = (unsigned)ceil_div(n_own, MF_BLOCK);
+  const int n_part = (int)(mf ? mf_grid : grid);   // CTAs of the product kernel = partial sums to add
   // bit 4 of `reserved`: halo push + all-reduce through NVLink peer memory inside our kernels (no NCCL)
   P2P* pp = ctx->p2p;
   const bool p2p = (o->reserved & 16) && pp && pp->attached && pp->nranks == ctx->nranks && pp->n_local == n_loc &&
@@ -1338,6 +1496,12 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
   prm.maxiter = o->maxiter; prm.reference = 0; prm.dist = 1; prm.pad = 0; prm.seq_base = 0;
   int check = o->check_every > 0 ? o->check_every : 32;
   const bool multi = ctx->nranks > 1 && ctx->nccl_comm != nullptr;
+  // the product: assembled BSR rows or the matrix-free operator (owned rows only, ghosts are read)
+  auto launch_product = [&]() -> int {
+    if (mf) LAT_LAUNCH(ctx, k_cg_spmv_mf, mf_grid, MF_BLOCK, 0, *mf, n_own, u, r, w, sc, partials, prm);
+    else LAT_LAUNCH(ctx, k_cg_spmv, grid, SPMV_BLOCK, 0, rowptr, colidx, vals, n_own, u, r, w, sc, partials, prm);
+    return LAT_OK;
+  };
   P2PPushArgs pa;
   memset(&pa, 0, sizeof pa);
   int push_total = 0;
@@ -1373,8 +1537,10 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
   // already have pushed its first halo of this solve into our ghost section: zeroing it would lose data
   // (observed: 1634 instead of 1246 iterations and a wrong iterate on the first solve).
   if (!p2p) LAT_CUDA(ctx, cudaMemsetAsync(u, 0, n * sizeof(double), ctx->stream));
-  if (PC != LAT_PC_NONE)
-    LAT_LAUNCH(ctx, k_precond_setup, (unsigned)ceil_div(n_own, 128), 128, 0, rowptr, colidx, vals, n_own, PC, dinv);
+  if (PC != LAT_PC_NONE) {
+    if (mf) LAT_LAUNCH(ctx, k_mf_precond, (unsigned)ceil_div(n_own, 128), 128, 0, *mf, n_own, PC, dinv);
+    else LAT_LAUNCH(ctx, k_precond_setup, (unsigned)ceil_div(n_own, 128), 128, 0, rowptr, colidx, vals, n_own, PC, dinv);
+  }
   LAT_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
   LAT_LAUNCH(ctx, k_cg_init<PC>, grid, SPMV_BLOCK, 0, n_own, b, dinv, x, r, u, p, sv);
 
@@ -1393,9 +1559,9 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
         LAT_LAUNCH(ctx, k_p2p_halo, halo_grid, 256, 0, h->send_idx, u, pp->d_peer, pa, u_off, sc, prm);
       if (prof_on && trace) cudaEventRecord(tr_ev[2], ctx->stream);
       if (prof_on) cudaEventRecord(prof_ev[0], ctx->stream);
-      LAT_LAUNCH(ctx, k_cg_spmv, grid, SPMV_BLOCK, 0, rowptr, colidx, vals, n_own, u, r, w, sc, partials, prm);
+      if (int prc = launch_product()) return prc;
       if (prof_on) cudaEventRecord(prof_ev[1], ctx->stream);
-      LAT_LAUNCH(ctx, k_p2p_reduce, 1, 1024, 0, partials, (int)grid, sc, prm, pp->d_peer, pp->nranks, pp->rank);
+      LAT_LAUNCH(ctx, k_p2p_reduce, 1, 1024, 0, partials, n_part, sc, prm, pp->d_peer, pp->nranks, pp->rank);
       if (prof_on && trace) cudaEventRecord(tr_ev[4], ctx->stream);
       if (prof_on) {
         cudaEventSynchronize(prof_ev[1]);
@@ -1416,8 +1582,8 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
     }
     int rc2 = multi ? halo_exchange(ctx, h, u) : LAT_OK;
     if (rc2) return rc2;
-    LAT_LAUNCH(ctx, k_cg_spmv, grid, SPMV_BLOCK, 0, rowptr, colidx, vals, n_own, u, r, w, sc, partials, prm);
-    LAT_LAUNCH(ctx, k_cg_reduce, 1, CG_REDUCE_BLOCK, 0, partials, (int)grid, sc, prm);
+    if (int prc = launch_product()) return prc;
+    LAT_LAUNCH(ctx, k_cg_reduce, 1, CG_REDUCE_BLOCK, 0, partials, n_part, sc, prm);
     rc2 = lat_allreduce_sum(ctx, sc->sums, 3);
     if (rc2) return rc2;
     LAT_LAUNCH(ctx, k_cg_finalize, 1, 1, 0, sc, prm);
@@ -1506,7 +1672,8 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
   double true_rr = -1.0;
   while (rc == LAT_OK && hs[0].done && !hs[0].breakdown && hs[0].bb > 0.0) {
     if (multi) { rc = halo_exchange(ctx, h, x); if (rc) break; }
-    rc = lat_spmv_internal(ctx, rowptr, colidx, vals, n_own, x, w);
+    if (mf) { k_mf_apply<true><<<mf_grid, MF_BLOCK, 0, ctx->stream>>>(*mf, n_own, x, w); ++ctx->launches; }
+    else rc = lat_spmv_internal(ctx, rowptr, colidx, vals, n_own, x, w);
     if (rc) break;
     k_cg_restart<PC><<<grid, SPMV_BLOCK, 0, ctx->stream>>>(n_own, b, w, dinv, r, u, p, sv, partials);
     k_cg_true_residual<<<1, CG_REDUCE_BLOCK, 0, ctx->stream>>>(partials, (int)grid, sc, prm, 0);
@@ -1554,6 +1721,26 @@ extern "C" int lat_pcg_bsr_dist(lat_ctx* ctx, const int32_t* rowptr, const int32
     case LAT_PC_NONE: return pcg_run_dist<LAT_PC_NONE>(ctx, rowptr, colidx, vals, halo, b, x, opts, result);
     case LAT_PC_JACOBI: return pcg_run_dist<LAT_PC_JACOBI>(ctx, rowptr, colidx, vals, halo, b, x, opts, result);
     case LAT_PC_BLOCK6: return pcg_run_dist<LAT_PC_BLOCK6>(ctx, rowptr, colidx, vals, halo, b, x, opts, result);
+    default: return lat_fail(ctx, LAT_ERR_ARG, "unknown preconditioner", __FILE__, __LINE__);
+  }
+}
+
+extern "C" int lat_pcg_matfree_dist(lat_ctx* ctx, const lat_halo* halo, const double* b, double* x,
+                                    const lat_pcg_opts* opts, lat_pcg_result* result) {
+  if (!ctx) return LAT_ERR_ARG;
+  LAT_CHECK_ARG(ctx, halo && b && x && opts && result);
+  LAT_CHECK_ARG(ctx, halo->n_owned > 0 && halo->n_local >= halo->n_owned && opts->maxiter >= 0);
+  LAT_CHECK_ARG(ctx, ctx->nranks == 1 || ctx->nccl_comm != nullptr);
+  LAT_CHECK_ARG(ctx, (reinterpret_cast<uintptr_t>(x) & 31) == 0);
+  MfOp op;
+  if (int rc = mf_get(ctx, &op)) return rc;
+  if (ctx->mf_nnodes != halo->n_local)
+    return lat_fail(ctx, LAT_ERR_STATE, "resident matrix-free operator was set up for a different local mesh", __FILE__, __LINE__);
+  LAT_CUDA(ctx, cudaSetDevice(ctx->device));
+  switch (opts->precond) {
+    case LAT_PC_NONE: return pcg_run_dist<LAT_PC_NONE>(ctx, nullptr, nullptr, nullptr, halo, b, x, opts, result, &op);
+    case LAT_PC_JACOBI: return pcg_run_dist<LAT_PC_JACOBI>(ctx, nullptr, nullptr, nullptr, halo, b, x, opts, result, &op);
+    case LAT_PC_BLOCK6: return pcg_run_dist<LAT_PC_BLOCK6>(ctx, nullptr, nullptr, nullptr, halo, b, x, opts, result, &op);
     default: return lat_fail(ctx, LAT_ERR_ARG, "unknown preconditioner", __FILE__, __LINE__);
   }
 }

@@ -194,6 +194,26 @@ class DistributedFEM:
         R = ctx.spmv(self.rowptr, self.colidx, self.vals, u)     # rows >= n_owned are partial: ignore
         return u, R, info
 
+    def solve_matrix_free(self, tol=1e-8, maxiter=200000, precond=2, b=None, u=None, check_every=0, profile_iters=0,
+                          want_reactions=True):
+        """:meth:`solve` without an assembled matrix (csrc/matfree.cuh): the operator is regenerated from the
+        local mesh in every product; halo exchange and all-reduce are unchanged."""
+        torch, ctx = self.torch, self.ctx
+        if b is None:
+            b = torch.empty(6 * self.n_local, dtype=torch.float64, device=ctx.device)
+        if u is None:
+            u = torch.empty(6 * self.n_local, dtype=torch.float64, device=ctx.device)
+        ctx.matfree_setup(self.x, self.y, self.z, self.en0, self.en1, self.rad, self.n_local, self.young, self.nu,
+                          self.kappa, fixed=self.fixed_d)
+        ctx.matfree_rhs(self.g_d, self.f_d, out=b)        # rows >= n_owned are partial: never read
+        u, info = ctx.pcg_matfree_dist(self.halo, b, u, tol=tol, maxiter=maxiter, precond=precond,
+                                       check_every=check_every, p2p=getattr(self, "p2p", False),
+                                       profile_iters=profile_iters)
+        ctx.set_dirichlet_values(self.fixed_d, self.g_d, u)
+        ctx.halo_exchange(self.halo, u)
+        R = ctx.matfree_apply(u, eliminated=False) if want_reactions else None
+        return u, R, info
+
     def compliance_gradient(self, u_local, group_global, n_groups, chain_global=None):
         """g[p] = -sum_e chain_e u_e^T dK_e/dr u_e over ALL elements of the lattice (lattice_opti.py:746-841).
         Every element is counted on exactly one rank (the owner of its first node); the per-rank partial

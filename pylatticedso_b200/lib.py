@@ -25,6 +25,7 @@ EXPORTS = [
     "lat_version", "lat_ctx_create", "lat_ctx_destroy", "lat_last_error", "lat_ctx_sync", "lat_launch_count",
     "lat_elem_stiffness", "lat_bsr_pattern_build", "lat_bsr_pattern_export", "lat_csr_structure",
     "lat_bsr_to_csr_values", "lat_assemble_bsr", "lat_apply_dirichlet", "lat_set_dirichlet_values", "lat_bsr_spmv", "lat_pcg_bsr",
+    "lat_matfree_setup", "lat_matfree_apply", "lat_matfree_rhs", "lat_pcg_matfree", "lat_pcg_matfree_dist",
     "lat_compliance_grad", "lat_schur_batch", "lat_ddm_matvec",
     "lat_nccl_unique_id", "lat_comm_create", "lat_comm_destroy", "lat_allreduce_sum", "lat_halo_exchange",
     "lat_pcg_bsr_dist", "lat_p2p_arena_create", "lat_p2p_attach", "lat_p2p_destroy", "lat_assemble_cells_bsr",
@@ -109,6 +110,11 @@ def load():
     lib.lat_set_dirichlet_values.argtypes = [vp, vp, vp, i64, vp]
     lib.lat_bsr_spmv.argtypes = [vp, vp, vp, vp, i64, vp, vp]
     lib.lat_pcg_bsr.argtypes = [vp, vp, vp, vp, i64, vp, vp, C.POINTER(PcgOpts), C.POINTER(PcgResult)]
+    lib.lat_matfree_setup.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, C.c_double, C.c_double, C.c_double, vp]
+    lib.lat_matfree_apply.argtypes = [vp, vp, vp, C.c_int]
+    lib.lat_matfree_rhs.argtypes = [vp, vp, vp, vp]
+    lib.lat_pcg_matfree.argtypes = [vp, vp, vp, C.POINTER(PcgOpts), C.POINTER(PcgResult)]
+    lib.lat_pcg_matfree_dist.argtypes = [vp, C.POINTER(Halo), vp, vp, C.POINTER(PcgOpts), C.POINTER(PcgResult)]
     lib.lat_compliance_grad.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, vp, vp, i64, vp, vp]
     lib.lat_schur_batch.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, i32, dbl, dbl, dbl, vp, vp, vp, i32, vp]
     lib.lat_ddm_matvec.argtypes = [vp, vp, i64, vp, vp, i64, i32, i64, vp, vp]
@@ -254,6 +260,36 @@ class Context:
                        launches=r.launches, spmv_ms=r.spmv_ms, update_ms=r.update_ms, profiled=r.profiled,
                        true_relres=r.true_relres, restarts=r.reserved)
 
+    # ---- matrix-free operator (resident in the context; needs bsr_pattern() of the same mesh) ----
+    def matfree_setup(self, x, y, z, en0, en1, rad, n_nodes, young, nu, kappa=0.9, fixed=None):
+        self.check(self.lib.lat_matfree_setup(self.h, _ptr(x), _ptr(y), _ptr(z), _ptr(en0), _ptr(en1), _ptr(rad),
+                                              en0.numel(), n_nodes, young, nu, kappa, _ptr(fixed)))
+
+    def matfree_apply(self, u, out=None, eliminated=True):
+        import torch
+        if out is None:
+            out = torch.empty_like(u)
+        self.check(self.lib.lat_matfree_apply(self.h, _ptr(u), _ptr(out), int(eliminated)))
+        return out
+
+    def matfree_rhs(self, g, f=None, out=None):
+        import torch
+        if out is None:
+            out = torch.empty_like(g)
+        self.check(self.lib.lat_matfree_rhs(self.h, _ptr(g), _ptr(f), _ptr(out)))
+        return out
+
+    def pcg_matfree(self, b, x=None, tol=1e-8, maxiter=10000, precond=PC_JACOBI, check_every=0, profile_iters=0):
+        import torch
+        if x is None:
+            x = torch.empty_like(b)
+        o = PcgOpts(tol, 0.0, 0.0, 0, maxiter, precond, 0, check_every, profile_iters, 0)
+        r = PcgResult()
+        self.check(self.lib.lat_pcg_matfree(self.h, _ptr(b), _ptr(x), C.byref(o), C.byref(r)))
+        return x, dict(iters=r.iters, info=r.info, relres=r.relres, norm_b=r.norm_b, solve_ms=r.solve_ms,
+                       launches=r.launches, spmv_ms=r.spmv_ms, update_ms=r.update_ms, profiled=r.profiled,
+                       true_relres=r.true_relres, restarts=r.reserved)
+
     def compliance_grad(self, x, y, z, en0, en1, rad, group, n_groups, u, young, nu, kappa=0.9, chain=None,
                         lam=None, want_elem=False):
         import torch
@@ -360,6 +396,16 @@ class Context:
     def p2p_destroy(self):
         self.lib.lat_p2p_destroy(self.h)
         self.p2p_ready = False
+
+    def pcg_matfree_dist(self, halo, b, x, tol=1e-8, maxiter=10000, precond=PC_JACOBI, check_every=0, p2p=False,
+                         no_graph=False, profile_iters=0):
+        o = PcgOpts(tol, 0.0, 0.0, 0, maxiter, precond, 0, check_every, profile_iters,
+                    (16 if p2p else 0) | (4 if no_graph else 0))
+        r = PcgResult()
+        self.check(self.lib.lat_pcg_matfree_dist(self.h, C.byref(halo), _ptr(b), _ptr(x), C.byref(o), C.byref(r)))
+        return x, dict(iters=r.iters, info=r.info, relres=r.relres, norm_b=r.norm_b, solve_ms=r.solve_ms,
+                       launches=r.launches, true_relres=r.true_relres, restarts=r.reserved, spmv_ms=r.spmv_ms,
+                       update_ms=r.update_ms, profiled=r.profiled)
 
     def pcg_dist(self, rowptr, colidx, vals, halo, b, x, tol=1e-8, maxiter=10000, precond=PC_JACOBI,
                  reference_semantics=False, mintol=0.0, alpha_max=0.0, restart_every=0, check_every=0, p2p=False,

@@ -36,17 +36,19 @@ def main():
         for mode in ("nccl", "p2p"):
             if mode == "p2p":
                 dfem.enable_p2p()
-            for rep in range(2 if mode == "p2p" else 1):      # second p2p solve: flags of the first must not match
-                u, R, info = dfem.solve(tol=1e-13, maxiter=100000, precond=L.PC_BLOCK6, check_every=16)
-            ug = dfem.gather_owned(u)
-            Rg = dfem.gather_owned(R)
-            if rank == 0:
-                eu = np.abs(ug - uo).max() / np.abs(uo).max()
-                er = np.abs(Rg - Ro).max() / np.abs(Ro).max()
-                print(f"[dist_check] {mode} {geom}{n} m={m_} world={world} n_dof={mesh.n_dof} iters={info['iters']} "
-                      f"info={info['info']} relres={info['relres']:.1e} solve_ms={info['solve_ms']:.2f} |u-uo|/|uo|={eu:.2e} "
-                      f"|R-Ro|/|Ro|={er:.2e}", flush=True)
-                ok = ok and info["info"] == 0 and eu < 1e-8 and er < 1e-8
+            for op in ("assembled", "matfree"):
+                solve = dfem.solve if op == "assembled" else dfem.solve_matrix_free
+                for rep in range(2 if mode == "p2p" else 1):      # second p2p solve: flags of the first must not match
+                    u, R, info = solve(tol=1e-13, maxiter=100000, precond=L.PC_BLOCK6, check_every=16)
+                ug = dfem.gather_owned(u)
+                Rg = dfem.gather_owned(R)
+                if rank == 0:
+                    eu = np.abs(ug - uo).max() / np.abs(uo).max()
+                    er = np.abs(Rg - Ro).max() / np.abs(Ro).max()
+                    print(f"[dist_check] {mode} {op} {geom}{n} m={m_} world={world} n_dof={mesh.n_dof} iters={info['iters']} "
+                          f"info={info['info']} relres={info['relres']:.1e} solve_ms={info['solve_ms']:.2f} |u-uo|/|uo|={eu:.2e} "
+                          f"|R-Ro|/|Ro|={er:.2e}", flush=True)
+                    ok = ok and info["info"] == 0 and eu < 1e-8 and er < 1e-8
         # sharded compliance gradient w.r.t. per-cell radii == oracle's
         ncell = int(mesh.cell_of_elem.max()) + 1
         gd = dfem.compliance_gradient(u, mesh.cell_of_elem, ncell).cpu().numpy()
