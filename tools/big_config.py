@@ -42,6 +42,13 @@ if world == 1:
     out.update(pcg=info, dof_iters_per_s=mesh.n_dof * info["iters"] / (info["solve_ms"] * 1e-3),
                spmv_GBps=(nz * 292 + nn * 148) / info["spmv_ms"] / 1e6, spmv_frac=(nz * 292 + nn * 148) / info["spmv_ms"] / 1e6 / peak,
                iteration_frac=(nz * 292 + nn * 100 + 6 * nn * 144) * info["iters"] / info["solve_ms"] / 1e6 / peak)
+    # the same system without an assembled matrix
+    fem.vals = None; del vbc; torch.cuda.empty_cache()
+    um, Rm, im = fem.solve_matrix_free(fixed, g, f, tol=1e-8, maxiter=100000, precond=L.PC_BLOCK6, profile_iters=32, want_reactions=False)
+    ctx.set_dirichlet_values(fd, gd, u)
+    out.update(matrix_free=dict(pcg=im, dof_iters_per_s=mesh.n_dof * im["iters"] / (im["solve_ms"] * 1e-3),
+                                rel_diff_vs_assembled=float((um - u).abs().max() / u.abs().max())))
+    fem.assemble()
     if name == "octet40":   # config 3: adjoint compliance gradient w.r.t. the 64 000 cell radii
         ctx.set_dirichlet_values(fd, gd, u)
         grp = torch.from_numpy(mesh.cell_of_elem.astype(np.int32)).to(dev)
@@ -69,6 +76,13 @@ else:
                dof_iters_per_s=mesh.n_dof * info["iters"] / (float(t[0]) * 1e-3),
                iteration_frac_of_aggregate_hbm=(nzb * 292 + nn * 100 + 6 * nn * 144) * info["iters"] / float(t[0]) / 1e6 / (peak * world),
                ghosts_per_rank=int(dfem.n_local - dfem.n_owned))
+    um, Rm, im = dfem.solve_matrix_free(tol=1e-8, maxiter=100000, precond=L.PC_BLOCK6, want_reactions=False)
+    um, Rm, im = dfem.solve_matrix_free(tol=1e-8, maxiter=100000, precond=L.PC_BLOCK6, want_reactions=False)
+    tm = torch.tensor([im["solve_ms"]], dtype=torch.float64, device=ctx.device)
+    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    dmax = ((um - u).abs().max() / u.abs().max()).reshape(1); dist.all_reduce(dmax, op=dist.ReduceOp.MAX)
+    out.update(matrix_free=dict(pcg=im, solve_ms_max=float(tm[0]), dof_iters_per_s=mesh.n_dof * im["iters"] / (float(tm[0]) * 1e-3),
+                                rel_diff_vs_assembled=float(dmax[0])))
     ctx.p2p_destroy(); ctx.comm_destroy()
 if rank == 0:
     print(json.dumps(out), flush=True)
