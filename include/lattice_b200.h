@@ -145,7 +145,9 @@ typedef struct {
                             with CUDA events around each kernel (fills spmv_ms / update_ms) */
   int32_t reserved;      /* bit 1: experimental TMA-staged SpMV kernel; bit 2: no CUDA graph in the multi-GPU path;
                             bit 3: classic two-reduction recurrences instead of Chronopoulos-Gear (textbook mode);
-                            bit 4 (lat_pcg_bsr_dist): NVLink peer-memory halo/all-reduce instead of NCCL */
+                            bit 4 (lat_pcg_bsr_dist): NVLink peer-memory halo/all-reduce instead of NCCL;
+                            bit 5: with bit 4, overlap the halo (side stream) with the product of the interior rows -- opt-in,
+                            measured no faster (profiles/r01_overlap_ab.txt) */
 } lat_pcg_opts;
 
 typedef struct {

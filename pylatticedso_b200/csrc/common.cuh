@@ -151,7 +151,9 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* partials, u
 // Block-level half of the reduction only: partials[i][blockIdx.x] = sum over the CTA of v[i].
 // Plain stores, no ordering needed -- the consumer is a later kernel.
 template <int NV, int BLOCK>
-__device__ __forceinline__ void block_partials(double (&v)[NV], double* partials) {
+__device__ __forceinline__ void block_partials(double (&v)[NV], double* partials, int stride = 0, int offset = 0) {
+  // layout [NV][stride]; this CTA's slot is offset + blockIdx.x (stride 0: this kernel's own grid).  Two
+  // kernels can fill one array (interior rows at offset 0, boundary rows behind them).
   __shared__ double s_bp[NV][BLOCK / 32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
@@ -164,7 +166,8 @@ __device__ __forceinline__ void block_partials(double (&v)[NV], double* partials
     double s = 0.0;
 #pragma unroll
     for (int k = 0; k < BLOCK / 32; ++k) s += s_bp[threadIdx.x][k];
-    partials[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = s;
+    const size_t st = stride > 0 ? (size_t)stride : (size_t)gridDim.x;
+    partials[(size_t)threadIdx.x * st + offset + blockIdx.x] = s;
   }
 }
 

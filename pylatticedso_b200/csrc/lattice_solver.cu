@@ -406,17 +406,30 @@ __global__ void k_cg_finalize(PcgScalars* sc, PcgParams prm) {
   cg_finish(sc, prm, sc->sums[0], sc->sums[1], sc->sums[2]);
 }
 
+// Which rows a product kernel covers.  Default: all of [0, n_nodes).  Multi-GPU overlap: the INTERIOR launch
+// passes skip[] (1 = row reads a ghost column: left to the boundary launch, which waits for the halo), the
+// BOUNDARY launch passes the list of those rows.  p_stride / p_offset place the per-CTA partial sums of both
+// launches in one array.
+struct RowSet {
+  const int32_t* rows = nullptr;   // non-null: n_nodes entries, row = rows[i]
+  const uint8_t* skip = nullptr;   // non-null: rows with skip[row] != 0 are not touched
+  int p_stride = 0, p_offset = 0;
+};
+
 __global__ void __launch_bounds__(SPMV_BLOCK) k_cg_spmv(const int32_t* __restrict__ rowptr,
                                                         const int32_t* __restrict__ colidx,
                                                         const double* __restrict__ vals, int64_t n_nodes,
                                                         const double* __restrict__ u, const double* __restrict__ r,
                                                         double* __restrict__ w, PcgScalars* __restrict__ sc,
-                                                        double* __restrict__ partials, PcgParams prm) {
+                                                        double* __restrict__ partials, PcgParams prm,
+                                                        RowSet rs = RowSet()) {
   const int lane = threadIdx.x & 31;
   const int g = lane / 6, rr_ = lane - g * 6;
   const int64_t warp = (int64_t)blockIdx.x * (SPMV_BLOCK / 32) + (threadIdx.x >> 5);
-  const int64_t n = warp * ROWS_PER_WARP + g;
-  const bool active = g < ROWS_PER_WARP && n < n_nodes;
+  int64_t n = warp * ROWS_PER_WARP + g;
+  bool active = g < ROWS_PER_WARP && n < n_nodes;
+  if (rs.rows) n = active ? rs.rows[n] : 0;
+  if (rs.skip && active && rs.skip[n]) active = false;
   // independent loads first: the row extent and the own-row entries do not depend on the status word
   int lo = 0, hi = 0;
   double uo = 0.0, ro = 0.0;
@@ -435,7 +448,7 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_cg_spmv(const int32_t* __restric
   }
   if (active) w[i] = acc;
   double v[3] = {ro * uo, acc * uo, ro * ro};
-  block_partials<3, SPMV_BLOCK>(v, partials);
+  block_partials<3, SPMV_BLOCK>(v, partials, rs.p_stride, rs.p_offset);
 }
 
 // Matrix-free twin of k_cg_spmv: w = A u regenerated from the geometry (matfree.cuh, one thread per node),
@@ -443,9 +456,11 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_cg_spmv(const int32_t* __restric
 __global__ void __launch_bounds__(MF_BLOCK, 9) k_cg_spmv_mf(MfOp op, int64_t n_nodes, const double* __restrict__ u,
                                                          const double* __restrict__ r, double* __restrict__ w,
                                                          PcgScalars* __restrict__ sc, double* __restrict__ partials,
-                                                         PcgParams prm) {
-  const int64_t n = (int64_t)blockIdx.x * MF_BLOCK + threadIdx.x;
-  const bool active = n < n_nodes;
+                                                         PcgParams prm, RowSet rs = RowSet()) {
+  int64_t n = (int64_t)blockIdx.x * MF_BLOCK + threadIdx.x;
+  bool active = n < n_nodes;
+  if (rs.rows) n = active ? rs.rows[n] : 0;
+  if (rs.skip && active && rs.skip[n]) active = false;
   MfU rr;
   rr.a = rr.b = rr.c = make_double2(0.0, 0.0);
   if (active) rr = mf_load_u(r, n);
@@ -463,7 +478,7 @@ __global__ void __launch_bounds__(MF_BLOCK, 9) k_cg_spmv_mf(MfOp op, int64_t n_n
       v[2] = fma(ro[k], ro[k], v[2]);
     }
   }
-  block_partials<3, MF_BLOCK>(v, partials);
+  block_partials<3, MF_BLOCK>(v, partials, rs.p_stride, rs.p_offset);
 }
 
 static constexpr int CG_REDUCE_BLOCK = 512;
@@ -1279,6 +1294,9 @@ struct P2P {
   bool attached = false;
   // device copies for kernels
   unsigned char** d_peer = nullptr;
+  // halo push/wait runs on a side stream next to the product of the interior rows (fork/join by events)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
@@ -1457,9 +1475,56 @@ extern "C" int lat_p2p_destroy(lat_ctx* ctx) {
     if (q != p->rank && p->peer[q]) cudaIpcCloseMemHandle(p->peer[q]);
   if (p->d_peer) cudaFree(p->d_peer);
   if (p->arena) cudaFree(p->arena);
+  if (p->side) cudaStreamDestroy(p->side);
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->ev_join) cudaEventDestroy(p->ev_join);
   delete p;
   ctx->p2p = nullptr;
   return LAT_OK;
+}
+
+// Rows of the owned block that read at least one ghost column: they must wait for the halo, all others
+// can be multiplied while the halo is in flight.
+__global__ void k_mark_boundary_bsr(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                    int64_t n_own, uint8_t* __restrict__ flag) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_own) return;
+  uint8_t f = 0;
+  for (int j = rowptr[n]; j < rowptr[n + 1]; ++j)
+    if (colidx[j] >= n_own) { f = 1; break; }
+  flag[n] = f;
+}
+__global__ void k_mark_boundary_mf(MfOp op, int64_t n_own, uint8_t* __restrict__ flag) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_own) return;
+  uint8_t f = 0;
+  for (int j = op.adjptr[n]; j < op.adjptr[n + 1]; ++j)
+    if (op.inc[j].other >= n_own) { f = 1; break; }
+  flag[n] = f;
+}
+// One CTA: ascending list of the flagged rows (deterministic order -> deterministic partial sums).
+__global__ void __launch_bounds__(1024) k_compact_rows(const uint8_t* __restrict__ flag, int64_t n, int32_t* __restrict__ rows,
+                                                       int64_t* __restrict__ count) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int64_t c0 = 0; c0 < n; c0 += 1024) {
+    const int64_t i = c0 + threadIdx.x;
+    const bool f = i < n && flag[i] != 0;
+    const unsigned m = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) s_warp[wid] = __popc(m);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int k = 0; k < 32; ++k) { const int c = s_warp[k]; if (k < wid) before += c; total += c; }
+    const int base = s_base;
+    if (f) rows[base + before + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
+    __syncthreads();
+    if (threadIdx.x == 0) s_base = base + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = s_base;
 }
 
 template <int PC>
@@ -1484,7 +1549,7 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
   double* sv = lat_buf<double>(ctx, "pcg_pb", n);
   double* w = lat_buf<double>(ctx, "pcg_Ap", n);
   double* dinv = lat_buf<double>(ctx, "pcg_dinv", PC == LAT_PC_BLOCK6 ? 21 * n_own : 6 * n_own);
-  double* partials = lat_buf<double>(ctx, "pcg_partials", (size_t)4 * grid + 8);
+  double* partials = lat_buf<double>(ctx, "pcg_partials", (size_t)4 * 2 * grid + 8);   // interior + boundary launches
   PcgScalars* sc = lat_buf<PcgScalars>(ctx, "pcg_scalars", 1);
   if (!r || !u || !p || !sv || !w || !dinv || !partials || !sc)
     return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
@@ -1498,8 +1563,8 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
   const bool multi = ctx->nranks > 1 && ctx->nccl_comm != nullptr;
   // the product: assembled BSR rows or the matrix-free operator (owned rows only, ghosts are read)
   auto launch_product = [&]() -> int {
-    if (mf) LAT_LAUNCH(ctx, k_cg_spmv_mf, mf_grid, MF_BLOCK, 0, *mf, n_own, u, r, w, sc, partials, prm);
-    else LAT_LAUNCH(ctx, k_cg_spmv, grid, SPMV_BLOCK, 0, rowptr, colidx, vals, n_own, u, r, w, sc, partials, prm);
+    if (mf) LAT_LAUNCH(ctx, k_cg_spmv_mf, mf_grid, MF_BLOCK, 0, *mf, n_own, u, r, w, sc, partials, prm, RowSet());
+    else LAT_LAUNCH(ctx, k_cg_spmv, grid, SPMV_BLOCK, 0, rowptr, colidx, vals, n_own, u, r, w, sc, partials, prm, RowSet());
     return LAT_OK;
   };
   P2PPushArgs pa;
@@ -1530,6 +1595,59 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
     if (!lat_buf<double>(ctx, "halo_send", (size_t)tot_send * 6 + 8))
       return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
   }
+  // Overlap (peer-memory path): the rows that read ghost columns are listed once per solve; per iteration the
+  // halo push/wait runs on a side stream while the main stream multiplies all other rows, then the listed
+  // rows follow.  OPT-IN (bit 5 of `reserved`): measured on 2 x B200 it is no faster than the sequential
+  // halo -> product (profiles/r01_overlap_ab.txt): NVLink moves a 1 MB halo in ~3 us, what is left is launch and
+  // flag latency, and the fork/join plus the extra boundary launch cost as much as the overlap hides.
+  int64_t n_bnd = 0;
+  unsigned bnd_grid = 0;
+  uint8_t* bflag = nullptr;
+  int32_t* brows = nullptr;
+  const bool overlap = p2p && h->n_neighbors > 0 && (o->reserved & 32);
+  if (overlap) {
+    bflag = lat_buf<uint8_t>(ctx, "pcg_bflag", n_own);
+    brows = lat_buf<int32_t>(ctx, "pcg_brows", n_own);
+    int64_t* d_cnt = lat_buf<int64_t>(ctx, "pcg_bcount", 1);
+    if (!bflag || !brows || !d_cnt) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+    if (mf) LAT_LAUNCH(ctx, k_mark_boundary_mf, (unsigned)ceil_div(n_own, 256), 256, 0, *mf, n_own, bflag);
+    else LAT_LAUNCH(ctx, k_mark_boundary_bsr, (unsigned)ceil_div(n_own, 256), 256, 0, rowptr, colidx, n_own, bflag);
+    LAT_LAUNCH(ctx, k_compact_rows, 1, 1024, 0, bflag, n_own, brows, d_cnt);
+    LAT_CUDA(ctx, cudaMemcpyAsync(ctx->h_i64, d_cnt, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    n_bnd = ctx->h_i64[0];
+    bnd_grid = (unsigned)ceil_div(n_bnd, mf ? MF_BLOCK : ROWS_PER_CTA);
+    if (!pp->side) {
+      // highest priority: the few CTAs of the halo kernel must be scheduled ahead of the product's thousands,
+      // otherwise the push (and with it every neighbour) waits for the interior product to drain
+      int prio_lo = 0, prio_hi = 0;
+      LAT_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      LAT_CUDA(ctx, cudaStreamCreateWithPriority(&pp->side, cudaStreamNonBlocking, prio_hi));
+      LAT_CUDA(ctx, cudaEventCreateWithFlags(&pp->ev_fork, cudaEventDisableTiming));
+      LAT_CUDA(ctx, cudaEventCreateWithFlags(&pp->ev_join, cudaEventDisableTiming));
+    }
+  }
+  const int n_part_ov = n_part + (int)bnd_grid;
+  auto launch_product_overlapped = [&]() -> int {
+    // fork: halo on the side stream
+    LAT_CUDA(ctx, cudaEventRecord(pp->ev_fork, ctx->stream));
+    LAT_CUDA(ctx, cudaStreamWaitEvent(pp->side, pp->ev_fork, 0));
+    k_p2p_halo<<<halo_grid, 256, 0, pp->side>>>(h->send_idx, u, pp->d_peer, pa, u_off, sc, prm);
+    ++ctx->launches;
+    LAT_CUDA(ctx, cudaEventRecord(pp->ev_join, pp->side));
+    RowSet in_rs, bd_rs;
+    in_rs.skip = bflag; in_rs.p_stride = n_part_ov; in_rs.p_offset = 0;
+    bd_rs.rows = brows; bd_rs.p_stride = n_part_ov; bd_rs.p_offset = n_part;
+    if (mf) LAT_LAUNCH(ctx, k_cg_spmv_mf, mf_grid, MF_BLOCK, 0, *mf, n_own, u, r, w, sc, partials, prm, in_rs);
+    else LAT_LAUNCH(ctx, k_cg_spmv, grid, SPMV_BLOCK, 0, rowptr, colidx, vals, n_own, u, r, w, sc, partials, prm, in_rs);
+    // join: the listed rows need the ghosts
+    LAT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, pp->ev_join, 0));
+    if (bnd_grid > 0) {
+      if (mf) LAT_LAUNCH(ctx, k_cg_spmv_mf, bnd_grid, MF_BLOCK, 0, *mf, n_bnd, u, r, w, sc, partials, prm, bd_rs);
+      else LAT_LAUNCH(ctx, k_cg_spmv, bnd_grid, SPMV_BLOCK, 0, rowptr, colidx, vals, n_bnd, u, r, w, sc, partials, prm, bd_rs);
+    }
+    return LAT_OK;
+  };
   LAT_CUDA(ctx, cudaMemsetAsync(sc, 0, sizeof(PcgScalars), ctx->stream));
   const int32_t one = 1;
   LAT_CUDA(ctx, cudaMemcpyAsync(&sc->first, &one, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -1553,6 +1671,11 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
   double prof_ms = 0.0;
   int prof_n = 0;
   auto spmv_and_reduce = [&]() -> int {
+    if (p2p && overlap && !prof_on) {
+      if (int prc = launch_product_overlapped()) return prc;
+      LAT_LAUNCH(ctx, k_p2p_reduce, 1, 1024, 0, partials, n_part_ov, sc, prm, pp->d_peer, pp->nranks, pp->rank);
+      return LAT_OK;
+    }
     if (p2p) {
       if (prof_on && trace) cudaEventRecord(tr_ev[1], ctx->stream);
       if (h->n_neighbors > 0)

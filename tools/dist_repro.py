@@ -10,11 +10,13 @@ ctx = L.Context(local); ctx.comm_create(rank, world)
 lat = M.synthetic_lattice("BCC", (20 * world, 20, 20), [0.05]); mesh = M.mesh_from_synthetic(lat, 2)
 fixed, g, f = M.compression_bc(mesh)
 dfem = D.DistributedFEM(ctx, mesh, 1013.0, 0.3, rank, world); dfem.set_bc(fixed, g, f)
-for mode in ("nccl", "p2p"):
-    if mode == "p2p": dfem.enable_p2p()
-    its = []
-    for rep in range(4):
-        u, R, info = dfem.solve(tol=1e-8, maxiter=200000, precond=2)
-        its.append((info["iters"], round(info["solve_ms"], 2), float(u[: 6 * dfem.n_owned].double().abs().sum())))
-    if rank == 0: print(mode, its, flush=True)
+for mode, kw in (("nccl", {}), ("p2p-sequential", dict(overlap=False)), ("p2p-overlap", dict(overlap=True))):
+    if mode == "p2p-sequential": dfem.enable_p2p()
+    for op, solve in (("assembled", dfem.solve), ("matfree", dfem.solve_matrix_free)):
+        its = []
+        for rep in range(4):
+            u, R, info = solve(tol=1e-8, maxiter=200000, precond=2, **kw)
+            its.append((info["iters"], round(info["solve_ms"], 2), round(1e3 * info["solve_ms"] / info["iters"], 1),
+                        float(u[: 6 * dfem.n_owned].double().abs().sum())))
+        if rank == 0: print(mode, op, "(iters, solve ms, us/iter, checksum)", its, flush=True)
 ctx.p2p_destroy(); ctx.comm_destroy(); dist.barrier(); dist.destroy_process_group()
