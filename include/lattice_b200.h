@@ -147,7 +147,10 @@ typedef struct {
                             bit 3: classic two-reduction recurrences instead of Chronopoulos-Gear (textbook mode);
                             bit 4 (lat_pcg_bsr_dist): NVLink peer-memory halo/all-reduce instead of NCCL;
                             bit 5: with bit 4, overlap the halo (side stream) with the product of the interior rows -- opt-in,
-                            measured no faster (profiles/r01_overlap_ab.txt) */
+                            measured no faster (profiles/r01_overlap_ab.txt);
+                            bit 6: with bit 4, use the separate halo kernel (k_p2p_halo) instead of the default fused halo
+                            (<= 2 neighbours: the update kernel pushes the boundary entries of u into the neighbours' ghost
+                            sections and only the product CTAs that read ghosts wait; 8-12 % faster per iteration) */
 } lat_pcg_opts;
 
 typedef struct {

@@ -185,6 +185,7 @@ struct PcgParams {
   int32_t maxiter, reference;
   int32_t dist, pad;  // dist = 1: kernels only store LOCAL sums; the host all-reduces and runs k_pcg_finalize_*
   unsigned long long seq_base;  // peer-memory path: (solve epoch << 32), so flags of earlier solves never match
+  unsigned long long push_base; // fused-halo path: halo pushes completed by earlier solves on this arena
 };
 
 // Stop tests, beta and bookkeeping of one iteration from the GLOBAL sums (single thread).
@@ -414,8 +415,64 @@ struct RowSet {
   const int32_t* rows = nullptr;   // non-null: n_nodes entries, row = rows[i]
   const uint8_t* skip = nullptr;   // non-null: rows with skip[row] != 0 are not touched
   int p_stride = 0, p_offset = 0;
+  // fused halo (peer-memory path): need[row] = bit mask of the neighbours whose ghosts the row reads.  A CTA
+  // that owns such a row waits (bounded) until the neighbour's cumulative entry counter in OUR arena reaches
+  // (push_base + seq + 1) * per_push[k]; all other CTAs start at once.  Ghost columns (>= n_own) are then read
+  // past L1 (a line straddling the owned/ghost border may have been cached before the data arrived).
+  const uint8_t* need = nullptr;
+  const uint8_t* cta_need = nullptr;          // OR of need[] over the rows of each CTA (uniform test, no barrier)
+  const unsigned long long* cnt = nullptr;    // my arena: halo_cnt[source rank]
+  int n_nb = 0, nb_rank[2] = {0, 0};
+  unsigned long long per_push[2] = {0, 0};
+  int64_t n_own = INT64_MAX;
 };
 
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// All threads of a CTA whose mask `need` (CTA-uniform) is non-zero call.
+__device__ __forceinline__ void halo_wait(const RowSet& rs, int need, PcgScalars* sc, const PcgParams& prm) {
+  if ((int)threadIdx.x < rs.n_nb && ((need >> threadIdx.x) & 1)) {
+    // (constant indices only: a dynamically indexed kernel-parameter array would be copied to local memory)
+    const unsigned long long per = threadIdx.x == 0 ? rs.per_push[0] : rs.per_push[1];
+    const int src = threadIdx.x == 0 ? rs.nb_rank[0] : rs.nb_rank[1];
+    const unsigned long long want = (prm.push_base + (unsigned long long)sc->seq + 1ull) * per;
+    long long spins = 0;
+    while (ld_acquire_sys_u64(rs.cnt + src) < want) {
+      if (++spins > (1ll << 24)) { sc->p2p_timeout = 1; break; }
+      __nanosleep(20);
+    }
+  }
+  __syncthreads();
+}
+
+// Fused halo push (peer-memory path): the kernel that produces u stores the boundary entries straight into the
+// neighbours' ghost sections and adds the number of entries to the neighbour's counter -- no halo kernel.
+struct HaloPush {
+  const int2* dst = nullptr;                  // per owned node: destination node in neighbour 0 / 1 (-1: none)
+  const uint8_t* cta_push = nullptr;          // per CTA of the update kernel: does any of its rows push?
+  double* peer_u[2] = {nullptr, nullptr};
+  unsigned long long* peer_cnt[2] = {nullptr, nullptr};   // &peer_arena->halo_cnt[my_rank]
+};
+// All threads of the CTA call (two CTA-wide counts).  d = the thread's destinations, comp its DOF, val its entry.
+__device__ __forceinline__ void halo_push(const HaloPush& hp, int2 d, int comp, double val) {
+  if (d.x >= 0) hp.peer_u[0][(int64_t)d.x * 6 + comp] = val;
+  if (d.y >= 0) hp.peer_u[1][(int64_t)d.y * 6 + comp] = val;
+  const int c0 = __syncthreads_count(d.x >= 0);   // barrier: the CTA's peer stores happen-before thread 0's release
+  const int c1 = __syncthreads_count(d.y >= 0);
+  if (threadIdx.x == 0 && (c0 | c1)) {
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+    if (c0) asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(hp.peer_cnt[0]), "l"((unsigned long long)c0) : "memory");
+    if (c1) asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(hp.peer_cnt[1]), "l"((unsigned long long)c1) : "memory");
+  }
+}
+
+// GHOST = true is the fused-halo instantiation (waits, ghost-reading rows load their columns past L1); the
+// default instantiation carries none of it -- a per-column branch in the gather loop cost 25 % on one GPU.
+template <bool GHOST = false>
 __global__ void __launch_bounds__(SPMV_BLOCK) k_cg_spmv(const int32_t* __restrict__ rowptr,
                                                         const int32_t* __restrict__ colidx,
                                                         const double* __restrict__ vals, int64_t n_nodes,
@@ -436,15 +493,35 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_cg_spmv(const int32_t* __restric
   const int64_t i = n * 6 + rr_;
   if (active) { lo = __ldg(rowptr + n); hi = __ldg(rowptr + n + 1); uo = u[i]; ro = r[i]; }
   if (sc->done || sc->iters >= prm.maxiter) return;
+  int need_row = 0;
+  if (GHOST) {
+    const int cta_need = rs.cta_need[blockIdx.x];
+    if (cta_need) {
+      need_row = active ? rs.need[n] : 0;
+      halo_wait(rs, cta_need, sc, prm);
+    }
+  }
   double acc = 0.0;
+  if (GHOST && need_row) {
+    // a row that reads ghosts: every column past L1 (the sector at the owned/ghost border may be stale there)
+    for (int j = lo; j < hi; ++j) {
+      const int c = __ldg(colidx + j);
+      const double2* vp = reinterpret_cast<const double2*>(vals + (int64_t)j * 36 + rr_ * 6);
+      const double2* xp = reinterpret_cast<const double2*>(u + (int64_t)c * 6);
+      const double2 a0 = __ldcs(vp), a1 = __ldcs(vp + 1), a2 = __ldcs(vp + 2);
+      const double2 x0 = __ldcg(xp), x1 = __ldcg(xp + 1), x2 = __ldcg(xp + 2);
+      acc = dot6(a0, a1, a2, x0, x1, x2, acc);
+    }
+  } else {
 #pragma unroll 4
-  for (int j = lo; j < hi; ++j) {
-    const int c = __ldg(colidx + j);
-    const double2* vp = reinterpret_cast<const double2*>(vals + (int64_t)j * 36 + rr_ * 6);
-    const double2* xp = reinterpret_cast<const double2*>(u + (int64_t)c * 6);
-    const double2 a0 = __ldcs(vp), a1 = __ldcs(vp + 1), a2 = __ldcs(vp + 2);
-    const double2 x0 = xp[0], x1 = xp[1], x2 = xp[2];
-    acc = dot6(a0, a1, a2, x0, x1, x2, acc);
+    for (int j = lo; j < hi; ++j) {
+      const int c = __ldg(colidx + j);
+      const double2* vp = reinterpret_cast<const double2*>(vals + (int64_t)j * 36 + rr_ * 6);
+      const double2* xp = reinterpret_cast<const double2*>(u + (int64_t)c * 6);
+      const double2 a0 = __ldcs(vp), a1 = __ldcs(vp + 1), a2 = __ldcs(vp + 2);
+      const double2 x0 = xp[0], x1 = xp[1], x2 = xp[2];
+      acc = dot6(a0, a1, a2, x0, x1, x2, acc);
+    }
   }
   if (active) w[i] = acc;
   double v[3] = {ro * uo, acc * uo, ro * ro};
@@ -453,6 +530,7 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_cg_spmv(const int32_t* __restric
 
 // Matrix-free twin of k_cg_spmv: w = A u regenerated from the geometry (matfree.cuh, one thread per node),
 // same three dots.
+template <bool GHOST = false>
 __global__ void __launch_bounds__(MF_BLOCK, 9) k_cg_spmv_mf(MfOp op, int64_t n_nodes, const double* __restrict__ u,
                                                          const double* __restrict__ r, double* __restrict__ w,
                                                          PcgScalars* __restrict__ sc, double* __restrict__ partials,
@@ -465,10 +543,19 @@ __global__ void __launch_bounds__(MF_BLOCK, 9) k_cg_spmv_mf(MfOp op, int64_t n_n
   rr.a = rr.b = rr.c = make_double2(0.0, 0.0);
   if (active) rr = mf_load_u(r, n);
   if (sc->done || sc->iters >= prm.maxiter) return;
+  int need_row = 0;
+  if (GHOST) {
+    const int cta_need = rs.cta_need[blockIdx.x];
+    if (cta_need) {
+      need_row = active ? rs.need[n] : 0;
+      halo_wait(rs, cta_need, sc, prm);
+    }
+  }
   double v[3] = {0.0, 0.0, 0.0};
   if (active) {
     double uo[6], f[6];
-    mf_node_product<true>(op, n, u, uo, f);
+    if (GHOST && need_row) mf_node_product<true, true>(op, n, u, uo, f);   // reads ghosts: gathers past L1
+    else mf_node_product<true, false>(op, n, u, uo, f);
     mf_store6(w, n, f);
     const double ro[6] = {rr.a.x, rr.a.y, rr.b.x, rr.b.y, rr.c.x, rr.c.y};
 #pragma unroll
@@ -499,7 +586,8 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_cg_update(int64_t n_nodes, const
                                                           double* __restrict__ x, double* __restrict__ r,
                                                           double* __restrict__ u, const double* __restrict__ w,
                                                           double* __restrict__ p, double* __restrict__ s,
-                                                          const PcgScalars* __restrict__ sc, PcgParams prm) {
+                                                          const PcgScalars* __restrict__ sc, PcgParams prm,
+                                                          HaloPush hp = HaloPush()) {
   const int lane = threadIdx.x & 31;
   const int g = lane / 6, rr_ = lane - g * 6;
   const int64_t warp = (int64_t)blockIdx.x * (SPMV_BLOCK / 32) + (threadIdx.x >> 5);
@@ -508,6 +596,9 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_cg_update(int64_t n_nodes, const
   const int64_t i = n * 6 + rr_;
   double uv = 0.0, wv = 0.0, pv = 0.0, sv = 0.0, xv = 0.0, rv = 0.0;
   if (active) { uv = u[i]; wv = w[i]; pv = p[i]; sv = s[i]; xv = x[i]; rv = r[i]; }
+  int2 dst = make_int2(-1, -1);
+  const bool pushes = hp.dst && hp.cta_push[blockIdx.x];   // CTA-uniform
+  if (pushes && active) dst = hp.dst[n];
   const PrecondRow<PC> pr = load_precond<PC>(dinv, n, rr_, active);   // same round trip as the vectors
   const int done = sc->done, iters = sc->iters;
   const double alpha = sc->alpha, beta = sc->beta;
@@ -518,6 +609,7 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_cg_update(int64_t n_nodes, const
   rv = fma(-alpha, sv, rv);
   const double zn = apply_precond<PC>(pr, g, rv);
   if (active) { p[i] = pv; s[i] = sv; x[i] = xv; r[i] = rv; u[i] = zn; }
+  if (pushes) halo_push(hp, dst, rr_, zn);
 }
 
 // init for the CG variant: x = 0, r = b, u = M^-1 b, p = s = 0
@@ -814,6 +906,7 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
   prm.dist = 0;
   prm.pad = 0;
   prm.seq_base = 0;
+  prm.push_base = 0;
   int check = o->check_every > 0 ? o->check_every : 32;
   if (check > o->maxiter) check = o->maxiter > 0 ? o->maxiter : 1;
 
@@ -821,9 +914,9 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
   const bool cgv = mf || (!o->reference_semantics && !(o->reserved & 8) && !plan.tma);
   auto launch_spmv = [&](cudaStream_t st) {
     if (mf)
-      k_cg_spmv_mf<<<mf_grid, MF_BLOCK, 0, st>>>(*mf, n_nodes, z, r, Ap, sc, partials, prm);
+      k_cg_spmv_mf<false><<<mf_grid, MF_BLOCK, 0, st>>>(*mf, n_nodes, z, r, Ap, sc, partials, prm, RowSet());
     else if (cgv)
-      k_cg_spmv<<<grid, SPMV_BLOCK, 0, st>>>(rowptr, colidx, vals, n_nodes, z, r, Ap, sc, partials, prm);
+      k_cg_spmv<false><<<grid, SPMV_BLOCK, 0, st>>>(rowptr, colidx, vals, n_nodes, z, r, Ap, sc, partials, prm, RowSet());
     else if (plan.tma)
       k_spmv_tma<1><<<plan.grid, SPMV_BLOCK, plan.smem, st>>>(rowptr, colidx, vals, n_nodes, plan.cta_row0,
                                                              plan.cap_blocks, z, pa, pb, Ap, sc, partials, prm);
@@ -1277,8 +1370,9 @@ static constexpr int P2P_SLOTS = 32;          // halo flag slots per source rank
 struct P2PArenaHdr {
   unsigned long long mail[2][P2P_MAXR][6];                  // [parity][source rank][3 doubles x {lo, hi}]
   unsigned long long halo_flag[P2P_MAXR][P2P_SLOTS];        // [source rank][slot]
-  unsigned long long pad[16];
+  unsigned long long halo_cnt[P2P_MAXR];                    // fused-halo path: cumulative entries received per source rank
 };
+static_assert(P2P_MAXR == 16, "halo_cnt replaces the former 128-byte pad");
 static_assert(sizeof(P2PArenaHdr) % 32 == 0, "u behind the header is read with 256-bit loads");
 struct P2P {
   int nranks = 1, rank = 0;
@@ -1294,6 +1388,7 @@ struct P2P {
   bool attached = false;
   // device copies for kernels
   unsigned char** d_peer = nullptr;
+  unsigned long long pushes_done = 0;   // fused-halo path: pushes completed by earlier solves (same on all ranks)
   // halo push/wait runs on a side stream next to the product of the interior rows (fork/join by events)
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -1484,23 +1579,85 @@ extern "C" int lat_p2p_destroy(lat_ctx* ctx) {
 }
 
 // Rows of the owned block that read at least one ghost column: they must wait for the halo, all others
-// can be multiplied while the halo is in flight.
-__global__ void k_mark_boundary_bsr(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
-                                    int64_t n_own, uint8_t* __restrict__ flag) {
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= n_own) return;
-  uint8_t f = 0;
-  for (int j = rowptr[n]; j < rowptr[n + 1]; ++j)
-    if (colidx[j] >= n_own) { f = 1; break; }
-  flag[n] = f;
+// can be multiplied while the halo is in flight.  flag[row] = bit mask of the neighbours (halo order) whose
+// ghosts the row reads; ghosts are stored neighbour-major behind the owned nodes.
+struct GhostMap {
+  int n_nb;
+  int64_t first[5];   // first local node of neighbour k's ghost segment; first[n_nb] = n_local
+};
+__device__ __forceinline__ int ghost_bit(const GhostMap& gm, int64_t col) {
+  int k = 0;
+  while (k + 1 < gm.n_nb && col >= gm.first[k + 1]) ++k;
+  return 1 << (k < 8 ? k : 7);
 }
-__global__ void k_mark_boundary_mf(MfOp op, int64_t n_own, uint8_t* __restrict__ flag) {
+__global__ void k_mark_boundary_bsr(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                    int64_t n_own, GhostMap gm, uint8_t* __restrict__ flag) {
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= n_own) return;
-  uint8_t f = 0;
+  int f = 0;
+  for (int j = rowptr[n]; j < rowptr[n + 1]; ++j)
+    if (colidx[j] >= n_own) f |= ghost_bit(gm, colidx[j]);
+  flag[n] = (uint8_t)f;
+}
+__global__ void k_mark_boundary_mf(MfOp op, int64_t n_own, GhostMap gm, uint8_t* __restrict__ flag) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_own) return;
+  int f = 0;
   for (int j = op.adjptr[n]; j < op.adjptr[n + 1]; ++j)
-    if (op.inc[j].other >= n_own) { f = 1; break; }
-  flag[n] = f;
+    if (op.inc[j].other >= n_own) f |= ghost_bit(gm, op.inc[j].other);
+  flag[n] = (uint8_t)f;
+}
+// Fused-halo path: per owned node the destination node inside neighbour 0 / 1 (-1: not sent there).
+__global__ void k_build_push_dst(const int32_t* __restrict__ send_idx, P2PPushArgs a, int2* __restrict__ dst) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.nb_first[a.n_nb]) return;
+  int k = 0;
+  while (k + 1 < a.n_nb && e >= a.nb_first[k + 1]) ++k;
+  const int v = (int)(a.nb_dst_node0[k] + (e - a.nb_first[k]));
+  if (k == 0) dst[send_idx[e]].x = v;
+  else dst[send_idx[e]].y = v;
+}
+// per-CTA OR of a per-row mask (rows_per_cta consecutive rows per CTA) / of "row has a push destination"
+__global__ void k_cta_or_rows(const uint8_t* __restrict__ rowmask, int64_t n_rows, int rows_per_cta, uint8_t* __restrict__ out) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c * rows_per_cta >= n_rows) return;
+  int f = 0;
+  for (int64_t n = c * rows_per_cta; n < (c + 1) * rows_per_cta && n < n_rows; ++n) f |= rowmask[n];
+  out[c] = (uint8_t)f;
+}
+__global__ void k_cta_or_push(const int2* __restrict__ dst, int64_t n_rows, int rows_per_cta, uint8_t* __restrict__ out) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c * rows_per_cta >= n_rows) return;
+  int f = 0;
+  for (int64_t n = c * rows_per_cta; n < (c + 1) * rows_per_cta && n < n_rows; ++n) f |= (dst[n].x >= 0) | ((dst[n].y >= 0) << 1);
+  out[c] = (uint8_t)f;
+}
+// Stand-alone push with the counter protocol (set-up pass and restarts, where u comes from k_cg_init / k_cg_restart).
+__global__ void __launch_bounds__(256) k_p2p_push_cnt(const int32_t* __restrict__ send_idx, const double* __restrict__ u,
+                                                      unsigned char* const* __restrict__ peers, P2PPushArgs a, size_t u_off,
+                                                      const PcgScalars* __restrict__ sc, PcgParams prm) {
+  if (sc->done || sc->iters >= prm.maxiter) return;
+  __shared__ unsigned int s_c[4];
+  if (threadIdx.x < 4) s_c[threadIdx.x] = 0;
+  __syncthreads();
+  const int total = a.nb_first[a.n_nb];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total * 6; i += gridDim.x * blockDim.x) {
+    const int e = i / 6, d = i - e * 6;
+    int k = 0;
+    while (k + 1 < a.n_nb && e >= a.nb_first[k + 1]) ++k;
+    double* dst = reinterpret_cast<double*>(peers[a.nb_rank[k]] + u_off);
+    dst[(a.nb_dst_node0[k] + (e - a.nb_first[k])) * 6 + d] = u[(int64_t)send_idx[e] * 6 + d];
+    atomicAdd(&s_c[k], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+    for (int k = 0; k < a.n_nb; ++k)
+      if (s_c[k]) {
+        P2PArenaHdr* hdr = reinterpret_cast<P2PArenaHdr*>(peers[a.nb_rank[k]]);
+        asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(&hdr->halo_cnt[a.my_rank]), "l"((unsigned long long)s_c[k]) : "memory");
+      }
+  }
 }
 // One CTA: ascending list of the flagged rows (deterministic order -> deterministic partial sums).
 __global__ void __launch_bounds__(1024) k_compact_rows(const uint8_t* __restrict__ flag, int64_t n, int32_t* __restrict__ rows,
@@ -1558,13 +1715,13 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
   const int64_t launches0 = ctx->launches;
   PcgParams prm;
   prm.tol = o->tol; prm.mintol = 0.0; prm.alpha_max = 0.0; prm.restart_every = 0;
-  prm.maxiter = o->maxiter; prm.reference = 0; prm.dist = 1; prm.pad = 0; prm.seq_base = 0;
+  prm.maxiter = o->maxiter; prm.reference = 0; prm.dist = 1; prm.pad = 0; prm.seq_base = 0; prm.push_base = 0;
   int check = o->check_every > 0 ? o->check_every : 32;
   const bool multi = ctx->nranks > 1 && ctx->nccl_comm != nullptr;
   // the product: assembled BSR rows or the matrix-free operator (owned rows only, ghosts are read)
   auto launch_product = [&]() -> int {
-    if (mf) LAT_LAUNCH(ctx, k_cg_spmv_mf, mf_grid, MF_BLOCK, 0, *mf, n_own, u, r, w, sc, partials, prm, RowSet());
-    else LAT_LAUNCH(ctx, k_cg_spmv, grid, SPMV_BLOCK, 0, rowptr, colidx, vals, n_own, u, r, w, sc, partials, prm, RowSet());
+    if (mf) LAT_LAUNCH(ctx, k_cg_spmv_mf<false>, mf_grid, MF_BLOCK, 0, *mf, n_own, u, r, w, sc, partials, prm, RowSet());
+    else LAT_LAUNCH(ctx, k_cg_spmv<false>, grid, SPMV_BLOCK, 0, rowptr, colidx, vals, n_own, u, r, w, sc, partials, prm, RowSet());
     return LAT_OK;
   };
   P2PPushArgs pa;
@@ -1600,6 +1757,14 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
   // rows follow.  OPT-IN (bit 5 of `reserved`): measured on 2 x B200 it is no faster than the sequential
   // halo -> product (profiles/r01_overlap_ab.txt): NVLink moves a 1 MB halo in ~3 us, what is left is launch and
   // flag latency, and the fork/join plus the extra boundary launch cost as much as the overlap hides.
+  GhostMap gmap;
+  memset(&gmap, 0, sizeof gmap);
+  gmap.n_nb = h->n_neighbors < 4 ? h->n_neighbors : 4;
+  {
+    int64_t off = n_own;
+    for (int k = 0; k < gmap.n_nb; ++k) { gmap.first[k] = off; off += h->recv_count[k]; }
+    gmap.first[gmap.n_nb] = n_loc;
+  }
   int64_t n_bnd = 0;
   unsigned bnd_grid = 0;
   uint8_t* bflag = nullptr;
@@ -1610,8 +1775,8 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
     brows = lat_buf<int32_t>(ctx, "pcg_brows", n_own);
     int64_t* d_cnt = lat_buf<int64_t>(ctx, "pcg_bcount", 1);
     if (!bflag || !brows || !d_cnt) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
-    if (mf) LAT_LAUNCH(ctx, k_mark_boundary_mf, (unsigned)ceil_div(n_own, 256), 256, 0, *mf, n_own, bflag);
-    else LAT_LAUNCH(ctx, k_mark_boundary_bsr, (unsigned)ceil_div(n_own, 256), 256, 0, rowptr, colidx, n_own, bflag);
+    if (mf) LAT_LAUNCH(ctx, k_mark_boundary_mf, (unsigned)ceil_div(n_own, 256), 256, 0, *mf, n_own, gmap, bflag);
+    else LAT_LAUNCH(ctx, k_mark_boundary_bsr, (unsigned)ceil_div(n_own, 256), 256, 0, rowptr, colidx, n_own, gmap, bflag);
     LAT_LAUNCH(ctx, k_compact_rows, 1, 1024, 0, bflag, n_own, brows, d_cnt);
     LAT_CUDA(ctx, cudaMemcpyAsync(ctx->h_i64, d_cnt, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1627,6 +1792,50 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
       LAT_CUDA(ctx, cudaEventCreateWithFlags(&pp->ev_join, cudaEventDisableTiming));
     }
   }
+  // Fused halo (default for <= 2 neighbours, i.e. slab partitions; bit 6 of `reserved` selects the separate
+  // halo kernel instead): no halo kernel in the iteration.  The
+  // update kernel pushes the boundary entries of the new u straight into the neighbours' ghost sections and bumps
+  // their entry counters; only the product CTAs that own a ghost-reading row wait for the counter.
+  const bool fused = p2p && !(o->reserved & 64) && h->n_neighbors >= 1 && h->n_neighbors <= 2 && !overlap;
+  HaloPush hpush;
+  RowSet wait_rs;
+  if (fused) {
+    if (!bflag) {
+      bflag = lat_buf<uint8_t>(ctx, "pcg_bflag", n_own);
+      if (!bflag) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+      if (mf) LAT_LAUNCH(ctx, k_mark_boundary_mf, (unsigned)ceil_div(n_own, 256), 256, 0, *mf, n_own, gmap, bflag);
+      else LAT_LAUNCH(ctx, k_mark_boundary_bsr, (unsigned)ceil_div(n_own, 256), 256, 0, rowptr, colidx, n_own, gmap, bflag);
+    }
+    int2* pdst = lat_buf<int2>(ctx, "pcg_push_dst", n_own);
+    if (!pdst) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+    LAT_CUDA(ctx, cudaMemsetAsync(pdst, 0xff, (size_t)n_own * sizeof(int2), ctx->stream));
+    if (push_total > 0) LAT_LAUNCH(ctx, k_build_push_dst, (unsigned)ceil_div(push_total, 256), 256, 0, h->send_idx, pa, pdst);
+    const int rpc = mf ? MF_BLOCK : ROWS_PER_CTA;              // rows per CTA of the product kernel
+    const unsigned n_cta_prod = mf ? mf_grid : grid;
+    uint8_t* cta_need = lat_buf<uint8_t>(ctx, "pcg_cta_need", n_cta_prod);
+    uint8_t* cta_push = lat_buf<uint8_t>(ctx, "pcg_cta_push", grid);
+    if (!cta_need || !cta_push) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+    LAT_LAUNCH(ctx, k_cta_or_rows, (unsigned)ceil_div(n_cta_prod, 128), 128, 0, bflag, n_own, rpc, cta_need);
+    LAT_LAUNCH(ctx, k_cta_or_push, (unsigned)ceil_div(grid, 128), 128, 0, pdst, n_own, (int)ROWS_PER_CTA, cta_push);
+    hpush.dst = pdst;
+    hpush.cta_push = cta_push;
+    wait_rs.cta_need = cta_need;
+    wait_rs.need = bflag;
+    wait_rs.cnt = reinterpret_cast<const P2PArenaHdr*>(pp->arena)->halo_cnt;
+    wait_rs.n_nb = h->n_neighbors;
+    wait_rs.n_own = n_own;
+    for (int k = 0; k < h->n_neighbors; ++k) {
+      hpush.peer_u[k] = reinterpret_cast<double*>(pp->peer[h->peer[k]] + u_off);
+      hpush.peer_cnt[k] = &reinterpret_cast<P2PArenaHdr*>(pp->peer[h->peer[k]])->halo_cnt[pp->rank];
+      wait_rs.nb_rank[k] = h->peer[k];
+      wait_rs.per_push[k] = (unsigned long long)h->recv_count[k] * 6ull;
+    }
+    prm.push_base = pp->pushes_done;
+  }
+  auto push_now = [&]() -> int {   // u was produced by a kernel without the fused push
+    if (fused) LAT_LAUNCH(ctx, k_p2p_push_cnt, halo_grid, 256, 0, h->send_idx, u, pp->d_peer, pa, u_off, sc, prm);
+    return LAT_OK;
+  };
   const int n_part_ov = n_part + (int)bnd_grid;
   auto launch_product_overlapped = [&]() -> int {
     // fork: halo on the side stream
@@ -1638,13 +1847,13 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
     RowSet in_rs, bd_rs;
     in_rs.skip = bflag; in_rs.p_stride = n_part_ov; in_rs.p_offset = 0;
     bd_rs.rows = brows; bd_rs.p_stride = n_part_ov; bd_rs.p_offset = n_part;
-    if (mf) LAT_LAUNCH(ctx, k_cg_spmv_mf, mf_grid, MF_BLOCK, 0, *mf, n_own, u, r, w, sc, partials, prm, in_rs);
-    else LAT_LAUNCH(ctx, k_cg_spmv, grid, SPMV_BLOCK, 0, rowptr, colidx, vals, n_own, u, r, w, sc, partials, prm, in_rs);
+    if (mf) LAT_LAUNCH(ctx, k_cg_spmv_mf<false>, mf_grid, MF_BLOCK, 0, *mf, n_own, u, r, w, sc, partials, prm, in_rs);
+    else LAT_LAUNCH(ctx, k_cg_spmv<false>, grid, SPMV_BLOCK, 0, rowptr, colidx, vals, n_own, u, r, w, sc, partials, prm, in_rs);
     // join: the listed rows need the ghosts
     LAT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, pp->ev_join, 0));
     if (bnd_grid > 0) {
-      if (mf) LAT_LAUNCH(ctx, k_cg_spmv_mf, bnd_grid, MF_BLOCK, 0, *mf, n_bnd, u, r, w, sc, partials, prm, bd_rs);
-      else LAT_LAUNCH(ctx, k_cg_spmv, bnd_grid, SPMV_BLOCK, 0, rowptr, colidx, vals, n_bnd, u, r, w, sc, partials, prm, bd_rs);
+      if (mf) LAT_LAUNCH(ctx, k_cg_spmv_mf<false>, bnd_grid, MF_BLOCK, 0, *mf, n_bnd, u, r, w, sc, partials, prm, bd_rs);
+      else LAT_LAUNCH(ctx, k_cg_spmv<false>, bnd_grid, SPMV_BLOCK, 0, rowptr, colidx, vals, n_bnd, u, r, w, sc, partials, prm, bd_rs);
     }
     return LAT_OK;
   };
@@ -1671,6 +1880,21 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
   double prof_ms = 0.0;
   int prof_n = 0;
   auto spmv_and_reduce = [&]() -> int {
+    if (fused) {
+      if (prof_on) cudaEventRecord(prof_ev[0], ctx->stream);
+      if (mf) LAT_LAUNCH(ctx, k_cg_spmv_mf<true>, mf_grid, MF_BLOCK, 0, *mf, n_own, u, r, w, sc, partials, prm, wait_rs);
+      else LAT_LAUNCH(ctx, k_cg_spmv<true>, grid, SPMV_BLOCK, 0, rowptr, colidx, vals, n_own, u, r, w, sc, partials, prm, wait_rs);
+      if (prof_on) cudaEventRecord(prof_ev[1], ctx->stream);
+      LAT_LAUNCH(ctx, k_p2p_reduce, 1, 1024, 0, partials, n_part, sc, prm, pp->d_peer, pp->nranks, pp->rank);
+      if (prof_on) {
+        cudaEventSynchronize(prof_ev[1]);
+        float ms1 = 0.f;
+        cudaEventElapsedTime(&ms1, prof_ev[0], prof_ev[1]);   // includes the halo wait of the boundary CTAs
+        prof_ms += ms1;
+        ++prof_n;
+      }
+      return LAT_OK;
+    }
     if (p2p && overlap && !prof_on) {
       if (int prc = launch_product_overlapped()) return prc;
       LAT_LAUNCH(ctx, k_p2p_reduce, 1, 1024, 0, partials, n_part_ov, sc, prm, pp->d_peer, pp->nranks, pp->rank);
@@ -1714,10 +1938,12 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
   };
   auto one_iteration = [&]() -> int {
     if (prof_on && trace) cudaEventRecord(tr_ev[0], ctx->stream);
-    LAT_LAUNCH(ctx, k_cg_update<PC>, grid, SPMV_BLOCK, 0, n_own, dinv, x, r, u, w, p, sv, sc, prm);
+    LAT_LAUNCH(ctx, k_cg_update<PC>, grid, SPMV_BLOCK, 0, n_own, dinv, x, r, u, w, p, sv, sc, prm, hpush);
     return spmv_and_reduce();
   };
-  int rc = spmv_and_reduce();  // set-up pass
+  int rc = push_now();
+  if (rc) return rc;
+  rc = spmv_and_reduce();  // set-up pass
   if (rc) return rc;
 
   // `check` iterations (kernels AND NCCL operations) are captured into one CUDA graph
@@ -1809,6 +2035,8 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
     if (ce != cudaSuccess) { rc = lat_cuda_fail(ctx, ce, "distributed PCG residual check", __FILE__, __LINE__); break; }
     true_rr = hs[0].true_rr;
     if (hs[0].done) break;
+    rc = push_now();
+    if (rc) break;
     rc = spmv_and_reduce();   // restart from x: set-up pass
     if (rc) break;
     rc = run_batches((int64_t)o->maxiter - hs[0].iters);
@@ -1819,6 +2047,7 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
   LAT_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
   LAT_CUDA(ctx, cudaMemcpyAsync(&hs[0], sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, ctx->stream));
   LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (fused) pp->pushes_done += (unsigned long long)hs[0].seq;   // identical on every rank (global stop test)
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
   res->iters = hs[0].iters;

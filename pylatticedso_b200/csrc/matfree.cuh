@@ -21,6 +21,8 @@
 // 23 us at BCC 20^3 m=2 (80 % of the nodes have 2 incidences -> 4 of 6 lanes idle, 7 waves of CTAs, each a
 // chain of 4 dependent L2 round trips); one thread per node is a single wave with no idle lanes.
 #pragma once
+#include <cstdint>
+#include <climits>
 #include "common.cuh"
 
 struct __align__(32) MfInc {   // one element end, in the node-sorted incidence order of the pattern
@@ -108,6 +110,20 @@ __device__ __forceinline__ MfNode mf_load_node(const MfOp& op, int64_t n) {
 // 6 consecutive doubles at v + 6 n as ONE 32 B + ONE 16 B access instead of three 16 B ones: 48 n is 32 B
 // aligned for even n, 48 n + 16 for odd n.  The L1 cost of a scattered per-thread access is per instruction
 // (one wavefront per lane and instruction), so this is a third fewer wavefronts on the gathers.
+// same access past L1 (ghost entries written by a peer GPU while this kernel may already be running)
+__device__ __forceinline__ MfU mf_load_u_cg(const double* __restrict__ v, int64_t n) {
+  const char* base = reinterpret_cast<const char*>(v + n * 6);
+  const bool odd = n & 1;
+  const double2 a = __ldcg(reinterpret_cast<const double2*>(base + (odd ? 0 : 32)));
+  double b0, b1, b2, b3;
+  asm volatile("ld.global.cg.v4.f64 {%0, %1, %2, %3}, [%4];"
+               : "=d"(b0), "=d"(b1), "=d"(b2), "=d"(b3) : "l"(base + (odd ? 16 : 0)) : "memory");
+  MfU r;
+  r.a = odd ? a : make_double2(b0, b1);
+  r.b = odd ? make_double2(b0, b1) : make_double2(b2, b3);
+  r.c = odd ? make_double2(b2, b3) : a;
+  return r;
+}
 __device__ __forceinline__ MfU mf_load_u(const double* __restrict__ v, int64_t n) {
   const char* base = reinterpret_cast<const char*>(v + n * 6);
   const bool odd = n & 1;
@@ -159,7 +175,7 @@ static constexpr int MF_BLOCK = 64;    // small CTAs: 9 per SM at <= 113 registe
 // independent gather chains (record -> node + u of the other end) are in flight per thread; joints and
 // strut-interior nodes are numbered apart (mesh.py), so the degree is nearly uniform inside a warp.
 // uo returns the node's own u (unmasked); f the product (identity rows already substituted when MASKED).
-template <bool MASKED>
+template <bool MASKED, bool CG = false>
 __device__ __forceinline__ void mf_node_product(const MfOp& op, int64_t n, const double* __restrict__ u,
                                                 double (&uo)[6], double (&f)[6]) {
   const int lo = __ldg(op.adjptr + n), hi = __ldg(op.adjptr + n + 1);
@@ -175,7 +191,8 @@ __device__ __forceinline__ void mf_node_product(const MfOp& op, int64_t n, const
     const MfRec ra = mf_load_rec(op, j), rb = mf_load_rec(op, j + 1);
     const int oa = __double2loint(ra.ow), ob = __double2loint(rb.ow);
     const MfNode na = mf_load_node(op, oa), nb = mf_load_node(op, ob);
-    const MfU ua = mf_load_u(u, oa), ub = mf_load_u(u, ob);
+    const MfU ua = CG ? mf_load_u_cg(u, oa) : mf_load_u(u, oa);   // CG: past L1 (fused-halo path, rows reading ghosts)
+    const MfU ub = CG ? mf_load_u_cg(u, ob) : mf_load_u(u, ob);
     mf_incidence<MASKED>(op, ra, na, ua, no.x, no.y, no.z, um, f);
     mf_incidence<MASKED>(op, rb, nb, ub, no.x, no.y, no.z, um, f);
   }
@@ -183,7 +200,7 @@ __device__ __forceinline__ void mf_node_product(const MfOp& op, int64_t n, const
     const MfRec ra = mf_load_rec(op, j);
     const int oa = __double2loint(ra.ow);
     const MfNode na = mf_load_node(op, oa);
-    const MfU ua = mf_load_u(u, oa);
+    const MfU ua = CG ? mf_load_u_cg(u, oa) : mf_load_u(u, oa);
     mf_incidence<MASKED>(op, ra, na, ua, no.x, no.y, no.z, um, f);
   }
 #pragma unroll

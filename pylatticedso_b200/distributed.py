@@ -172,7 +172,7 @@ class DistributedFEM:
         self.p2p = True
 
     def solve(self, tol=1e-8, maxiter=200000, precond=2, vals_bc=None, b=None, u=None, check_every=0, profile_iters=0,
-              overlap=False):
+              overlap=False, fused_halo=True):
         """Returns (u_local [6 n_local] incl. ghosts, reactions on owned rows, info)."""
         torch, ctx = self.torch, self.ctx
         if self.vals is None:
@@ -189,14 +189,14 @@ class DistributedFEM:
                                               L._ptr(self.f_d), L._ptr(vals_bc), L._ptr(b)))
         u, info = ctx.pcg_dist(self.rowptr, self.colidx, vals_bc, self.halo, b, u, tol=tol, maxiter=maxiter,
                                precond=precond, check_every=check_every, p2p=getattr(self, "p2p", False),
-                               profile_iters=profile_iters, overlap=overlap)
+                               profile_iters=profile_iters, overlap=overlap, fused_halo=fused_halo)
         ctx.set_dirichlet_values(self.fixed_d, self.g_d, u)
         ctx.halo_exchange(self.halo, u)
         R = ctx.spmv(self.rowptr, self.colidx, self.vals, u)     # rows >= n_owned are partial: ignore
         return u, R, info
 
     def solve_matrix_free(self, tol=1e-8, maxiter=200000, precond=2, b=None, u=None, check_every=0, profile_iters=0,
-                          want_reactions=True, overlap=False):
+                          want_reactions=True, overlap=False, fused_halo=True):
         """:meth:`solve` without an assembled matrix (csrc/matfree.cuh): the operator is regenerated from the
         local mesh in every product; halo exchange and all-reduce are unchanged."""
         torch, ctx = self.torch, self.ctx
@@ -209,7 +209,7 @@ class DistributedFEM:
         ctx.matfree_rhs(self.g_d, self.f_d, out=b)        # rows >= n_owned are partial: never read
         u, info = ctx.pcg_matfree_dist(self.halo, b, u, tol=tol, maxiter=maxiter, precond=precond,
                                        check_every=check_every, p2p=getattr(self, "p2p", False),
-                                       profile_iters=profile_iters, overlap=overlap)
+                                       profile_iters=profile_iters, overlap=overlap, fused_halo=fused_halo)
         ctx.set_dirichlet_values(self.fixed_d, self.g_d, u)
         ctx.halo_exchange(self.halo, u)
         R = ctx.matfree_apply(u, eliminated=False) if want_reactions else None

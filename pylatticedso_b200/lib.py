@@ -398,9 +398,9 @@ class Context:
         self.p2p_ready = False
 
     def pcg_matfree_dist(self, halo, b, x, tol=1e-8, maxiter=10000, precond=PC_JACOBI, check_every=0, p2p=False,
-                         no_graph=False, profile_iters=0, overlap=False):
+                         no_graph=False, profile_iters=0, overlap=False, fused_halo=True):
         o = PcgOpts(tol, 0.0, 0.0, 0, maxiter, precond, 0, check_every, profile_iters,
-                    (16 if p2p else 0) | (4 if no_graph else 0) | (32 if overlap else 0))
+                    (16 if p2p else 0) | (4 if no_graph else 0) | (32 if overlap else 0) | (0 if fused_halo else 64))
         r = PcgResult()
         self.check(self.lib.lat_pcg_matfree_dist(self.h, C.byref(halo), _ptr(b), _ptr(x), C.byref(o), C.byref(r)))
         return x, dict(iters=r.iters, info=r.info, relres=r.relres, norm_b=r.norm_b, solve_ms=r.solve_ms,
@@ -409,10 +409,10 @@ class Context:
 
     def pcg_dist(self, rowptr, colidx, vals, halo, b, x, tol=1e-8, maxiter=10000, precond=PC_JACOBI,
                  reference_semantics=False, mintol=0.0, alpha_max=0.0, restart_every=0, check_every=0, p2p=False,
-                 no_graph=False, profile_iters=0, overlap=False):
+                 no_graph=False, profile_iters=0, overlap=False, fused_halo=True):
         o = PcgOpts(tol, mintol, alpha_max, restart_every, maxiter, precond, int(reference_semantics), check_every,
                     profile_iters,
-                    (16 if p2p else 0) | (4 if no_graph else 0) | (32 if overlap else 0))
+                    (16 if p2p else 0) | (4 if no_graph else 0) | (32 if overlap else 0) | (0 if fused_halo else 64))
         r = PcgResult()
         self.check(self.lib.lat_pcg_bsr_dist(self.h, _ptr(rowptr), _ptr(colidx), _ptr(vals), C.byref(halo), _ptr(b),
                                              _ptr(x), C.byref(o), C.byref(r)))

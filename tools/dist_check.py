@@ -33,13 +33,14 @@ def main():
         if rank == 0:
             K = orc.assemble_csr(mesh.xyz, np.stack([mesh.en0, mesh.en1], 1), mesh.rad, E, NU)
             uo, Ro = orc.solve_static(K, fixed.astype(bool), g, f)
-        for mode in ("nccl", "p2p"):
+        for mode in ("nccl", "p2p", "p2p-fused"):
             if mode == "p2p":
                 dfem.enable_p2p()
+            kw = dict(fused_halo=(mode == "p2p-fused"))
             for op in ("assembled", "matfree"):
                 solve = dfem.solve if op == "assembled" else dfem.solve_matrix_free
-                for rep in range(2 if mode == "p2p" else 1):      # second p2p solve: flags of the first must not match
-                    u, R, info = solve(tol=1e-13, maxiter=100000, precond=L.PC_BLOCK6, check_every=16)
+                for rep in range(1 if mode == "nccl" else 2):      # second p2p solve: flags of the first must not match
+                    u, R, info = solve(tol=1e-13, maxiter=100000, precond=L.PC_BLOCK6, check_every=16, **kw)
                 ug = dfem.gather_owned(u)
                 Rg = dfem.gather_owned(R)
                 if rank == 0:

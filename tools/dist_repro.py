@@ -10,7 +10,8 @@ ctx = L.Context(local); ctx.comm_create(rank, world)
 lat = M.synthetic_lattice("BCC", (20 * world, 20, 20), [0.05]); mesh = M.mesh_from_synthetic(lat, 2)
 fixed, g, f = M.compression_bc(mesh)
 dfem = D.DistributedFEM(ctx, mesh, 1013.0, 0.3, rank, world); dfem.set_bc(fixed, g, f)
-for mode, kw in (("nccl", {}), ("p2p-sequential", dict(overlap=False)), ("p2p-overlap", dict(overlap=True))):
+for mode, kw in (("nccl", {}), ("p2p-sequential", dict(overlap=False, fused_halo=False)), ("p2p-overlap", dict(overlap=True, fused_halo=False)),
+                 ("p2p-fused", dict(fused_halo=True))):
     if mode == "p2p-sequential": dfem.enable_p2p()
     for op, solve in (("assembled", dfem.solve), ("matfree", dfem.solve_matrix_free)):
         its = []
