@@ -472,8 +472,12 @@ __device__ __forceinline__ void halo_push(const HaloPush& hp, int2 d, int comp, 
 
 // GHOST = true is the fused-halo instantiation (waits, ghost-reading rows load their columns past L1); the
 // default instantiation carries none of it -- a per-column branch in the gather loop cost 25 % on one GPU.
-template <bool GHOST = false>
-__global__ void __launch_bounds__(SPMV_BLOCK) k_cg_spmv(const int32_t* __restrict__ rowptr,
+// SUBSET = true enables rs.rows / rs.skip (opt-in overlap path); without it the row extent and own entries
+// are loaded before the status word is looked at -- a skip[] load in front of them serialised one more
+// memory round trip per CTA (+9 % at 15 waves of CTAs).
+template <bool GHOST = false, bool SUBSET = false>
+__global__ void __launch_bounds__(SPMV_BLOCK) k_cg_spmv(
+const int32_t* __restrict__ rowptr,
                                                         const int32_t* __restrict__ colidx,
                                                         const double* __restrict__ vals, int64_t n_nodes,
                                                         const double* __restrict__ u, const double* __restrict__ r,
@@ -485,8 +489,10 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_cg_spmv(const int32_t* __restric
   const int64_t warp = (int64_t)blockIdx.x * (SPMV_BLOCK / 32) + (threadIdx.x >> 5);
   int64_t n = warp * ROWS_PER_WARP + g;
   bool active = g < ROWS_PER_WARP && n < n_nodes;
-  if (rs.rows) n = active ? rs.rows[n] : 0;
-  if (rs.skip && active && rs.skip[n]) active = false;
+  if (SUBSET) {
+    if (rs.rows) n = active ? rs.rows[n] : 0;
+    if (rs.skip && active && rs.skip[n]) active = false;
+  }
   // independent loads first: the row extent and the own-row entries do not depend on the status word
   int lo = 0, hi = 0;
   double uo = 0.0, ro = 0.0;
@@ -530,15 +536,17 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_cg_spmv(const int32_t* __restric
 
 // Matrix-free twin of k_cg_spmv: w = A u regenerated from the geometry (matfree.cuh, one thread per node),
 // same three dots.
-template <bool GHOST = false>
+template <bool GHOST = false, bool SUBSET = false>
 __global__ void __launch_bounds__(MF_BLOCK, 9) k_cg_spmv_mf(MfOp op, int64_t n_nodes, const double* __restrict__ u,
                                                          const double* __restrict__ r, double* __restrict__ w,
                                                          PcgScalars* __restrict__ sc, double* __restrict__ partials,
                                                          PcgParams prm, RowSet rs = RowSet()) {
   int64_t n = (int64_t)blockIdx.x * MF_BLOCK + threadIdx.x;
   bool active = n < n_nodes;
-  if (rs.rows) n = active ? rs.rows[n] : 0;
-  if (rs.skip && active && rs.skip[n]) active = false;
+  if (SUBSET) {
+    if (rs.rows) n = active ? rs.rows[n] : 0;
+    if (rs.skip && active && rs.skip[n]) active = false;
+  }
   MfU rr;
   rr.a = rr.b = rr.c = make_double2(0.0, 0.0);
   if (active) rr = mf_load_u(r, n);
@@ -1847,13 +1855,13 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
     RowSet in_rs, bd_rs;
     in_rs.skip = bflag; in_rs.p_stride = n_part_ov; in_rs.p_offset = 0;
     bd_rs.rows = brows; bd_rs.p_stride = n_part_ov; bd_rs.p_offset = n_part;
-    if (mf) LAT_LAUNCH(ctx, k_cg_spmv_mf<false>, mf_grid, MF_BLOCK, 0, *mf, n_own, u, r, w, sc, partials, prm, in_rs);
-    else LAT_LAUNCH(ctx, k_cg_spmv<false>, grid, SPMV_BLOCK, 0, rowptr, colidx, vals, n_own, u, r, w, sc, partials, prm, in_rs);
+    if (mf) LAT_LAUNCH(ctx, (k_cg_spmv_mf<false, true>), mf_grid, MF_BLOCK, 0, *mf, n_own, u, r, w, sc, partials, prm, in_rs);
+    else LAT_LAUNCH(ctx, (k_cg_spmv<false, true>), grid, SPMV_BLOCK, 0, rowptr, colidx, vals, n_own, u, r, w, sc, partials, prm, in_rs);
     // join: the listed rows need the ghosts
     LAT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, pp->ev_join, 0));
     if (bnd_grid > 0) {
-      if (mf) LAT_LAUNCH(ctx, k_cg_spmv_mf<false>, bnd_grid, MF_BLOCK, 0, *mf, n_bnd, u, r, w, sc, partials, prm, bd_rs);
-      else LAT_LAUNCH(ctx, k_cg_spmv<false>, bnd_grid, SPMV_BLOCK, 0, rowptr, colidx, vals, n_bnd, u, r, w, sc, partials, prm, bd_rs);
+      if (mf) LAT_LAUNCH(ctx, (k_cg_spmv_mf<false, true>), bnd_grid, MF_BLOCK, 0, *mf, n_bnd, u, r, w, sc, partials, prm, bd_rs);
+      else LAT_LAUNCH(ctx, (k_cg_spmv<false, true>), bnd_grid, SPMV_BLOCK, 0, rowptr, colidx, vals, n_bnd, u, r, w, sc, partials, prm, bd_rs);
     }
     return LAT_OK;
   };

@@ -33,7 +33,7 @@ for geom, n, m_, r in (("BCC", 60, 1, 0.05), ("Octet", 40, 1, 0.03)):
     rowptr, colidx = ctx.bsr_pattern(en0, en1, N); nnzb = colidx.numel()
     print(f"{'pattern build (one-off)':34s} {cfg:28s} {ms:10.2f} ms   N={N} E={Ecount} nnzb={nnzb}", flush=True)
     vals = torch.empty(nnzb * 36, dtype=torch.float64, device=dev)
-    ms = timeit(lambda: ctx.assemble_bsr(x, y, z, en0, en1, rad, N, nnzb, E, NU, out=vals))
+    ms = timeit(lambda: ctx.assemble_bsr(x, y, z, en0, en1, rad, N, nnzb, E, NU, mode=L.ASM_GATHER, out=vals))
     line("k_assemble_gather (fused)", cfg, Ecount, "elements", ms, Ecount * 1216)
     print(f"{'':34s} {'  actual HBM write 288 B/block':28s} {nnzb*288/ms/1e6:8.0f} GB/s  frac={nnzb*288/ms/1e6/peak:5.2f}")
     ms = timeit(lambda: ctx.assemble_bsr(x, y, z, en0, en1, rad, N, nnzb, E, NU, mode=L.ASM_ROWS, out=vals))
@@ -64,6 +64,17 @@ for geom, n, m_, r in (("BCC", 60, 1, 0.05), ("Octet", 40, 1, 0.03)):
         print(f"{'PCG (CG form) ' + name:34s} {cfg:28s} iters={info['iters']} info={info['info']} solve={info['solve_ms']:.2f} ms  {6*N*info['iters']/info['solve_ms']/1e6:8.2f} G DOF-it/s  "
               f"spmv={1e3*info['spmv_ms']:.1f} us ({(nnzb*292+N*148)/info['spmv_ms']/1e6:.0f} GB/s frac={(nnzb*292+N*148)/info['spmv_ms']/1e6/peak:.2f}) update={1e3*info['update_ms']:.1f} us  "
               f"iteration(SURVEY bytes)={it_bytes*info['iters']/info['solve_ms']/1e6:.0f} GB/s frac={it_bytes*info['iters']/info['solve_ms']/1e6/peak:.2f}", flush=True)
+    # matrix-free operator on the same system: product alone, then the PCG
+    ctx.matfree_setup(x, y, z, en0, en1, rad, N, E, NU, fixed=fd)
+    ms = timeit(lambda: ctx.matfree_apply(u, out=yv, eliminated=True))
+    n_inc = 2 * Ecount
+    print(f"{'k_mf_apply (matrix-free y = A u)':34s} {cfg:28s} {6*N/ms/1e6:10.2f} G DOF/s  {ms*1e3:10.1f} us  {n_inc/ms/1e6:6.1f} G incidences/s  "
+          f"streamed {(n_inc*32 + N*(32+96))/ms/1e6:.0f} GB/s  [assembled-equivalent {(nnzb*292+N*100)/ms/1e6:.0f} GB/s = {(nnzb*292+N*100)/ms/1e6/peak:.2f} of HBM peak]", flush=True)
+    bm = ctx.matfree_rhs(gd, fv)
+    for pc, name in ((1, "jacobi"), (2, "block6")):
+        uu, info = ctx.pcg_matfree(bm, tol=1e-8, maxiter=20000, precond=pc, profile_iters=64)
+        print(f"{'PCG matrix-free ' + name:34s} {cfg:28s} iters={info['iters']} info={info['info']} solve={info['solve_ms']:.2f} ms  {6*N*info['iters']/info['solve_ms']/1e6:8.2f} G DOF-it/s  "
+              f"product={1e3*info['spmv_ms']:.1f} us update={1e3*info['update_ms']:.1f} us ({6*N*(88+(28 if pc==2 else 8))/info['update_ms']/1e6:.0f} GB/s frac={6*N*(88+(28 if pc==2 else 8))/info['update_ms']/1e6/peak:.2f})", flush=True)
     del vals, vbc, u, yv
     torch.cuda.empty_cache()
 
