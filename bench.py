@@ -38,9 +38,9 @@ if ROOT not in sys.path:
 E_MOD, NU, KAPPA = 1013.0, 0.3, 0.9
 METRIC = "pcg_dof_iters_per_s"
 UNIT = "DOF-iterations/s"
-# ncu --set full capture of k_cg_spmv on this workload (profiles/r01_ncu_full_v3_cg_kernels.csv):
+# ncu --set full capture of k_cg_spmv on this workload (profiles/r01_ncu_full_v4_kernels.txt):
 # dram__bytes_read.sum 106.76 MB + dram__bytes_write.sum 3.65 MB per launch (algorithmic: 110.5 MB)
-NCU_TRAFFIC_CG_SPMV = 110.4e6
+NCU_TRAFFIC_CG_SPMV = 111.3e6   # dram__bytes_read.sum + dram__bytes_write.sum of one k_cg_spmv launch (profiles/r01_ncu_full_v4_kernels.txt)
 WORKLOAD = "BCC 20x20x20, r=0.05, 2 elements/strut (487566 DOF), uniaxial compression, block-Jacobi PCG to 1e-8"
 
 
@@ -418,7 +418,7 @@ def run_b200(args):
                      "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": (ach / hbm_peak) if ach else None,
                      "traffic": NCU_TRAFFIC_CG_SPMV if world == 1 else None,
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full "
-                                       "(profiles/r01_ncu_full_v3_cg_kernels.csv)",
+                                       "(profiles/r01_ncu_full_v4_kernels.txt)",
                      "peak_source": peak_src, "bytes_per_launch": spmv_bytes(nn, nz),
                      "avg_launch_ms": res["spmv_ms"], "launches_timed": res["nprof"],
                      "note": None if world == 1 else "rank 0's kernel over rank 0's slab (per-GPU peak); see pcg.iteration_frac_of_hbm "
