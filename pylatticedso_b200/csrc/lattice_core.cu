@@ -145,6 +145,39 @@ __global__ void __launch_bounds__(128) k_elem_stiffness(
   }
 }
 
+// Same output, one thread per ELEMENT: the four 6x6 quadrants are generated with compile-time indices
+// (no div/mod per entry) and each 96 B row of K_e leaves as three 256-bit stores.  The per-entry kernel above
+// is issue-bound at 0.32 of HBM; it stays as the fallback for an output that is not 32 B aligned.
+__device__ __forceinline__ void st256_ke(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__global__ void __launch_bounds__(128) k_elem_stiffness_rows(
+    const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+    const int32_t* __restrict__ en0, const int32_t* __restrict__ en1,
+    const double* __restrict__ rad, int64_t n_elem, double young, double nu, double kappa,
+    int drad, double* __restrict__ Ke) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_elem) return;
+  const int a = en0[e], b = en1[e];
+  const ElemCoef co = elem_coef(x[a], y[a], z[a], x[b], y[b], z[b], rad[e], young, nu, kappa, drad != 0);
+  double* out = Ke + e * 144;
+#pragma unroll
+  for (int re = 0; re < 2; ++re) {
+    double q0[36], q1[36];
+#pragma unroll
+    for (int k = 0; k < 36; ++k) { q0[k] = 0.0; q1[k] = 0.0; }
+    elem_block_accum(co, re, 0, 1.0, q0);
+    elem_block_accum(co, re, 1, 1.0, q1);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      double* row = out + (re * 6 + i) * 12;
+      st256_ke(row, q0[i * 6], q0[i * 6 + 1], q0[i * 6 + 2], q0[i * 6 + 3]);
+      st256_ke(row + 4, q0[i * 6 + 4], q0[i * 6 + 5], q1[i * 6], q1[i * 6 + 1]);
+      st256_ke(row + 8, q1[i * 6 + 2], q1[i * 6 + 3], q1[i * 6 + 4], q1[i * 6 + 5]);
+    }
+  }
+}
+
 extern "C" int lat_elem_stiffness(lat_ctx* ctx, const double* x, const double* y, const double* z,
                                   const int32_t* en0, const int32_t* en1, const double* rad,
                                   int64_t n_elem, double young, double nu, double kappa, int drad,
@@ -155,8 +188,12 @@ extern "C" int lat_elem_stiffness(lat_ctx* ctx, const double* x, const double* y
   LAT_CHECK_ARG(ctx, x && y && z && en0 && en1 && rad && Ke);
   LAT_CUDA(ctx, cudaSetDevice(ctx->device));
   const int64_t grid = ceil_div(n_elem, 128);
-  LAT_LAUNCH(ctx, k_elem_stiffness, (unsigned)grid, 128, 0, x, y, z, en0, en1, rad, n_elem, young, nu,
-             kappa, drad, Ke);
+  if ((reinterpret_cast<uintptr_t>(Ke) & 31) == 0)
+    LAT_LAUNCH(ctx, k_elem_stiffness_rows, (unsigned)grid, 128, 0, x, y, z, en0, en1, rad, n_elem, young, nu,
+               kappa, drad, Ke);
+  else
+    LAT_LAUNCH(ctx, k_elem_stiffness, (unsigned)grid, 128, 0, x, y, z, en0, en1, rad, n_elem, young, nu,
+               kappa, drad, Ke);
   return LAT_OK;
 }
 
