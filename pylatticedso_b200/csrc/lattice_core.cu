@@ -759,6 +759,38 @@ __global__ void __launch_bounds__(256) k_dirichlet_vals(const int32_t* __restric
   vout[i] = v;
 }
 
+// Same elimination, one thread per 6x6 BLOCK with nine 256-bit loads and stores (the per-entry kernel above
+// spends its time on index arithmetic: 3.0 TB/s).  In place, a block that touches no constrained DOF is not
+// read at all.  vin may alias vout.
+__global__ void __launch_bounds__(128) k_dirichlet_blocks(const int32_t* __restrict__ blockrow,
+                                                          const int32_t* __restrict__ colidx,
+                                                          const uint8_t* __restrict__ mask, int64_t nnzb,
+                                                          const double* vin, double* vout) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nnzb) return;
+  const int rn = blockrow[b], cn = colidx[b];
+  const unsigned rm = mask[rn], cm = mask[cn];
+  if (vin == vout && (rm | cm) == 0u) return;
+  const double* src = vin + b * 36;
+  double* dst = vout + b * 36;
+  double v[36];
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];"
+                 : "=d"(v[4 * k]), "=d"(v[4 * k + 1]), "=d"(v[4 * k + 2]), "=d"(v[4 * k + 3]) : "l"(src + 4 * k) : "memory");
+  if (rm | cm) {
+#pragma unroll
+    for (int e = 0; e < 36; ++e) {
+      const int a = e / 6, c = e - a * 6;
+      if (((rm >> a) & 1u) | ((cm >> c) & 1u)) v[e] = (rn == cn && a == c) ? 1.0 : 0.0;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * k), "d"(v[4 * k]), "d"(v[4 * k + 1]),
+                 "d"(v[4 * k + 2]), "d"(v[4 * k + 3]) : "memory");
+}
+
 __global__ void k_blockrow_from_rowptr(const int32_t* __restrict__ rowptr, int64_t n_nodes, int32_t* __restrict__ blockrow) {
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= n_nodes) return;
@@ -823,7 +855,10 @@ extern "C" int lat_apply_dirichlet(lat_ctx* ctx, const int32_t* rowptr, const in
     if (!mask || !blockrow) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
     LAT_LAUNCH(ctx, k_node_mask, (unsigned)ceil_div(n_nodes, 256), 256, 0, fixed, n_nodes, mask);
     LAT_LAUNCH(ctx, k_blockrow_from_rowptr, (unsigned)ceil_div(n_nodes, 256), 256, 0, rowptr, n_nodes, blockrow);
-    LAT_LAUNCH(ctx, k_dirichlet_vals, (unsigned)ceil_div(nz * 36, 256), 256, 0, blockrow, colidx, mask, nz, vals, vals_bc);
+    if (((reinterpret_cast<uintptr_t>(vals) | reinterpret_cast<uintptr_t>(vals_bc)) & 31) == 0)
+      LAT_LAUNCH(ctx, k_dirichlet_blocks, (unsigned)ceil_div(nz, 128), 128, 0, blockrow, colidx, mask, nz, vals, vals_bc);
+    else
+      LAT_LAUNCH(ctx, k_dirichlet_vals, (unsigned)ceil_div(nz * 36, 256), 256, 0, blockrow, colidx, mask, nz, vals, vals_bc);
   }
   return LAT_OK;
 }
