@@ -367,3 +367,36 @@ def compliance_gradient(xyz, en, rad, u, group, n_groups, E, nu, kappa=KAPPA, ch
     ok = np.asarray(group) >= 0
     np.add.at(g, np.asarray(group)[ok], -q[ok])
     return g
+
+
+def element_action_closed_form(x_own, x_other, r, u_own, u_other, E, nu, kappa=KAPPA):
+    """Force of ONE element on its end node ``own`` as the closed form the CUDA matrix-free operator evaluates
+    (pylatticedso_b200/csrc/matfree.cuh) -- checker for that algebra, vectorised over a batch:
+
+        dw = w_i - w_j,  st = th_i + th_j,  dth = th_i - th_j,  t = (x_j - x_i)/L
+        f_w  = aI dw + aT t (t.dw) - c (t x st)
+        f_th = bI (st - t (t.st)) + dI dth + dT t (t.dth) + c (t x dw)
+
+    with aI = GS/L, aT = (ES-GS)/L, c = GS/2, bI = GS L/4, dI = EI/L, dT = (GJ-EI)/L -- equal to the rows of
+    ``element_stiffness`` (beam_model.py:197-216 through the explicit frame) for either end of the element.
+    Returns [n, 6]."""
+    x_own, x_other = np.atleast_2d(x_own).astype(np.float64), np.atleast_2d(x_other).astype(np.float64)
+    u_own, u_other = np.atleast_2d(u_own).astype(np.float64), np.atleast_2d(u_other).astype(np.float64)
+    r = np.atleast_1d(np.asarray(r, dtype=np.float64))
+    d = x_other - x_own
+    L = np.linalg.norm(d, axis=1)
+    t = d / L[:, None]
+    G = E / (2.0 * (1.0 + nu))
+    S = np.pi * r ** 2
+    I = np.pi * r ** 4 / 4.0
+    ES, GS, EI, GJ = E * S, G * kappa * S, E * I, G * 2.0 * I
+    aI, aT, c, bI, dI, dT = GS / L, (ES - GS) / L, 0.5 * GS, 0.25 * GS * L, EI / L, (GJ - EI) / L
+    dw = u_own[:, :3] - u_other[:, :3]
+    st = u_own[:, 3:] + u_other[:, 3:]
+    dth = u_own[:, 3:] - u_other[:, 3:]
+    dot = lambda a, b: np.einsum("ij,ij->i", a, b)[:, None]
+    col = lambda v: v[:, None]
+    f_w = col(aI) * dw + col(aT) * t * dot(t, dw) - col(c) * np.cross(t, st)
+    f_t = col(bI) * (st - t * dot(t, st)) + col(dI) * dth + col(dT) * t * dot(t, dth) + col(c) * np.cross(t, dw)
+    return np.concatenate([f_w, f_t], axis=1)
+
