@@ -271,6 +271,20 @@ int lat_schur_batch(lat_ctx* ctx, const double* xyz, const int32_t* len0, const 
                     int32_t n_loc_elem, double young, double nu, double kappa, double* S,
                     const int32_t* elem_group, const double* drad_chain, int32_t n_grad, double* dS);
 
+/* Same S_c through the strut pre-pass (no sensitivities): every chain of collinear elements between two joints
+ * (the reference meshes a strut with ~18 elements, schur_complement.py / gmsh h = 0.05 cell size) is condensed
+ * exactly onto its end joints first -- one thread per (cell, strut), O(elements) scalar work -- and the dense
+ * condensation runs on the joint-only cell (BCC: 54 DOFs for any subdivision).
+ *   chain_ptr int32[n_chains+1], chain_elem / chain_flip int32[n_loc_elem]: the elements of each chain in walking
+ *   order (flip = 1: walked from its second to its first node); chain_a / chain_b int32[n_chains]: end joints in
+ *   the REDUCED numbering (n_joints joints, the n_bnd_nodes boundary nodes first, in the order of S's rows).
+ *   xyz / rad / len0 / len1 keep the FULL local numbering of lat_schur_batch. */
+int lat_schur_batch_chains(lat_ctx* ctx, const double* xyz, const int32_t* len0, const int32_t* len1,
+                           const double* rad, int64_t n_cells, int32_t n_loc_nodes, int32_t n_loc_elem,
+                           const int32_t* chain_ptr, const int32_t* chain_elem, const int32_t* chain_flip,
+                           const int32_t* chain_a, const int32_t* chain_b, int32_t n_chains, int32_t n_joints,
+                           int32_t n_bnd_nodes, double young, double nu, double kappa, double* S);
+
 /* ---- A8: DDM interface operator ------------------------------------------------
  * y = sum_c B_c S_c B_c^T x  (LatticeSim.calculate_reaction_force_global ->
  * update_reaction_force_each_cell -> solve_sub_problem, lattice_sim.py:1180-1252,

@@ -400,3 +400,127 @@ def element_action_closed_form(x_own, x_other, r, u_own, u_other, E, nu, kappa=K
     f_t = col(bI) * (st - t * dot(t, st)) + col(dI) * dth + col(dT) * t * dot(t, dth) + col(c) * np.cross(t, dw)
     return np.concatenate([f_w, f_t], axis=1)
 
+
+# ---------------------------------------------------------------------------------------------------------
+# Chain condensation (checker for lat_schur_batch's strut pre-pass, pylatticedso_b200/csrc/lattice_schur.cu)
+# ---------------------------------------------------------------------------------------------------------
+def find_chains(n_nodes, en, keep, xyz, tol=1e-9):
+    """Split a cell mesh into straight strut chains.  A CHAIN NODE is a node that is not in ``keep`` (the
+    boundary nodes), has exactly two incident elements and these are collinear.  Returns a list of
+    (A, B, [(element, flipped), ...]) walking from joint A to joint B; elements that touch no chain node
+    come back as chains of length one.  Exact restatement target: eliminating the chain nodes first is plain
+    static condensation, so the Schur complement on ``keep`` is unchanged."""
+    en = np.asarray(en)
+    deg = np.bincount(en.ravel(), minlength=n_nodes)
+    inc = [[] for _ in range(n_nodes)]
+    for e, (a, b) in enumerate(en):
+        inc[a].append(e)
+        inc[b].append(e)
+    is_keep = np.zeros(n_nodes, dtype=bool)
+    is_keep[np.asarray(keep)] = True
+    d = xyz[en[:, 1]] - xyz[en[:, 0]]
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    chain_node = np.zeros(n_nodes, dtype=bool)
+    for n in range(n_nodes):
+        if not is_keep[n] and deg[n] == 2:
+            e0, e1 = inc[n]
+            chain_node[n] = np.linalg.norm(np.cross(d[e0], d[e1])) < tol
+    used = np.zeros(len(en), dtype=bool)
+    chains = []
+    for e_start in range(len(en)):
+        if used[e_start]:
+            continue
+        a, b = en[e_start]
+        if chain_node[a] and chain_node[b]:
+            continue                      # interior of a chain: reached from one of its ends
+        # orient so that the walk starts at a joint
+        start, nxt, flipped = (a, b, False) if not chain_node[a] else (b, a, True)
+        seq = [(e_start, flipped)]
+        used[e_start] = True
+        while chain_node[nxt]:
+            e_next = [e for e in inc[nxt] if not used[e]][0]
+            used[e_next] = True
+            a2, b2 = en[e_next]
+            fl = a2 != nxt
+            seq.append((e_next, fl))
+            nxt = b2 if not fl else a2
+        chains.append((int(start), int(nxt), seq))
+    assert used.all(), "closed loop of chain nodes"
+    return chains
+
+
+def condensed_strut(xyz, en, rad, chain, E, nu, kappa=KAPPA):
+    """12x12 stiffness of a straight chain of elements condensed onto its two end joints, computed the way
+    the CUDA pre-pass does: in the frame of the strut the problem splits into an axial spring series
+    (sum L/ES), a torsion spring series (sum L/GJ) and ONE planar Timoshenko beam (the two bending planes are
+    identical for a circular section), whose 4x4 matrix on (W_A, Phi_A, W_B, Phi_B) is condensed with 2x2 pivots:
+        M_WW(re,ce) = sA GS/L,  M_WPhi(re,ce) = (re==0 ? -GS/2 : GS/2),  M_PhiPhi(re,ce) = GS L/4 + sA EI/L.
+    Back in 3-D:  ww = M_WW (I - tt) + k_ax tt,  w-theta = M_WPhi [t]x,  theta-w = -M_PhiW [t]x,
+                  theta-theta = M_PhiPhi (I - tt) + k_tor tt."""
+    A, B, seq = chain
+    G = E / (2.0 * (1.0 + nu))
+    t = None
+    flex_ax = flex_tor = 0.0
+    M = None                         # planar beam condensed so far on (W_A, Phi_A, W_k, Phi_k)
+    for e, flipped in seq:
+        a, b = (en[e][1], en[e][0]) if flipped else (en[e][0], en[e][1])
+        dvec = xyz[b] - xyz[a]
+        L = np.linalg.norm(dvec)
+        if t is None:
+            t = dvec / L
+        r = rad[e]
+        S = np.pi * r * r
+        I = np.pi * r ** 4 / 4.0
+        ES, GS, EI, GJ = E * S, G * kappa * S, E * I, G * 2.0 * I
+        flex_ax += L / ES
+        flex_tor += L / GJ
+        Me = np.array([[GS / L, -GS / 2, -GS / L, -GS / 2],
+                       [-GS / 2, GS * L / 4 + EI / L, GS / 2, GS * L / 4 - EI / L],
+                       [-GS / L, GS / 2, GS / L, GS / 2],
+                       [-GS / 2, GS * L / 4 - EI / L, GS / 2, GS * L / 4 + EI / L]])
+        if M is None:
+            M = Me
+        else:
+            # 6x6 on (A, k, next); eliminate the middle pair k
+            T = np.zeros((6, 6))
+            T[:4, :4] += M
+            T[2:, 2:] += Me
+            keep = [0, 1, 4, 5]
+            P = T[2:4, 2:4]
+            C = T[np.ix_(keep, [2, 3])]
+            M = T[np.ix_(keep, keep)] - C @ np.linalg.solve(P, C.T)
+    k_ax, k_tor = 1.0 / flex_ax, 1.0 / flex_tor
+    tt = np.outer(t, t)
+    Pp = np.eye(3) - tt
+    Sk = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+    K = np.zeros((12, 12))
+    for re in range(2):
+        for ce in range(2):
+            sA = 1.0 if re == ce else -1.0
+            K[6 * re:6 * re + 3, 6 * ce:6 * ce + 3] = M[2 * re, 2 * ce] * Pp + sA * k_ax * tt
+            K[6 * re:6 * re + 3, 6 * ce + 3:6 * ce + 6] = M[2 * re, 2 * ce + 1] * Sk
+            K[6 * re + 3:6 * re + 6, 6 * ce:6 * ce + 3] = -M[2 * re + 1, 2 * ce] * Sk
+            K[6 * re + 3:6 * re + 6, 6 * ce + 3:6 * ce + 6] = M[2 * re + 1, 2 * ce + 1] * Pp + sA * k_tor * tt
+    return K, (A, B)
+
+
+def schur_via_chain_condensation(xyz, en, rad, bnd_nodes, E, nu, kappa=KAPPA):
+    """Schur complement on the boundary DOFs computed from the JOINT-ONLY cell (every straight strut replaced by
+    its condensed 12x12 super-element).  Equal to ``schur_complement(assemble_csr(...), bnd_dofs)``."""
+    xyz = np.asarray(xyz, dtype=np.float64)
+    en = np.asarray(en)
+    n_nodes = xyz.shape[0]
+    chains = find_chains(n_nodes, en, bnd_nodes, xyz)
+    joints = sorted({c[0] for c in chains} | {c[1] for c in chains} | set(int(b) for b in bnd_nodes))
+    jpos = {n: k for k, n in enumerate(joints)}
+    Kj = np.zeros((6 * len(joints), 6 * len(joints)))
+    for ch in chains:
+        Ks, (A, B) = condensed_strut(xyz, en, rad, ch, E, nu, kappa)
+        idx = np.r_[6 * jpos[A] + np.arange(6), 6 * jpos[B] + np.arange(6)]
+        Kj[np.ix_(idx, idx)] += Ks
+    bd = np.concatenate([6 * jpos[int(b)] + np.arange(6) for b in bnd_nodes])
+    it = np.setdiff1d(np.arange(Kj.shape[0]), bd)
+    if it.size == 0:
+        return Kj[np.ix_(bd, bd)], chains
+    return Kj[np.ix_(bd, bd)] - Kj[np.ix_(bd, it)] @ np.linalg.solve(Kj[np.ix_(it, it)], Kj[np.ix_(it, bd)]), chains
+

@@ -39,17 +39,139 @@ __device__ void strain_vectors_dev(const double* xa, const double* xb, double* B
   *Lout = L;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Strut pre-pass: exact static condensation of straight element chains
+// ---------------------------------------------------------------------------------------------------
+// The reference meshes every strut with ~18 elements (gmsh rule h = 0.05 cell size), i.e. 822 of the 870 DOFs
+// of a BCC cell sit on degree-2 nodes inside straight struts.  In the frame of a straight strut of circular
+// section the stiffness splits into an axial spring series (sum L/ES), a torsion spring series (sum L/GJ) and
+// ONE planar Timoshenko beam (both bending planes are identical) on (W, Phi = i*Theta):
+//     M_WW(re,ce) = sA GS/L    M_WPhi(re,ce) = (re == 0 ? -GS/2 : GS/2)    M_PhiPhi(re,ce) = GS L/4 + sA EI/L
+// whose chain is condensed with 2x2 pivots by ONE THREAD per (cell, strut): O(m) scalar work instead of m - 1
+// dense 6x6 pivots.  Back in 3-D the condensed 12x12 "super-element" is
+//     ww = M_WW (I - tt) + k_ax tt,  w-th = M_WPhi [t]x,  th-w = -M_PhiW [t]x,  th-th = M_PhiPhi (I - tt) + k_tor tt
+// and the cell keeps its joints only (BCC: 9 nodes for ANY subdivision).  Checker: oracle.condensed_strut /
+// schur_via_chain_condensation, equal to the reference's 30 stored Schur matrices to 1.3e-12.
+struct SupCoef {
+  double tx, ty, tz, kax, ktor;
+  double m[10];   // symmetric 4x4 on (W_A, Phi_A, W_B, Phi_B), upper triangle row-major
+  double pad;
+};
+__host__ __device__ __forceinline__ int sym4(int r, int c) {   // index into m[] of entry (r, c)
+  const int i = r < c ? r : c, j = r < c ? c : r;
+  return i * 4 - (i * (i - 1)) / 2 + (j - i);
+}
+
+__global__ void __launch_bounds__(128) k_chain_condense(
+    const double* __restrict__ xyz, const int32_t* __restrict__ len0, const int32_t* __restrict__ len1,
+    const double* __restrict__ rad, int64_t n_cells, int nn, int ne, const int32_t* __restrict__ chain_ptr,
+    const int32_t* __restrict__ chain_elem, const int32_t* __restrict__ chain_flip, int n_chains, double young,
+    double nu, double kappa, SupCoef* __restrict__ sup) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_cells * n_chains) return;
+  const int64_t c = w / n_chains;
+  const int ch = (int)(w - c * n_chains);
+  const double* cx = xyz + c * (int64_t)nn * 3;
+  const double* cr = rad + c * (int64_t)ne;
+  const double PI = 3.14159265358979323846, G = young / (2.0 * (1.0 + nu));
+  double flex_ax = 0.0, flex_tor = 0.0;
+  double tx = 0.0, ty = 0.0, tz = 0.0;
+  // condensed planar beam so far, blocks on (A, k): aa, ak, kk (2x2 each; aa, kk symmetric)
+  double aa[2][2], ak[2][2], kk[2][2];
+  for (int q = chain_ptr[ch]; q < chain_ptr[ch + 1]; ++q) {
+    const int e = chain_elem[q];
+    const bool fl = chain_flip[q] != 0;
+    const int a = fl ? len1[e] : len0[e], b = fl ? len0[e] : len1[e];
+    const double dx = cx[b * 3] - cx[a * 3], dy = cx[b * 3 + 1] - cx[a * 3 + 1], dz = cx[b * 3 + 2] - cx[a * 3 + 2];
+    const double L = sqrt(dx * dx + dy * dy + dz * dz), iL = 1.0 / L;
+    const double r = cr[e];
+    const double S = PI * r * r, I = PI * r * r * r * r * 0.25;
+    const double ES = young * S, GS = G * kappa * S, EI = young * I, GJ = G * 2.0 * I;
+    flex_ax += L / ES;
+    flex_tor += L / GJ;
+    // element planar beam on (k, n): diagonal blocks [[GS/L, -+GS/2], [-+GS/2, GS L/4 + EI/L]], coupling below
+    const double g1 = GS * iL, g2 = 0.5 * GS, dp = 0.25 * GS * L + EI * iL, dm = 0.25 * GS * L - EI * iL;
+    if (q == chain_ptr[ch]) {
+      tx = dx * iL; ty = dy * iL; tz = dz * iL;
+      aa[0][0] = g1; aa[0][1] = -g2; aa[1][0] = -g2; aa[1][1] = dp;
+      ak[0][0] = -g1; ak[0][1] = -g2; ak[1][0] = g2; ak[1][1] = dm;
+      kk[0][0] = g1; kk[0][1] = g2; kk[1][0] = g2; kk[1][1] = dp;
+      continue;
+    }
+    // pivot P = kk + E_kk with E_kk = [[g1, -g2], [-g2, dp]];  E_kn = [[-g1, -g2], [g2, dm]];  E_nn = [[g1, g2], [g2, dp]]
+    const double p00 = kk[0][0] + g1, p01 = kk[0][1] - g2, p11 = kk[1][1] + dp;
+    const double idet = 1.0 / (p00 * p11 - p01 * p01);
+    const double i00 = p11 * idet, i01 = -p01 * idet, i11 = p00 * idet;     // P^-1 (symmetric)
+    const double ekn[2][2] = {{-g1, -g2}, {g2, dm}};
+    // X = ak P^-1 (2x2),  Y = E_kn^T P^-1 ... work with explicit products
+    double x[2][2], y[2][2];   // x = ak * Pinv,  y = ekn^T * Pinv
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      x[i][0] = ak[i][0] * i00 + ak[i][1] * i01;
+      x[i][1] = ak[i][0] * i01 + ak[i][1] * i11;
+      y[i][0] = ekn[0][i] * i00 + ekn[1][i] * i01;
+      y[i][1] = ekn[0][i] * i01 + ekn[1][i] * i11;
+    }
+    double naa[2][2], nan_[2][2], nnn[2][2];
+    const double enn[2][2] = {{g1, g2}, {g2, dp}};
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        naa[i][j] = aa[i][j] - (x[i][0] * ak[j][0] + x[i][1] * ak[j][1]);        // aa - ak P^-1 ak^T
+        nan_[i][j] = -(x[i][0] * ekn[0][j] + x[i][1] * ekn[1][j]);               // -ak P^-1 E_kn
+        nnn[i][j] = enn[i][j] - (y[i][0] * ekn[0][j] + y[i][1] * ekn[1][j]);     // E_nn - E_kn^T P^-1 E_kn
+      }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { aa[i][j] = naa[i][j]; ak[i][j] = nan_[i][j]; kk[i][j] = nnn[i][j]; }
+  }
+  SupCoef o;
+  o.tx = tx; o.ty = ty; o.tz = tz;
+  o.kax = 1.0 / flex_ax;
+  o.ktor = 1.0 / flex_tor;
+  o.m[sym4(0, 0)] = aa[0][0]; o.m[sym4(0, 1)] = 0.5 * (aa[0][1] + aa[1][0]); o.m[sym4(1, 1)] = aa[1][1];
+  o.m[sym4(0, 2)] = ak[0][0]; o.m[sym4(0, 3)] = ak[0][1]; o.m[sym4(1, 2)] = ak[1][0]; o.m[sym4(1, 3)] = ak[1][1];
+  o.m[sym4(2, 2)] = kk[0][0]; o.m[sym4(2, 3)] = 0.5 * (kk[0][1] + kk[1][0]); o.m[sym4(3, 3)] = kk[1][1];
+  o.pad = 0.0;
+  sup[w] = o;
+}
+
+// entry (i, j) of the 6x6 block (row end re, column end ce) of a super-element
+__device__ __forceinline__ double sup_block_entry(const SupCoef& s, int re, int ce, int i, int j) {
+  const bool rw = i < 3, cw = j < 3;
+  const int a = rw ? i : i - 3, b = cw ? j : j - 3;
+  const double ta = (a == 0) ? s.tx : (a == 1 ? s.ty : s.tz);
+  const double tb = (b == 0) ? s.tx : (b == 1 ? s.ty : s.tz);
+  const double d = (a == b) ? 1.0 : 0.0;
+  const double mv = s.m[sym4(2 * re + (rw ? 0 : 1), 2 * ce + (cw ? 0 : 1))];
+  const double sA = (re == ce) ? 1.0 : -1.0;
+  if (rw && cw) return mv * (d - ta * tb) + sA * s.kax * ta * tb;
+  if (!rw && !cw) return mv * (d - ta * tb) + sA * s.ktor * ta * tb;
+  double sk = 0.0;
+  if (a != b) {
+    const int k = 3 - a - b;
+    const double tk = (k == 0) ? s.tx : (k == 1 ? s.ty : s.tz);
+    sk = ((b - a + 3) % 3 == 1) ? -tk : tk;  // [t]x entry (a, b)
+  }
+  return rw ? mv * sk : -mv * sk;
+}
+
 // One CTA per cell (grid-stride over cells).  A = dense cell stiffness in factorisation order
 // (interior DOFs first), lower triangle used.  Partial right-looking Cholesky over the nI interior
 // pivots; the rows of column k that are exactly zero are skipped (the cell graph is a set of strut
 // chains joined at a few nodes, so most of the column is structurally zero), which keeps the cost
 // proportional to the fill, not to n^3.  The trailing nB x nB block is then the Schur complement.
-template <bool SMEM>
+// SUPER = true: the "elements" are the condensed struts of k_chain_condense (sup[n_cells][ne]) on the joint-only
+// cell; xyz / rad are not read and there are no sensitivities in this mode.
+template <bool SMEM, bool SUPER = false>
 __global__ void __launch_bounds__(SCHUR_BLOCK) k_schur_dense(
     const double* __restrict__ xyz, const int32_t* __restrict__ len0, const int32_t* __restrict__ len1,
     const double* __restrict__ rad, int64_t n_cells, int nn, int nbn, int ne, double young, double nu, double kappa,
     double* __restrict__ S, double* __restrict__ ws, const int32_t* __restrict__ elem_group,
-    const double* __restrict__ drad_chain, int n_grad, double* __restrict__ dS) {
+    const double* __restrict__ drad_chain, int n_grad, double* __restrict__ dS,
+    const SupCoef* __restrict__ sup = nullptr) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int n = 6 * nn, nB = 6 * nbn, nI = n - nB;
   const int ld = n | 1;  // odd leading dimension: column walks are bank-conflict free
@@ -57,7 +179,9 @@ __global__ void __launch_bounds__(SCHUR_BLOCK) k_schur_dense(
   size_t off = 0;
   double* A = SMEM ? reinterpret_cast<double*>(sm_raw) : (ws + (size_t)blockIdx.x * n * ld);
   if (SMEM) off += (size_t)n * ld * sizeof(double);
-  ElemCoef* s_coef = reinterpret_cast<ElemCoef*>(sm_raw + off); off += (size_t)ne * sizeof(ElemCoef);
+  ElemCoef* s_coef = reinterpret_cast<ElemCoef*>(sm_raw + off);
+  SupCoef* s_sup = reinterpret_cast<SupCoef*>(sm_raw + off);
+  off += (size_t)ne * (SUPER ? sizeof(SupCoef) : sizeof(ElemCoef));
   double* s_diag = reinterpret_cast<double*>(sm_raw + off); off += (size_t)n * sizeof(double);
   double* s_v = reinterpret_cast<double*>(sm_raw + off); off += (size_t)6 * SCHUR_MAX_NB * sizeof(double);
   double* s_B = reinterpret_cast<double*>(sm_raw + off); off += 80 * sizeof(double);  // 72 strain entries + L + weights
@@ -76,9 +200,13 @@ __global__ void __launch_bounds__(SCHUR_BLOCK) k_schur_dense(
     __syncthreads();
     if (tid == 0) { s_cnt = 0; s_bad = 0; }
     for (int e = tid; e < ne; e += SCHUR_BLOCK) {
-      const int a = s_e0[e], b = s_e1[e];
-      s_coef[e] = elem_coef(cx[a * 3], cx[a * 3 + 1], cx[a * 3 + 2], cx[b * 3], cx[b * 3 + 1], cx[b * 3 + 2], cr[e],
-                            young, nu, kappa, false);
+      if (SUPER) {
+        s_sup[e] = sup[c * (int64_t)ne + e];
+      } else {
+        const int a = s_e0[e], b = s_e1[e];
+        s_coef[e] = elem_coef(cx[a * 3], cx[a * 3 + 1], cx[a * 3 + 2], cx[b * 3], cx[b * 3 + 1], cx[b * 3 + 2], cr[e],
+                              young, nu, kappa, false);
+      }
     }
     for (int i = tid; i < n * ld; i += SCHUR_BLOCK) A[i] = 0.0;
     __syncthreads();
@@ -90,11 +218,13 @@ __global__ void __launch_bounds__(SCHUR_BLOCK) k_schur_dense(
       for (int e = 0; e < ne; ++e) {
         const int e0 = s_e0[e], e1 = s_e1[e];
         if (e0 == a) {
-          diag += elem_block_entry(s_coef[e], 0, 0, i, j);
-          A[ra * ld + node_pos(e1, nn, nbn) * 6 + j] += elem_block_entry(s_coef[e], 0, 1, i, j);
+          diag += SUPER ? sup_block_entry(s_sup[e], 0, 0, i, j) : elem_block_entry(s_coef[e], 0, 0, i, j);
+          A[ra * ld + node_pos(e1, nn, nbn) * 6 + j] +=
+              SUPER ? sup_block_entry(s_sup[e], 0, 1, i, j) : elem_block_entry(s_coef[e], 0, 1, i, j);
         } else if (e1 == a) {
-          diag += elem_block_entry(s_coef[e], 1, 1, i, j);
-          A[ra * ld + node_pos(e0, nn, nbn) * 6 + j] += elem_block_entry(s_coef[e], 1, 0, i, j);
+          diag += SUPER ? sup_block_entry(s_sup[e], 1, 1, i, j) : elem_block_entry(s_coef[e], 1, 1, i, j);
+          A[ra * ld + node_pos(e0, nn, nbn) * 6 + j] +=
+              SUPER ? sup_block_entry(s_sup[e], 1, 0, i, j) : elem_block_entry(s_coef[e], 1, 0, i, j);
         }
       }
       A[ra * ld + node_pos(a, nn, nbn) * 6 + j] += diag;
@@ -134,7 +264,7 @@ __global__ void __launch_bounds__(SCHUR_BLOCK) k_schur_dense(
       const int hi = bi > bj ? bi : bj, lo = bi > bj ? bj : bi;
       Sc[q] = bad ? qnan : A[(nI + hi) * ld + nI + lo];
     }
-    if (dS == nullptr || n_grad <= 0) continue;
+    if (SUPER || dS == nullptr || n_grad <= 0) continue;
     // ---- sensitivities: dS_g = E^T dK_g E with E = [-X; I], X = K_II^-1 K_IB.
     // rows nI.. of A hold Y^T = K_BI L^-T; back-substitute in place to X^T = Y^T L^-1.
     __syncthreads();
@@ -235,6 +365,51 @@ extern "C" int lat_schur_batch(lat_ctx* ctx, const double* xyz, const int32_t* l
     LAT_CUDA(ctx, cudaFuncSetAttribute(k_schur_dense<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LAT_LAUNCH(ctx, k_schur_dense<false>, (unsigned)grid, SCHUR_BLOCK, smem, xyz, len0, len1, rad, n_cells, n_loc_nodes,
                n_bnd_nodes, n_loc_elem, young, nu, kappa, S, ws, elem_group, drad_chain, n_grad, dS);
+  }
+  return LAT_OK;
+}
+
+// Same result through the strut pre-pass: chains of collinear elements between joints are condensed first
+// (k_chain_condense), then the dense kernel runs on the joint-only cell.  chain_a / chain_b: the two joints of
+// each chain in the REDUCED numbering (boundary joints first, in the order of S's rows).
+extern "C" int lat_schur_batch_chains(lat_ctx* ctx, const double* xyz, const int32_t* len0, const int32_t* len1,
+                                      const double* rad, int64_t n_cells, int32_t n_loc_nodes, int32_t n_loc_elem,
+                                      const int32_t* chain_ptr, const int32_t* chain_elem, const int32_t* chain_flip,
+                                      const int32_t* chain_a, const int32_t* chain_b, int32_t n_chains,
+                                      int32_t n_joints, int32_t n_bnd_nodes, double young, double nu, double kappa,
+                                      double* S) {
+  if (!ctx) return LAT_ERR_ARG;
+  LAT_CHECK_ARG(ctx, xyz && len0 && len1 && rad && S && chain_ptr && chain_elem && chain_flip && chain_a && chain_b);
+  LAT_CHECK_ARG(ctx, n_cells >= 0 && n_loc_nodes > 0 && n_loc_elem > 0 && n_chains > 0);
+  LAT_CHECK_ARG(ctx, n_bnd_nodes > 0 && n_bnd_nodes <= n_joints && n_joints <= n_loc_nodes && 6 * n_bnd_nodes <= SCHUR_MAX_NB);
+  if (n_cells == 0) return LAT_OK;
+  LAT_CUDA(ctx, cudaSetDevice(ctx->device));
+  SupCoef* sup = lat_buf<SupCoef>(ctx, "schur_sup", (size_t)n_cells * n_chains);
+  if (!sup) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+  LAT_LAUNCH(ctx, k_chain_condense, (unsigned)ceil_div(n_cells * n_chains, 128), 128, 0, xyz, len0, len1, rad, n_cells,
+             n_loc_nodes, n_loc_elem, chain_ptr, chain_elem, chain_flip, n_chains, young, nu, kappa, sup);
+  const int n = 6 * n_joints, ld = n | 1;
+  const size_t aux = (size_t)n_chains * sizeof(SupCoef) + (size_t)n * 8 + 6 * SCHUR_MAX_NB * 8 + 80 * 8 + (size_t)n * 4 +
+                     2 * (size_t)n_chains * 4 + 64;
+  const size_t a_bytes = (size_t)n * ld * sizeof(double);
+  const bool in_smem = a_bytes + aux <= 220 * 1024;
+  const size_t smem = in_smem ? a_bytes + aux : aux;
+  if (smem > 220 * 1024) return lat_fail(ctx, LAT_ERR_UNSUPPORTED, "cell mesh too large for lat_schur_batch_chains", __FILE__, __LINE__);
+  int per_sm = in_smem ? (int)((220 * 1024) / (smem + 1024)) : 2;
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 8) per_sm = 8;
+  int64_t grid = (int64_t)ctx->sm_count * per_sm;
+  if (grid > n_cells) grid = n_cells;
+  if (in_smem) {
+    LAT_CUDA(ctx, cudaFuncSetAttribute(k_schur_dense<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LAT_LAUNCH(ctx, (k_schur_dense<true, true>), (unsigned)grid, SCHUR_BLOCK, smem, nullptr, chain_a, chain_b, nullptr, n_cells,
+               n_joints, n_bnd_nodes, n_chains, young, nu, kappa, S, nullptr, nullptr, nullptr, 0, nullptr, sup);
+  } else {
+    double* ws = lat_buf<double>(ctx, "schur_ws", (size_t)grid * n * ld);
+    if (!ws) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+    LAT_CUDA(ctx, cudaFuncSetAttribute(k_schur_dense<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LAT_LAUNCH(ctx, (k_schur_dense<false, true>), (unsigned)grid, SCHUR_BLOCK, smem, nullptr, chain_a, chain_b, nullptr, n_cells,
+               n_joints, n_bnd_nodes, n_chains, young, nu, kappa, S, ws, nullptr, nullptr, 0, nullptr, sup);
   }
   return LAT_OK;
 }

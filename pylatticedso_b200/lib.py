@@ -26,7 +26,7 @@ EXPORTS = [
     "lat_elem_stiffness", "lat_bsr_pattern_build", "lat_bsr_pattern_export", "lat_csr_structure",
     "lat_bsr_to_csr_values", "lat_assemble_bsr", "lat_apply_dirichlet", "lat_set_dirichlet_values", "lat_bsr_spmv", "lat_pcg_bsr",
     "lat_matfree_setup", "lat_matfree_apply", "lat_matfree_rhs", "lat_pcg_matfree", "lat_pcg_matfree_dist",
-    "lat_compliance_grad", "lat_schur_batch", "lat_ddm_matvec",
+    "lat_compliance_grad", "lat_schur_batch", "lat_schur_batch_chains", "lat_ddm_matvec",
     "lat_nccl_unique_id", "lat_comm_create", "lat_comm_destroy", "lat_allreduce_sum", "lat_halo_exchange",
     "lat_pcg_bsr_dist", "lat_p2p_arena_create", "lat_p2p_attach", "lat_p2p_destroy", "lat_assemble_cells_bsr",
 ]
@@ -117,6 +117,7 @@ def load():
     lib.lat_pcg_matfree_dist.argtypes = [vp, C.POINTER(Halo), vp, vp, C.POINTER(PcgOpts), C.POINTER(PcgResult)]
     lib.lat_compliance_grad.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, vp, vp, i64, vp, vp]
     lib.lat_schur_batch.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, i32, dbl, dbl, dbl, vp, vp, vp, i32, vp]
+    lib.lat_schur_batch_chains.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, dbl, dbl, dbl, vp]
     lib.lat_ddm_matvec.argtypes = [vp, vp, i64, vp, vp, i64, i32, i64, vp, vp]
     lib.lat_assemble_cells_bsr.argtypes = [vp, vp, i64, vp, i64, i32, vp, vp, i64, vp]
     lib.lat_nccl_unique_id.argtypes = [vp]
@@ -313,6 +314,20 @@ class Context:
                                             n_bnd_nodes, ne, young, nu, kappa, _ptr(S), _ptr(elem_group), _ptr(chain),
                                             n_grad, _ptr(dS)))
         return (S, dS) if n_grad > 0 else S
+
+    def schur_batch_chains(self, xyz, len0, len1, rad, chains, n_bnd_nodes, young, nu, kappa=0.9):
+        """Schur complements through the strut pre-pass.  ``chains``: dict of device int32 tensors
+        (ptr, elem, flip, a, b) + n_joints, see ``schur.strut_chains``."""
+        import torch
+        n_cells, nn = int(xyz.shape[0]), int(xyz.shape[1])
+        nB = 6 * n_bnd_nodes
+        S = torch.empty((n_cells, nB, nB), dtype=torch.float64, device=self.device)
+        self.check(self.lib.lat_schur_batch_chains(self.h, _ptr(xyz), _ptr(len0), _ptr(len1), _ptr(rad), n_cells, nn,
+                                                   int(len0.numel()), _ptr(chains["ptr"]), _ptr(chains["elem"]),
+                                                   _ptr(chains["flip"]), _ptr(chains["a"]), _ptr(chains["b"]),
+                                                   int(chains["a"].numel()), int(chains["n_joints"]), n_bnd_nodes,
+                                                   young, nu, kappa, _ptr(S)))
+        return S
 
     def ddm_matvec(self, S, gidx, x, n_free=None, u_fixed=None, out=None):
         """y = sum_c B_c S_c B_c^T x.  S: [n_cells, nb, nb] or [nb, nb] (shared by all cells)."""

@@ -33,6 +33,62 @@ def local_cell_mesh(mesh: BeamMesh, boundary_nodes):
     return perm, xyz, perm[mesh.en0].astype(np.int32), perm[mesh.en1].astype(np.int32)
 
 
+def strut_chains(xyz, len0, len1, n_bnd_nodes, tol=1e-9):
+    """Straight element chains of a local cell mesh (boundary nodes = the first ``n_bnd_nodes`` local nodes).
+
+    A chain node is an interior node with exactly two incident elements that are collinear; every maximal run of
+    chain nodes between two joints is one chain.  Returns host arrays for ``lat_schur_batch_chains``:
+    ptr / elem / flip (elements of each chain in walking order), a / b (end joints in the REDUCED numbering: the
+    boundary nodes keep their index, interior joints follow in ascending local order) and n_joints -- or ``None``
+    when nothing can be condensed (every strut is a single element)."""
+    xyz = np.asarray(xyz, dtype=np.float64)
+    len0, len1 = np.asarray(len0, dtype=np.int64), np.asarray(len1, dtype=np.int64)
+    nn, ne = xyz.shape[0], len0.shape[0]
+    deg = np.bincount(np.concatenate([len0, len1]), minlength=nn)
+    d = xyz[len1] - xyz[len0]
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    incident = [[] for _ in range(nn)]
+    for e in range(ne):
+        incident[len0[e]].append(e)
+        incident[len1[e]].append(e)
+    is_chain = np.zeros(nn, dtype=bool)
+    for n in range(n_bnd_nodes, nn):
+        if deg[n] == 2:
+            e0, e1 = incident[n]
+            is_chain[n] = np.linalg.norm(np.cross(d[e0], d[e1])) < tol
+    if not is_chain.any():
+        return None
+    joints = np.flatnonzero(~is_chain)
+    red = np.full(nn, -1, dtype=np.int64)
+    red[joints] = np.arange(joints.size)          # boundary nodes are the first local nodes -> they stay first
+    used = np.zeros(ne, dtype=bool)
+    ptr, elem, flip, ca, cb = [0], [], [], [], []
+    for e0 in range(ne):
+        if used[e0] or (is_chain[len0[e0]] and is_chain[len1[e0]]):
+            continue
+        start, nxt, fl = (len0[e0], len1[e0], 0) if not is_chain[len0[e0]] else (len1[e0], len0[e0], 1)
+        used[e0] = True
+        elem.append(e0); flip.append(fl)
+        while is_chain[nxt]:
+            e = [q for q in incident[nxt] if not used[q]][0]
+            used[e] = True
+            fl = 0 if len0[e] == nxt else 1
+            elem.append(e); flip.append(fl)
+            nxt = len1[e] if fl == 0 else len0[e]
+        ptr.append(len(elem)); ca.append(red[start]); cb.append(red[nxt])
+    if not used.all():
+        return None                                # a closed ring of chain nodes: leave it to the dense path
+    i32 = lambda v: np.asarray(v, dtype=np.int32)
+    return dict(ptr=i32(ptr), elem=i32(elem), flip=i32(flip), a=i32(ca), b=i32(cb), n_joints=int(joints.size))
+
+
+def _chains_to_device(chains, dev):
+    import torch
+    out = {k: torch.from_numpy(v).to(dev) for k, v in chains.items() if k != "n_joints"}
+    out["n_joints"] = chains["n_joints"]
+    return out
+
+
 def get_schur_complement(lattice, cell_index=None, elements_per_strut="gmsh", ctx=None):
     """Drop-in for ``get_schur_complement(lattice, cell_index) -> ndarray[nB, nB]`` (C order;
     boundary DOF order = 6 DOFs of each node of ``cell.node_in_order_simulation``)."""
@@ -49,8 +105,13 @@ def get_schur_complement(lattice, cell_index=None, elements_per_strut="gmsh", ct
     ctx = ctx or L.Context()
     perm, xyz, l0, l1 = local_cell_mesh(mesh, bnd)
     dev = ctx.device
-    S = ctx.schur_batch(torch.from_numpy(xyz[None]).to(dev), torch.from_numpy(l0).to(dev), torch.from_numpy(l1).to(dev),
-                        torch.from_numpy(mesh.rad[None].copy()).to(dev), len(bnd), E, nu, KAPPA)
+    chains = strut_chains(xyz, l0, l1, len(bnd))
+    args = (torch.from_numpy(xyz[None]).to(dev), torch.from_numpy(l0).to(dev), torch.from_numpy(l1).to(dev),
+            torch.from_numpy(mesh.rad[None].copy()).to(dev))
+    if chains is not None:      # strut pre-pass: condense the ~18 elements of every strut first
+        S = ctx.schur_batch_chains(*args, _chains_to_device(chains, dev), len(bnd), E, nu, KAPPA)
+    else:
+        S = ctx.schur_batch(*args, len(bnd), E, nu, KAPPA)
     out = S[0].cpu().numpy()
     if not np.isfinite(out).all():
         raise RuntimeError("Schur complement: interior stiffness block is not positive definite")
@@ -72,8 +133,14 @@ class CellBatch:
         self.elem_group = None if elem_group is None else t(elem_group, np.int32)
         self.chain = None if chain is None else t(chain, np.float64)
         self.n_grad = int(n_grad)
+        # strut pre-pass (values only): topology is shared, so the chains are found once on cell 0
+        ch = strut_chains(np.asarray(xyz)[0], len0, len1, self.n_bnd_nodes)
+        self.chains = None if ch is None else _chains_to_device(ch, dev)
 
-    def schur(self, with_gradients=False):
+    def schur(self, with_gradients=False, use_chains=True):
+        if not with_gradients and use_chains and self.chains is not None:
+            return self.ctx.schur_batch_chains(self.xyz, self.len0, self.len1, self.rad, self.chains, self.n_bnd_nodes,
+                                               self.young, self.nu, self.kappa)
         if with_gradients:
             return self.ctx.schur_batch(self.xyz, self.len0, self.len1, self.rad, self.n_bnd_nodes, self.young, self.nu,
                                         self.kappa, self.elem_group, self.chain, self.n_grad)
