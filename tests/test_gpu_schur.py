@@ -28,6 +28,16 @@ def test_schur_batch_reproduces_reference_goldens(ctx, geom, tol):
         err = np.abs(S - SM[i]).max() / np.abs(SM[i]).max()
         assert err < tol, (geom, i, err)
         assert np.array_equal(S, S.T)
+        # the same golden through the strut pre-pass (lat_schur_batch_chains): chains condensed first, joints after
+        from pylatticedso_b200.schur import _chains_to_device, strut_chains
+        ch = strut_chains(xyz, l0, l1, len(bnd_nodes))
+        assert ch is not None
+        S2 = ctx.schur_batch_chains(t(ctx, xyz[None], np.float64), t(ctx, l0, np.int32), t(ctx, l1, np.int32),
+                                    t(ctx, m.rad[None], np.float64), _chains_to_device(ch, ctx.device), len(bnd_nodes),
+                                    E_MOD, NU)[0].cpu().numpy()
+        err2 = np.abs(S2 - SM[i]).max() / np.abs(SM[i]).max()
+        assert err2 < tol, (geom, i, "chains", err2)
+        assert np.array_equal(S2, S2.T)
 
 
 def test_schur_batch_many_cells_and_gradients(ctx):

@@ -80,3 +80,43 @@ def test_flatten_object_graph_matches_generator_and_oracle():
     fixed, g, f = M.bc_arrays_from_lattice(lat, a)
     fs, gs, fs_ = M.compression_bc(M.mesh_from_synthetic(syn, 1))
     assert np.array_equal(fixed, fs) and np.array_equal(g, gs) and np.array_equal(f, fs_)
+
+
+@pytest.mark.parametrize("geom", ["BCC", "Hybrid1", "Hybrid4"])
+def test_strut_chains_of_the_golden_cells(geom):
+    """Host side of the Schur strut pre-pass: every element lies in exactly one chain, chains run joint to joint,
+    boundary nodes keep their index in the reduced numbering, and the chain set equals the oracle's."""
+    from conftest import load_golden, mesh_from_npz
+    from oracle import lattice_oracle as orc
+    from pylatticedso_b200.schur import local_cell_mesh, strut_chains
+    G = load_golden(f"schur_{geom}.npz")
+    m = mesh_from_npz(G, "c0_")
+    bnd = G["c0_bnd"].reshape(-1, 6)[:, 0] // 6
+    perm, xyz, l0, l1 = local_cell_mesh(m, bnd)
+    ch = strut_chains(xyz, l0, l1, len(bnd))
+    assert ch is not None and ch["ptr"][0] == 0 and ch["ptr"][-1] == len(l0)
+    assert sorted(ch["elem"].tolist()) == list(range(len(l0)))
+    assert ch["a"].max() < ch["n_joints"] and ch["b"].max() < ch["n_joints"] and ch["n_joints"] >= len(bnd)
+    oc = orc.find_chains(xyz.shape[0], np.stack([l0, l1], 1), np.arange(len(bnd)), xyz)
+    assert len(oc) == len(ch["a"])
+    assert sorted(tuple(sorted(e for e, _ in c[2])) for c in oc) == sorted(
+        tuple(sorted(ch["elem"][ch["ptr"][k]:ch["ptr"][k + 1]].tolist())) for k in range(len(ch["a"])))
+    # walking order: consecutive elements share a node, flips orient them from a to b
+    for k in range(len(ch["a"])):
+        prev = None
+        for q in range(ch["ptr"][k], ch["ptr"][k + 1]):
+            e, fl = ch["elem"][q], ch["flip"][q]
+            a, b = (l1[e], l0[e]) if fl else (l0[e], l1[e])
+            assert prev is None or prev == a
+            prev = b
+
+
+def test_strut_chains_none_for_single_element_struts():
+    from pylatticedso_b200 import mesh as M
+    from pylatticedso_b200.schur import bcc_cell_order_nodes, local_cell_mesh, strut_chains
+    lat = M.synthetic_lattice("BCC", (1, 1, 1), [0.05])
+    mesh = M.mesh_from_synthetic(lat, 1)
+    bnd = bcc_cell_order_nodes(lat.pxyz, (0, 1, 0, 1, 0, 1))
+    perm, xyz, l0, l1 = local_cell_mesh(mesh, bnd)
+    assert strut_chains(xyz, l0, l1, len(bnd)) is None
+

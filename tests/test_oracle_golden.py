@@ -103,3 +103,37 @@ def test_matrix_free_closed_form_equals_element_stiffness():
     assert (np.abs(f0 - f[:, :6]) <= 1e-12 * scale).all()
     assert (np.abs(f1 - f[:, 6:]) <= 1e-12 * scale).all()
 
+
+@pytest.mark.parametrize("geom,tol", [("BCC", 1e-12), ("Hybrid1", 5e-12), ("Hybrid4", 1e-12)])
+def test_chain_condensation_reproduces_reference_schur_goldens(geom, tol):
+    """The strut pre-pass restated on the CPU (spring series + planar-beam chain condensation, joint-only cell)
+    against the reference's 30 stored Schur matrices -- the checker of k_chain_condense."""
+    G = load_golden(f"schur_{geom}.npz")
+    SM = G["schur_matrices"]
+    for i in range(SM.shape[0]):
+        m = mesh_from_npz(G, f"c{i}_")
+        bnd_nodes = G[f"c{i}_bnd"].reshape(-1, 6)[:, 0] // 6
+        S, chains = orc.schur_via_chain_condensation(m.xyz, np.stack([m.en0, m.en1], 1), m.rad, bnd_nodes, E_MOD, NU)
+        assert max(len(c[2]) for c in chains) > 1            # the goldens do have multi-element struts
+        err = np.abs(S - SM[i]).max() / np.abs(SM[i]).max()
+        assert err < tol, (geom, i, err)
+
+
+def test_condensed_strut_equals_dense_condensation():
+    """Non-uniform element lengths and radii, flipped elements: condensed 12x12 == dense Schur of the chain."""
+    rng = np.random.default_rng(5)
+    m = 9
+    A = np.array([0.1, 0.2, 0.3]); B = A + np.array([0.5, -0.4, 0.7])
+    fr = np.sort(rng.random(m - 1))
+    pts = np.vstack([A] + [A + f * (B - A) for f in fr] + [B])
+    en = np.array([[k, k + 1] for k in range(m)])
+    en[2] = en[2][::-1]; en[6] = en[6][::-1]
+    rad = rng.uniform(0.02, 0.08, m)
+    chain = (0, m, [(k, bool(en[k][0] != k)) for k in range(m)])
+    Ks, _ = orc.condensed_strut(pts, en, rad, chain, E_MOD, NU)
+    K = orc.assemble_csr(pts, en, rad, E_MOD, NU).toarray()
+    bd = np.r_[0:6, 6 * m:6 * m + 6]
+    it = np.setdiff1d(np.arange(6 * (m + 1)), bd)
+    Sd = K[np.ix_(bd, bd)] - K[np.ix_(bd, it)] @ np.linalg.solve(K[np.ix_(it, it)], K[np.ix_(it, bd)])
+    assert np.abs(Ks - Sd).max() <= 1e-12 * np.abs(Sd).max()
+
