@@ -285,6 +285,18 @@ int lat_schur_batch_chains(lat_ctx* ctx, const double* xyz, const int32_t* len0,
                            const int32_t* chain_a, const int32_t* chain_b, int32_t n_chains, int32_t n_joints,
                            int32_t n_bnd_nodes, double young, double nu, double kappa, double* S);
 
+/* ---- joint-only global assembly (B200 design choice; exact static condensation of the struts) --------------
+ * The reference applies loads and constraints to lattice points only (full_scale_lattice_simulation.py:77-153), so
+ * eliminating the strut-interior nodes changes neither the joint displacements nor the joint reactions.  Every chain
+ * of elements between two joints becomes one 12x12 super-element (k_chain_condense, as in lat_schur_batch_chains) and
+ * the BSR matrix is assembled over the JOINT mesh: call lat_bsr_pattern_build(chain_a, chain_b, n_chains, n_joints)
+ * first, then this; lat_apply_dirichlet / lat_pcg_bsr / lat_bsr_spmv work on the result unchanged.
+ *   xyz: [n_nodes_full][3] row-major; len0/len1/rad: the subdivided mesh; chain_*: as lat_schur_batch_chains. */
+int lat_assemble_bsr_struts(lat_ctx* ctx, const double* xyz, const int32_t* len0, const int32_t* len1,
+                            const double* rad, int64_t n_nodes_full, int64_t n_elem, const int32_t* chain_ptr,
+                            const int32_t* chain_elem, const int32_t* chain_flip, int64_t n_chains, int64_t n_joints,
+                            double young, double nu, double kappa, double* vals);
+
 /* ---- A8: DDM interface operator ------------------------------------------------
  * y = sum_c B_c S_c B_c^T x  (LatticeSim.calculate_reaction_force_global ->
  * update_reaction_force_each_cell -> solve_sub_problem, lattice_sim.py:1180-1252,

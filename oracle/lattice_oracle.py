@@ -524,3 +524,27 @@ def schur_via_chain_condensation(xyz, en, rad, bnd_nodes, E, nu, kappa=KAPPA):
         return Kj[np.ix_(bd, bd)], chains
     return Kj[np.ix_(bd, bd)] - Kj[np.ix_(bd, it)] @ np.linalg.solve(Kj[np.ix_(it, it)], Kj[np.ix_(it, bd)]), chains
 
+
+def assemble_joint_only(xyz, en, rad, n_points, E, nu, kappa=KAPPA):
+    """Joint-only stiffness of a subdivided lattice mesh (mesh.py numbering: the first ``n_points`` nodes are the
+    lattice points, elements beam-major from point1 to point2): every strut replaced by its condensed 12x12
+    super-element.  With no load and no constraint on strut-interior nodes, solving this system gives exactly the
+    joint displacements and joint reactions of the full system (static condensation).  Checker for
+    lat_assemble_bsr_struts.  Returns (K_joints csr, chains)."""
+    xyz = np.asarray(xyz, dtype=np.float64)
+    en = np.asarray(en)
+    starts = np.flatnonzero(en[:, 0] < n_points)
+    ends = np.r_[starts[1:], len(en)]
+    rows, cols, vals = [], [], []
+    chains = []
+    for s0, s1 in zip(starts, ends):
+        ch = (int(en[s0, 0]), int(en[s1 - 1, 1]), [(e, False) for e in range(s0, s1)])
+        assert ch[1] < n_points
+        chains.append(ch)
+        Ks, (A, B) = condensed_strut(xyz, en, rad, ch, E, nu, kappa)
+        idx = np.r_[6 * A + np.arange(6), 6 * B + np.arange(6)]
+        rows.append(np.repeat(idx, 12)); cols.append(np.tile(idx, 12)); vals.append(Ks.ravel())
+    K = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
+                      shape=(6 * n_points, 6 * n_points)).tocsr()
+    return K, chains
+

@@ -158,6 +158,114 @@ __device__ __forceinline__ double sup_block_entry(const SupCoef& s, int re, int 
   return rw ? mv * sk : -mv * sk;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Joint-only GLOBAL assembly: the same super-elements in the BSR matrix of the whole lattice
+// ---------------------------------------------------------------------------------------------------
+// With no load and no constraint on strut-interior nodes (the reference applies both to lattice points only),
+// static condensation of every strut is exact: the joint-only system K_J u_J = f_J has the joint displacements
+// and reactions of the full system with 5x (2 elements per strut) to ~70x (the reference's 18) fewer DOFs and a
+// far better condition number.  One thread per block row, as k_assemble_rows (256-bit stores, deterministic).
+__device__ __forceinline__ void sup_block_accum(const SupCoef& s, int re, int ce, double (&acc)[36]) {
+  double mWW, mWP, mPW, mPP;   // constant indices only (a runtime index into s.m[] would go through local memory)
+  if (re == 0 && ce == 0) { mWW = s.m[0]; mWP = s.m[1]; mPW = s.m[1]; mPP = s.m[4]; }
+  else if (re == 0 && ce == 1) { mWW = s.m[2]; mWP = s.m[3]; mPW = s.m[5]; mPP = s.m[6]; }
+  else if (re == 1 && ce == 0) { mWW = s.m[2]; mWP = s.m[5]; mPW = s.m[3]; mPP = s.m[6]; }
+  else { mWW = s.m[7]; mWP = s.m[8]; mPW = s.m[8]; mPP = s.m[9]; }
+  const double sA = (re == ce) ? 1.0 : -1.0;
+  const double t[3] = {s.tx, s.ty, s.tz};
+  const double ax = sA * s.kax, tor = sA * s.ktor;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const double tt = t[a] * t[b];
+      const double d = (a == b) ? 1.0 : 0.0;
+      double sk = 0.0;   // [t]x entry (a, b)
+      if (a == 0 && b == 1) sk = -t[2];
+      if (a == 0 && b == 2) sk = t[1];
+      if (a == 1 && b == 0) sk = t[2];
+      if (a == 1 && b == 2) sk = -t[0];
+      if (a == 2 && b == 0) sk = -t[1];
+      if (a == 2 && b == 1) sk = t[0];
+      acc[a * 6 + b] += mWW * (d - tt) + ax * tt;
+      acc[a * 6 + 3 + b] += mWP * sk;
+      acc[(a + 3) * 6 + b] += -mPW * sk;
+      acc[(a + 3) * 6 + 3 + b] += mPP * (d - tt) + tor * tt;
+    }
+  }
+}
+__device__ __forceinline__ void store_block_sup(double* __restrict__ dst, const double (&q)[36], bool accumulate) {
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    double a = q[4 * k], b = q[4 * k + 1], c = q[4 * k + 2], d = q[4 * k + 3];
+    if (accumulate) {
+      double oa, ob, oc, od;
+      asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(oa), "=d"(ob), "=d"(oc), "=d"(od) : "l"(dst + 4 * k) : "memory");
+      a += oa; b += ob; c += oc; d += od;
+    }
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * k), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+  }
+}
+__global__ void __launch_bounds__(128) k_assemble_rows_sup(
+    const SupCoef* __restrict__ sup, const int32_t* __restrict__ adjptr, const int32_t* __restrict__ adj_other,
+    const int32_t* __restrict__ adj_el, const int32_t* __restrict__ rowptr, int64_t n_nodes, double* __restrict__ vals) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_nodes) return;
+  const int lo = adjptr[n], hi = adjptr[n + 1];
+  if (hi == lo) return;
+  int w = rowptr[n];
+  int wdiag = -1;
+  double dacc[36];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) dacc[k] = 0.0;
+  int prev = -1;
+  for (int i = lo; i < hi; ++i) {
+    const int other = adj_other[i];
+    const int ee = adj_el[i];
+    const SupCoef s = sup[ee >> 1];
+    const int end = ee & 1;
+    sup_block_accum(s, end, end, dacc);
+    double q[36];
+#pragma unroll
+    for (int k = 0; k < 36; ++k) q[k] = 0.0;
+    sup_block_accum(s, end, end ^ 1, q);
+    const bool dup = (other == prev);
+    if (!dup) {
+      if (wdiag < 0 && other > (int)n) { wdiag = w; ++w; }
+      ++w;
+    }
+    store_block_sup(vals + (int64_t)(w - 1) * 36, q, dup);
+    prev = other;
+  }
+  if (wdiag < 0) wdiag = w;
+  store_block_sup(vals + (int64_t)wdiag * 36, dacc, false);
+}
+
+// xyz: [n_nodes_full][3] (AoS), len0/len1/rad: the FULL (subdivided) mesh; chains as in lat_schur_batch_chains with
+// one "cell".  The resident pattern must be the one of the JOINT mesh (chain_a, chain_b over n_joints nodes).
+extern "C" int lat_assemble_bsr_struts(lat_ctx* ctx, const double* xyz, const int32_t* len0, const int32_t* len1,
+                                       const double* rad, int64_t n_nodes_full, int64_t n_elem,
+                                       const int32_t* chain_ptr, const int32_t* chain_elem, const int32_t* chain_flip,
+                                       int64_t n_chains, int64_t n_joints, double young, double nu, double kappa,
+                                       double* vals) {
+  if (!ctx) return LAT_ERR_ARG;
+  LAT_CHECK_ARG(ctx, xyz && len0 && len1 && rad && chain_ptr && chain_elem && chain_flip && vals);
+  LAT_CHECK_ARG(ctx, n_nodes_full > 0 && n_elem > 0 && n_chains > 0 && n_joints > 0 && n_joints <= n_nodes_full);
+  LAT_CHECK_ARG(ctx, n_nodes_full < ((int64_t)1 << 30) && n_elem < ((int64_t)1 << 30));
+  LAT_CHECK_ARG(ctx, (reinterpret_cast<uintptr_t>(vals) & 31) == 0);
+  if (ctx->pat_nnzb < 0 || ctx->pat_nelem != n_chains || ctx->pat_nnodes != n_joints)
+    return lat_fail(ctx, LAT_ERR_STATE, "resident pattern is not the joint mesh (chain ends over n_joints nodes): call lat_bsr_pattern_build", __FILE__, __LINE__);
+  LAT_CUDA(ctx, cudaSetDevice(ctx->device));
+  SupCoef* sup = lat_buf<SupCoef>(ctx, "strut_sup", (size_t)n_chains);
+  if (!sup) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+  LAT_LAUNCH(ctx, k_chain_condense, (unsigned)ceil_div(n_chains, 128), 128, 0, xyz, len0, len1, rad, (int64_t)1,
+             (int)n_nodes_full, (int)n_elem, chain_ptr, chain_elem, chain_flip, (int)n_chains, young, nu, kappa, sup);
+  LAT_LAUNCH(ctx, k_assemble_rows_sup, (unsigned)ceil_div(n_joints, 128), 128, 0, sup,
+             (const int32_t*)ctx->bufs["pat_adjptr"].p, (const int32_t*)ctx->bufs["pat_adj_other"].p,
+             (const int32_t*)ctx->bufs["pat_adj_el"].p, (const int32_t*)ctx->bufs["pat_rowptr"].p, n_joints, vals);
+  return LAT_OK;
+}
+
 // One CTA per cell (grid-stride over cells).  A = dense cell stiffness in factorisation order
 // (interior DOFs first), lower triangle used.  Partial right-looking Cholesky over the nI interior
 // pivots; the rows of column k that are exactly zero are skipped (the cell graph is a set of strut

@@ -26,7 +26,7 @@ EXPORTS = [
     "lat_elem_stiffness", "lat_bsr_pattern_build", "lat_bsr_pattern_export", "lat_csr_structure",
     "lat_bsr_to_csr_values", "lat_assemble_bsr", "lat_apply_dirichlet", "lat_set_dirichlet_values", "lat_bsr_spmv", "lat_pcg_bsr",
     "lat_matfree_setup", "lat_matfree_apply", "lat_matfree_rhs", "lat_pcg_matfree", "lat_pcg_matfree_dist",
-    "lat_compliance_grad", "lat_schur_batch", "lat_schur_batch_chains", "lat_ddm_matvec",
+    "lat_compliance_grad", "lat_schur_batch", "lat_schur_batch_chains", "lat_assemble_bsr_struts", "lat_ddm_matvec",
     "lat_nccl_unique_id", "lat_comm_create", "lat_comm_destroy", "lat_allreduce_sum", "lat_halo_exchange",
     "lat_pcg_bsr_dist", "lat_p2p_arena_create", "lat_p2p_attach", "lat_p2p_destroy", "lat_assemble_cells_bsr",
 ]
@@ -117,6 +117,7 @@ def load():
     lib.lat_pcg_matfree_dist.argtypes = [vp, C.POINTER(Halo), vp, vp, C.POINTER(PcgOpts), C.POINTER(PcgResult)]
     lib.lat_compliance_grad.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, vp, vp, i64, vp, vp]
     lib.lat_schur_batch.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, i32, dbl, dbl, dbl, vp, vp, vp, i32, vp]
+    lib.lat_assemble_bsr_struts.argtypes = [vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, i64, i64, dbl, dbl, dbl, vp]
     lib.lat_schur_batch_chains.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, dbl, dbl, dbl, vp]
     lib.lat_ddm_matvec.argtypes = [vp, vp, i64, vp, vp, i64, i32, i64, vp, vp]
     lib.lat_assemble_cells_bsr.argtypes = [vp, vp, i64, vp, i64, i32, vp, vp, i64, vp]
@@ -314,6 +315,17 @@ class Context:
                                             n_bnd_nodes, ne, young, nu, kappa, _ptr(S), _ptr(elem_group), _ptr(chain),
                                             n_grad, _ptr(dS)))
         return (S, dS) if n_grad > 0 else S
+
+    def assemble_bsr_struts(self, xyz, len0, len1, rad, chain_ptr, chain_elem, chain_flip, n_joints, nnzb, young, nu,
+                            kappa=0.9, out=None):
+        """Joint-only BSR values (the pattern of the joint mesh must be resident: bsr_pattern(chain_a, chain_b, n_joints))."""
+        import torch
+        if out is None:
+            out = torch.empty(nnzb * 36, dtype=torch.float64, device=self.device)
+        self.check(self.lib.lat_assemble_bsr_struts(self.h, _ptr(xyz), _ptr(len0), _ptr(len1), _ptr(rad), int(xyz.shape[0]),
+                                                    int(len0.numel()), _ptr(chain_ptr), _ptr(chain_elem), _ptr(chain_flip),
+                                                    int(chain_ptr.numel()) - 1, n_joints, young, nu, kappa, _ptr(out)))
+        return out
 
     def schur_batch_chains(self, xyz, len0, len1, rad, chains, n_bnd_nodes, young, nu, kappa=0.9):
         """Schur complements through the strut pre-pass.  ``chains``: dict of device int32 tensors

@@ -9,13 +9,16 @@ from oracle import lattice_oracle as orc
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("matrix_free", [False, True])
+@pytest.mark.parametrize("matrix_free", [False, True, "condensed"])
 def test_solve_fem_dropin_writes_back_like_the_reference(ctx, matrix_free):
     from pylatticedso_b200 import mesh as M
     from pylatticedso_b200.fem import solve_FEM_B200
     lat = FakeLattice("BCC", (3, 2, 2), 0.05)
     lat.compression()
-    xsol, model = solve_FEM_B200(lat, elements_per_strut=2, tol=1e-12, ctx=ctx, matrix_free=matrix_free)
+    if matrix_free == "condensed":
+        xsol, model = solve_FEM_B200(lat, elements_per_strut=2, tol=1e-12, ctx=ctx, condense_struts=True)
+    else:
+        xsol, model = solve_FEM_B200(lat, elements_per_strut=2, tol=1e-12, ctx=ctx, matrix_free=matrix_free)
     assert model.info["info"] == 0
     mesh = M.mesh_from_synthetic(lat.syn, 2)
     fixed, g, f = M.compression_bc(mesh)

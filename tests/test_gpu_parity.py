@@ -302,3 +302,41 @@ def test_adjoint_gradient_of_a_displacement_objective(ctx):
         rp, rm = r0.copy(), r0.copy(); rp[c] += h; rm[c] -= h
         fd[c] = (J(rp) - J(rm)) / (2 * h)
     assert np.abs(g.cpu().numpy() - fd).max() < 1e-6 * np.abs(fd).max()
+
+
+@pytest.mark.parametrize("geom,cells,mseg", [("BCC", (3, 2, 2), 5), ("Octet", (2, 1, 2), 3), ("BCC", (2, 2, 2), 1)])
+def test_joint_only_solve_equals_full_solve_at_the_joints(ctx, geom, cells, mseg):
+    """lat_assemble_bsr_struts: exact static condensation of every strut; displacements and reactions of the lattice
+    points equal the oracle's FULL solve (all strut-interior nodes kept) to 1e-8."""
+    from pylatticedso_b200 import mesh as M
+    from pylatticedso_b200.fem import BeamFEM
+    lat = M.synthetic_lattice(geom, cells, [0.04], grad_radius=("linear", [True, False, True], [0.01, 0, 0.005]))
+    m = M.mesh_from_synthetic(lat, mseg)
+    fixed, g, f = M.compression_bc(m)
+    f = f.copy(); f[6 * 3 + 1] = 0.02
+    K = orc.assemble_csr(m.xyz, np.stack([m.en0, m.en1], 1), m.rad, E_MOD, NU)
+    uo, Ro = orc.solve_static(K, fixed.astype(bool), g, f)
+    fem = BeamFEM(m, E_MOD, NU, ctx=ctx)
+    u, R, info = fem.solve_condensed(fixed, g, f, tol=1e-12, maxiter=50000)
+    nj = 6 * m.n_points
+    assert info["info"] == 0 and info["n_dof_condensed"] == nj and u.numel() == nj
+    assert np.abs(u.cpu().numpy() - uo[:nj]).max() <= 1e-8 * np.abs(uo).max()
+    assert np.abs(R.cpu().numpy() - Ro[:nj]).max() <= 1e-8 * np.abs(Ro).max()
+    # assembled joint-only matrix == the oracle's (super-elements through the dense chain condensation)
+    Kj, _ = orc.assemble_joint_only(m.xyz, np.stack([m.en0, m.en1], 1), m.rad, m.n_points, E_MOD, NU)
+    y = np.random.default_rng(0).standard_normal(nj)
+    import torch
+    ptr, sa, sb = fem.strut_topology()
+    rowptr, colidx = ctx.bsr_pattern(torch.from_numpy(sa).to(ctx.device), torch.from_numpy(sb).to(ctx.device), m.n_points)
+    xyz = torch.stack([fem.x, fem.y, fem.z], dim=1).contiguous()
+    ti = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(ctx.device)
+    vals = ctx.assemble_bsr_struts(xyz, fem.en0, fem.en1, fem.rad, ti(ptr), ti(np.arange(m.n_elems)), ti(np.zeros(m.n_elems)),
+                                   m.n_points, int(colidx.numel()), E_MOD, NU)
+    Ky = ctx.spmv(rowptr, colidx, vals, torch.from_numpy(y).to(ctx.device)).cpu().numpy()
+    assert np.abs(Ky - Kj @ y).max() <= 1e-11 * np.abs(Kj @ y).max()
+    # loads on strut-interior nodes are refused
+    if m.n_nodes > m.n_points:
+        f2 = f.copy(); f2[-1] = 1.0
+        with pytest.raises(ValueError):
+            fem.solve_condensed(fixed, g, f2)
+
