@@ -137,3 +137,24 @@ def test_condensed_strut_equals_dense_condensation():
     Sd = K[np.ix_(bd, bd)] - K[np.ix_(bd, it)] @ np.linalg.solve(K[np.ix_(it, it)], K[np.ix_(it, bd)])
     assert np.abs(Ks - Sd).max() <= 1e-12 * np.abs(Sd).max()
 
+
+@pytest.mark.parametrize("geom,cells,mseg", [("BCC", (2, 2, 2), 5), ("Octet", (2, 1, 2), 3)])
+def test_joint_only_system_equals_full_system_at_the_joints(geom, cells, mseg):
+    """Static condensation of every strut (checker of lat_assemble_bsr_struts): with loads and constraints on
+    lattice points only, the joint-only solve has the joint displacements and reactions of the full solve."""
+    from pylatticedso_b200 import mesh as M
+    lat = M.synthetic_lattice(geom, cells, [0.04], grad_radius=("linear", [True, False, True], [0.01, 0, 0.005]))
+    mesh = M.mesh_from_synthetic(lat, mseg)
+    fixed, g, f = M.compression_bc(mesh)
+    f = f.copy(); f[6 * 3 + 1] = 0.02
+    en = np.stack([mesh.en0, mesh.en1], 1)
+    K = orc.assemble_csr(mesh.xyz, en, mesh.rad, E_MOD, NU)
+    u, R = orc.solve_static(K, fixed.astype(bool), g, f)
+    nj = 6 * mesh.n_points
+    assert not fixed[nj:].any() and not f[nj:].any()
+    Kj, chains = orc.assemble_joint_only(mesh.xyz, en, mesh.rad, mesh.n_points, E_MOD, NU)
+    assert len(chains) * mseg == mesh.n_elems
+    uj, Rj = orc.solve_static(Kj, fixed[:nj].astype(bool), g[:nj], f[:nj])
+    assert np.abs(u[:nj] - uj).max() <= 1e-10 * np.abs(u).max()
+    assert np.abs(R[:nj] - Rj).max() <= 1e-10 * np.abs(R).max()
+
