@@ -296,6 +296,14 @@ int lat_assemble_bsr_struts(lat_ctx* ctx, const double* xyz, const int32_t* len0
                             const double* rad, int64_t n_nodes_full, int64_t n_elem, const int32_t* chain_ptr,
                             const int32_t* chain_elem, const int32_t* chain_flip, int64_t n_chains, int64_t n_joints,
                             double young, double nu, double kappa, double* vals);
+/* Back-substitution of the joint-only solve: displacements of the strut-interior nodes from the joint displacements
+ * (exact: no load on interior nodes).  u_full [6 n_nodes_full] must already hold the joints in its first 6 n_joints
+ * entries (joints are the first nodes of the subdivided mesh); u_joints may alias u_full.  One thread per strut,
+ * max_chain_len <= 64 elements per strut (LAT_ERR_UNSUPPORTED otherwise). */
+int lat_strut_recover(lat_ctx* ctx, const double* xyz, const int32_t* len0, const int32_t* len1, const double* rad,
+                      const int32_t* chain_ptr, const int32_t* chain_elem, const int32_t* chain_flip,
+                      const int32_t* chain_a, const int32_t* chain_b, int64_t n_chains, int32_t max_chain_len,
+                      double young, double nu, double kappa, const double* u_joints, double* u_full);
 
 /* ---- A8: DDM interface operator ------------------------------------------------
  * y = sum_c B_c S_c B_c^T x  (LatticeSim.calculate_reaction_force_global ->

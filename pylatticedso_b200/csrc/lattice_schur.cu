@@ -266,6 +266,155 @@ extern "C" int lat_assemble_bsr_struts(lat_ctx* ctx, const double* xyz, const in
   return LAT_OK;
 }
 
+// Back-substitution of the joint-only solve: the displacements of the strut-interior nodes from the two joint
+// displacements of their strut.  One thread per strut: axial and torsional components follow the spring series
+// (linear in the accumulated flexibility), the two bending planes share one block-tridiagonal 2x2 system that is
+// swept forward exactly as in k_chain_condense (pivot inverses kept in local memory) and solved backwards for
+// both planes.  Planes: (W, Phi) = (w.a1, -th.a2) and (w.a2, th.a1) for any orthonormal a1, a2 = t x a1.
+static constexpr int STRUT_MAX_SEG = 64;
+struct PlanarElem { double g1, g2, dp, dm, fax, ftor; };
+__device__ __forceinline__ PlanarElem planar_elem(const double* __restrict__ xyz, const int32_t* __restrict__ len0,
+                                                  const int32_t* __restrict__ len1, const double* __restrict__ rad,
+                                                  int e, double young, double G, double kappa) {
+  const int a = len0[e], b = len1[e];
+  const double dx = xyz[b * 3] - xyz[a * 3], dy = xyz[b * 3 + 1] - xyz[a * 3 + 1], dz = xyz[b * 3 + 2] - xyz[a * 3 + 2];
+  const double L = sqrt(dx * dx + dy * dy + dz * dz), iL = 1.0 / L;
+  const double r = rad[e];
+  const double PI = 3.14159265358979323846;
+  const double S = PI * r * r, I = PI * r * r * r * r * 0.25;
+  const double ES = young * S, GS = G * kappa * S, EI = young * I, GJ = G * 2.0 * I;
+  PlanarElem p;
+  p.g1 = GS * iL; p.g2 = 0.5 * GS; p.dp = 0.25 * GS * L + EI * iL; p.dm = 0.25 * GS * L - EI * iL;
+  p.fax = L / ES; p.ftor = L / GJ;
+  return p;
+}
+__global__ void __launch_bounds__(64) k_strut_recover(
+    const double* __restrict__ xyz, const int32_t* __restrict__ len0, const int32_t* __restrict__ len1,
+    const double* __restrict__ rad, const int32_t* __restrict__ chain_ptr, const int32_t* __restrict__ chain_elem,
+    const int32_t* __restrict__ chain_flip, const int32_t* __restrict__ chain_a, const int32_t* __restrict__ chain_b,
+    int64_t n_chains, double young, double nu, double kappa, const double* __restrict__ uj, double* __restrict__ ufull) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_chains) return;
+  const int q0 = chain_ptr[s], m = chain_ptr[s + 1] - q0;
+  if (m < 2 || m > STRUT_MAX_SEG) return;
+  const double G = young / (2.0 * (1.0 + nu));
+  const int A = chain_a[s], B = chain_b[s];
+  // strut direction (walking order) and a frame
+  double t[3];
+  {
+    const int e = chain_elem[q0];
+    const bool fl = chain_flip[q0] != 0;
+    const int a = fl ? len1[e] : len0[e], b = fl ? len0[e] : len1[e];
+    const double dx = xyz[b * 3] - xyz[a * 3], dy = xyz[b * 3 + 1] - xyz[a * 3 + 1], dz = xyz[b * 3 + 2] - xyz[a * 3 + 2];
+    const double iL = rsqrt(dx * dx + dy * dy + dz * dz);
+    t[0] = dx * iL; t[1] = dy * iL; t[2] = dz * iL;
+    const double n2 = 1.0 / sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);   // rsqrt is approximate: renormalise
+    t[0] *= n2; t[1] *= n2; t[2] *= n2;
+  }
+  double a1[3], a2[3];
+  if (fabs(t[0]) < 0.9) { a1[0] = 0.0; a1[1] = t[2]; a1[2] = -t[1]; }      // t x ex
+  else { a1[0] = -t[2]; a1[1] = 0.0; a1[2] = t[0]; }                        // t x ey
+  {
+    const double n1 = 1.0 / sqrt(a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2]);
+    a1[0] *= n1; a1[1] *= n1; a1[2] *= n1;
+  }
+  a2[0] = t[1] * a1[2] - t[2] * a1[1]; a2[1] = t[2] * a1[0] - t[0] * a1[2]; a2[2] = t[0] * a1[1] - t[1] * a1[0];
+  double uA[6], uB[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { uA[k] = uj[(int64_t)A * 6 + k]; uB[k] = uj[(int64_t)B * 6 + k]; }
+  auto dot3 = [](const double* p, const double* q) { return p[0] * q[0] + p[1] * q[1] + p[2] * q[2]; };
+  // planar unknowns of the two planes at the joints: x = (W, Phi)
+  const double xA[2][2] = {{dot3(uA, a1), -dot3(uA + 3, a2)}, {dot3(uA, a2), dot3(uA + 3, a1)}};
+  double xn[2][2] = {{dot3(uB, a1), -dot3(uB + 3, a2)}, {dot3(uB, a2), dot3(uB + 3, a1)}};   // x_{k+1}, starts at B
+  const double wAt = dot3(uA, t), wBt = dot3(uB, t), tAt = dot3(uA + 3, t), tBt = dot3(uB + 3, t);
+  // forward sweep
+  double pinv[STRUT_MAX_SEG][3], akk[STRUT_MAX_SEG][4];
+  double fax_tot = 0.0, ftor_tot = 0.0;
+  double kk[2][2], ak[2][2];
+  for (int k = 0; k < m; ++k) {
+    const PlanarElem p = planar_elem(xyz, len0, len1, rad, chain_elem[q0 + k], young, G, kappa);
+    fax_tot += p.fax; ftor_tot += p.ftor;
+    if (k == 0) {
+      kk[0][0] = p.g1; kk[0][1] = p.g2; kk[1][0] = p.g2; kk[1][1] = p.dp;
+      ak[0][0] = -p.g1; ak[0][1] = -p.g2; ak[1][0] = p.g2; ak[1][1] = p.dm;
+      continue;
+    }
+    const double p00 = kk[0][0] + p.g1, p01 = kk[0][1] - p.g2, p11 = kk[1][1] + p.dp;
+    const double idet = 1.0 / (p00 * p11 - p01 * p01);
+    const double i00 = p11 * idet, i01 = -p01 * idet, i11 = p00 * idet;
+    pinv[k][0] = i00; pinv[k][1] = i01; pinv[k][2] = i11;
+    akk[k][0] = ak[0][0]; akk[k][1] = ak[0][1]; akk[k][2] = ak[1][0]; akk[k][3] = ak[1][1];
+    const double ekn[2][2] = {{-p.g1, -p.g2}, {p.g2, p.dm}};
+    const double enn[2][2] = {{p.g1, p.g2}, {p.g2, p.dp}};
+    double x[2][2], y[2][2], nak[2][2], nkk[2][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      x[i][0] = ak[i][0] * i00 + ak[i][1] * i01;
+      x[i][1] = ak[i][0] * i01 + ak[i][1] * i11;
+      y[i][0] = ekn[0][i] * i00 + ekn[1][i] * i01;
+      y[i][1] = ekn[0][i] * i01 + ekn[1][i] * i11;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        nak[i][j] = -(x[i][0] * ekn[0][j] + x[i][1] * ekn[1][j]);
+        nkk[i][j] = enn[i][j] - (y[i][0] * ekn[0][j] + y[i][1] * ekn[1][j]);
+      }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { ak[i][j] = nak[i][j]; kk[i][j] = nkk[i][j]; }
+  }
+  // backward: x_k = -P_k^-1 (ak_k^T x_A + E_kn(element k) x_{k+1}),  k = m-1 .. 1
+  double fax_suffix = 0.0, ftor_suffix = 0.0;   // flexibility of the elements k .. m-1
+  for (int k = m - 1; k >= 1; --k) {
+    const PlanarElem p = planar_elem(xyz, len0, len1, rad, chain_elem[q0 + k], young, G, kappa);
+    fax_suffix += p.fax; ftor_suffix += p.ftor;
+    const double i00 = pinv[k][0], i01 = pinv[k][1], i11 = pinv[k][2];
+    double xk[2][2];
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl) {
+      // rhs = ak_k^T x_A + E_kn x_{k+1}
+      const double r0 = akk[k][0] * xA[pl][0] + akk[k][2] * xA[pl][1] + (-p.g1) * xn[pl][0] + (-p.g2) * xn[pl][1];
+      const double r1 = akk[k][1] * xA[pl][0] + akk[k][3] * xA[pl][1] + p.g2 * xn[pl][0] + p.dm * xn[pl][1];
+      xk[pl][0] = -(i00 * r0 + i01 * r1);
+      xk[pl][1] = -(i01 * r0 + i11 * r1);
+    }
+    const double cax = 1.0 - fax_suffix / fax_tot, ctor = 1.0 - ftor_suffix / ftor_tot;   // share of elements 0 .. k-1
+    const double wt = wAt + (wBt - wAt) * cax, tt = tAt + (tBt - tAt) * ctor;
+    // node between element k-1 and k (walking order): the end node of element k-1
+    const int ep = chain_elem[q0 + k - 1];
+    const int node = chain_flip[q0 + k - 1] ? len0[ep] : len1[ep];
+    double* o = ufull + (int64_t)node * 6;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      o[c] = wt * t[c] + xk[0][0] * a1[c] + xk[1][0] * a2[c];
+      o[3 + c] = tt * t[c] + xk[1][1] * a1[c] - xk[0][1] * a2[c];
+    }
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl) { xn[pl][0] = xk[pl][0]; xn[pl][1] = xk[pl][1]; }
+  }
+}
+
+// u_full[0 .. 6 n_joints) must already hold the joint displacements (joints are the first nodes of the full mesh);
+// this fills the strut-interior nodes.  max_chain_len <= 64.
+extern "C" int lat_strut_recover(lat_ctx* ctx, const double* xyz, const int32_t* len0, const int32_t* len1,
+                                 const double* rad, const int32_t* chain_ptr, const int32_t* chain_elem,
+                                 const int32_t* chain_flip, const int32_t* chain_a, const int32_t* chain_b,
+                                 int64_t n_chains, int32_t max_chain_len, double young, double nu, double kappa,
+                                 const double* u_joints, double* u_full) {
+  if (!ctx) return LAT_ERR_ARG;
+  LAT_CHECK_ARG(ctx, xyz && len0 && len1 && rad && chain_ptr && chain_elem && chain_flip && chain_a && chain_b && u_joints && u_full);
+  LAT_CHECK_ARG(ctx, n_chains > 0);
+  if (max_chain_len > STRUT_MAX_SEG)
+    return lat_fail(ctx, LAT_ERR_UNSUPPORTED, "lat_strut_recover: more than 64 elements per strut", __FILE__, __LINE__);
+  LAT_CUDA(ctx, cudaSetDevice(ctx->device));
+  LAT_LAUNCH(ctx, k_strut_recover, (unsigned)ceil_div(n_chains, 64), 64, 0, xyz, len0, len1, rad, chain_ptr, chain_elem,
+             chain_flip, chain_a, chain_b, n_chains, young, nu, kappa, u_joints, u_full);
+  return LAT_OK;
+}
+
 // One CTA per cell (grid-stride over cells).  A = dense cell stiffness in factorisation order
 // (interior DOFs first), lower triangle used.  Partial right-looking Cholesky over the nI interior
 // pivots; the rows of column k that are exactly zero are skipped (the cell graph is a set of strut

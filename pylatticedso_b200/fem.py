@@ -142,12 +142,14 @@ class BeamFEM:
             raise ValueError("mesh is not beam-major between lattice points")
         return np.r_[starts, m.n_elems].astype(np.int32), sa, sb
 
-    def solve_condensed(self, fixed, g, f, tol=1e-8, maxiter=200000, precond=L.PC_BLOCK6, **pcg_kw):
+    def solve_condensed(self, fixed, g, f, tol=1e-8, maxiter=200000, precond=L.PC_BLOCK6, full_field=False, **pcg_kw):
         """Joint-only solve: every strut (all its elements) is condensed exactly onto its two lattice points
         (``lat_assemble_bsr_struts``), the BSR system over the ``n_points`` joints is solved by the same PCG.  Needs
         loads and constraints on lattice points only -- what the reference applies -- and returns
         (u_joints [6 n_points], reactions on the joints, info): identical to the joint entries of :meth:`solve`
-        with 5x (2 elements per strut) to ~70x (the reference's 18) fewer DOFs and far fewer iterations."""
+        with 5x (2 elements per strut) to ~70x (the reference's 18) fewer DOFs and far fewer iterations.
+        ``full_field=True`` additionally back-substitutes the strut-interior nodes (``lat_strut_recover``) and returns
+        u and R over ALL nodes of the mesh (R is zero on interior nodes), e.g. for the element-form gradient."""
         torch = self.torch
         m, ctx, dev = self.mesh, self.ctx, self.ctx.device
         nj = 6 * m.n_points
@@ -171,6 +173,16 @@ class BeamFEM:
         ctx.set_dirichlet_values(fd, gd, u)
         R = ctx.spmv(rowptr, colidx, vals, u)
         info = dict(info, n_dof_condensed=nj, n_dof_full=m.n_dof)
+        if full_field:
+            u_full = torch.zeros(m.n_dof, dtype=torch.float64, device=dev)
+            u_full[:nj] = u
+            if m.n_nodes > m.n_points:
+                ctx.strut_recover(xyz, self.en0, self.en1, self.rad, t(ptr, np.int32), t(np.arange(ne), np.int32),
+                                  t(np.zeros(ne), np.int32), sa_d, sb_d, int(np.diff(ptr).max()), self.young, self.nu,
+                                  self.kappa, u, u_full)
+            R_full = torch.zeros(m.n_dof, dtype=torch.float64, device=dev)
+            R_full[:nj] = R
+            return u_full, R_full, info
         return u, R, info
 
     def adjoint_gradient(self, u, dJdu, fixed, group, n_groups, chain=None, tol=1e-10, maxiter=200000,
@@ -219,9 +231,9 @@ def solve_FEM_B200(lattice, elements_per_strut="gmsh", tol=1e-10, maxiter=500000
 
     ``matrix_free=True`` solves the same system without assembling K (csrc/matfree.cuh): same result to the
     solver tolerance, 1.4-2.8x faster iterations and no 288 B/block matrix in HBM.
-    ``condense_struts=True`` solves the exact joint-only system (:meth:`BeamFEM.solve_condensed`): the write-back
-    below only ever touches lattice points, so nothing is lost; ``model.u`` / ``model.R`` then cover the lattice
-    points only.
+    ``condense_struts=True`` solves the exact joint-only system (:meth:`BeamFEM.solve_condensed`) and
+    back-substitutes the strut-interior nodes, so ``model.u`` / ``model.R`` are the same full fields as on the other
+    paths (the write-back below only touches lattice points anyway).
 
     Leaves ``Point.displacement_vector`` on every lattice node and
     ``Point.reaction_force_vector`` on nodes with a fixed DOF
@@ -232,8 +244,11 @@ def solve_FEM_B200(lattice, elements_per_strut="gmsh", tol=1e-10, maxiter=500000
     mesh = flatten_lattice(lattice, None, elements_per_strut)
     fixed, g, f = bc_arrays_from_lattice(lattice, mesh, dedup_point_loads=dedup_point_loads)
     fem = BeamFEM(mesh, E, nu, ctx=ctx)
-    solve = fem.solve_condensed if condense_struts else (fem.solve_matrix_free if matrix_free else fem.solve)
-    u, R, info = solve(fixed, g, f, tol=tol, maxiter=maxiter, precond=precond)
+    if condense_struts:      # joint-only solve + back-substitution: model.u / model.R cover all nodes like the other paths
+        u, R, info = fem.solve_condensed(fixed, g, f, tol=tol, maxiter=maxiter, precond=precond, full_field=True)
+    else:
+        solve = fem.solve_matrix_free if matrix_free else fem.solve
+        u, R, info = solve(fixed, g, f, tol=tol, maxiter=maxiter, precond=precond)
     u_h = u.cpu().numpy().reshape(-1, NDOF)
     R_h = R.cpu().numpy().reshape(-1, NDOF)
     for k, p in enumerate(mesh.meta["points"]):

@@ -26,7 +26,7 @@ EXPORTS = [
     "lat_elem_stiffness", "lat_bsr_pattern_build", "lat_bsr_pattern_export", "lat_csr_structure",
     "lat_bsr_to_csr_values", "lat_assemble_bsr", "lat_apply_dirichlet", "lat_set_dirichlet_values", "lat_bsr_spmv", "lat_pcg_bsr",
     "lat_matfree_setup", "lat_matfree_apply", "lat_matfree_rhs", "lat_pcg_matfree", "lat_pcg_matfree_dist",
-    "lat_compliance_grad", "lat_schur_batch", "lat_schur_batch_chains", "lat_assemble_bsr_struts", "lat_ddm_matvec",
+    "lat_compliance_grad", "lat_schur_batch", "lat_schur_batch_chains", "lat_assemble_bsr_struts", "lat_strut_recover", "lat_ddm_matvec",
     "lat_nccl_unique_id", "lat_comm_create", "lat_comm_destroy", "lat_allreduce_sum", "lat_halo_exchange",
     "lat_pcg_bsr_dist", "lat_p2p_arena_create", "lat_p2p_attach", "lat_p2p_destroy", "lat_assemble_cells_bsr",
 ]
@@ -117,6 +117,7 @@ def load():
     lib.lat_pcg_matfree_dist.argtypes = [vp, C.POINTER(Halo), vp, vp, C.POINTER(PcgOpts), C.POINTER(PcgResult)]
     lib.lat_compliance_grad.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, vp, vp, i64, vp, vp]
     lib.lat_schur_batch.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, i32, dbl, dbl, dbl, vp, vp, vp, i32, vp]
+    lib.lat_strut_recover.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, dbl, dbl, dbl, vp, vp]
     lib.lat_assemble_bsr_struts.argtypes = [vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, i64, i64, dbl, dbl, dbl, vp]
     lib.lat_schur_batch_chains.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, dbl, dbl, dbl, vp]
     lib.lat_ddm_matvec.argtypes = [vp, vp, i64, vp, vp, i64, i32, i64, vp, vp]
@@ -326,6 +327,13 @@ class Context:
                                                     int(len0.numel()), _ptr(chain_ptr), _ptr(chain_elem), _ptr(chain_flip),
                                                     int(chain_ptr.numel()) - 1, n_joints, young, nu, kappa, _ptr(out)))
         return out
+
+    def strut_recover(self, xyz, len0, len1, rad, chain_ptr, chain_elem, chain_flip, chain_a, chain_b, max_len, young, nu,
+                      kappa, u_joints, u_full):
+        self.check(self.lib.lat_strut_recover(self.h, _ptr(xyz), _ptr(len0), _ptr(len1), _ptr(rad), _ptr(chain_ptr),
+                                              _ptr(chain_elem), _ptr(chain_flip), _ptr(chain_a), _ptr(chain_b),
+                                              int(chain_a.numel()), int(max_len), young, nu, kappa, _ptr(u_joints), _ptr(u_full)))
+        return u_full
 
     def schur_batch_chains(self, xyz, len0, len1, rad, chains, n_bnd_nodes, young, nu, kappa=0.9):
         """Schur complements through the strut pre-pass.  ``chains``: dict of device int32 tensors

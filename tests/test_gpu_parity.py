@@ -322,6 +322,11 @@ def test_joint_only_solve_equals_full_solve_at_the_joints(ctx, geom, cells, mseg
     assert info["info"] == 0 and info["n_dof_condensed"] == nj and u.numel() == nj
     assert np.abs(u.cpu().numpy() - uo[:nj]).max() <= 1e-8 * np.abs(uo).max()
     assert np.abs(R.cpu().numpy() - Ro[:nj]).max() <= 1e-8 * np.abs(Ro).max()
+    # back-substitution of the strut-interior nodes (lat_strut_recover): the FULL field equals the oracle's full solve
+    uf, Rf, _ = fem.solve_condensed(fixed, g, f, tol=1e-12, maxiter=50000, full_field=True)
+    assert uf.numel() == m.n_dof
+    assert np.abs(uf.cpu().numpy() - uo).max() <= 1e-8 * np.abs(uo).max()
+    assert np.abs(Rf.cpu().numpy() - Ro).max() <= 1e-8 * np.abs(Ro).max()
     # assembled joint-only matrix == the oracle's (super-elements through the dense chain condensation)
     Kj, _ = orc.assemble_joint_only(m.xyz, np.stack([m.en0, m.en1], 1), m.rad, m.n_points, E_MOD, NU)
     y = np.random.default_rng(0).standard_normal(nj)
