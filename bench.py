@@ -390,7 +390,30 @@ def run_b200(args):
             if s_ >= args.warmup:
                 cms += e[0].elapsed_time(e[1]); cit += info["iters"]
         cond = dict(ms=cms / args.steps, iters=cit / args.steps, n_dof=info["n_dof_condensed"])
-    res = dict(cond=cond, mf_ms=mf_ms, mf_iters=mf_iters, mf_prod_ms=float(np.mean(mf_prod)),
+    # ---- secondary (N = 1): the other two rates SURVEY section 8(d) names -- gradient elements/s and Schur cells/s
+    extra = None
+    if not distributed:
+        from pylatticedso_b200.schur import synthetic_cell_batch
+        grp = torch.from_numpy(np.ascontiguousarray(mesh.cell_of_elem, dtype=np.int32)).to(dev)
+        ng = int(mesh.cell_of_elem.max()) + 1
+        gfun = lambda: ctx.compliance_grad(fem.x, fem.y, fem.z, fem.en0, fem.en1, fem.rad, grp, ng, u_d, E_MOD, NU, KAPPA)
+        for _ in range(3):
+            gfun()
+        a, b_ = ev(), ev()
+        a.record()
+        for _ in range(10):
+            gfun()
+        b_.record(); torch.cuda.synchronize()
+        g_ms = a.elapsed_time(b_) / 10
+        n_sc = 50000
+        batch, _bnd = synthetic_cell_batch(ctx, "BCC", 0.02 + 0.06 * np.random.default_rng(1).random(n_sc), 18, E_MOD, NU)
+        batch.schur()
+        a, b_ = ev(), ev()
+        a.record(); batch.schur(); b_.record(); torch.cuda.synchronize()
+        s_ms = a.elapsed_time(b_)
+        extra = dict(grad_eps=mesh.n_elems / (g_ms * 1e-3), grad_ms=g_ms, schur_cps=n_sc / (s_ms * 1e-3), schur_ms=s_ms, schur_cells=n_sc)
+        del batch
+    res = dict(extra=extra, cond=cond, mf_ms=mf_ms, mf_iters=mf_iters, mf_prod_ms=float(np.mean(mf_prod)),
                tot_ms=tot_ms, asm_ms=asm_ms, solve_ms=solve_ms, iters=iters, launches=launches, clocks=clocks,
                spmv_ms=float(np.mean(spmv_ms)), update_ms=float(np.mean(upd_ms)), nprof=nprof,
                e2e_ms=e2e_ms, e2e_iters=e2e_iters, h2d=h2d, d2h=d2h, pattern_ms=pattern_ms,
@@ -456,6 +479,13 @@ def run_b200(args):
         "gpu_launches": res["launches"],
         "clocks": res["clocks"],
     }
+    if res.get("extra"):
+        x_ = res["extra"]
+        line["gradient"] = {"value": x_["grad_eps"], "unit": "elements/s", "ms": x_["grad_ms"],
+                            "note": "lat_compliance_grad (adjoint compliance sensitivity, 168 B/element) on the bench mesh"}
+        line["schur"] = {"value": x_["schur_cps"], "unit": "cells/s", "ms": x_["schur_ms"], "cells": x_["schur_cells"],
+                         "note": "lat_schur_batch_chains: BCC cells at the reference mesh density (18 elements per strut, "
+                                 "870 DOF -> 48 boundary DOF), strut pre-pass + joint-only condensation"}
     if res.get("cond"):
         c = res["cond"]
         line["strut_condensed"] = {"ms_per_step": c["ms"], "n_dof": c["n_dof"], "iterations_per_step": c["iters"],
