@@ -6,7 +6,9 @@ from pylatticedso_b200 import lib as L, mesh as M
 E, NU = 1013.0, 0.3
 ctx = L.Context(); dev = ctx.device
 t = lambda a, d: torch.from_numpy(np.ascontiguousarray(a, dtype=d)).to(dev)
-lat = M.synthetic_lattice("BCC", (60, 60, 60), [0.05]); mesh = M.mesh_from_synthetic(lat, 1)
+geom, nn_ = (sys.argv[1], int(sys.argv[2])) if len(sys.argv) > 2 else ("BCC", 60)
+lat = M.synthetic_lattice(geom, (nn_, nn_, nn_), [0.05 if geom == "BCC" else 0.03]); mesh = M.mesh_from_synthetic(lat, 1)
+print(geom, nn_)
 x, y, z, en0, en1, rad = t(mesh.x, np.float64), t(mesh.y, np.float64), t(mesh.z, np.float64), t(mesh.en0, np.int32), t(mesh.en1, np.int32), t(mesh.rad, np.float64)
 N = mesh.n_nodes
 rowptr, colidx = ctx.bsr_pattern(en0, en1, N); nnzb = colidx.numel()
