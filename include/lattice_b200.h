@@ -298,7 +298,7 @@ int lat_assemble_bsr_struts(lat_ctx* ctx, const double* xyz, const int32_t* len0
                             double young, double nu, double kappa, double* vals);
 /* Back-substitution of the joint-only solve: displacements of the strut-interior nodes from the joint displacements
  * (exact: no load on interior nodes).  u_full [6 n_nodes_full] must already hold the joints in its first 6 n_joints
- * entries (joints are the first nodes of the subdivided mesh); u_joints may alias u_full.  One thread per strut,
+ * entries (joints are the first nodes of the subdivided mesh); u_joints is a separate buffer.  One thread per strut,
  * max_chain_len <= 64 elements per strut (LAT_ERR_UNSUPPORTED otherwise). */
 int lat_strut_recover(lat_ctx* ctx, const double* xyz, const int32_t* len0, const int32_t* len1, const double* rad,
                       const int32_t* chain_ptr, const int32_t* chain_elem, const int32_t* chain_flip,
