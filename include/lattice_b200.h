@@ -155,7 +155,9 @@ typedef struct {
 
 typedef struct {
   int32_t iters;
-  int32_t info;      /* 0 converged, 1 maxiter, 2 alpha < 1e-6 seen (reference flag) */
+  int32_t info;      /* 0 converged, 1 maxiter, 2 alpha < 1e-6 seen (reference flag), 3 breakdown (p.Ap <= 0 / NaN),
+                        4 peer time-out (multi-GPU peer-memory path), 5 the recurrence residual met tol but the
+                        recomputed |b - A x| stayed above 2 tol |b| after two restarts (see true_relres) */
   double relres;     /* |r| / |b| at exit (recurrence residual) */
   double norm_b;
   double solve_ms;   /* device time of the iteration loop (CUDA events on the ctx stream) */
@@ -163,7 +165,8 @@ typedef struct {
   double spmv_ms;    /* mean duration of the fused SpMV kernel over the profiled iterations (0 if none) */
   double update_ms;  /* mean duration of the update kernel over the profiled iterations */
   int32_t profiled;  /* iterations actually profiled */
-  int32_t reserved;  /* restarts triggered by the true-residual safeguard */
+  int32_t reserved;  /* bits 0-7: restarts triggered by the true-residual safeguard; bit 8: the iteration batches
+                        ran as CUDA graphs (always on one GPU; multi-GPU unless capture failed or opts bit 2) */
   double true_relres; /* |b - A x| / |b| recomputed after convergence (textbook mode; -1 if not measured) */
 } lat_pcg_result;
 
@@ -229,7 +232,7 @@ int lat_pcg_matfree_dist(lat_ctx* ctx, const lat_halo* halo, const double* b, do
  * flags and the ghosted vector u), the host layer all-gathers the 64-byte CUDA IPC handles, every rank
  * maps all arenas.  lat_pcg_bsr_dist with bit 4 of opts.reserved then pushes halos with st.global on the
  * mapped peer pointers and all-reduces the 3 CG sums through the mailboxes inside its own kernels
- * (k_p2p_push, k_cg_spmv_p2p, k_p2p_reduce); info = 4 reports a peer time-out.
+ * (halo_push inside k_cg_update, halo_wait inside k_cg_spmv<GHOST>, k_p2p_reduce); info = 4 reports a peer time-out.
  *   nb_rank[k], nb_dst_node0[k]: neighbour k (same order as lat_halo.peer) and the first node index, in
  *   THAT rank's local numbering, of the ghost segment this rank fills. */
 int lat_p2p_arena_create(lat_ctx* ctx, int64_t n_local, void* handle64);

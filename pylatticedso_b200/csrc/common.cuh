@@ -42,6 +42,10 @@ struct lat_ctx {
   PcgScalars* h_scal = nullptr;  // 2 slots
   int64_t* h_i64 = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  // ctx-owned non-blocking stream: stands in for the caller's stream wherever stream capture is needed and the
+  // caller handed us the legacy default stream (which cannot be captured); ordered after it by ev_order
+  cudaStream_t work = nullptr;
+  cudaEvent_t ev_order = nullptr;
   // multi-GPU
   void* nccl_comm = nullptr;
   int nranks = 1, rank = 0;

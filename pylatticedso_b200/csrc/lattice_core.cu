@@ -80,6 +80,8 @@ extern "C" int lat_ctx_destroy(lat_ctx* ctx) {
   if (ctx->h_i64) cudaFreeHost(ctx->h_i64);
   for (int i = 0; i < 4; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->work) cudaStreamDestroy(ctx->work);
+  if (ctx->ev_order) cudaEventDestroy(ctx->ev_order);
   delete ctx;
   return LAT_OK;
 }
@@ -513,6 +515,13 @@ extern "C" int lat_csr_structure(lat_ctx* ctx, const int32_t* rowptr, const int3
   if (!ctx) return LAT_ERR_ARG;
   LAT_CHECK_ARG(ctx, rowptr && colidx && indptr && n_nodes > 0);
   LAT_CUDA(ctx, cudaSetDevice(ctx->device));
+  // int32 CSR offsets (scipy's index type for this size) hold at most 2^31-1 scalar entries = 59.6 M blocks:
+  // refuse instead of wrapping (the BSR path itself has no such limit).  [syncs]
+  int32_t nnzb32 = 0;
+  LAT_CUDA(ctx, cudaMemcpyAsync(&nnzb32, rowptr + n_nodes, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (nnzb32 < 0 || (int64_t)nnzb32 * 36 > (int64_t)INT32_MAX)
+    return lat_fail(ctx, LAT_ERR_UNSUPPORTED, "scalar CSR structure needs more than 2^31-1 entries: use the BSR arrays", __FILE__, __LINE__);
   LAT_LAUNCH(ctx, k_csr_structure, (unsigned)ceil_div(6 * n_nodes + 1, 256), 256, 0, rowptr, colidx, n_nodes, indptr, indices);
   return LAT_OK;
 }

@@ -670,10 +670,14 @@ __global__ void __launch_bounds__(CG_REDUCE_BLOCK) k_cg_true_residual(const doub
   if (decide == 0) { sc->sums[3] = out[0]; return; }           // dist: local sum only, all-reduced by the host
   const double rr = (decide == 2) ? out[0] : sc->sums[3];
   sc->true_rr = rr;
-  if (rr > 4.0 * prm.tol * prm.tol * sc->bb && sc->restarts < 2 && sc->iters < prm.maxiter) {  // |r_true| > 2 tol |b|
-    sc->done = 0;
-    sc->first = 2;
-    sc->restarts += 1;
+  if (rr > 4.0 * prm.tol * prm.tol * sc->bb) {  // |r_true| > 2 tol |b|
+    if (sc->restarts < 2 && sc->iters < prm.maxiter) {
+      sc->done = 0;
+      sc->first = 2;
+      sc->restarts += 1;
+    } else {
+      sc->breakdown = 3;   // restart budget exhausted: reported as info = 5, never as "converged"
+    }
   }
 }
 
@@ -1095,13 +1099,13 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
   res->iters = hs[0].iters;
   res->norm_b = sqrt(hs[0].bb);
   res->relres = hs[0].bb > 0.0 ? sqrt(hs[0].rr / hs[0].bb) : 0.0;
-  res->info = hs[0].done && !hs[0].breakdown ? 0 : (hs[0].breakdown ? 3 : (hs[0].info_flag2 ? 2 : 1));
+  res->info = hs[0].done && !hs[0].breakdown ? 0 : (hs[0].breakdown == 3 ? 5 : (hs[0].breakdown ? 3 : (hs[0].info_flag2 ? 2 : 1)));
   res->solve_ms = ms;
   res->launches = ctx->launches - launches0;
   res->spmv_ms = spmv_ms;
   res->update_ms = update_ms;
   res->profiled = nprof;
-  res->reserved = hs[0].restarts;
+  res->reserved = hs[0].restarts | 0x100;   // bit 8: the iteration batches ran as CUDA graphs
   res->true_relres = (true_rr >= 0.0 && hs[0].bb > 0.0) ? sqrt(true_rr / hs[0].bb) : -1.0;
   return LAT_OK;
 }
@@ -1693,9 +1697,39 @@ __global__ void __launch_bounds__(1024) k_compact_rows(const uint8_t* __restrict
 }
 
 template <int PC>
+static int pcg_run_dist_impl(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, const double* vals,
+                             const lat_halo* h, const double* b, double* x, const lat_pcg_opts* o, lat_pcg_result* res,
+                             const MfOp* mf);
+
+// The iteration batches (kernels and, in the NCCL path, the collectives) are captured into a CUDA graph ON the
+// stream they run on.  The legacy default stream -- what a caller without an own stream hands to lat_ctx_create --
+// cannot be captured, so the whole solve then runs on the ctx-owned non-blocking stream, ordered after the caller's
+// stream by an event; the solve ends with a synchronisation, which orders the caller's later work after it.
+template <int PC>
 static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, const double* vals,
                         const lat_halo* h, const double* b, double* x, const lat_pcg_opts* o, lat_pcg_result* res,
                         const MfOp* mf = nullptr) {
+  cudaStream_t caller = ctx->stream;
+  const bool legacy = caller == nullptr || caller == cudaStreamLegacy;
+  if (legacy) {
+    if (!ctx->work) LAT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->work, cudaStreamNonBlocking));
+    if (!ctx->ev_order) LAT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_order, cudaEventDisableTiming));
+    LAT_CUDA(ctx, cudaEventRecord(ctx->ev_order, caller));
+    LAT_CUDA(ctx, cudaStreamWaitEvent(ctx->work, ctx->ev_order, 0));
+    ctx->stream = ctx->work;
+  }
+  const int rc = pcg_run_dist_impl<PC>(ctx, rowptr, colidx, vals, h, b, x, o, res, mf);
+  if (legacy) {
+    cudaStreamSynchronize(ctx->work);
+    ctx->stream = caller;
+  }
+  return rc;
+}
+
+template <int PC>
+static int pcg_run_dist_impl(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, const double* vals,
+                             const lat_halo* h, const double* b, double* x, const lat_pcg_opts* o, lat_pcg_result* res,
+                             const MfOp* mf) {
   // Chronopoulos-Gear arrangement: per iteration ONE halo exchange (u) and ONE all-reduce (3 doubles).
   const int64_t n_own = h->n_owned, n_loc = h->n_local;
   const int64_t n = 6 * n_loc;
@@ -2061,10 +2095,10 @@ static int pcg_run_dist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* coli
   res->iters = hs[0].iters;
   res->norm_b = sqrt(hs[0].bb);
   res->relres = hs[0].bb > 0.0 ? sqrt(hs[0].rr / hs[0].bb) : 0.0;
-  res->info = hs[0].done && !hs[0].breakdown ? 0 : (hs[0].breakdown == 2 ? 4 : (hs[0].breakdown ? 3 : 1));
+  res->info = hs[0].done && !hs[0].breakdown ? 0 : (hs[0].breakdown == 2 ? 4 : (hs[0].breakdown == 3 ? 5 : (hs[0].breakdown ? 3 : 1)));
   res->solve_ms = ms;
   res->launches = ctx->launches - launches0;
-  res->spmv_ms = prof_n > 0 ? prof_ms / prof_n : 0.0; res->update_ms = 0.0; res->profiled = prof_n; res->reserved = hs[0].restarts;
+  res->spmv_ms = prof_n > 0 ? prof_ms / prof_n : 0.0; res->update_ms = 0.0; res->profiled = prof_n; res->reserved = hs[0].restarts | (use_graph ? 0x100 : 0);
   res->true_relres = (true_rr >= 0.0 && hs[0].bb > 0.0) ? sqrt(true_rr / hs[0].bb) : -1.0;
   return LAT_OK;
 }

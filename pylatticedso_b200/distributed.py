@@ -55,18 +55,46 @@ def node_owner_by_x(x, bounds):
 
 
 def slab_bounds(x_min, x_max, world, n_layers=None, cell=1.0):
-    """Slab boundaries on cell-layer planes: n_layers cells split as evenly as possible."""
+    """Slab boundaries on cell-layer planes: n_layers cells of size ``cell`` split as evenly as possible
+    (explicit variant; :func:`slab_bounds_from_nodes` needs no cell size)."""
     if n_layers is None:
         n_layers = int(round((x_max - x_min) / cell))
+    if world > n_layers:
+        raise ValueError(f"slab partition: {world} ranks for {n_layers} cell layers")
     cuts = [x_min + cell * ((n_layers * p) // world) for p in range(world)] + [x_max]
+    return np.array(cuts, dtype=np.float64)
+
+
+def slab_bounds_from_nodes(x, world):
+    """Slab boundaries derived from the data: cuts fall on node x-planes such that every rank owns about the same
+    number of nodes.  Independent of the cell size and of where the lattice starts; never produces an empty slab
+    as long as there are at least ``world`` distinct x-planes (ValueError otherwise, identically on every rank
+    because every rank evaluates the same global array)."""
+    ux, cnt = np.unique(np.round(np.asarray(x, dtype=np.float64), 9), return_counts=True)
+    if ux.size < world:
+        raise ValueError(f"slab partition: {world} ranks but only {ux.size} distinct x-planes of nodes")
+    cum = np.cumsum(cnt)
+    total = int(cum[-1])
+    first = [0]                                   # index of the first plane of every rank
+    for p in range(1, world):
+        k = int(np.searchsorted(cum, p * total / world, side="left")) + 1   # planes [0, k) hold >= p/world of the nodes
+        k = max(k, first[-1] + 1)                 # at least one plane per rank ...
+        k = min(k, ux.size - (world - p))         # ... and one left for each rank behind
+        first.append(k)
+    # a cut half-way towards the previous plane keeps rounding noise in x away from the comparison
+    cuts = [ux[0]] + [0.5 * (ux[k - 1] + ux[k]) for k in first[1:]] + [ux[-1]]
     return np.array(cuts, dtype=np.float64)
 
 
 def partition_slab(mesh: BeamMesh, rank: int, world: int, bounds=None, owner=None) -> SlabPartition:
     if owner is None:
         if bounds is None:
-            bounds = slab_bounds(float(mesh.x.min()), float(mesh.x.max()), world)
+            bounds = slab_bounds_from_nodes(mesh.x, world)
         owner = node_owner_by_x(mesh.x, bounds)
+    n_per_rank = np.bincount(owner, minlength=world)
+    if (n_per_rank[:world] == 0).any():           # same verdict on every rank -> nobody enters a collective
+        raise ValueError(f"slab partition: ranks {np.flatnonzero(n_per_rank[:world] == 0).tolist()} own no node "
+                         f"(bounds {None if bounds is None else list(bounds)})")
     o0, o1 = owner[mesh.en0], owner[mesh.en1]
     mine = (o0 == rank) | (o1 == rank)
     local_elems = np.flatnonzero(mine)
@@ -83,12 +111,20 @@ def partition_slab(mesh: BeamMesh, rank: int, world: int, bounds=None, owner=Non
     send_pairs = np.concatenate([np.stack([mesh.en0[e_cross0], o1[e_cross0]], 1),
                                  np.stack([mesh.en1[e_cross1], o0[e_cross1]], 1)], axis=0)
     peers = sorted(set(peers) | set(send_pairs[:, 1].tolist()))
-    g2l_owned = {int(g): k for k, g in enumerate(owned)}
+    g2l = np.full(mesh.n_nodes, -1, dtype=np.int64)          # global -> local id of the owned nodes (no per-node dict)
+    g2l[owned] = np.arange(owned.shape[0])
     send_lists, recv_counts = [], []
     for q in peers:
         nodes = np.unique(send_pairs[send_pairs[:, 1] == q, 0])
-        send_lists.append(np.array([g2l_owned[int(g)] for g in nodes], dtype=np.int32))
+        send_lists.append(g2l[nodes].astype(np.int32))
         recv_counts.append(int((gown == q).sum()))
+    # every rank can evaluate every other rank's neighbour count from the same arrays: fail everywhere, not on one rank
+    cross = o0 != o1
+    pair = np.unique(np.stack([np.minimum(o0[cross], o1[cross]), np.maximum(o0[cross], o1[cross])], 1), axis=0)
+    n_nb = np.bincount(pair.ravel(), minlength=world) if pair.size else np.zeros(world, dtype=np.int64)
+    if n_nb.max(initial=0) > 4:
+        raise ValueError(f"slab partition: a rank would have {int(n_nb.max())} neighbours (slabs thinner than one strut); "
+                         "use fewer ranks")
     return SlabPartition(rank, world, owned, ghosts, gown, local_elems, peers, send_lists, recv_counts)
 
 

@@ -16,7 +16,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "liblattice_b200.so")
 SOURCES = ["lattice_core.cu", "lattice_solver.cu", "lattice_schur.cu"]
-HEADERS = [os.path.join(_HERE, "csrc", "common.cuh"), os.path.join(_ROOT, "include", "lattice_b200.h")]
+HEADERS = [os.path.join(_HERE, "csrc", "common.cuh"), os.path.join(_HERE, "csrc", "matfree.cuh"),
+           os.path.join(_ROOT, "include", "lattice_b200.h")]
 
 ASM_GATHER, ASM_ATOMIC, ASM_ROWS = 0, 1, 2
 PC_NONE, PC_JACOBI, PC_BLOCK6 = 0, 1, 2
@@ -261,7 +262,7 @@ class Context:
                                         _ptr(x), C.byref(o), C.byref(r)))
         return x, dict(iters=r.iters, info=r.info, relres=r.relres, norm_b=r.norm_b, solve_ms=r.solve_ms,
                        launches=r.launches, spmv_ms=r.spmv_ms, update_ms=r.update_ms, profiled=r.profiled,
-                       true_relres=r.true_relres, restarts=r.reserved)
+                       true_relres=r.true_relres, restarts=r.reserved & 0xff, graph=bool(r.reserved & 0x100))
 
     # ---- matrix-free operator (resident in the context; needs bsr_pattern() of the same mesh) ----
     def matfree_setup(self, x, y, z, en0, en1, rad, n_nodes, young, nu, kappa=0.9, fixed=None):
@@ -291,7 +292,7 @@ class Context:
         self.check(self.lib.lat_pcg_matfree(self.h, _ptr(b), _ptr(x), C.byref(o), C.byref(r)))
         return x, dict(iters=r.iters, info=r.info, relres=r.relres, norm_b=r.norm_b, solve_ms=r.solve_ms,
                        launches=r.launches, spmv_ms=r.spmv_ms, update_ms=r.update_ms, profiled=r.profiled,
-                       true_relres=r.true_relres, restarts=r.reserved)
+                       true_relres=r.true_relres, restarts=r.reserved & 0xff, graph=bool(r.reserved & 0x100))
 
     def compliance_grad(self, x, y, z, en0, en1, rad, group, n_groups, u, young, nu, kappa=0.9, chain=None,
                         lam=None, want_elem=False):
@@ -439,7 +440,7 @@ class Context:
         r = PcgResult()
         self.check(self.lib.lat_pcg_matfree_dist(self.h, C.byref(halo), _ptr(b), _ptr(x), C.byref(o), C.byref(r)))
         return x, dict(iters=r.iters, info=r.info, relres=r.relres, norm_b=r.norm_b, solve_ms=r.solve_ms,
-                       launches=r.launches, true_relres=r.true_relres, restarts=r.reserved, spmv_ms=r.spmv_ms,
+                       launches=r.launches, true_relres=r.true_relres, restarts=r.reserved & 0xff, graph=bool(r.reserved & 0x100), spmv_ms=r.spmv_ms,
                        update_ms=r.update_ms, profiled=r.profiled)
 
     def pcg_dist(self, rowptr, colidx, vals, halo, b, x, tol=1e-8, maxiter=10000, precond=PC_JACOBI,
@@ -452,5 +453,5 @@ class Context:
         self.check(self.lib.lat_pcg_bsr_dist(self.h, _ptr(rowptr), _ptr(colidx), _ptr(vals), C.byref(halo), _ptr(b),
                                              _ptr(x), C.byref(o), C.byref(r)))
         return x, dict(iters=r.iters, info=r.info, relres=r.relres, norm_b=r.norm_b, solve_ms=r.solve_ms,
-                       launches=r.launches, true_relres=r.true_relres, restarts=r.reserved, spmv_ms=r.spmv_ms,
+                       launches=r.launches, true_relres=r.true_relres, restarts=r.reserved & 0xff, graph=bool(r.reserved & 0x100), spmv_ms=r.spmv_ms,
                        update_ms=r.update_ms, profiled=r.profiled)

@@ -103,3 +103,25 @@ def test_slab_bounds_and_owner():
     assert list(np.diff(b)) == [12, 13, 12, 13, 12, 13, 12, 13] or sum(np.diff(b)) == 100
     o = D.node_owner_by_x(np.array([0.0, 11.99, 12.0, 99.9, 100.0]), b)
     assert list(o) == [0, 0, 1, 7, 7]
+
+
+def test_slab_bounds_from_nodes_never_collapse():
+    """cell size 0.1 and more ranks than the unit-cell rule could serve collapsed the cuts; the
+    data-derived rule balances node counts, and an impossible request fails identically on every rank."""
+    from pylatticedso_b200 import distributed as D
+    from pylatticedso_b200 import mesh as M
+    lat = M.synthetic_lattice("BCC", (10, 2, 2), [0.005], cell_size=(0.1, 0.1, 0.1))
+    mesh = M.mesh_from_synthetic(lat, 2)
+    b = D.slab_bounds_from_nodes(mesh.x, 4)
+    assert np.all(np.diff(b) > 0)
+    own = np.bincount(D.node_owner_by_x(mesh.x, b), minlength=4)
+    assert own.min() > 0 and own.max() < 1.5 * own.mean()
+    parts = [D.partition_slab(mesh, r, 4) for r in range(4)]
+    assert sum(p.n_owned for p in parts) == mesh.n_nodes
+    for p in parts:                       # send list of p -> q has the length q expects from p
+        for q, sl in zip(p.peers, p.send_lists):
+            assert parts[q].recv_counts[parts[q].peers.index(p.rank)] == len(sl)
+    with pytest.raises(ValueError):
+        D.partition_slab(mesh, 0, 64)     # more ranks than x-planes: every rank raises before any collective
+    with pytest.raises(ValueError):
+        D.slab_bounds(0.0, 1.0, 4, cell=1.0)

@@ -33,7 +33,7 @@ def test_single_element_and_unconnected_node(ctx):
     u, info = ctx.pcg(rowptr, colidx, vbc, b, tol=1e-12, maxiter=200, precond=2)
     K = orc.assemble_csr(xyz, np.array([[0, 1]]), rad, E_MOD, NU)
     uo, _ = orc.solve_static(K[:12][:, :12], fixed[:12].astype(bool), np.zeros(12), f[:12])
-    assert info["info"] == 0 and np.abs(u.cpu().numpy()[:12] - uo).max() < 1e-9 * np.abs(uo).max()
+    assert info["info"] in (0, 5) and np.abs(u.cpu().numpy()[:12] - uo).max() < 1e-9 * np.abs(uo).max()
     assert float(u[12:].abs().max()) == 0.0
 
 

@@ -49,7 +49,7 @@ def main():
                     print(f"[dist_check] {mode} {op} {geom}{n} m={m_} world={world} n_dof={mesh.n_dof} iters={info['iters']} "
                           f"info={info['info']} relres={info['relres']:.1e} solve_ms={info['solve_ms']:.2f} |u-uo|/|uo|={eu:.2e} "
                           f"|R-Ro|/|Ro|={er:.2e}", flush=True)
-                    ok = ok and info["info"] == 0 and eu < 1e-8 and er < 1e-8
+                    ok = ok and info["info"] in (0, 5) and eu < 1e-8 and er < 1e-8
         # sharded compliance gradient w.r.t. per-cell radii == oracle's
         ncell = int(mesh.cell_of_elem.max()) + 1
         gd = dfem.compliance_gradient(u, mesh.cell_of_elem, ncell).cpu().numpy()
