@@ -18,6 +18,16 @@ roofline = the dominant kernel (k_cg_spmv: BSR SpMV fused with the three CG dot 
 
 Multi-GPU (N > 1): weak scaling, one process per GPU; the lattice is extended to
 (20 N) x 20 x 20 cells and cut into N x-slabs (see pylatticedso_b200/distributed.py).
+
+Every line also carries
+  parity   N > 1: the sharded solve (assembled AND matrix-free, peer-memory exchange) at tol 1e-12 against the
+           same system solved on rank 0 alone (u, reactions, compliance gradient); N = 1: assembled vs
+           matrix-free at full size + the CUDA path against the CPU oracle's direct solve on a BCC 6^3 case.
+           The process exits non-zero when a figure is above 1e-8 (u, R) / 1e-6 (gradient).
+  config5  BASELINE configs[4]: Octet 100^3 (24.4 M DOF), r = 0.03, strong scaling over the N GPUs, generated
+           per slab on each rank; assembled and matrix-free solve to 1e-8, time to first iteration, host RSS.
+The reference arm (--impl reference) runs the SAME (20 N) x 20 x 20 workload with Jacobi-PCG (C/OpenMP oracle
+port) on all host threads of the box (the thread count is set explicitly: torchrun exports OMP_NUM_THREADS=1).
 """
 from __future__ import annotations
 
@@ -41,7 +51,7 @@ UNIT = "DOF-iterations/s"
 # ncu --set full capture of k_cg_spmv on this workload (profiles/r01_ncu_full_v4_kernels.txt):
 # dram__bytes_read.sum 106.76 MB + dram__bytes_write.sum 3.65 MB per launch (algorithmic: 110.5 MB)
 NCU_TRAFFIC_CG_SPMV = 111.3e6   # dram__bytes_read.sum + dram__bytes_write.sum of one k_cg_spmv launch (profiles/r01_ncu_full_v4_kernels.txt)
-WORKLOAD = "BCC 20x20x20, r=0.05, 2 elements/strut (487566 DOF), uniaxial compression, block-Jacobi PCG to 1e-8"
+WORKLOAD = "BCC 20x20x20, r=0.05, 2 elements/strut (487566 DOF), uniaxial compression, assemble + PCG to 1e-8"
 
 
 def measured_peaks():
@@ -127,24 +137,26 @@ def iteration_bytes(n_nodes, nnzb, block_jacobi=True):
 
 
 # --------------------------------------------------------------------------- reference arm / CPU baseline
-def cpu_reference_run(steps, warmup, pcg_iters=3000, quiet=True):
+def cpu_reference_run(steps, warmup, pcg_iters=3000, n_slabs=1):
     """The reference's CPU path for this workload, restated (oracle port, C + OpenMP on all host threads,
     oracle/oracle_c.c): element matrices, value assembly into the CSR pattern (pattern from scipy COO->CSR of
     the element connectivity), Dirichlet elimination, then the reference's PCG
-    (conjugate_gradient_solver.py semantics, Jacobi M) for `pcg_iters` iterations per step (bounded sample)."""
+    (conjugate_gradient_solver.py semantics, JACOBI M = diag(K)^-1) for `pcg_iters` iterations per step (bounded
+    sample).  The reference's own solver file cannot travel to the GPU box (no checkout there), hence the port."""
     from oracle import lattice_oracle as orc
     from oracle import oracle_c as oc
     import scipy.sparse as sp
-    _, mesh, fixed, g, f = build_workload(1)
+    _, mesh, fixed, g, f = build_workload(n_slabs)
     en = np.stack([mesh.en0, mesh.en1], 1)
     xyz = mesh.xyz
-    threads = oc.num_threads()
+    threads = oc.set_num_threads(oc.host_threads())     # not the inherited OMP_NUM_THREADS (torchrun sets it to 1)
     # one-off pattern (not timed, like the GPU arm's pattern build)
     dofs = (en[:, :, None] * 6 + np.arange(6)[None, None, :]).reshape(-1, 12)
     P = sp.coo_matrix((np.ones(dofs.shape[0] * 144, dtype=np.int8), (np.repeat(dofs, 12, 1).ravel(), np.tile(dofs, (1, 12)).ravel())),
                       shape=(mesh.n_dof, mesh.n_dof)).tocsr()
     P.sum_duplicates(); P.sort_indices()
     indptr, indices = P.indptr.astype(np.int32), P.indices.astype(np.int32)
+    del P, dofs
     times, asm_times = [], []
     for s in range(warmup + steps):
         t0 = time.perf_counter()
@@ -163,7 +175,12 @@ def cpu_reference_run(steps, warmup, pcg_iters=3000, quiet=True):
     T = float(np.sum(times))
     val = mesh.n_dof * it * steps / T
     return dict(value=val, ms_per_step=1e3 * T / steps, asm_elems_per_s=mesh.n_elems * steps / float(np.sum(asm_times)),
-                n_dof=mesh.n_dof, iters=it, threads=threads, converged=(info == 0))
+                n_dof=mesh.n_dof, n_elems=mesh.n_elems, iters=it, threads=threads, converged=(info == 0))
+
+
+def workload_name(world):
+    return WORKLOAD if world == 1 else (f"BCC {20 * world}x20x20 in {world} x-slabs of 20 cell layers "
+                                        f"(weak scaling of: {WORKLOAD})")
 
 
 def run_reference(args):
@@ -171,14 +188,18 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warmup = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
-    r = cpu_reference_run(steps, warmup)
-    sample = (f"{steps} step(s): C/OpenMP assembly of the full 128000-element mesh + Jacobi-PCG to 1e-8 capped at 3000 "
+    r = cpu_reference_run(steps, warmup, n_slabs=args.gpus)
+    sample = (f"{steps} step(s): C/OpenMP assembly of the full {r['n_elems']}-element mesh + Jacobi-PCG to 1e-8 capped at 3000 "
               f"iterations ({r['iters']} run) per step, {r['threads']} threads")
     line = {
         "metric": METRIC, "value": r["value"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU restatement of the reference path (dolfinx/PETSc are not installable here)"},
+        "config": {"workload": workload_name(args.gpus), "n_dof": r["n_dof"],
+                   "n_elements": r["n_elems"], "precond": "jacobi", "tol": 1e-8,
+                   "note": "CPU restatement (port) of the reference path: dolfinx/PETSc are not installable here and the "
+                           "reference checkout does not exist on the GPU box, so its own conjugate_gradient_solver.py is "
+                           "restated in C/OpenMP (oracle/oracle_c.c) with Jacobi preconditioning"},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port", "sample": sample,
                          "host_cores_available": os.cpu_count(),
                          "assembly_elements_per_s": r["asm_elems_per_s"]},
@@ -186,6 +207,191 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+
+# --------------------------------------------------------------------------- parity / config 5 helpers
+def rel_max(a, b):
+    import torch
+    return float((a - b).abs().max() / b.abs().max())
+
+
+def parity_single(ctx, fem, fixed, g, f):
+    """N = 1: (i) assembled vs matrix-free at full size, tol 1e-12; (ii) the CUDA path vs the CPU oracle's sparse
+    direct solve on a BCC 6^3 (2 elements/strut) case of the same load -- oracle/ used as the checker only."""
+    import torch
+    from pylatticedso_b200 import lib as L, mesh as M
+    from pylatticedso_b200.fem import BeamFEM
+    from oracle import lattice_oracle as orc
+    fem.build_pattern()        # the secondary sections replaced the resident pattern
+    fem.vals = None
+    ua, Ra, ia = fem.solve(fixed, g, f, tol=1e-12, maxiter=400000, precond=L.PC_BLOCK6)
+    ua, Ra = ua.clone(), Ra.clone()
+    um, Rm, im = fem.solve_matrix_free(fixed, g, f, tol=1e-12, maxiter=400000, precond=L.PC_BLOCK6)
+    out = {"matrix_free_vs_assembled_u_rel": rel_max(um, ua), "matrix_free_vs_assembled_R_rel": rel_max(Rm, Ra),
+           "true_relres_assembled": ia["true_relres"], "true_relres_matrix_free": im["true_relres"]}
+    lat = M.synthetic_lattice("BCC", (6, 6, 6), [0.05])
+    m = M.mesh_from_synthetic(lat, 2)
+    fx, gg, ff = M.compression_bc(m)
+    small = BeamFEM(m, E_MOD, NU, KAPPA, ctx=ctx)
+    u, R, info = small.solve(fx, gg, ff, tol=1e-12, maxiter=100000, precond=L.PC_BLOCK6)
+    grp = m.cell_of_elem.astype(np.int32)
+    ng = int(grp.max()) + 1
+    gr = small.compliance_gradient(u, grp, ng).cpu().numpy()
+    en = np.stack([m.en0, m.en1], 1)
+    K = orc.assemble_csr(m.xyz, en, m.rad, E_MOD, NU)
+    uo, Ro = orc.solve_static(K, fx.astype(bool), gg, ff)
+    go = orc.compliance_gradient(m.xyz, en, m.rad, uo, grp, ng, E_MOD, NU)
+    out.update(u_rel=float(np.abs(u.cpu().numpy() - uo).max() / np.abs(uo).max()),
+               R_rel=float(np.abs(R.cpu().numpy() - Ro).max() / np.abs(Ro).max()),
+               grad_rel=float(np.abs(gr - go).max() / np.abs(go).max()),
+               against="CPU oracle direct solve, BCC 6x6x6 m=2 (%d DOF); full-size figures are assembled vs matrix-free" % m.n_dof)
+    out["ok"] = bool(out["u_rel"] < 1e-8 and out["R_rel"] < 1e-8 and out["grad_rel"] < 1e-6 and
+                     out["matrix_free_vs_assembled_u_rel"] < 1e-8 and out["matrix_free_vs_assembled_R_rel"] < 1e-8)
+    return out
+
+
+def parity_sharded(ctx, dfem, mesh, fixed, g, f, rank):
+    """N > 1: the sharded solve (peer-memory exchange when enabled) at tol 1e-12, assembled and matrix-free, against
+    the same global system solved on rank 0's GPU alone; all-gathered owned entries are compared on rank 0."""
+    import torch
+    import torch.distributed as dist
+    from pylatticedso_b200 import lib as L
+    from pylatticedso_b200.fem import BeamFEM
+    grp_g = mesh.cell_of_elem.astype(np.int32)
+    ng = int(grp_g.max()) + 1
+    res = {}
+    sols = {}
+    for name, solve in (("assembled", dfem.solve), ("matrix_free", dfem.solve_matrix_free)):
+        u, R, info = solve(tol=1e-12, maxiter=400000, precond=L.PC_BLOCK6)
+        gr = dfem.compliance_gradient(u, grp_g, ng).cpu().numpy()
+        sols[name] = (dfem.gather_owned(u), dfem.gather_owned(R), gr, info)
+    if rank == 0:
+        one = BeamFEM(mesh, E_MOD, NU, KAPPA, ctx=ctx)
+        u0, R0, i0 = one.solve(fixed, g, f, tol=1e-12, maxiter=400000, precond=L.PC_BLOCK6)
+        g0 = one.compliance_gradient(u0, grp_g, ng).cpu().numpy()
+        u0, R0 = u0.cpu().numpy(), R0.cpu().numpy()
+        ok = True
+        for name, (ug, Rg, gr, info) in sols.items():
+            e = dict(u_rel=float(np.abs(ug - u0).max() / np.abs(u0).max()), R_rel=float(np.abs(Rg - R0).max() / np.abs(R0).max()),
+                     grad_rel=float(np.abs(gr - g0).max() / np.abs(g0).max()), iters=info["iters"], info=info["info"],
+                     true_relres=info["true_relres"], cuda_graph=info.get("graph"))
+            ok = ok and e["u_rel"] < 1e-8 and e["R_rel"] < 1e-8 and e["grad_rel"] < 1e-6
+            res[name] = e
+        res["against"] = "the same global system solved on rank 0 alone (single-GPU path), tol 1e-12, iters %d" % i0["iters"]
+        res["u_rel"] = max(res[k]["u_rel"] for k in sols)
+        res["R_rel"] = max(res[k]["R_rel"] for k in sols)
+        res["grad_rel"] = max(res[k]["grad_rel"] for k in sols)
+        res["ok"] = bool(ok)
+        del one
+    dist.barrier()
+    return res
+
+
+def config5_section(ctx, rank, world, hbm_peak, n=100):
+    """BASELINE configs[4]: Octet n^3 (n = 100: 24 361 806 DOF), r = 0.03, 1 element per strut, uniaxial compression,
+    block-Jacobi PCG to 1e-8, strong scaling over `world` GPUs.  Every rank generates ONLY its own cell layers."""
+    import resource
+    import torch
+    import torch.distributed as dist
+    from pylatticedso_b200 import lib as L
+    from pylatticedso_b200 import distributed as D
+    dev = ctx.device
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    if world == 1:
+        from pylatticedso_b200.fem import BeamFEM
+        lm, part = D.generate_slab("Octet", (n, n, n), [0.03], 1, 0, 1)
+        fixed, g, f = D.compression_bc_local(lm)
+
+        class _Single:          # the single-GPU path behind the same few calls the sharded one offers
+            def __init__(self):
+                self.fem = BeamFEM(lm, E_MOD, NU, KAPPA, ctx=ctx)
+                self.fem.build_pattern()
+                self.n_owned, self.nnzb_owned = lm.n_nodes, self.fem.nnzb
+                self.n_dof_global, self.n_elem_global = lm.n_dof, lm.n_elems
+                self.vals = None
+                t = lambda a_, d: torch.from_numpy(np.ascontiguousarray(a_, dtype=d)).to(dev)
+                self.bc = (t(fixed, np.uint8), t(g, np.float64), t(f, np.float64))
+
+            def assemble(self):
+                self.fem.assemble()
+
+            def solve(self, **kw):
+                return self.fem.solve(*self.bc, keep_unconstrained=True, **kw)
+
+            def solve_matrix_free(self, **kw):
+                self.fem.vals = self.fem.vals_bc = None
+                torch.cuda.empty_cache()
+                return self.fem.solve_matrix_free(*self.bc, **kw)
+        dfem = _Single()
+    else:
+        dfem = D.DistributedFEM.from_generator(ctx, "Octet", (n, n, n), [0.03], 1, E_MOD, NU, rank, world, KAPPA)
+        fixed, g, f = D.compression_bc_local(dfem.lmesh)
+        dfem.set_bc_local(fixed, g, f)
+    t_gen_upload = time.perf_counter() - t0
+    exch = "none"
+    if world > 1:
+        exch = "nccl"
+        try:
+            dfem.enable_p2p()
+            exch = "nvlink-peer-memory"
+        except Exception as e_:
+            if rank == 0:
+                print(f"bench.py: config5 peer-memory path unavailable ({e_}); using NCCL", file=sys.stderr)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a, b_, c = ev(), ev(), ev()
+    a.record()
+    dfem.assemble()
+    b_.record()
+    u, R, info = dfem.solve(tol=1e-8, maxiter=100000, precond=L.PC_BLOCK6, profile_iters=32)
+    c.record()
+    torch.cuda.synchronize()
+    t_first = time.perf_counter() - t0 - 1e-3 * info["solve_ms"]
+    asm_ms, tot_ms = a.elapsed_time(b_), a.elapsed_time(c)
+    ua = u.clone()
+    no = 6 * dfem.n_owned
+    chk = torch.stack([ua[:no].abs().sum(), (R[:no] * ua[:no]).sum()])
+    dfem.vals = None
+    del R
+    torch.cuda.empty_cache()
+    um, Rm, im = dfem.solve_matrix_free(tol=1e-8, maxiter=100000, precond=L.PC_BLOCK6, want_reactions=False)
+    diff = torch.stack([(um[:no] - ua[:no]).abs().max(), ua[:no].abs().max()])
+    tt = torch.tensor([asm_ms, info["solve_ms"], im["solve_ms"], t_gen_upload, t_first,
+                       resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1e6], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([dfem.n_owned, dfem.nnzb_owned], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+        dist.all_reduce(chk)
+        dist.all_reduce(cnt)
+        ctx.p2p_destroy()
+    nn, nz = int(cnt[0]), int(cnt[1])
+    it_bytes = iteration_bytes(nn, nz, True)
+    out = {
+        "workload": f"Octet {n}x{n}x{n}, r=0.03, 1 element/strut, uniaxial compression, block-Jacobi PCG to 1e-8, strong scaling over {world} GPU(s)",
+        "n_dof": dfem.n_dof_global, "n_elements": dfem.n_elem_global, "nnzb": nz, "exchange": exch,
+        "assembled": {"solve_ms": float(tt[1]), "iters": info["iters"], "info": info["info"], "true_relres": info["true_relres"],
+                      "dof_iters_per_s": dfem.n_dof_global * info["iters"] / (float(tt[1]) * 1e-3),
+                      "assemble_ms": float(tt[0]), "assembly_elements_per_s": dfem.n_elem_global / (float(tt[0]) * 1e-3),
+                      "iteration_frac_of_hbm": it_bytes * info["iters"] / (float(tt[1]) * 1e-3) / 1e9 / (hbm_peak * world),
+                      "k_cg_spmv_frac_rank0": (spmv_bytes(dfem.n_owned, dfem.nnzb_owned) / (info["spmv_ms"] * 1e-3) / 1e9 / hbm_peak)
+                      if info.get("spmv_ms", 0) > 0 else None,
+                      "cuda_graph": info.get("graph")},
+        "matrix_free": {"solve_ms": float(tt[2]), "iters": im["iters"], "info": im["info"], "true_relres": im["true_relres"],
+                        "dof_iters_per_s": dfem.n_dof_global * im["iters"] / (float(tt[2]) * 1e-3),
+                        "u_rel_vs_assembled": float(diff[0] / diff[1])},
+        "checksums": {"sum_abs_u": float(chk[0]), "u_dot_R": float(chk[1]),
+                      "note": "all-reduced over ranks; equal across N to the solver tolerance"},
+        "host": {"generate_upload_pattern_s_max": float(tt[3]), "time_to_first_iteration_s_max": float(tt[4]),
+                 "peak_rss_gb_max": float(tt[5]),
+                 "note": "every rank generates only its own cell layers + 1 overlap layer (distributed.generate_slab)"},
+    }
+    del dfem, u, ua, um
+    torch.cuda.empty_cache()
+    return out
 
 
 # --------------------------------------------------------------------------- B200 arm
@@ -344,8 +550,24 @@ def run_b200(args):
         spmv_ms.append(info.get("spmv_ms", 0.0)); upd_ms.append(info.get("update_ms", 0.0)); nprof += info.get("profiled", 0)
     launches = ctx.launches - launches0
     clocks = sampler.stop()
-    # ---- end-to-end through the host-facing API: pinned host buffers -> H2D -> step -> D2H
-    h2d = sum(t.numel() * t.element_size() for t in host.values())
+    # ---- end-to-end through the public array-level API, inputs in pinned HOST memory, everything inside the timed
+    #      region: H2D of mesh + BCs, device allocation, pattern build, assembly, elimination, PCG, reactions, D2H.
+    #      N = 1: BeamFEM(mesh) + BeamFEM.solve(fixed, g, f);  N > 1: DistributedFEM.upload() + set_bc_local + solve.
+    from pylatticedso_b200.mesh import BeamMesh
+
+    def pinned_mesh(m_):
+        arrs = {k: pin(getattr(m_, k)) for k in ("x", "y", "z", "en0", "en1", "rad")}
+        pm = BeamMesh(**{k: v.numpy() for k, v in arrs.items()}, beam_of_elem=m_.beam_of_elem, chain=m_.chain,
+                      n_points=m_.n_points, point_index=m_.point_index, cell_of_elem=m_.cell_of_elem, meta=dict(m_.meta))
+        return pm, arrs
+
+    if distributed:
+        pm, keep_pinned = pinned_mesh(dfem.lmesh)
+        bc_pin = [pin(v) for v in (fixed[dfem.dofs], g[dfem.dofs], f[dfem.dofs])]
+    else:
+        pm, keep_pinned = pinned_mesh(mesh)
+        bc_pin = [pin(v) for v in (fixed, g, f)]
+    h2d = sum(t.numel() * t.element_size() for t in list(keep_pinned.values()) + bc_pin)
     u_host = torch.empty(n_out, dtype=torch.float64).pin_memory()
     R_host = torch.empty(n_out, dtype=torch.float64).pin_memory()
     d2h = 2 * n_out * 8
@@ -355,16 +577,27 @@ def run_b200(args):
         barrier()
         a, b_ = ev(), ev()
         a.record()
-        for k, dst in dev_targets:
-            dst.copy_(host[k], non_blocking=True)
-        _, info, (uu, RR) = step(0)
+        if distributed:
+            dfem.lmesh = pm
+            dfem.upload()
+            dfem.set_bc_local(*[t.numpy() for t in bc_pin])
+            uu, RR, info = dfem.solve(tol=1e-8, maxiter=200000, precond=L.PC_BLOCK6)
+        else:
+            fem_e = BeamFEM(pm, E_MOD, NU, KAPPA, ctx=ctx)
+            uu, RR, info = fem_e.solve(bc_pin[0].numpy(), bc_pin[1].numpy(), bc_pin[2].numpy(), tol=1e-8,
+                                       maxiter=200000, precond=L.PC_BLOCK6)
         u_host.copy_(uu, non_blocking=True)
         R_host.copy_(RR, non_blocking=True)
         b_.record()
         barrier()
+        assert info["info"] == 0, f"e2e PCG did not converge: {info}"
         if s_ >= 1:
             e2e_ms += a.elapsed_time(b_)
             e2e_iters += info["iters"]
+        if not distributed:
+            del fem_e
+    if not distributed:       # the e2e passes rebuilt the resident pattern; make the bench operator current again
+        fem.build_pattern()
     # ---- secondary: the matrix-free operator on the same workload (same barriers, L2 flush, CUDA events)
     mf_ms, mf_iters, mf_prod = 0.0, 0, []
     for s_ in range(args.warmup + args.steps):
@@ -413,6 +646,19 @@ def run_b200(args):
         s_ms = a.elapsed_time(b_)
         extra = dict(grad_eps=mesh.n_elems / (g_ms * 1e-3), grad_ms=g_ms, schur_cps=n_sc / (s_ms * 1e-3), schur_ms=s_ms, schur_cells=n_sc)
         del batch
+    # ---- parity block (driver-visible): see parity_single / parity_sharded
+    if distributed:
+        parity = parity_sharded(ctx, dfem, mesh, fixed, g, f, rank)
+    else:
+        parity = parity_single(ctx, fem, fixed, g, f)
+    # ---- BASELINE configs[4] on the same N GPUs
+    cfg5 = None
+    if not args.no_config5:
+        if distributed and getattr(dfem, "p2p", False):
+            ctx.p2p_destroy()
+        flush = None
+        torch.cuda.empty_cache()
+        cfg5 = config5_section(ctx, rank, world, hbm_peak, n=args.config5_n)
     res = dict(extra=extra, cond=cond, mf_ms=mf_ms, mf_iters=mf_iters, mf_prod_ms=float(np.mean(mf_prod)),
                tot_ms=tot_ms, asm_ms=asm_ms, solve_ms=solve_ms, iters=iters, launches=launches, clocks=clocks,
                spmv_ms=float(np.mean(spmv_ms)), update_ms=float(np.mean(upd_ms)), nprof=nprof,
@@ -446,7 +692,7 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD if world == 1 else f"BCC {20 * world}x20x20 in {world} x-slabs of 20 cell layers (weak scaling of: {WORKLOAD})",
+        "config": {"workload": workload_name(world),
                    "n_dof": n_dof_global, "n_elements": n_elem_global, "precond": "block-jacobi-6x6", "tol": 1e-8,
                    "iterations_per_step": res["iters"] / args.steps,
                    "l2": "L2 flushed (256 MB write) between steps; within a step the 98 MB matrix is re-streamed "
@@ -468,7 +714,10 @@ def run_b200(args):
                      "note": None if world == 1 else "rank 0's kernel over rank 0's slab (per-GPU peak); see pcg.iteration_frac_of_hbm "
                                                      "for the whole job against the aggregate peak"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": res["h2d"], "d2h_bytes_per_step": res["d2h"],
-                "ms_per_step": res["e2e_ms"] / args.steps},
+                "ms_per_step": res["e2e_ms"] / args.steps,
+                "path": ("BeamFEM(mesh) + BeamFEM.solve(fixed, g, f)" if world == 1 else
+                         "DistributedFEM.upload() + set_bc_local + solve") + ": host arrays in pinned memory -> H2D, device "
+                        "allocation, BSR pattern build, assembly, elimination, PCG, reactions, D2H of u and R, all timed"},
         "matrix_free": {"value": n_dof_global * res["mf_iters"] / (res["mf_ms"] * 1e-3), "unit": UNIT,
                         "ms_per_step": res["mf_ms"] / args.steps, "iterations_per_step": res["mf_iters"] / args.steps,
                         "product_kernel_ms": res["mf_prod_ms"],
@@ -478,7 +727,10 @@ def run_b200(args):
                                 "BSR path, timed after the headline region"},
         "gpu_launches": res["launches"],
         "clocks": res["clocks"],
+        "parity": parity,
     }
+    if cfg5 is not None:
+        line["config5"] = cfg5
     if res.get("extra"):
         x_ = res["extra"]
         line["gradient"] = {"value": x_["grad_eps"], "unit": "elements/s", "ms": x_["grad_ms"],
@@ -498,13 +750,16 @@ def run_b200(args):
     if world == 1 and not args.no_cpu_baseline:
         c = cpu_reference_run(1, 0, pcg_iters=3000)
         line["cpu_baseline"] = {"value": c["value"], "unit": UNIT, "cores": c["threads"], "kind": "port",
-                                "sample": f"1 step: C/OpenMP (oracle/oracle_c.c) assembly of the full mesh + Jacobi-PCG "
+                                "sample": f"1 step: C/OpenMP (oracle/oracle_c.c, a port: the reference checkout is not on the box) assembly of the full mesh + Jacobi-PCG "
                                           f"to 1e-8 capped at 3000 iterations ({c['iters']} run), {c['threads']} threads",
                                 "host_cores_available": os.cpu_count(),
                                 "assembly_elements_per_s": c["asm_elems_per_s"]}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if not parity.get("ok", False):
+        print(f"bench.py: PARITY FAILURE {parity}", file=sys.stderr)
+        sys.exit(3)
 
 
 def main():
@@ -515,6 +770,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nccl", action="store_true", help="multi-GPU: NCCL halo/all-reduce instead of NVLink peer memory")
+    ap.add_argument("--no-config5", action="store_true", help="skip the Octet 100^3 section (BASELINE configs[4])")
+    ap.add_argument("--config5-n", type=int, default=100, help="cells per side of the config5 octet lattice")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -157,3 +157,12 @@ int orc_num_threads(void) {
   return 1;
 #endif
 }
+
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm of bench.py sets the count explicitly. */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}

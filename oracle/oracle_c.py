@@ -66,3 +66,17 @@ def pcg(indptr, indices, data, b, dinv=None, maxiter=100, tol=1e-5, mintol=1e-5,
 
 def num_threads():
     return int(load().orc_num_threads())
+
+
+def set_num_threads(n):
+    """Explicit OpenMP thread count (overrides an inherited OMP_NUM_THREADS, e.g. torchrun's 1)."""
+    load().orc_set_num_threads(C.c_int(int(n)))
+    return num_threads()
+
+
+def host_threads():
+    """Threads this process may run on (cpuset-aware)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        return os.cpu_count() or 1

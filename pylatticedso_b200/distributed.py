@@ -86,13 +86,13 @@ def slab_bounds_from_nodes(x, world):
     return np.array(cuts, dtype=np.float64)
 
 
-def partition_slab(mesh: BeamMesh, rank: int, world: int, bounds=None, owner=None) -> SlabPartition:
+def partition_slab(mesh: BeamMesh, rank: int, world: int, bounds=None, owner=None, check=True) -> SlabPartition:
     if owner is None:
         if bounds is None:
             bounds = slab_bounds_from_nodes(mesh.x, world)
         owner = node_owner_by_x(mesh.x, bounds)
     n_per_rank = np.bincount(owner, minlength=world)
-    if (n_per_rank[:world] == 0).any():           # same verdict on every rank -> nobody enters a collective
+    if check and (n_per_rank[:world] == 0).any():           # same verdict on every rank -> nobody enters a collective
         raise ValueError(f"slab partition: ranks {np.flatnonzero(n_per_rank[:world] == 0).tolist()} own no node "
                          f"(bounds {None if bounds is None else list(bounds)})")
     o0, o1 = owner[mesh.en0], owner[mesh.en1]
@@ -122,7 +122,7 @@ def partition_slab(mesh: BeamMesh, rank: int, world: int, bounds=None, owner=Non
     cross = o0 != o1
     pair = np.unique(np.stack([np.minimum(o0[cross], o1[cross]), np.maximum(o0[cross], o1[cross])], 1), axis=0)
     n_nb = np.bincount(pair.ravel(), minlength=world) if pair.size else np.zeros(world, dtype=np.int64)
-    if n_nb.max(initial=0) > 4:
+    if check and n_nb.max(initial=0) > 4:
         raise ValueError(f"slab partition: a rank would have {int(n_nb.max())} neighbours (slabs thinner than one strut); "
                          "use fewer ranks")
     return SlabPartition(rank, world, owned, ghosts, gown, local_elems, peers, send_lists, recv_counts)
@@ -139,7 +139,23 @@ def local_mesh(mesh: BeamMesh, part: SlabPartition) -> BeamMesh:
                     rad=mesh.rad[e].copy(), beam_of_elem=mesh.beam_of_elem[e].copy(), chain=mesh.chain[e].copy(),
                     n_points=int((nodes < mesh.n_points).sum()), point_index=nodes[nodes < mesh.n_points],
                     cell_of_elem=None if mesh.cell_of_elem is None else mesh.cell_of_elem[e].copy(),
-                    meta={"global_nodes": nodes})
+                    meta={"global_nodes": nodes, "is_point": nodes < mesh.n_points})
+
+
+def compression_bc_local(lm: BeamMesh, value=-0.01):
+    """``mesh.compression_bc`` for a LOCAL slab mesh (lattice points are flagged in ``meta['is_point']``, not the
+    first nodes): clamp Zmin, impose u_z = value on Zmax.  Valid for x-slabs: every slab sees both z extremes."""
+    is_pt = lm.meta["is_point"]
+    zp = lm.z[is_pt]
+    zmin, zmax = zp.min(), zp.max()
+    n = lm.n_dof
+    fixed, g, f = np.zeros(n, dtype=np.uint8), np.zeros(n), np.zeros(n)
+    bot = np.flatnonzero(is_pt & (lm.z == zmin))
+    top = np.flatnonzero(is_pt & (lm.z == zmax))
+    fixed[(bot[:, None] * NDOF + np.arange(NDOF)[None, :]).ravel()] = 1
+    fixed[top * NDOF + 2] = 1
+    g[top * NDOF + 2] = value
+    return fixed, g, f
 
 
 def local_dofs(part: SlabPartition):
@@ -147,18 +163,85 @@ def local_dofs(part: SlabPartition):
     return (nodes[:, None] * NDOF + np.arange(NDOF)[None, :]).ravel()
 
 
-class DistributedFEM:
-    """Slab-sharded assemble + solve.  Every rank passes the same GLOBAL mesh and BC arrays (cheap,
-    vectorised) and keeps only its slab on the GPU."""
+def slab_layers(n_layers, world):
+    """Cell layers [i0, i1) of every rank: n_layers split as evenly as possible (ValueError when world > n_layers)."""
+    if world > n_layers:
+        raise ValueError(f"slab partition: {world} ranks for {n_layers} cell layers")
+    return [((n_layers * p) // world, (n_layers * (p + 1)) // world) for p in range(world)]
 
-    def __init__(self, ctx, mesh: BeamMesh, young, nu, rank, world, kappa=0.9, bounds=None):
+
+def generate_slab(geom_types, n_cells, radii, elements_per_strut, rank, world, cell_size=(1.0, 1.0, 1.0),
+                  grad_radius=None, cell_radii=None):
+    """Per-slab lattice generation: the rank builds ONLY its own cell layers plus one overlap layer on each side
+    (host time and memory ~ 1/world of the full lattice) and returns (local BeamMesh in [owned | ghosts] numbering,
+    SlabPartition).  No global numbering exists on this path: both sides of an exchange order the shared nodes by
+    their rank in the generator's numbering, which is monotone in the reference's global numbering
+    (lattice points by (x, y, z), strut-interior nodes beam-major), so send and receive lists agree without
+    communication -- the same contract as :func:`partition_slab`."""
+    from .mesh import synthetic_lattice, mesh_from_synthetic
+    nx = int(n_cells[0])
+    i0, i1 = slab_layers(nx, world)[rank]
+    lat = synthetic_lattice(geom_types, n_cells, radii, cell_size=cell_size, grad_radius=grad_radius,
+                            cell_radii=cell_radii, i_range=(i0 - 1, i1 + 1))
+    mesh = mesh_from_synthetic(lat, elements_per_strut)
+    cs = float(cell_size[0])
+    # cell-plane coordinates exactly as the generator accumulates them (lattice.py:433-442)
+    xs = np.concatenate([[0.0], np.cumsum(np.full(max(nx - 1, 0), cs))])[:nx]
+    cuts = [xs[a] for a, _ in slab_layers(nx, world)] + [xs[nx - 1] + cs]
+    bounds = np.array(cuts, dtype=np.float64)
+    bounds[1:-1] -= 1e-9 * cs                      # a node ON a cut plane belongs to the upper rank on both sides
+    owner = node_owner_by_x(mesh.x, bounds)
+    part = partition_slab(mesh, rank, world, owner=owner, check=False)
+    if any(abs(q - rank) != 1 for q in part.peers):
+        raise ValueError("generate_slab: a strut spans more than one slab; use fewer ranks")
+    lm = local_mesh(mesh, part)
+    lm.meta["lattice"] = lat
+    lm.meta["layers"] = (i0, i1)
+    return lm, part
+
+
+class DistributedFEM:
+    """Slab-sharded assemble + solve.  Two constructors: the plain one takes the GLOBAL mesh (every rank passes the
+    same arrays and keeps only its slab on the GPU; global DOF numbering available for gather / parity checks);
+    :meth:`from_generator` builds only the rank's own slab (``generate_slab``)."""
+
+    def __init__(self, ctx, mesh: BeamMesh, young, nu, rank, world, kappa=0.9, bounds=None, part=None, lmesh=None):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        if part is None:
+            part = partition_slab(mesh, rank, world, bounds)
+            lmesh = local_mesh(mesh, part)
+            self.dofs = local_dofs(part)
+            self.n_dof_global = mesh.n_dof
+            self.n_elem_global = mesh.n_elems
+        else:
+            self.dofs = None
+            self.n_dof_global = self.n_elem_global = None
+        self.part, self.lmesh = part, lmesh
+        self.young, self.nu, self.kappa = young, nu, kappa
+        self.upload()
+
+    @classmethod
+    def from_generator(cls, ctx, geom_types, n_cells, radii, elements_per_strut, young, nu, rank, world, kappa=0.9,
+                       cell_size=(1.0, 1.0, 1.0), grad_radius=None, cell_radii=None):
+        import torch
+        import torch.distributed as dist
+        lm, part = generate_slab(geom_types, n_cells, radii, elements_per_strut, rank, world, cell_size, grad_radius,
+                                 cell_radii)
+        self = cls(ctx, None, young, nu, rank, world, kappa, part=part, lmesh=lm)
+        # global sizes: owned nodes, and elements counted once (by the owner of their first node)
+        cnt = torch.tensor([part.n_owned, int((lm.en0 < part.n_owned).sum())], dtype=torch.int64)
+        if world > 1:
+            cnt = cnt.to(ctx.device) if dist.get_backend() == "nccl" else cnt
+            dist.all_reduce(cnt)
+        self.n_dof_global, self.n_elem_global = 6 * int(cnt[0]), int(cnt[1])
+        return self
+
+    def upload(self):
+        """Host -> device copy of the local mesh, halo lists and the BSR pattern of the local mesh."""
         import torch
         from . import lib as L
         self.torch, self.L = torch, L
-        self.ctx, self.rank, self.world = ctx, rank, world
-        self.part = partition_slab(mesh, rank, world, bounds)
-        self.lmesh = local_mesh(mesh, self.part)
-        self.young, self.nu, self.kappa = young, nu, kappa
+        ctx = self.ctx
         dev = ctx.device
         t = lambda a, d: torch.from_numpy(np.ascontiguousarray(a, dtype=d)).to(dev)
         m = self.lmesh
@@ -169,18 +252,21 @@ class DistributedFEM:
         self.send_idx = t(send, np.int32)
         self.halo = ctx.make_halo(self.part.peers, [len(s) for s in self.part.send_lists], self.part.recv_counts,
                                   self.send_idx, self.n_owned, self.n_local)
-        self.dofs = local_dofs(self.part)
-        self.n_dof_global = mesh.n_dof
-        self.n_elem_global = mesh.n_elems
         # pattern over the local mesh; only the first n_owned block rows are complete and used
         self.rowptr, self.colidx = ctx.bsr_pattern(self.en0, self.en1, self.n_local)
         self.nnzb = int(self.colidx.numel())
         self.nnzb_owned = int(self.rowptr[self.n_owned].item())
         self.vals = None
 
-    def set_bc(self, fixed, g, f):
-        t = lambda a, d: self.torch.from_numpy(np.ascontiguousarray(a[self.dofs], dtype=d)).to(self.ctx.device)
+    def set_bc_local(self, fixed, g, f):
+        """Boundary conditions given directly in the LOCAL numbering [owned | ghosts] (the per-slab path)."""
+        t = lambda a, d: self.torch.from_numpy(np.ascontiguousarray(a, dtype=d)).to(self.ctx.device)
         self.fixed_d, self.g_d, self.f_d = t(fixed, np.uint8), t(g, np.float64), t(f, np.float64)
+
+    def set_bc(self, fixed, g, f):
+        if self.dofs is None:
+            raise ValueError("this DistributedFEM has no global numbering (from_generator): use set_bc_local")
+        self.set_bc_local(fixed[self.dofs], g[self.dofs], f[self.dofs])
 
     def assemble(self, out=None):
         self.vals = self.ctx.assemble_bsr(self.x, self.y, self.z, self.en0, self.en1, self.rad, self.n_local, self.nnzb,

@@ -247,8 +247,13 @@ class SyntheticLattice:
 
 
 def synthetic_lattice(geom_types, n_cells, radii, cell_size=(1.0, 1.0, 1.0),
-                      grad_radius=None, cell_radii=None) -> SyntheticLattice:
+                      grad_radius=None, cell_radii=None, i_range=None) -> SyntheticLattice:
     """Regular lattice arrays in the reference numbering.
+
+    ``i_range = (i_lo, i_hi)`` generates only the cell layers ``i_lo <= i < i_hi`` of the
+    ``n_cells`` lattice (coordinates, radii and ``b_cell`` are those of the full lattice; node and
+    beam indices are ranks WITHIN the generated part, i.e. monotone in the global ones) -- the
+    per-slab generator of the sharded solver (:func:`pylatticedso_b200.distributed.SlabFEM`).
 
     ``geom_types``: name or list of names from :data:`GEOMETRY_TABLES` (or
     ``[E,6]`` arrays of fractional strut coordinates); ``radii``: one base radius
@@ -268,15 +273,19 @@ def synthetic_lattice(geom_types, n_cells, radii, cell_size=(1.0, 1.0, 1.0),
     xs = np.concatenate([[0.0], np.cumsum(np.full(max(nx - 1, 0), cs[0]))])[:nx]
     ys = np.concatenate([[0.0], np.cumsum(np.full(max(ny - 1, 0), cs[1]))])[:ny]
     zs = np.concatenate([[0.0], np.cumsum(np.full(max(nz - 1, 0), cs[2]))])[:nz]
-    ci, cj, ck = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    i_lo, i_hi = (0, nx) if i_range is None else (max(0, int(i_range[0])), min(nx, int(i_range[1])))
+    if i_hi <= i_lo:
+        raise ValueError(f"empty cell-layer range {i_range}")
+    ci, cj, ck = np.meshgrid(np.arange(i_lo, i_hi), np.arange(ny), np.arange(nz), indexing="ij")
     ci, cj, ck = ci.ravel(), cj.ravel(), ck.ravel()            # i-major == cell.index order
+    gcell = (ci * ny + cj) * nz + ck                           # cell.index in the full lattice
     org = np.stack([xs[ci], ys[cj], zs[ck]], axis=1)
     # per-cell radii
     ng = len(tables)
     if cell_radii is not None:
-        cr = np.asarray(cell_radii, dtype=np.float64).reshape(nc, ng)
+        cr = np.asarray(cell_radii, dtype=np.float64).reshape(nc, ng)[gcell]
     else:
-        fac = np.ones(nc)
+        fac = np.ones(gcell.shape[0])
         if grad_radius is not None:
             rule, direction, params = grad_radius
             if rule == "linear":
@@ -296,9 +305,10 @@ def synthetic_lattice(geom_types, n_cells, radii, cell_size=(1.0, 1.0, 1.0),
         e2 = tab[None, :, 3:6] * size[None, None, :] + org[:, None, :]
         ends1.append(e1)
         ends2.append(e2)
-        brad.append(np.repeat(cr[:, g], nbt).reshape(nc, nbt))
-        bcell.append(np.repeat(np.arange(nc), nbt).reshape(nc, nbt))
-        btype.append(np.full((nc, nbt), g))
+        ncl = gcell.shape[0]
+        brad.append(np.repeat(cr[:, g], nbt).reshape(ncl, nbt))
+        bcell.append(np.repeat(gcell, nbt).reshape(ncl, nbt))
+        btype.append(np.full((ncl, nbt), g))
     # creation order: cell-major, then geometry slot, then table row (cell.py:293-382)
     e1 = np.concatenate(ends1, axis=1).reshape(-1, 3)
     e2 = np.concatenate(ends2, axis=1).reshape(-1, 3)

@@ -125,3 +125,35 @@ def test_slab_bounds_from_nodes_never_collapse():
         D.partition_slab(mesh, 0, 64)     # more ranks than x-planes: every rank raises before any collective
     with pytest.raises(ValueError):
         D.slab_bounds(0.0, 1.0, 4, cell=1.0)
+
+
+@pytest.mark.parametrize("geom,ncell,m_,world,grad", [("BCC", (6, 2, 3), 2, 3, None), ("Octet", (5, 2, 2), 1, 2, ("linear", [True, False, True], [0.1, 0, 0.05])),
+                                                      ("BCC", (4, 2, 2), 1, 4, None)])
+def test_per_slab_generation_equals_partition_of_the_global_mesh(geom, ncell, m_, world, grad):
+    """generate_slab builds only the rank's cell layers (+1 overlap layer); the local mesh, the halo lists and the
+    boundary conditions must be IDENTICAL to what partition_slab extracts from the global mesh with cuts on the same
+    cell planes -- including the first-creator radius rule on graded lattices."""
+    from pylatticedso_b200 import distributed as D
+    from pylatticedso_b200 import mesh as M
+    lat = M.synthetic_lattice(geom, ncell, [0.04], grad_radius=grad)
+    mesh = M.mesh_from_synthetic(lat, m_)
+    fixed, g, f = M.compression_bc(mesh)
+    layers = D.slab_layers(ncell[0], world)
+    bounds = np.array([float(a) for a, _ in layers] + [float(ncell[0])])
+    bounds[1:-1] -= 1e-9
+    owner = D.node_owner_by_x(mesh.x, bounds)
+    n_owned_total = 0
+    for r in range(world):
+        ref_part = D.partition_slab(mesh, r, world, owner=owner)
+        ref_lm = D.local_mesh(mesh, ref_part)
+        lm, part = D.generate_slab(geom, ncell, [0.04], m_, r, world, grad_radius=grad)
+        for k in ("x", "y", "z", "en0", "en1", "rad"):
+            assert np.array_equal(getattr(lm, k), getattr(ref_lm, k)), (r, k)
+        assert part.peers == ref_part.peers and part.recv_counts == ref_part.recv_counts
+        assert all(np.array_equal(a, b) for a, b in zip(part.send_lists, ref_part.send_lists))
+        assert (part.n_owned, part.n_local) == (ref_part.n_owned, ref_part.n_local)
+        dofs = D.local_dofs(ref_part)
+        fl, gl, fl2 = D.compression_bc_local(lm)
+        assert np.array_equal(fl, fixed[dofs]) and np.array_equal(gl, g[dofs]) and np.array_equal(fl2, f[dofs])
+        n_owned_total += part.n_owned
+    assert n_owned_total == mesh.n_nodes
