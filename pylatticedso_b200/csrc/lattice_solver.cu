@@ -1110,6 +1110,87 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
   return LAT_OK;
 }
 
+// ---------------------------------------------------------------------------
+// persistent on-chip PCG (pcg_persist.cuh): host side
+// ---------------------------------------------------------------------------
+#include "pcg_persist.cuh"
+
+// Returns LAT_OK with *used = true when the solve ran in the persistent kernel; *used = false (and LAT_OK) when the
+// system does not fit the shared memory of the device or cooperative launch is unavailable -- the caller then
+// runs the three-kernel iteration.
+template <int PC>
+static int pcg_run_persist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, const double* vals,
+                           int64_t n_nodes, const double* b, double* x, const lat_pcg_opts* o, lat_pcg_result* res,
+                           bool* used) {
+  *used = false;
+  int coop = 0, smem_optin = 0;
+  LAT_CUDA(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+  LAT_CUDA(ctx, cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+  if (!coop || n_nodes >= (int64_t)INT32_MAX / 8) return LAT_OK;
+  const int G = ctx->sm_count;
+  // cheap size screen before any work: 5 vectors of the average CTA must fit at all
+  if ((double)n_nodes / G * 6 * 8 * PERSIST_NVEC > (double)smem_optin) return LAT_OK;
+  int32_t* cta_row0 = lat_buf<int32_t>(ctx, "persist_row0", (size_t)G + 2);
+  int32_t* maxima = lat_buf<int32_t>(ctx, "persist_max", 4);
+  if (!cta_row0 || !maxima) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+  LAT_CUDA(ctx, cudaMemsetAsync(maxima, 0, 4 * sizeof(int32_t), ctx->stream));
+  LAT_LAUNCH(ctx, k_persist_partition, (unsigned)ceil_div(G + 1, 128), 128, 0, rowptr, n_nodes, G, cta_row0, maxima);
+  LAT_LAUNCH(ctx, k_persist_maxima, (unsigned)ceil_div(G, 128), 128, 0, rowptr, cta_row0, G, maxima);
+  int32_t hmax[2] = {0, 0};
+  LAT_CUDA(ctx, cudaMemcpyAsync(hmax, maxima, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const int rows_cap = hmax[0] > 0 ? hmax[0] : 1, blk_cap = hmax[1] > 0 ? hmax[1] : 1;
+  const size_t smem = (size_t)PERSIST_NVEC * rows_cap * 48 + (size_t)3 * G * 8 + (size_t)(rows_cap + 1) * 4 + (size_t)blk_cap * 4 + 16;
+  if (smem + 2048 > (size_t)smem_optin) return LAT_OK;     // does not fit on chip: three-kernel path
+  LAT_CUDA(ctx, cudaFuncSetAttribute(k_pcg_persist<PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  LAT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_persist<PC>, PERSIST_BLOCK, smem));
+  if (per_sm < 1) return LAT_OK;
+
+  const int64_t n = 6 * n_nodes;
+  double* u = lat_buf<double>(ctx, "pcg_z", n);
+  double* dinv = lat_buf<double>(ctx, "pcg_dinv", PC == LAT_PC_BLOCK6 ? 21 * n_nodes : n);
+  PcgScalars* sc = lat_buf<PcgScalars>(ctx, "pcg_scalars", 1);
+  unsigned long long* mail = lat_buf<unsigned long long>(ctx, "persist_mail", (size_t)G * 8);
+  unsigned int* flags = lat_buf<unsigned int>(ctx, "persist_flags", (size_t)G);
+  if (!u || !dinv || !sc || !mail || !flags) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+  const int64_t launches0 = ctx->launches - 2;
+  LAT_CUDA(ctx, cudaMemsetAsync(sc, 0, sizeof(PcgScalars), ctx->stream));
+  LAT_CUDA(ctx, cudaMemsetAsync(mail, 0, (size_t)G * 8 * sizeof(unsigned long long), ctx->stream));
+  LAT_CUDA(ctx, cudaMemsetAsync(flags, 0, (size_t)G * sizeof(unsigned int), ctx->stream));
+  if (PC != LAT_PC_NONE)
+    LAT_LAUNCH(ctx, k_precond_setup, (unsigned)ceil_div(n_nodes, 128), 128, 0, rowptr, colidx, vals, n_nodes, PC, dinv);
+  PersistArgs a;
+  a.rowptr = rowptr; a.colidx = colidx; a.vals = vals; a.n_nodes = n_nodes; a.b = b; a.x = x; a.u = u; a.dinv = dinv;
+  a.sc = sc;
+  a.prm.tol = o->tol; a.prm.mintol = 0.0; a.prm.alpha_max = 0.0; a.prm.restart_every = 0; a.prm.maxiter = o->maxiter;
+  a.prm.reference = 0; a.prm.dist = 0; a.prm.pad = 0; a.prm.seq_base = 0; a.prm.push_base = 0;
+  a.mail = mail; a.flags = flags; a.cta_row0 = cta_row0; a.rows_cap = rows_cap; a.blk_cap = blk_cap;
+  void* kargs[] = {&a};
+  LAT_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+  LAT_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_pcg_persist<PC>, dim3(G), dim3(PERSIST_BLOCK), kargs, smem, ctx->stream));
+  ctx->launches++;
+  LAT_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+  PcgScalars* hs = ctx->h_scal;
+  LAT_CUDA(ctx, cudaMemcpyAsync(&hs[0], sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, ctx->stream));
+  LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+  res->iters = hs[0].iters;
+  res->norm_b = sqrt(hs[0].bb);
+  res->relres = hs[0].bb > 0.0 ? sqrt(hs[0].rr / hs[0].bb) : 0.0;
+  res->info = hs[0].done && !hs[0].breakdown ? 0 : (hs[0].breakdown == 2 ? 4 : (hs[0].breakdown == 3 ? 5 : (hs[0].breakdown ? 3 : 1)));
+  res->solve_ms = ms;
+  res->launches = ctx->launches - launches0;
+  res->spmv_ms = 0.0;
+  res->update_ms = 0.0;
+  res->profiled = 0;
+  res->reserved = hs[0].restarts | 0x200;    // bit 9: solved by the persistent on-chip kernel
+  res->true_relres = (hs[0].true_rr >= 0.0 && hs[0].bb > 0.0) ? sqrt(hs[0].true_rr / hs[0].bb) : -1.0;
+  *used = true;
+  return LAT_OK;
+}
+
 extern "C" int lat_pcg_bsr(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, const double* vals,
                            int64_t n_nodes, const double* b, double* x, const lat_pcg_opts* opts,
                            lat_pcg_result* result) {
@@ -1117,6 +1198,20 @@ extern "C" int lat_pcg_bsr(lat_ctx* ctx, const int32_t* rowptr, const int32_t* c
   LAT_CHECK_ARG(ctx, rowptr && colidx && vals && b && x && opts && result && n_nodes > 0);
   LAT_CHECK_ARG(ctx, opts->maxiter >= 0 && opts->tol >= 0.0);
   LAT_CUDA(ctx, cudaSetDevice(ctx->device));
+  // Textbook mode, nothing experimental requested: try the persistent on-chip kernel first (bit 7 of `reserved`
+  // opts out; profile_iters > 0 asks for per-kernel timings, which only the three-kernel iteration has).
+  const bool want_persist = !opts->reference_semantics && !(opts->reserved & (2 | 8 | 128)) && opts->profile_iters <= 0;
+  if (want_persist) {
+    bool used = false;
+    int rc = LAT_OK;
+    switch (opts->precond) {
+      case LAT_PC_NONE: rc = pcg_run_persist<LAT_PC_NONE>(ctx, rowptr, colidx, vals, n_nodes, b, x, opts, result, &used); break;
+      case LAT_PC_JACOBI: rc = pcg_run_persist<LAT_PC_JACOBI>(ctx, rowptr, colidx, vals, n_nodes, b, x, opts, result, &used); break;
+      case LAT_PC_BLOCK6: rc = pcg_run_persist<LAT_PC_BLOCK6>(ctx, rowptr, colidx, vals, n_nodes, b, x, opts, result, &used); break;
+      default: return lat_fail(ctx, LAT_ERR_ARG, "unknown preconditioner", __FILE__, __LINE__);
+    }
+    if (rc != LAT_OK || used) return rc;
+  }
   switch (opts->precond) {
     case LAT_PC_NONE: return pcg_run<LAT_PC_NONE>(ctx, rowptr, colidx, vals, n_nodes, b, x, opts, result);
     case LAT_PC_JACOBI: return pcg_run<LAT_PC_JACOBI>(ctx, rowptr, colidx, vals, n_nodes, b, x, opts, result);

@@ -17,6 +17,7 @@ _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "liblattice_b200.so")
 SOURCES = ["lattice_core.cu", "lattice_solver.cu", "lattice_schur.cu"]
 HEADERS = [os.path.join(_HERE, "csrc", "common.cuh"), os.path.join(_HERE, "csrc", "matfree.cuh"),
+           os.path.join(_HERE, "csrc", "pcg_persist.cuh"),
            os.path.join(_ROOT, "include", "lattice_b200.h")]
 
 ASM_GATHER, ASM_ATOMIC, ASM_ROWS = 0, 1, 2
@@ -251,18 +252,22 @@ class Context:
 
     def pcg(self, rowptr, colidx, vals, b, x=None, tol=1e-8, maxiter=10000, precond=PC_JACOBI,
             reference_semantics=False, mintol=0.0, alpha_max=0.0, restart_every=0, check_every=0,
-            profile_iters=0, tma_spmv=False, classic=False, debug=0):
+            profile_iters=0, tma_spmv=False, classic=False, debug=0, persistent=True):
+        """``persistent=True`` (default): systems whose vectors fit the GPU's shared memory are solved by ONE
+        persistent cooperative kernel (csrc/pcg_persist.cuh; ``info['persistent']``); larger ones, reference
+        semantics and profiled runs use the three-kernel iteration."""
         import torch
         if x is None:
             x = torch.empty_like(b)
         o = PcgOpts(tol, mintol, alpha_max, restart_every, maxiter, precond, int(reference_semantics), check_every,
-                    profile_iters, (2 if tma_spmv else 0) | (8 if classic else 0) | (debug << 8))
+                    profile_iters, (2 if tma_spmv else 0) | (8 if classic else 0) | (0 if persistent else 128) | (debug << 8))
         r = PcgResult()
         self.check(self.lib.lat_pcg_bsr(self.h, _ptr(rowptr), _ptr(colidx), _ptr(vals), rowptr.numel() - 1, _ptr(b),
                                         _ptr(x), C.byref(o), C.byref(r)))
         return x, dict(iters=r.iters, info=r.info, relres=r.relres, norm_b=r.norm_b, solve_ms=r.solve_ms,
                        launches=r.launches, spmv_ms=r.spmv_ms, update_ms=r.update_ms, profiled=r.profiled,
-                       true_relres=r.true_relres, restarts=r.reserved & 0xff, graph=bool(r.reserved & 0x100))
+                       true_relres=r.true_relres, restarts=r.reserved & 0xff, graph=bool(r.reserved & 0x100),
+                       persistent=bool(r.reserved & 0x200))
 
     # ---- matrix-free operator (resident in the context; needs bsr_pattern() of the same mesh) ----
     def matfree_setup(self, x, y, z, en0, en1, rad, n_nodes, young, nu, kappa=0.9, fixed=None):

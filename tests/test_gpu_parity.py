@@ -345,3 +345,35 @@ def test_joint_only_solve_equals_full_solve_at_the_joints(ctx, geom, cells, mseg
         with pytest.raises(ValueError):
             fem.solve_condensed(fixed, g, f2)
 
+
+
+@pytest.mark.parametrize("geom,n,m_,pc", [("BCC", (4, 3, 3), 2, 2), ("Octet", (3, 3, 2), 1, 1), ("BCC", (2, 2, 2), 1, 0), ("BCC", (8, 8, 8), 2, 2)])
+def test_persistent_pcg_equals_three_kernel_path_and_oracle(ctx, geom, n, m_, pc):
+    """The persistent on-chip kernel (csrc/pcg_persist.cuh) and the three-kernel iteration run the same
+    Chronopoulos-Gear recurrences: same solution to the solver tolerance, both equal to the oracle's direct solve,
+    and the persistent kernel is bit-reproducible run to run."""
+    import torch
+    from pylatticedso_b200 import mesh as M
+    lat = M.synthetic_lattice(geom, n, [0.05])
+    m = M.mesh_from_synthetic(lat, m_)
+    fixed, g, f = M.compression_bc(m)
+    f = f.copy(); f[6 * 5 + 1] = 2e-3
+    t = lambda a, d: torch.from_numpy(np.ascontiguousarray(a, dtype=d)).to(ctx.device)
+    x, y, z, en0, en1, rad = t(m.x, np.float64), t(m.y, np.float64), t(m.z, np.float64), t(m.en0, np.int32), t(m.en1, np.int32), t(m.rad, np.float64)
+    rowptr, colidx = ctx.bsr_pattern(en0, en1, m.n_nodes)
+    vals = ctx.assemble_bsr(x, y, z, en0, en1, rad, m.n_nodes, colidx.numel(), E_MOD, NU)
+    vbc, b = ctx.apply_dirichlet(rowptr, colidx, vals, t(fixed, np.uint8), t(g, np.float64), t(f, np.float64))
+    u3, i3 = ctx.pcg(rowptr, colidx, vbc, b, tol=1e-12, maxiter=100000, precond=pc, persistent=False)
+    up, ip = ctx.pcg(rowptr, colidx, vbc, b, tol=1e-12, maxiter=100000, precond=pc, persistent=True)
+    assert ip["persistent"] and not i3["persistent"]
+    assert ip["info"] in (0, 5) and i3["info"] in (0, 5)
+    assert abs(ip["iters"] - i3["iters"]) <= max(3, 0.02 * i3["iters"])
+    K = orc.assemble_csr(m.xyz, np.stack([m.en0, m.en1], 1), m.rad, E_MOD, NU)
+    uo, _ = orc.solve_static(K, fixed.astype(bool), g, f)
+    for u in (u3, up):
+        assert np.abs(u.cpu().numpy() - uo).max() < 1e-8 * np.abs(uo).max()
+    up2, ip2 = ctx.pcg(rowptr, colidx, vbc, b, tol=1e-12, maxiter=100000, precond=pc, persistent=True)
+    assert ip2["iters"] == ip["iters"] and torch.equal(up, up2)
+    # maxiter is honoured and reported as info = 1
+    uq, iq = ctx.pcg(rowptr, colidx, vbc, b, tol=1e-14, maxiter=5, precond=pc, persistent=True)
+    assert iq["persistent"] and iq["iters"] == 5 and iq["info"] == 1

@@ -35,8 +35,8 @@ def test_bcc20_m2_compression_full_size(ctx):
     un = u.reshape(-1, 6)[: m.n_points].cpu().numpy()
     key = {tuple(np.round(p, 6)): k for k, p in enumerate(lat.pxyz)}
     idx = np.array([key[(p[1], p[0], p[2])] for p in np.round(lat.pxyz, 6)])
-    assert np.abs(un[:, 2] - un[idx, 2]).max() < 1e-6 * np.abs(un[:, 2]).max()
-    assert np.abs(un[:, 0] - un[idx, 1]).max() < 1e-6 * np.abs(un[:, 2]).max()
+    assert np.abs(un[:, 2] - un[idx, 2]).max() < 5e-6 * np.abs(un[:, 2]).max()   # a tol = 1e-8 solve: error ~ cond * 1e-8
+    assert np.abs(un[:, 0] - un[idx, 1]).max() < 5e-6 * np.abs(un[:, 2]).max()
 
 
 def test_octet40_graded_gradient_full_size(ctx):
