@@ -29,6 +29,68 @@ __device__ __forceinline__ double dot6(const double2& a0, const double2& a1, con
   return acc;
 }
 
+
+// ---------------------------------------------------------------------------
+// "Transposed piece" mapping of a 6x6 block onto the six lanes of a row group (round 2).
+// A block is 18 pieces of 16 bytes (piece p = scalar row p/3, column pair p%3).  Lane r of the group loads pieces
+// r, 6+r, 12+r: the six lanes together read 96 CONTIGUOUS bytes per instruction (the row-per-lane mapping read
+// 6 x 16 B at stride 48 B = three 128-byte lines per block and instruction, which made the product kernels L1-wavefront
+// bound: profiles/r02_persist_ncu.txt), and every lane needs only ONE 16-byte piece of x (column pair c = r%3)
+// instead of all 48 bytes.  The lane accumulates partial sums of scalar rows h, 2+h, 4+h (h = r/3) over the blocks of the
+// row; at the end of the row the three lanes with the same h are added in a fixed order and lane (h, c) keeps the
+// total of scalar row 2c+h.  16 instead of 24 registers per block in flight, ~6 instead of ~13 L1 wavefronts per block.
+// ---------------------------------------------------------------------------
+struct Piece3 { double2 a0, a1, a2, x; };
+__device__ __forceinline__ int lane_dof(int r) { return 2 * (r % 3) + r / 3; }   // scalar row the lane ends up owning
+template <bool STREAM>
+__device__ __forceinline__ Piece3 piece_load(const double* __restrict__ vals, int64_t j, int r, const double* xcol, int c) {
+  Piece3 q;
+  const double2* vp = reinterpret_cast<const double2*>(vals + j * 36 + 2 * r);
+  if (STREAM) { q.a0 = __ldcs(vp); q.a1 = __ldcs(vp + 6); q.a2 = __ldcs(vp + 12); }
+  else { q.a0 = __ldg(vp); q.a1 = __ldg(vp + 6); q.a2 = __ldg(vp + 12); }
+  q.x = *reinterpret_cast<const double2*>(xcol + 2 * c);
+  return q;
+}
+__device__ __forceinline__ void piece_fma(const Piece3& q, double& s0, double& s1, double& s2) {
+  s0 = fma(q.a0.x, q.x.x, s0); s0 = fma(q.a0.y, q.x.y, s0);
+  s1 = fma(q.a1.x, q.x.x, s1); s1 = fma(q.a1.y, q.x.y, s1);
+  s2 = fma(q.a2.x, q.x.x, s2); s2 = fma(q.a2.y, q.x.y, s2);
+}
+// All 32 lanes call.  Returns the total of the scalar row lane_dof(r) of the lane's node.
+__device__ __forceinline__ double piece_finish(int g, int r, double s0, double s1, double s2) {
+  const int h = r / 3, c = r - 3 * h;
+  const int base = (g < 5 ? g : 4) * 6 + 3 * h;
+  const double a0 = __shfl_sync(0xffffffffu, s0, base), a1 = __shfl_sync(0xffffffffu, s0, base + 1), a2 = __shfl_sync(0xffffffffu, s0, base + 2);
+  const double b0 = __shfl_sync(0xffffffffu, s1, base), b1 = __shfl_sync(0xffffffffu, s1, base + 1), b2 = __shfl_sync(0xffffffffu, s1, base + 2);
+  const double c0 = __shfl_sync(0xffffffffu, s2, base), c1 = __shfl_sync(0xffffffffu, s2, base + 1), c2 = __shfl_sync(0xffffffffu, s2, base + 2);
+  const double t0 = (a0 + a1) + a2, t1 = (b0 + b1) + b2, t2 = (c0 + c1) + c2;
+  return c == 0 ? t0 : (c == 1 ? t1 : t2);
+}
+// acc over the blocks [lo, hi) of one block row, three blocks (all loads first) per trip.  NC: gather x past L1.
+template <bool STREAM, bool CG_GATHER>
+__device__ __forceinline__ void piece_row(const int32_t* colidx, const double* __restrict__ vals, int lo, int hi,
+                                          int r, const double* x, double& s0, double& s1, double& s2) {
+  const int c = r % 3;
+  for (int j = lo; j < hi; j += 3) {
+    const bool p1 = j + 1 < hi, p2 = j + 2 < hi;
+    const int j1 = p1 ? j + 1 : j, j2 = p2 ? j + 2 : j;
+    const int c0 = colidx[j], c1 = colidx[j1], c2 = colidx[j2];   // global (read-only path) or shared memory
+    Piece3 q0, q1, q2;
+    if (CG_GATHER) {
+      q0 = piece_load<STREAM>(vals, j, r, x, 0);  q0.x = __ldcg(reinterpret_cast<const double2*>(x + (int64_t)c0 * 6 + 2 * c));
+      q1 = piece_load<STREAM>(vals, j1, r, x, 0); q1.x = __ldcg(reinterpret_cast<const double2*>(x + (int64_t)c1 * 6 + 2 * c));
+      q2 = piece_load<STREAM>(vals, j2, r, x, 0); q2.x = __ldcg(reinterpret_cast<const double2*>(x + (int64_t)c2 * 6 + 2 * c));
+    } else {
+      q0 = piece_load<STREAM>(vals, j, r, x + (int64_t)c0 * 6, c);
+      q1 = piece_load<STREAM>(vals, j1, r, x + (int64_t)c1 * 6, c);
+      q2 = piece_load<STREAM>(vals, j2, r, x + (int64_t)c2 * 6, c);
+    }
+    piece_fma(q0, s0, s1, s2);
+    if (p1) piece_fma(q1, s0, s1, s2);
+    if (p2) piece_fma(q2, s0, s1, s2);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // plain y = A x
 // ---------------------------------------------------------------------------
@@ -40,19 +102,13 @@ __global__ void __launch_bounds__(SPMV_BLOCK) k_bsr_spmv(const int32_t* __restri
   const int g = lane / 6, r = lane - g * 6;
   const int64_t warp = (int64_t)blockIdx.x * (SPMV_BLOCK / 32) + (threadIdx.x >> 5);
   const int64_t n = warp * ROWS_PER_WARP + g;
-  if (g >= ROWS_PER_WARP || n >= n_nodes) return;
-  const int lo = rowptr[n], hi = rowptr[n + 1];
-  double acc = 0.0;
-#pragma unroll 4
-  for (int j = lo; j < hi; ++j) {
-    const int c = __ldg(colidx + j);
-    const double2* vp = reinterpret_cast<const double2*>(vals + (int64_t)j * 36 + r * 6);
-    const double2* xp = reinterpret_cast<const double2*>(x + (int64_t)c * 6);
-    const double2 a0 = __ldcs(vp), a1 = __ldcs(vp + 1), a2 = __ldcs(vp + 2);  // streamed once: evict-first
-    const double2 x0 = __ldg(xp), x1 = __ldg(xp + 1), x2 = __ldg(xp + 2);
-    acc = dot6(a0, a1, a2, x0, x1, x2, acc);
-  }
-  y[n * 6 + r] = acc;
+  const bool active = g < ROWS_PER_WARP && n < n_nodes;
+  int lo = 0, hi = 0;
+  if (active) { lo = rowptr[n]; hi = rowptr[n + 1]; }
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  piece_row<true, false>(colidx, vals, lo, hi, r, x, s0, s1, s2);      // matrix streamed once: evict-first
+  const double tot = piece_finish(g, r, s0, s1, s2);
+  if (active) y[n * 6 + lane_dof(r)] = tot;
 }
 
 int lat_spmv_internal(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, const double* vals,
@@ -496,7 +552,7 @@ const int32_t* __restrict__ rowptr,
   // independent loads first: the row extent and the own-row entries do not depend on the status word
   int lo = 0, hi = 0;
   double uo = 0.0, ro = 0.0;
-  const int64_t i = n * 6 + rr_;
+  const int64_t i = n * 6 + lane_dof(rr_);     // the scalar row this lane owns in the transposed-piece mapping
   if (active) { lo = __ldg(rowptr + n); hi = __ldg(rowptr + n + 1); uo = u[i]; ro = r[i]; }
   if (sc->done || sc->iters >= prm.maxiter) return;
   int need_row = 0;
@@ -507,28 +563,10 @@ const int32_t* __restrict__ rowptr,
       halo_wait(rs, cta_need, sc, prm);
     }
   }
-  double acc = 0.0;
-  if (GHOST && need_row) {
-    // a row that reads ghosts: every column past L1 (the sector at the owned/ghost border may be stale there)
-    for (int j = lo; j < hi; ++j) {
-      const int c = __ldg(colidx + j);
-      const double2* vp = reinterpret_cast<const double2*>(vals + (int64_t)j * 36 + rr_ * 6);
-      const double2* xp = reinterpret_cast<const double2*>(u + (int64_t)c * 6);
-      const double2 a0 = __ldcs(vp), a1 = __ldcs(vp + 1), a2 = __ldcs(vp + 2);
-      const double2 x0 = __ldcg(xp), x1 = __ldcg(xp + 1), x2 = __ldcg(xp + 2);
-      acc = dot6(a0, a1, a2, x0, x1, x2, acc);
-    }
-  } else {
-#pragma unroll 4
-    for (int j = lo; j < hi; ++j) {
-      const int c = __ldg(colidx + j);
-      const double2* vp = reinterpret_cast<const double2*>(vals + (int64_t)j * 36 + rr_ * 6);
-      const double2* xp = reinterpret_cast<const double2*>(u + (int64_t)c * 6);
-      const double2 a0 = __ldcs(vp), a1 = __ldcs(vp + 1), a2 = __ldcs(vp + 2);
-      const double2 x0 = xp[0], x1 = xp[1], x2 = xp[2];
-      acc = dot6(a0, a1, a2, x0, x1, x2, acc);
-    }
-  }
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  if (GHOST && need_row) piece_row<true, true>(colidx, vals, lo, hi, rr_, u, s0, s1, s2);   // ghost-reading row: gathers past L1
+  else piece_row<true, false>(colidx, vals, lo, hi, rr_, u, s0, s1, s2);
+  const double acc = piece_finish(g, rr_, s0, s1, s2);
   if (active) w[i] = acc;
   double v[3] = {ro * uo, acc * uo, ro * ro};
   block_partials<3, SPMV_BLOCK>(v, partials, rs.p_stride, rs.p_offset);
@@ -1127,21 +1165,28 @@ static int pcg_run_persist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* c
   LAT_CUDA(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
   LAT_CUDA(ctx, cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
   if (!coop || n_nodes >= (int64_t)INT32_MAX / 8) return LAT_OK;
-  const int G = ctx->sm_count;
+  const int G = ctx->sm_count < PERSIST_INBOX_STRIDE ? ctx->sm_count : PERSIST_INBOX_STRIDE;
   // cheap size screen before any work: 5 vectors of the average CTA must fit at all
-  if ((double)n_nodes / G * 6 * 8 * PERSIST_NVEC > (double)smem_optin) return LAT_OK;
-  int32_t* cta_row0 = lat_buf<int32_t>(ctx, "persist_row0", (size_t)G + 2);
+  if ((double)n_nodes / G * (PERSIST_NVEC * 48 + persist_pc_width(PC) * 8) > (double)smem_optin) return LAT_OK;
+  if ((n_nodes + PERSIST_CHUNK - 1) / PERSIST_CHUNK > (int64_t)64 * G) return LAT_OK;   // s_chunk_base holds 64 chunks per CTA
   int32_t* maxima = lat_buf<int32_t>(ctx, "persist_max", 4);
-  if (!cta_row0 || !maxima) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+  if (!maxima) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
   LAT_CUDA(ctx, cudaMemsetAsync(maxima, 0, 4 * sizeof(int32_t), ctx->stream));
-  LAT_LAUNCH(ctx, k_persist_partition, (unsigned)ceil_div(G + 1, 128), 128, 0, rowptr, n_nodes, G, cta_row0, maxima);
-  LAT_LAUNCH(ctx, k_persist_maxima, (unsigned)ceil_div(G, 128), 128, 0, rowptr, cta_row0, G, maxima);
+  LAT_LAUNCH(ctx, k_persist_caps, (unsigned)ceil_div(G, 128), 128, 0, rowptr, n_nodes, G, maxima);
   int32_t hmax[2] = {0, 0};
   LAT_CUDA(ctx, cudaMemcpyAsync(hmax, maxima, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   const int rows_cap = hmax[0] > 0 ? hmax[0] : 1, blk_cap = hmax[1] > 0 ? hmax[1] : 1;
-  const size_t smem = (size_t)PERSIST_NVEC * rows_cap * 48 + (size_t)3 * G * 8 + (size_t)(rows_cap + 1) * 4 + (size_t)blk_cap * 4 + 16;
-  if (smem + 2048 > (size_t)smem_optin) return LAT_OK;     // does not fit on chip: three-kernel path
+  // Shared memory and L1 share 256 KB per SM, and the product phase needs its L1: the preconditioner rows are
+  // cached on chip only while the total stays below ~160 KB (LAT_PERSIST_PCSMEM_KB overrides the limit).
+  const size_t smem_base = (size_t)rows_cap * (PERSIST_NVEC * 48) + (size_t)3 * G * 8 + (size_t)(2 * rows_cap + 1) * 4 +
+                           (size_t)blk_cap * 4 + 32;
+  const size_t smem_pc = (size_t)rows_cap * persist_pc_width(PC) * 8;
+  const char* env_kb = getenv("LAT_PERSIST_PCSMEM_KB");
+  const size_t pc_limit = (size_t)(env_kb ? atoi(env_kb) : 160) * 1024;
+  const bool pc_smem = smem_base + smem_pc + 2560 <= (size_t)smem_optin && smem_base + smem_pc <= pc_limit;
+  const size_t smem = smem_base + (pc_smem ? smem_pc : 0);
+  if (smem + 2560 > (size_t)smem_optin) return LAT_OK;     // does not fit on chip: three-kernel path
   LAT_CUDA(ctx, cudaFuncSetAttribute(k_pcg_persist<PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   LAT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_persist<PC>, PERSIST_BLOCK, smem));
@@ -1152,12 +1197,12 @@ static int pcg_run_persist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* c
   double* dinv = lat_buf<double>(ctx, "pcg_dinv", PC == LAT_PC_BLOCK6 ? 21 * n_nodes : n);
   PcgScalars* sc = lat_buf<PcgScalars>(ctx, "pcg_scalars", 1);
   unsigned long long* mail = lat_buf<unsigned long long>(ctx, "persist_mail", (size_t)G * 8);
-  unsigned int* flags = lat_buf<unsigned int>(ctx, "persist_flags", (size_t)G);
+  unsigned int* flags = lat_buf<unsigned int>(ctx, "persist_flags", (size_t)G * PERSIST_INBOX_STRIDE);
   if (!u || !dinv || !sc || !mail || !flags) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
-  const int64_t launches0 = ctx->launches - 2;
+  const int64_t launches0 = ctx->launches - 1;
   LAT_CUDA(ctx, cudaMemsetAsync(sc, 0, sizeof(PcgScalars), ctx->stream));
   LAT_CUDA(ctx, cudaMemsetAsync(mail, 0, (size_t)G * 8 * sizeof(unsigned long long), ctx->stream));
-  LAT_CUDA(ctx, cudaMemsetAsync(flags, 0, (size_t)G * sizeof(unsigned int), ctx->stream));
+  LAT_CUDA(ctx, cudaMemsetAsync(flags, 0, (size_t)G * PERSIST_INBOX_STRIDE * sizeof(unsigned int), ctx->stream));
   if (PC != LAT_PC_NONE)
     LAT_LAUNCH(ctx, k_precond_setup, (unsigned)ceil_div(n_nodes, 128), 128, 0, rowptr, colidx, vals, n_nodes, PC, dinv);
   PersistArgs a;
@@ -1165,7 +1210,16 @@ static int pcg_run_persist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* c
   a.sc = sc;
   a.prm.tol = o->tol; a.prm.mintol = 0.0; a.prm.alpha_max = 0.0; a.prm.restart_every = 0; a.prm.maxiter = o->maxiter;
   a.prm.reference = 0; a.prm.dist = 0; a.prm.pad = 0; a.prm.seq_base = 0; a.prm.push_base = 0;
-  a.mail = mail; a.flags = flags; a.cta_row0 = cta_row0; a.rows_cap = rows_cap; a.blk_cap = blk_cap;
+  a.mail = mail; a.flags = flags; a.rows_cap = rows_cap; a.blk_cap = blk_cap; a.pc_smem = pc_smem ? 1 : 0;
+  a.trace = nullptr;
+  a.trace_iters = 0;
+  const char* env_tr = getenv("LAT_PERSIST_TRACE");     // LAT_PERSIST_TRACE=n: phase breakdown of the first n iterations on stderr
+  if (env_tr && atoi(env_tr) > 0) {
+    a.trace_iters = atoi(env_tr) > 256 ? 256 : atoi(env_tr);
+    a.trace = lat_buf<long long>(ctx, "persist_trace", (size_t)G * a.trace_iters * 9 + 2 * G);
+    if (!a.trace) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+    LAT_CUDA(ctx, cudaMemsetAsync(a.trace, 0, ((size_t)G * a.trace_iters * 9 + 2 * G) * sizeof(long long), ctx->stream));
+  }
   void* kargs[] = {&a};
   LAT_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
   LAT_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_pcg_persist<PC>, dim3(G), dim3(PERSIST_BLOCK), kargs, smem, ctx->stream));
@@ -1176,6 +1230,54 @@ static int pcg_run_persist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* c
   LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+  if (a.trace) {
+    std::vector<long long> tr((size_t)G * a.trace_iters * 9 + 2 * G);
+    cudaMemcpy(tr.data(), a.trace, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    int clk_khz = 1;
+    cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, ctx->device);
+    const int n_it = hs[0].iters < a.trace_iters ? hs[0].iters : a.trace_iters;
+    double fine[5] = {0, 0, 0, 0, 0}; double sum[4] = {0, 0, 0, 0}, prod_min = 0, prod_max = 0, upd_min = 0, upd_max = 0;
+    int cnt = 0;
+    for (int it = 2; it < n_it; ++it) {
+      double pmin = 1e30, pmax = 0, umin = 1e30, umax = 0;
+      for (int c = 0; c < G; ++c) {
+        const long long* t = &tr[((size_t)c * a.trace_iters + it) * 9];
+        if (!t[4]) continue;
+        const double d[4] = {(double)(t[1] - t[0]), (double)(t[2] - t[1]), (double)(t[3] - t[2]), (double)(t[4] - t[3])};
+        for (int k = 0; k < 4; ++k) sum[k] += d[k];
+        fine[0] += (double)(t[5] - t[3]); fine[1] += (double)(t[6] - t[5]); fine[2] += (double)(t[7] - t[6]); fine[3] += (double)(t[8] - t[7]); fine[4] += (double)(t[4] - t[8]);
+        pmin = d[0] < pmin ? d[0] : pmin; pmax = d[0] > pmax ? d[0] : pmax;
+        umin = d[2] < umin ? d[2] : umin; umax = d[2] > umax ? d[2] : umax;
+        ++cnt;
+      }
+      prod_min += pmin; prod_max += pmax; upd_min += umin; upd_max += umax;
+    }
+    const double us = 1e3 / (double)clk_khz;   // cycles -> us at the nominal SM clock
+    if (const char* fn = getenv("LAT_PERSIST_TRACE_FILE")) {   // per-CTA means: cta rows blocks product_us update_us
+      if (FILE* fp = fopen(fn, "w")) {
+        for (int c = 0; c < G; ++c) {
+          double p = 0, u2 = 0; int k = 0;
+          for (int it = 2; it < n_it; ++it) {
+            const long long* t = &tr[((size_t)c * a.trace_iters + it) * 9];
+            if (!t[4]) continue;
+            p += (double)(t[1] - t[0]); u2 += (double)(t[3] - t[2]); ++k;
+          }
+          fprintf(fp, "%d %lld %lld %.3f %.3f\n", c, tr[(size_t)G * a.trace_iters * 9 + 2 * c], tr[(size_t)G * a.trace_iters * 9 + 2 * c + 1],
+                  k ? p / k * us : 0.0, k ? u2 / k * us : 0.0);
+        }
+        fclose(fp);
+      }
+    }
+    const int nit = n_it > 2 ? n_it - 2 : 1;
+    if (cnt > 0)
+      fprintf(stderr, "[lat persist trace] mean over %d CTAs x %d iterations (us at %.0f MHz): product %.2f (fastest CTA %.2f, slowest %.2f) | "
+                      "reduce/barrier B %.2f | update %.2f (fastest %.2f, slowest %.2f) | barrier A %.2f\n",
+              G, nit, clk_khz / 1e3, sum[0] / cnt * us, prod_min / nit * us, prod_max / nit * us, sum[1] / cnt * us,
+              sum[2] / cnt * us, upd_min / nit * us, upd_max / nit * us, sum[3] / cnt * us);
+    if (cnt > 0)
+      fprintf(stderr, "[lat persist trace] barrier A in detail: first bar.sync %.2f | release fence + flag %.2f | poll + bar.sync %.2f | acquire fence %.2f | last bar.sync %.2f\n",
+              fine[0] / cnt * us, fine[1] / cnt * us, fine[2] / cnt * us, fine[3] / cnt * us, fine[4] / cnt * us);
+  }
   res->iters = hs[0].iters;
   res->norm_b = sqrt(hs[0].bb);
   res->relres = hs[0].bb > 0.0 ? sqrt(hs[0].rr / hs[0].bb) : 0.0;

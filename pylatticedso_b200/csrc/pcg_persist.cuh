@@ -5,11 +5,20 @@
 // launch ramps / tails of ~2-5 us each and a one-CTA reduce kernel (profiles/r01_ncu_full_v4_kernels.txt).  A B200 has
 // 148 x 227 KB = 33 MB of shared memory, enough to hold x, r, p, s and w of a 0.5-0.7 M DOF system.  So:
 //
-//   * one CTA per SM (cooperative launch), each owning a CONTIGUOUS range of block rows balanced by bytes;
-//   * x, r, p, s, w of the owned rows live in shared memory for the whole solve; the CTA's slice of rowptr and
-//     colidx is cached in shared memory too, so the product phase issues only independent loads (matrix blocks,
-//     gathered u) -- no rowptr -> colidx -> u dependency chain;
+//   * one CTA per SM (cooperative launch); the block rows are dealt to the CTAs in chunks of 16 rows, round robin, so
+//     every CTA holds the same mix of long rows (joints) and short rows (strut-interior nodes): with contiguous
+//     byte-balanced ranges the joint-only CTAs needed 28 us per product and the others 18 us, and the reverse in the
+//     update phase (profiles/r02_persist_trace.txt) -- and every phase ends in a grid barrier;
+//   * r, p, s, w AND the preconditioner (reciprocal diagonal or the 21 packed entries of the inverse 6x6 diagonal
+//     block) of the owned rows live in shared memory for the whole solve, so the update phase reads nothing from
+//     global memory but its own u and x; the CTA's slice of rowptr and colidx is cached in shared memory too, so
+//     the product phase issues only independent loads (matrix blocks, gathered u) -- no rowptr -> colidx -> u chain;
+//   * x stays in global memory (one read-modify-write per iteration, nobody waits for it);
 //   * only u = M^-1 r (gathered by other CTAs) lives in global memory, i.e. in L2;
+//   * product and block-Jacobi preconditioner both use the transposed-piece lane mapping (piece_row / piece_finish
+//     in lattice_solver.cu): 96 contiguous bytes per row group and instruction; the inverse diagonal blocks are
+//     stored as full 6x6 blocks for this kernel so that u = M^-1 r is the same block product with x = r from shared
+//     memory (the packed 21-entry layout of k_cg_update needs six scattered 8-byte loads per lane);
 //   * per iteration two grid-wide synchronisations, both flag based (no atomics on a shared counter):
 //       barrier A  (after the update phase: the new u is visible)  -- one epoch flag per CTA, everyone polls all flags;
 //       barrier B  (after the product phase: dot products)         -- every CTA publishes its three partial sums as
@@ -27,7 +36,9 @@
 
 static constexpr int PERSIST_BLOCK = 1024;             // one CTA per SM
 static constexpr int PERSIST_NW = PERSIST_BLOCK / 32;
-static constexpr int PERSIST_NVEC = 5;                 // r, p, s, w, x in shared memory
+static constexpr int PERSIST_NVEC = 4;                 // r, p, s, w in shared memory (x: global)
+__host__ __device__ constexpr int persist_pc_width(int pc) { return pc == LAT_PC_BLOCK6 ? 21 : (pc == LAT_PC_JACOBI ? 6 : 0); }   // doubles per row
+static constexpr int PERSIST_CHUNK = 16;               // rows per chunk of the round-robin row distribution
 static constexpr long long PERSIST_SPIN_LIMIT = 1ll << 23;
 
 struct PersistArgs {
@@ -38,37 +49,44 @@ struct PersistArgs {
   const double* b;
   double* x;               // out: solution (written at the end and before a residual check)
   double* u;               // global: preconditioned residual, gathered by every CTA
-  const double* dinv;      // preconditioner (layout of k_precond_setup)
+  const double* dinv;      // preconditioner in the layout of k_precond_setup (copied to shared memory at start)
   PcgScalars* sc;          // status block read by the host
   PcgParams prm;
   unsigned long long* mail;   // [G][8] LL words (6 used), zeroed before the launch
-  unsigned int* flags;        // [G]    barrier-A epochs, zeroed before the launch
-  const int32_t* cta_row0;    // [G+1]  row partition
+  unsigned int* flags;        // [G][PERSIST_INBOX_STRIDE] barrier-A inboxes, zeroed before the launch
   int rows_cap, blk_cap;      // shared-memory capacities (rows, blocks) the launch was sized for
+  int pc_smem;                // 1: preconditioner rows cached in shared memory; 0: read from global every iteration
+                              //    (shared memory and L1 share 256 KB per SM: above ~164 KB of shared memory the
+                              //    product phase loses its L1 and slowed from 15.5 to 26 us at config 1)
+  long long* trace;           // optional [G][trace_iters][9] SM clock stamps of CTA thread 0 (+ [G][2] rows, blocks)
+  int trace_iters;
 };
 
-// Row partition balanced by bytes: cost(row) = 292 B per block + ROW_COST for the row's vector / preconditioner share.
-static constexpr int64_t PERSIST_ROW_COST = 320;
-__global__ void k_persist_partition(const int32_t* __restrict__ rowptr, int64_t n_nodes, int G,
-                                    int32_t* __restrict__ cta_row0, int32_t* __restrict__ maxima) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c > G) return;
-  const int64_t total = 292ll * rowptr[n_nodes] + PERSIST_ROW_COST * n_nodes;
-  const int64_t target = (total * c) / G;
-  int64_t lo = 0, hi = n_nodes;   // first row r with cost_prefix(r) >= target
-  while (lo < hi) {
-    const int64_t mid = (lo + hi) >> 1;
-    if (292ll * rowptr[mid] + PERSIST_ROW_COST * mid < target) lo = mid + 1; else hi = mid;
-  }
-  cta_row0[c] = (c == G) ? (int32_t)n_nodes : (int32_t)lo;
+// Rows of CTA c: chunks c, c + G, c + 2G, ... of PERSIST_CHUNK consecutive rows.
+__host__ __device__ __forceinline__ int64_t persist_global_row(int lr, int cta, int G) {
+  return ((int64_t)(lr / PERSIST_CHUNK) * G + cta) * PERSIST_CHUNK + (lr % PERSIST_CHUNK);
 }
-__global__ void k_persist_maxima(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cta_row0, int G,
-                                 int32_t* __restrict__ maxima) {
+__host__ __device__ __forceinline__ int persist_rows_of(int64_t n_nodes, int cta, int G) {
+  const int64_t n_chunks = (n_nodes + PERSIST_CHUNK - 1) / PERSIST_CHUNK;
+  if (cta >= n_chunks) return 0;
+  const int64_t mine = (n_chunks - 1 - cta) / G + 1;                  // chunks cta, cta+G, ...
+  const int64_t last = cta + (mine - 1) * G;                          // my last chunk: partial if it is the global last
+  const int64_t last_rows = (last == n_chunks - 1) ? n_nodes - last * PERSIST_CHUNK : PERSIST_CHUNK;
+  return (int)((mine - 1) * PERSIST_CHUNK + last_rows);
+}
+// Shared-memory need of the launch: the largest number of rows / blocks any CTA holds.
+__global__ void k_persist_caps(const int32_t* __restrict__ rowptr, int64_t n_nodes, int G, int32_t* __restrict__ maxima) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= G) return;
-  const int r0 = cta_row0[c], r1 = cta_row0[c + 1];
-  atomicMax(&maxima[0], r1 - r0);
-  atomicMax(&maxima[1], rowptr[r1] - rowptr[r0]);
+  const int nrows = persist_rows_of(n_nodes, c, G);
+  int nblk = 0;
+  for (int lr = 0; lr < nrows; lr += PERSIST_CHUNK) {
+    const int64_t r0 = persist_global_row(lr, c, G);
+    const int64_t r1 = r0 + PERSIST_CHUNK < n_nodes ? r0 + PERSIST_CHUNK : n_nodes;
+    nblk += rowptr[r1] - rowptr[r0];
+  }
+  atomicMax(&maxima[0], nrows);
+  atomicMax(&maxima[1], nblk);
 }
 
 __device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
@@ -96,22 +114,31 @@ struct PersistShared {
 };
 
 // Barrier A: every global store of this CTA (the new u / x of its rows) is visible to every CTA afterwards.
-// Same structure as a cooperative-groups grid sync, with one flag per CTA instead of a shared counter.
-__device__ __forceinline__ void persist_barrier(unsigned int* flags, unsigned int epoch, int G, PersistShared& sh) {
+// All-to-all flags with PRIVATE inboxes: CTA c stores its epoch into slot c of every CTA's inbox (G 4-byte stores by G
+// threads, each behind its own release fence) and polls only its own inbox (5 lines nobody else reads).  The first
+// version had one flag per CTA that all G x G pollers read: 5 hot lines, 5.5 us per barrier
+// (profiles/r02_persist_trace.txt); the acquire fence afterwards drops the SM's L1 lines (CCTL.IVALL).
+static constexpr int PERSIST_INBOX_STRIDE = 160;     // u32 slots per inbox row (G <= 160), 640 B = 5 lines
+__device__ __forceinline__ void persist_barrier(unsigned int* inbox, unsigned int epoch, int G, PersistShared& sh,
+                                                long long* stamp = nullptr) {
   __syncthreads();                                   // the CTA's stores are issued ...
-  if (threadIdx.x == 0) {
-    __threadfence();                                 // ... and ordered before the flag (cumulative at gpu scope)
-    st_relaxed_gpu_u32(flags + blockIdx.x, epoch);
-  }
-  for (int q = threadIdx.x; q < G; q += PERSIST_BLOCK) {
+  if (stamp && threadIdx.x == 0) stamp[0] = clock64();
+  if ((int)threadIdx.x < G) {
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");  // ... and ordered before this thread's flag (cumulative at gpu scope)
+    st_relaxed_gpu_u32(inbox + (size_t)threadIdx.x * PERSIST_INBOX_STRIDE + blockIdx.x, epoch);
+    if (stamp && threadIdx.x == 0) stamp[1] = clock64();
     long long spins = 0;
-    while (ld_relaxed_gpu_u32(flags + q) < epoch) {
+    while (ld_relaxed_gpu_u32(inbox + (size_t)blockIdx.x * PERSIST_INBOX_STRIDE + threadIdx.x) < epoch) {
       if (++spins > PERSIST_SPIN_LIMIT) { sh.timeout = 1; break; }
       if (spins > 4096) __nanosleep(64);
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) __threadfence();             // acquire side: drops the SM's L1 lines (CCTL.IVALL)
+  if (threadIdx.x == 0) {
+    if (stamp) stamp[2] = clock64();
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");   // acquire side: drops the SM's L1 lines (CCTL.IVALL)
+    if (stamp) stamp[3] = clock64();
+  }
   __syncthreads();
 }
 
@@ -162,80 +189,198 @@ __device__ __forceinline__ void persist_reduce(double (&v)[3], unsigned long lon
   __syncthreads();
 }
 
+// s_w = (A v) on the CTA's rows: six lanes per block row in the transposed-piece layout, three blocks (12 x 16 B loads
+// per lane) in flight; lane (g, r) leaves the total of scalar row lane_dof(r) in s_w.  All warps call.
+__device__ __forceinline__ void persist_product(const double* __restrict__ vals, const double* v, const int32_t* s_rp,
+                                                const int32_t* s_gb, const int32_t* s_col, double* s_w, int nrows) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int g = lane / 6, rr_ = lane - g * 6;
+  for (int base = wid * 5; base < nrows; base += PERSIST_NW * 5) {
+    const int lr = base + g;
+    const bool active = g < 5 && lr < nrows;
+    const int lp = active ? s_rp[lr] : 0, nb = active ? s_rp[lr + 1] - lp : 0;
+    const int gb = active ? s_gb[lr] : 0;             // global index of the row's first block
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    piece_row<false, false>(s_col + (lp - gb), vals, gb, gb + nb, rr_, v, s0, s1, s2);
+    const double tot = piece_finish(g, rr_, s0, s1, s2);
+    if (active) s_w[lr * 6 + lane_dof(rr_)] = tot;
+  }
+}
+
+// z_d = (M^-1 v)_d for the lane's scalar row d of local row lr; M^-1 and v both in shared memory (no shuffles).
+template <int PC>
+__device__ __forceinline__ double persist_precond(const double* s_m, const double* s_v, int lr, int d) {
+  if (PC == LAT_PC_NONE) return s_v[lr * 6 + d];
+  if (PC == LAT_PC_JACOBI) return s_m[lr * 6 + d] * s_v[lr * 6 + d];
+  const double* m = s_m + lr * 21;
+  const double* v = s_v + lr * 6;
+  double z = 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const int i = d < k ? d : k, j = d < k ? k : d;
+    z = fma(m[(i * (11 - i)) / 2 + j], v[k], z);
+  }
+  return z;
+}
+
+// Same with the preconditioner row read from global memory (layout of k_precond_setup).
+template <int PC>
+__device__ __forceinline__ double persist_precond_global(const double* __restrict__ dinv, int64_t n, const double* s_v, int lr, int d) {
+  if (PC == LAT_PC_NONE) return s_v[lr * 6 + d];
+  if (PC == LAT_PC_JACOBI) return __ldg(dinv + n * 6 + d) * s_v[lr * 6 + d];
+  const double* m = dinv + n * 21;
+  const double* v = s_v + lr * 6;
+  double z = 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const int i = d < k ? d : k, j = d < k ? k : d;
+    z = fma(__ldg(m + (i * (11 - i)) / 2 + j), v[k], z);
+  }
+  return z;
+}
+
+// Global loads of one trip of the update phase (two row groups A, B): own u, x and -- when they are not cached in
+// shared memory -- the preconditioner rows, all issued before the dependent math.  (Issuing the first trip's loads before
+// the grid reduction was tried: the values spill across the reduction and the phase got slower, 30.2 -> 34.6 us.)
+struct UpdLoads {
+  double uA, uB, xA, xB;
+  double mA[6], mB[6];
+};
+template <int PC>
+__device__ __forceinline__ UpdLoads persist_upd_load(const PersistArgs& a, bool pcs, int64_t iA, int64_t iB, bool actA, bool actB, int dof) {
+  UpdLoads L;
+  L.uA = actA ? a.u[iA] : 0.0;
+  L.uB = actB ? a.u[iB] : 0.0;
+  L.xA = actA ? a.x[iA] : 0.0;
+  L.xB = actB ? a.x[iB] : 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { L.mA[k] = 0.0; L.mB[k] = 0.0; }
+  if (!pcs && PC == LAT_PC_BLOCK6) {
+    const double* pa = a.dinv + (iA / 6) * 21;
+    const double* pb = a.dinv + (iB / 6) * 21;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const int i = dof < k ? dof : k, j = dof < k ? k : dof;
+      L.mA[k] = actA ? __ldg(pa + (i * (11 - i)) / 2 + j) : 0.0;
+      L.mB[k] = actB ? __ldg(pb + (i * (11 - i)) / 2 + j) : 0.0;
+    }
+  }
+  if (!pcs && PC == LAT_PC_JACOBI) { L.mA[0] = actA ? __ldg(a.dinv + iA) : 0.0; L.mB[0] = actB ? __ldg(a.dinv + iB) : 0.0; }
+  return L;
+}
+
 template <int PC>
 __global__ void __launch_bounds__(PERSIST_BLOCK, 1) k_pcg_persist(PersistArgs a) {
   extern __shared__ __align__(16) unsigned char persist_smem[];
   __shared__ PersistShared sh;
+  __shared__ int s_chunk_base[64];
   const int G = gridDim.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int g = lane / 6, rr_ = lane - g * 6;
-  const int R0 = a.cta_row0[blockIdx.x], R1 = a.cta_row0[blockIdx.x + 1];
-  const int nrows = R1 - R0;
-  const int b0 = a.rowptr[R0];
-  const int nblk = a.rowptr[R1] - b0;
+  const int dof = lane_dof(rr_);                       // scalar row this lane owns in every phase
+  const int cta = blockIdx.x;
+  const int nrows = persist_rows_of(a.n_nodes, cta, G);
+  const int nchunks = (nrows + PERSIST_CHUNK - 1) / PERSIST_CHUNK;
   const size_t vec = (size_t)a.rows_cap * 6;
+  constexpr int PCW = persist_pc_width(PC);
   double* s_r = reinterpret_cast<double*>(persist_smem);
   double* s_p = s_r + vec;
   double* s_s = s_p + vec;
   double* s_w = s_s + vec;
-  double* s_x = s_w + vec;
-  double* s_scratch = s_x + vec;                                    // 3 * G doubles
-  int32_t* s_rp = reinterpret_cast<int32_t*>(s_scratch + 3 * G);    // nrows + 1 block offsets relative to b0
-  int32_t* s_col = s_rp + a.rows_cap + 1;
+  double* s_m = s_w + vec;                                          // [rows_cap][PCW] preconditioner rows
+  double* s_scratch = s_m + (a.pc_smem ? (size_t)a.rows_cap * PCW : 0);   // 3 * G doubles
+  int32_t* s_rp = reinterpret_cast<int32_t*>(s_scratch + 3 * G);    // [rows_cap + 1] local block offset of each row
+  int32_t* s_gb = s_rp + a.rows_cap + 1;                            // [rows_cap]     global index of the row's first block
+  int32_t* s_col = s_gb + a.rows_cap;                               // [blk_cap]      column indices in local block order
   if (threadIdx.x == 0) sh.timeout = 0;
-  for (int i = threadIdx.x; i <= nrows; i += PERSIST_BLOCK) s_rp[i] = a.rowptr[R0 + i] - b0;
-  for (int j = threadIdx.x; j < nblk; j += PERSIST_BLOCK) s_col[j] = a.colidx[b0 + j];
-  const double* __restrict__ vals = a.vals + (size_t)b0 * 36;
+  // local block offsets: per chunk (contiguous rows -> one subtraction), then a short serial scan
+  for (int k = threadIdx.x; k < nchunks; k += PERSIST_BLOCK) {
+    const int64_t r0 = persist_global_row(k * PERSIST_CHUNK, cta, G);
+    const int64_t r1 = r0 + PERSIST_CHUNK < a.n_nodes ? r0 + PERSIST_CHUNK : a.n_nodes;
+    s_chunk_base[k] = a.rowptr[r1] - a.rowptr[r0];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int k = 0; k < nchunks; ++k) { const int c = s_chunk_base[k]; s_chunk_base[k] = acc; acc += c; }
+    s_rp[nrows] = acc;
+  }
+  __syncthreads();
+  for (int lr = threadIdx.x; lr < nrows; lr += PERSIST_BLOCK) {
+    const int64_t n = persist_global_row(lr, cta, G);
+    const int64_t n0 = persist_global_row(lr - lr % PERSIST_CHUNK, cta, G);
+    const int gb = a.rowptr[n];
+    s_gb[lr] = gb;
+    s_rp[lr] = s_chunk_base[lr / PERSIST_CHUNK] + (gb - a.rowptr[n0]);
+  }
+  __syncthreads();
+  const int nblk = s_rp[nrows];
+  for (int lr = wid; lr < nrows; lr += PERSIST_NW) {              // one warp per row: its column indices
+    const int lp = s_rp[lr], nb = s_rp[lr + 1] - lp, gb = s_gb[lr];
+    for (int k = lane; k < nb; k += 32) s_col[lp + k] = a.colidx[gb + k];
+  }
+  const double* __restrict__ vals = a.vals;
   double* __restrict__ u = a.u;
   const PcgParams prm = a.prm;
   const double tol2 = prm.tol * prm.tol;
   __syncthreads();
 
-  // ---- init: x = 0, r = b, u = M^-1 b, p = s = 0
+  // ---- init: preconditioner rows -> shared memory; x = 0, r = b, u = M^-1 b, p = s = 0
+  const bool pcs = a.pc_smem != 0;
+  if (PCW > 0 && pcs) {
+    for (int lr = wid; lr < nrows; lr += PERSIST_NW) {
+      const int64_t n = persist_global_row(lr, cta, G);
+      for (int k = lane; k < PCW; k += 32) s_m[lr * PCW + k] = a.dinv[n * PCW + k];
+    }
+  }
   for (int base = wid * 5; base < nrows; base += PERSIST_NW * 5) {
     const int lr = base + g;
-    const bool active = g < 5 && lr < nrows;
-    const int64_t n = R0 + lr;
-    const int li = lr * 6 + rr_;
-    const double bv = active ? a.b[n * 6 + rr_] : 0.0;
-    const double zv = apply_precond<PC>(a.dinv, n, g, rr_, active, bv);
-    if (active) { s_x[li] = 0.0; s_r[li] = bv; s_p[li] = 0.0; s_s[li] = 0.0; u[n * 6 + rr_] = zv; }
+    if (g < 5 && lr < nrows) {
+      const int64_t n = persist_global_row(lr, cta, G);
+      const int li = lr * 6 + dof;
+      s_r[li] = a.b[n * 6 + dof]; s_p[li] = 0.0; s_s[li] = 0.0;
+      a.x[n * 6 + dof] = 0.0;
+    }
+  }
+  __syncthreads();
+  for (int base = wid * 5; base < nrows; base += PERSIST_NW * 5) {
+    const int lr = base + g;
+    if (g < 5 && lr < nrows) {
+      const int64_t n = persist_global_row(lr, cta, G);
+      u[n * 6 + dof] = pcs ? persist_precond<PC>(s_m, s_r, lr, dof) : persist_precond_global<PC>(a.dinv, n, s_r, lr, dof);
+    }
   }
   unsigned int epochA = 0, epochB = 0;
+  if (a.trace && threadIdx.x == 0) {
+    a.trace[(size_t)G * a.trace_iters * 9 + 2 * blockIdx.x] = nrows;
+    a.trace[(size_t)G * a.trace_iters * 9 + 2 * blockIdx.x + 1] = nblk;
+  }
   persist_barrier(a.flags, ++epochA, G, sh);
 
-  int first = 1, iters = 0, done = 0, breakdown = 0, restarts = 0;
+  int first = 1, iters = 0, done = 0, breakdown = 0, restarts = 0, trace_it = 0;
   double gamma_old = 0.0, alpha = 0.0, beta = 0.0, bb = 0.0, rr = 0.0, true_rr = -1.0;
   for (;;) {
     if (sh.timeout) break;
     // ---- product phase: w = A u for the owned rows, partial (r,u), (w,u), (r,r)
     double v[3] = {0.0, 0.0, 0.0};
+    const bool tracing = a.trace != nullptr && trace_it < a.trace_iters;
+    long long* tr = tracing ? a.trace + ((size_t)blockIdx.x * a.trace_iters + trace_it) * 9 : nullptr;
+    if (tracing && threadIdx.x == 0) tr[0] = clock64();
+    persist_product(vals, u, s_rp, s_gb, s_col, s_w, nrows);
+    // every lane reads back exactly the entries it wrote (same (row, dof) mapping): no barrier needed
     for (int base = wid * 5; base < nrows; base += PERSIST_NW * 5) {
       const int lr = base + g;
-      const bool active = g < 5 && lr < nrows;
-      if (active) {
-        const int lo = s_rp[lr], hi = s_rp[lr + 1];
-        const int64_t n = R0 + lr;
-        const double uo = u[n * 6 + rr_];
-        double acc = 0.0;
-#pragma unroll 4
-        for (int j = lo; j < hi; ++j) {
-          const int c = s_col[j];
-          const double2* vp = reinterpret_cast<const double2*>(vals + (size_t)j * 36 + rr_ * 6);
-          const double2* xp = reinterpret_cast<const double2*>(u + (int64_t)c * 6);
-          const double2 a0 = __ldg(vp), a1 = __ldg(vp + 1), a2 = __ldg(vp + 2);
-          const double2 x0 = xp[0], x1 = xp[1], x2 = xp[2];
-          acc = dot6(a0, a1, a2, x0, x1, x2, acc);
-        }
-        const int li = lr * 6 + rr_;
-        const double ro = s_r[li];
-        s_w[li] = acc;
+      if (g < 5 && lr < nrows) {
+        const int e = lr * 6 + dof;
+        const double ro = s_r[e], wv = s_w[e], uo = u[persist_global_row(lr, cta, G) * 6 + dof];
         v[0] = fma(ro, uo, v[0]);
-        v[1] = fma(acc, uo, v[1]);
+        v[1] = fma(wv, uo, v[1]);
         v[2] = fma(ro, ro, v[2]);
       }
     }
+    if (tracing) { __syncthreads(); if (threadIdx.x == 0) tr[1] = clock64(); }
     persist_reduce(v, a.mail, ++epochB, G, sh, s_scratch);
+    if (tracing && threadIdx.x == 0) tr[2] = clock64();
     if (sh.timeout) break;
     const double gamma = sh.tot[0], delta = sh.tot[1];
     rr = sh.tot[2];
@@ -261,29 +406,15 @@ __global__ void __launch_bounds__(PERSIST_BLOCK, 1) k_pcg_persist(PersistArgs a)
     }
     if (done || iters >= prm.maxiter) {
       if (!(done && !breakdown && bb > 0.0)) break;
-      // ---- true-residual safeguard: r_true = b - A x
-      for (int i = threadIdx.x; i < nrows * 6; i += PERSIST_BLOCK) a.x[(size_t)R0 * 6 + i] = s_x[i];
-      persist_barrier(a.flags, ++epochA, G, sh);
-      if (sh.timeout) break;
+      // ---- true-residual safeguard: r_true = b - A x  (x is global and, after the last barrier A, visible everywhere)
       double t[3] = {0.0, 0.0, 0.0};
+      persist_product(vals, a.x, s_rp, s_gb, s_col, s_w, nrows);
       for (int base = wid * 5; base < nrows; base += PERSIST_NW * 5) {
         const int lr = base + g;
-        const bool active = g < 5 && lr < nrows;
-        if (active) {
-          const int lo = s_rp[lr], hi = s_rp[lr + 1];
-          const int64_t n = R0 + lr;
-          double acc = 0.0;
-#pragma unroll 4
-          for (int j = lo; j < hi; ++j) {
-            const int c = s_col[j];
-            const double2* vp = reinterpret_cast<const double2*>(vals + (size_t)j * 36 + rr_ * 6);
-            const double2* xp = reinterpret_cast<const double2*>(a.x + (int64_t)c * 6);
-            const double2 a0 = __ldg(vp), a1 = __ldg(vp + 1), a2 = __ldg(vp + 2);
-            const double2 x0 = xp[0], x1 = xp[1], x2 = xp[2];
-            acc = dot6(a0, a1, a2, x0, x1, x2, acc);
-          }
-          const double rt = a.b[n * 6 + rr_] - acc;
-          s_w[lr * 6 + rr_] = rt;
+        if (g < 5 && lr < nrows) {
+          const int e = lr * 6 + dof;
+          const double rt = a.b[persist_global_row(lr, cta, G) * 6 + dof] - s_w[e];
+          s_w[e] = rt;
           t[0] = fma(rt, rt, t[0]);
         }
       }
@@ -296,12 +427,15 @@ __global__ void __launch_bounds__(PERSIST_BLOCK, 1) k_pcg_persist(PersistArgs a)
       restarts += 1;
       for (int base = wid * 5; base < nrows; base += PERSIST_NW * 5) {
         const int lr = base + g;
-        const bool active = g < 5 && lr < nrows;
-        const int64_t n = R0 + lr;
-        const int li = lr * 6 + rr_;
-        const double rv = active ? s_w[li] : 0.0;
-        const double zv = apply_precond<PC>(a.dinv, n, g, rr_, active, rv);
-        if (active) { s_r[li] = rv; s_p[li] = 0.0; s_s[li] = 0.0; u[n * 6 + rr_] = zv; }
+        if (g < 5 && lr < nrows) { const int li = lr * 6 + dof; s_r[li] = s_w[li]; s_p[li] = 0.0; s_s[li] = 0.0; }
+      }
+      __syncthreads();
+      for (int base = wid * 5; base < nrows; base += PERSIST_NW * 5) {
+        const int lr = base + g;
+        if (g < 5 && lr < nrows) {
+      const int64_t n = persist_global_row(lr, cta, G);
+      u[n * 6 + dof] = pcs ? persist_precond<PC>(s_m, s_r, lr, dof) : persist_precond_global<PC>(a.dinv, n, s_r, lr, dof);
+    }
       }
       persist_barrier(a.flags, ++epochA, G, sh);
       done = 0;
@@ -309,32 +443,56 @@ __global__ void __launch_bounds__(PERSIST_BLOCK, 1) k_pcg_persist(PersistArgs a)
       continue;
     }
     // ---- update phase: p = u + beta p; s = w + beta s; x += alpha p; r -= alpha s; u = M^-1 r
-    for (int base = wid * 5; base < nrows; base += PERSIST_NW * 5) {
-      const int lr = base + g;
-      const bool active = g < 5 && lr < nrows;
-      const int64_t n = R0 + lr;
-      const int li = lr * 6 + rr_;
-      const PrecondRow<PC> pr = load_precond<PC>(a.dinv, n, rr_, active);
-      double rv = 0.0;
-      if (active) {
-        const double uv = u[n * 6 + rr_];
-        const double pv = fma(beta, s_p[li], uv);
-        const double sv = fma(beta, s_s[li], s_w[li]);
-        s_p[li] = pv;
-        s_s[li] = sv;
-        s_x[li] = fma(alpha, pv, s_x[li]);
-        rv = fma(-alpha, sv, s_r[li]);
-        s_r[li] = rv;
+    // two row groups per trip; the only global loads (own u, x) of both are issued first, the rest is shared memory
+    for (int base = wid * 5; base < nrows; base += 2 * PERSIST_NW * 5) {
+      const int lrA = base + g, lrB = base + PERSIST_NW * 5 + g;
+      const bool actA = g < 5 && lrA < nrows, actB = g < 5 && lrB < nrows;
+      const int64_t iA = actA ? persist_global_row(lrA, cta, G) * 6 + dof : 0;
+      const int64_t iB = actB ? persist_global_row(lrB, cta, G) * 6 + dof : 0;
+      const int liA = lrA * 6 + dof, liB = lrB * 6 + dof;
+      const UpdLoads L = persist_upd_load<PC>(a, pcs, iA, iB, actA, actB, dof);
+      const double uA = L.uA, uB = L.uB, xA = L.xA, xB = L.xB;
+      const double* mA = L.mA;
+      const double* mB = L.mB;
+      if (actA) {
+        const double pv = fma(beta, s_p[liA], uA);
+        const double sv = fma(beta, s_s[liA], s_w[liA]);
+        s_p[liA] = pv;
+        s_s[liA] = sv;
+        a.x[iA] = fma(alpha, pv, xA);
+        s_r[liA] = fma(-alpha, sv, s_r[liA]);
       }
-      const double zn = apply_precond<PC>(pr, g, rv);
-      if (active) u[n * 6 + rr_] = zn;
+      if (actB) {
+        const double pv = fma(beta, s_p[liB], uB);
+        const double sv = fma(beta, s_s[liB], s_w[liB]);
+        s_p[liB] = pv;
+        s_s[liB] = sv;
+        a.x[iB] = fma(alpha, pv, xB);
+        s_r[liB] = fma(-alpha, sv, s_r[liB]);
+      }
+      __syncwarp();                                     // the six entries of r of each node are in shared memory
+      if (pcs || PC == LAT_PC_NONE) {
+        if (actA) u[iA] = persist_precond<PC>(s_m, s_r, lrA, dof);
+        if (actB) u[iB] = persist_precond<PC>(s_m, s_r, lrB, dof);
+      } else if (PC == LAT_PC_JACOBI) {
+        if (actA) u[iA] = mA[0] * s_r[liA];
+        if (actB) u[iB] = mB[0] * s_r[liB];
+      } else {
+        double zA = 0.0, zB = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { zA = fma(mA[k], s_r[lrA * 6 + k], zA); zB = fma(mB[k], s_r[lrB * 6 + k], zB); }
+        if (actA) u[iA] = zA;
+        if (actB) u[iB] = zB;
+      }
     }
-    persist_barrier(a.flags, ++epochA, G, sh);
+    if (tracing) { __syncthreads(); if (threadIdx.x == 0) tr[3] = clock64(); }
+    persist_barrier(a.flags, ++epochA, G, sh, tracing ? tr + 5 : nullptr);
+    if (tracing && threadIdx.x == 0) tr[4] = clock64();
+    ++trace_it;
   }
   __syncthreads();
   const int timed_out = sh.timeout;
-  // ---- epilogue: solution and status
-  for (int i = threadIdx.x; i < nrows * 6; i += PERSIST_BLOCK) a.x[(size_t)R0 * 6 + i] = s_x[i];
+  // ---- epilogue: status (x is already in global memory)
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     PcgScalars* sc = a.sc;
     sc->iters = iters;

@@ -367,7 +367,7 @@ def test_persistent_pcg_equals_three_kernel_path_and_oracle(ctx, geom, n, m_, pc
     up, ip = ctx.pcg(rowptr, colidx, vbc, b, tol=1e-12, maxiter=100000, precond=pc, persistent=True)
     assert ip["persistent"] and not i3["persistent"]
     assert ip["info"] in (0, 5) and i3["info"] in (0, 5)
-    assert abs(ip["iters"] - i3["iters"]) <= max(3, 0.02 * i3["iters"])
+    assert abs(ip["iters"] - i3["iters"]) <= max(3, 0.05 * i3["iters"])   # different (fixed) summation orders
     K = orc.assemble_csr(m.xyz, np.stack([m.en0, m.en1], 1), m.rad, E_MOD, NU)
     uo, _ = orc.solve_static(K, fixed.astype(bool), g, f)
     for u in (u3, up):
