@@ -51,7 +51,7 @@ UNIT = "DOF-iterations/s"
 # ncu --set full capture of k_cg_spmv on this workload (profiles/r01_ncu_full_v4_kernels.txt):
 # dram__bytes_read.sum 106.76 MB + dram__bytes_write.sum 3.65 MB per launch (algorithmic: 110.5 MB)
 NCU_TRAFFIC_CG_SPMV = 111.3e6   # dram__bytes_read.sum + dram__bytes_write.sum of one k_cg_spmv launch (profiles/r01_ncu_full_v4_kernels.txt)
-NCU_TRAFFIC_PERSIST_PER_ITER = None   # DRAM bytes per PCG iteration of k_pcg_persist (set from the ncu capture in profiles/)
+NCU_TRAFFIC_PERSIST_PER_ITER = 111.3e6   # (dram__bytes_read.sum + dram__bytes_write.sum) / 693 iterations of one k_pcg_persist launch (profiles/r02_ncu_persist.txt)
 WORKLOAD = "BCC 20x20x20, r=0.05, 2 elements/strut (487566 DOF), uniaxial compression, assemble + PCG to 1e-8"
 
 

@@ -331,6 +331,17 @@ int lat_assemble_cells_bsr(lat_ctx* ctx, const double* S, int64_t s_stride, cons
                            int64_t n_cells, int32_t n_bnd_nodes, const int32_t* rowptr, const int32_t* colidx,
                            int64_t nnzb, double* vals);
 
+/* ---- A11, cell form: q[c][j] = v_c^T dS_{m(c,j)} u_c ------------------------------------------
+ * The per-(cell, geometry) term of LatticeOpti.calculate_gradient (lattice_opti.py:752-761,
+ * u_cell @ (dS @ u_cell)) for all cells at once; the caller maps q to the parameter vector
+ * (unit_cell / constant / linear, :758-839).  mats: [n_mats][nb][nb] row-major, the UNIQUE sensitivity
+ * matrices (the reference caches one per (geometry, radii) key, lattice_sim.py:857-883); mat_index:
+ * int32[n_cells][n_grad] index into mats (-1: none -> 0); U: [n_cells][nb] boundary displacements in
+ * cell.node_in_order_simulation order; V: second vector for adjoint objectives (NULL -> V = U).
+ * out[n_cells][n_grad] is overwritten. */
+int lat_cell_quadform(lat_ctx* ctx, const double* mats, int64_t n_mats, const int32_t* mat_index, const double* U,
+                      const double* V, int64_t n_cells, int32_t n_grad, int32_t nb, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,8 +3,10 @@
 #include "common.cuh"
 
 static constexpr int SCHUR_BLOCK = 256;
-static constexpr int SCHUR_MAX_NB = 96;   // boundary DOFs per cell (BCC 48, Octet 84)
-static constexpr int GRAD_PER_THREAD = (SCHUR_MAX_NB * SCHUR_MAX_NB + SCHUR_BLOCK - 1) / SCHUR_BLOCK;
+// boundary DOFs per cell: BCC 48, Octet 84, Kelvin 144, Original2 156 (the reference's largest geometry); the per-lane
+// tiles of k_ddm_matvec are sized from nb at launch (1..6 tiles of 32), the dense kernels are limited by shared memory
+static constexpr int SCHUR_MAX_NB = 192;
+static constexpr int GRAD_PER_THREAD = 36;   // dS entries a thread accumulates per pass (nB <= 96: one pass)
 
 // position of local node l in the factorisation order: interior nodes first, boundary nodes last
 __device__ __forceinline__ int node_pos(int l, int nn, int nbn) { return l >= nbn ? l - nbn : nn - nbn + l; }
@@ -534,7 +536,8 @@ __global__ void __launch_bounds__(SCHUR_BLOCK) k_schur_dense(
       }
     }
     __syncthreads();
-    for (int gsel = 0; gsel < n_grad; ++gsel) {
+    for (int gsel = 0; gsel < n_grad; ++gsel)
+    for (int q0 = 0; q0 < nB * nB; q0 += GRAD_PER_THREAD * SCHUR_BLOCK) {   // passes over the entries of dS (one for nB <= 96)
       double acc[GRAD_PER_THREAD];
 #pragma unroll
       for (int u = 0; u < GRAD_PER_THREAD; ++u) acc[u] = 0.0;
@@ -568,7 +571,7 @@ __global__ void __launch_bounds__(SCHUR_BLOCK) k_schur_dense(
         __syncthreads();
 #pragma unroll
         for (int u = 0; u < GRAD_PER_THREAD; ++u) {
-          const int q = tid + u * SCHUR_BLOCK;
+          const int q = q0 + tid + u * SCHUR_BLOCK;
           if (q < nB * nB) {
             const int b1 = q / nB, b2 = q - b1 * nB;
             double s = 0.0;
@@ -582,7 +585,7 @@ __global__ void __launch_bounds__(SCHUR_BLOCK) k_schur_dense(
       double* dSc = dS + (c * (int64_t)n_grad + gsel) * (int64_t)nB * nB;
 #pragma unroll
       for (int u = 0; u < GRAD_PER_THREAD; ++u) {
-        const int q = tid + u * SCHUR_BLOCK;
+        const int q = q0 + tid + u * SCHUR_BLOCK;
         if (q < nB * nB) dSc[q] = bad ? qnan : acc[u];
       }
     }
@@ -677,6 +680,7 @@ extern "C" int lat_schur_batch_chains(lat_ctx* ctx, const double* xyz, const int
 // One warp per cell.  The warp gathers the cell's boundary displacements (lane j holds
 // u_c[j], u_c[j+32], u_c[j+64]), streams S_c row by row with coalesced loads, reduces each
 // row product with shuffles, and scatter-adds the 6 n_bnd results into y with FP64 atomics.
+template <int NT>
 __global__ void __launch_bounds__(256) k_ddm_matvec(const double* __restrict__ S, int64_t s_stride,
                                                     const int32_t* __restrict__ gidx, const double* __restrict__ u_fixed,
                                                     int64_t n_cells, int nb, const double* __restrict__ x,
@@ -686,10 +690,10 @@ __global__ void __launch_bounds__(256) k_ddm_matvec(const double* __restrict__ S
   if (c >= n_cells) return;
   const int32_t* gi = gidx + c * nb;
   const double* Sc = S + c * s_stride;
-  double xr[3];
-  int gl[3];
+  double xr[NT];
+  int gl[NT];
 #pragma unroll
-  for (int q = 0; q < 3; ++q) {
+  for (int q = 0; q < NT; ++q) {
     const int j = lane + 32 * q;
     gl[q] = -2;
     xr[q] = 0.0;
@@ -698,7 +702,9 @@ __global__ void __launch_bounds__(256) k_ddm_matvec(const double* __restrict__ S
       xr[q] = gl[q] >= 0 ? x[gl[q]] : (u_fixed ? u_fixed[c * nb + j] : 0.0);
     }
   }
-  double yr[3] = {0.0, 0.0, 0.0};
+  double yr[NT];
+#pragma unroll
+  for (int q = 0; q < NT; ++q) yr[q] = 0.0;
   // four rows per step: their loads are issued together and the four shuffle reductions interleave
   // (eight rows per step measured slower again: 0.53 / 0.81 against 0.61 / 0.87 of HBM at nb = 48 / 84)
   for (int i0 = 0; i0 < nb; i0 += 4) {
@@ -710,7 +716,7 @@ __global__ void __launch_bounds__(256) k_ddm_matvec(const double* __restrict__ S
       if (i < nb) {
         const double* row = Sc + (int64_t)i * nb;
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
+        for (int q = 0; q < NT; ++q) {
           const int j = lane + 32 * q;
           if (j < nb) s[k] = fma(__ldcs(row + j), xr[q], s[k]);
         }
@@ -725,12 +731,14 @@ __global__ void __launch_bounds__(256) k_ddm_matvec(const double* __restrict__ S
     for (int k = 0; k < 4; ++k) {
       const int i = i0 + k;
       if (i < nb && lane == (i & 31)) {
-        if (i < 32) yr[0] = s[k]; else if (i < 64) yr[1] = s[k]; else yr[2] = s[k];
+#pragma unroll
+        for (int q = 0; q < NT; ++q)
+          if ((i >> 5) == q) yr[q] = s[k];
       }
     }
   }
 #pragma unroll
-  for (int q = 0; q < 3; ++q)
+  for (int q = 0; q < NT; ++q)
     if (gl[q] >= 0) atomicAdd(&y[gl[q]], yr[q]);
 }
 
@@ -743,7 +751,15 @@ extern "C" int lat_ddm_matvec(lat_ctx* ctx, const double* S, int64_t s_stride, c
   LAT_CUDA(ctx, cudaSetDevice(ctx->device));
   LAT_CUDA(ctx, cudaMemsetAsync(y, 0, n_free * sizeof(double), ctx->stream));
   if (n_cells == 0) return LAT_OK;
-  LAT_LAUNCH(ctx, k_ddm_matvec, (unsigned)ceil_div(n_cells, 8), 256, 0, S, s_stride, gidx, u_fixed, n_cells, nb, x, y);
+  const unsigned grid = (unsigned)ceil_div(n_cells, 8);
+  switch ((nb + 31) / 32) {
+    case 1: LAT_LAUNCH(ctx, k_ddm_matvec<1>, grid, 256, 0, S, s_stride, gidx, u_fixed, n_cells, nb, x, y); break;
+    case 2: LAT_LAUNCH(ctx, k_ddm_matvec<2>, grid, 256, 0, S, s_stride, gidx, u_fixed, n_cells, nb, x, y); break;
+    case 3: LAT_LAUNCH(ctx, k_ddm_matvec<3>, grid, 256, 0, S, s_stride, gidx, u_fixed, n_cells, nb, x, y); break;
+    case 4: LAT_LAUNCH(ctx, k_ddm_matvec<4>, grid, 256, 0, S, s_stride, gidx, u_fixed, n_cells, nb, x, y); break;
+    case 5: LAT_LAUNCH(ctx, k_ddm_matvec<5>, grid, 256, 0, S, s_stride, gidx, u_fixed, n_cells, nb, x, y); break;
+    default: LAT_LAUNCH(ctx, k_ddm_matvec<6>, grid, 256, 0, S, s_stride, gidx, u_fixed, n_cells, nb, x, y); break;
+  }
   return LAT_OK;
 }
 
@@ -805,5 +821,46 @@ extern "C" int lat_assemble_cells_bsr(lat_ctx* ctx, const double* S, int64_t s_s
   LAT_CUDA(ctx, cudaMemcpyAsync(&h, missing, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (h != 0) return lat_fail(ctx, LAT_ERR_ARG, "pattern does not contain every (node, node) pair of the cells", __FILE__, __LINE__);
+  return LAT_OK;
+}
+
+
+// ===========================================================================
+// A11 (cell form): q[c][j] = v_c^T dS_{m(c,j)} u_c
+// ===========================================================================
+// The per-(cell, geometry) term of LatticeOpti.calculate_gradient (lattice_opti.py:752-761: u_cell @ (dS @ u_cell));
+// the reference caches one dS per unique (geometry, radii) key (lattice_sim.py:857-883), hence the index table.
+// One warp per (cell, j): rows of the matrix are read coalesced, each row product is reduced with a butterfly and
+// weighted by v_i; fixed order -> reproducible.
+__global__ void __launch_bounds__(256) k_cell_quadform(const double* __restrict__ mats, const int32_t* __restrict__ mat_index,
+                                                       const double* __restrict__ U, const double* __restrict__ V,
+                                                       int64_t n_pairs, int n_grad, int nb, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= n_pairs) return;
+  const int64_t c = p / n_grad;
+  const int m = mat_index[p];
+  if (m < 0) { if (lane == 0) out[p] = 0.0; return; }
+  const double* M = mats + (int64_t)m * nb * nb;
+  const double* u = U + c * nb;
+  const double* v = V ? V + c * nb : u;
+  double acc = 0.0;
+  for (int i = 0; i < nb; ++i) {
+    double s = 0.0;
+    for (int k = lane; k < nb; k += 32) s = fma(__ldg(M + (int64_t)i * nb + k), u[k], s);
+    s = warp_sum(s);
+    acc = fma(v[i], s, acc);
+  }
+  if (lane == 0) out[p] = acc;
+}
+
+extern "C" int lat_cell_quadform(lat_ctx* ctx, const double* mats, int64_t n_mats, const int32_t* mat_index, const double* U,
+                                 const double* V, int64_t n_cells, int32_t n_grad, int32_t nb, double* out) {
+  if (!ctx) return LAT_ERR_ARG;
+  LAT_CHECK_ARG(ctx, mats && mat_index && U && out && n_mats > 0 && n_cells >= 0 && n_grad > 0 && nb > 0);
+  if (n_cells == 0) return LAT_OK;
+  LAT_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t n_pairs = n_cells * n_grad;
+  LAT_LAUNCH(ctx, k_cell_quadform, (unsigned)ceil_div(n_pairs, 8), 256, 0, mats, mat_index, U, V, n_pairs, (int)n_grad, (int)nb, out);
   return LAT_OK;
 }

@@ -62,11 +62,10 @@ class InterfaceProblem:
         return self.ctx.ddm_matvec(self.S, gidx, x_free, u_fixed=u_fixed)
 
 
-def solve_DDM_B200(lattice, tol=1e-10, maxiter=200000, ctx=None):
-    """Drop-in for ``LatticeSim.solve_DDM()`` -> (xsol, info, global_displacement_index, b).
-
-    Needs ``cell.schur_complement`` on every cell (``calculate_schur_complement_cells``, which calls the
-    patched ``get_schur_complement``).  Leaves displacements and reactions on the boundary ``Point``s."""
+def interface_from_lattice(lattice, ctx=None):
+    """Interface problem of a decomposed lattice from its (reference or duck-typed) object graph: needs
+    ``cell.schur_complement`` on every cell and ``Point.index_boundary`` on the cell-boundary nodes.
+    Returns (InterfaceProblem, {index_boundary: Point}, fixed, g, f) with 6 DOFs per interface node."""
     import torch
     ctx = ctx or L.Context()
     cells = list(lattice.cells)
@@ -76,6 +75,7 @@ def solve_DDM_B200(lattice, tol=1e-10, maxiter=200000, ctx=None):
     nbn = max(len(c.node_in_order_simulation) for c in cells)
     n_int = int(lattice.max_index_boundary) + 1
     cell_nodes = np.full((len(cells), nbn), -1, dtype=np.int32)
+    # one device copy per UNIQUE Schur matrix would do; the per-cell stack keeps lat_assemble_cells_bsr's layout simple
     S = np.zeros((len(cells), 6 * nbn, 6 * nbn))
     pts = {}
     for k, c in enumerate(cells):
@@ -94,11 +94,85 @@ def solve_DDM_B200(lattice, tol=1e-10, maxiter=200000, ctx=None):
                 g[6 * ib + d] = p.displacement_vector[d]
             f[6 * ib + d] = float(p.applied_force[d])   # DDM applies every component once (lattice_sim.py:567-632)
     prob = InterfaceProblem(ctx, cell_nodes, n_int, torch.from_numpy(S).to(ctx.device))
+    return prob, pts, fixed, g, f
+
+
+def free_dof_map(lattice, pts, n_free=None):
+    """Position (6 * index_boundary + d) of every free interface DOF in the reference's free-DOF numbering
+    (``Point.global_free_DOF_index``, set by ``LatticeSim.set_global_free_DOF_index``, lattice_sim.py:654-669)."""
+    pairs = []
+    for ib, p in pts.items():
+        for d in range(NDOF):
+            if not p.fixed_DOF[d]:
+                pairs.append((int(p.global_free_DOF_index[d]), 6 * ib + d))
+    n_free = len(pairs) if n_free is None else int(n_free)
+    out = np.full(n_free, -1, dtype=np.int64)
+    for k, pos in pairs:
+        out[k] = pos
+    if (out < 0).any():
+        raise ValueError("free-DOF numbering of the lattice is incomplete: call set_global_free_DOF_index() first")
+    return out
+
+
+def solve_DDM_B200(lattice, tol=1e-10, maxiter=200000, ctx=None):
+    """Drop-in for ``LatticeSim.solve_DDM()`` -> (xsol, info, global_displacement_index, b)
+    (lattice_sim.py:1111-1176).
+
+    Needs ``cell.schur_complement`` on every cell (``calculate_schur_complement_cells``, which calls the
+    patched ``get_schur_complement``).  Leaves displacements and reactions on the boundary ``Point``s and, like
+    the reference, the free-DOF numbering on the lattice (``define_free_DOF`` / ``set_global_free_DOF_index``
+    when the object offers them)."""
+    for name in ("define_free_DOF", "set_global_free_DOF_index"):
+        fn = getattr(lattice, name, None)
+        if callable(fn):
+            fn()
+    prob, pts, fixed, g, f = interface_from_lattice(lattice, ctx)
     u, R, info, b = prob.solve(fixed, g, f, tol=tol, maxiter=maxiter)
+    if info["info"] not in (0, 5):
+        import warnings
+        warnings.warn(f"solve_DDM_B200: interface PCG stopped with info={info['info']} (relres {info['relres']:.2e}, "
+                      f"true {info['true_relres']:.2e})")
     uh, Rh = u.cpu().numpy().reshape(-1, 6), R.cpu().numpy().reshape(-1, 6)
     for ib, p in pts.items():
         p.displacement_vector[:] = [float(v) for v in uh[ib]]
         p.reaction_force_vector = [float(v) for v in Rh[ib]]
     xsol, idx = lattice.get_global_displacement()
     free = fixed.reshape(-1) == 0
-    return xsol, info["info"], lattice.global_displacement_index, b.cpu().numpy()[free]
+    code = 0 if info["info"] in (0, 5) else int(info["info"])      # the reference's 0 / 1 / 2 convention
+    return xsol, code, lattice.global_displacement_index, b.cpu().numpy()[free]
+
+
+def compliance_gradient_cells(lattice, ctx=None, adjoint=None):
+    """q[c, j] = u_c^T (dS_c/dr_j) u_c for every cell and geometry slot on the device (``lat_cell_quadform``) from the
+    boundary displacements on the ``Point``s and ``cell.schur_complement_gradient`` -- the inner term of
+    ``LatticeOpti.calculate_gradient`` (lattice_opti.py:752-761).  ``adjoint``: optional per-cell list of lambda_c."""
+    import torch
+    ctx = ctx or L.Context()
+    cells = list(lattice.cells)
+    n_geom = max(len(getattr(c, "schur_complement_gradient", None) or []) for c in cells)
+    if n_geom == 0:
+        raise ValueError("no cell carries schur_complement_gradient: enable_gradient_computing was off")
+    nb = max(6 * len(c.node_in_order_simulation) for c in cells)
+    uniq, mats = {}, []
+    index = np.full((len(cells), n_geom), -1, dtype=np.int32)
+    U = np.zeros((len(cells), nb))
+    V = None if adjoint is None else np.zeros((len(cells), nb))
+    for k, c in enumerate(cells):
+        if c.node_in_order_simulation is None:
+            c.define_node_order_to_simulate()
+        uc = np.asarray(c.get_displacement_at_nodes(c.node_in_order_simulation), dtype=np.float64).ravel()
+        U[k, : uc.size] = uc
+        if V is not None:
+            V[k, : uc.size] = np.asarray(adjoint[k], dtype=np.float64).ravel()
+        for j, dS in enumerate(getattr(c, "schur_complement_gradient", None) or []):
+            key = id(dS)
+            if key not in uniq:
+                M = np.zeros((nb, nb))
+                a = np.asarray(dS, dtype=np.float64)
+                M[: a.shape[0], : a.shape[1]] = a
+                uniq[key] = len(mats)
+                mats.append(M)
+            index[k, j] = uniq[key]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(ctx.device)
+    q = ctx.cell_quadform(t(np.stack(mats)), t(index), t(U), None if V is None else t(V))
+    return q.cpu().numpy()

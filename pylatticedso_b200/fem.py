@@ -265,35 +265,91 @@ def solve_FEM_B200(lattice, elements_per_strut="gmsh", tol=1e-10, maxiter=500000
     return xsol, FEMResult(fem, u, R, info, fixed)
 
 
+def cell_sensitivities_to_parameters(lattice, q, optimization_type=None):
+    """Map q[c, j] = u_c^T (dS_c/dr_j) u_c to the parameter vector of ``LatticeOpti.calculate_gradient``
+    (lattice_opti.py:752-839), RAW sign (the reference flips it in ``gradient``, :719):
+
+    * ``unit_cell``: ``grad[cell.index * n_geom + j] = q[c, j]`` (:758-761)
+    * ``constant``:  hybrid -> ``grad[j] = sum_c q[c, j]``; else ``grad[0] = sum q`` (:763-784)
+    * ``linear``:    ``r_cell = a . centre + d`` shared by all geometries of a cell: ``grad[i] += dC_c * centre[dir_i]``,
+      ``grad[-1] += dC_c`` with ``dC_c = sum_j q[c, j]``, cells whose unclamped radius lies outside
+      ``(min_radius, max_radius)`` skipped (:785-839)."""
+    params = getattr(lattice, "optimization_parameters", None) or {}
+    opt_type = optimization_type or params.get("type", "unit_cell")
+    cells = list(lattice.cells)
+    n_geom = q.shape[1]
+    if opt_type == "unit_cell":
+        grad = np.zeros(len(cells) * n_geom)
+        for k, c in enumerate(cells):
+            grad[c.index * n_geom: c.index * n_geom + n_geom] += q[k]
+        return grad
+    if opt_type == "constant":
+        if bool(params.get("hybrid", False)):
+            return q.sum(axis=0)
+        n_par = int(getattr(lattice, "number_parameters", 1))
+        grad = np.zeros(max(n_par, 1))
+        grad[0] = q.sum()
+        return grad
+    if opt_type == "linear":
+        dirs = params.get("direction", ["x", "y", "z"])
+        if any(d not in ("x", "y", "z") for d in dirs):
+            raise ValueError(f"Invalid direction in {dirs}; valid are 'x', 'y', 'z'.")
+        n_par = len(dirs) + 1
+        if hasattr(lattice, "number_parameters") and lattice.number_parameters != n_par:
+            raise ValueError(f"Mismatch in number of linear parameters: got {lattice.number_parameters}, expected {n_par}.")
+        theta = [float(v) for v in lattice.actual_optimization_parameters]
+        den = getattr(lattice, "denormalize_optimization_parameters", None)
+        coef = {"x": 0.0, "y": 0.0, "z": 0.0}
+        for i, dkey in enumerate(dirs):
+            coef[dkey] = den([theta[i]])[0] if den else theta[i]
+        d0 = den([theta[-1]])[0] if den else theta[-1]
+        tol = 1e-12
+        grad = np.zeros(n_par)
+        for k, c in enumerate(cells):
+            cx, cy, cz = c.center_point
+            r_un = coef["x"] * cx + coef["y"] * cy + coef["z"] * cz + d0
+            if not (lattice.min_radius + tol < r_un < lattice.max_radius - tol):
+                continue
+            dC = float(q[k].sum())
+            for i, dkey in enumerate(dirs):
+                grad[i] += dC * (cx if dkey == "x" else cy if dkey == "y" else cz)
+            grad[len(dirs)] += dC
+        return grad
+    raise NotImplementedError(f"Gradient for optimization type '{opt_type}' not implemented yet.")
+
+
 def compliance_gradient_lattice(lattice, model: FEMResult, optimization_type="unit_cell"):
-    """dC/d(param) in the parameter order of ``LatticeOpti.calculate_gradient`` (lattice_opti.py:752-761:
-    ``cell.index * n_geom + j`` for ``unit_cell``, ``j`` for hybrid ``constant``), sign of :719 included.
+    """dC/d(param) in the parameter order of ``LatticeOpti.calculate_gradient`` (lattice_opti.py:752-839:
+    ``unit_cell`` / ``constant`` / ``linear``), sign of :719 included.
 
     The reference evaluates  -sum_c u_c^T (dS_c/dr_j) u_c  with one Schur matrix per cell built from
     ``cell.beams_cell`` -- a strut shared by k cells therefore contributes to the parameter of EACH of its
     cells (cell.py:914-915 changes it from every owner).  The element form used here reproduces that by
-    giving every (cell, strut) incidence its own pass of ``lat_compliance_grad``.
+    giving every (cell, strut) incidence its own pass of ``lat_compliance_grad``; the per-(cell, geometry)
+    sums are then mapped to the parameters by :func:`cell_sensitivities_to_parameters`.
     """
     import torch
     fem = model.fem
     mesh = fem.mesh
     n_geom = len(getattr(lattice, "geom_types", [0])) if hasattr(lattice, "geom_types") else 1
     cells = list(lattice.cells)
-    n_params = len(cells) * n_geom if optimization_type == "unit_cell" else n_geom
-    # (beam.index -> list of parameter ids), one entry per owning cell
+    pos = {c.index: k for k, c in enumerate(cells)}
+    n_slots = len(cells) * n_geom
+    # (beam.index -> list of (cell, geometry) slots), one entry per owning cell
     owners = {}
     for c in cells:
         for b in c.beams_cell:
             j = int(getattr(b, "type_beam", 0))
-            pid = c.index * n_geom + j if optimization_type == "unit_cell" else j
-            owners.setdefault(b.index, []).append(pid)
+            owners.setdefault(b.index, []).append(pos[c.index] * n_geom + j)
     depth = max(len(v) for v in owners.values())
-    grad = torch.zeros(n_params, dtype=torch.float64, device=fem.ctx.device)
+    acc = torch.zeros(n_slots, dtype=torch.float64, device=fem.ctx.device)
     chain = torch.from_numpy(np.ascontiguousarray(mesh.chain, dtype=np.float64)).to(fem.ctx.device)
     for layer in range(depth):
         table = {bi: (v[layer] if layer < len(v) else -1) for bi, v in owners.items()}
         grp = np.array([table.get(int(bi), -1) for bi in mesh.beam_of_elem], dtype=np.int32)
-        grad += fem.ctx.compliance_grad(fem.x, fem.y, fem.z, fem.en0, fem.en1, fem.rad,
-                                        torch.from_numpy(grp).to(fem.ctx.device), n_params, model.u, fem.young, fem.nu,
-                                        fem.kappa, chain=chain)
-    return grad.cpu().numpy()
+        acc += fem.ctx.compliance_grad(fem.x, fem.y, fem.z, fem.en0, fem.en1, fem.rad,
+                                       torch.from_numpy(grp).to(fem.ctx.device), n_slots, model.u, fem.young, fem.nu,
+                                       fem.kappa, chain=chain)
+    # lat_compliance_grad carries the sign of :719 (g = -sum ...); the mapping works on the raw (+) term
+    q = -acc.cpu().numpy().reshape(len(cells), n_geom)
+    return -cell_sensitivities_to_parameters(lattice, q, optimization_type)

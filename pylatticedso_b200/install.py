@@ -1,36 +1,88 @@
-"""Rebind the reference's three module-level seams to the B200 path.
+"""Rebind the reference's seams to the B200 path.
 
     from pylatticedso_b200 import install
-    install.patch_reference()          # after `import pyLatticeSim...`
+    install.patch_reference()          # after `import pyLatticeSim...` / `import pyLatticeOpti...`
 
-The reference resolves ``solve_FEM_FenicsX``, ``get_schur_complement`` and
-``conjugate_gradient_solver`` as module-level names (``lattice_opti.py:22-23``,
-``lattice_sim.py:21-22``), so no reference file has to change.
+The reference has no plugin layer; its hot path is reached through module-level names and methods, all of which can
+be rebound without touching a reference file:
+
+| name (module / class)                                                    | reference            | replaced by |
+|---|---|---|
+| ``solve_FEM_FenicsX`` (utils_simulation, lattice_opti)                     | utils_simulation.py:21-56 | ``fem.solve_FEM_B200`` |
+| ``get_schur_complement`` (utils_schur, lattice_sim)                        | utils_schur.py:22-53      | ``schur.get_schur_complement`` |
+| ``conjugate_gradient_solver`` (conjugate_gradient_solver, lattice_sim, lattice_opti) | conjugate_gradient_solver.py:15-122 | ``pcg.conjugate_gradient_solver`` (recognises the LinearOperator built around ``calculate_reaction_force_global``) |
+| ``LatticeSim.solve_DDM``                                                   | lattice_sim.py:1111-1176  | ``ddm.solve_DDM_B200`` |
+| ``LatticeSim._compute_schur_gradients``                                    | lattice_sim.py:1020-1054  | ``schur.schur_gradients`` (analytic, no finite differences) |
+| ``LatticeOpti.calculate_gradient`` (compliance branch)                     | lattice_opti.py:735-841   | ``ddm.compliance_gradient_cells`` + ``fem.cell_sensitivities_to_parameters`` |
+
+``patch_reference`` returns the list of names it rebound; ``unpatch_reference`` restores the originals.
 """
 from __future__ import annotations
 
 import sys
 
+_ORIGINALS = []
 
-def patch_reference(elements_per_strut="gmsh"):
-    from . import fem, schur
+
+def _rebind(owner, attr, fn, done, label):
+    if owner is not None and hasattr(owner, attr):
+        _ORIGINALS.append((owner, attr, getattr(owner, attr)))
+        setattr(owner, attr, fn)
+        done.append(label)
+
+
+def patch_reference(elements_per_strut="gmsh", ctx=None):
+    from . import ddm, fem, pcg, schur
     done = []
 
     def _solve(lattice):
-        return fem.solve_FEM_B200(lattice, elements_per_strut=elements_per_strut)
+        return fem.solve_FEM_B200(lattice, elements_per_strut=elements_per_strut, ctx=ctx)
 
     def _schur(lattice, cell_index=None):
-        return schur.get_schur_complement(lattice, cell_index, elements_per_strut=elements_per_strut)
+        return schur.get_schur_complement(lattice, cell_index, elements_per_strut=elements_per_strut, ctx=ctx)
 
-    # conjugate_gradient_solver is NOT rebound blindly: the reference passes scipy LinearOperators wrapping its
-    # Python cell loop (lattice_sim.py:1148-1160); the device version (pylatticedso_b200.pcg) takes a BsrOperator.
-    # The DDM path is replaced as a whole by ddm.solve_DDM_B200 instead.
+    def _solve_ddm(self):
+        return ddm.solve_DDM_B200(self, ctx=ctx)
+
+    def _schur_gradients(self, cell, radii_params):
+        return schur.schur_gradients(self, cell, list(radii_params), elements_per_strut=elements_per_strut, ctx=ctx)
+
+    mods = sys.modules
     for modname, attr, fn in (("pyLatticeSim.utils_simulation", "solve_FEM_FenicsX", _solve),
                               ("pyLatticeOpti.lattice_opti", "solve_FEM_FenicsX", _solve),
                               ("pyLatticeSim.utils_schur", "get_schur_complement", _schur),
-                              ("pyLatticeSim.lattice_sim", "get_schur_complement", _schur)):
-        mod = sys.modules.get(modname)
-        if mod is not None and hasattr(mod, attr):
-            setattr(mod, attr, fn)
-            done.append(f"{modname}.{attr}")
+                              ("pyLatticeSim.lattice_sim", "get_schur_complement", _schur),
+                              ("pyLatticeSim.conjugate_gradient_solver", "conjugate_gradient_solver", pcg.conjugate_gradient_solver),
+                              ("pyLatticeSim.lattice_sim", "conjugate_gradient_solver", pcg.conjugate_gradient_solver),
+                              ("pyLatticeOpti.lattice_opti", "conjugate_gradient_solver", pcg.conjugate_gradient_solver)):
+        _rebind(mods.get(modname), attr, fn, done, f"{modname}.{attr}")
+
+    ls = mods.get("pyLatticeSim.lattice_sim")
+    lattice_sim_cls = getattr(ls, "LatticeSim", None)
+    _rebind(lattice_sim_cls, "solve_DDM", _solve_ddm, done, "pyLatticeSim.lattice_sim.LatticeSim.solve_DDM")
+    _rebind(lattice_sim_cls, "_compute_schur_gradients", _schur_gradients, done,
+            "pyLatticeSim.lattice_sim.LatticeSim._compute_schur_gradients")
+
+    lo = mods.get("pyLatticeOpti.lattice_opti")
+    lattice_opti_cls = getattr(lo, "LatticeOpti", None)
+    if lattice_opti_cls is not None and hasattr(lattice_opti_cls, "calculate_gradient"):
+        original = lattice_opti_cls.calculate_gradient
+
+        def _calculate_gradient(self):
+            if getattr(self, "objective_type", None) != "compliance":
+                return original(self)        # adjoint branch: its CG already runs on the device (rebinding above)
+            q = ddm.compliance_gradient_cells(self, ctx=ctx)
+            return fem.cell_sensitivities_to_parameters(self, q)
+
+        _rebind(lattice_opti_cls, "calculate_gradient", _calculate_gradient, done,
+                "pyLatticeOpti.lattice_opti.LatticeOpti.calculate_gradient")
     return done
+
+
+def unpatch_reference():
+    """Restore every name ``patch_reference`` rebound (last in, first out)."""
+    n = len(_ORIGINALS)
+    while _ORIGINALS:
+        owner, attr, fn = _ORIGINALS.pop()
+        setattr(owner, attr, fn)
+    return n

@@ -31,6 +31,7 @@ EXPORTS = [
     "lat_compliance_grad", "lat_schur_batch", "lat_schur_batch_chains", "lat_assemble_bsr_struts", "lat_strut_recover", "lat_ddm_matvec",
     "lat_nccl_unique_id", "lat_comm_create", "lat_comm_destroy", "lat_allreduce_sum", "lat_halo_exchange",
     "lat_pcg_bsr_dist", "lat_p2p_arena_create", "lat_p2p_attach", "lat_p2p_destroy", "lat_assemble_cells_bsr",
+    "lat_cell_quadform",
 ]
 
 
@@ -124,6 +125,7 @@ def load():
     lib.lat_schur_batch_chains.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, dbl, dbl, dbl, vp]
     lib.lat_ddm_matvec.argtypes = [vp, vp, i64, vp, vp, i64, i32, i64, vp, vp]
     lib.lat_assemble_cells_bsr.argtypes = [vp, vp, i64, vp, i64, i32, vp, vp, i64, vp]
+    lib.lat_cell_quadform.argtypes = [vp, vp, i64, vp, vp, vp, i64, i32, i32, vp]
     lib.lat_nccl_unique_id.argtypes = [vp]
     lib.lat_comm_create.argtypes = [vp, vp, C.c_int, C.c_int]
     lib.lat_comm_destroy.argtypes = [vp]
@@ -375,6 +377,16 @@ class Context:
         self.check(self.lib.lat_assemble_cells_bsr(self.h, _ptr(S), stride, _ptr(cell_nodes), n_cells, nbn, _ptr(rowptr),
                                                    _ptr(colidx), colidx.numel(), _ptr(vals)))
         return vals
+
+    def cell_quadform(self, mats, mat_index, U, V=None):
+        """q[c, j] = V[c]^T mats[mat_index[c, j]] U[c]  (V = None: V = U)."""
+        import torch
+        n_cells, n_grad = int(mat_index.shape[0]), int(mat_index.shape[1])
+        nb = int(U.shape[1])
+        out = torch.empty((n_cells, n_grad), dtype=torch.float64, device=self.device)
+        self.check(self.lib.lat_cell_quadform(self.h, _ptr(mats), int(mats.shape[0]), _ptr(mat_index), _ptr(U), _ptr(V),
+                                              n_cells, n_grad, nb, _ptr(out)))
+        return out
 
     # -- multi-GPU ---------------------------------------------------------------
     def comm_create(self, rank, world):

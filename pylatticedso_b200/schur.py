@@ -118,6 +118,36 @@ def get_schur_complement(lattice, cell_index=None, elements_per_strut="gmsh", ct
     return out
 
 
+def schur_gradients(lattice, cell, radii_params, elements_per_strut="gmsh", ctx=None):
+    """Drop-in for ``LatticeSim._compute_schur_gradients(cell, radii_params) -> [dS/dr_j]`` (lattice_sim.py:1020-1054).
+    The reference differentiates ``get_schur_complement`` by central finite differences (2 n_geom extra condensations,
+    ~1e-6 relative noise); here dS_j = E^T (dK/dr_j) E is evaluated analytically by ``lat_schur_batch`` in the same
+    launch that condenses the cell.  Element radius = ``radii_params[beam.type_beam]`` times the penalisation factor
+    of the beam (x1.5 on ``beam_mod`` segments, beam.py:405-436), exactly what ``change_beam_radius`` would set."""
+    import torch
+    cell.define_node_order_to_simulate()
+    mesh = flatten_lattice(lattice, cell.index, elements_per_strut)
+    loc = {int(i): k for k, i in enumerate(mesh.point_index)}
+    bnd = np.array([loc[p.index] for p in cell.node_in_order_simulation], dtype=np.int64)
+    E, nu = material_constants(lattice)
+    ctx = ctx or L.Context()
+    perm, xyz, l0, l1 = local_cell_mesh(mesh, bnd)
+    radii_params = [float(r) for r in radii_params]
+    types = np.asarray(mesh.type_of_elem, dtype=np.int64)
+    if types.max(initial=0) >= len(radii_params):
+        raise ValueError("radii_params has fewer entries than the cell has beam types")
+    rad = np.asarray(radii_params)[types] * mesh.chain
+    dev = ctx.device
+    t = lambda a, d: torch.from_numpy(np.ascontiguousarray(a, dtype=d)).to(dev)
+    S, dS = ctx.schur_batch(t(xyz[None], np.float64), t(l0, np.int32), t(l1, np.int32), t(rad[None], np.float64), len(bnd),
+                            E, nu, KAPPA, elem_group=t(types, np.int32), chain=t(mesh.chain, np.float64),
+                            n_grad=len(radii_params))
+    out = dS[0].cpu().numpy()
+    if not np.isfinite(out).all():
+        raise RuntimeError("Schur sensitivities: interior stiffness block is not positive definite")
+    return [np.ascontiguousarray(out[j]) for j in range(len(radii_params))]
+
+
 class CellBatch:
     """Topology shared by a batch of cells + per-cell coordinates/radii resident on the GPU."""
 

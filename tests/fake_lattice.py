@@ -109,3 +109,118 @@ class FakeLattice:
                     seen.add(node.index_boundary)
         self.global_displacement_index = idx
         return np.array(out), idx
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Reference-shaped objects rebuilt FROM A DUMP of the reference object graph (tests/golden/objgraph_*.npz,
+# written by tests/golden/make_golden.py::make_objgraph from real pyLatticeDSO objects).  Nothing here comes
+# from the repo's own generator: coordinates, numbering, beam radii / penalisation flags, cell membership,
+# index_boundary, fixed_DOF, imposed values, loads and the (node, DOF) order of get_global_displacement are
+# all read from the dump.
+# ---------------------------------------------------------------------------------------------------------
+class DumpCell:
+    def __init__(self, index, center, radii):
+        self.index = int(index)
+        self.center_point = tuple(float(v) for v in center)
+        self.radii = [float(v) for v in radii]
+        self.points_cell, self.beams_cell = set(), set()
+        self.node_in_order_simulation = None
+        self.schur_complement = None
+
+
+class DumpLattice:
+    material_name = "VeroClear"
+
+    def __init__(self, G):
+        self.cell_size_x = float(G["cell_size_x"])
+        self.max_index_boundary = int(G["max_index_boundary"])
+        self.geom_types = list(range(int(G["n_geom"])))
+        self.points = {}
+        for k, idx in enumerate(G["p_index"]):
+            p = FakePoint(*G["p_xyz"][k], idx)
+            ib = int(G["p_index_boundary"][k])
+            p.index_boundary = None if ib < 0 else ib
+            p.fixed_DOF = [int(v) for v in G["p_fixed"][k]]
+            p.displacement_vector = [float(v) for v in G["p_imposed"][k]]
+            p.applied_force = [float(v) for v in G["p_force"][k]]
+            self.points[int(idx)] = p
+        self.beams = {}
+        for k, idx in enumerate(G["b_index"]):
+            b = FakeBeam(self.points[int(G["b_p1"][k])], self.points[int(G["b_p2"][k])], G["b_radius"][k], idx,
+                         type_beam=int(G["b_type"][k]))
+            b.beam_mod = bool(G["b_mod"][k])
+            b.penalization_coefficient = float(G["b_pen"][k])
+            self.beams[int(idx)] = b
+        self.cells = []
+        for k, idx in enumerate(G["c_index"]):
+            c = DumpCell(idx, G["c_center"][k], G["c_radii"][k])
+            c.points_cell = {self.points[int(i)] for i in G["c_points"][G["c_points_ptr"][k]: G["c_points_ptr"][k + 1]]}
+            c.beams_cell = {self.beams[int(i)] for i in G["c_beams"][G["c_beams_ptr"][k]: G["c_beams_ptr"][k + 1]]}
+            self.cells.append(c)
+        self._order = [(int(n), int(d)) for n, d in G["xsol_order"]]
+        self.global_displacement_index = None
+
+    def get_number_cells(self):
+        return len(self.cells)
+
+    def get_global_displacement(self):
+        """LatticeSim.get_global_displacement (lattice_sim.py:502-542) in the ORDER the reference produced (dumped)."""
+        vals = [self.points[n].displacement_vector[d] for n, d in self._order]
+        self.global_displacement_index = [self.points[n].index_boundary for n, _ in self._order]
+        return np.array(vals), self.global_displacement_index
+
+
+def lattice_from_dump(G):
+    return DumpLattice(G)
+
+
+class DumpDdmLattice:
+    """DDM view of a reference lattice rebuilt from tests/golden/objgraph_ddm_*.npz: cell-boundary nodes, the
+    reference's free-DOF numbering (Point.global_free_DOF_index), per-cell boundary-node order and Schur matrix."""
+    material_name = "VeroClear"
+
+    def __init__(self, G):
+        self.cell_size_x = float(G["cell_size_x"])
+        self.max_index_boundary = int(G["max_index_boundary"])
+        self._free_DOF = int(G["free_DOF"])
+        self.free_DOF = None
+        self.points = {}
+        self._gfree = {}
+        for k, idx in enumerate(G["p_index"]):
+            p = FakePoint(*G["p_xyz"][k], idx)
+            ib = int(G["p_index_boundary"][k])
+            p.index_boundary = None if ib < 0 else ib
+            p.fixed_DOF = [int(v) for v in G["p_fixed"][k]]
+            p.displacement_vector = [float(v) for v in G["p_imposed"][k]]
+            p.applied_force = [float(v) for v in G["p_force"][k]]
+            self.points[int(idx)] = p
+            self._gfree[int(idx)] = [None if v < 0 else int(v) for v in G["p_free_index"][k]]
+        S = np.array(G["schur_shared"])
+        self.cells = []
+        for k, idx in enumerate(G["c_index"]):
+            c = DumpCell(idx, (0.0, 0.0, 0.0), [0.05])
+            c.node_in_order_simulation = [self.points[int(i)] for i in G["cell_node_order"][k]]
+            c.points_cell = set(c.node_in_order_simulation)
+            c.schur_complement = S
+            c.define_node_order_to_simulate = lambda: None
+            self.cells.append(c)
+        self._order = [(int(n), int(d)) for n, d in G["xsol_order"]]
+        self.global_displacement_index = None
+        self.python_loop_calls = 0
+
+    def define_free_DOF(self):
+        self.free_DOF = self._free_DOF
+
+    def set_global_free_DOF_index(self):
+        for idx, p in self.points.items():
+            p.global_free_DOF_index = list(self._gfree[idx])
+
+    def get_global_displacement(self):
+        vals = [self.points[n].displacement_vector[d] for n, d in self._order]
+        self.global_displacement_index = [self.points[n].index_boundary for n, _ in self._order]
+        return np.array(vals), self.global_displacement_index
+
+    def calculate_reaction_force_global(self, v, rightHandSide=False):
+        """The reference's Python loop over all cells (lattice_sim.py:1180-1252): must NEVER run on the B200 path."""
+        self.python_loop_calls += 1
+        raise AssertionError("the device path called the Python cell loop")

@@ -21,6 +21,14 @@ What it freezes:
 * grad_loop_*.npz        reference-in-the-loop compliance and gradient: the
                          reference's OWN LatticeOpti.objective/gradient
                          (lattice_opti.py:430-465,701-731) on a 3x1x1 BCC lattice.
+* objgraph_*.npz         the reference OBJECT GRAPH of a penalised 3x2x2 BCC lattice and of a graded
+                         2x2x3 Octet lattice (points, beams, cells, index_boundary, fixed_DOF, imposed
+                         values, loads) plus what the reference's own write-back leaves on it when
+                         fed the oracle's FEM solution: Point.displacement_vector, the k-fold
+                         accumulated Point.reaction_force_vector (point.py:372-385 through
+                         full_scale_lattice_simulation.py:111-120) and LatticeSim.get_global_displacement()
+                         with its (node, DOF) order.  The GPU drop-in test rebuilds duck-typed objects
+                         FROM THIS DUMP (tests/fake_lattice.lattice_from_dump), not from the repo's generator.
 * pcg_reference.npz      inputs/outputs of the reference's OWN
                          conjugate_gradient_solver (conjugate_gradient_solver.py)
                          on small SPD systems, including alpha-clamp and restart.
@@ -240,6 +248,156 @@ def make_c1_parity(ls):
                         reactions_points_oracle=R.reshape(-1, 6)[:npnt], n_dof=np.int64(mesh.n_dof), **arr)
 
 
+def make_objgraph(ls):
+    """Dump the reference object graph + the result of the reference's own write-back methods (module docstring)."""
+    cases = {
+        "bcc322_pen": (base_cfg("BCC", (3, 2, 2), [0.05], True, True, {"boundary_conditions": {
+            "Displacement": {"Fixed": {"Surface": ["Zmin"], "DOF": ["X", "Y", "Z", "RX", "RY", "RZ"], "Value": [0, 0, 0, 0, 0, 0]},
+                             "Load": {"Surface": ["Zmax"], "DOF": ["Z"], "Value": [-0.01]}},
+            "Force": {"Push": {"Surface": ["Xmax"], "DOF": ["X", "Y"], "Value": [0.3, -0.1]}}}}), {}),
+        "octet223_graded": (base_cfg("Octet", (2, 2, 3), [0.03], False, False, {
+            "gradient": {"radii": {"rule": "linear", "direction": [False, False, True], "parameters": [0.0, 0.0, 0.2]}},
+            "boundary_conditions": {
+                "Displacement": {"Fixed": {"Surface": ["Xmin"], "DOF": ["X", "Y", "Z", "RX", "RY", "RZ"], "Value": [0, 0, 0, 0, 0, 0]}},
+                "Force": {"Pull": {"Surface": ["Xmax"], "DOF": ["Z"], "Value": [-0.2]}}}}), {}),
+    }
+    for name, (cfg, _) in cases.items():
+        refshim.set_inline_presets({"g": cfg})
+        with quiet():
+            lat = ls.LatticeSim("g", enable_domain_decomposition_solver=False)
+        mesh = M.flatten_lattice(lat, None, "gmsh")
+        pts = mesh.meta["points"]                       # node.index order
+        loc = {p.index: k for k, p in enumerate(pts)}
+        beams = {}
+        for c in lat.cells:
+            for b in c.beams_cell:
+                beams[b.index] = b
+        border = sorted(beams)
+        # ---- inputs
+        P = dict(p_index=np.array([p.index for p in pts], dtype=np.int64),
+                 p_xyz=np.array([[p.x, p.y, p.z] for p in pts], dtype=np.float64),
+                 p_index_boundary=np.array([-1 if p.index_boundary is None else p.index_boundary for p in pts], dtype=np.int64),
+                 p_fixed=np.array([[int(bool(v)) for v in p.fixed_DOF] for p in pts], dtype=np.uint8),
+                 p_imposed=np.array([list(p.displacement_vector) for p in pts], dtype=np.float64),
+                 p_force=np.array([list(p.applied_force) for p in pts], dtype=np.float64))
+        B = dict(b_index=np.array(border, dtype=np.int64),
+                 b_p1=np.array([beams[i].point1.index for i in border], dtype=np.int64),
+                 b_p2=np.array([beams[i].point2.index for i in border], dtype=np.int64),
+                 b_radius=np.array([beams[i].radius for i in border], dtype=np.float64),
+                 b_mod=np.array([bool(getattr(beams[i], "beam_mod", False)) for i in border], dtype=np.uint8),
+                 b_type=np.array([int(getattr(beams[i], "type_beam", 0)) for i in border], dtype=np.int64),
+                 b_pen=np.array([float(getattr(beams[i], "penalization_coefficient", 1.5)) for i in border], dtype=np.float64))
+        cp_ptr, cp, cb_ptr, cb = [0], [], [0], []
+        for c in lat.cells:
+            cp.extend(sorted(p.index for p in c.points_cell)); cp_ptr.append(len(cp))
+            cb.extend(sorted(b.index for b in c.beams_cell)); cb_ptr.append(len(cb))
+        Cc = dict(c_index=np.array([c.index for c in lat.cells], dtype=np.int64),
+                  c_points_ptr=np.array(cp_ptr, dtype=np.int64), c_points=np.array(cp, dtype=np.int64),
+                  c_beams_ptr=np.array(cb_ptr, dtype=np.int64), c_beams=np.array(cb, dtype=np.int64),
+                  c_center=np.array([list(c.center_point) for c in lat.cells], dtype=np.float64),
+                  c_radii=np.array([list(c.radii) for c in lat.cells], dtype=np.float64))
+        # ---- (node, DOF) order of get_global_displacement: inject a code into every displacement entry
+        saved = [list(p.displacement_vector) for p in pts]
+        for p in pts:
+            p.displacement_vector[:] = [float(p.index * 6 + d + 1) for d in range(6)]
+        with quiet():
+            codes, gdi = lat.get_global_displacement()
+        order = np.array([[(int(c) - 1) // 6, (int(c) - 1) % 6] for c in codes], dtype=np.int64)
+        for p, v in zip(pts, saved):
+            p.displacement_vector[:] = v
+        # ---- the oracle's FEM solution, written back by the reference's own objects
+        fixed, g, f = M.bc_arrays_from_lattice(lat, mesh)            # reference quirk kept: loads once per owning cell
+        K = orc.assemble_csr(mesh.xyz, np.stack([mesh.en0, mesh.en1], 1), mesh.rad, E_MOD, NU)
+        u, R = orc.solve_static(K, fixed.astype(bool), g, f)
+        un, Rn = u.reshape(-1, 6), R.reshape(-1, 6)
+        for k, p in enumerate(pts):
+            p.displacement_vector[:] = [float(v) for v in un[k]]
+            p.reaction_force_vector = [0.0] * 6
+        for c in lat.cells:                                          # full_scale_lattice_simulation.py:111-120
+            for node in c.points_cell:
+                if 1 in node.fixed_DOF:
+                    node.set_reaction_force([float(v) for v in Rn[loc[node.index]]])
+        with quiet():
+            xsol, gdi = lat.get_global_displacement()
+        out = dict(P, **B, **Cc, xsol_order=order, xsol_expected=np.asarray(xsol, dtype=np.float64),
+                   global_displacement_index=np.asarray(gdi, dtype=np.int64),
+                   u_points_expected=np.array([list(p.displacement_vector) for p in pts], dtype=np.float64),
+                   reaction_points_expected=np.array([list(p.reaction_force_vector) for p in pts], dtype=np.float64),
+                   cell_size_x=np.float64(lat.cell_size_x), max_index_boundary=np.int64(lat.max_index_boundary),
+                   n_geom=np.int64(len(lat.geom_types)))
+        np.savez_compressed(os.path.join(HERE, f"objgraph_{name}.npz"), **out)
+        kmax = max(sum(1 for c in lat.cells if p in c.points_cell) for p in pts)
+        print(f"objgraph_{name}: points={len(pts)} beams={len(border)} cells={len(lat.cells)} fe_dof={mesh.n_dof} "
+              f"fixed={int(fixed.sum())} xsol={len(xsol)} max cells per node={kmax}")
+
+
+def make_ddm_objects(ls):
+    """objgraph_ddm_bcc322.npz: the DDM view of a penalised 3x2x2 BCC lattice (periodic joints: one Schur matrix shared
+    by all cells, computed by the oracle) together with what the REFERENCE'S OWN code computes on it:
+    y = LatticeSim.calculate_reaction_force_global(v) for a random v (lattice_sim.py:1180-1252, the Python loop over
+    cells), and (xsol, b) of LatticeSim.solve_DDM (:1111-1176, exact preconditioner)."""
+    ddm = {"DDM": {"enable_preconditioner": True, "preconditioner_type": "exact", "max_iterations": 500,
+                   "schur_complement_computation": {"type": "exact"}}}
+    bc = {"Displacement": {"Fixed": {"Surface": ["Xmin"], "DOF": ["X", "Y", "Z", "RX", "RY", "RZ"], "Value": [0, 0, 0, 0, 0, 0]},
+                           "Load": {"Surface": ["Xmax"], "DOF": ["Z"], "Value": [-0.01]}},
+          "Force": {"Push": {"Surface": ["Zmax"], "DOF": ["Y"], "Value": [0.05]}}}
+    cfg = base_cfg("BCC", (3, 2, 2), [0.05], True, True, {"simulation_parameters": ddm, "boundary_conditions": bc})
+    refshim.set_inline_presets({"d": cfg})
+    orig = ls.get_schur_complement
+    try:
+        _oracle_schur_rebind(ls)
+        with quiet():
+            lat = ls.LatticeSim("d", enable_domain_decomposition_solver=True)
+            xsol, info, gdi, b = lat.solve_DDM()
+        u_after = {}
+        for c in lat.cells:
+            for p in c.points_cell:
+                if p.index_boundary is not None:
+                    u_after[p.index] = (list(p.displacement_vector), list(p.reaction_force_vector))
+        rng = np.random.default_rng(11)
+        v = rng.standard_normal(lat.free_DOF) * 1e-3
+        with quiet():
+            lat._initialize_displacement()
+            y = np.asarray(lat.calculate_reaction_force_global(v), dtype=np.float64)
+            lat._initialize_displacement()
+            lat.set_boundary_conditions()
+        mesh = M.flatten_lattice(lat, None, "gmsh")
+        pts = mesh.meta["points"]
+        S = np.asarray(lat.cells[0].schur_complement, dtype=np.float64)
+        assert all(np.array_equal(np.asarray(c.schur_complement), S) for c in lat.cells)
+        order = np.array([[p.index for p in c.node_in_order_simulation] for c in lat.cells], dtype=np.int64)
+        gfree = np.array([[-1 if (p.fixed_DOF[d] or p.index_boundary is None or p.global_free_DOF_index[d] is None)
+                           else int(p.global_free_DOF_index[d]) for d in range(6)] for p in pts], dtype=np.int64)
+        out = dict(p_index=np.array([p.index for p in pts], dtype=np.int64),
+                   p_xyz=np.array([[p.x, p.y, p.z] for p in pts]),
+                   p_index_boundary=np.array([-1 if p.index_boundary is None else p.index_boundary for p in pts], dtype=np.int64),
+                   p_fixed=np.array([[int(bool(q)) for q in p.fixed_DOF] for p in pts], dtype=np.uint8),
+                   p_imposed=np.array([list(p.displacement_vector) for p in pts]),
+                   p_force=np.array([list(p.applied_force) for p in pts]),
+                   p_free_index=gfree, cell_node_order=order, c_index=np.array([c.index for c in lat.cells], dtype=np.int64),
+                   schur_shared=S, v=v, y_reference=y, xsol_reference=np.asarray(xsol, dtype=np.float64),
+                   b_reference=np.asarray(b, dtype=np.float64), info_reference=np.int64(info),
+                   global_displacement_index=np.asarray(gdi, dtype=np.int64), free_DOF=np.int64(lat.free_DOF),
+                   max_index_boundary=np.int64(lat.max_index_boundary), cell_size_x=np.float64(lat.cell_size_x))
+        # (node, DOF) order of get_global_displacement, as in make_objgraph
+        saved = [list(p.displacement_vector) for p in pts]
+        for p in pts:
+            p.displacement_vector[:] = [float(p.index * 6 + d + 1) for d in range(6)]
+        with quiet():
+            codes, _ = lat.get_global_displacement()
+        out["xsol_order"] = np.array([[(int(c) - 1) // 6, (int(c) - 1) % 6] for c in codes], dtype=np.int64)
+        for p, q in zip(pts, saved):
+            p.displacement_vector[:] = q
+        bnd = [p for p in pts if p.index_boundary is not None]
+        out["u_boundary_reference"] = np.array([u_after[p.index][0] for p in bnd])
+        out["boundary_point_index"] = np.array([p.index for p in bnd], dtype=np.int64)
+        np.savez_compressed(os.path.join(HERE, "objgraph_ddm_bcc322.npz"), **out)
+        print(f"objgraph_ddm_bcc322: free_DOF={lat.free_DOF} cells={len(lat.cells)} info={info} |y|={np.abs(y).max():.3e} "
+              f"|xsol|={np.abs(xsol).max():.3e}")
+    finally:
+        ls.get_schur_complement = orig
+
+
 def make_pcg(ls):
     import importlib
     cgm = importlib.import_module("pyLatticeSim.conjugate_gradient_solver")
@@ -279,6 +437,8 @@ def main():
     make_ddm_loop(ls)
     make_grad_loop(ls)
     make_c1_parity(ls)
+    make_objgraph(ls)
+    make_ddm_objects(ls)
     make_pcg(ls)
     tot = sum(os.path.getsize(os.path.join(HERE, f)) for f in os.listdir(HERE) if f.endswith(".npz"))
     print(f"total fixture size {tot / 1e6:.2f} MB")
