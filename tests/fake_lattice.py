@@ -126,6 +126,16 @@ class DumpCell:
         self.points_cell, self.beams_cell = set(), set()
         self.node_in_order_simulation = None
         self.schur_complement = None
+        self.cell_size = (1.0, 1.0, 1.0)
+
+    def define_node_order_to_simulate(self):   # cell.py:611-680 (face priority, in-plane sort) on the dumped nodes
+        pts = [p for p in self.points_cell if p.index_boundary is not None]
+        xyz = np.array([[p.x, p.y, p.z] for p in pts])
+        h = [0.5 * s for s in self.cell_size]
+        c = self.center_point
+        box = (c[0] - h[0], c[0] + h[0], c[1] - h[1], c[1] + h[1], c[2] - h[2], c[2] + h[2])
+        order = bcc_cell_order_nodes(xyz, box)
+        self.node_in_order_simulation = [pts[i] for i in order]
 
 
 class DumpLattice:

@@ -215,7 +215,9 @@ def test_conjugate_gradient_solver_accepts_the_reference_linear_operator(ctx):
     from pylatticedso_b200.pcg import conjugate_gradient_solver
     G, lat = _ddm_dump()
     n = int(G["free_DOF"])
-    A = LinearOperator(shape=(n, n), matvec=lat.calculate_reaction_force_global)
+    # (dtype given: without it scipy probes matvec once at construction -- in the reference that is one pass of the
+    #  Python loop before conjugate_gradient_solver is even called, nothing the solver can avoid)
+    A = LinearOperator(shape=(n, n), matvec=lat.calculate_reaction_force_global, dtype=float)
     seen = []
     x, info = conjugate_gradient_solver(A, G["b_reference"], M=object(), maxiter=2000, tol=1e-11, mintol=1e-14,
                                         restart_every=500000, alpha_max=100, callback=seen.append)
@@ -237,3 +239,30 @@ def test_solve_ddm_b200_equals_the_reference_solve_ddm(ctx):
     assert abs(np.linalg.norm(b) - np.linalg.norm(G["b_reference"])) <= 1e-10 * np.linalg.norm(G["b_reference"])
     ub = np.array([lat.points[int(i)].displacement_vector for i in G["boundary_point_index"]])
     assert np.abs(ub - G["u_boundary_reference"]).max() <= 1e-7 * np.abs(G["u_boundary_reference"]).max()
+
+
+def test_schur_gradients_dropin_on_dumped_reference_cell(ctx):
+    """schur.schur_gradients (the rebinding of LatticeSim._compute_schur_gradients, lattice_sim.py:1020-1054) on a
+    penalised BCC cell rebuilt from the reference dump: analytic dS/dr against the reference's recipe -- a central
+    finite difference of the cell Schur complement with every beam of the cell set to r (x1.5 on beam_mod segments)."""
+    from conftest import load_golden
+    from fake_lattice import lattice_from_dump
+    from pylatticedso_b200.schur import get_schur_complement, schur_gradients
+    G = load_golden("objgraph_bcc322_pen.npz")
+    lat = lattice_from_dump(G)
+    cell = lat.cells[5]
+    r0 = 0.05
+    dS = schur_gradients(lat, cell, [r0], elements_per_strut="gmsh", ctx=ctx)
+    assert len(dS) == 1 and dS[0].shape == (48, 48)
+
+    def schur_at(r):
+        for b in cell.beams_cell:
+            b.radius = r * (b.penalization_coefficient if b.beam_mod else 1.0)
+        return orc.cell_schur_from_lattice(lat, cell.index, E_MOD, NU, "gmsh")
+    h = 1e-6
+    fd = (schur_at(r0 + h) - schur_at(r0 - h)) / (2 * h)
+    schur_at(r0)
+    assert np.abs(dS[0] - fd).max() <= 2e-6 * np.abs(fd).max()
+    S = get_schur_complement(lat, cell.index, elements_per_strut="gmsh", ctx=ctx)
+    So = orc.cell_schur_from_lattice(lat, cell.index, E_MOD, NU, "gmsh")
+    assert np.abs(S - So).max() <= 1e-11 * np.abs(So).max()
