@@ -288,6 +288,23 @@ int lat_schur_batch_chains(lat_ctx* ctx, const double* xyz, const int32_t* len0,
                            const int32_t* chain_a, const int32_t* chain_b, int32_t n_chains, int32_t n_joints,
                            int32_t n_bnd_nodes, double young, double nu, double kappa, double* S);
 
+/* Same S_c (and, optionally, the analytic sensitivities dS_c/dr_g) through the strut pre-pass with the warp-level
+ * kernel for STAR cells: one interior joint (joint index n_bnd_nodes) joined to every boundary joint by exactly one strut
+ * -- a BCC cell at ANY subdivision.  A half-warp owns a cell: S(k,l) = delta_kl D_k - O_k Kcc^-1 O_l^T from the 6x6 blocks of
+ * the condensed struts, Kcc = sum_k C_k inverted in registers; no n x n matrix and no CTA barrier (k_schur_star).
+ *   chain_group int32[n_chains]: radius group of every strut (all elements of a strut share it), drad_chain[n_loc_elem]:
+ *   d rad_e / d r_group (NULL -> 1); dS: [n_cells][n_grad][6 n_bnd][6 n_bnd] or NULL.  The strut pre-pass is differentiated
+ *   in forward mode, so the sensitivities no longer need lat_schur_batch's dense route over all strut-interior DOFs
+ *   (replaces the central finite differences of lattice_sim.py:1020-1054).
+ * Other topologies: S falls through to lat_schur_batch_chains; with dS != NULL the call returns LAT_ERR_UNSUPPORTED
+ * (use lat_schur_batch).  [syncs: two small D2H copies of the chain ends] */
+int lat_schur_batch_struts(lat_ctx* ctx, const double* xyz, const int32_t* len0, const int32_t* len1,
+                           const double* rad, int64_t n_cells, int32_t n_loc_nodes, int32_t n_loc_elem,
+                           const int32_t* chain_ptr, const int32_t* chain_elem, const int32_t* chain_flip,
+                           const int32_t* chain_a, const int32_t* chain_b, int32_t n_chains, int32_t n_joints,
+                           int32_t n_bnd_nodes, double young, double nu, double kappa, double* S,
+                           const int32_t* chain_group, const double* drad_chain, int32_t n_grad, double* dS);
+
 /* ---- joint-only global assembly (B200 design choice; exact static condensation of the struts) --------------
  * The reference applies loads and constraints to lattice points only (full_scale_lattice_simulation.py:77-153), so
  * eliminating the strut-interior nodes changes neither the joint displacements nor the joint reactions.  Every chain

@@ -1,5 +1,7 @@
 // lattice_schur.cu -- batched per-cell Schur complements (dense partial Cholesky, one CTA per
 // cell) and the DDM interface operator (batched S_c GEMV with gather/scatter).  sm_100a.
+#include <vector>
+
 #include "common.cuh"
 
 static constexpr int SCHUR_BLOCK = 256;
@@ -670,6 +672,402 @@ extern "C" int lat_schur_batch_chains(lat_ctx* ctx, const double* xyz, const int
     LAT_CUDA(ctx, cudaFuncSetAttribute(k_schur_dense<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LAT_LAUNCH(ctx, (k_schur_dense<false, true>), (unsigned)grid, SCHUR_BLOCK, smem, nullptr, chain_a, chain_b, nullptr, n_cells,
                n_joints, n_bnd_nodes, n_chains, young, nu, kappa, S, ws, nullptr, nullptr, 0, nullptr, sup);
+  }
+  return LAT_OK;
+}
+
+
+// ===========================================================================
+// A7, star cells: warp-level Schur complement (+ analytic dS/dr) of cells with ONE interior joint
+// ===========================================================================
+// After the strut pre-pass a BCC cell is 8 corner joints + 1 centre joint joined by 8 super-elements: 54 DOFs with SIX
+// interior pivots.  k_schur_dense<SUPER> spends a 256-thread CTA, a 54x55 shared-memory matrix and ~20 CTA barriers on
+// that (0.05 of HBM); here a HALF-WARP owns a cell:
+//   S(k, l) = delta_kl D_k - O_k Kcc^-1 O_l^T,   Kcc = sum_k C_k
+// with D_k / C_k the corner / centre diagonal 6x6 blocks and O_k the corner-row, centre-column block of strut k.  Lane k
+// builds the blocks of strut k from its 16 SupCoef scalars, one lane inverts the 6x6 Kcc in registers, lane h then owns
+// rows h, h+16, ... of S and writes them with 128-bit stores.  No n x n matrix, no CTA barrier.
+// Sensitivities: the strut pre-pass is differentiated in forward mode (Dual below) w.r.t. the radius parameter of the
+// strut's group, giving dC, dO, dD, and
+//   dS(k, l) = delta_kl dD_k - dW_k O_l^T - W_k dO_l^T,   W_k = O_k Kcc^-1,   dW_k = dO_k Kcc^-1 - W_k dKcc Kcc^-1
+// -- the gradients no longer need the dense 822-interior-DOF route (0.07 M cells/s in round 1).
+struct Dual {
+  double v, d;
+  __host__ __device__ Dual() : v(0.0), d(0.0) {}
+  __host__ __device__ Dual(double a) : v(a), d(0.0) {}
+  __host__ __device__ Dual(double a, double b) : v(a), d(b) {}
+};
+__host__ __device__ __forceinline__ Dual operator+(Dual a, Dual b) { return Dual(a.v + b.v, a.d + b.d); }
+__host__ __device__ __forceinline__ Dual operator-(Dual a, Dual b) { return Dual(a.v - b.v, a.d - b.d); }
+__host__ __device__ __forceinline__ Dual operator-(Dual a) { return Dual(-a.v, -a.d); }
+__host__ __device__ __forceinline__ Dual operator*(Dual a, Dual b) { return Dual(a.v * b.v, a.d * b.v + a.v * b.d); }
+__host__ __device__ __forceinline__ Dual operator/(Dual a, Dual b) { const double q = a.v / b.v; return Dual(q, (a.d - q * b.d) / b.v); }
+
+// k_chain_condense in dual numbers: sup = value, dsup = d/d(rho) with r_e = r_e(rho), dr_e/drho = drad_chain[e]
+// (1.5 on penalised segments, NULL -> 1).  Same recursion, same order of operations for the value part.
+__global__ void __launch_bounds__(128) k_chain_condense_dual(
+    const double* __restrict__ xyz, const int32_t* __restrict__ len0, const int32_t* __restrict__ len1,
+    const double* __restrict__ rad, const double* __restrict__ drad_chain, int64_t n_cells, int nn, int ne,
+    const int32_t* __restrict__ chain_ptr, const int32_t* __restrict__ chain_elem, const int32_t* __restrict__ chain_flip,
+    int n_chains, double young, double nu, double kappa, SupCoef* __restrict__ sup, SupCoef* __restrict__ dsup) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_cells * n_chains) return;
+  const int64_t c = w / n_chains;
+  const int ch = (int)(w - c * n_chains);
+  const double* cx = xyz + c * (int64_t)nn * 3;
+  const double* cr = rad + c * (int64_t)ne;
+  const double PI = 3.14159265358979323846, G = young / (2.0 * (1.0 + nu));
+  Dual flex_ax, flex_tor;
+  double tx = 0.0, ty = 0.0, tz = 0.0;
+  Dual aa[2][2], ak[2][2], kk[2][2];
+  for (int q = chain_ptr[ch]; q < chain_ptr[ch + 1]; ++q) {
+    const int e = chain_elem[q];
+    const bool fl = chain_flip[q] != 0;
+    const int a = fl ? len1[e] : len0[e], b = fl ? len0[e] : len1[e];
+    const double dx = cx[b * 3] - cx[a * 3], dy = cx[b * 3 + 1] - cx[a * 3 + 1], dz = cx[b * 3 + 2] - cx[a * 3 + 2];
+    const double L = sqrt(dx * dx + dy * dy + dz * dz), iL = 1.0 / L;
+    const Dual r(cr[e], drad_chain ? drad_chain[e] : 1.0);
+    const Dual S = Dual(PI) * r * r, I = Dual(PI * 0.25) * r * r * r * r;
+    const Dual ES = Dual(young) * S, GS = Dual(G * kappa) * S, EI = Dual(young) * I, GJ = Dual(G * 2.0) * I;
+    flex_ax = flex_ax + Dual(L) / ES;
+    flex_tor = flex_tor + Dual(L) / GJ;
+    const Dual g1 = GS * Dual(iL), g2 = Dual(0.5) * GS, dp = Dual(0.25 * L) * GS + EI * Dual(iL), dm = Dual(0.25 * L) * GS - EI * Dual(iL);
+    if (q == chain_ptr[ch]) {
+      tx = dx * iL; ty = dy * iL; tz = dz * iL;
+      aa[0][0] = g1; aa[0][1] = -g2; aa[1][0] = -g2; aa[1][1] = dp;
+      ak[0][0] = -g1; ak[0][1] = -g2; ak[1][0] = g2; ak[1][1] = dm;
+      kk[0][0] = g1; kk[0][1] = g2; kk[1][0] = g2; kk[1][1] = dp;
+      continue;
+    }
+    const Dual p00 = kk[0][0] + g1, p01 = kk[0][1] - g2, p11 = kk[1][1] + dp;
+    const Dual idet = Dual(1.0) / (p00 * p11 - p01 * p01);
+    const Dual i00 = p11 * idet, i01 = -(p01 * idet), i11 = p00 * idet;
+    const Dual ekn[2][2] = {{-g1, -g2}, {g2, dm}};
+    const Dual enn[2][2] = {{g1, g2}, {g2, dp}};
+    Dual x[2][2], y[2][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      x[i][0] = ak[i][0] * i00 + ak[i][1] * i01;
+      x[i][1] = ak[i][0] * i01 + ak[i][1] * i11;
+      y[i][0] = ekn[0][i] * i00 + ekn[1][i] * i01;
+      y[i][1] = ekn[0][i] * i01 + ekn[1][i] * i11;
+    }
+    Dual naa[2][2], nak[2][2], nkk[2][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        naa[i][j] = aa[i][j] - (x[i][0] * ak[j][0] + x[i][1] * ak[j][1]);
+        nak[i][j] = -(x[i][0] * ekn[0][j] + x[i][1] * ekn[1][j]);
+        nkk[i][j] = enn[i][j] - (y[i][0] * ekn[0][j] + y[i][1] * ekn[1][j]);
+      }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { aa[i][j] = naa[i][j]; ak[i][j] = nak[i][j]; kk[i][j] = nkk[i][j]; }
+  }
+  const Dual kax = Dual(1.0) / flex_ax, ktor = Dual(1.0) / flex_tor;
+  SupCoef o, d;
+  o.tx = tx; o.ty = ty; o.tz = tz; d.tx = tx; d.ty = ty; d.tz = tz;
+  o.kax = kax.v; d.kax = kax.d; o.ktor = ktor.v; d.ktor = ktor.d;
+  const Dual m01 = Dual(0.5) * (aa[0][1] + aa[1][0]), m23 = Dual(0.5) * (kk[0][1] + kk[1][0]);
+  const Dual mm[10] = {aa[0][0], m01, ak[0][0], ak[0][1], aa[1][1], ak[1][0], ak[1][1], kk[0][0], m23, kk[1][1]};
+#pragma unroll
+  for (int k = 0; k < 10; ++k) { o.m[k] = mm[k].v; d.m[k] = mm[k].d; }
+  o.pad = 0.0; d.pad = 0.0;
+  sup[w] = o;
+  dsup[w] = d;
+}
+
+// Topology of a star cell, shared by all cells of the batch (device arrays of n_struts entries):
+//   corner[k]  boundary joint (= block row of S) at the far end of strut k;  cend[k]  which end (0 / 1) is the centre
+//   strut_of[j] strut whose corner is boundary joint j;  group[k]  radius group of strut k (sensitivities)
+static constexpr int STAR_CELLS_PER_CTA = 8;         // 128 threads: a half-warp per cell
+static constexpr int STAR_MAX_STRUTS = 16;           // one strut per lane of the half-warp
+
+__device__ __forceinline__ void sup_block(const SupCoef& s, int re, int ce, double* dst /*[36] shared*/) {
+  double q[36];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) q[k] = 0.0;
+  sup_block_accum(s, re, ce, q);
+#pragma unroll
+  for (int k = 0; k < 36; ++k) dst[k] = q[k];
+}
+
+// 12 (or, for the odd tail, 6) consecutive doubles of a row of S; rows start at multiples of 48 n_s bytes, so the
+// 96-byte pieces are 32-byte aligned whenever the row length is a multiple of 4 doubles (n_s even)
+__device__ __forceinline__ void star_store(double* dst, const double (&v)[12], bool both) {
+  if (both && (reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "d"(v[4 * q]), "d"(v[4 * q + 1]), "d"(v[4 * q + 2]),
+                   "d"(v[4 * q + 3]) : "memory");
+  } else {
+    double2* o2 = reinterpret_cast<double2*>(dst);
+#pragma unroll
+    for (int q = 0; q < (both ? 6 : 3); ++q) o2[q] = make_double2(v[2 * q], v[2 * q + 1]);
+  }
+}
+
+template <bool GRAD>
+__global__ void __launch_bounds__(16 * STAR_CELLS_PER_CTA) k_schur_star(
+    const SupCoef* __restrict__ sup, const SupCoef* __restrict__ dsup, const int32_t* __restrict__ cend,
+    const int32_t* __restrict__ strut_of, const int32_t* __restrict__ group, int64_t n_cells, int ns, int n_grad,
+    double* __restrict__ S, double* __restrict__ dS) {
+  extern __shared__ __align__(16) double star_smem[];
+  // per cell slot: O, W, D (+ dO, dW, dD), then Kinv[36], T[36]
+  const int per_cell = (GRAD ? 6 : 3) * ns * 36 + 72;
+  const int slot = threadIdx.x >> 4, h = threadIdx.x & 15;
+  double* base = star_smem + (size_t)slot * per_cell;
+  double* sO = base;
+  double* sW = sO + ns * 36;
+  double* sD = sW + ns * 36;
+  double* sdO = GRAD ? sD + ns * 36 : nullptr;
+  double* sdW = GRAD ? sdO + ns * 36 : nullptr;
+  double* sdD = GRAD ? sdW + ns * 36 : nullptr;
+  double* sK = base + (GRAD ? 6 : 3) * ns * 36;   // Kcc^-1
+  double* sT = sK + 36;                           // scratch 6x6
+  const int nB = 6 * ns;
+  for (int64_t cell0 = (int64_t)blockIdx.x * STAR_CELLS_PER_CTA; cell0 < n_cells; cell0 += (int64_t)gridDim.x * STAR_CELLS_PER_CTA) {
+    const int64_t cell = cell0 + slot;
+    const bool live = cell < n_cells;
+    // 1. strut blocks: lane k builds O_k, D_k and (into W's space) C_k
+    if (live && h < ns) {
+      const SupCoef s = sup[cell * ns + h];
+      const int ec = cend[h], eb = ec ^ 1;
+      sup_block(s, eb, ec, sO + h * 36);
+      sup_block(s, eb, eb, sD + h * 36);
+      sup_block(s, ec, ec, sW + h * 36);
+      if (GRAD) {
+        const SupCoef d = dsup[cell * ns + h];
+        sup_block(d, eb, ec, sdO + h * 36);
+        sup_block(d, eb, eb, sdD + h * 36);
+        sup_block(d, ec, ec, sdW + h * 36);
+      }
+    }
+    __syncwarp();
+    // 2. Kcc = sum_k C_k (fixed order), 3. inverse by Gauss-Jordan without pivoting (SPD) in lane 0's registers
+    for (int e = h; e < 36; e += 16) {
+      double acc = 0.0;
+      for (int k = 0; k < ns; ++k) acc += sW[k * 36 + e];
+      sT[e] = acc;
+    }
+    __syncwarp();
+    if (h == 0) {
+      double a[6][6], inv[6][6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { a[i][k] = sT[i * 6 + k]; inv[i][k] = (i == k) ? 1.0 : 0.0; }
+#pragma unroll
+      for (int p = 0; p < 6; ++p) {
+        const double ip = 1.0 / a[p][p];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { a[p][k] *= ip; inv[p][k] *= ip; }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          if (i == p) continue;
+          const double f = a[i][p];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) { a[i][k] -= f * a[p][k]; inv[i][k] -= f * inv[p][k]; }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) sK[i * 6 + k] = 0.5 * (inv[i][k] + inv[k][i]);
+    }
+    __syncwarp();
+    // 4. W_k = O_k Kcc^-1 (lane k)
+    if (h < ns) {
+      double w[36];
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          double acc = 0.0;
+#pragma unroll
+          for (int m = 0; m < 6; ++m) acc = fma(sO[h * 36 + i * 6 + m], sK[m * 6 + j], acc);
+          w[i * 6 + j] = acc;
+        }
+#pragma unroll
+      for (int k = 0; k < 36; ++k) sW[h * 36 + k] = w[k];
+    }
+    __syncwarp();
+    // 5. rows h, h+16, ... of S:  S[i][6 l' + b] = delta D_k[a][b] - sum_m W_k[a][m] O_l[b][m]
+    for (int i = h; i < nB; i += 16) {
+      if (!live) continue;
+      const int j = i / 6, a = i - 6 * j;
+      const int k = strut_of[j];
+      double wr[6];
+#pragma unroll
+      for (int m = 0; m < 6; ++m) wr[m] = sW[k * 36 + a * 6 + m];
+      double* out = S + (cell * nB + i) * (int64_t)nB;
+      // two column joints (12 doubles = three full 32-byte sectors) per step: 256-bit stores; a scattered 128-bit store
+      // costs one L1 wavefront per lane for half a sector (same lesson as k_assemble_rows)
+      for (int jc = 0; jc < ns; jc += 2) {
+        double v[12];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int jcc = jc + half < ns ? jc + half : jc;
+          const int l = strut_of[jcc];
+#pragma unroll
+          for (int b = 0; b < 6; ++b) {
+            double acc = (jcc == j) ? sD[k * 36 + a * 6 + b] : 0.0;
+#pragma unroll
+            for (int m = 0; m < 6; ++m) acc = fma(-wr[m], sO[l * 36 + b * 6 + m], acc);
+            v[half * 6 + b] = acc;
+          }
+        }
+        star_store(out + jc * 6, v, jc + 1 < ns);
+      }
+    }
+    if (GRAD) {
+      for (int gsel = 0; gsel < n_grad; ++gsel) {
+        __syncwarp();
+        // dKcc = sum_{k in g} dC_k  (dC sits in dW's space until dW overwrites it below, so keep it in sT first)
+        for (int e = h; e < 36; e += 16) {
+          double acc = 0.0;
+          for (int k = 0; k < ns; ++k)
+            if (group[k] == gsel) acc += sdW[k * 36 + e];
+          sT[e] = acc;
+        }
+        __syncwarp();
+        // T = dKcc Kcc^-1 (36 entries over the lanes), kept in registers then written back
+        double t_loc[3] = {0.0, 0.0, 0.0};
+        for (int q = 0, e = h; e < 36; e += 16, ++q) {
+          const int i = e / 6, jj = e - 6 * i;
+          double acc = 0.0;
+#pragma unroll
+          for (int m = 0; m < 6; ++m) acc = fma(sT[i * 6 + m], sK[m * 6 + jj], acc);
+          t_loc[q] = acc;
+        }
+        __syncwarp();
+        for (int q = 0, e = h; e < 36; e += 16, ++q) sT[e] = t_loc[q];
+        __syncwarp();
+        // dW_k = [k in g] dO_k Kcc^-1 - W_k T: a row owner needs only the row of ITS strut, computed in registers
+        // (sdW keeps holding dC_k, which the next group needs again)
+        for (int i = h; i < nB; i += 16) {
+          if (!live) continue;
+          const int j = i / 6, a = i - 6 * j;
+          const int k = strut_of[j];
+          const bool kin = group[k] == gsel;
+          double wr[6], dwr[6];
+#pragma unroll
+          for (int m = 0; m < 6; ++m) wr[m] = sW[k * 36 + a * 6 + m];
+#pragma unroll
+          for (int jj = 0; jj < 6; ++jj) {
+            double acc = 0.0;
+#pragma unroll
+            for (int m = 0; m < 6; ++m) {
+              if (kin) acc = fma(sdO[k * 36 + a * 6 + m], sK[m * 6 + jj], acc);
+              acc = fma(-wr[m], sT[m * 6 + jj], acc);
+            }
+            dwr[jj] = acc;
+          }
+          double* out = dS + ((cell * n_grad + gsel) * nB + i) * (int64_t)nB;
+          for (int jc = 0; jc < ns; jc += 2) {
+            double v[12];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int jcc = jc + half < ns ? jc + half : jc;
+              const int l = strut_of[jcc];
+              const bool lin = group[l] == gsel;
+#pragma unroll
+              for (int b = 0; b < 6; ++b) {
+                double acc = (jcc == j && kin) ? sdD[k * 36 + a * 6 + b] : 0.0;
+#pragma unroll
+                for (int m = 0; m < 6; ++m) {
+                  acc = fma(-dwr[m], sO[l * 36 + b * 6 + m], acc);
+                  if (lin) acc = fma(-wr[m], sdO[l * 36 + b * 6 + m], acc);
+                }
+                v[half * 6 + b] = acc;
+              }
+            }
+            star_store(out + jc * 6, v, jc + 1 < ns);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// Host: is this chain topology a star?  (one interior joint = joint n_bnd, every strut joins it to a distinct boundary
+// joint, every boundary joint has a strut).  Fills the device tables of k_schur_star.
+static bool star_topology(const std::vector<int32_t>& ca, const std::vector<int32_t>& cb, int n_joints, int n_bnd,
+                          std::vector<int32_t>* cend, std::vector<int32_t>* strut_of) {
+  const int ns = (int)ca.size();
+  if (n_joints != n_bnd + 1 || ns != n_bnd || ns > STAR_MAX_STRUTS) return false;
+  cend->assign(ns, 0);
+  strut_of->assign(n_bnd, -1);
+  for (int k = 0; k < ns; ++k) {
+    int corner;
+    if (ca[k] == n_bnd && cb[k] < n_bnd) { (*cend)[k] = 0; corner = cb[k]; }
+    else if (cb[k] == n_bnd && ca[k] < n_bnd) { (*cend)[k] = 1; corner = ca[k]; }
+    else return false;
+    if ((*strut_of)[corner] >= 0) return false;
+    (*strut_of)[corner] = k;
+  }
+  return true;
+}
+
+extern "C" int lat_schur_batch_struts(lat_ctx* ctx, const double* xyz, const int32_t* len0, const int32_t* len1,
+                                      const double* rad, int64_t n_cells, int32_t n_loc_nodes, int32_t n_loc_elem,
+                                      const int32_t* chain_ptr, const int32_t* chain_elem, const int32_t* chain_flip,
+                                      const int32_t* chain_a, const int32_t* chain_b, int32_t n_chains, int32_t n_joints,
+                                      int32_t n_bnd_nodes, double young, double nu, double kappa, double* S,
+                                      const int32_t* chain_group, const double* drad_chain, int32_t n_grad, double* dS) {
+  if (!ctx) return LAT_ERR_ARG;
+  LAT_CHECK_ARG(ctx, xyz && len0 && len1 && rad && S && chain_ptr && chain_elem && chain_flip && chain_a && chain_b);
+  LAT_CHECK_ARG(ctx, n_cells >= 0 && n_loc_nodes > 0 && n_loc_elem > 0 && n_chains > 0);
+  LAT_CHECK_ARG(ctx, n_bnd_nodes > 0 && n_bnd_nodes <= n_joints && n_joints <= n_loc_nodes && 6 * n_bnd_nodes <= SCHUR_MAX_NB);
+  LAT_CHECK_ARG(ctx, dS == nullptr || (chain_group != nullptr && n_grad > 0));
+  if (n_cells == 0) return LAT_OK;
+  LAT_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<int32_t> ca(n_chains), cb(n_chains), cend, strut_of;
+  LAT_CUDA(ctx, cudaMemcpyAsync(ca.data(), chain_a, n_chains * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  LAT_CUDA(ctx, cudaMemcpyAsync(cb.data(), chain_b, n_chains * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (!star_topology(ca, cb, n_joints, n_bnd_nodes, &cend, &strut_of)) {
+    if (dS) return lat_fail(ctx, LAT_ERR_UNSUPPORTED, "sensitivities through the strut pre-pass need a star cell (one interior joint): use lat_schur_batch", __FILE__, __LINE__);
+    return lat_schur_batch_chains(ctx, xyz, len0, len1, rad, n_cells, n_loc_nodes, n_loc_elem, chain_ptr, chain_elem, chain_flip,
+                                  chain_a, chain_b, n_chains, n_joints, n_bnd_nodes, young, nu, kappa, S);
+  }
+  const int ns = n_chains;
+  SupCoef* sup = lat_buf<SupCoef>(ctx, "schur_sup", (size_t)n_cells * ns);
+  SupCoef* dsup = dS ? lat_buf<SupCoef>(ctx, "schur_dsup", (size_t)n_cells * ns) : nullptr;
+  int32_t* tab = lat_buf<int32_t>(ctx, "schur_star_tab", (size_t)3 * STAR_MAX_STRUTS);
+  if (!sup || (dS && !dsup) || !tab) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+  std::vector<int32_t> host_tab(3 * STAR_MAX_STRUTS, 0);
+  for (int k = 0; k < ns; ++k) { host_tab[k] = cend[k]; host_tab[STAR_MAX_STRUTS + k] = strut_of[k]; }
+  if (dS) {
+    std::vector<int32_t> grp(ns);
+    LAT_CUDA(ctx, cudaMemcpyAsync(grp.data(), chain_group, ns * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < ns; ++k) host_tab[2 * STAR_MAX_STRUTS + k] = grp[k];
+  }
+  LAT_CUDA(ctx, cudaMemcpyAsync(tab, host_tab.data(), host_tab.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // host_tab goes out of scope
+  const unsigned cgrid = (unsigned)ceil_div(n_cells * ns, 128);
+  if (dS)
+    LAT_LAUNCH(ctx, k_chain_condense_dual, cgrid, 128, 0, xyz, len0, len1, rad, drad_chain, n_cells, n_loc_nodes, n_loc_elem,
+               chain_ptr, chain_elem, chain_flip, ns, young, nu, kappa, sup, dsup);
+  else
+    LAT_LAUNCH(ctx, k_chain_condense, cgrid, 128, 0, xyz, len0, len1, rad, n_cells, n_loc_nodes, n_loc_elem, chain_ptr,
+               chain_elem, chain_flip, ns, young, nu, kappa, sup);
+  const size_t smem = (size_t)STAR_CELLS_PER_CTA * ((dS ? 6 : 3) * ns * 36 + 72) * sizeof(double);
+  int64_t grid = ceil_div(n_cells, STAR_CELLS_PER_CTA);
+  const int64_t cap = (int64_t)ctx->sm_count * 8;
+  if (grid > cap) grid = cap;
+  if (dS) {
+    LAT_CUDA(ctx, cudaFuncSetAttribute(k_schur_star<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LAT_LAUNCH(ctx, k_schur_star<true>, (unsigned)grid, 16 * STAR_CELLS_PER_CTA, smem, sup, dsup, tab, tab + STAR_MAX_STRUTS,
+               tab + 2 * STAR_MAX_STRUTS, n_cells, ns, (int)n_grad, S, dS);
+  } else {
+    LAT_CUDA(ctx, cudaFuncSetAttribute(k_schur_star<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LAT_LAUNCH(ctx, k_schur_star<false>, (unsigned)grid, 16 * STAR_CELLS_PER_CTA, smem, sup, nullptr, tab, tab + STAR_MAX_STRUTS,
+               tab + 2 * STAR_MAX_STRUTS, n_cells, ns, 0, S, nullptr);
   }
   return LAT_OK;
 }

@@ -31,7 +31,7 @@ EXPORTS = [
     "lat_compliance_grad", "lat_schur_batch", "lat_schur_batch_chains", "lat_assemble_bsr_struts", "lat_strut_recover", "lat_ddm_matvec",
     "lat_nccl_unique_id", "lat_comm_create", "lat_comm_destroy", "lat_allreduce_sum", "lat_halo_exchange",
     "lat_pcg_bsr_dist", "lat_p2p_arena_create", "lat_p2p_attach", "lat_p2p_destroy", "lat_assemble_cells_bsr",
-    "lat_cell_quadform",
+    "lat_cell_quadform", "lat_schur_batch_struts",
 ]
 
 
@@ -123,6 +123,8 @@ def load():
     lib.lat_strut_recover.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, dbl, dbl, dbl, vp, vp]
     lib.lat_assemble_bsr_struts.argtypes = [vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, i64, i64, dbl, dbl, dbl, vp]
     lib.lat_schur_batch_chains.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, dbl, dbl, dbl, vp]
+    lib.lat_schur_batch_struts.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, dbl, dbl, dbl, vp,
+                                           vp, vp, i32, vp]
     lib.lat_ddm_matvec.argtypes = [vp, vp, i64, vp, vp, i64, i32, i64, vp, vp]
     lib.lat_assemble_cells_bsr.argtypes = [vp, vp, i64, vp, i64, i32, vp, vp, i64, vp]
     lib.lat_cell_quadform.argtypes = [vp, vp, i64, vp, vp, vp, i64, i32, i32, vp]
@@ -356,6 +358,23 @@ class Context:
                                                    int(chains["a"].numel()), int(chains["n_joints"]), n_bnd_nodes,
                                                    young, nu, kappa, _ptr(S)))
         return S
+
+    def schur_batch_struts(self, xyz, len0, len1, rad, chains, n_bnd_nodes, young, nu, kappa=0.9, chain_group=None,
+                           drad_chain=None, n_grad=0):
+        """Schur complements (and dS for ``n_grad`` radius groups) through the strut pre-pass; star cells (BCC) run in
+        the half-warp kernel, other topologies fall through to ``schur_batch_chains`` (values only)."""
+        import torch
+        n_cells, nn = int(xyz.shape[0]), int(xyz.shape[1])
+        nB = 6 * n_bnd_nodes
+        S = torch.empty((n_cells, nB, nB), dtype=torch.float64, device=self.device)
+        dS = torch.empty((n_cells, n_grad, nB, nB), dtype=torch.float64, device=self.device) if n_grad > 0 else None
+        self.check(self.lib.lat_schur_batch_struts(self.h, _ptr(xyz), _ptr(len0), _ptr(len1), _ptr(rad), n_cells, nn,
+                                                   int(len0.numel()), _ptr(chains["ptr"]), _ptr(chains["elem"]),
+                                                   _ptr(chains["flip"]), _ptr(chains["a"]), _ptr(chains["b"]),
+                                                   int(chains["a"].numel()), int(chains["n_joints"]), n_bnd_nodes,
+                                                   young, nu, kappa, _ptr(S), _ptr(chain_group), _ptr(drad_chain),
+                                                   n_grad, _ptr(dS)))
+        return (S, dS) if n_grad > 0 else S
 
     def ddm_matvec(self, S, gidx, x, n_free=None, u_fixed=None, out=None):
         """y = sum_c B_c S_c B_c^T x.  S: [n_cells, nb, nb] or [nb, nb] (shared by all cells)."""

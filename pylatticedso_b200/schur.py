@@ -33,14 +33,15 @@ def local_cell_mesh(mesh: BeamMesh, boundary_nodes):
     return perm, xyz, perm[mesh.en0].astype(np.int32), perm[mesh.en1].astype(np.int32)
 
 
-def strut_chains(xyz, len0, len1, n_bnd_nodes, tol=1e-9):
+def strut_chains(xyz, len0, len1, n_bnd_nodes, tol=1e-9, allow_trivial=False):
     """Straight element chains of a local cell mesh (boundary nodes = the first ``n_bnd_nodes`` local nodes).
 
     A chain node is an interior node with exactly two incident elements that are collinear; every maximal run of
     chain nodes between two joints is one chain.  Returns host arrays for ``lat_schur_batch_chains``:
     ptr / elem / flip (elements of each chain in walking order), a / b (end joints in the REDUCED numbering: the
     boundary nodes keep their index, interior joints follow in ascending local order) and n_joints -- or ``None``
-    when nothing can be condensed (every strut is a single element)."""
+    when nothing can be condensed (every strut is a single element; ``allow_trivial=True`` then returns one
+    single-element chain per element, which is what the star-cell kernel wants)."""
     xyz = np.asarray(xyz, dtype=np.float64)
     len0, len1 = np.asarray(len0, dtype=np.int64), np.asarray(len1, dtype=np.int64)
     nn, ne = xyz.shape[0], len0.shape[0]
@@ -56,7 +57,7 @@ def strut_chains(xyz, len0, len1, n_bnd_nodes, tol=1e-9):
         if deg[n] == 2:
             e0, e1 = incident[n]
             is_chain[n] = np.linalg.norm(np.cross(d[e0], d[e1])) < tol
-    if not is_chain.any():
+    if not is_chain.any() and not allow_trivial:
         return None
     joints = np.flatnonzero(~is_chain)
     red = np.full(nn, -1, dtype=np.int64)
@@ -80,6 +81,27 @@ def strut_chains(xyz, len0, len1, n_bnd_nodes, tol=1e-9):
         return None                                # a closed ring of chain nodes: leave it to the dense path
     i32 = lambda v: np.asarray(v, dtype=np.int32)
     return dict(ptr=i32(ptr), elem=i32(elem), flip=i32(flip), a=i32(ca), b=i32(cb), n_joints=int(joints.size))
+
+
+def is_star(chains, n_bnd_nodes):
+    """One interior joint joined to every boundary joint by exactly one strut (a BCC cell at any subdivision)."""
+    if chains is None or chains["n_joints"] != n_bnd_nodes + 1 or len(chains["a"]) != n_bnd_nodes or n_bnd_nodes > 16:
+        return False
+    c = n_bnd_nodes
+    corners = [int(b) if int(a) == c else (int(a) if int(b) == c else -1) for a, b in zip(chains["a"], chains["b"])]
+    return all(0 <= k < c for k in corners) and len(set(corners)) == c
+
+
+def chain_groups(chains, elem_group):
+    """Radius group of every chain, or None when the elements of some chain do not share one group."""
+    eg = np.asarray(elem_group, dtype=np.int64)
+    out = np.empty(len(chains["a"]), dtype=np.int32)
+    for k in range(len(chains["a"])):
+        g = eg[chains["elem"][chains["ptr"][k]: chains["ptr"][k + 1]]]
+        if (g != g[0]).any():
+            return None
+        out[k] = g[0]
+    return out
 
 
 def _chains_to_device(chains, dev):
@@ -106,10 +128,13 @@ def get_schur_complement(lattice, cell_index=None, elements_per_strut="gmsh", ct
     perm, xyz, l0, l1 = local_cell_mesh(mesh, bnd)
     dev = ctx.device
     chains = strut_chains(xyz, l0, l1, len(bnd))
+    if chains is None:
+        trivial = strut_chains(xyz, l0, l1, len(bnd), allow_trivial=True)
+        chains = trivial if is_star(trivial, len(bnd)) else None
     args = (torch.from_numpy(xyz[None]).to(dev), torch.from_numpy(l0).to(dev), torch.from_numpy(l1).to(dev),
             torch.from_numpy(mesh.rad[None].copy()).to(dev))
-    if chains is not None:      # strut pre-pass: condense the ~18 elements of every strut first
-        S = ctx.schur_batch_chains(*args, _chains_to_device(chains, dev), len(bnd), E, nu, KAPPA)
+    if chains is not None:      # strut pre-pass: condense the ~18 elements of every strut first (star cells: warp kernel)
+        S = ctx.schur_batch_struts(*args, _chains_to_device(chains, dev), len(bnd), E, nu, KAPPA)
     else:
         S = ctx.schur_batch(*args, len(bnd), E, nu, KAPPA)
     out = S[0].cpu().numpy()
@@ -139,9 +164,16 @@ def schur_gradients(lattice, cell, radii_params, elements_per_strut="gmsh", ctx=
     rad = np.asarray(radii_params)[types] * mesh.chain
     dev = ctx.device
     t = lambda a, d: torch.from_numpy(np.ascontiguousarray(a, dtype=d)).to(dev)
-    S, dS = ctx.schur_batch(t(xyz[None], np.float64), t(l0, np.int32), t(l1, np.int32), t(rad[None], np.float64), len(bnd),
-                            E, nu, KAPPA, elem_group=t(types, np.int32), chain=t(mesh.chain, np.float64),
-                            n_grad=len(radii_params))
+    chains = strut_chains(xyz, l0, l1, len(bnd), allow_trivial=True)
+    cg = chain_groups(chains, types) if is_star(chains, len(bnd)) else None
+    if cg is not None:          # star cell: sensitivities through the differentiated strut pre-pass
+        S, dS = ctx.schur_batch_struts(t(xyz[None], np.float64), t(l0, np.int32), t(l1, np.int32), t(rad[None], np.float64),
+                                       _chains_to_device(chains, dev), len(bnd), E, nu, KAPPA, chain_group=t(cg, np.int32),
+                                       drad_chain=t(mesh.chain, np.float64), n_grad=len(radii_params))
+    else:
+        S, dS = ctx.schur_batch(t(xyz[None], np.float64), t(l0, np.int32), t(l1, np.int32), t(rad[None], np.float64), len(bnd),
+                                E, nu, KAPPA, elem_group=t(types, np.int32), chain=t(mesh.chain, np.float64),
+                                n_grad=len(radii_params))
     out = dS[0].cpu().numpy()
     if not np.isfinite(out).all():
         raise RuntimeError("Schur sensitivities: interior stiffness block is not positive definite")
@@ -163,14 +195,27 @@ class CellBatch:
         self.elem_group = None if elem_group is None else t(elem_group, np.int32)
         self.chain = None if chain is None else t(chain, np.float64)
         self.n_grad = int(n_grad)
-        # strut pre-pass (values only): topology is shared, so the chains are found once on cell 0
+        # strut pre-pass: topology is shared, so the chains are found once on cell 0; star cells (one interior joint,
+        # BCC) also take single-element "chains" and carry the sensitivities through the pre-pass
         ch = strut_chains(np.asarray(xyz)[0], len0, len1, self.n_bnd_nodes)
+        if ch is None:
+            tr = strut_chains(np.asarray(xyz)[0], len0, len1, self.n_bnd_nodes, allow_trivial=True)
+            ch = tr if is_star(tr, self.n_bnd_nodes) else None
+        self.star = is_star(ch, self.n_bnd_nodes)
         self.chains = None if ch is None else _chains_to_device(ch, dev)
+        self.chain_group = None
+        if self.star and elem_group is not None:
+            cg = chain_groups(ch, elem_group)
+            self.chain_group = None if cg is None else t(cg, np.int32)
 
     def schur(self, with_gradients=False, use_chains=True):
-        if not with_gradients and use_chains and self.chains is not None:
-            return self.ctx.schur_batch_chains(self.xyz, self.len0, self.len1, self.rad, self.chains, self.n_bnd_nodes,
+        if use_chains and self.chains is not None and not with_gradients:
+            return self.ctx.schur_batch_struts(self.xyz, self.len0, self.len1, self.rad, self.chains, self.n_bnd_nodes,
                                                self.young, self.nu, self.kappa)
+        if use_chains and with_gradients and self.star and self.chain_group is not None:
+            return self.ctx.schur_batch_struts(self.xyz, self.len0, self.len1, self.rad, self.chains, self.n_bnd_nodes,
+                                               self.young, self.nu, self.kappa, chain_group=self.chain_group,
+                                               drad_chain=self.chain, n_grad=self.n_grad)
         if with_gradients:
             return self.ctx.schur_batch(self.xyz, self.len0, self.len1, self.rad, self.n_bnd_nodes, self.young, self.nu,
                                         self.kappa, self.elem_group, self.chain, self.n_grad)

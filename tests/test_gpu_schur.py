@@ -38,6 +38,16 @@ def test_schur_batch_reproduces_reference_goldens(ctx, geom, tol):
         err2 = np.abs(S2 - SM[i]).max() / np.abs(SM[i]).max()
         assert err2 < tol, (geom, i, "chains", err2)
         assert np.array_equal(S2, S2.T)
+        # and through lat_schur_batch_struts: the penalised BCC cell is a star (8 struts of 18 elements with the x1.5
+        # segments inside, one interior joint) and runs in the half-warp kernel; the hybrids fall through to the chains path
+        from pylatticedso_b200.schur import is_star
+        S3 = ctx.schur_batch_struts(t(ctx, xyz[None], np.float64), t(ctx, l0, np.int32), t(ctx, l1, np.int32),
+                                    t(ctx, m.rad[None], np.float64), _chains_to_device(ch, ctx.device), len(bnd_nodes),
+                                    E_MOD, NU)[0].cpu().numpy()
+        assert is_star(ch, len(bnd_nodes)) == (geom == "BCC")
+        err3 = np.abs(S3 - SM[i]).max() / np.abs(SM[i]).max()
+        assert err3 < tol, (geom, i, "struts", err3)
+        assert np.abs(S3 - S3.T).max() <= 1e-13 * np.abs(S3).max()
 
 
 def test_schur_batch_many_cells_and_gradients(ctx):
@@ -62,6 +72,11 @@ def test_schur_batch_many_cells_and_gradients(ctx):
             h = 1e-6
             fd = (f(radii[c] + h) - f(radii[c] - h)) / (2 * h)
             assert np.abs(dS[c, 0] - fd).max() < 1e-6 * np.abs(fd).max()
+        # the star kernel (differentiated strut pre-pass) against the dense route over all interior DOFs
+        assert batch.star
+        Sd, dSd = batch.schur(with_gradients=True, use_chains=False)
+        assert np.abs(S - Sd.cpu().numpy()).max() < 1e-12 * np.abs(S).max()
+        assert np.abs(dS - dSd.cpu().numpy()).max() < 1e-9 * np.abs(dS).max()
         # S is symmetric positive semi-definite with exactly the 6 rigid-body modes in its null space
         w = np.linalg.eigvalsh(S[5])
         assert w.min() > -1e-9 * w.max() and (np.abs(w) < 1e-9 * w.max()).sum() == 6
