@@ -359,6 +359,45 @@ int lat_assemble_cells_bsr(lat_ctx* ctx, const double* S, int64_t s_stride, cons
 int lat_cell_quadform(lat_ctx* ctx, const double* mats, int64_t n_mats, const int32_t* mat_index, const double* U,
                       const double* V, int64_t n_cells, int32_t n_grad, int32_t nb, double* out);
 
+/* ---- N4: reduced-basis / surrogate Schur pipeline (csrc/lattice_surrogate.cu) ------------------------------
+ * All pointers are device pointers unless stated otherwise. */
+
+/* Greedy reduced basis of Schur snapshots: reduce_basis_greedy (greedy_algorithm.py:35-155, the while loop of
+ * :112-124 with its dgemv/dger deflation).  snaps: [n_snap][len], snapshot s = vec(S_s) in any fixed order (the
+ * reference uses Fortran order, :99).  Out: basis [n_snap][len] capacity, row kk = kk-th basis vector
+ * (reducedbasis[kk], unit 2-norm); coef [n_snap][n_snap] capacity, row kk = newcoef of step kk; mainelem
+ * int32[n_snap] (s_I of each step, device); norms [n_snap] = |vec(S_s)|_2; *k_out (HOST) = basis size.  [syncs] */
+int lat_greedy_basis(lat_ctx* ctx, const double* snaps, int64_t n_snap, int64_t len, double tol, double* basis,
+                     double* coef, int32_t* mainelem, double* norms, int32_t* k_out);
+/* Upper-triangular solve U X = R in place: dtrtrs of greedy_algorithm.py:129.  U [n][ldu], R [n][m], row-major. */
+int lat_upper_solve(lat_ctx* ctx, const double* U, int32_t n, int32_t ldu, double* R, int32_t m);
+/* Least-squares coefficients alphas[s][:] = argmin |B^T a - V_s| : la.lstsq(basisF, v) of greedy_algorithm.py:135-138
+ * and project_to_reduced_basis (:233-266), by the normal equations of the (near-orthonormal) basis.
+ * basis [k][len] (rows = basis vectors), V [n][len], alphas [n][k].  [syncs] */
+int lat_basis_project(lat_ctx* ctx, const double* basis, int32_t k, int64_t len, const double* V, int64_t n,
+                      double* alphas);
+/* ThinPlateSplineRBF.__init__ (utils_rbf.py:22-61): assemble [[Phi + reg I, P], [P^T, 0]] and solve by LU with
+ * partial pivoting.  x_train [N][d], y [N][m]; wcp [(N+d+1)][m]: rows [0,N) = W, then CP.  [syncs] */
+int lat_rbf_fit(lat_ctx* ctx, const double* x_train, int32_t N, int32_t d, const double* y, int32_t m, double reg,
+                double* wcp);
+/* ThinPlateSplineRBF.evaluate / .gradient (utils_rbf.py:82-144) for M queries xq [M][d]:
+ * f [M][m] (or NULL), grad [M][d][m] (or NULL). */
+int lat_rbf_eval(lat_ctx* ctx, const double* x_train, int32_t N, int32_t d, const double* wcp, int32_t m,
+                 const double* xq, int64_t M, double* f, double* grad);
+/* alpha look-up of the "nearest_neighbor" (mode 0, lattice_sim.py:939-942) and "linear" (mode 1, the np.interp branch
+ * of evaluate_alphas_linear_surrogate, :781-792; d = 1 only) surrogates.  alpha_train [N][m], out [M][m]. */
+int lat_alpha_lookup(lat_ctx* ctx, int32_t mode, const double* x_train, int32_t N, int32_t d,
+                     const double* alpha_train, int32_t m, const double* xq, int64_t M, double* out);
+/* Basis in the layout of lat_basis_expand: basis [len][k] row-major (the npz's basis_reduced_ortho) ->
+ * basisP [4*ceil(k/4)][len]; n_fortran = n applies the reference's order='F' reshape of every column
+ * (lattice_sim.py:973-976): basisP[kk][a*n + b] = basis[a + n*b][kk]; 0 = keep the order. */
+int lat_basis_prepare(lat_ctx* ctx, const double* basis, int64_t len, int32_t k, int32_t n_fortran, double* basisP);
+/* out[q][:] = sum_kk alphas[q][kk] basisP[kk][:]  -- the GEMM of get_schur_complement_from_reduced_basis_batch
+ * (lattice_sim.py:961-976) and of _compute_schur_gradients_RBF (:1075-1080) for M queries, on the FP64 tensor cores
+ * (DMMA).  alphas [M][lda]; out [M][len], 32-byte aligned, len % 4 == 0. */
+int lat_basis_expand(lat_ctx* ctx, const double* basisP, int32_t k, int64_t len, const double* alphas, int64_t M,
+                     int32_t lda, double* out);
+
 #ifdef __cplusplus
 }
 #endif

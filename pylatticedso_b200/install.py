@@ -14,6 +14,9 @@ be rebound without touching a reference file:
 | ``LatticeSim.solve_DDM``                                                   | lattice_sim.py:1111-1176  | ``ddm.solve_DDM_B200`` |
 | ``LatticeSim._compute_schur_gradients``                                    | lattice_sim.py:1020-1054  | ``schur.schur_gradients`` (analytic, no finite differences) |
 | ``LatticeOpti.calculate_gradient`` (compliance branch)                     | lattice_opti.py:735-841   | ``ddm.compliance_gradient_cells`` + ``fem.cell_sensitivities_to_parameters`` |
+| ``reduce_basis_greedy``, ``project_to_reduced_basis`` (greedy_algorithm)  | greedy_algorithm.py:35-155, 233-266 | ``surrogate.reduce_basis_greedy`` / ``project_to_reduced_basis`` |
+| ``ThinPlateSplineRBF`` (utils_rbf, lattice_sim)                            | utils_rbf.py:13-144       | ``surrogate.ThinPlateSplineRBF`` |
+| ``LatticeSim.get_schur_complement_from_reduced_basis_batch`` / ``..._from_reduced_basis`` / ``_compute_schur_gradients_RBF`` / ``_define_radial_basis_functions`` | lattice_sim.py:921-1018, 1056-1082, 809-812 | ``surrogate.lattice_*`` (RBF / nearest-neighbour / 1-D linear alphas + DMMA ``basis @ alphas``) |
 
 ``patch_reference`` returns the list of names it rebound; ``unpatch_reference`` restores the originals.
 """
@@ -32,7 +35,7 @@ def _rebind(owner, attr, fn, done, label):
 
 
 def patch_reference(elements_per_strut="gmsh", ctx=None):
-    from . import ddm, fem, pcg, schur
+    from . import ddm, fem, pcg, schur, surrogate
     done = []
 
     def _solve(lattice):
@@ -62,6 +65,57 @@ def patch_reference(elements_per_strut="gmsh", ctx=None):
     _rebind(lattice_sim_cls, "solve_DDM", _solve_ddm, done, "pyLatticeSim.lattice_sim.LatticeSim.solve_DDM")
     _rebind(lattice_sim_cls, "_compute_schur_gradients", _schur_gradients, done,
             "pyLatticeSim.lattice_sim.LatticeSim._compute_schur_gradients")
+
+    # N4: reduced-basis / surrogate pipeline
+    def _greedy(schur_dict, tol_greedy, file_name=None, verbose=1):
+        return surrogate.reduce_basis_greedy(schur_dict, tol_greedy, file_name=file_name, verbose=verbose, ctx=ctx)
+
+    def _project(schur_dict, basis):
+        return surrogate.project_to_reduced_basis(schur_dict, basis, ctx=ctx)
+
+    class _TPS(surrogate.ThinPlateSplineRBF):
+        def __init__(self, x_train, y_train, reg=0.0):
+            super().__init__(x_train, y_train, reg=reg, ctx=ctx)
+
+    def _linear_or_reference(original):
+        def _batch(self, geometric_params_list):
+            # N-D "linear" (scipy Delaunay interpolation, lattice_sim.py:794-807) is not a device kernel: reference code
+            nd = np_ndim(self.reduce_basis_dict["list_elements"])
+            if self.type_schur_complement_computation == "linear" and nd > 1:
+                return original(self, geometric_params_list)
+            return surrogate.lattice_schur_batch(self, geometric_params_list, ctx=ctx)
+        return _batch
+
+    def np_ndim(list_elements):
+        import numpy as np
+        a = np.asarray(list_elements)
+        return 1 if a.ndim == 1 else a.shape[1]
+
+    for modname in ("pyLatticeSim.greedy_algorithm",):
+        _rebind(mods.get(modname), "reduce_basis_greedy", _greedy, done, f"{modname}.reduce_basis_greedy")
+        _rebind(mods.get(modname), "project_to_reduced_basis", _project, done, f"{modname}.project_to_reduced_basis")
+    for modname in ("pyLatticeSim.utils_rbf", "pyLatticeSim.lattice_sim"):
+        _rebind(mods.get(modname), "ThinPlateSplineRBF", _TPS, done, f"{modname}.ThinPlateSplineRBF")
+    if lattice_sim_cls is not None and hasattr(lattice_sim_cls, "get_schur_complement_from_reduced_basis_batch"):
+        orig_batch = lattice_sim_cls.get_schur_complement_from_reduced_basis_batch
+        orig_single = lattice_sim_cls.get_schur_complement_from_reduced_basis
+        _batch = _linear_or_reference(orig_batch)
+
+        def _single(self, geometric_params):
+            if self.type_schur_complement_computation == "linear" and np_ndim(self.reduce_basis_dict["list_elements"]) > 1:
+                return orig_single(self, geometric_params)
+            return surrogate.lattice_schur_single(self, geometric_params, ctx=ctx)
+
+        pre = "pyLatticeSim.lattice_sim.LatticeSim."
+        _rebind(lattice_sim_cls, "get_schur_complement_from_reduced_basis_batch", _batch, done,
+                pre + "get_schur_complement_from_reduced_basis_batch")
+        _rebind(lattice_sim_cls, "get_schur_complement_from_reduced_basis", _single, done,
+                pre + "get_schur_complement_from_reduced_basis")
+        _rebind(lattice_sim_cls, "_compute_schur_gradients_RBF",
+                lambda self, radii_params: surrogate.lattice_schur_gradients_rbf(self, radii_params, ctx=ctx), done,
+                pre + "_compute_schur_gradients_RBF")
+        _rebind(lattice_sim_cls, "_define_radial_basis_functions", lambda self: surrogate.lattice_define_rbf(self, ctx=ctx), done,
+                pre + "_define_radial_basis_functions")
 
     lo = mods.get("pyLatticeOpti.lattice_opti")
     lattice_opti_cls = getattr(lo, "LatticeOpti", None)

@@ -15,7 +15,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "liblattice_b200.so")
-SOURCES = ["lattice_core.cu", "lattice_solver.cu", "lattice_schur.cu"]
+SOURCES = ["lattice_core.cu", "lattice_solver.cu", "lattice_schur.cu", "lattice_surrogate.cu"]
 HEADERS = [os.path.join(_HERE, "csrc", "common.cuh"), os.path.join(_HERE, "csrc", "matfree.cuh"),
            os.path.join(_HERE, "csrc", "pcg_persist.cuh"),
            os.path.join(_ROOT, "include", "lattice_b200.h")]
@@ -32,6 +32,8 @@ EXPORTS = [
     "lat_nccl_unique_id", "lat_comm_create", "lat_comm_destroy", "lat_allreduce_sum", "lat_halo_exchange",
     "lat_pcg_bsr_dist", "lat_p2p_arena_create", "lat_p2p_attach", "lat_p2p_destroy", "lat_assemble_cells_bsr",
     "lat_cell_quadform", "lat_schur_batch_struts",
+    "lat_greedy_basis", "lat_upper_solve", "lat_basis_project", "lat_rbf_fit", "lat_rbf_eval", "lat_alpha_lookup",
+    "lat_basis_prepare", "lat_basis_expand",
 ]
 
 
@@ -137,6 +139,14 @@ def load():
     lib.lat_p2p_attach.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]
     lib.lat_p2p_destroy.argtypes = [vp]
     lib.lat_pcg_bsr_dist.argtypes = [vp, vp, vp, vp, C.POINTER(Halo), vp, vp, C.POINTER(PcgOpts), C.POINTER(PcgResult)]
+    lib.lat_greedy_basis.argtypes = [vp, vp, i64, i64, dbl, vp, vp, vp, vp, C.POINTER(i32)]
+    lib.lat_upper_solve.argtypes = [vp, vp, i32, i32, vp, i32]
+    lib.lat_basis_project.argtypes = [vp, vp, i32, i64, vp, i64, vp]
+    lib.lat_rbf_fit.argtypes = [vp, vp, i32, i32, vp, i32, dbl, vp]
+    lib.lat_rbf_eval.argtypes = [vp, vp, i32, i32, vp, i32, vp, i64, vp, vp]
+    lib.lat_alpha_lookup.argtypes = [vp, i32, vp, i32, i32, vp, i32, vp, i64, vp]
+    lib.lat_basis_prepare.argtypes = [vp, vp, i64, i32, i32, vp]
+    lib.lat_basis_expand.argtypes = [vp, vp, i32, i64, vp, i64, i32, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("lat_last_error", "lat_launch_count"):

@@ -19,6 +19,13 @@ EXPECTED = {
     "pyLatticeOpti.lattice_opti.conjugate_gradient_solver",
     "pyLatticeSim.lattice_sim.LatticeSim.solve_DDM", "pyLatticeSim.lattice_sim.LatticeSim._compute_schur_gradients",
     "pyLatticeOpti.lattice_opti.LatticeOpti.calculate_gradient",
+    # N4: reduced-basis / surrogate pipeline
+    "pyLatticeSim.greedy_algorithm.reduce_basis_greedy", "pyLatticeSim.greedy_algorithm.project_to_reduced_basis",
+    "pyLatticeSim.utils_rbf.ThinPlateSplineRBF", "pyLatticeSim.lattice_sim.ThinPlateSplineRBF",
+    "pyLatticeSim.lattice_sim.LatticeSim.get_schur_complement_from_reduced_basis_batch",
+    "pyLatticeSim.lattice_sim.LatticeSim.get_schur_complement_from_reduced_basis",
+    "pyLatticeSim.lattice_sim.LatticeSim._compute_schur_gradients_RBF",
+    "pyLatticeSim.lattice_sim.LatticeSim._define_radial_basis_functions",
 }
 
 
@@ -67,6 +74,10 @@ def test_patch_reference_rebinds_every_seam_and_fails_loudly_without_gpu(ref):
                 sys.modules["pyLatticeSim.utils_simulation"].solve_FEM_FenicsX(lat)
             with pytest.raises(LatticeB200Error):
                 ls.get_schur_complement(lat, 0)
+            with pytest.raises(LatticeB200Error):            # surrogate seam: the device layer, not scipy BLAS
+                sys.modules["pyLatticeSim.greedy_algorithm"].reduce_basis_greedy({(0.1,): np.eye(6), (0.2,): 2 * np.eye(6)}, 1e-3)
+            with pytest.raises(LatticeB200Error):
+                ls.ThinPlateSplineRBF(np.array([[0.0], [1.0], [2.0]]), np.array([1.0, 2.0, 4.0]))
     finally:
         assert install.unpatch_reference() == len(EXPECTED)
     for n, fn in before.items():
