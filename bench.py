@@ -263,7 +263,9 @@ def parity_sharded(ctx, dfem, mesh, fixed, g, f, rank):
     ng = int(grp_g.max()) + 1
     res = {}
     sols = {}
-    for name, solve in (("assembled", dfem.solve), ("matrix_free", dfem.solve_matrix_free)):
+    for name, solve in (("assembled", dfem.solve),
+                        ("assembled_three_kernel", lambda **kw: dfem.solve(persistent=False, **kw)),
+                        ("matrix_free", dfem.solve_matrix_free)):
         u, R, info = solve(tol=1e-12, maxiter=400000, precond=L.PC_BLOCK6)
         gr = dfem.compliance_gradient(u, grp_g, ng).cpu().numpy()
         sols[name] = (dfem.gather_owned(u), dfem.gather_owned(R), gr, info)
@@ -276,7 +278,7 @@ def parity_sharded(ctx, dfem, mesh, fixed, g, f, rank):
         for name, (ug, Rg, gr, info) in sols.items():
             e = dict(u_rel=float(np.abs(ug - u0).max() / np.abs(u0).max()), R_rel=float(np.abs(Rg - R0).max() / np.abs(R0).max()),
                      grad_rel=float(np.abs(gr - g0).max() / np.abs(g0).max()), iters=info["iters"], info=info["info"],
-                     true_relres=info["true_relres"], cuda_graph=info.get("graph"))
+                     true_relres=info["true_relres"], cuda_graph=info.get("graph"), persistent_kernel=info.get("persistent", False))
             ok = ok and e["u_rel"] < 1e-8 and e["R_rel"] < 1e-8 and e["grad_rel"] < 1e-6
             res[name] = e
         res["against"] = "the same global system solved on rank 0 alone (single-GPU path), tol 1e-12, iters %d" % i0["iters"]
@@ -541,9 +543,9 @@ def run_b200(args):
     for _ in range(args.steps):
         flush.fill_(1.0)            # evict the previous step's matrix from L2 (untimed)
         barrier()
-        # N = 1: the solve is ONE launch of the persistent on-chip kernel, timed by the library with CUDA events on its
-        # stream (info["solve_ms"]); N > 1: three-kernel iteration, the first 32 iterations with events around k_cg_spmv
-        e, info, _ = step(32 if distributed else 0)
+        # the solve is ONE launch of the persistent on-chip kernel per GPU (N > 1: halo exchange and all-reduce inside its
+        # grid barriers), timed by the library with CUDA events on its stream (info["solve_ms"])
+        e, info, _ = step(0)
         barrier()
         persistent = bool(info.get("persistent", False))
         tot_ms += e[0].elapsed_time(e[3])
@@ -620,13 +622,18 @@ def run_b200(args):
     # ---- secondary (N = 1): the same solve through the three-kernel iteration (what larger systems use), with
     #      CUDA events around k_cg_spmv for the first 32 iterations
     three = None
-    if not distributed:
+    if True:
         t_ms, t_it, t_sp, t_up = 0.0, 0, [], []
         for s_ in range(1 + args.steps):
             flush.fill_(1.0)
             barrier()
-            _, info3 = ctx.pcg(fem.rowptr, fem.colidx, vals_bc, b_d, x=u_d, tol=1e-8, maxiter=200000, precond=L.PC_BLOCK6,
-                               profile_iters=32, persistent=False)
+            if distributed:
+                _, _, info3 = dfem.solve(tol=1e-8, maxiter=200000, precond=L.PC_BLOCK6, vals_bc=vals_bc, b=b_d, u=u_d,
+                                         profile_iters=32, persistent=False)
+            else:
+                _, info3 = ctx.pcg(fem.rowptr, fem.colidx, vals_bc, b_d, x=u_d, tol=1e-8, maxiter=200000, precond=L.PC_BLOCK6,
+                                   profile_iters=32, persistent=False)
+            barrier()
             if s_ >= 1:
                 t_ms += info3["solve_ms"]; t_it += info3["iters"]; t_sp.append(info3["spmv_ms"]); t_up.append(info3["update_ms"])
         three = dict(ms=t_ms / args.steps, iters=t_it / args.steps, spmv_ms=float(np.mean(t_sp)), update_ms=float(np.mean(t_up)))
@@ -720,7 +727,7 @@ def run_b200(args):
         roofline = {"kernel": "k_pcg_persist (the whole block-Jacobi PCG solve as one persistent cooperative kernel: BSR 6x6 product, "
                               "dot products, grid reductions, vector updates and preconditioner; r, p, s, w in shared memory)",
                     "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                    "traffic": NCU_TRAFFIC_PERSIST_PER_ITER * per_step_iters if NCU_TRAFFIC_PERSIST_PER_ITER else None,
+                    "traffic": NCU_TRAFFIC_PERSIST_PER_ITER * per_step_iters if (NCU_TRAFFIC_PERSIST_PER_ITER and world == 1) else None,
                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full, scaled to this "
                                       "step's iteration count (profiles/r02_ncu_persist.txt)",
                     "peak_source": peak_src, "bytes_per_launch": it_b * per_step_iters,
@@ -728,6 +735,8 @@ def run_b200(args):
                     "frac_on_design_bytes": design_b * per_step_iters / (launch_ms * 1e-3) / 1e9 / hbm_peak,
                     "avg_launch_ms": launch_ms, "us_per_iteration": 1e3 * launch_ms / per_step_iters,
                     "launches_timed": args.steps,
+                    "scope": None if world == 1 else "rank 0's kernel over rank 0's slab against ONE GPU's peak; the halo exchange and the "
+                                                     "rank-level all-reduce happen inside the kernel's two grid barriers",
                     "note": "frac uses SURVEY 8(d)'s algorithmic bytes of a PCG iteration (SpMV + 96 B/DOF + 28 B/DOF); the kernel "
                             "never moves the 56 MB/iteration of vector traffic those include, which is how it beats the "
                             "three-kernel iteration; frac_on_design_bytes counts only what this design must stream"}
@@ -784,6 +793,8 @@ def run_b200(args):
     if res.get("three"):
         t3 = res["three"]
         b3 = spmv_bytes(nn, nz)
+        if world > 1:       # t3["ms"] is rank 0's library-timed solve; the ranks run in lock step
+            b3 = spmv_bytes(nn, nz)
         line["three_kernel_path"] = {"solve_ms_per_step": t3["ms"], "iterations_per_step": t3["iters"],
                                      "value": n_dof_global * t3["iters"] / (t3["ms"] * 1e-3), "unit": UNIT,
                                      "k_cg_spmv_ms": t3["spmv_ms"], "k_cg_spmv_GBps": b3 / (t3["spmv_ms"] * 1e-3) / 1e9,

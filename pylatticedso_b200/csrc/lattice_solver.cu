@@ -10,6 +10,8 @@
 #include <cstring>
 #include <vector>
 
+#include <stddef.h>
+
 #include "common.cuh"
 #include "matfree.cuh"
 
@@ -1153,47 +1155,87 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
 // ---------------------------------------------------------------------------
 #include "pcg_persist.cuh"
 
+// Multi-GPU set-up of the persistent kernel, filled by pcg_run_dist_impl (peer-memory arena, fused-halo tables).
+struct PersistDistSetup {
+  double* u = nullptr;                        // the ghosted u inside this rank's arena
+  int nranks = 1, my_rank = 0, n_nb = 0;
+  long long ghost_first[2] = {0, 0};
+  int ghost_entries[2] = {0, 0};
+  unsigned long long push_base = 0, seq_base = 0;
+  const int2* push_dst = nullptr;
+  unsigned long long* peer_ll[2] = {nullptr, nullptr};
+  const unsigned long long* my_ll = nullptr;
+  unsigned char* const* peers = nullptr;
+  unsigned long long pushes = 0;              // out: productions of u (= halo pushes) of the solve
+};
+
 // Returns LAT_OK with *used = true when the solve ran in the persistent kernel; *used = false (and LAT_OK) when the
 // system does not fit the shared memory of the device or cooperative launch is unavailable -- the caller then
-// runs the three-kernel iteration.
+// runs the three-kernel iteration.  With `dist` the decision is collective (every rank's slab must fit: one tiny
+// all-reduce), n_nodes counts the owned rows and u lives in the arena.
 template <int PC>
 static int pcg_run_persist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, const double* vals,
                            int64_t n_nodes, const double* b, double* x, const lat_pcg_opts* o, lat_pcg_result* res,
-                           bool* used) {
+                           bool* used, PersistDistSetup* dist = nullptr) {
   *used = false;
   int coop = 0, smem_optin = 0;
   LAT_CUDA(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
   LAT_CUDA(ctx, cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
-  if (!coop || n_nodes >= (int64_t)INT32_MAX / 8) return LAT_OK;
   const int G = ctx->sm_count < PERSIST_INBOX_STRIDE ? ctx->sm_count : PERSIST_INBOX_STRIDE;
+  bool fits = coop && n_nodes < (int64_t)INT32_MAX / 8;
   // cheap size screen before any work: 5 vectors of the average CTA must fit at all
-  if ((double)n_nodes / G * (PERSIST_NVEC * 48 + persist_pc_width(PC) * 8) > (double)smem_optin) return LAT_OK;
-  if ((n_nodes + PERSIST_CHUNK - 1) / PERSIST_CHUNK > (int64_t)64 * G) return LAT_OK;   // s_chunk_base holds 64 chunks per CTA
-  int32_t* maxima = lat_buf<int32_t>(ctx, "persist_max", 4);
-  if (!maxima) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
-  LAT_CUDA(ctx, cudaMemsetAsync(maxima, 0, 4 * sizeof(int32_t), ctx->stream));
-  LAT_LAUNCH(ctx, k_persist_caps, (unsigned)ceil_div(G, 128), 128, 0, rowptr, n_nodes, G, maxima);
-  int32_t hmax[2] = {0, 0};
-  LAT_CUDA(ctx, cudaMemcpyAsync(hmax, maxima, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  const int rows_cap = hmax[0] > 0 ? hmax[0] : 1, blk_cap = hmax[1] > 0 ? hmax[1] : 1;
-  // Shared memory and L1 share 256 KB per SM, and the product phase needs its L1: the preconditioner rows are
-  // cached on chip only while the total stays below ~160 KB (LAT_PERSIST_PCSMEM_KB overrides the limit).
-  const size_t smem_base = (size_t)rows_cap * (PERSIST_NVEC * 48) + (size_t)3 * G * 8 + (size_t)(2 * rows_cap + 1) * 4 +
-                           (size_t)blk_cap * 4 + 32;
-  const size_t smem_pc = (size_t)rows_cap * persist_pc_width(PC) * 8;
-  const char* env_kb = getenv("LAT_PERSIST_PCSMEM_KB");
-  const size_t pc_limit = (size_t)(env_kb ? atoi(env_kb) : 160) * 1024;
-  const bool pc_smem = smem_base + smem_pc + 2560 <= (size_t)smem_optin && smem_base + smem_pc <= pc_limit;
-  const size_t smem = smem_base + (pc_smem ? smem_pc : 0);
-  if (smem + 2560 > (size_t)smem_optin) return LAT_OK;     // does not fit on chip: three-kernel path
-  LAT_CUDA(ctx, cudaFuncSetAttribute(k_pcg_persist<PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  LAT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_persist<PC>, PERSIST_BLOCK, smem));
-  if (per_sm < 1) return LAT_OK;
+  if ((double)n_nodes / G * (PERSIST_NVEC * 48 + persist_pc_width(PC) * 8) > (double)smem_optin) fits = false;
+  if ((n_nodes + PERSIST_CHUNK - 1) / PERSIST_CHUNK > (int64_t)64 * G) fits = false;   // s_chunk_base holds 64 chunks per CTA
+  if (!fits && !dist) return LAT_OK;
+  int rows_cap = 1, blk_cap = 1;
+  bool pc_smem = false;
+  size_t smem = 0;
+  if (fits) {
+    int32_t* maxima = lat_buf<int32_t>(ctx, "persist_max", 4);
+    if (!maxima) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+    LAT_CUDA(ctx, cudaMemsetAsync(maxima, 0, 4 * sizeof(int32_t), ctx->stream));
+    LAT_LAUNCH(ctx, k_persist_caps, (unsigned)ceil_div(G, 128), 128, 0, rowptr, n_nodes, G, maxima);
+    int32_t hmax[2] = {0, 0};
+    LAT_CUDA(ctx, cudaMemcpyAsync(hmax, maxima, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    rows_cap = hmax[0] > 0 ? hmax[0] : 1;
+    blk_cap = hmax[1] > 0 ? hmax[1] : 1;
+    // Shared memory and L1 share 256 KB per SM, and the product phase needs its L1: the preconditioner rows are
+    // cached on chip only while the total stays below ~160 KB (LAT_PERSIST_PCSMEM_KB overrides the limit).
+    const size_t smem_base = (size_t)rows_cap * (PERSIST_NVEC * 48) + (size_t)3 * G * 8 + (size_t)(2 * rows_cap + 1) * 4 +
+                             (size_t)blk_cap * 4 + (size_t)((rows_cap + 15) / 16) * 16 + 32;
+    const size_t smem_pc = (size_t)rows_cap * persist_pc_width(PC) * 8;
+    const char* env_kb = getenv("LAT_PERSIST_PCSMEM_KB");
+    const size_t pc_limit = (size_t)(env_kb ? atoi(env_kb) : 160) * 1024;
+    pc_smem = smem_base + smem_pc + 2560 <= (size_t)smem_optin && smem_base + smem_pc <= pc_limit;
+    smem = smem_base + (pc_smem ? smem_pc : 0);
+    if (smem + 2560 > (size_t)smem_optin) fits = false;     // does not fit on chip: three-kernel path
+  }
+  const void* kfn = dist ? (const void*)k_pcg_persist<PC, true> : (const void*)k_pcg_persist<PC, false>;
+  if (fits) {
+    LAT_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    if (dist) LAT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_persist<PC, true>, PERSIST_BLOCK, smem));
+    else LAT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_persist<PC, false>, PERSIST_BLOCK, smem));
+    if (per_sm < 1) fits = false;
+  }
+  if (dist && dist->nranks > 1) {
+    // collective decision: one rank in the persistent kernel and another in the three-kernel iteration would wait
+    // for each other for ever
+    double* vote = lat_buf<double>(ctx, "persist_vote", 1);
+    if (!vote) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+    const double mine = fits ? 0.0 : 1.0;
+    LAT_CUDA(ctx, cudaMemcpyAsync(vote, &mine, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (int rc = lat_allreduce_sum(ctx, vote, 1)) return rc;
+    double against = 1.0;
+    LAT_CUDA(ctx, cudaMemcpyAsync(&against, vote, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (against > 0.0) fits = false;
+  }
+  if (!fits) return LAT_OK;
 
   const int64_t n = 6 * n_nodes;
-  double* u = lat_buf<double>(ctx, "pcg_z", n);
+  double* u = dist ? dist->u : lat_buf<double>(ctx, "pcg_z", n);
   double* dinv = lat_buf<double>(ctx, "pcg_dinv", PC == LAT_PC_BLOCK6 ? 21 * n_nodes : n);
   PcgScalars* sc = lat_buf<PcgScalars>(ctx, "pcg_scalars", 1);
   unsigned long long* mail = lat_buf<unsigned long long>(ctx, "persist_mail", (size_t)G * 8);
@@ -1211,6 +1253,19 @@ static int pcg_run_persist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* c
   a.prm.tol = o->tol; a.prm.mintol = 0.0; a.prm.alpha_max = 0.0; a.prm.restart_every = 0; a.prm.maxiter = o->maxiter;
   a.prm.reference = 0; a.prm.dist = 0; a.prm.pad = 0; a.prm.seq_base = 0; a.prm.push_base = 0;
   a.mail = mail; a.flags = flags; a.rows_cap = rows_cap; a.blk_cap = blk_cap; a.pc_smem = pc_smem ? 1 : 0;
+  a.nranks = 1; a.my_rank = 0; a.n_nb = 0;
+  a.ghost_first[0] = a.ghost_first[1] = 0; a.ghost_entries[0] = a.ghost_entries[1] = 0;
+  a.push_base = 0; a.seq_base = 0;
+  a.push_dst = nullptr; a.peer_ll[0] = a.peer_ll[1] = nullptr; a.my_ll = nullptr; a.peers = nullptr;
+  if (dist) {
+    a.nranks = dist->nranks; a.my_rank = dist->my_rank; a.n_nb = dist->n_nb;
+    for (int k = 0; k < 2; ++k) {
+      a.ghost_first[k] = dist->ghost_first[k]; a.ghost_entries[k] = dist->ghost_entries[k];
+      a.peer_ll[k] = dist->peer_ll[k];
+    }
+    a.push_base = dist->push_base; a.seq_base = dist->seq_base; a.prm.seq_base = dist->seq_base; a.prm.push_base = dist->push_base;
+    a.push_dst = dist->push_dst; a.my_ll = dist->my_ll; a.peers = dist->peers;
+  }
   a.trace = nullptr;
   a.trace_iters = 0;
   const char* env_tr = getenv("LAT_PERSIST_TRACE");     // LAT_PERSIST_TRACE=n: phase breakdown of the first n iterations on stderr
@@ -1222,7 +1277,7 @@ static int pcg_run_persist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* c
   }
   void* kargs[] = {&a};
   LAT_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-  LAT_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_pcg_persist<PC>, dim3(G), dim3(PERSIST_BLOCK), kargs, smem, ctx->stream));
+  LAT_CUDA(ctx, cudaLaunchCooperativeKernel(kfn, dim3(G), dim3(PERSIST_BLOCK), kargs, smem, ctx->stream));
   ctx->launches++;
   LAT_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
   PcgScalars* hs = ctx->h_scal;
@@ -1288,6 +1343,7 @@ static int pcg_run_persist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* c
   res->update_ms = 0.0;
   res->profiled = 0;
   res->reserved = hs[0].restarts | 0x200;    // bit 9: solved by the persistent on-chip kernel
+  if (dist) dist->pushes = hs[0].counter[0];
   res->true_relres = (hs[0].true_rr >= 0.0 && hs[0].bb > 0.0) ? sqrt(hs[0].true_rr / hs[0].bb) : -1.0;
   *used = true;
   return LAT_OK;
@@ -1580,9 +1636,14 @@ struct P2PArenaHdr {
   unsigned long long mail[2][P2P_MAXR][6];                  // [parity][source rank][3 doubles x {lo, hi}]
   unsigned long long halo_flag[P2P_MAXR][P2P_SLOTS];        // [source rank][slot]
   unsigned long long halo_cnt[P2P_MAXR];                    // fused-halo path: cumulative entries received per source rank
+  unsigned long long n_local_nodes, pad[3];                 // of the arena's owner: places the halo inbox behind u
 };
+// Arena = header | u [6 n_local] | 256 B | halo inbox of the persistent kernel: two LL words per entry of u.
+static inline size_t p2p_ll_offset(int64_t n_local) { return sizeof(P2PArenaHdr) + (size_t)n_local * 6 * sizeof(double) + 256; }
 static_assert(P2P_MAXR == 16, "halo_cnt replaces the former 128-byte pad");
 static_assert(sizeof(P2PArenaHdr) % 32 == 0, "u behind the header is read with 256-bit loads");
+static_assert(offsetof(P2PArenaHdr, mail) == 0 && sizeof(PersistRankMail) == sizeof(P2PArenaHdr::mail) && P2P_MAXR == 16,
+              "pcg_persist.cuh posts its rank totals into the mail words at the head of the arena");
 struct P2P {
   int nranks = 1, rank = 0;
   unsigned long long epoch = 0;
@@ -1598,6 +1659,8 @@ struct P2P {
   // device copies for kernels
   unsigned char** d_peer = nullptr;
   unsigned long long pushes_done = 0;   // fused-halo path: pushes completed by earlier solves (same on all ranks)
+  unsigned long long ll_pushes = 0;     // persistent kernel: productions of u so far (tags of the halo inbox words)
+  int64_t peer_n_local[P2P_MAXR] = {0}; // n_local of every rank (read from the mapped headers)
   // halo push/wait runs on a side stream next to the product of the interior rows (fork/join by events)
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -1733,9 +1796,11 @@ extern "C" int lat_p2p_arena_create(lat_ctx* ctx, int64_t n_local, void* handle6
   P2P* p = ctx->p2p;
   if (p->attached) return lat_fail(ctx, LAT_ERR_STATE, "p2p arena already attached: destroy the comm first", __FILE__, __LINE__);
   if (p->arena) { cudaFree(p->arena); p->arena = nullptr; }
-  p->arena_bytes = sizeof(P2PArenaHdr) + (size_t)n_local * 6 * sizeof(double) + 256;
+  p->arena_bytes = p2p_ll_offset(n_local) + (size_t)n_local * 6 * 2 * sizeof(unsigned long long);
   LAT_CUDA(ctx, cudaMalloc(&p->arena, p->arena_bytes));
   LAT_CUDA(ctx, cudaMemset(p->arena, 0, p->arena_bytes));
+  const unsigned long long nl = (unsigned long long)n_local;
+  LAT_CUDA(ctx, cudaMemcpy(p->arena + offsetof(P2PArenaHdr, n_local_nodes), &nl, sizeof nl, cudaMemcpyHostToDevice));
   p->n_local = n_local;
   cudaIpcMemHandle_t h;
   LAT_CUDA(ctx, cudaIpcGetMemHandle(&h, p->arena));
@@ -1761,6 +1826,11 @@ extern "C" int lat_p2p_attach(lat_ctx* ctx, const void* handles, int nranks, int
     void* ptr = nullptr;
     LAT_CUDA(ctx, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
     p->peer[q] = reinterpret_cast<unsigned char*>(ptr);
+  }
+  for (int q = 0; q < nranks; ++q) {   // every owner wrote its header before the handles were exchanged
+    unsigned long long nl = 0;
+    LAT_CUDA(ctx, cudaMemcpy(&nl, p->peer[q] + offsetof(P2PArenaHdr, n_local_nodes), sizeof nl, cudaMemcpyDeviceToHost));
+    p->peer_n_local[q] = (int64_t)nl;
   }
   p->n_nb = n_neighbors;
   for (int k = 0; k < n_neighbors; ++k) { p->nb_rank[k] = nb_rank[k]; p->nb_dst_off[k] = nb_dst_node0[k]; }
@@ -2096,6 +2166,28 @@ static int pcg_run_dist_impl(lat_ctx* ctx, const int32_t* rowptr, const int32_t*
     }
     return LAT_OK;
   };
+  // Slabs that fit the shared memory of every rank: the whole solve in ONE persistent kernel per GPU, halo and
+  // all-reduce inside its two grid barriers (pcg_persist.cuh, "Multi-GPU").  Bit 7 of `reserved` opts out.
+  if (fused && !mf && multi && !(o->reserved & 128) && o->profile_iters <= 0) {
+    PersistDistSetup ds;
+    ds.u = u;
+    ds.nranks = pp->nranks; ds.my_rank = pp->rank; ds.n_nb = h->n_neighbors;
+    for (int k = 0; k < h->n_neighbors; ++k) {
+      ds.ghost_first[k] = 6 * gmap.first[k];
+      ds.ghost_entries[k] = 6 * h->recv_count[k];
+      ds.peer_ll[k] = reinterpret_cast<unsigned long long*>(pp->peer[h->peer[k]] + p2p_ll_offset(pp->peer_n_local[h->peer[k]]));
+    }
+    ds.push_base = pp->ll_pushes; ds.seq_base = prm.seq_base;
+    ds.push_dst = hpush.dst; ds.peers = pp->d_peer;
+    ds.my_ll = reinterpret_cast<const unsigned long long*>(pp->arena + p2p_ll_offset(pp->n_local));
+    bool used = false;
+    const int prc = pcg_run_persist<PC>(ctx, rowptr, colidx, vals, n_own, b, x, o, res, &used, &ds);
+    if (prc != LAT_OK) return prc;
+    if (used) {
+      pp->ll_pushes += ds.pushes;
+      return LAT_OK;
+    }
+  }
   LAT_CUDA(ctx, cudaMemsetAsync(sc, 0, sizeof(PcgScalars), ctx->stream));
   const int32_t one = 1;
   LAT_CUDA(ctx, cudaMemcpyAsync(&sc->first, &one, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));

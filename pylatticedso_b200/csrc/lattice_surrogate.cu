@@ -466,7 +466,7 @@ int launch_expand(lat_ctx* ctx, const double* basisP, const double* alphas, int6
                   double* out) {
   // column split: enough CTAs for two waves when there are few queries, otherwise long column runs per CTA
   const int64_t gx = ceil_div(M, 256);
-  int cols = 768;
+  int cols = 1024;                                    // a multiple of 16 at every halving
   while (cols > 16 && gx * ceil_div(L, cols) < 2 * ctx->sm_count) cols /= 2;
   const dim3 grid((unsigned)gx, (unsigned)ceil_div(L, cols));
   if (k0 == 0) LAT_LAUNCH(ctx, (k_basis_expand<KT, false>), grid, 256, 0, basisP, alphas, M, k, lda, k0, Kp, L, cols, out);

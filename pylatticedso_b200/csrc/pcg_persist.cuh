@@ -31,7 +31,23 @@
 // HBM traffic per iteration: the matrix (+ block-Jacobi inverse); the vectors never leave the SM.  All spins are
 // bounded: a CTA that waits longer than ~1 s reports info = 4 and every CTA leaves.
 //
-// Included by lattice_solver.cu after PcgScalars / PcgParams / dot6 / load_precond / apply_precond.
+// Multi-GPU (template DIST, slab partitions with <= 2 neighbours, every rank's slab on chip): the same kernel runs on
+// every GPU, one cooperative launch per rank, and the two grid synchronisations of an iteration also carry the exchange:
+//   * the update phase sends every boundary entry of the new u to the neighbour that mirrors it as two 8-byte
+//     {32 data bits | 32 tag bits} words (tag = number of the production of u) into the neighbour's halo INBOX: data
+//     and flag travel in one NVLink store, so the sender needs no system-scope release fence (one NVLink round trip
+//     per CTA: the first version -- plain stores + fence.acq_rel.sys + a counter -- spent 10-13 us in barrier A
+//     instead of 4.4, profiles/r02_persist_dist_trace.txt) and the receiver no acquire fence; at the start of barrier A
+//     every CTA unpacks its share of the inbox into the ghost section of u (plain local stores, published by the
+//     barrier's own gpu-scope release like the rest of u), so the barrier returns when the local u AND the ghosts are
+//     complete;
+//   * barrier B first reduces inside the GPU as before, then CTA 0 posts the three local totals to every rank's
+//     mailbox (LL words, one hop) and every CTA of every rank adds the rank totals in rank order: identical bits on
+//     all CTAs of all ranks, so all of them take the same branches and execute the same number of barriers;
+//   * the true-residual check multiplies u := x (pushed like any other u), so x needs no ghosts.
+// No NCCL call and no host round trip inside the solve; all cross-GPU spins are bounded (info = 4 on time-out).
+//
+// Included by lattice_solver.cu after PcgScalars / PcgParams / dot6 / load_precond / apply_precond and the P2P arena.
 #pragma once
 
 static constexpr int PERSIST_BLOCK = 1024;             // one CTA per SM
@@ -60,6 +76,17 @@ struct PersistArgs {
                               //    product phase loses its L1 and slowed from 15.5 to 26 us at config 1)
   long long* trace;           // optional [G][trace_iters][9] SM clock stamps of CTA thread 0 (+ [G][2] rows, blocks)
   int trace_iters;
+  // ---- multi-GPU (DIST = true): slab partition over NVLink peer memory, see "Multi-GPU" below.  u is the ghosted
+  // vector inside this rank's arena ([owned | ghosts]); n_nodes counts the OWNED rows.
+  int nranks, my_rank, n_nb;
+  long long ghost_first[2];             // first ghost entry (6 x node) of neighbour k in my u
+  int ghost_entries[2];                 // entries neighbour k sends me with every new u (6 x ghost nodes)
+  unsigned long long push_base;         // productions of u completed by earlier solves (same on every rank): halo tags
+  unsigned long long seq_base;          // epoch of this solve << 32 (flag of the rank-level mailbox words)
+  const int2* push_dst;                 // per owned node: ghost node in neighbour 0 / 1 that mirrors it (-1: none)
+  unsigned long long* peer_ll[2];       // the neighbours' halo inboxes (IPC-mapped): two LL words per entry of THEIR u
+  const unsigned long long* my_ll;      // my halo inbox
+  unsigned char* const* peers;          // all arenas (device array), for the rank-level all-reduce
 };
 
 // Rows of CTA c: chunks c, c + G, c + 2G, ... of PERSIST_CHUNK consecutive rows.
@@ -106,12 +133,7 @@ __device__ __forceinline__ void st_relaxed_gpu_u32(unsigned int* p, unsigned int
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-struct PersistShared {
-  double red[3][PERSIST_NW];
-  double loc[3];
-  double tot[3];
-  int timeout;
-};
+
 
 // Barrier A: every global store of this CTA (the new u / x of its rows) is visible to every CTA afterwards.
 // All-to-all flags with PRIVATE inboxes: CTA c stores its epoch into slot c of every CTA's inbox (G 4-byte stores by G
@@ -119,10 +141,48 @@ struct PersistShared {
 // version had one flag per CTA that all G x G pollers read: 5 hot lines, 5.5 us per barrier
 // (profiles/r02_persist_trace.txt); the acquire fence afterwards drops the SM's L1 lines (CCTL.IVALL).
 static constexpr int PERSIST_INBOX_STRIDE = 160;     // u32 slots per inbox row (G <= 160), 640 B = 5 lines
+static constexpr long long PERSIST_SPIN_LIMIT_SYS = 1ll << 25;   // cross-GPU waits: the peers may start their kernel later
+struct PersistShared {
+  double red[3][PERSIST_NW];
+  double loc[3];
+  double tot[3];
+  int timeout;
+};
+__device__ __forceinline__ unsigned int persist_tag(const PersistArgs& a, unsigned int epoch) {
+  return ((unsigned int)(a.push_base + (unsigned long long)epoch) & 0x7fffffffu) | 0x80000000u;     // never 0
+}
+// DIST, receiver side: CTA c unpacks entries [c * per, (c + 1) * per) of each neighbour's part of the inbox.
+__device__ __forceinline__ void persist_unpack(const PersistArgs& a, unsigned int tag, int G, PersistShared& sh) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    if (k >= a.n_nb) break;
+    const int E = k == 0 ? a.ghost_entries[0] : a.ghost_entries[1];
+    const long long first = k == 0 ? a.ghost_first[0] : a.ghost_first[1];
+    const int per = (E + G - 1) / G;
+    const int lo = blockIdx.x * per, hi = lo + per < E ? lo + per : E;
+    for (int e = lo + threadIdx.x; e < hi; e += PERSIST_BLOCK) {
+      const unsigned long long* src = a.my_ll + (size_t)(first + e) * 2;
+      unsigned long long w0, w1;
+      long long spins = 0;
+      for (;;) {
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+        if ((unsigned int)(w0 >> 32) == tag && (unsigned int)(w1 >> 32) == tag) break;
+        if (++spins > PERSIST_SPIN_LIMIT_SYS) { sh.timeout = 1; break; }
+        if (spins > 4096) __nanosleep(64);
+      }
+      a.u[first + e] = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+    }
+  }
+}
+template <bool DIST>
 __device__ __forceinline__ void persist_barrier(unsigned int* inbox, unsigned int epoch, int G, PersistShared& sh,
-                                                long long* stamp = nullptr) {
+                                                long long* stamp, const PersistArgs& a) {
   __syncthreads();                                   // the CTA's stores are issued ...
   if (stamp && threadIdx.x == 0) stamp[0] = clock64();
+  if (DIST) {
+    persist_unpack(a, persist_tag(a, epoch), G, sh); // ... the ghosts this CTA is responsible for are in u ...
+    __syncthreads();
+  }
   if ((int)threadIdx.x < G) {
     asm volatile("fence.acq_rel.gpu;" ::: "memory");  // ... and ordered before this thread's flag (cumulative at gpu scope)
     st_relaxed_gpu_u32(inbox + (size_t)threadIdx.x * PERSIST_INBOX_STRIDE + blockIdx.x, epoch);
@@ -145,8 +205,14 @@ __device__ __forceinline__ void persist_barrier(unsigned int* inbox, unsigned in
 // Barrier B: grid-wide sum of three values, result in sh.tot[] for every thread of every CTA (same bits everywhere).
 // One shared mailbox (56 lines read by every CTA).  Private inboxes as in barrier A were tried and are SLOWER here
 // (148 x 888 eight-byte stores per reduction: 3.8 -> 6.2 us); so were L1-bypassing gathers without the acquire fence.
+// DIST: the local totals then travel once over NVLink -- CTA 0 posts them into every rank's arena (the mail words of
+// P2PArenaHdr: [parity][source rank][6], same LL format, flag = solve epoch + reduction number) and EVERY CTA of every
+// rank adds the rank totals in rank order.
+struct PersistRankMail { unsigned long long mail[2][16][6]; };     // = the head of P2PArenaHdr (static_assert there)
+template <bool DIST>
 __device__ __forceinline__ void persist_reduce(double (&v)[3], unsigned long long* mail, unsigned int epoch, int G,
-                                               PersistShared& sh, double* s_scratch /* >= 3*G doubles */) {
+                                               PersistShared& sh, double* s_scratch /* >= 3*G doubles */,
+                                               const PersistArgs& a) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
@@ -189,6 +255,41 @@ __device__ __forceinline__ void persist_reduce(double (&v)[3], unsigned long lon
     if (lane == 0) sh.tot[wid] = s;
   }
   __syncthreads();
+  if (DIST && a.nranks > 1) {
+    const unsigned long long seq = a.seq_base + (unsigned long long)epoch;
+    // 12 bits of the solve epoch + 20 bits of the reduction number, never 0 (the arena starts zeroed)
+    const unsigned long long rflag = ((((seq >> 32) & 0xfffull) << 20) | ((seq & 0xfffffull) + 1ull) | 0x80000000ull) << 32;
+    const int par = (int)(epoch & 1u);
+    const int nw = a.nranks * 6;
+    if (blockIdx.x == 0 && (int)threadIdx.x < nw) {
+      const int q = threadIdx.x / 6, w = threadIdx.x - q * 6;
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(sh.tot[w >> 1]);
+      const unsigned long long half = (w & 1) ? (bits >> 32) : (bits & 0xffffffffull);
+      PersistRankMail* hdr = reinterpret_cast<PersistRankMail*>(a.peers[q]);
+      asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(&hdr->mail[par][a.my_rank][w]), "l"(rflag | half) : "memory");
+    }
+    __syncthreads();                                   // sh.tot is overwritten below
+    if ((int)threadIdx.x < nw) {
+      const int q = threadIdx.x / 6, w = threadIdx.x - q * 6;
+      const PersistRankMail* mine = reinterpret_cast<const PersistRankMail*>(a.peers[a.my_rank]);
+      unsigned long long word;
+      long long spins = 0;
+      for (;;) {
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(word) : "l"(&mine->mail[par][q][w]) : "memory");
+        if ((word & 0xffffffff00000000ull) == rflag) break;
+        if (++spins > PERSIST_SPIN_LIMIT_SYS) { sh.timeout = 1; break; }
+        if (spins > 4096) __nanosleep(64);
+      }
+      reinterpret_cast<unsigned int*>(s_scratch)[(size_t)(q * 3 + (w >> 1)) * 2 + (w & 1)] = (unsigned int)(word & 0xffffffffull);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      double s = 0.0;
+      for (int q = 0; q < a.nranks; ++q) s += s_scratch[q * 3 + threadIdx.x];     // rank order
+      sh.tot[threadIdx.x] = s;
+    }
+    __syncthreads();
+  }
 }
 
 // s_w = (A v) on the CTA's rows: six lanes per block row in the transposed-piece layout, three blocks (12 x 16 B loads
@@ -271,7 +372,23 @@ __device__ __forceinline__ UpdLoads persist_upd_load(const PersistArgs& a, bool 
   return L;
 }
 
-template <int PC>
+// Store one entry of a freshly produced u: the owned copy and, for the nodes a neighbour mirrors, two LL words into
+// that neighbour's halo inbox (slot = entry index in THEIR u).
+template <bool DIST>
+__device__ __forceinline__ void persist_store_u(const PersistArgs& a, const uint8_t* s_pflag, int lr, int64_t n, int dof, double val,
+                                                unsigned int tag) {
+  a.u[n * 6 + dof] = val;
+  if (DIST && s_pflag[lr]) {
+    const int2 d = a.push_dst[n];
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(val);
+    const unsigned long long t = (unsigned long long)tag << 32;
+    const unsigned long long w0 = t | (bits & 0xffffffffull), w1 = t | (bits >> 32);
+    if (d.x >= 0) asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(a.peer_ll[0] + ((size_t)d.x * 6 + dof) * 2), "l"(w0), "l"(w1) : "memory");
+    if (d.y >= 0) asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(a.peer_ll[1] + ((size_t)d.y * 6 + dof) * 2), "l"(w0), "l"(w1) : "memory");
+  }
+}
+
+template <int PC, bool DIST = false>
 __global__ void __launch_bounds__(PERSIST_BLOCK, 1) k_pcg_persist(PersistArgs a) {
   extern __shared__ __align__(16) unsigned char persist_smem[];
   __shared__ PersistShared sh;
@@ -294,6 +411,7 @@ __global__ void __launch_bounds__(PERSIST_BLOCK, 1) k_pcg_persist(PersistArgs a)
   int32_t* s_rp = reinterpret_cast<int32_t*>(s_scratch + 3 * G);    // [rows_cap + 1] local block offset of each row
   int32_t* s_gb = s_rp + a.rows_cap + 1;                            // [rows_cap]     global index of the row's first block
   int32_t* s_col = s_gb + a.rows_cap;                               // [blk_cap]      column indices in local block order
+  uint8_t* s_pflag = reinterpret_cast<uint8_t*>(s_col + a.blk_cap); // [rows_cap]     DIST: row is mirrored by a neighbour
   if (threadIdx.x == 0) sh.timeout = 0;
   // local block offsets: per chunk (contiguous rows -> one subtraction), then a short serial scan
   for (int k = threadIdx.x; k < nchunks; k += PERSIST_BLOCK) {
@@ -320,6 +438,12 @@ __global__ void __launch_bounds__(PERSIST_BLOCK, 1) k_pcg_persist(PersistArgs a)
   for (int lr = wid; lr < nrows; lr += PERSIST_NW) {              // one warp per row: its column indices
     const int lp = s_rp[lr], nb = s_rp[lr + 1] - lp, gb = s_gb[lr];
     for (int k = lane; k < nb; k += 32) s_col[lp + k] = a.colidx[gb + k];
+  }
+  if (DIST) {
+    for (int lr = threadIdx.x; lr < nrows; lr += PERSIST_BLOCK) {
+      const int2 d = a.push_dst[persist_global_row(lr, cta, G)];
+      s_pflag[lr] = (uint8_t)((d.x >= 0) | ((d.y >= 0) << 1));
+    }
   }
   const double* __restrict__ vals = a.vals;
   double* __restrict__ u = a.u;
@@ -349,7 +473,9 @@ __global__ void __launch_bounds__(PERSIST_BLOCK, 1) k_pcg_persist(PersistArgs a)
     const int lr = base + g;
     if (g < 5 && lr < nrows) {
       const int64_t n = persist_global_row(lr, cta, G);
-      u[n * 6 + dof] = pcs ? persist_precond<PC>(s_m, s_r, lr, dof) : persist_precond_global<PC>(a.dinv, n, s_r, lr, dof);
+      persist_store_u<DIST>(a, s_pflag, lr, n, dof,
+                            pcs ? persist_precond<PC>(s_m, s_r, lr, dof) : persist_precond_global<PC>(a.dinv, n, s_r, lr, dof),
+                            persist_tag(a, 1u));
     }
   }
   unsigned int epochA = 0, epochB = 0;
@@ -357,7 +483,7 @@ __global__ void __launch_bounds__(PERSIST_BLOCK, 1) k_pcg_persist(PersistArgs a)
     a.trace[(size_t)G * a.trace_iters * 9 + 2 * blockIdx.x] = nrows;
     a.trace[(size_t)G * a.trace_iters * 9 + 2 * blockIdx.x + 1] = nblk;
   }
-  persist_barrier(a.flags, ++epochA, G, sh);
+  persist_barrier<DIST>(a.flags, ++epochA, G, sh, nullptr, a);
 
   int first = 1, iters = 0, done = 0, breakdown = 0, restarts = 0, trace_it = 0;
   double gamma_old = 0.0, alpha = 0.0, beta = 0.0, bb = 0.0, rr = 0.0, true_rr = -1.0;
@@ -381,7 +507,7 @@ __global__ void __launch_bounds__(PERSIST_BLOCK, 1) k_pcg_persist(PersistArgs a)
       }
     }
     if (tracing) { __syncthreads(); if (threadIdx.x == 0) tr[1] = clock64(); }
-    persist_reduce(v, a.mail, ++epochB, G, sh, s_scratch);
+    persist_reduce<DIST>(v, a.mail, ++epochB, G, sh, s_scratch, a);
     if (tracing && threadIdx.x == 0) tr[2] = clock64();
     if (sh.timeout) break;
     const double gamma = sh.tot[0], delta = sh.tot[1];
@@ -410,7 +536,19 @@ __global__ void __launch_bounds__(PERSIST_BLOCK, 1) k_pcg_persist(PersistArgs a)
       if (!(done && !breakdown && bb > 0.0)) break;
       // ---- true-residual safeguard: r_true = b - A x  (x is global and, after the last barrier A, visible everywhere)
       double t[3] = {0.0, 0.0, 0.0};
-      persist_product(vals, a.x, s_rp, s_gb, s_col, s_w, nrows);
+      if (DIST) {
+        // x has no ghosts: multiply u := x, exchanged like every other u (u is rebuilt from r on a restart)
+        for (int base = wid * 5; base < nrows; base += PERSIST_NW * 5) {
+          const int lr = base + g;
+          if (g < 5 && lr < nrows) {
+            const int64_t n = persist_global_row(lr, cta, G);
+            persist_store_u<DIST>(a, s_pflag, lr, n, dof, a.x[n * 6 + dof], persist_tag(a, epochA + 1u));
+          }
+        }
+        persist_barrier<DIST>(a.flags, ++epochA, G, sh, nullptr, a);
+        if (sh.timeout) break;
+      }
+      persist_product(vals, DIST ? (const double*)u : (const double*)a.x, s_rp, s_gb, s_col, s_w, nrows);
       for (int base = wid * 5; base < nrows; base += PERSIST_NW * 5) {
         const int lr = base + g;
         if (g < 5 && lr < nrows) {
@@ -420,7 +558,7 @@ __global__ void __launch_bounds__(PERSIST_BLOCK, 1) k_pcg_persist(PersistArgs a)
           t[0] = fma(rt, rt, t[0]);
         }
       }
-      persist_reduce(t, a.mail, ++epochB, G, sh, s_scratch);
+      persist_reduce<DIST>(t, a.mail, ++epochB, G, sh, s_scratch, a);
       if (sh.timeout) break;
       true_rr = sh.tot[0];
       if (!(true_rr > 4.0 * tol2 * bb)) break;                       // accepted
@@ -435,17 +573,20 @@ __global__ void __launch_bounds__(PERSIST_BLOCK, 1) k_pcg_persist(PersistArgs a)
       for (int base = wid * 5; base < nrows; base += PERSIST_NW * 5) {
         const int lr = base + g;
         if (g < 5 && lr < nrows) {
-      const int64_t n = persist_global_row(lr, cta, G);
-      u[n * 6 + dof] = pcs ? persist_precond<PC>(s_m, s_r, lr, dof) : persist_precond_global<PC>(a.dinv, n, s_r, lr, dof);
-    }
+          const int64_t n = persist_global_row(lr, cta, G);
+          persist_store_u<DIST>(a, s_pflag, lr, n, dof,
+                                pcs ? persist_precond<PC>(s_m, s_r, lr, dof) : persist_precond_global<PC>(a.dinv, n, s_r, lr, dof),
+                                persist_tag(a, epochA + 1u));
+        }
       }
-      persist_barrier(a.flags, ++epochA, G, sh);
+      persist_barrier<DIST>(a.flags, ++epochA, G, sh, nullptr, a);
       done = 0;
       first = 2;
       continue;
     }
     // ---- update phase: p = u + beta p; s = w + beta s; x += alpha p; r -= alpha s; u = M^-1 r
     // two row groups per trip; the only global loads (own u, x) of both are issued first, the rest is shared memory
+    const unsigned int utag = DIST ? persist_tag(a, epochA + 1u) : 0u;
     for (int base = wid * 5; base < nrows; base += 2 * PERSIST_NW * 5) {
       const int lrA = base + g, lrB = base + PERSIST_NW * 5 + g;
       const bool actA = g < 5 && lrA < nrows, actB = g < 5 && lrB < nrows;
@@ -473,22 +614,22 @@ __global__ void __launch_bounds__(PERSIST_BLOCK, 1) k_pcg_persist(PersistArgs a)
         s_r[liB] = fma(-alpha, sv, s_r[liB]);
       }
       __syncwarp();                                     // the six entries of r of each node are in shared memory
+      double zA = 0.0, zB = 0.0;
       if (pcs || PC == LAT_PC_NONE) {
-        if (actA) u[iA] = persist_precond<PC>(s_m, s_r, lrA, dof);
-        if (actB) u[iB] = persist_precond<PC>(s_m, s_r, lrB, dof);
+        if (actA) zA = persist_precond<PC>(s_m, s_r, lrA, dof);
+        if (actB) zB = persist_precond<PC>(s_m, s_r, lrB, dof);
       } else if (PC == LAT_PC_JACOBI) {
-        if (actA) u[iA] = mA[0] * s_r[liA];
-        if (actB) u[iB] = mB[0] * s_r[liB];
+        if (actA) zA = mA[0] * s_r[liA];
+        if (actB) zB = mB[0] * s_r[liB];
       } else {
-        double zA = 0.0, zB = 0.0;
 #pragma unroll
         for (int k = 0; k < 6; ++k) { zA = fma(mA[k], s_r[lrA * 6 + k], zA); zB = fma(mB[k], s_r[lrB * 6 + k], zB); }
-        if (actA) u[iA] = zA;
-        if (actB) u[iB] = zB;
       }
+      if (actA) persist_store_u<DIST>(a, s_pflag, lrA, iA / 6, dof, zA, utag);
+      if (actB) persist_store_u<DIST>(a, s_pflag, lrB, iB / 6, dof, zB, utag);
     }
     if (tracing) { __syncthreads(); if (threadIdx.x == 0) tr[3] = clock64(); }
-    persist_barrier(a.flags, ++epochA, G, sh, tracing ? tr + 5 : nullptr);
+    persist_barrier<DIST>(a.flags, ++epochA, G, sh, tracing ? tr + 5 : nullptr, a);
     if (tracing && threadIdx.x == 0) tr[4] = clock64();
     ++trace_it;
   }
@@ -505,6 +646,7 @@ __global__ void __launch_bounds__(PERSIST_BLOCK, 1) k_pcg_persist(PersistArgs a)
     sc->restarts = restarts;
     sc->true_rr = true_rr;
     sc->seq = (int)epochB;
+    sc->counter[0] = epochA;          // productions of u (= halo pushes) of this solve
   }
   if (timed_out && threadIdx.x == 0) a.sc->p2p_timeout = 1;
 }

@@ -294,7 +294,7 @@ class DistributedFEM:
         self.p2p = True
 
     def solve(self, tol=1e-8, maxiter=200000, precond=2, vals_bc=None, b=None, u=None, check_every=0, profile_iters=0,
-              overlap=False, fused_halo=True):
+              overlap=False, fused_halo=True, persistent=True):
         """Returns (u_local [6 n_local] incl. ghosts, reactions on owned rows, info)."""
         torch, ctx = self.torch, self.ctx
         if self.vals is None:
@@ -311,7 +311,7 @@ class DistributedFEM:
                                               L._ptr(self.f_d), L._ptr(vals_bc), L._ptr(b)))
         u, info = ctx.pcg_dist(self.rowptr, self.colidx, vals_bc, self.halo, b, u, tol=tol, maxiter=maxiter,
                                precond=precond, check_every=check_every, p2p=getattr(self, "p2p", False),
-                               profile_iters=profile_iters, overlap=overlap, fused_halo=fused_halo)
+                               profile_iters=profile_iters, overlap=overlap, fused_halo=fused_halo, persistent=persistent)
         ctx.set_dirichlet_values(self.fixed_d, self.g_d, u)
         ctx.halo_exchange(self.halo, u)
         R = ctx.spmv(self.rowptr, self.colidx, self.vals, u)     # rows >= n_owned are partial: ignore

@@ -491,13 +491,17 @@ class Context:
 
     def pcg_dist(self, rowptr, colidx, vals, halo, b, x, tol=1e-8, maxiter=10000, precond=PC_JACOBI,
                  reference_semantics=False, mintol=0.0, alpha_max=0.0, restart_every=0, check_every=0, p2p=False,
-                 no_graph=False, profile_iters=0, overlap=False, fused_halo=True):
+                 no_graph=False, profile_iters=0, overlap=False, fused_halo=True, persistent=True):
+        """``persistent=True`` (default, peer-memory path with the fused halo): slabs whose vectors fit every GPU's
+        shared memory are solved by one persistent cooperative kernel per rank with the halo exchange and the
+        all-reduce inside its grid barriers (csrc/pcg_persist.cuh, "Multi-GPU"; ``info['persistent']``)."""
         o = PcgOpts(tol, mintol, alpha_max, restart_every, maxiter, precond, int(reference_semantics), check_every,
                     profile_iters,
-                    (16 if p2p else 0) | (4 if no_graph else 0) | (32 if overlap else 0) | (0 if fused_halo else 64))
+                    (16 if p2p else 0) | (4 if no_graph else 0) | (32 if overlap else 0) | (0 if fused_halo else 64) |
+                    (0 if persistent else 128))
         r = PcgResult()
         self.check(self.lib.lat_pcg_bsr_dist(self.h, _ptr(rowptr), _ptr(colidx), _ptr(vals), C.byref(halo), _ptr(b),
                                              _ptr(x), C.byref(o), C.byref(r)))
         return x, dict(iters=r.iters, info=r.info, relres=r.relres, norm_b=r.norm_b, solve_ms=r.solve_ms,
                        launches=r.launches, true_relres=r.true_relres, restarts=r.reserved & 0xff, graph=bool(r.reserved & 0x100), spmv_ms=r.spmv_ms,
-                       update_ms=r.update_ms, profiled=r.profiled)
+                       update_ms=r.update_ms, profiled=r.profiled, persistent=bool(r.reserved & 0x200))
