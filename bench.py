@@ -286,6 +286,7 @@ def parity_sharded(ctx, dfem, mesh, fixed, g, f, rank):
         res["R_rel"] = max(res[k]["R_rel"] for k in sols)
         res["grad_rel"] = max(res[k]["grad_rel"] for k in sols)
         res["ok"] = bool(ok)
+        res["_u_full"] = u0             # popped by the joint-only section (not part of the JSON line)
         del one
     dist.barrier()
     return res
@@ -678,6 +679,43 @@ def run_b200(args):
         parity = parity_sharded(ctx, dfem, mesh, fixed, g, f, rank)
     else:
         parity = parity_single(ctx, fem, fixed, g, f)
+    # ---- secondary (N > 1): the strut-condensed joint-only system, sharded (DistributedJointFEM), same load case;
+    #      after the parity block because it needs the context's peer-memory arena for its own (smaller) vectors
+    if distributed:
+        if getattr(dfem, "p2p", False):
+            ctx.p2p_destroy()
+            dfem.p2p = False
+        jf = D.DistributedJointFEM(ctx, mesh, E_MOD, NU, rank, world, KAPPA)
+        nj = 6 * mesh.n_points
+        jf.set_bc(fixed[:nj], g[:nj], f[:nj])
+        if comm_mode == "nvlink-peer-memory":
+            jf.enable_p2p()
+        cms, cit = 0.0, 0
+        for s_ in range(args.warmup + args.steps):
+            flush.fill_(1.0)
+            barrier()
+            a, b_ = ev(), ev()
+            a.record()
+            jf.assemble()
+            uj, Rj, info = jf.solve(tol=1e-8, maxiter=200000, precond=L.PC_BLOCK6)
+            b_.record()
+            barrier()
+            assert info["info"] == 0, f"joint-only PCG did not converge: {info}"
+            if s_ >= args.warmup:
+                cms += a.elapsed_time(b_); cit += info["iters"]
+        # parity of the sharded joint-only solve: against the sharded FULL solve of the parity block at the lattice points
+        uj12, _, _ = jf.solve(tol=1e-12, maxiter=400000, precond=L.PC_BLOCK6)
+        ujg = jf.gather_owned(uj12)
+        cond = dict(ms=cms / args.steps, iters=cit / args.steps, n_dof=nj, persistent=bool(info.get("persistent", False)))
+        if rank == 0 and parity.get("_u_full") is not None:
+            u_full = parity.pop("_u_full")
+            cond["u_rel_vs_full_solve"] = float(np.abs(ujg - u_full[:nj]).max() / np.abs(u_full).max())
+            parity["joint_only_u_rel"] = cond["u_rel_vs_full_solve"]
+            parity["ok"] = bool(parity["ok"] and cond["u_rel_vs_full_solve"] < 1e-8)
+        parity.pop("_u_full", None)
+        if getattr(jf, "p2p", False):
+            ctx.p2p_destroy()
+        del jf
     # ---- BASELINE configs[4] on the same N GPUs
     cfg5 = None
     if not args.no_config5:
@@ -698,6 +736,10 @@ def run_b200(args):
         t = torch.tensor([res["tot_ms"], res["e2e_ms"], res["asm_ms"], res["solve_ms"], res["mf_ms"]], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         tot_ms, res["e2e_ms"], res["asm_ms"], res["solve_ms"], res["mf_ms"] = (float(v) for v in t)
+        if res.get("cond"):
+            tc = torch.tensor([res["cond"]["ms"]], dtype=torch.float64, device=dev)
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+            res["cond"]["ms"] = float(tc[0])
         t2 = torch.tensor([res["h2d"], res["d2h"], res["launches"], res["n_nodes"], res["nnzb"]], dtype=torch.float64, device=dev)
         dist.all_reduce(t2, op=dist.ReduceOp.SUM)
         res["h2d"], res["d2h"], res["launches"] = int(t2[0]), int(t2[1]), int(t2[2])
@@ -806,6 +848,8 @@ def run_b200(args):
         c = res["cond"]
         line["strut_condensed"] = {"ms_per_step": c["ms"], "n_dof": c["n_dof"], "iterations_per_step": c["iters"],
                                    "speedup_vs_headline_step": (tot_ms / args.steps) / c["ms"],
+                                   "sharded": world > 1, "persistent_kernel": c.get("persistent"),
+                                   "u_rel_vs_full_solve": c.get("u_rel_vs_full_solve"),
                                    "note": "same load case and tolerance through the exact joint-only system (every strut "
                                            "condensed onto its two lattice points, lat_assemble_bsr_struts): identical "
                                            "lattice-point displacements and reactions; a time-to-solution figure, not "

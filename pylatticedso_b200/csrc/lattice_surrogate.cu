@@ -10,6 +10,7 @@
 // n_B^2 = 1296..7056, n_q = every cell of the lattice): it runs on the FP64 tensor cores (mma.sync m8n8k4 = DMMA) and
 // is bound by writing S (8 n_B^2 bytes per cell) for small k and by the DMMA pipe from k ~ 40 on.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -400,23 +401,23 @@ __device__ __forceinline__ void st256(double* p, double a, double b, double c, d
   asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
 
-// out[q][l] (+)= sum_kk alphas[q][k0 + kk] basisP[k0 + kk][l].  One warp = 32 rows (four 8-row DMMA tiles) whose
+// out[q][l] (+)= sum_kk alphas[q][k0 + kk] basisP[k0 + kk][l].  One warp = 8 MT rows (MT 8-row DMMA tiles) whose
 // coefficients stay in registers in A-fragment layout (lane (r8, c4) holds alpha[q0 + 8 mt + r8][4 kk + c4]); the warp
 // walks its column range in groups of 16: B fragments straight from basisP through L1 (the eight warps of a CTA walk
 // the same columns), two 8-column tiles per group with the columns interleaved so that every lane ends up with FOUR
 // CONSECUTIVE outputs of one row -> one 256-bit store per tile row, 128 contiguous bytes per row and instruction.
 //   tile t in {0,1}, tile column n  <->  output column l0 + 4 (n / 2) + 2 t + (n % 2)
-template <int KT, bool ACCUM>
+template <int KT, int MT, bool ACCUM>
 __global__ void __launch_bounds__(256) k_basis_expand(const double* __restrict__ basisP, const double* __restrict__ alphas, int64_t M,
                                                       int k, int lda, int k0, int Kp, int64_t L, int cols_per_cta,
                                                       double* __restrict__ out) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int r8 = lane >> 2, c4 = lane & 3;
-  const int64_t q0 = ((int64_t)blockIdx.x * 8 + wid) * 32;
+  const int64_t q0 = ((int64_t)blockIdx.x * 8 + wid) * (8 * MT);
   if (q0 >= M) return;
-  double a[4][KT];
+  double a[MT][KT];
 #pragma unroll
-  for (int mt = 0; mt < 4; ++mt) {
+  for (int mt = 0; mt < MT; ++mt) {
     const int64_t q = q0 + 8 * mt + r8;
 #pragma unroll
     for (int kk = 0; kk < KT; ++kk) {
@@ -428,9 +429,9 @@ __global__ void __launch_bounds__(256) k_basis_expand(const double* __restrict__
   const int64_t l_end = l_begin + cols_per_cta < L ? l_begin + cols_per_cta : L;
   const int bcol = 4 * (r8 >> 1) + (r8 & 1);
   for (int64_t l0 = l_begin; l0 < l_end; l0 += 16) {
-    double c[4][2][2];
+    double c[MT][2][2];
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt) { c[mt][0][0] = c[mt][0][1] = c[mt][1][0] = c[mt][1][1] = 0.0; }
+    for (int mt = 0; mt < MT; ++mt) { c[mt][0][0] = c[mt][0][1] = c[mt][1][0] = c[mt][1][1] = 0.0; }
     const bool bval = l0 + bcol < L;                       // L % 4 == 0: the +2 column is valid with it
     const double* bp = basisP + (size_t)(k0 + c4) * L + l0 + bcol;
 #pragma unroll
@@ -439,7 +440,7 @@ __global__ void __launch_bounds__(256) k_basis_expand(const double* __restrict__
       const double b0 = bk ? __ldg(bp + (size_t)(4 * kk) * L) : 0.0;
       const double b1 = bk ? __ldg(bp + (size_t)(4 * kk) * L + 2) : 0.0;
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt) {
+      for (int mt = 0; mt < MT; ++mt) {
         dmma884(c[mt][0][0], c[mt][0][1], a[mt][kk], b0);
         dmma884(c[mt][1][0], c[mt][1][1], a[mt][kk], b1);
       }
@@ -447,7 +448,7 @@ __global__ void __launch_bounds__(256) k_basis_expand(const double* __restrict__
     const int64_t lc = l0 + 4 * c4;
     if (lc < L) {
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt) {
+      for (int mt = 0; mt < MT; ++mt) {
         const int64_t q = q0 + 8 * mt + r8;
         if (q < M) {
           double* o = out + q * L + lc;
@@ -461,17 +462,28 @@ __global__ void __launch_bounds__(256) k_basis_expand(const double* __restrict__
   }
 }
 
-template <int KT>
+template <int KT, int MT>
 int launch_expand(lat_ctx* ctx, const double* basisP, const double* alphas, int64_t M, int k, int lda, int k0, int Kp, int64_t L,
                   double* out) {
   // column split: enough CTAs for two waves when there are few queries, otherwise long column runs per CTA
-  const int64_t gx = ceil_div(M, 256);
+  const int64_t gx = ceil_div(M, 64 * MT);
   int cols = 1024;                                    // a multiple of 16 at every halving
   while (cols > 16 && gx * ceil_div(L, cols) < 2 * ctx->sm_count) cols /= 2;
   const dim3 grid((unsigned)gx, (unsigned)ceil_div(L, cols));
-  if (k0 == 0) LAT_LAUNCH(ctx, (k_basis_expand<KT, false>), grid, 256, 0, basisP, alphas, M, k, lda, k0, Kp, L, cols, out);
-  else LAT_LAUNCH(ctx, (k_basis_expand<KT, true>), grid, 256, 0, basisP, alphas, M, k, lda, k0, Kp, L, cols, out);
+  if (k0 == 0) LAT_LAUNCH(ctx, (k_basis_expand<KT, MT, false>), grid, 256, 0, basisP, alphas, M, k, lda, k0, Kp, L, cols, out);
+  else LAT_LAUNCH(ctx, (k_basis_expand<KT, MT, true>), grid, 256, 0, basisP, alphas, M, k, lda, k0, Kp, L, cols, out);
   return LAT_OK;
+}
+// Rows per warp: 32 (four tiles share every B fragment).  16 rows per warp (half the registers, three CTAs per SM instead
+// of one at 10 k-steps) was measured and is SLOWER from 5 k-steps on (k = 38: 1.71 vs 1.41 ms): the kernel is not
+// occupancy bound, the B fragments are (profiles/r02_surrogate_ab.txt).  LAT_EXPAND_MT=2 selects it for experiments.
+template <int KT>
+int launch_expand_kt(lat_ctx* ctx, const double* basisP, const double* alphas, int64_t M, int k, int lda, int k0, int Kp, int64_t L,
+                     double* out) {
+  const char* env = getenv("LAT_EXPAND_MT");
+  const int mt = env ? atoi(env) : 4;
+  if (mt == 4) return launch_expand<KT, 4>(ctx, basisP, alphas, M, k, lda, k0, Kp, L, out);
+  return launch_expand<KT, 2>(ctx, basisP, alphas, M, k, lda, k0, Kp, L, out);
 }
 
 }  // namespace
@@ -602,12 +614,18 @@ extern "C" int lat_basis_expand(lat_ctx* ctx, const double* basisP, int32_t k, i
   for (int k0 = 0; k0 < Kp; k0 += 64) {
     const int kt = (Kp - k0 < 64 ? Kp - k0 : 64) / 4;
     int rc;
-    if (kt <= 1) rc = launch_expand<1>(ctx, basisP, alphas, M, k, lda, k0, Kp, len, out);
-    else if (kt <= 2) rc = launch_expand<2>(ctx, basisP, alphas, M, k, lda, k0, Kp, len, out);
-    else if (kt <= 4) rc = launch_expand<4>(ctx, basisP, alphas, M, k, lda, k0, Kp, len, out);
-    else if (kt <= 8) rc = launch_expand<8>(ctx, basisP, alphas, M, k, lda, k0, Kp, len, out);
-    else if (kt <= 12) rc = launch_expand<12>(ctx, basisP, alphas, M, k, lda, k0, Kp, len, out);
-    else rc = launch_expand<16>(ctx, basisP, alphas, M, k, lda, k0, Kp, len, out);
+    switch (kt) {
+      case 1: rc = launch_expand_kt<1>(ctx, basisP, alphas, M, k, lda, k0, Kp, len, out); break;
+      case 2: rc = launch_expand_kt<2>(ctx, basisP, alphas, M, k, lda, k0, Kp, len, out); break;
+      case 3: rc = launch_expand_kt<3>(ctx, basisP, alphas, M, k, lda, k0, Kp, len, out); break;
+      case 4: rc = launch_expand_kt<4>(ctx, basisP, alphas, M, k, lda, k0, Kp, len, out); break;
+      case 5: rc = launch_expand_kt<5>(ctx, basisP, alphas, M, k, lda, k0, Kp, len, out); break;
+      case 6: rc = launch_expand_kt<6>(ctx, basisP, alphas, M, k, lda, k0, Kp, len, out); break;
+      case 7: case 8: rc = launch_expand_kt<8>(ctx, basisP, alphas, M, k, lda, k0, Kp, len, out); break;
+      case 9: case 10: rc = launch_expand_kt<10>(ctx, basisP, alphas, M, k, lda, k0, Kp, len, out); break;
+      case 11: case 12: rc = launch_expand_kt<12>(ctx, basisP, alphas, M, k, lda, k0, Kp, len, out); break;
+      default: rc = launch_expand_kt<16>(ctx, basisP, alphas, M, k, lda, k0, Kp, len, out); break;
+    }
     if (rc != LAT_OK) return rc;
   }
   return LAT_OK;

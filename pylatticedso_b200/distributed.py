@@ -377,3 +377,94 @@ class DistributedFEM:
             gi = idb[q][:k].cpu().numpy()
             out.reshape(-1, 6)[gi] = bufs[q][: 6 * k].cpu().numpy().reshape(-1, 6)
         return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# joint-only (strut-condensed) system, sharded
+# ---------------------------------------------------------------------------------------------------------------
+def strut_topology(mesh: BeamMesh):
+    """Struts of a subdivided mesh in mesh.py numbering (lattice points first, elements beam-major from point1 to
+    point2): element range ``ptr[s]:ptr[s+1]`` and the two end joints ``a[s]``, ``b[s]`` of every strut."""
+    starts = np.flatnonzero(mesh.en0 < mesh.n_points)
+    ptr = np.r_[starts, mesh.n_elems]
+    a, b = mesh.en0[starts].astype(np.int64), mesh.en1[ptr[1:] - 1].astype(np.int64)
+    if (b >= mesh.n_points).any() or (np.diff(ptr) < 1).any():
+        raise ValueError("mesh is not beam-major between lattice points")
+    return ptr.astype(np.int64), a, b
+
+
+def joint_mesh(mesh: BeamMesh, sa, sb) -> BeamMesh:
+    """The lattice points as nodes and the struts as elements: what the joint-only system is partitioned on."""
+    npnt = mesh.n_points
+    ns = sa.shape[0]
+    return BeamMesh(x=mesh.x[:npnt].copy(), y=mesh.y[:npnt].copy(), z=mesh.z[:npnt].copy(), en0=sa.astype(np.int32),
+                    en1=sb.astype(np.int32), rad=np.zeros(ns), beam_of_elem=np.arange(ns), chain=np.ones(ns), n_points=npnt,
+                    point_index=np.arange(npnt), cell_of_elem=None, meta={})
+
+
+def local_strut_mesh(mesh: BeamMesh, ptr, part: SlabPartition):
+    """Sub-mesh a rank needs for the joint-only system: its local struts (``part.local_elems`` of the joint mesh) with
+    all their elements.  Local node numbering: [owned joints | ghost joints | strut-interior nodes, strut-major].
+    Returns dict(xyz, len0, len1, rad, chain_ptr, sa, sb, max_len, interior_global)."""
+    struts = part.local_elems
+    joints = part.local_nodes
+    g2l = np.full(mesh.n_nodes, -1, dtype=np.int64)
+    g2l[joints] = np.arange(joints.shape[0])
+    cnt = (ptr[struts + 1] - ptr[struts]).astype(np.int64)
+    cptr = np.r_[0, np.cumsum(cnt)]
+    # global element ids of the local struts, strut-major
+    elems = (np.repeat(ptr[struts] - cptr[:-1], cnt) + np.arange(cptr[-1])).astype(np.int64)
+    e0, e1 = mesh.en0[elems].astype(np.int64), mesh.en1[elems].astype(np.int64)
+    interior = e1[e1 >= mesh.n_points]                    # every interior node is the second node of exactly one element
+    g2l[interior] = joints.shape[0] + np.arange(interior.shape[0])
+    nodes = np.concatenate([joints, interior])
+    return dict(xyz=np.stack([mesh.x[nodes], mesh.y[nodes], mesh.z[nodes]], axis=1), len0=g2l[e0].astype(np.int32),
+                len1=g2l[e1].astype(np.int32), rad=mesh.rad[elems].copy(), chain_ptr=cptr.astype(np.int32),
+                max_len=int(cnt.max(initial=1)), interior_global=interior, elems_global=elems)
+
+
+class DistributedJointFEM(DistributedFEM):
+    """:class:`DistributedFEM` on the exact joint-only system (every strut condensed onto its two lattice points,
+    ``lat_assemble_bsr_struts``): the slab partition, halo lists, peer-memory exchange and PCG are those of the base
+    class applied to the JOINT mesh; each rank condenses the struts that touch one of its joints.  Loads and
+    constraints live on lattice points (what the reference applies, full_scale_lattice_simulation.py:77-153).
+    ``solve`` returns the joint displacements / reactions in the local joint numbering [owned | ghosts];
+    :meth:`recover_full_field` back-substitutes the interior nodes of the rank's struts."""
+
+    def __init__(self, ctx, mesh: BeamMesh, young, nu, rank, world, kappa=0.9, bounds=None):
+        ptr, sa, sb = strut_topology(mesh)
+        jm = joint_mesh(mesh, sa, sb)
+        part = partition_slab(jm, rank, world, bounds)
+        self.full = local_strut_mesh(mesh, ptr, part)
+        self.n_dof_full_global = mesh.n_dof
+        super().__init__(ctx, None, young, nu, rank, world, kappa, part=part, lmesh=local_mesh(jm, part))
+        self.dofs = local_dofs(part)                       # joint DOFs = the first 6 n_points DOFs of the full mesh
+        self.n_dof_global, self.n_elem_global = 6 * mesh.n_points, mesh.n_elems
+        t = lambda a, d: self.torch.from_numpy(np.ascontiguousarray(a, dtype=d)).to(ctx.device)
+        f = self.full
+        ne = f["len0"].shape[0]
+        self.f_xyz, self.f_len0, self.f_len1, self.f_rad = t(f["xyz"], np.float64), t(f["len0"], np.int32), t(f["len1"], np.int32), t(f["rad"], np.float64)
+        self.f_ptr, self.f_elem, self.f_flip = t(f["chain_ptr"], np.int32), t(np.arange(ne), np.int32), t(np.zeros(ne), np.int32)
+
+    def assemble(self, out=None):
+        self.vals = self.ctx.assemble_bsr_struts(self.f_xyz, self.f_len0, self.f_len1, self.f_rad, self.f_ptr, self.f_elem,
+                                                 self.f_flip, self.n_local, self.nnzb, self.young, self.nu, self.kappa, out=out)
+        return self.vals
+
+    def solve_matrix_free(self, *a, **k):
+        raise NotImplementedError("the joint-only system is an assembled operator")
+
+    def compliance_gradient(self, *a, **k):
+        raise NotImplementedError("use recover_full_field + the element-form gradient of the full mesh")
+
+    def recover_full_field(self, u_joints_local):
+        """Displacements of ALL local nodes ([owned joints | ghost joints | interior nodes of the local struts]) from
+        the joint solution (ghost joints valid, as ``solve`` returns them): ``lat_strut_recover``."""
+        torch, ctx = self.torch, self.ctx
+        nloc = int(self.f_xyz.shape[0])
+        u_full = torch.zeros(6 * nloc, dtype=torch.float64, device=ctx.device)
+        u_full[: 6 * self.n_local] = u_joints_local
+        if nloc > self.n_local:
+            ctx.strut_recover(self.f_xyz, self.f_len0, self.f_len1, self.f_rad, self.f_ptr, self.f_elem, self.f_flip,
+                              self.en0, self.en1, self.full["max_len"], self.young, self.nu, self.kappa, u_joints_local, u_full)
+        return u_full

@@ -157,3 +157,32 @@ def test_per_slab_generation_equals_partition_of_the_global_mesh(geom, ncell, m_
         assert np.array_equal(fl, fixed[dofs]) and np.array_equal(gl, g[dofs]) and np.array_equal(fl2, f[dofs])
         n_owned_total += part.n_owned
     assert n_owned_total == mesh.n_nodes
+
+
+def test_joint_only_partition_covers_every_strut_and_keeps_the_geometry():
+    """Host logic of DistributedJointFEM: the joint mesh is partitioned like any mesh; every strut is local to the
+    owner(s) of its two joints with ALL its elements, in a numbering [joints | strut-interior nodes]."""
+    from pylatticedso_b200 import distributed as D, mesh as M
+    lat = M.synthetic_lattice("Octet", (5, 2, 2), [0.04])
+    mesh = M.mesh_from_synthetic(lat, 3)
+    ptr, sa, sb = D.strut_topology(mesh)
+    assert ptr[-1] == mesh.n_elems and (np.diff(ptr) == 3).all()
+    jm = D.joint_mesh(mesh, sa, sb)
+    world = 3
+    owned_total, seen = 0, np.zeros(mesh.n_elems, dtype=int)
+    for r in range(world):
+        part = D.partition_slab(jm, r, world)
+        f = D.local_strut_mesh(mesh, ptr, part)
+        owned_total += part.n_owned
+        seen[f["elems_global"]] += 1
+        nj = part.n_local
+        assert f["xyz"].shape[0] == nj + f["interior_global"].shape[0]
+        assert (f["len1"][f["chain_ptr"][1:] - 1] < nj).all() and (f["len0"][f["chain_ptr"][:-1]] < nj).all()   # strut ends are joints
+        glob = mesh.xyz[mesh.en1[f["elems_global"]]] - mesh.xyz[mesh.en0[f["elems_global"]]]
+        np.testing.assert_array_equal(f["xyz"][f["len1"]] - f["xyz"][f["len0"]], glob)
+        np.testing.assert_array_equal(f["rad"], mesh.rad[f["elems_global"]])
+        lm = D.local_mesh(jm, part)                                  # strut ends in local joint numbering, same order
+        np.testing.assert_array_equal(lm.en0, f["len0"][f["chain_ptr"][:-1]])
+        np.testing.assert_array_equal(lm.en1, f["len1"][f["chain_ptr"][1:] - 1])
+    assert owned_total == mesh.n_points
+    assert seen.min() == 1 and seen.max() == 2                       # struts across a cut are condensed on both sides

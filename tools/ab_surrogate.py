@@ -42,7 +42,7 @@ def case(ctx, name, rb, M, d_grad=False):
     t_ex = timed(lambda: s.expand_device(al, out=out))
     by = M * s.length * 8
     fl = 2.0 * M * s.length * (4 * ((s.k + 3) // 4))
-    print(f"{name}: M={M} n={s.n} k={s.k} d={s.d} centres={s.list_elements.shape[0]}")
+    print(f"{name} [LAT_EXPAND_MT={os.environ.get('LAT_EXPAND_MT', 'default')}]: M={M} n={s.n} k={s.k} d={s.d} centres={s.list_elements.shape[0]}")
     print(f"   RBF alphas (k_tps_eval)        : {t_al:8.3f} ms")
     print(f"   basis @ alphas (k_basis_expand): {t_ex:8.3f} ms   S written at {by / t_ex / 1e6:7.0f} GB/s = {by / t_ex / 1e6 / PEAK:.2f} of HBM;"
           f"  DMMA {fl / t_ex / 1e9:6.2f} TFLOP/s;  {M / t_ex / 1e3:7.2f} M cells/s")

@@ -30,9 +30,8 @@ def main():
         f = f.copy(); f[6 * 7 + 0] = 0.01
         dfem = D.DistributedFEM(ctx, mesh, E, NU, rank, world)
         dfem.set_bc(fixed, g, f)
-        if rank == 0:
-            K = orc.assemble_csr(mesh.xyz, np.stack([mesh.en0, mesh.en1], 1), mesh.rad, E, NU)
-            uo, Ro = orc.solve_static(K, fixed.astype(bool), g, f)
+        K = orc.assemble_csr(mesh.xyz, np.stack([mesh.en0, mesh.en1], 1), mesh.rad, E, NU)     # every rank: the joint-only
+        uo, Ro = orc.solve_static(K, fixed.astype(bool), g, f)                                  # check compares locally
         # p2p-fused: the persistent on-chip kernel (halo + all-reduce inside its grid barriers) where the slabs fit the
         # shared memory, i.e. here; p2p-fused-3k: the same exchange in the three-kernel iteration
         for mode in ("nccl", "p2p", "p2p-fused", "p2p-fused-3k"):
@@ -68,6 +67,29 @@ def main():
             print(f"[dist_check] gradient {geom}{n} world={world} n_groups={ncell} |g-go|/|go|={eg:.2e}", flush=True)
             ok = ok and eg < 1e-6
         ctx.p2p_destroy()
+        # joint-only (strut-condensed) system, sharded: joints == the oracle's FULL solve at the lattice points, and the
+        # back-substituted interior nodes of every rank's struts == the oracle's full field
+        if m_ > 1:
+            jf = D.DistributedJointFEM(ctx, mesh, E, NU, rank, world)
+            nj = 6 * mesh.n_points
+            jf.set_bc(fixed[:nj], g[:nj], f[:nj])
+            jf.enable_p2p()
+            for persistent in (True, False):
+                uj, Rj, info = jf.solve(tol=1e-13, maxiter=100000, precond=L.PC_BLOCK6, persistent=persistent)
+                ujg, Rjg = jf.gather_owned(uj), jf.gather_owned(Rj)
+                uf = jf.recover_full_field(uj).cpu().numpy().reshape(-1, 6)
+                nodes = np.concatenate([jf.part.local_nodes, jf.full["interior_global"]])
+                e_int = np.abs(uf - uo.reshape(-1, 6)[nodes]).max() / np.abs(uo).max()
+                e_all = torch.tensor([e_int], dtype=torch.float64, device=ctx.device)
+                dist.all_reduce(e_all, op=dist.ReduceOp.MAX)
+                if rank == 0:
+                    eu = np.abs(ujg - uo[:nj]).max() / np.abs(uo).max()
+                    er = np.abs(Rjg - Ro[:nj]).max() / np.abs(Ro).max()
+                    print(f"[dist_check] joint-only {geom}{n} m={m_} world={world} n_dof={nj} (full {mesh.n_dof}) iters={info['iters']} "
+                          f"info={info['info']} persistent={info.get('persistent', False)} solve_ms={info['solve_ms']:.2f} "
+                          f"|u-uo|/|uo|={eu:.2e} |R-Ro|/|Ro|={er:.2e} full field (max over ranks) {float(e_all):.2e}", flush=True)
+                    ok = ok and info["info"] in (0, 5) and eu < 1e-8 and er < 1e-8 and float(e_all) < 1e-8
+            ctx.p2p_destroy()
     ctx.comm_destroy()
     dist.barrier()
     dist.destroy_process_group()
