@@ -130,6 +130,14 @@ def _subdivide(pxyz, b_p1, b_p2, b_rad, b_idx, b_chain, nseg, n_points, point_in
     appended beam-major after the ``n_points`` lattice points."""
     nb = b_p1.shape[0]
     nseg = np.asarray(nseg, dtype=np.int64)
+    if nb and int(nseg.max()) == 1:                      # one element per strut: the beams ARE the elements
+        cp = lambda v, d: np.array(v, dtype=d, copy=True)
+        return BeamMesh(
+            x=np.ascontiguousarray(pxyz[:, 0]), y=np.ascontiguousarray(pxyz[:, 1]), z=np.ascontiguousarray(pxyz[:, 2]),
+            en0=b_p1.astype(np.int32), en1=b_p2.astype(np.int32), rad=cp(b_rad, np.float64), beam_of_elem=cp(b_idx, np.int64),
+            chain=cp(b_chain, np.float64), n_points=int(n_points), point_index=np.asarray(point_index, dtype=np.int64),
+            cell_of_elem=None if b_cell is None else cp(b_cell, np.int64),
+            type_of_elem=None if b_type is None else cp(b_type, np.int64), meta=meta or {})
     a = pxyz[b_p1]
     c = pxyz[b_p2]
     n_int = nseg - 1
@@ -246,8 +254,68 @@ class SyntheticLattice:
         return (i * self.n_cells[1] + j) * self.n_cells[2] + k
 
 
+def _grid_lattice(tables, ci, cj, ck, gcell, org, size, cr, dims, i_lo, i_hi):
+    """Sort-free numbering for tables whose fractional coordinates are multiples of 1/2 (BCC, Octet, ...).
+
+    On the half-cell grid every strut end has integer coordinates, so the reference's numbering rules become dense
+    scatters + prefix sums: node.index = rank of the grid key (= rank in the (x,y,z) sort, cell.py:317-321); a strut is
+    (lower end, offset to the upper end) and the lexicographic order of the offsets IS the order of the upper ends, so
+    the occupied slots of a dense [node][offset] array are the struts in beam.index order (lattice.py:675-683); "first
+    creation wins" (cell.py:366-378) = the lowest creating instance, found with a reversed scatter.  Bit-identical to
+    the generic sort/unique path (tests/test_mesh.py) at a fraction of its time: 72 M strut ends for Octet 100^3."""
+    nx, ny, nz = dims
+    T = np.concatenate(tables, axis=0)
+    geom_of_row = np.concatenate([np.full(t.shape[0], g, dtype=np.int64) for g, t in enumerate(tables)])
+    T2 = np.rint(T * 2.0).astype(np.int64)                       # (nbt, 6) half-cell units
+    nbt = T2.shape[0]
+    ncl = ci.shape[0]
+    Gy, Gz = 2 * ny + 1, 2 * nz + 1
+    n_slots = (2 * (i_hi - i_lo) + 1) * Gy * Gz
+    cbase = ((2 * (ci - i_lo)) * Gy + 2 * cj) * Gz + 2 * ck       # key of the cell origin
+    off1 = (T2[:, 0] * Gy + T2[:, 1]) * Gz + T2[:, 2]
+    off2 = (T2[:, 3] * Gy + T2[:, 4]) * Gz + T2[:, 5]
+    key1 = (cbase[:, None] + off1[None, :]).ravel()
+    key2 = (cbase[:, None] + off2[None, :]).ravel()
+    n_inst = key1.shape[0]
+    # first creation of every grid point: ends 1 of all instances are created before ends 2 (allp = [e1; e2])
+    first = np.full(n_slots, -1, dtype=np.int64)
+    first[key2[::-1]] = np.arange(2 * n_inst - 1, n_inst - 1, -1)
+    first[key1[::-1]] = np.arange(n_inst - 1, -1, -1)           # repeated index: the last assignment wins = lowest instance
+    occ = first >= 0
+    node_of_slot = np.cumsum(occ, dtype=np.int64) - 1
+    slots = np.flatnonzero(occ)
+    npnt = slots.shape[0]
+    fidx = first[slots]
+    del first, occ
+    end2 = fidx >= n_inst
+    inst = np.where(end2, fidx - n_inst, fidx)
+    cell_l, row = inst // nbt, inst % nbt
+    frac = np.where(end2[:, None], T[row, 3:6], T[row, 0:3])
+    pxyz = frac * size[None, :] + org[cell_l]                   # the same expression as the generic path
+    n1 = node_of_slot[key1]
+    n2 = node_of_slot[key2]
+    del node_of_slot
+    # struts: canonical offset (upper end - lower end) per table row; node order == key order
+    swap = off2 < off1
+    d = np.where(swap[:, None], T2[:, 0:3] - T2[:, 3:6], T2[:, 3:6] - T2[:, 0:3])
+    dkey = (d[:, 0] * (4 * Gy) + d[:, 1]) * (4 * Gz) + d[:, 2]  # lexicographic in (dx, dy, dz); |d| <= 2
+    codes_u, code = np.unique(dkey, return_inverse=True)
+    nd = codes_u.shape[0]
+    code = code.ravel().astype(np.int64)
+    lo = np.where(np.tile(swap, ncl), n2, n1)
+    bkey = lo * nd + np.tile(code, ncl)
+    del lo
+    bfirst = np.full(npnt * nd, -1, dtype=np.int64)
+    bfirst[bkey[::-1]] = np.arange(n_inst - 1, -1, -1)
+    del bkey
+    binst = bfirst[np.flatnonzero(bfirst >= 0)]                 # already in (lower end, upper end) order
+    del bfirst
+    bcell_l, brow = binst // nbt, binst % nbt
+    return (pxyz, n1[binst], n2[binst], cr[bcell_l, geom_of_row[brow]], gcell[bcell_l], geom_of_row[brow])
+
+
 def synthetic_lattice(geom_types, n_cells, radii, cell_size=(1.0, 1.0, 1.0),
-                      grad_radius=None, cell_radii=None, i_range=None) -> SyntheticLattice:
+                      grad_radius=None, cell_radii=None, i_range=None, _force_generic=False) -> SyntheticLattice:
     """Regular lattice arrays in the reference numbering.
 
     ``i_range = (i_lo, i_hi)`` generates only the cell layers ``i_lo <= i < i_hi`` of the
@@ -296,8 +364,15 @@ def synthetic_lattice(geom_types, n_cells, radii, cell_size=(1.0, 1.0, 1.0),
             elif rule != "constant":
                 raise NotImplementedError(f"gradient rule {rule!r}")
         cr = np.stack([np.float64(r) * fac for r in radii], axis=1)
-    ends1, ends2, brad, bcell, btype = [], [], [], [], []
     size = np.array(cs)
+    if not _force_generic and all(np.abs(t * 2.0 - np.rint(t * 2.0)).max() < 1e-12 and t.min() >= 0.0 and t.max() <= 1.0
+                                  for t in tables):
+        pxyz, p1, p2, brad, bcell, btype = _grid_lattice(tables, ci, cj, ck, gcell, org, size, cr, (nx, ny, nz), i_lo, i_hi)
+        return SyntheticLattice(pxyz=pxyz, b_p1=p1.astype(np.int64), b_p2=p2.astype(np.int64), b_rad=brad,
+                                b_cell=bcell.astype(np.int64), b_type=btype.astype(np.int64), n_cells=(nx, ny, nz),
+                                cell_size=cs, cell_radii=cr,
+                                geom_types=tuple(g if isinstance(g, str) else "custom" for g in geom_types))
+    ends1, ends2, brad, bcell, btype = [], [], [], [], []
     for g, tab in enumerate(tables):
         nbt = tab.shape[0]
         # x = frac * size + origin (cell.py:340-346)

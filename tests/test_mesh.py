@@ -120,3 +120,26 @@ def test_strut_chains_none_for_single_element_struts():
     perm, xyz, l0, l1 = local_cell_mesh(mesh, bnd)
     assert strut_chains(xyz, l0, l1, len(bnd)) is None
 
+
+
+@pytest.mark.parametrize("geom,n,radii,kw", [
+    ("BCC", (3, 2, 2), [0.05], {}),
+    ("Octet", (3, 4, 2), [0.03], {}),
+    (["BCC", "Octet"], (2, 3, 3), [0.05, 0.02], {}),
+    ("Octet", (6, 3, 2), [0.03], dict(i_range=(2, 5))),
+    ("BCC", (5, 3, 4), [0.04], dict(grad_radius=("linear", [1, 0, 1], [0.1, 0, 0.2]))),
+    ("BCC", (4, 2, 3), [0.04], dict(cell_size=(0.1, 0.3, 0.7))),
+    ("Octet", (3, 3, 3), [0.04], dict(cell_radii=np.random.default_rng(0).uniform(0.01, 0.05, (27, 1)))),
+])
+def test_sort_free_grid_generator_is_bit_identical_to_the_generic_numbering(geom, n, radii, kw):
+    """mesh._grid_lattice (dense scatters + prefix sums on the half-cell grid) against the sort/unique restatement of
+    the reference's numbering rules, which the numbering_*.npz fixtures pin to the reference objects."""
+    from pylatticedso_b200 import mesh as M
+    a = M.synthetic_lattice(geom, n, radii, **kw)
+    b = M.synthetic_lattice(geom, n, radii, _force_generic=True, **kw)
+    for f in ("pxyz", "b_p1", "b_p2", "b_rad", "b_cell", "b_type", "cell_radii"):
+        x, y = getattr(a, f), getattr(b, f)
+        assert x.shape == y.shape and np.array_equal(x, y), f
+    ma, mb = M.mesh_from_synthetic(a, 1), M.mesh_from_synthetic(b, 2)
+    assert ma.n_elems == a.b_p1.shape[0] and mb.n_elems == 2 * ma.n_elems
+    np.testing.assert_array_equal(ma.en0, a.b_p1)
