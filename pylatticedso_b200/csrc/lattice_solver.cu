@@ -1268,6 +1268,24 @@ static int pcg_run_persist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* c
   }
   a.trace = nullptr;
   a.trace_iters = 0;
+  // L2 residency of part of the matrix: the blocks of l2_keep / 16 of the rows are loaded with an evict_last policy and
+  // stay in the 126 MB L2 from one iteration to the next, the rest is streamed evict_first.  Target ~44 MB resident
+  // (config 1, 98 MB matrix: 7 / 16 -> product phase 15.4 -> 11.5 us, iteration 30.2 -> 24.6 us; 12 / 16 and more thrash,
+  // profiles/r02_persist_l2keep_ab.txt).  LAT_PERSIST_L2KEEP overrides (0 = plain loads).
+  {
+    int64_t nnzb_h = 0;
+    {
+      int32_t last = 0;
+      LAT_CUDA(ctx, cudaMemcpyAsync(&last, rowptr + n_nodes, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      nnzb_h = last;
+    }
+    const double mat_mb = (double)nnzb_h * 288.0 / 1e6;
+    int keep = mat_mb > 0.0 ? (int)(16.0 * 44.0 / mat_mb + 0.5) : 8;
+    keep = keep < 0 ? 0 : (keep > 8 ? 8 : keep);
+    const char* env_keep = getenv("LAT_PERSIST_L2KEEP");
+    a.l2_keep = env_keep ? atoi(env_keep) : keep;
+  }
   const char* env_tr = getenv("LAT_PERSIST_TRACE");     // LAT_PERSIST_TRACE=n: phase breakdown of the first n iterations on stderr
   if (env_tr && atoi(env_tr) > 0) {
     a.trace_iters = atoi(env_tr) > 256 ? 256 : atoi(env_tr);

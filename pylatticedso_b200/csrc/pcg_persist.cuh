@@ -76,6 +76,8 @@ struct PersistArgs {
                               //    product phase loses its L1 and slowed from 15.5 to 26 us at config 1)
   long long* trace;           // optional [G][trace_iters][9] SM clock stamps of CTA thread 0 (+ [G][2] rows, blocks)
   int trace_iters;
+  int l2_keep;                // 0: plain loads; k = 1..16: the matrix blocks of k / 16 of the rows are loaded with an L2
+                              // evict_last policy (they stay L2-resident from one iteration to the next), the rest evict_first
   // ---- multi-GPU (DIST = true): slab partition over NVLink peer memory, see "Multi-GPU" below.  u is the ghosted
   // vector inside this rank's arena ([owned | ghosts]); n_nodes counts the OWNED rows.
   int nranks, my_rank, n_nb;
@@ -292,19 +294,60 @@ __device__ __forceinline__ void persist_reduce(double (&v)[3], unsigned long lon
   }
 }
 
+// Matrix loads with an explicit L2 eviction policy (createpolicy + ld.global.L2::cache_hint), past L1.
+__device__ __forceinline__ double2 ld_policy(const double2* p, unsigned long long pol) {
+  double2 v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ Piece3 piece_load_policy(const double* __restrict__ vals, int64_t j, int r, const double* xcol, int c,
+                                                    unsigned long long pol) {
+  Piece3 q;
+  const double2* vp = reinterpret_cast<const double2*>(vals + j * 36 + 2 * r);
+  q.a0 = ld_policy(vp, pol); q.a1 = ld_policy(vp + 6, pol); q.a2 = ld_policy(vp + 12, pol);
+  q.x = *reinterpret_cast<const double2*>(xcol + 2 * c);
+  return q;
+}
+__device__ __forceinline__ void piece_row_policy(const int32_t* colidx, const double* __restrict__ vals, int lo, int hi, int r,
+                                                 const double* x, double& s0, double& s1, double& s2, unsigned long long pol) {
+  const int c = r % 3;
+  for (int j = lo; j < hi; j += 3) {
+    const bool p1 = j + 1 < hi, p2 = j + 2 < hi;
+    const int j1 = p1 ? j + 1 : j, j2 = p2 ? j + 2 : j;
+    const int c0 = colidx[j], c1 = colidx[j1], c2 = colidx[j2];
+    const Piece3 q0 = piece_load_policy(vals, j, r, x + (int64_t)c0 * 6, c, pol);
+    const Piece3 q1 = piece_load_policy(vals, j1, r, x + (int64_t)c1 * 6, c, pol);
+    const Piece3 q2 = piece_load_policy(vals, j2, r, x + (int64_t)c2 * 6, c, pol);
+    piece_fma(q0, s0, s1, s2);
+    if (p1) piece_fma(q1, s0, s1, s2);
+    if (p2) piece_fma(q2, s0, s1, s2);
+  }
+}
+
 // s_w = (A v) on the CTA's rows: six lanes per block row in the transposed-piece layout, three blocks (12 x 16 B loads
 // per lane) in flight; lane (g, r) leaves the total of scalar row lane_dof(r) in s_w.  All warps call.
 __device__ __forceinline__ void persist_product(const double* __restrict__ vals, const double* v, const int32_t* s_rp,
-                                                const int32_t* s_gb, const int32_t* s_col, double* s_w, int nrows) {
+                                                const int32_t* s_gb, const int32_t* s_col, double* s_w, int nrows, int l2_keep = 0) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int g = lane / 6, rr_ = lane - g * 6;
+  unsigned long long pol_keep = 0, pol_stream = 0;
+  if (l2_keep > 0) {
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  }
   for (int base = wid * 5; base < nrows; base += PERSIST_NW * 5) {
     const int lr = base + g;
     const bool active = g < 5 && lr < nrows;
     const int lp = active ? s_rp[lr] : 0, nb = active ? s_rp[lr + 1] - lp : 0;
     const int gb = active ? s_gb[lr] : 0;             // global index of the row's first block
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    piece_row<false, false>(s_col + (lp - gb), vals, gb, gb + nb, rr_, v, s0, s1, s2);
+    if (l2_keep > 0) {
+      // the same rows are kept in every iteration: 16-row chunks, lr / 16 cycles through 16 classes
+      const unsigned long long pol = ((lr >> 4) & 15) < l2_keep ? pol_keep : pol_stream;
+      piece_row_policy(s_col + (lp - gb), vals, gb, gb + nb, rr_, v, s0, s1, s2, pol);
+    } else {
+      piece_row<false, false>(s_col + (lp - gb), vals, gb, gb + nb, rr_, v, s0, s1, s2);
+    }
     const double tot = piece_finish(g, rr_, s0, s1, s2);
     if (active) s_w[lr * 6 + lane_dof(rr_)] = tot;
   }
@@ -494,7 +537,7 @@ __global__ void __launch_bounds__(PERSIST_BLOCK, 1) k_pcg_persist(PersistArgs a)
     const bool tracing = a.trace != nullptr && trace_it < a.trace_iters;
     long long* tr = tracing ? a.trace + ((size_t)blockIdx.x * a.trace_iters + trace_it) * 9 : nullptr;
     if (tracing && threadIdx.x == 0) tr[0] = clock64();
-    persist_product(vals, u, s_rp, s_gb, s_col, s_w, nrows);
+    persist_product(vals, u, s_rp, s_gb, s_col, s_w, nrows, a.l2_keep);
     // every lane reads back exactly the entries it wrote (same (row, dof) mapping): no barrier needed
     for (int base = wid * 5; base < nrows; base += PERSIST_NW * 5) {
       const int lr = base + g;
