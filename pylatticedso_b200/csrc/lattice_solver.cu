@@ -1210,6 +1210,10 @@ static int pcg_run_persist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* c
     pc_smem = smem_base + smem_pc + 2560 <= (size_t)smem_optin && smem_base + smem_pc <= pc_limit;
     smem = smem_base + (pc_smem ? smem_pc : 0);
     if (smem + 2560 > (size_t)smem_optin) fits = false;     // does not fit on chip: three-kernel path
+    // ... and above ~176 KB of shared memory the product phase has too little L1 left for its gathers of u: BCC 24^3
+    // (0.84 M DOF, 187 KB) runs at 61.3 us per iteration here against 53.2 us in the three-kernel iteration
+    // (tools/ab_persist.py); LAT_PERSIST_FORCE=1 keeps the on-chip kernel up to the hardware limit
+    if (smem > (size_t)176 * 1024 && !getenv("LAT_PERSIST_FORCE")) fits = false;
   }
   const void* kfn = dist ? (const void*)k_pcg_persist<PC, true> : (const void*)k_pcg_persist<PC, false>;
   if (fits) {
@@ -1247,7 +1251,14 @@ static int pcg_run_persist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* c
   LAT_CUDA(ctx, cudaMemsetAsync(flags, 0, (size_t)G * PERSIST_INBOX_STRIDE * sizeof(unsigned int), ctx->stream));
   if (PC != LAT_PC_NONE)
     LAT_LAUNCH(ctx, k_precond_setup, (unsigned)ceil_div(n_nodes, 128), 128, 0, rowptr, colidx, vals, n_nodes, PC, dinv);
+  float* dinv_full = nullptr;
+  if (PC == LAT_PC_BLOCK6 && !pc_smem) {
+    dinv_full = lat_buf<float>(ctx, "pcg_dinv_full", (size_t)36 * n_nodes);
+    if (!dinv_full) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+    LAT_LAUNCH(ctx, k_persist_expand_dinv, (unsigned)ceil_div(36 * n_nodes, 256), 256, 0, dinv, n_nodes, dinv_full);
+  }
   PersistArgs a;
+  a.dinv_full = dinv_full;
   a.rowptr = rowptr; a.colidx = colidx; a.vals = vals; a.n_nodes = n_nodes; a.b = b; a.x = x; a.u = u; a.dinv = dinv;
   a.sc = sc;
   a.prm.tol = o->tol; a.prm.mintol = 0.0; a.prm.alpha_max = 0.0; a.prm.restart_every = 0; a.prm.maxiter = o->maxiter;

@@ -66,6 +66,9 @@ struct PersistArgs {
   double* x;               // out: solution (written at the end and before a residual check)
   double* u;               // global: preconditioned residual, gathered by every CTA
   const double* dinv;      // preconditioner in the layout of k_precond_setup (copied to shared memory at start)
+  const float* dinv_full;  // block-Jacobi rows NOT cached in shared memory: the inverse blocks as full 6x6 in FP32 (144 B:
+                           // a lane fetches its row with three 8-byte loads, k_persist_expand_dinv); else nullptr.  A
+                           // preconditioner needs no more than single precision; the rounded blocks stay symmetric.
   PcgScalars* sc;          // status block read by the host
   PcgParams prm;
   unsigned long long* mail;   // [G][8] LL words (6 used), zeroed before the launch
@@ -103,6 +106,16 @@ __host__ __device__ __forceinline__ int persist_rows_of(int64_t n_nodes, int cta
   const int64_t last_rows = (last == n_chunks - 1) ? n_nodes - last * PERSIST_CHUNK : PERSIST_CHUNK;
   return (int)((mine - 1) * PERSIST_CHUNK + last_rows);
 }
+// Packed symmetric inverse blocks (21 FP64 entries) -> full row-major 6x6 blocks in FP32.
+__global__ void k_persist_expand_dinv(const double* __restrict__ packed, int64_t n_nodes, float* __restrict__ full) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_nodes * 36) return;
+  const int64_t n = t / 36;
+  const int e = (int)(t - n * 36), r = e / 6, c = e - r * 6;
+  const int i = r < c ? r : c, j = r < c ? c : r;
+  full[t] = (float)packed[n * 21 + (i * (11 - i)) / 2 + j];
+}
+
 // Shared-memory need of the launch: the largest number of rows / blocks any CTA holds.
 __global__ void k_persist_caps(const int32_t* __restrict__ rowptr, int64_t n_nodes, int G, int32_t* __restrict__ maxima) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -402,13 +415,18 @@ __device__ __forceinline__ UpdLoads persist_upd_load(const PersistArgs& a, bool 
 #pragma unroll
   for (int k = 0; k < 6; ++k) { L.mA[k] = 0.0; L.mB[k] = 0.0; }
   if (!pcs && PC == LAT_PC_BLOCK6) {
-    const double* pa = a.dinv + (iA / 6) * 21;
-    const double* pb = a.dinv + (iB / 6) * 21;
+    // row `dof` of the full 6x6 inverse block: 24 contiguous bytes, three 8-byte loads.  (The packed 21-entry FP64
+    // layout needs six scattered 8-byte loads per lane: 12 instructions x ~10 L1 wavefronts per warp and trip made the
+    // block-Jacobi update 3.9 us slower than the Jacobi one; full FP64 blocks cost the product phase the L2 space they
+    // take, profiles/r02_persist_l2keep_ab.txt.)
+    const float2* pa = reinterpret_cast<const float2*>(a.dinv_full + (iA / 6) * 36 + dof * 6);
+    const float2* pb = reinterpret_cast<const float2*>(a.dinv_full + (iB / 6) * 36 + dof * 6);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      const int i = dof < k ? dof : k, j = dof < k ? k : dof;
-      L.mA[k] = actA ? __ldg(pa + (i * (11 - i)) / 2 + j) : 0.0;
-      L.mB[k] = actB ? __ldg(pb + (i * (11 - i)) / 2 + j) : 0.0;
+    for (int k = 0; k < 3; ++k) {
+      const float2 va = actA ? __ldg(pa + k) : make_float2(0.f, 0.f);
+      const float2 vb = actB ? __ldg(pb + k) : make_float2(0.f, 0.f);
+      L.mA[2 * k] = (double)va.x; L.mA[2 * k + 1] = (double)va.y;
+      L.mB[2 * k] = (double)vb.x; L.mB[2 * k + 1] = (double)vb.y;
     }
   }
   if (!pcs && PC == LAT_PC_JACOBI) { L.mA[0] = actA ? __ldg(a.dinv + iA) : 0.0; L.mB[0] = actB ? __ldg(a.dinv + iB) : 0.0; }
