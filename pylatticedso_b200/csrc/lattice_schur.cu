@@ -794,18 +794,18 @@ __device__ __forceinline__ void sup_block(const SupCoef& s, int re, int ce, doub
   for (int k = 0; k < 36; ++k) dst[k] = q[k];
 }
 
-// 12 (or, for the odd tail, 6) consecutive doubles of a row of S; rows start at multiples of 48 n_s bytes, so the
-// 96-byte pieces are 32-byte aligned whenever the row length is a multiple of 4 doubles (n_s even)
-__device__ __forceinline__ void star_store(double* dst, const double (&v)[12], bool both) {
-  if (both && (reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
-#pragma unroll
-    for (int q = 0; q < 3; ++q)
-      asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "d"(v[4 * q]), "d"(v[4 * q + 1]), "d"(v[4 * q + 2]),
-                   "d"(v[4 * q + 3]) : "memory");
+// Four (at the row tail: fewer) consecutive doubles of a row of S: one 256-bit store when the piece is 32-byte aligned
+// (always for an even number of struts: rows are multiples of 96 bytes then)
+__device__ __forceinline__ void star_store4(double* dst, const double (&v)[4], int ncol) {
+  if (ncol == 4 && (reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+  } else if (ncol == 4 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    reinterpret_cast<double2*>(dst)[0] = make_double2(v[0], v[1]);
+    reinterpret_cast<double2*>(dst)[1] = make_double2(v[2], v[3]);
   } else {
-    double2* o2 = reinterpret_cast<double2*>(dst);
 #pragma unroll
-    for (int q = 0; q < (both ? 6 : 3); ++q) o2[q] = make_double2(v[2 * q], v[2 * q + 1]);
+    for (int q = 0; q < 4; ++q)
+      if (q < ncol) dst[q] = v[q];
   }
 }
 
@@ -815,8 +815,8 @@ __global__ void __launch_bounds__(16 * STAR_CELLS_PER_CTA) k_schur_star(
     const int32_t* __restrict__ strut_of, const int32_t* __restrict__ group, int64_t n_cells, int ns, int n_grad,
     double* __restrict__ S, double* __restrict__ dS) {
   extern __shared__ __align__(16) double star_smem[];
-  // per cell slot: O, W, D (+ dO, dW, dD), then Kinv[36], T[36]
-  const int per_cell = (GRAD ? 6 : 3) * ns * 36 + 72;
+  // per cell slot: O, W, D (+ dO, dW, dD, dW of the current group), then Kinv[36], T[36]
+  const int per_cell = (GRAD ? 7 : 3) * ns * 36 + 72;
   const int slot = threadIdx.x >> 4, h = threadIdx.x & 15;
   double* base = star_smem + (size_t)slot * per_cell;
   double* sO = base;
@@ -825,9 +825,16 @@ __global__ void __launch_bounds__(16 * STAR_CELLS_PER_CTA) k_schur_star(
   double* sdO = GRAD ? sD + ns * 36 : nullptr;
   double* sdW = GRAD ? sdO + ns * 36 : nullptr;
   double* sdD = GRAD ? sdW + ns * 36 : nullptr;
-  double* sK = base + (GRAD ? 6 : 3) * ns * 36;   // Kcc^-1
+  double* sG = GRAD ? sdD + ns * 36 : nullptr;
+  double* sK = base + (GRAD ? 7 : 3) * ns * 36;   // Kcc^-1
   double* sT = sK + 36;                           // scratch 6x6
   const int nB = 6 * ns;
+  __shared__ int s_strut_of[STAR_MAX_STRUTS], s_group[STAR_MAX_STRUTS];
+  if (threadIdx.x < STAR_MAX_STRUTS) {
+    s_strut_of[threadIdx.x] = (int)threadIdx.x < ns ? strut_of[threadIdx.x] : 0;
+    s_group[threadIdx.x] = (GRAD && (int)threadIdx.x < ns) ? group[threadIdx.x] : 0;
+  }
+  __syncthreads();
   for (int64_t cell0 = (int64_t)blockIdx.x * STAR_CELLS_PER_CTA; cell0 < n_cells; cell0 += (int64_t)gridDim.x * STAR_CELLS_PER_CTA) {
     const int64_t cell = cell0 + slot;
     const bool live = cell < n_cells;
@@ -894,38 +901,53 @@ __global__ void __launch_bounds__(16 * STAR_CELLS_PER_CTA) k_schur_star(
       for (int k = 0; k < 36; ++k) sW[h * 36 + k] = w[k];
     }
     __syncwarp();
-    // 5. rows h, h+16, ... of S:  S[i][6 l' + b] = delta D_k[a][b] - sum_m W_k[a][m] O_l[b][m]
-    for (int i = h; i < nB; i += 16) {
-      if (!live) continue;
-      const int j = i / 6, a = i - 6 * j;
-      const int k = strut_of[j];
-      double wr[6];
+    // 5. S row by row, the whole half-warp on ONE row: lane h owns columns 4h .. 4h+3 (+64, ...), so a row leaves as
+    //    contiguous 32-byte pieces -- 384 contiguous bytes per row and instruction for n_s = 8.  (First version: every
+    //    lane owned whole rows; a store instruction then touched 32 different lines and the kernel ran at 98 % of the
+    //    L1 store-wavefront limit, 0.46 of HBM: profiles/r02_ncu_schur_star.txt.)
+    //    S[i][6 l' + b] = delta D_k[a][b] - sum_m W_k[a][m] O_l[b][m]
+    for (int c0 = 4 * h; c0 < nB; c0 += 64) {
+      int ofs[4], jcol[4], bq[4];
 #pragma unroll
-      for (int m = 0; m < 6; ++m) wr[m] = sW[k * 36 + a * 6 + m];
-      double* out = S + (cell * nB + i) * (int64_t)nB;
-      // two column joints (12 doubles = three full 32-byte sectors) per step: 256-bit stores; a scattered 128-bit store
-      // costs one L1 wavefront per lane for half a sector (same lesson as k_assemble_rows)
-      for (int jc = 0; jc < ns; jc += 2) {
-        double v[12];
+      for (int q = 0; q < 4; ++q) {
+        const int col = c0 + q < nB ? c0 + q : nB - 1;
+        jcol[q] = col / 6;
+        bq[q] = col - 6 * jcol[q];
+        ofs[q] = strut_of[jcol[q]] * 36 + bq[q] * 6;
+      }
+      const int ncol = nB - c0 < 4 ? nB - c0 : 4;
+      if (live) {
+        // the lane's four columns are the same for every row: their O_l[b][:] stay in registers (24 doubles), the
+        // row's W_k[a][:] is a broadcast read
+        double oc[4][6];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int jcc = jc + half < ns ? jc + half : jc;
-          const int l = strut_of[jcc];
+        for (int q = 0; q < 4; ++q)
 #pragma unroll
-          for (int b = 0; b < 6; ++b) {
-            double acc = (jcc == j) ? sD[k * 36 + a * 6 + b] : 0.0;
+          for (int m = 0; m < 6; ++m) oc[q][m] = sO[ofs[q] + m];
+        double* out = S + cell * (int64_t)nB * nB + c0;
+        for (int j = 0; j < ns; ++j) {
+          const int k = s_strut_of[j];
 #pragma unroll
-            for (int m = 0; m < 6; ++m) acc = fma(-wr[m], sO[l * 36 + b * 6 + m], acc);
-            v[half * 6 + b] = acc;
+          for (int a = 0; a < 6; ++a) {
+            const double* wrow = sW + k * 36 + a * 6;
+            double v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              double acc = (jcol[q] == j) ? sD[k * 36 + a * 6 + bq[q]] : 0.0;
+#pragma unroll
+              for (int m = 0; m < 6; ++m) acc = fma(-wrow[m], oc[q][m], acc);
+              v[q] = acc;
+            }
+            star_store4(out, v, ncol);
+            out += nB;
           }
         }
-        star_store(out + jc * 6, v, jc + 1 < ns);
       }
     }
     if (GRAD) {
       for (int gsel = 0; gsel < n_grad; ++gsel) {
         __syncwarp();
-        // dKcc = sum_{k in g} dC_k  (dC sits in dW's space until dW overwrites it below, so keep it in sT first)
+        // dKcc = sum_{k in g} dC_k  (dC sits in sdW)
         for (int e = h; e < 36; e += 16) {
           double acc = 0.0;
           for (int k = 0; k < ns; ++k)
@@ -945,46 +967,66 @@ __global__ void __launch_bounds__(16 * STAR_CELLS_PER_CTA) k_schur_star(
         __syncwarp();
         for (int q = 0, e = h; e < 36; e += 16, ++q) sT[e] = t_loc[q];
         __syncwarp();
-        // dW_k = [k in g] dO_k Kcc^-1 - W_k T: a row owner needs only the row of ITS strut, computed in registers
-        // (sdW keeps holding dC_k, which the next group needs again)
-        for (int i = h; i < nB; i += 16) {
-          if (!live) continue;
-          const int j = i / 6, a = i - 6 * j;
-          const int k = strut_of[j];
-          const bool kin = group[k] == gsel;
-          double wr[6], dwr[6];
+        // dW_k = [k in g] dO_k Kcc^-1 - W_k T  (lane k, into its own scratch block: sdW keeps holding dC_k, which the
+        // next group needs again)
+        if (h < ns) {
+          const bool kin = group[h] == gsel;
+          double w[36];
 #pragma unroll
-          for (int m = 0; m < 6; ++m) wr[m] = sW[k * 36 + a * 6 + m];
+          for (int i = 0; i < 6; ++i)
 #pragma unroll
-          for (int jj = 0; jj < 6; ++jj) {
-            double acc = 0.0;
+            for (int jj = 0; jj < 6; ++jj) {
+              double acc = 0.0;
 #pragma unroll
-            for (int m = 0; m < 6; ++m) {
-              if (kin) acc = fma(sdO[k * 36 + a * 6 + m], sK[m * 6 + jj], acc);
-              acc = fma(-wr[m], sT[m * 6 + jj], acc);
+              for (int m = 0; m < 6; ++m) {
+                if (kin) acc = fma(sdO[h * 36 + i * 6 + m], sK[m * 6 + jj], acc);
+                acc = fma(-sW[h * 36 + i * 6 + m], sT[m * 6 + jj], acc);
+              }
+              w[i * 6 + jj] = acc;
             }
-            dwr[jj] = acc;
+#pragma unroll
+          for (int e = 0; e < 36; ++e) sG[h * 36 + e] = w[e];
+        }
+        __syncwarp();
+        for (int c0 = 4 * h; c0 < nB; c0 += 64) {
+          int ofs[4], jcol[4], bq[4];
+          bool lin[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int col = c0 + q < nB ? c0 + q : nB - 1;
+            jcol[q] = col / 6;
+            bq[q] = col - 6 * jcol[q];
+            const int l = strut_of[jcol[q]];
+            ofs[q] = l * 36 + bq[q] * 6;
+            lin[q] = group[l] == gsel;
           }
-          double* out = dS + ((cell * n_grad + gsel) * nB + i) * (int64_t)nB;
-          for (int jc = 0; jc < ns; jc += 2) {
-            double v[12];
+          const int ncol = nB - c0 < 4 ? nB - c0 : 4;
+          if (live) {
+            double oc[4][6], doc[4][6];
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              const int jcc = jc + half < ns ? jc + half : jc;
-              const int l = strut_of[jcc];
-              const bool lin = group[l] == gsel;
+            for (int q = 0; q < 4; ++q)
 #pragma unroll
-              for (int b = 0; b < 6; ++b) {
-                double acc = (jcc == j && kin) ? sdD[k * 36 + a * 6 + b] : 0.0;
+              for (int m = 0; m < 6; ++m) { oc[q][m] = sO[ofs[q] + m]; doc[q][m] = lin[q] ? sdO[ofs[q] + m] : 0.0; }
+            double* out = dS + (cell * n_grad + gsel) * (int64_t)nB * nB + c0;
+            for (int j = 0; j < ns; ++j) {
+              const int k = s_strut_of[j];
+              const bool kin = s_group[k] == gsel;
 #pragma unroll
-                for (int m = 0; m < 6; ++m) {
-                  acc = fma(-dwr[m], sO[l * 36 + b * 6 + m], acc);
-                  if (lin) acc = fma(-wr[m], sdO[l * 36 + b * 6 + m], acc);
+              for (int a = 0; a < 6; ++a) {
+                const double* wrow = sW + k * 36 + a * 6;
+                const double* dwrow = sG + k * 36 + a * 6;
+                double v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  double acc = (jcol[q] == j && kin) ? sdD[k * 36 + a * 6 + bq[q]] : 0.0;
+#pragma unroll
+                  for (int m = 0; m < 6; ++m) { acc = fma(-dwrow[m], oc[q][m], acc); acc = fma(-wrow[m], doc[q][m], acc); }
+                  v[q] = acc;
                 }
-                v[half * 6 + b] = acc;
+                star_store4(out, v, ncol);
+                out += nB;
               }
             }
-            star_store(out + jc * 6, v, jc + 1 < ns);
           }
         }
       }
@@ -1056,7 +1098,7 @@ extern "C" int lat_schur_batch_struts(lat_ctx* ctx, const double* xyz, const int
   else
     LAT_LAUNCH(ctx, k_chain_condense, cgrid, 128, 0, xyz, len0, len1, rad, n_cells, n_loc_nodes, n_loc_elem, chain_ptr,
                chain_elem, chain_flip, ns, young, nu, kappa, sup);
-  const size_t smem = (size_t)STAR_CELLS_PER_CTA * ((dS ? 6 : 3) * ns * 36 + 72) * sizeof(double);
+  const size_t smem = (size_t)STAR_CELLS_PER_CTA * ((dS ? 7 : 3) * ns * 36 + 72) * sizeof(double);
   int64_t grid = ceil_div(n_cells, STAR_CELLS_PER_CTA);
   const int64_t cap = (int64_t)ctx->sm_count * 8;
   if (grid > cap) grid = cap;

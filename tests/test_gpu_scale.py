@@ -100,3 +100,72 @@ def test_config0_bcc5_parity_mode_against_oracle(ctx):
     assert np.abs(up - uo).max() < 1e-8 * np.abs(uo).max()
     fx = fixed.reshape(-1, 6)[: m.n_points].astype(bool)
     assert np.abs(Rp[fx] - Ro[fx]).max() < 1e-8 * np.abs(Ro[fx]).max()
+
+
+def test_octet40_gradient_and_product_against_the_oracle_on_samples(ctx):
+    """configs[2] at full size, oracle-checked on samples: the per-cell compliance gradient of 256 random cells and
+    512 random rows of K u against the numpy oracle evaluated on exactly the elements involved."""
+    import torch
+    from oracle import lattice_oracle as orc
+    from pylatticedso_b200 import mesh as M
+    lat = M.synthetic_lattice("Octet", (40, 40, 40), [0.03], grad_radius=("linear", [False, False, True], [0, 0, 0.0125]))
+    m = M.mesh_from_synthetic(lat, 1)
+    t = lambda a, d: torch.from_numpy(np.ascontiguousarray(a, dtype=d)).to(ctx.device)
+    x, y, z, en0, en1, rad = t(m.x, np.float64), t(m.y, np.float64), t(m.z, np.float64), t(m.en0, np.int32), t(m.en1, np.int32), t(m.rad, np.float64)
+    rng = np.random.default_rng(5)
+    u = rng.standard_normal(m.n_dof) * 1e-3
+    ng = 64000
+    g = ctx.compliance_grad(x, y, z, en0, en1, rad, t(m.cell_of_elem, np.int32), ng, t(u, np.float64), E_MOD, NU).cpu().numpy()
+    cells = rng.choice(ng, 256, replace=False)
+    sel = np.flatnonzero(np.isin(m.cell_of_elem, cells))
+    remap = -np.ones(ng, dtype=np.int64); remap[cells] = np.arange(cells.size)
+    en = np.stack([m.en0[sel], m.en1[sel]], 1).astype(np.int64)
+    go = orc.compliance_gradient(m.xyz, en, m.rad[sel], u, remap[m.cell_of_elem[sel]], cells.size, E_MOD, NU)
+    assert np.abs(g[cells] - go).max() < 1e-10 * np.abs(go).max()
+    # K u on sampled rows: the oracle assembles only the elements that touch the sampled nodes
+    rowptr, colidx = ctx.bsr_pattern(en0, en1, m.n_nodes)
+    vals = ctx.assemble_bsr(x, y, z, en0, en1, rad, m.n_nodes, colidx.numel(), E_MOD, NU)
+    Ku = ctx.spmv(rowptr, colidx, vals, t(u, np.float64)).cpu().numpy().reshape(-1, 6)
+    nodes = rng.choice(m.n_nodes, 512, replace=False)
+    touch = np.flatnonzero(np.isin(m.en0, nodes) | np.isin(m.en1, nodes))
+    en = np.stack([m.en0[touch], m.en1[touch]], 1).astype(np.int64)
+    Ke = orc.element_stiffness(m.xyz[en[:, 0]], m.xyz[en[:, 1]], m.rad[touch], E_MOD, NU)
+    dofs = (en[:, :, None] * 6 + np.arange(6)[None, None, :]).reshape(-1, 12)
+    fe = np.einsum("eab,eb->ea", Ke, u[dofs])
+    ref = np.zeros((m.n_nodes, 6))
+    np.add.at(ref, en[:, 0], fe[:, :6])
+    np.add.at(ref, en[:, 1], fe[:, 6:])
+    assert np.abs(Ku[nodes] - ref[nodes]).max() < 1e-11 * np.abs(ref[nodes]).max()
+
+
+def test_config3_bcc60_schur_batch_full_size_against_the_oracle_on_samples(ctx):
+    """configs[3] at full size and at the reference's mesh density: 216 000 BCC cells (18 elements per strut, 870 DOF
+    -> 48 boundary DOF each) with random radii through the star-cell kernel, values and dS/dr; 12 sampled cells
+    against the oracle's DENSE condensation and a central difference of it; symmetry of every matrix."""
+    import torch
+    from oracle import lattice_oracle as orc
+    from pylatticedso_b200 import mesh as M
+    from pylatticedso_b200.schur import bcc_cell_order_nodes, synthetic_cell_batch
+    rng = np.random.default_rng(11)
+    n_cells = 216000
+    radii = rng.uniform(0.02, 0.08, n_cells)
+    batch, bnd = synthetic_cell_batch(ctx, "BCC", radii, 18, E_MOD, NU, with_gradients=True)
+    S, dS = batch.schur(with_gradients=True)
+    assert tuple(S.shape) == (n_cells, 48, 48) and tuple(dS.shape)[:1] == (n_cells,)
+    assert float((S - S.transpose(1, 2)).abs().max()) < 1e-10 * float(S.abs().max())
+    lat = M.synthetic_lattice("BCC", (1, 1, 1), [1.0])
+    mesh = M.mesh_from_synthetic(lat, 18)
+    en = np.stack([mesh.en0, mesh.en1], 1).astype(np.int64)
+    bdofs = (np.asarray(bnd)[:, None] * 6 + np.arange(6)[None, :]).ravel()
+    pick = rng.choice(n_cells, 12, replace=False)
+
+    def dense(r):
+        return orc.schur_complement(orc.assemble_csr(mesh.xyz, en, np.full(mesh.n_elems, r), E_MOD, NU), bdofs)
+    for c in pick:
+        So = dense(radii[c])
+        assert np.abs(S[c].cpu().numpy() - So).max() < 1e-10 * np.abs(So).max()
+    c = pick[0]
+    h = 1e-6
+    fd = (dense(radii[c] + h) - dense(radii[c] - h)) / (2 * h)
+    got = dS[c].cpu().numpy().reshape(48, 48)
+    assert np.abs(got - fd).max() < 1e-6 * np.abs(fd).max()
