@@ -428,21 +428,52 @@ __global__ void __launch_bounds__(256) k_basis_expand(const double* __restrict__
   const int64_t l_begin = (int64_t)blockIdx.y * cols_per_cta;
   const int64_t l_end = l_begin + cols_per_cta < L ? l_begin + cols_per_cta : L;
   const int bcol = 4 * (r8 >> 1) + (r8 & 1);
+  // B fragments of a 16-column group: 2 KT loads straight from the (L2 / L1 resident) basis.  Up to 10 k-steps the NEXT
+  // group's fragments are fetched before the current group's DMMAs are issued (software pipelining: with one CTA per
+  // SM at these register counts nothing else hides the load latency: 42 % long-scoreboard stalls without it).
+  constexpr bool PREFETCH = KT <= 10;
+  double bn[PREFETCH ? KT : 1][2];
+  auto load_b = [&](int64_t l0, double (&bb)[PREFETCH ? KT : 1][2]) {
+    const bool bval = l0 + bcol < L && l0 < l_end;         // L % 4 == 0: the +2 column is valid with it
+    const double* bp = basisP + (size_t)(k0 + c4) * L + l0 + bcol;
+#pragma unroll
+    for (int kk = 0; kk < (PREFETCH ? KT : 1); ++kk) {
+      const bool bk = bval && k0 + 4 * kk + c4 < Kp;        // KT may be rounded up past the padded basis
+      bb[kk][0] = bk ? __ldg(bp + (size_t)(4 * kk) * L) : 0.0;
+      bb[kk][1] = bk ? __ldg(bp + (size_t)(4 * kk) * L + 2) : 0.0;
+    }
+  };
+  if (PREFETCH) load_b(l_begin, bn);
   for (int64_t l0 = l_begin; l0 < l_end; l0 += 16) {
     double c[MT][2][2];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) { c[mt][0][0] = c[mt][0][1] = c[mt][1][0] = c[mt][1][1] = 0.0; }
-    const bool bval = l0 + bcol < L;                       // L % 4 == 0: the +2 column is valid with it
-    const double* bp = basisP + (size_t)(k0 + c4) * L + l0 + bcol;
+    if (PREFETCH) {
+      double b[PREFETCH ? KT : 1][2];
 #pragma unroll
-    for (int kk = 0; kk < KT; ++kk) {
-      const bool bk = bval && k0 + 4 * kk + c4 < Kp;          // KT may be rounded up past the padded basis
-      const double b0 = bk ? __ldg(bp + (size_t)(4 * kk) * L) : 0.0;
-      const double b1 = bk ? __ldg(bp + (size_t)(4 * kk) * L + 2) : 0.0;
+      for (int kk = 0; kk < (PREFETCH ? KT : 1); ++kk) { b[kk][0] = bn[kk][0]; b[kk][1] = bn[kk][1]; }
+      load_b(l0 + 16, bn);
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        dmma884(c[mt][0][0], c[mt][0][1], a[mt][kk], b0);
-        dmma884(c[mt][1][0], c[mt][1][1], a[mt][kk], b1);
+      for (int kk = 0; kk < (PREFETCH ? KT : 1); ++kk) {
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          dmma884(c[mt][0][0], c[mt][0][1], a[mt][kk], b[kk][0]);
+          dmma884(c[mt][1][0], c[mt][1][1], a[mt][kk], b[kk][1]);
+        }
+      }
+    } else {
+      const bool bval = l0 + bcol < L;
+      const double* bp = basisP + (size_t)(k0 + c4) * L + l0 + bcol;
+#pragma unroll
+      for (int kk = 0; kk < KT; ++kk) {
+        const bool bk = bval && k0 + 4 * kk + c4 < Kp;
+        const double b0 = bk ? __ldg(bp + (size_t)(4 * kk) * L) : 0.0;
+        const double b1 = bk ? __ldg(bp + (size_t)(4 * kk) * L + 2) : 0.0;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          dmma884(c[mt][0][0], c[mt][0][1], a[mt][kk], b0);
+          dmma884(c[mt][1][0], c[mt][1][1], a[mt][kk], b1);
+        }
       }
     }
     const int64_t lc = l0 + 4 * c4;
