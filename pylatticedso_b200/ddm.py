@@ -67,7 +67,7 @@ def interface_from_lattice(lattice, ctx=None):
     ``cell.schur_complement`` on every cell and ``Point.index_boundary`` on the cell-boundary nodes.
     Returns (InterfaceProblem, {index_boundary: Point}, fixed, g, f) with 6 DOFs per interface node."""
     import torch
-    ctx = ctx or L.Context()
+    ctx = ctx or L.default_context()
     cells = list(lattice.cells)
     for c in cells:
         if c.node_in_order_simulation is None:
@@ -147,7 +147,7 @@ def compliance_gradient_cells(lattice, ctx=None, adjoint=None):
     boundary displacements on the ``Point``s and ``cell.schur_complement_gradient`` -- the inner term of
     ``LatticeOpti.calculate_gradient`` (lattice_opti.py:752-761).  ``adjoint``: optional per-cell list of lambda_c."""
     import torch
-    ctx = ctx or L.Context()
+    ctx = ctx or L.default_context()
     cells = list(lattice.cells)
     n_geom = max(len(getattr(c, "schur_complement_gradient", None) or []) for c in cells)
     if n_geom == 0:

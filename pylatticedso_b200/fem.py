@@ -41,6 +41,7 @@ class BeamFEM:
                  pinned: bool = False):
         import torch
         self.torch = torch
+        # an operator owns a resident sparsity pattern inside its context: without an explicit ctx it gets a private one
         self.ctx = ctx or L.Context()
         self.mesh = mesh
         self.young, self.nu, self.kappa = float(young), float(nu), float(kappa)
@@ -243,7 +244,7 @@ def solve_FEM_B200(lattice, elements_per_strut="gmsh", tol=1e-10, maxiter=500000
     E, nu = material_constants(lattice)
     mesh = flatten_lattice(lattice, None, elements_per_strut)
     fixed, g, f = bc_arrays_from_lattice(lattice, mesh, dedup_point_loads=dedup_point_loads)
-    fem = BeamFEM(mesh, E, nu, ctx=ctx)
+    fem = BeamFEM(mesh, E, nu, ctx=ctx or L.default_context())     # one shared workspace across drop-in calls
     if condense_struts:      # joint-only solve + back-substitution: model.u / model.R cover all nodes like the other paths
         u, R, info = fem.solve_condensed(fixed, g, f, tol=tol, maxiter=maxiter, precond=precond, full_field=True)
     else:

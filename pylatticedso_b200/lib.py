@@ -161,6 +161,23 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
+_default_ctx = {}
+
+
+def default_context(device=None):
+    """Process-wide context of a device (created on first use): what every host entry point uses when the caller
+    passes ``ctx=None``, so that repeated drop-in calls share one workspace instead of allocating a context each."""
+    import torch
+    if not torch.cuda.is_available():
+        raise LatticeB200Error("no CUDA device available: pylatticedso_b200 has no CPU fallback")
+    idx = torch.cuda.current_device() if device is None else (device if isinstance(device, int) else torch.device(device).index or 0)
+    c = _default_ctx.get(idx)
+    if c is None or c.h is None:
+        c = Context(idx)
+        _default_ctx[idx] = c
+    return c
+
+
 class Context:
     """One library context = one GPU + one CUDA stream (torch's current stream)."""
 

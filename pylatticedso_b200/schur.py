@@ -124,7 +124,7 @@ def get_schur_complement(lattice, cell_index=None, elements_per_strut="gmsh", ct
     loc = {int(i): k for k, i in enumerate(mesh.point_index)}
     bnd = np.array([loc[p.index] for p in cell.node_in_order_simulation], dtype=np.int64)
     E, nu = material_constants(lattice)
-    ctx = ctx or L.Context()
+    ctx = ctx or L.default_context()
     perm, xyz, l0, l1 = local_cell_mesh(mesh, bnd)
     dev = ctx.device
     chains = strut_chains(xyz, l0, l1, len(bnd))
@@ -155,7 +155,7 @@ def schur_gradients(lattice, cell, radii_params, elements_per_strut="gmsh", ctx=
     loc = {int(i): k for k, i in enumerate(mesh.point_index)}
     bnd = np.array([loc[p.index] for p in cell.node_in_order_simulation], dtype=np.int64)
     E, nu = material_constants(lattice)
-    ctx = ctx or L.Context()
+    ctx = ctx or L.default_context()
     perm, xyz, l0, l1 = local_cell_mesh(mesh, bnd)
     radii_params = [float(r) for r in radii_params]
     types = np.asarray(mesh.type_of_elem, dtype=np.int64)

@@ -28,7 +28,7 @@ _ptr = L._ptr
 
 
 def _ctx(ctx):
-    return ctx if ctx is not None else L.Context()
+    return ctx if ctx is not None else L.default_context()
 
 
 def _dev(ctx, a, dtype=None):
