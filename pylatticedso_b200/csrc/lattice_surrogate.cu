@@ -151,12 +151,18 @@ __global__ void k_transpose(const double* __restrict__ in, int rows, int cols, d
 // ---------------------------------------------------------------------------------------------------------------
 // SPD solve G X = R in place (Cholesky, right looking).  G [n][n] row-major, R [n][m] row-major.
 __global__ void __launch_bounds__(1024) k_chol_solve(double* __restrict__ G, int n, double* __restrict__ R, int m, int* __restrict__ fail) {
-  __shared__ double piv;
+  __shared__ double piv, floor_;
+  if (threadIdx.x == 0) {                      // pivots below 1e-13 of the largest diagonal entry = numerically rank deficient
+    double dmax = 0.0;
+    for (int j = 0; j < n; ++j) dmax = fmax(dmax, G[(size_t)j * n + j]);
+    floor_ = 1e-13 * dmax;
+  }
+  __syncthreads();
   for (int j = 0; j < n; ++j) {
     if (threadIdx.x == 0) {
       const double d = G[(size_t)j * n + j];
-      if (!(d > 0.0)) *fail = j + 1;
-      piv = sqrt(d > 0.0 ? d : 1.0);
+      if (!(d > floor_)) *fail = j + 1;
+      piv = sqrt(d > floor_ ? d : 1.0);
     }
     __syncthreads();
     const double p = piv;
@@ -603,8 +609,8 @@ extern "C" int lat_rbf_fit(lat_ctx* ctx, const double* x_train, int32_t N, int32
 extern "C" int lat_rbf_eval(lat_ctx* ctx, const double* x_train, int32_t N, int32_t d, const double* wcp, int32_t m,
                             const double* xq, int64_t M, double* f, double* grad) {
   if (!ctx) return LAT_ERR_ARG;
-  LAT_CHECK_ARG(ctx, x_train && wcp && xq && (f || grad) && N > 0 && d > 0 && d <= TPS_DMAX && m > 0 && M >= 0);
   if (M == 0) return LAT_OK;
+  LAT_CHECK_ARG(ctx, x_train && wcp && xq && (f || grad) && N > 0 && d > 0 && d <= TPS_DMAX && m > 0 && M > 0);
   LAT_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t smem = sizeof(double) * TPS_Q * TPS_C * (grad ? 1 + d : 1);
   LAT_CUDA(ctx, cudaFuncSetAttribute(k_tps_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * TPS_Q * TPS_C * (1 + TPS_DMAX))));
@@ -615,11 +621,11 @@ extern "C" int lat_rbf_eval(lat_ctx* ctx, const double* x_train, int32_t N, int3
 extern "C" int lat_alpha_lookup(lat_ctx* ctx, int32_t mode, const double* x_train, int32_t N, int32_t d, const double* alpha_train,
                                 int32_t m, const double* xq, int64_t M, double* out) {
   if (!ctx) return LAT_ERR_ARG;
-  LAT_CHECK_ARG(ctx, x_train && alpha_train && xq && out && N > 0 && d > 0 && m > 0 && M >= 0 && (mode == 0 || mode == 1));
   if (mode == 1 && d != 1)
     return lat_fail(ctx, LAT_ERR_UNSUPPORTED, "the linear surrogate is implemented for one parameter (np.interp branch, lattice_sim.py:781-792)",
                     __FILE__, __LINE__);
   if (M == 0) return LAT_OK;
+  LAT_CHECK_ARG(ctx, x_train && alpha_train && xq && out && N > 0 && d > 0 && m > 0 && M > 0 && (mode == 0 || mode == 1));
   LAT_CUDA(ctx, cudaSetDevice(ctx->device));
   LAT_LAUNCH(ctx, k_alpha_lookup, (unsigned)ceil_div(M, 128), 128, 0, mode, x_train, N, d, alpha_train, m, xq, M, out);
   return LAT_OK;
@@ -637,9 +643,9 @@ extern "C" int lat_basis_prepare(lat_ctx* ctx, const double* basis, int64_t len,
 extern "C" int lat_basis_expand(lat_ctx* ctx, const double* basisP, int32_t k, int64_t len, const double* alphas, int64_t M,
                                 int32_t lda, double* out) {
   if (!ctx) return LAT_ERR_ARG;
-  LAT_CHECK_ARG(ctx, basisP && alphas && out && k > 0 && lda >= k && M >= 0);
+  if (M == 0) return LAT_OK;                                       // an empty batch has no buffers to check
+  LAT_CHECK_ARG(ctx, basisP && alphas && out && k > 0 && lda >= k && M > 0);
   LAT_CHECK_ARG(ctx, len > 0 && len % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 31) == 0);      // 256-bit stores
-  if (M == 0) return LAT_OK;
   LAT_CUDA(ctx, cudaSetDevice(ctx->device));
   const int Kp = 4 * (int)ceil_div(k, 4);
   for (int k0 = 0; k0 < Kp; k0 += 64) {

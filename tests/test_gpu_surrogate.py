@@ -159,3 +159,43 @@ def test_latticesim_drop_ins_on_a_duck_typed_lattice(ctx, ref, rb6):
     surrogate.lattice_define_rbf(me, ctx=ctx)
     np.testing.assert_allclose(me.radial_basis_function.evaluate(ref["q1"]), ref["s1_rbf_alphas"], rtol=0,
                                atol=1e-10 * np.abs(ref["s1_rbf_alphas"]).max())
+
+
+def test_error_paths_and_edges(ctx, rb6):
+    """Loud failures instead of silent garbage: duplicate RBF centres, a rank-deficient basis in the projection, the
+    N-parameter linear surrogate (not a device kernel); empty query batches are a no-op."""
+    import torch
+    from pylatticedso_b200 import surrogate
+    from pylatticedso_b200.lib import LatticeB200Error
+    with pytest.raises(LatticeB200Error, match="singular"):
+        surrogate.ThinPlateSplineRBF(np.array([[0.1], [0.1], [0.3]]), np.array([1.0, 1.0, 2.0]), ctx=ctx)
+    B = np.random.default_rng(0).standard_normal((36, 2))
+    with pytest.raises(LatticeB200Error, match="rank deficient"):
+        surrogate.project_to_reduced_basis({0: np.ones((6, 6))}, np.column_stack([B[:, 0], B[:, 0]]), ctx=ctx)
+    two_d = {"basis_reduced_ortho": rb6["basis_reduced_ortho"], "alpha_ortho": np.zeros((5, 4)),
+             "list_elements": np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0], [1.0, 1.0]])}
+    s = surrogate.SchurSurrogate(two_d, "linear", ctx=ctx)
+    with pytest.raises(LatticeB200Error, match="one parameter"):
+        s.schur_batch([[0.5, 0.5]])
+    with pytest.raises(NotImplementedError):
+        surrogate.SchurSurrogate(rb6, "kriging", ctx=ctx)
+    s = surrogate.SchurSurrogate(rb6, "RBF", ctx=ctx)
+    empty = s.expand_device(torch.empty((0, 5), dtype=torch.float64, device=ctx.device))
+    assert tuple(empty.shape) == (0, 48, 48)
+    with pytest.raises(ValueError):
+        s.schur_batch([[0.05, 0.06]])                     # two parameters for a one-parameter surrogate
+
+
+def test_rbf_many_centres_and_three_parameters(ctx):
+    """More centres than one shared-memory chunk (128) and d = 3: device fit / value / gradient against the oracle."""
+    from oracle import surrogate_oracle as so
+    from pylatticedso_b200 import surrogate
+    rng = np.random.default_rng(21)
+    X = rng.uniform(0.0, 1.0, (300, 3))
+    Y = np.stack([np.sin(X @ np.array([1.0, 2.0, 3.0])), X[:, 0] * X[:, 1], np.exp(-X[:, 2])], axis=1)
+    r = surrogate.ThinPlateSplineRBF(X, Y, reg=1e-10, ctx=ctx)
+    wcp = so.tps_fit(X, Y, reg=1e-10)
+    q = rng.uniform(0.0, 1.0, (77, 3))
+    np.testing.assert_allclose(r.evaluate(q), so.tps_evaluate(X, wcp, q), rtol=0, atol=1e-7)
+    np.testing.assert_allclose(r.gradient(q), so.tps_gradient(X, wcp, q), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(r.evaluate(X[:10]), Y[:10], rtol=0, atol=1e-6)        # interpolation at the centres
