@@ -590,7 +590,7 @@ extern "C" int lat_basis_project(lat_ctx* ctx, const double* basis, int32_t k, i
 extern "C" int lat_rbf_fit(lat_ctx* ctx, const double* x_train, int32_t N, int32_t d, const double* y, int32_t m, double reg,
                            double* wcp) {
   if (!ctx) return LAT_ERR_ARG;
-  LAT_CHECK_ARG(ctx, x_train && y && wcp && N > 0 && d > 0 && d <= TPS_DMAX && m > 0 && N + d + 1 <= 8192);
+  LAT_CHECK_ARG(ctx, x_train && y && wcp && N > 0 && d > 0 && d <= TPS_DMAX && m > 0 && N + d + 1 <= 4096);     // one-CTA LU
   LAT_CUDA(ctx, cudaSetDevice(ctx->device));
   const int n = N + d + 1;
   double* A = lat_buf<double>(ctx, "rbf_A", (size_t)n * n);
