@@ -169,3 +169,47 @@ def test_config3_bcc60_schur_batch_full_size_against_the_oracle_on_samples(ctx):
     fd = (dense(radii[c] + h) - dense(radii[c] - h)) / (2 * h)
     got = dS[c].cpu().numpy().reshape(48, 48)
     assert np.abs(got - fd).max() < 1e-6 * np.abs(fd).max()
+
+
+def test_config4_octet100_full_size_solve(ctx):
+    """configs[4] at full size on one GPU (24 361 806 DOF): the matrix-free solve to 1e-8, its true residual through the
+    independent un-eliminated product, 512 sampled rows of K u against the numpy oracle's element matrices, and the
+    assembled product (15 GB matrix) against the matrix-free one on the solution."""
+    import torch
+    from oracle import lattice_oracle as orc
+    from pylatticedso_b200 import distributed as D, lib as L
+    from pylatticedso_b200.fem import BeamFEM
+    lm, _ = D.generate_slab("Octet", (100, 100, 100), [0.03], 1, 0, 1)
+    assert (lm.n_nodes, lm.n_elems, lm.n_dof) == (4060301, 24120000, 24361806)
+    fixed, g, f = D.compression_bc_local(lm)
+    fem = BeamFEM(lm, E_MOD, NU, ctx=ctx)
+    fem.build_pattern()
+    assert fem.nnzb == lm.n_nodes + 2 * lm.n_elems
+    t = lambda a, d: torch.from_numpy(np.ascontiguousarray(a, dtype=d)).to(ctx.device)
+    bc = (t(fixed, np.uint8), t(g, np.float64), t(f, np.float64))
+    u, R, info = fem.solve_matrix_free(*bc, tol=1e-8, maxiter=100000, precond=L.PC_BLOCK6)
+    assert info["info"] == 0 and info["relres"] <= 1e-8 and info["true_relres"] <= 2e-8
+    fx = bc[0].bool()
+    assert float((u[fx] - bc[1][fx]).abs().max()) < 1e-14
+    assert float((R - bc[2])[~fx].norm()) <= 3e-8 * info["norm_b"]          # R = K u from the un-eliminated operator
+    Rn = R.reshape(-1, 6)
+    assert float(Rn[:, :3].sum(0).abs().max()) < 1e-6 * float(Rn[:, 2].abs().sum())   # the reactions balance
+    # sampled rows of K u against the oracle (elements that touch the sampled nodes only)
+    rng = np.random.default_rng(9)
+    uh = u.cpu().numpy()
+    nodes = rng.choice(lm.n_nodes, 512, replace=False)
+    touch = np.flatnonzero(np.isin(lm.en0, nodes) | np.isin(lm.en1, nodes))
+    en = np.stack([lm.en0[touch], lm.en1[touch]], 1).astype(np.int64)
+    Ke = orc.element_stiffness(lm.xyz[en[:, 0]], lm.xyz[en[:, 1]], lm.rad[touch], E_MOD, NU)
+    dofs = (en[:, :, None] * 6 + np.arange(6)[None, None, :]).reshape(-1, 12)
+    fe = np.einsum("eab,eb->ea", Ke, uh[dofs])
+    ref = np.zeros((lm.n_nodes, 6))
+    np.add.at(ref, en[:, 0], fe[:, :6])
+    np.add.at(ref, en[:, 1], fe[:, 6:])
+    Rh = Rn.cpu().numpy()
+    scale = np.abs(fe).max()                                                  # rows of an equilibrium state cancel
+    assert np.abs(Rh[nodes] - ref[nodes]).max() < 1e-11 * scale
+    # assembled operator == matrix-free operator on the solution
+    fem.assemble()
+    Ra = ctx.spmv(fem.rowptr, fem.colidx, fem.vals, u)
+    assert float((Ra - R).abs().max()) < 1e-11 * scale
