@@ -158,3 +158,27 @@ def test_joint_only_system_equals_full_system_at_the_joints(geom, cells, mseg):
     assert np.abs(u[:nj] - uj).max() <= 1e-10 * np.abs(u).max()
     assert np.abs(R[:nj] - Rj).max() <= 1e-10 * np.abs(R).max()
 
+
+
+def test_ill_restart_iterate_is_rounding_sensitive_at_the_1e4_level():
+    """Why the GPU parity test accepts 1e-3 on x for `ill_restart` only (tests/test_gpu_parity.py): the case runs 300
+    NON-converged iterations on a matrix with cond ~ 2e8, and on the CPU itself a rounding-level change -- b perturbed
+    by 1e-16 relative, or the SAME matrix-vector product summed in a different column order -- moves the final
+    iterate by 1e-5..1e-4 relative while iteration count and info code stay put.  Bit-level agreement of x is not a
+    property of the algorithm here; iteration count, info code and a 1e-3 band are what can be compared."""
+    G = load_golden("pcg_reference.npz")
+    A, b = G["A_ill"], G["ill_restart_b"]
+    maxiter, tol, mintol, restart, amax = G["ill_restart_params"]
+    d = 1.0 / np.diag(A)
+    Minv = (lambda v: d * v) if bool(G["ill_restart_jacobi"]) else None
+    kw = dict(maxiter=int(maxiter), tol=tol, mintol=mintol, restart_every=int(restart), alpha_max=amax)
+    x0, info0, it0 = orc.reference_pcg(A, b, Minv, **kw)
+    assert np.linalg.cond(A) > 1e8 and it0 == 300 and info0 == int(G["ill_restart_info"])
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(A.shape[0])
+    Ac = np.ascontiguousarray(A[:, perm])
+    x1, info1, it1 = orc.reference_pcg(lambda v: Ac @ v[perm], b, Minv, **kw)           # same product, other summation order
+    x2, info2, it2 = orc.reference_pcg(A, b * (1.0 + 1e-16 * rng.standard_normal(b.shape)), Minv, **kw)
+    assert (info1, it1) == (info0, it0) and (info2, it2) == (info0, it0)
+    dev = max(np.abs(x1 - x0).max(), np.abs(x2 - x0).max()) / np.abs(x0).max()
+    assert 1e-7 < dev < 1e-3
