@@ -93,6 +93,36 @@ __device__ __forceinline__ void piece_row(const int32_t* colidx, const double* _
   }
 }
 
+// Matrix loads with an explicit L2 eviction policy (createpolicy + ld.global.L2::cache_hint), past L1.
+__device__ __forceinline__ double2 ld_policy(const double2* p, unsigned long long pol) {
+  double2 v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ Piece3 piece_load_policy(const double* __restrict__ vals, int64_t j, int r, const double* xcol, int c,
+                                                    unsigned long long pol) {
+  Piece3 q;
+  const double2* vp = reinterpret_cast<const double2*>(vals + j * 36 + 2 * r);
+  q.a0 = ld_policy(vp, pol); q.a1 = ld_policy(vp + 6, pol); q.a2 = ld_policy(vp + 12, pol);
+  q.x = *reinterpret_cast<const double2*>(xcol + 2 * c);
+  return q;
+}
+__device__ __forceinline__ void piece_row_policy(const int32_t* colidx, const double* __restrict__ vals, int lo, int hi, int r,
+                                                 const double* x, double& s0, double& s1, double& s2, unsigned long long pol) {
+  const int c = r % 3;
+  for (int j = lo; j < hi; j += 3) {
+    const bool p1 = j + 1 < hi, p2 = j + 2 < hi;
+    const int j1 = p1 ? j + 1 : j, j2 = p2 ? j + 2 : j;
+    const int c0 = colidx[j], c1 = colidx[j1], c2 = colidx[j2];
+    const Piece3 q0 = piece_load_policy(vals, j, r, x + (int64_t)c0 * 6, c, pol);
+    const Piece3 q1 = piece_load_policy(vals, j1, r, x + (int64_t)c1 * 6, c, pol);
+    const Piece3 q2 = piece_load_policy(vals, j2, r, x + (int64_t)c2 * 6, c, pol);
+    piece_fma(q0, s0, s1, s2);
+    if (p1) piece_fma(q1, s0, s1, s2);
+    if (p2) piece_fma(q2, s0, s1, s2);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // plain y = A x
 // ---------------------------------------------------------------------------
@@ -241,7 +271,8 @@ struct PcgParams {
   double tol, mintol, alpha_max;
   int64_t restart_every;
   int32_t maxiter, reference;
-  int32_t dist, pad;  // dist = 1: kernels only store LOCAL sums; the host all-reduces and runs k_pcg_finalize_*
+  int32_t dist, l2_keep;  // dist = 1: kernels only store LOCAL sums; the host all-reduces and runs k_pcg_finalize_*
+                          // l2_keep = k > 0 (k_cg_spmv<.., .., true>): the matrix blocks of k/16 of the rows stay L2-resident
   unsigned long long seq_base;  // peer-memory path: (solve epoch << 32), so flags of earlier solves never match
   unsigned long long push_base; // fused-halo path: halo pushes completed by earlier solves on this arena
 };
@@ -533,7 +564,7 @@ __device__ __forceinline__ void halo_push(const HaloPush& hp, int2 d, int comp, 
 // SUBSET = true enables rs.rows / rs.skip (opt-in overlap path); without it the row extent and own entries
 // are loaded before the status word is looked at -- a skip[] load in front of them serialised one more
 // memory round trip per CTA (+9 % at 15 waves of CTAs).
-template <bool GHOST = false, bool SUBSET = false>
+template <bool GHOST = false, bool SUBSET = false, bool L2KEEP = false>
 __global__ void __launch_bounds__(SPMV_BLOCK) k_cg_spmv(
 const int32_t* __restrict__ rowptr,
                                                         const int32_t* __restrict__ colidx,
@@ -567,7 +598,14 @@ const int32_t* __restrict__ rowptr,
   }
   double s0 = 0.0, s1 = 0.0, s2 = 0.0;
   if (GHOST && need_row) piece_row<true, true>(colidx, vals, lo, hi, rr_, u, s0, s1, s2);   // ghost-reading row: gathers past L1
-  else piece_row<true, false>(colidx, vals, lo, hi, rr_, u, s0, s1, s2);
+  else if (L2KEEP) {
+    // matrices of up to a few L2 sizes: ~44 MB of the blocks (the same 16-row classes in every iteration) are loaded
+    // evict_last and stay in L2 between iterations, the rest streams evict_first (as in k_pcg_persist)
+    unsigned long long pol;
+    if (((n >> 4) & 15) < prm.l2_keep) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    piece_row_policy(colidx, vals, lo, hi, rr_, u, s0, s1, s2, pol);
+  } else piece_row<true, false>(colidx, vals, lo, hi, rr_, u, s0, s1, s2);
   const double acc = piece_finish(g, rr_, s0, s1, s2);
   if (active) w[i] = acc;
   double v[3] = {ro * uo, acc * uo, ro * ro};
@@ -956,17 +994,32 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
   prm.maxiter = o->maxiter;
   prm.reference = o->reference_semantics;
   prm.dist = 0;
-  prm.pad = 0;
+  prm.l2_keep = 0;
   prm.seq_base = 0;
   prm.push_base = 0;
   int check = o->check_every > 0 ? o->check_every : 32;
   if (check > o->maxiter) check = o->maxiter > 0 ? o->maxiter : 1;
+  if (!mf && rowptr) {
+    // L2-resident part of the matrix (see k_cg_spmv<.., .., true>): ~44 MB, for matrices of up to one L2 size only --
+    // measured (tools/ab_spmv_l2keep.py): 98 MB 35.7 -> 32.5 us per iteration, 168 MB 55.4 -> 56.2, 397 MB 130.5 -> 131.8
+    // (the update kernel streams the vectors between two products and evicts what a larger matrix leaves room for)
+    int32_t last = 0;
+    LAT_CUDA(ctx, cudaMemcpyAsync(&last, rowptr + n_nodes, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const double mat_mb = (double)last * 288.0 / 1e6;
+    int keep = (mat_mb > 0.0 && mat_mb <= 128.0) ? (int)(16.0 * 44.0 / mat_mb + 0.5) : 0;
+    keep = keep < 0 ? 0 : (keep > 8 ? 8 : keep);
+    const char* env_keep = getenv("LAT_SPMV_L2KEEP");
+    prm.l2_keep = env_keep ? atoi(env_keep) : keep;
+  }
 
   // bit 3 of `reserved` forces the classic two-reduction recurrences in the textbook mode
   const bool cgv = mf || (!o->reference_semantics && !(o->reserved & 8) && !plan.tma);
   auto launch_spmv = [&](cudaStream_t st) {
     if (mf)
       k_cg_spmv_mf<false><<<mf_grid, MF_BLOCK, 0, st>>>(*mf, n_nodes, z, r, Ap, sc, partials, prm, RowSet());
+    else if (cgv && prm.l2_keep > 0)
+      k_cg_spmv<false, false, true><<<grid, SPMV_BLOCK, 0, st>>>(rowptr, colidx, vals, n_nodes, z, r, Ap, sc, partials, prm, RowSet());
     else if (cgv)
       k_cg_spmv<false><<<grid, SPMV_BLOCK, 0, st>>>(rowptr, colidx, vals, n_nodes, z, r, Ap, sc, partials, prm, RowSet());
     else if (plan.tma)
@@ -1262,7 +1315,7 @@ static int pcg_run_persist(lat_ctx* ctx, const int32_t* rowptr, const int32_t* c
   a.rowptr = rowptr; a.colidx = colidx; a.vals = vals; a.n_nodes = n_nodes; a.b = b; a.x = x; a.u = u; a.dinv = dinv;
   a.sc = sc;
   a.prm.tol = o->tol; a.prm.mintol = 0.0; a.prm.alpha_max = 0.0; a.prm.restart_every = 0; a.prm.maxiter = o->maxiter;
-  a.prm.reference = 0; a.prm.dist = 0; a.prm.pad = 0; a.prm.seq_base = 0; a.prm.push_base = 0;
+  a.prm.reference = 0; a.prm.dist = 0; a.prm.l2_keep = 0; a.prm.seq_base = 0; a.prm.push_base = 0;
   a.mail = mail; a.flags = flags; a.rows_cap = rows_cap; a.blk_cap = blk_cap; a.pc_smem = pc_smem ? 1 : 0;
   a.nranks = 1; a.my_rank = 0; a.n_nb = 0;
   a.ghost_first[0] = a.ghost_first[1] = 0; a.ghost_entries[0] = a.ghost_entries[1] = 0;
@@ -2053,7 +2106,7 @@ static int pcg_run_dist_impl(lat_ctx* ctx, const int32_t* rowptr, const int32_t*
   const int64_t launches0 = ctx->launches;
   PcgParams prm;
   prm.tol = o->tol; prm.mintol = 0.0; prm.alpha_max = 0.0; prm.restart_every = 0;
-  prm.maxiter = o->maxiter; prm.reference = 0; prm.dist = 1; prm.pad = 0; prm.seq_base = 0; prm.push_base = 0;
+  prm.maxiter = o->maxiter; prm.reference = 0; prm.dist = 1; prm.l2_keep = 0; prm.seq_base = 0; prm.push_base = 0;
   int check = o->check_every > 0 ? o->check_every : 32;
   const bool multi = ctx->nranks > 1 && ctx->nccl_comm != nullptr;
   // the product: assembled BSR rows or the matrix-free operator (owned rows only, ghosts are read)

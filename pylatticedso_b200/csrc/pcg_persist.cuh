@@ -307,36 +307,6 @@ __device__ __forceinline__ void persist_reduce(double (&v)[3], unsigned long lon
   }
 }
 
-// Matrix loads with an explicit L2 eviction policy (createpolicy + ld.global.L2::cache_hint), past L1.
-__device__ __forceinline__ double2 ld_policy(const double2* p, unsigned long long pol) {
-  double2 v;
-  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ Piece3 piece_load_policy(const double* __restrict__ vals, int64_t j, int r, const double* xcol, int c,
-                                                    unsigned long long pol) {
-  Piece3 q;
-  const double2* vp = reinterpret_cast<const double2*>(vals + j * 36 + 2 * r);
-  q.a0 = ld_policy(vp, pol); q.a1 = ld_policy(vp + 6, pol); q.a2 = ld_policy(vp + 12, pol);
-  q.x = *reinterpret_cast<const double2*>(xcol + 2 * c);
-  return q;
-}
-__device__ __forceinline__ void piece_row_policy(const int32_t* colidx, const double* __restrict__ vals, int lo, int hi, int r,
-                                                 const double* x, double& s0, double& s1, double& s2, unsigned long long pol) {
-  const int c = r % 3;
-  for (int j = lo; j < hi; j += 3) {
-    const bool p1 = j + 1 < hi, p2 = j + 2 < hi;
-    const int j1 = p1 ? j + 1 : j, j2 = p2 ? j + 2 : j;
-    const int c0 = colidx[j], c1 = colidx[j1], c2 = colidx[j2];
-    const Piece3 q0 = piece_load_policy(vals, j, r, x + (int64_t)c0 * 6, c, pol);
-    const Piece3 q1 = piece_load_policy(vals, j1, r, x + (int64_t)c1 * 6, c, pol);
-    const Piece3 q2 = piece_load_policy(vals, j2, r, x + (int64_t)c2 * 6, c, pol);
-    piece_fma(q0, s0, s1, s2);
-    if (p1) piece_fma(q1, s0, s1, s2);
-    if (p2) piece_fma(q2, s0, s1, s2);
-  }
-}
-
 // s_w = (A v) on the CTA's rows: six lanes per block row in the transposed-piece layout, three blocks (12 x 16 B loads
 // per lane) in flight; lane (g, r) leaves the total of scalar row lane_dof(r) in s_w.  All warps call.
 __device__ __forceinline__ void persist_product(const double* __restrict__ vals, const double* v, const int32_t* s_rp,
