@@ -782,7 +782,9 @@ __global__ void __launch_bounds__(128) k_chain_condense_dual(
 // Topology of a star cell, shared by all cells of the batch (device arrays of n_struts entries):
 //   corner[k]  boundary joint (= block row of S) at the far end of strut k;  cend[k]  which end (0 / 1) is the centre
 //   strut_of[j] strut whose corner is boundary joint j;  group[k]  radius group of strut k (sensitivities)
-static constexpr int STAR_CELLS_PER_CTA = 8;         // 128 threads: a half-warp per cell
+// a half-warp per cell; 8 cells (128 threads, 60 KB of shared memory for 8 struts) per CTA for the values, 4 with the
+// sensitivities (7 instead of 3 block sets per cell: 8 cells would need 134 KB = ONE resident CTA, 4 warps per SM)
+__host__ __device__ constexpr int star_cells_per_cta(bool grad) { return grad ? 4 : 8; }
 static constexpr int STAR_MAX_STRUTS = 16;           // one strut per lane of the half-warp
 
 __device__ __forceinline__ void sup_block(const SupCoef& s, int re, int ce, double* dst /*[36] shared*/) {
@@ -810,7 +812,7 @@ __device__ __forceinline__ void star_store4(double* dst, const double (&v)[4], i
 }
 
 template <bool GRAD>
-__global__ void __launch_bounds__(16 * STAR_CELLS_PER_CTA) k_schur_star(
+__global__ void __launch_bounds__(16 * star_cells_per_cta(GRAD), 3) k_schur_star(
     const SupCoef* __restrict__ sup, const SupCoef* __restrict__ dsup, const int32_t* __restrict__ cend,
     const int32_t* __restrict__ strut_of, const int32_t* __restrict__ group, int64_t n_cells, int ns, int n_grad,
     double* __restrict__ S, double* __restrict__ dS) {
@@ -835,7 +837,8 @@ __global__ void __launch_bounds__(16 * STAR_CELLS_PER_CTA) k_schur_star(
     s_group[threadIdx.x] = (GRAD && (int)threadIdx.x < ns) ? group[threadIdx.x] : 0;
   }
   __syncthreads();
-  for (int64_t cell0 = (int64_t)blockIdx.x * STAR_CELLS_PER_CTA; cell0 < n_cells; cell0 += (int64_t)gridDim.x * STAR_CELLS_PER_CTA) {
+  constexpr int CPC = star_cells_per_cta(GRAD);
+  for (int64_t cell0 = (int64_t)blockIdx.x * CPC; cell0 < n_cells; cell0 += (int64_t)gridDim.x * CPC) {
     const int64_t cell = cell0 + slot;
     const bool live = cell < n_cells;
     // 1. strut blocks: lane k builds O_k, D_k and (into W's space) C_k
@@ -1098,17 +1101,18 @@ extern "C" int lat_schur_batch_struts(lat_ctx* ctx, const double* xyz, const int
   else
     LAT_LAUNCH(ctx, k_chain_condense, cgrid, 128, 0, xyz, len0, len1, rad, n_cells, n_loc_nodes, n_loc_elem, chain_ptr,
                chain_elem, chain_flip, ns, young, nu, kappa, sup);
-  const size_t smem = (size_t)STAR_CELLS_PER_CTA * ((dS ? 7 : 3) * ns * 36 + 72) * sizeof(double);
-  int64_t grid = ceil_div(n_cells, STAR_CELLS_PER_CTA);
+  const int cpc = star_cells_per_cta(dS != nullptr);
+  const size_t smem = (size_t)cpc * ((dS ? 7 : 3) * ns * 36 + 72) * sizeof(double);
+  int64_t grid = ceil_div(n_cells, cpc);
   const int64_t cap = (int64_t)ctx->sm_count * 8;
   if (grid > cap) grid = cap;
   if (dS) {
     LAT_CUDA(ctx, cudaFuncSetAttribute(k_schur_star<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LAT_LAUNCH(ctx, k_schur_star<true>, (unsigned)grid, 16 * STAR_CELLS_PER_CTA, smem, sup, dsup, tab, tab + STAR_MAX_STRUTS,
+    LAT_LAUNCH(ctx, k_schur_star<true>, (unsigned)grid, 16 * cpc, smem, sup, dsup, tab, tab + STAR_MAX_STRUTS,
                tab + 2 * STAR_MAX_STRUTS, n_cells, ns, (int)n_grad, S, dS);
   } else {
     LAT_CUDA(ctx, cudaFuncSetAttribute(k_schur_star<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LAT_LAUNCH(ctx, k_schur_star<false>, (unsigned)grid, 16 * STAR_CELLS_PER_CTA, smem, sup, nullptr, tab, tab + STAR_MAX_STRUTS,
+    LAT_LAUNCH(ctx, k_schur_star<false>, (unsigned)grid, 16 * cpc, smem, sup, nullptr, tab, tab + STAR_MAX_STRUTS,
                tab + 2 * STAR_MAX_STRUTS, n_cells, ns, 0, S, nullptr);
   }
   return LAT_OK;
