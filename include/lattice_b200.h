@@ -388,6 +388,12 @@ int lat_rbf_eval(lat_ctx* ctx, const double* x_train, int32_t N, int32_t d, cons
  * of evaluate_alphas_linear_surrogate, :781-792; d = 1 only) surrogates.  alpha_train [N][m], out [M][m]. */
 int lat_alpha_lookup(lat_ctx* ctx, int32_t mode, const double* x_train, int32_t N, int32_t d,
                      const double* alpha_train, int32_t m, const double* xq, int64_t M, double* out);
+/* N-parameter "linear" surrogate (LinearNDInterpolator inside the convex hull of the centres, NearestNDInterpolator
+ * outside: evaluate_alphas_linear_surrogate, lattice_sim.py:794-807) on a Delaunay triangulation of the centres given
+ * in scipy.spatial.Delaunay's layout: simplices int32 [n_simplices][d+1], transform [n_simplices][d+1][d]. */
+int lat_alpha_simplex(lat_ctx* ctx, const int32_t* simplices, const double* transform, int32_t n_simplices, int32_t d,
+                      const double* x_train, int32_t N, const double* alpha_train, int32_t m, const double* xq,
+                      int64_t M, double* out);
 /* Basis in the layout of lat_basis_expand: basis [len][k] row-major (the npz's basis_reduced_ortho) ->
  * basisP [4*ceil(k/4)][len]; n_fortran = n applies the reference's order='F' reshape of every column
  * (lattice_sim.py:973-976): basisP[kk][a*n + b] = basis[a + n*b][kk]; 0 = keep the order. */

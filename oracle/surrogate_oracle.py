@@ -127,6 +127,20 @@ def alphas_linear_1d(list_elements, alpha_train, xq):
     return np.stack([np.interp(q, xs, As[:, j]) for j in range(As.shape[1])], axis=1)
 
 
+def alphas_linear_nd(list_elements, alpha_train, xq):
+    """N-parameter branch of evaluate_alphas_linear_surrogate (:794-807): scipy's LinearNDInterpolator inside the convex
+    hull of the centres, NearestNDInterpolator where it returns NaN."""
+    from scipy.interpolate import LinearNDInterpolator, NearestNDInterpolator
+    X, A = np.asarray(list_elements, float), np.asarray(alpha_train, float)
+    lin, nn = LinearNDInterpolator(X, A), NearestNDInterpolator(X, A)
+    Q = np.atleast_2d(np.asarray(xq, float))
+    y = lin(Q)
+    bad = np.isnan(y).any(axis=1)
+    if bad.any():
+        y[bad] = nn(Q[bad])
+    return y
+
+
 def schur_from_alphas(basis, alphas, n):
     """(n_q, n, n) from basis (n*n, k) and alphas (n_q, k): S_flat = basis @ alphas.T, each column reshaped in
     Fortran order (:961-976)."""

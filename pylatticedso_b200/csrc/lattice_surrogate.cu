@@ -384,6 +384,53 @@ __global__ void k_alpha_lookup(int mode, const double* __restrict__ X, int N, in
   }
 }
 
+// N-parameter "linear" surrogate: piecewise-linear interpolation on a Delaunay triangulation of the centres, nearest
+// centre outside the convex hull (scipy LinearNDInterpolator / NearestNDInterpolator, lattice_sim.py:794-807).  The
+// triangulation is set-up geometry (built once on the host by the same Qhull call scipy makes); the kernel locates the
+// simplex of every query with the triangulation's own barycentric transforms: b = T_s (x - r_s), b_d = 1 - sum b.
+// simplices: int32 [ns][d+1]; transform: [ns][d+1][d] (rows 0..d-1 = T_s, row d = r_s), as scipy.spatial.Delaunay stores it.
+__global__ void k_alpha_simplex(const int32_t* __restrict__ simplices, const double* __restrict__ transform, int ns, int d,
+                                const double* __restrict__ X, int N, const double* __restrict__ alpha, int m,
+                                const double* __restrict__ xq, int64_t M, double* __restrict__ out) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= M) return;
+  const double* xx = xq + q * d;
+  const double eps = 100.0 * 2.220446049250313e-16;          // Qhull's inside test (scipy _qhull: 100 * DBL_EPSILON)
+  double bary[TPS_DMAX + 1];
+  int found = -1;
+  for (int s = 0; s < ns && found < 0; ++s) {
+    const double* T = transform + (size_t)s * (d + 1) * d;
+    double last = 1.0;
+    bool inside = true;
+    for (int i = 0; i < d; ++i) {
+      double b = 0.0;
+      for (int j = 0; j < d; ++j) b = fma(T[i * d + j], xx[j] - T[d * d + j], b);
+      bary[i] = b;
+      last -= b;
+      inside = inside && (b >= -eps) && (b <= 1.0 + eps);     // NaN transforms (degenerate simplices) fail both tests
+    }
+    bary[d] = last;
+    inside = inside && (last >= -eps) && (last <= 1.0 + eps);
+    if (inside) found = s;
+  }
+  if (found >= 0) {
+    const int32_t* vtx = simplices + (size_t)found * (d + 1);
+    for (int j = 0; j < m; ++j) {
+      double v = 0.0;
+      for (int i = 0; i <= d; ++i) v = fma(bary[i], alpha[(size_t)vtx[i] * m + j], v);
+      out[q * m + j] = v;
+    }
+    return;
+  }
+  int best = 0;
+  double bd = INFINITY;
+  for (int i = 0; i < N; ++i) {
+    const double r = tps_dist(xx, X + (size_t)i * d, d);
+    if (r < bd) { bd = r; best = i; }
+  }
+  for (int j = 0; j < m; ++j) out[q * m + j] = alpha[(size_t)best * m + j];
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // 3. S = basis @ alpha on the FP64 tensor cores
 // ---------------------------------------------------------------------------------------------------------------
@@ -628,6 +675,19 @@ extern "C" int lat_alpha_lookup(lat_ctx* ctx, int32_t mode, const double* x_trai
   LAT_CHECK_ARG(ctx, x_train && alpha_train && xq && out && N > 0 && d > 0 && m > 0 && M > 0 && (mode == 0 || mode == 1));
   LAT_CUDA(ctx, cudaSetDevice(ctx->device));
   LAT_LAUNCH(ctx, k_alpha_lookup, (unsigned)ceil_div(M, 128), 128, 0, mode, x_train, N, d, alpha_train, m, xq, M, out);
+  return LAT_OK;
+}
+
+extern "C" int lat_alpha_simplex(lat_ctx* ctx, const int32_t* simplices, const double* transform, int32_t n_simplices, int32_t d,
+                                 const double* x_train, int32_t N, const double* alpha_train, int32_t m, const double* xq,
+                                 int64_t M, double* out) {
+  if (!ctx) return LAT_ERR_ARG;
+  if (M == 0) return LAT_OK;
+  LAT_CHECK_ARG(ctx, simplices && transform && x_train && alpha_train && xq && out && n_simplices > 0 && d > 0 && d <= TPS_DMAX &&
+                         N > 0 && m > 0 && M > 0);
+  LAT_CUDA(ctx, cudaSetDevice(ctx->device));
+  LAT_LAUNCH(ctx, k_alpha_simplex, (unsigned)ceil_div(M, 128), 128, 0, simplices, transform, n_simplices, d, x_train, N,
+             alpha_train, m, xq, M, out);
   return LAT_OK;
 }
 

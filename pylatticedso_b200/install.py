@@ -16,7 +16,7 @@ be rebound without touching a reference file:
 | ``LatticeOpti.calculate_gradient`` (compliance branch)                     | lattice_opti.py:735-841   | ``ddm.compliance_gradient_cells`` + ``fem.cell_sensitivities_to_parameters`` |
 | ``reduce_basis_greedy``, ``project_to_reduced_basis`` (greedy_algorithm)  | greedy_algorithm.py:35-155, 233-266 | ``surrogate.reduce_basis_greedy`` / ``project_to_reduced_basis`` |
 | ``ThinPlateSplineRBF`` (utils_rbf, lattice_sim)                            | utils_rbf.py:13-144       | ``surrogate.ThinPlateSplineRBF`` |
-| ``LatticeSim.get_schur_complement_from_reduced_basis_batch`` / ``..._from_reduced_basis`` / ``_compute_schur_gradients_RBF`` / ``_define_radial_basis_functions`` | lattice_sim.py:921-1018, 1056-1082, 809-812 | ``surrogate.lattice_*`` (RBF / nearest-neighbour / 1-D linear alphas + DMMA ``basis @ alphas``) |
+| ``LatticeSim.get_schur_complement_from_reduced_basis_batch`` / ``..._from_reduced_basis`` / ``_compute_schur_gradients_RBF`` / ``_define_radial_basis_functions`` | lattice_sim.py:921-1018, 1056-1082, 809-812 | ``surrogate.lattice_*`` (RBF / nearest-neighbour / linear alphas + DMMA ``basis @ alphas``) |
 
 ``patch_reference`` returns the list of names it rebound; ``unpatch_reference`` restores the originals.
 """
@@ -77,33 +77,16 @@ def patch_reference(elements_per_strut="gmsh", ctx=None):
         def __init__(self, x_train, y_train, reg=0.0):
             super().__init__(x_train, y_train, reg=reg, ctx=ctx)
 
-    def _linear_or_reference(original):
-        def _batch(self, geometric_params_list):
-            # N-D "linear" (scipy Delaunay interpolation, lattice_sim.py:794-807) is not a device kernel: reference code
-            nd = np_ndim(self.reduce_basis_dict["list_elements"])
-            if self.type_schur_complement_computation == "linear" and nd > 1:
-                return original(self, geometric_params_list)
-            return surrogate.lattice_schur_batch(self, geometric_params_list, ctx=ctx)
-        return _batch
-
-    def np_ndim(list_elements):
-        import numpy as np
-        a = np.asarray(list_elements)
-        return 1 if a.ndim == 1 else a.shape[1]
-
     for modname in ("pyLatticeSim.greedy_algorithm",):
         _rebind(mods.get(modname), "reduce_basis_greedy", _greedy, done, f"{modname}.reduce_basis_greedy")
         _rebind(mods.get(modname), "project_to_reduced_basis", _project, done, f"{modname}.project_to_reduced_basis")
     for modname in ("pyLatticeSim.utils_rbf", "pyLatticeSim.lattice_sim"):
         _rebind(mods.get(modname), "ThinPlateSplineRBF", _TPS, done, f"{modname}.ThinPlateSplineRBF")
     if lattice_sim_cls is not None and hasattr(lattice_sim_cls, "get_schur_complement_from_reduced_basis_batch"):
-        orig_batch = lattice_sim_cls.get_schur_complement_from_reduced_basis_batch
-        orig_single = lattice_sim_cls.get_schur_complement_from_reduced_basis
-        _batch = _linear_or_reference(orig_batch)
+        def _batch(self, geometric_params_list):
+            return surrogate.lattice_schur_batch(self, geometric_params_list, ctx=ctx)
 
         def _single(self, geometric_params):
-            if self.type_schur_complement_computation == "linear" and np_ndim(self.reduce_basis_dict["list_elements"]) > 1:
-                return orig_single(self, geometric_params)
             return surrogate.lattice_schur_single(self, geometric_params, ctx=ctx)
 
         pre = "pyLatticeSim.lattice_sim.LatticeSim."

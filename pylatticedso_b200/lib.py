@@ -33,7 +33,7 @@ EXPORTS = [
     "lat_pcg_bsr_dist", "lat_p2p_arena_create", "lat_p2p_attach", "lat_p2p_destroy", "lat_assemble_cells_bsr",
     "lat_cell_quadform", "lat_schur_batch_struts",
     "lat_greedy_basis", "lat_upper_solve", "lat_basis_project", "lat_rbf_fit", "lat_rbf_eval", "lat_alpha_lookup",
-    "lat_basis_prepare", "lat_basis_expand",
+    "lat_basis_prepare", "lat_basis_expand", "lat_alpha_simplex",
 ]
 
 
@@ -145,6 +145,7 @@ def load():
     lib.lat_rbf_fit.argtypes = [vp, vp, i32, i32, vp, i32, dbl, vp]
     lib.lat_rbf_eval.argtypes = [vp, vp, i32, i32, vp, i32, vp, i64, vp, vp]
     lib.lat_alpha_lookup.argtypes = [vp, i32, vp, i32, i32, vp, i32, vp, i64, vp]
+    lib.lat_alpha_simplex.argtypes = [vp, vp, vp, i32, i32, vp, i32, vp, i32, vp, i64, vp]
     lib.lat_basis_prepare.argtypes = [vp, vp, i64, i32, i32, vp]
     lib.lat_basis_expand.argtypes = [vp, vp, i32, i64, vp, i64, i32, vp]
     for name in EXPORTS:

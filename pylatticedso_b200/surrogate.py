@@ -9,7 +9,7 @@ return values, every number computed by ``csrc/lattice_surrogate.cu``:
 | ``greedy_algorithm.project_to_reduced_basis`` (:233-266)                 | :func:`project_to_reduced_basis` |
 | ``save_reduced_basis`` / ``load_reduced_basis`` / ``find_name_file_reduced_basis`` (:157-231) | same names (npz schema kept) |
 | ``utils_rbf.ThinPlateSplineRBF`` (utils_rbf.py:13-144)                   | :class:`ThinPlateSplineRBF` |
-| ``LatticeSim.get_schur_complement_from_reduced_basis_batch`` (lattice_sim.py:921-978), ``..._from_reduced_basis`` (:980-1018), ``_compute_schur_gradients_RBF`` (:1056-1082), ``evaluate_alphas_linear_surrogate`` (:755-807, 1-D branch) | :class:`SchurSurrogate` and the ``lattice_*`` drop-ins bound by ``install.patch_reference`` |
+| ``LatticeSim.get_schur_complement_from_reduced_basis_batch`` (lattice_sim.py:921-978), ``..._from_reduced_basis`` (:980-1018), ``_compute_schur_gradients_RBF`` (:1056-1082), ``evaluate_alphas_linear_surrogate`` (:755-807) | :class:`SchurSurrogate` and the ``lattice_*`` drop-ins bound by ``install.patch_reference`` |
 
 There is no CPU fallback: without the CUDA library / a GPU every entry point raises ``LatticeB200Error``.
 """
@@ -229,6 +229,12 @@ class SchurSurrogate:
         self._X = _dev(self.ctx, self.list_elements)
         self._A = _dev(self.ctx, self.alpha_train)
         self.rbf = ThinPlateSplineRBF(self.list_elements, self.alpha_train, ctx=self.ctx) if kind == "RBF" else None
+        self._tri = None
+        if kind == "linear" and self.d > 1:
+            # set-up geometry on the host: the Qhull triangulation scipy's LinearNDInterpolator builds (lattice_sim.py:797)
+            from scipy.spatial import Delaunay
+            tri = Delaunay(self.list_elements)
+            self._tri = (_dev(self.ctx, tri.simplices, np.int32), _dev(self.ctx, tri.transform), int(tri.simplices.shape[0]))
 
     def _queries(self, params):
         xq = np.asarray(params, dtype=np.float64)
@@ -243,6 +249,12 @@ class SchurSurrogate:
         if self.kind == "RBF":
             return self.rbf.evaluate_device(xq)
         out = torch.empty((xq.shape[0], self.k), dtype=torch.float64, device=self.ctx.device)
+        if self._tri is not None:
+            simplices, transform, ns = self._tri
+            self.ctx.check(self.ctx.lib.lat_alpha_simplex(self.ctx.h, _ptr(simplices), _ptr(transform), ns, self.d, _ptr(self._X),
+                                                          self.list_elements.shape[0], _ptr(self._A), self.k, _ptr(xq),
+                                                          xq.shape[0], _ptr(out)))
+            return out
         self.ctx.check(self.ctx.lib.lat_alpha_lookup(self.ctx.h, 0 if self.kind == "nearest_neighbor" else 1, _ptr(self._X),
                                                      self.list_elements.shape[0], self.d, _ptr(self._A), self.k, _ptr(xq),
                                                      xq.shape[0], _ptr(out)))

@@ -79,6 +79,16 @@ def main():
     q2 = np.vstack([rng.uniform(x2.min(0), x2.max(0), (20, 2)), x2[[0, 17, 99]]])
     r2 = rbf.ThinPlateSplineRBF(x2, a2)
     out.update({"x2": x2, "a2": a2, "q2": q2, "r2_eval": r2.evaluate(q2), "r2_grad": r2.gradient(q2)})
+    # --- 2-D "linear" surrogate (scipy Delaunay interpolation inside the hull, nearest neighbour outside,
+    #     lattice_sim.py:794-807) through the reference's own method, incl. queries outside the convex hull
+    q2l = np.vstack([q2, x2.min(0) - 0.01, x2.max(0) + 0.02, [x2[:, 0].mean(), x2[:, 1].max() + 0.05]])
+    me = types.SimpleNamespace(reduce_basis_dict={"list_elements": x2}, alpha_coefficients_greedy=a2, _verbose=0)
+    f = ls.LatticeSim.evaluate_alphas_linear_surrogate
+    f = getattr(f, "__wrapped__", f)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        out["l2_eval"] = np.stack([np.asarray(f(me, list(q))) for q in q2l])
+    out["q2l"] = q2l
     np.savez_compressed(os.path.join(HERE, "surrogate_ref.npz"), **out)
     print({k: np.asarray(v).shape for k, v in out.items()})
 

@@ -163,7 +163,7 @@ def test_latticesim_drop_ins_on_a_duck_typed_lattice(ctx, ref, rb6):
 
 def test_error_paths_and_edges(ctx, rb6):
     """Loud failures instead of silent garbage: duplicate RBF centres, a rank-deficient basis in the projection, the
-    N-parameter linear surrogate (not a device kernel); empty query batches are a no-op."""
+    1-D look-up called with two parameters; empty query batches are a no-op."""
     import torch
     from pylatticedso_b200 import surrogate
     from pylatticedso_b200.lib import LatticeB200Error
@@ -172,11 +172,10 @@ def test_error_paths_and_edges(ctx, rb6):
     B = np.random.default_rng(0).standard_normal((36, 2))
     with pytest.raises(LatticeB200Error, match="rank deficient"):
         surrogate.project_to_reduced_basis({0: np.ones((6, 6))}, np.column_stack([B[:, 0], B[:, 0]]), ctx=ctx)
-    two_d = {"basis_reduced_ortho": rb6["basis_reduced_ortho"], "alpha_ortho": np.zeros((5, 4)),
-             "list_elements": np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0], [1.0, 1.0]])}
-    s = surrogate.SchurSurrogate(two_d, "linear", ctx=ctx)
-    with pytest.raises(LatticeB200Error, match="one parameter"):
-        s.schur_batch([[0.5, 0.5]])
+    with pytest.raises(LatticeB200Error, match="one parameter"):       # the C entry point of the 1-D look-up says so
+        x2 = surrogate._dev(ctx, np.zeros((4, 2)))
+        ctx.check(ctx.lib.lat_alpha_lookup(ctx.h, 1, surrogate._ptr(x2), 4, 2, surrogate._ptr(x2), 2, surrogate._ptr(x2), 4,
+                                           surrogate._ptr(x2)))
     with pytest.raises(NotImplementedError):
         surrogate.SchurSurrogate(rb6, "kriging", ctx=ctx)
     s = surrogate.SchurSurrogate(rb6, "RBF", ctx=ctx)
@@ -199,3 +198,14 @@ def test_rbf_many_centres_and_three_parameters(ctx):
     np.testing.assert_allclose(r.evaluate(q), so.tps_evaluate(X, wcp, q), rtol=0, atol=1e-7)
     np.testing.assert_allclose(r.gradient(q), so.tps_gradient(X, wcp, q), rtol=0, atol=1e-6)
     np.testing.assert_allclose(r.evaluate(X[:10]), Y[:10], rtol=0, atol=1e-6)        # interpolation at the centres
+
+
+def test_linear_surrogate_in_two_parameters_against_the_reference(ctx, ref):
+    """evaluate_alphas_linear_surrogate, N-parameter branch (lattice_sim.py:794-807): Delaunay interpolation inside the
+    hull of the 100 centres of the reference's BCC+Hybrid4 set, nearest centre outside (three of the queries)."""
+    from pylatticedso_b200 import surrogate
+    k = ref["a2"].shape[1]
+    s = surrogate.SchurSurrogate({"basis_reduced_ortho": np.eye(36, k), "alpha_ortho": ref["a2"].T, "list_elements": ref["x2"]},
+                                 "linear", ctx=ctx)
+    got = s.alphas_device(s._queries(ref["q2l"])).cpu().numpy()
+    np.testing.assert_allclose(got, ref["l2_eval"], rtol=0, atol=1e-12 * np.abs(ref["l2_eval"]).max())

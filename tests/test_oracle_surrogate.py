@@ -77,3 +77,8 @@ def test_rbf_2d(ref):
     np.testing.assert_allclose(so.tps_evaluate(ref["x2"], wcp, ref["q2"]), ref["r2_eval"], rtol=0, atol=1e-9 * scale)
     np.testing.assert_allclose(so.tps_gradient(ref["x2"], wcp, ref["q2"]), ref["r2_grad"], rtol=0,
                                atol=1e-9 * np.abs(ref["r2_grad"]).max())
+
+
+def test_linear_nd(ref):
+    np.testing.assert_allclose(so.alphas_linear_nd(ref["x2"], ref["a2"], ref["q2l"]), ref["l2_eval"], rtol=0,
+                               atol=1e-12 * np.abs(ref["l2_eval"]).max())
