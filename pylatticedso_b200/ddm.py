@@ -176,3 +176,37 @@ def compliance_gradient_cells(lattice, ctx=None, adjoint=None):
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(ctx.device)
     q = ctx.cell_quadform(t(np.stack(mats)), t(index), t(U), None if V is None else t(V))
     return q.cpu().numpy()
+
+
+def regular_bcc_interface(ctx, n_cells, cell_radii, elements_per_strut, young, nu, kappa=0.9):
+    """Interface problem of a regular BCC lattice with one radius per cell (BASELINE configs[3]: BCC 60^3 with per-cell
+    radii), built without an object graph: batched per-cell condensation (star-cell kernel) + the assembled interface
+    operator over the (n+1)^3 cell corners.  Interface node (i, j, k) has index (i (ny+1) + j)(nz+1) + k.
+    Returns (InterfaceProblem, corner_xyz [n_corners, 3], timings dict in ms)."""
+    import torch
+    from .mesh import synthetic_lattice
+    from .schur import bcc_cell_order_nodes, synthetic_cell_batch
+    nx, ny, nz = (int(v) for v in n_cells)
+    radii = np.asarray(cell_radii, dtype=np.float64).ravel()
+    if radii.shape[0] != nx * ny * nz:
+        raise ValueError("one radius per cell, in cell-index (i-major) order")
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    e = [ev() for _ in range(4)]
+    e[0].record()
+    batch, _ = synthetic_cell_batch(ctx, "BCC", radii, elements_per_strut, young, nu)
+    e[1].record()
+    S = batch.schur()
+    e[2].record()
+    unit = synthetic_lattice("BCC", (1, 1, 1), [1.0])
+    order = bcc_cell_order_nodes(unit.pxyz, (0, 1, 0, 1, 0, 1))
+    off = np.rint(unit.pxyz[order]).astype(np.int64)                          # (8, 3) corner offsets in boundary order
+    ci, cj, ck = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    ci, cj, ck = ci.ravel(), cj.ravel(), ck.ravel()                            # i-major == cell.index order
+    cell_nodes = ((ci[:, None] + off[None, :, 0]) * (ny + 1) + (cj[:, None] + off[None, :, 1])) * (nz + 1) + (ck[:, None] + off[None, :, 2])
+    prob = InterfaceProblem(ctx, cell_nodes.astype(np.int32), (nx + 1) * (ny + 1) * (nz + 1), S)
+    e[3].record()
+    torch.cuda.synchronize()
+    gi, gj, gk = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), np.arange(nz + 1), indexing="ij")
+    corner_xyz = np.stack([gi.ravel(), gj.ravel(), gk.ravel()], axis=1).astype(np.float64)
+    return prob, corner_xyz, dict(setup_ms=e[0].elapsed_time(e[1]), condense_ms=e[1].elapsed_time(e[2]),
+                                  interface_assembly_ms=e[2].elapsed_time(e[3]))
