@@ -20,13 +20,24 @@ from .mesh import NDOF
 
 
 def cell_pair_elements(cell_nodes):
-    """All unordered node pairs of every cell as virtual 2-node elements (pattern input)."""
-    cn = np.asarray(cell_nodes, dtype=np.int64)
-    nbn = cn.shape[1]
+    """All unordered node pairs of every cell as virtual 2-node elements (pattern input), pair-major: one strided
+    column copy per pair (28 for eight corner nodes) instead of a fancy-indexed gather of every entry
+    (6 M pairs at BASELINE config 3: 115 -> ~15 ms on the host)."""
+    cn = np.ascontiguousarray(cell_nodes, dtype=np.int32)
+    nc, nbn = cn.shape
     ia, ib = np.triu_indices(nbn, k=1)
-    a, b = cn[:, ia].ravel(), cn[:, ib].ravel()
-    ok = (a >= 0) & (b >= 0) & (a != b)
-    return a[ok].astype(np.int32), b[ok].astype(np.int32)
+    a = np.empty((ia.shape[0], nc), dtype=np.int32)
+    b = np.empty((ia.shape[0], nc), dtype=np.int32)
+    for p, (i, j) in enumerate(zip(ia, ib)):
+        a[p] = cn[:, i]
+        b[p] = cn[:, j]
+    a, b = a.ravel(), b.ravel()
+    ok = a != b
+    if cn.min(initial=0) < 0:
+        ok &= (a >= 0) & (b >= 0)
+    if not ok.all():
+        a, b = a[ok], b[ok]
+    return a, b
 
 
 class InterfaceProblem:
