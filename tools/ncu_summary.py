@@ -14,6 +14,10 @@ WANT = [
     "dram__bytes_read.sum", "dram__bytes_write.sum",
     "dram__throughput.avg.pct_of_peak_sustained_elapsed",
     "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+    "LTS.TriageCompute.lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "LTS.TriageCompute.lts__t_sector_throughput_srcunit_tex.avg.pct_of_peak_sustained_elapsed",
+    "derived__lts__lts2xbar_bytes.sum.per_second", "derived__lts__lts2xbar_bytes.sum.peak_sustained",
+    "l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__m_xbar2l1tex_read_bytes.sum.per_second",
     "l1tex__throughput.avg.pct_of_peak_sustained_active",
     "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed",
     "sm__warps_active.avg.pct_of_peak_sustained_active",
