@@ -209,3 +209,41 @@ def test_linear_surrogate_in_two_parameters_against_the_reference(ctx, ref):
                                  "linear", ctx=ctx)
     got = s.alphas_device(s._queries(ref["q2l"])).cpu().numpy()
     np.testing.assert_allclose(got, ref["l2_eval"], rtol=0, atol=1e-12 * np.abs(ref["l2_eval"]).max())
+
+
+def test_linear_surrogate_three_parameters_against_scipy(ctx):
+    """k_alpha_simplex in three parameters (tetrahedra) on scattered centres: scipy's LinearNDInterpolator inside the
+    hull, nearest centre outside -- the oracle's restatement of lattice_sim.py:794-807."""
+    from oracle import surrogate_oracle as so
+    from pylatticedso_b200 import surrogate
+    rng = np.random.default_rng(17)
+    X = rng.uniform(0.0, 1.0, (60, 3))
+    A = rng.standard_normal((60, 7))
+    s = surrogate.SchurSurrogate({"basis_reduced_ortho": np.eye(36, 7), "alpha_ortho": A.T, "list_elements": X}, "linear", ctx=ctx)
+    Q = np.vstack([rng.uniform(0.1, 0.9, (200, 3)), rng.uniform(-0.5, 1.5, (50, 3))])
+    got = s.alphas_device(s._queries(Q)).cpu().numpy()
+    want = so.alphas_linear_nd(X, A, Q)
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-11 * np.abs(want).max())
+
+
+def test_greedy_on_a_larger_synthetic_snapshot_set_equals_the_oracle(ctx):
+    """120 snapshots of a smooth 2-parameter family of symmetric 24x24 matrices: same selected snapshots, basis size,
+    basis and coefficients as the oracle's restatement of the reference loop."""
+    from oracle import surrogate_oracle as so
+    from pylatticedso_b200 import surrogate
+    rng = np.random.default_rng(2)
+    B0, B1, B2, B3 = (0.5 * (M_ + M_.T) for M_ in rng.standard_normal((4, 24, 24)))
+    sd = {}
+    for a in np.linspace(0.1, 1.0, 12):
+        for b in np.linspace(0.2, 0.8, 10):
+            sd[(round(float(a), 6), round(float(b), 6))] = B0 + a * B1 + b * b * B2 + np.sin(3 * a * b) * B3 + 1e-3 * np.exp(a) * np.eye(24)
+    got = surrogate.reduce_basis_greedy(sd, 1e-8, verbose=0, ctx=ctx)
+    want = so.greedy_reduced_basis(sd, 1e-8)
+    assert got[3].shape == want[3].shape and (got[0] == want[0]).all()
+    assert np.abs(got[3] - want[3]).max() < 1e-7                       # later basis vectors amplify rounding (deflation)
+    # what matters downstream: the reconstruction of every snapshot from (basis, alpha)
+    keys = sorted(sd)
+    rec = got[3] @ got[4]
+    for j, k_ in enumerate(keys):
+        S = rec[:, j].reshape(24, 24, order="F")
+        assert np.abs(S - sd[k_]).max() < 1e-6 * np.abs(sd[k_]).max()
