@@ -674,6 +674,24 @@ def run_b200(args):
         s_ms = a.elapsed_time(b_)
         extra = dict(grad_eps=mesh.n_elems / (g_ms * 1e-3), grad_ms=g_ms, schur_cps=n_sc / (s_ms * 1e-3), schur_ms=s_ms, schur_cells=n_sc)
         del batch
+        # N4: surrogate Schur complements of BASELINE config 4's 216 000 cells from the reference's stored BCC basis
+        from pylatticedso_b200 import surrogate
+        rb = np.load(os.path.join(ROOT, "tests", "golden", "reduced_basis_BCC_tol_1e-6.npz"))
+        sur = surrogate.SchurSurrogate(rb, "RBF", ctx=ctx)
+        xq = surrogate._dev(ctx, np.random.default_rng(44).uniform(0.01, 0.1, (216000, 1)))
+        s_out = torch.empty((216000, 48, 48), dtype=torch.float64, device=dev)
+        sur.expand_device(sur.alphas_device(xq), out=s_out)
+        a, b_ = ev(), ev()
+        a.record(); sur.expand_device(sur.alphas_device(xq), out=s_out); b_.record(); torch.cuda.synchronize()
+        extra["surrogate_ms"] = a.elapsed_time(b_)
+        del s_out, sur
+        torch.cuda.empty_cache()
+        # BASELINE configs[3] end to end through the DDM path, against the full FEM solve of the same lattice
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("ddm_config3", os.path.join(ROOT, "tools", "ddm_config3.py"))
+        ddm3 = importlib.util.module_from_spec(spec); spec.loader.exec_module(ddm3)
+        extra["ddm3"] = ddm3.run(ctx, 60, 1, tol=1e-10, verbose=False)
+        torch.cuda.empty_cache()
     # ---- parity block (driver-visible): see parity_single / parity_sharded
     if distributed:
         parity = parity_sharded(ctx, dfem, mesh, fixed, g, f, rank)
@@ -833,6 +851,20 @@ def run_b200(args):
         x_ = res["extra"]
         line["gradient"] = {"value": x_["grad_eps"], "unit": "elements/s", "ms": x_["grad_ms"],
                             "note": "lat_compliance_grad (adjoint compliance sensitivity, 168 B/element) on the bench mesh"}
+        line["surrogate"] = {"value": 216000 / (x_["surrogate_ms"] * 1e-3), "unit": "cells/s", "ms": x_["surrogate_ms"], "cells": 216000,
+                             "note": "N4: thin-plate-spline RBF coefficients + basis @ alphas on the FP64 tensor cores (DMMA), 48x48 "
+                                     "Schur complements from the reference's stored BCC reduced basis (k = 5)"}
+        d3 = x_["ddm3"]
+        line["ddm_config3"] = {"workload": "BCC 60x60x60 = 216000 cells, per-cell radii (rng 44), 1 element per strut, compression",
+                               "interface_dof": d3["interface_dof"], "condense_ms": d3["condense_ms"],
+                               "interface_assembly_ms": d3["interface_assembly_ms"], "pcg_iters": d3["ddm_iters"],
+                               "pcg_ms": d3["ddm_pcg_ms"], "full_fem_dof": d3["fem_dof"], "full_fem_pcg_ms": d3["fem_pcg_ms"],
+                               "full_fem_iters": d3["fem_iters"], "u_rel_vs_full_fem": d3["u_rel"], "R_rel_vs_full_fem": d3["R_rel"],
+                               "note": "BASELINE configs[3] end to end (tools/ddm_config3.py): batched condensation -> assembled "
+                                       "interface operator -> block-Jacobi PCG, both solves to 1e-10; static condensation is exact, "
+                                       "so the corner displacements must equal the full FEM solve"}
+        parity["ddm_config3_u_rel"] = d3["u_rel"]
+        parity["ok"] = bool(parity["ok"] and d3["u_rel"] < 1e-7 and d3["ddm_info"] == 0)
         line["schur"] = {"value": x_["schur_cps"], "unit": "cells/s", "ms": x_["schur_ms"], "cells": x_["schur_cells"],
                          "note": "lat_schur_batch_chains: BCC cells at the reference mesh density (18 elements per strut, "
                                  "870 DOF -> 48 boundary DOF), strut pre-pass + joint-only condensation"}
