@@ -199,8 +199,10 @@ class CellBatch:
         # BCC) also take single-element "chains" and carry the sensitivities through the pre-pass
         ch = strut_chains(np.asarray(xyz)[0], len0, len1, self.n_bnd_nodes)
         if ch is None:
+            # single-element struts: star cells and cells without an interior joint (Octet) still go through the
+            # strut path (half-warp star kernel / direct assembly of the joint-only matrix)
             tr = strut_chains(np.asarray(xyz)[0], len0, len1, self.n_bnd_nodes, allow_trivial=True)
-            ch = tr if is_star(tr, self.n_bnd_nodes) else None
+            ch = tr if (tr is not None and (is_star(tr, self.n_bnd_nodes) or tr["n_joints"] == self.n_bnd_nodes)) else None
         self.star = is_star(ch, self.n_bnd_nodes)
         self.chains = None if ch is None else _chains_to_device(ch, dev)
         self.chain_group = None

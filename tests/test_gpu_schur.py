@@ -187,3 +187,26 @@ def test_ddm_regular_bcc_per_cell_radii_equals_full_fem(ctx):
     out = mod.run(ctx, 8, 3, tol=1e-12, verbose=False)
     assert out["ddm_info"] in (0, 5) and out["u_rel"] < 1e-8 and out["R_rel"] < 1e-8
     assert out["interface_dof"] == 6 * 9 ** 3 and out["fem_dof"] > 10 * out["interface_dof"]
+
+
+@pytest.mark.parametrize("m_", [1, 3])
+def test_octet_cells_without_interior_joint_direct_path(ctx, m_):
+    """Octet cells (14 joints, all on the cell boundary, 84 boundary DOF): the strut path assembles S directly
+    (k_schur_direct); equal to the dense condensation of all interior nodes and to the oracle."""
+    from oracle import lattice_oracle as orc
+    from pylatticedso_b200 import mesh as M
+    from pylatticedso_b200.schur import synthetic_cell_batch
+    rng = np.random.default_rng(5)
+    radii = rng.uniform(0.02, 0.06, 40)
+    batch, bnd = synthetic_cell_batch(ctx, "Octet", radii, m_, E_MOD, NU)
+    assert batch.chains is not None and batch.chains["n_joints"] == len(bnd) == 14 and not batch.star
+    S = batch.schur().cpu().numpy()
+    Sd = batch.schur(use_chains=False).cpu().numpy()
+    assert S.shape == (40, 84, 84)
+    assert np.abs(S - Sd).max() < 1e-12 * np.abs(Sd).max()
+    cell = M.mesh_from_synthetic(M.synthetic_lattice("Octet", (1, 1, 1), [1.0]), m_)
+    en = np.stack([cell.en0, cell.en1], 1).astype(np.int64)
+    bdofs = (np.asarray(bnd)[:, None] * 6 + np.arange(6)[None, :]).ravel()
+    K = orc.assemble_csr(cell.xyz, en, np.full(cell.n_elems, radii[7]), E_MOD, NU)
+    So = orc.schur_complement(K, bdofs) if m_ > 1 else K.toarray()[np.ix_(bdofs, bdofs)]
+    assert np.abs(S[7] - So).max() < 1e-11 * np.abs(So).max()
