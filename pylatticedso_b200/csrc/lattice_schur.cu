@@ -1044,15 +1044,18 @@ __global__ void __launch_bounds__(16 * star_cells_per_cta(GRAD), 3) k_schur_star
 // row by row -- lane h owns columns 4h..4h+3 (+128, ...) of every row, a block row of six rows at a time, 256-bit
 // stores of contiguous pieces; pair[i][j] = strut that joins joints i and j (its stored block is (a -> b): the other
 // direction reads it transposed) or -1.  The dense kernel needs 5.5-9.4 ms for 64 000 Octet cells (0.06-0.10 of HBM).
-static constexpr int DIRECT_WARPS = 4;
+static constexpr int DIRECT_WARPS = 8;    // 8 warps (1.84 ms) against 4 (2.11 ms) and 2 (2.12 ms) for 64 000 Octet cells
 __global__ void __launch_bounds__(32 * DIRECT_WARPS) k_schur_direct(
-    const SupCoef* __restrict__ sup, const int32_t* __restrict__ ca, const int32_t* __restrict__ cb,
+    const SupCoef* __restrict__ sup, const int32_t* __restrict__ inc_ptr, const int16_t* __restrict__ inc,
     const int16_t* __restrict__ pair, int64_t n_cells, int ns, int nj, double* __restrict__ S) {
   extern __shared__ __align__(16) double direct_smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int per_cell = (ns + nj) * 36;
   double* sB = direct_smem + (size_t)wid * per_cell;      // [ns][36] coupling blocks (row joint a, column joint b)
   double* sD = sB + ns * 36;                               // [nj][36] diagonal blocks
+  __shared__ double sZ[36];                                // the block of a joint pair without a strut
+  if (threadIdx.x < 36) sZ[threadIdx.x] = 0.0;
+  __syncthreads();
   const int nB = 6 * nj;
   for (int64_t cell = (int64_t)blockIdx.x * DIRECT_WARPS + wid; cell < n_cells; cell += (int64_t)gridDim.x * DIRECT_WARPS) {
     __syncwarp();
@@ -1061,10 +1064,11 @@ __global__ void __launch_bounds__(32 * DIRECT_WARPS) k_schur_direct(
       double q[36];
 #pragma unroll
       for (int e = 0; e < 36; ++e) q[e] = 0.0;
-      for (int k = 0; k < ns; ++k) {
-        const int a = ca[k], b = cb[k];
-        if (a == j) sup_block_accum(sup[cell * ns + k], 0, 0, q);
-        if (b == j) sup_block_accum(sup[cell * ns + k], 1, 1, q);
+      // the struts of joint j in ascending strut order (fixed summation order); inc = +(k+1): end a, -(k+1): end b
+      for (int t = inc_ptr[j]; t < inc_ptr[j + 1]; ++t) {
+        const int p = inc[t];
+        const int e = p > 0 ? 0 : 1;
+        sup_block_accum(sup[cell * ns + (p > 0 ? p - 1 : -p - 1)], e, e, q);
       }
 #pragma unroll
       for (int e = 0; e < 36; ++e) sD[j * 36 + e] = q[e];
@@ -1080,27 +1084,28 @@ __global__ void __launch_bounds__(32 * DIRECT_WARPS) k_schur_direct(
       }
       const int ncol = nB - c0 < 4 ? nB - c0 : 4;
       double* out = S + cell * (int64_t)nB * nB + c0;
+      // rows are multiples of 32 bytes when nB % 4 == 0: then every full piece of this lane is a 256-bit store
+      const bool fast = ncol == 4 && (nB & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 31) == 0;
       for (int i = 0; i < nj; ++i) {
-        // the lane's (at most two) column joints against row joint i: where its entries come from
+        // the lane's (at most two) column joints against row joint i: base + a * sa + offset, or the zero block
         const double* src[4];
-        int stride_a[4], stride_b[4];
+        int sa[4], ob[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int j = jq[q];
-          if (j == i) { src[q] = sD + i * 36; stride_a[q] = 6; stride_b[q] = 1; }
-          else {
-            const int p = pair[i * nj + j];                 // strut k: +k+1 if i is its end a, -(k+1) if i is its end b
-            if (p > 0) { src[q] = sB + (p - 1) * 36; stride_a[q] = 6; stride_b[q] = 1; }
-            else if (p < 0) { src[q] = sB + (-p - 1) * 36; stride_a[q] = 1; stride_b[q] = 6; }    // transposed
-            else { src[q] = nullptr; stride_a[q] = 0; stride_b[q] = 0; }
-          }
+          const int p = j == i ? 0 : pair[i * nj + j];      // strut k: +(k+1) if i is its end a, -(k+1) if i is its end b
+          if (j == i) { src[q] = sD + i * 36; sa[q] = 6; ob[q] = bq[q]; }
+          else if (p > 0) { src[q] = sB + (p - 1) * 36; sa[q] = 6; ob[q] = bq[q]; }
+          else if (p < 0) { src[q] = sB + (-p - 1) * 36; sa[q] = 1; ob[q] = 6 * bq[q]; }     // transposed
+          else { src[q] = sZ; sa[q] = 0; ob[q] = 0; }
         }
 #pragma unroll
         for (int a = 0; a < 6; ++a) {
           double v[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) v[q] = src[q] ? src[q][a * stride_a[q] + bq[q] * stride_b[q]] : 0.0;
-          star_store4(out, v, ncol);
+          for (int q = 0; q < 4; ++q) v[q] = src[q][a * sa[q] + ob[q]];
+          if (fast) asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(out), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+          else star_store4(out, v, ncol);
           out += nB;
         }
       }
@@ -1159,9 +1164,21 @@ extern "C" int lat_schur_batch_struts(lat_ctx* ctx, const double* xyz, const int
       const int ns = n_chains;
       SupCoef* sup = lat_buf<SupCoef>(ctx, "schur_sup", (size_t)n_cells * ns);
       int16_t* dpair = lat_buf<int16_t>(ctx, "schur_pair", pair.size());
-      if (!sup || !dpair) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+      int32_t* dincp = lat_buf<int32_t>(ctx, "schur_incp", (size_t)n_joints + 1);
+      int16_t* dinc = lat_buf<int16_t>(ctx, "schur_inc", (size_t)2 * ns);
+      if (!sup || !dpair || !dincp || !dinc) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+      std::vector<int32_t> incp(n_joints + 1, 0);
+      std::vector<int16_t> incv((size_t)2 * ns);
+      for (int k = 0; k < ns; ++k) { incp[ca[k] + 1]++; incp[cb[k] + 1]++; }
+      for (int j = 0; j < n_joints; ++j) incp[j + 1] += incp[j];
+      {
+        std::vector<int32_t> fill(incp.begin(), incp.end() - 1);
+        for (int k = 0; k < ns; ++k) { incv[fill[ca[k]]++] = (int16_t)(k + 1); incv[fill[cb[k]]++] = (int16_t)(-(k + 1)); }
+      }
       LAT_CUDA(ctx, cudaMemcpyAsync(dpair, pair.data(), pair.size() * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
-      LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // `pair` goes out of scope
+      LAT_CUDA(ctx, cudaMemcpyAsync(dincp, incp.data(), incp.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+      LAT_CUDA(ctx, cudaMemcpyAsync(dinc, incv.data(), incv.size() * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+      LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the host tables go out of scope
       LAT_LAUNCH(ctx, k_chain_condense, (unsigned)ceil_div(n_cells * ns, 128), 128, 0, xyz, len0, len1, rad, n_cells, n_loc_nodes,
                  n_loc_elem, chain_ptr, chain_elem, chain_flip, ns, young, nu, kappa, sup);
       const size_t smem = (size_t)DIRECT_WARPS * (ns + n_joints) * 36 * sizeof(double);
@@ -1170,7 +1187,7 @@ extern "C" int lat_schur_batch_struts(lat_ctx* ctx, const double* xyz, const int
         int64_t grid = ceil_div(n_cells, DIRECT_WARPS);
         const int64_t cap = (int64_t)ctx->sm_count * 16;
         if (grid > cap) grid = cap;
-        LAT_LAUNCH(ctx, k_schur_direct, (unsigned)grid, 32 * DIRECT_WARPS, smem, sup, chain_a, chain_b, dpair, n_cells, ns, n_joints, S);
+        LAT_LAUNCH(ctx, k_schur_direct, (unsigned)grid, 32 * DIRECT_WARPS, smem, sup, dincp, dinc, dpair, n_cells, ns, n_joints, S);
         return LAT_OK;
       }
     }
