@@ -37,7 +37,7 @@ __device__ __forceinline__ double dot6(const double2& a0, const double2& a1, con
 // A block is 18 pieces of 16 bytes (piece p = scalar row p/3, column pair p%3).  Lane r of the group loads pieces
 // r, 6+r, 12+r: the six lanes together read 96 CONTIGUOUS bytes per instruction (the row-per-lane mapping read
 // 6 x 16 B at stride 48 B = three 128-byte lines per block and instruction, which made the product kernels L1-wavefront
-// bound: profiles/r02_persist_ncu.txt), and every lane needs only ONE 16-byte piece of x (column pair c = r%3)
+// bound: profiles/r02_ncu_persist_before_l2_policy.txt), and every lane needs only ONE 16-byte piece of x (column pair c = r%3)
 // instead of all 48 bytes.  The lane accumulates partial sums of scalar rows h, 2+h, 4+h (h = r/3) over the blocks of the
 // row; at the end of the row the three lanes with the same h are added in a fixed order and lane (h, c) keeps the
 // total of scalar row 2c+h.  16 instead of 24 registers per block in flight, ~6 instead of ~13 L1 wavefronts per block.

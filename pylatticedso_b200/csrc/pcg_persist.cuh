@@ -8,7 +8,7 @@
 //   * one CTA per SM (cooperative launch); the block rows are dealt to the CTAs in chunks of 16 rows, round robin, so
 //     every CTA holds the same mix of long rows (joints) and short rows (strut-interior nodes): with contiguous
 //     byte-balanced ranges the joint-only CTAs needed 28 us per product and the others 18 us, and the reverse in the
-//     update phase (profiles/r02_persist_trace.txt) -- and every phase ends in a grid barrier;
+//     update phase (profiles/r02_persist_trace_contiguous_partition.txt) -- and every phase ends in a grid barrier;
 //   * r, p, s, w AND the preconditioner (reciprocal diagonal or the 21 packed entries of the inverse 6x6 diagonal
 //     block) of the owned rows live in shared memory for the whole solve, so the update phase reads nothing from
 //     global memory but its own u and x; the CTA's slice of rowptr and colidx is cached in shared memory too, so
@@ -154,7 +154,7 @@ __device__ __forceinline__ void st_relaxed_gpu_u32(unsigned int* p, unsigned int
 // All-to-all flags with PRIVATE inboxes: CTA c stores its epoch into slot c of every CTA's inbox (G 4-byte stores by G
 // threads, each behind its own release fence) and polls only its own inbox (5 lines nobody else reads).  The first
 // version had one flag per CTA that all G x G pollers read: 5 hot lines, 5.5 us per barrier
-// (profiles/r02_persist_trace.txt); the acquire fence afterwards drops the SM's L1 lines (CCTL.IVALL).
+// (profiles/r02_persist_trace_contiguous_partition.txt); the acquire fence afterwards drops the SM's L1 lines (CCTL.IVALL).
 static constexpr int PERSIST_INBOX_STRIDE = 160;     // u32 slots per inbox row (G <= 160), 640 B = 5 lines
 static constexpr long long PERSIST_SPIN_LIMIT_SYS = 1ll << 25;   // cross-GPU waits: the peers may start their kernel later
 struct PersistShared {
