@@ -9,10 +9,15 @@
 //     every CTA holds the same mix of long rows (joints) and short rows (strut-interior nodes): with contiguous
 //     byte-balanced ranges the joint-only CTAs needed 28 us per product and the others 18 us, and the reverse in the
 //     update phase (profiles/r02_persist_trace_contiguous_partition.txt) -- and every phase ends in a grid barrier;
-//   * r, p, s, w AND the preconditioner (reciprocal diagonal or the 21 packed entries of the inverse 6x6 diagonal
-//     block) of the owned rows live in shared memory for the whole solve, so the update phase reads nothing from
-//     global memory but its own u and x; the CTA's slice of rowptr and colidx is cached in shared memory too, so
-//     the product phase issues only independent loads (matrix blocks, gathered u) -- no rowptr -> colidx -> u chain;
+//   * r, p, s, w of the owned rows live in shared memory for the whole solve -- and so does the preconditioner while the
+//     total stays below ~160 KB (the product phase needs the rest of the 256 KB as L1 for its gathers of u; at config 1
+//     the Jacobi diagonal fits, the block-Jacobi rows do not and are read from L2 as full FP32 6x6 blocks, three 8-byte
+//     loads per lane); the CTA's slice of rowptr and colidx is cached in shared memory too, so the product phase
+//     issues only independent loads (matrix blocks, gathered u) -- no rowptr -> colidx -> u chain;
+//   * ~44 MB of the matrix stay in L2 from one iteration to the next: the blocks of a fixed set of 16-row classes are
+//     loaded with an evict_last policy, the rest streams evict_first, all past L1 (createpolicy +
+//     ld.global.L1::no_allocate.L2::cache_hint): DRAM traffic 111 -> 40 MB per iteration, product phase 15.4 -> 11.5 us
+//     (profiles/r02_persist_l2keep_ab.txt);
 //   * x stays in global memory (one read-modify-write per iteration, nobody waits for it);
 //   * only u = M^-1 r (gathered by other CTAs) lives in global memory, i.e. in L2;
 //   * product and block-Jacobi preconditioner both use the transposed-piece lane mapping (piece_row / piece_finish
@@ -28,8 +33,9 @@
 //   * the Chronopoulos-Gear recurrences, the stop test, the true-residual safeguard and its restart run inside the
 //     kernel; the host launches once and reads the status block.
 //
-// HBM traffic per iteration: the matrix (+ block-Jacobi inverse); the vectors never leave the SM.  All spins are
-// bounded: a CTA that waits longer than ~1 s reports info = 4 and every CTA leaves.
+// HBM traffic per iteration: the non-resident part of the matrix; the vectors never leave the SM.  Config 1: 23.0 us per
+// iteration (product 11.5 | reduce / barrier B 3.4 | update 5.0 | barrier A 2.7) against 35.5 us for the three-kernel
+// iteration of round 1.  All spins are bounded: a CTA that waits longer than ~1 s reports info = 4 and every CTA leaves.
 //
 // Multi-GPU (template DIST, slab partitions with <= 2 neighbours, every rank's slab on chip): the same kernel runs on
 // every GPU, one cooperative launch per rank, and the two grid synchronisations of an iteration also carry the exchange:
