@@ -210,3 +210,38 @@ def test_octet_cells_without_interior_joint_direct_path(ctx, m_):
     K = orc.assemble_csr(cell.xyz, en, np.full(cell.n_elems, radii[7]), E_MOD, NU)
     So = orc.schur_complement(K, bdofs) if m_ > 1 else K.toarray()[np.ix_(bdofs, bdofs)]
     assert np.abs(S[7] - So).max() < 1e-11 * np.abs(So).max()
+
+
+# strut tables of four more reference geometries (src/pyLatticeDesign/geometries/*.json: constant data)
+_BCCZ = [[0.5, 0.5, 0.5, 1, 1, 1], [0, 0, 0, 0.5, 0.5, 0.5], [0.5, 0.5, 0.5, 1, 1, 0], [0, 0, 1, 0.5, 0.5, 0.5], [0.5, 0.5, 0.5, 0, 1, 0],
+         [1, 0, 1, 0.5, 0.5, 0.5], [0.5, 0.5, 0.5, 0, 1, 1], [1, 0, 0, 0.5, 0.5, 0.5], [0.5, 0.5, 0, 0.5, 0.5, 0.5], [0.5, 0.5, 0.5, 0.5, 0.5, 1]]
+_HYBRID2 = [[0.5, 0, 0, 0.5, 0.5, 0.5], [1, 0, 0.5, 0.5, 0.5, 0.5], [0.5, 0, 1, 0.5, 0.5, 0.5], [0, 0, 0.5, 0.5, 0.5, 0.5], [0.5, 1, 0, 0.5, 0.5, 0.5],
+            [1, 1, 0.5, 0.5, 0.5, 0.5], [0.5, 1, 1, 0.5, 0.5, 0.5], [0, 1, 0.5, 0.5, 0.5, 0.5], [0, 0.5, 0, 0.5, 0.5, 0.5], [0, 0.5, 1, 0.5, 0.5, 0.5],
+            [1, 0.5, 0, 0.5, 0.5, 0.5], [1, 0.5, 1, 0.5, 0.5, 0.5]]
+_CUBIC = [[0, 0, 0, 0, 0, 1], [1, 0, 0, 1, 0, 1], [0, 1, 0, 0, 1, 1], [1, 1, 0, 1, 1, 1], [0, 0, 0, 1, 0, 0], [0, 0, 0, 0, 1, 0], [1, 1, 0, 0, 1, 0],
+          [1, 1, 0, 1, 0, 0], [0, 0, 1, 1, 0, 1], [0, 0, 1, 0, 1, 1], [1, 1, 1, 0, 1, 1], [1, 1, 1, 1, 0, 1]]
+_KELVIN = [[0.5, 0.25, 0, 0.25, 0.5, 0], [0.5, 0.25, 0, 0.75, 0.5, 0], [0.5, 0.75, 0, 0.25, 0.5, 0], [0.5, 0.75, 0, 0.75, 0.5, 0],
+           [0.5, 0.25, 1, 0.25, 0.5, 1], [0.5, 0.25, 1, 0.75, 0.5, 1], [0.5, 0.75, 1, 0.25, 0.5, 1], [0.5, 0.75, 1, 0.75, 0.5, 1],
+           [0.5, 0, 0.25, 0.25, 0, 0.5], [0.5, 0, 0.25, 0.75, 0, 0.5], [0.5, 0, 0.75, 0.25, 0, 0.5], [0.5, 0, 0.75, 0.75, 0, 0.5],
+           [0.5, 1, 0.25, 0.25, 1, 0.5], [0.5, 1, 0.25, 0.75, 1, 0.5], [0.5, 1, 0.75, 0.25, 1, 0.5], [0.5, 1, 0.75, 0.75, 1, 0.5],
+           [0, 0.5, 0.25, 0, 0.25, 0.5], [0, 0.5, 0.25, 0, 0.75, 0.5], [0, 0.5, 0.75, 0, 0.25, 0.5], [0, 0.5, 0.75, 0, 0.75, 0.5],
+           [1, 0.5, 0.25, 1, 0.25, 0.5], [1, 0.5, 0.25, 1, 0.75, 0.5], [1, 0.5, 0.75, 1, 0.25, 0.5], [1, 0.5, 0.75, 1, 0.75, 0.5],
+           [0.5, 0.25, 0, 0.5, 0, 0.25], [0.25, 0.5, 0, 0, 0.5, 0.25], [0.75, 0.5, 0, 1, 0.5, 0.25], [0.5, 0.75, 0, 0.5, 1, 0.25],
+           [0.25, 0, 0.5, 0, 0.25, 0.5], [0.75, 0, 0.5, 1, 0.25, 0.5], [0.75, 1, 0.5, 1, 0.75, 0.5], [0.25, 1, 0.5, 0, 0.75, 0.5],
+           [0.5, 0, 0.75, 0.5, 0.25, 1], [0, 0.5, 0.75, 0.25, 0.5, 1], [0.5, 1, 0.75, 0.5, 0.75, 1], [1, 0.5, 0.75, 0.75, 0.5, 1]]
+
+
+@pytest.mark.parametrize("name,table,n_bnd,kind", [("BCCZ", _BCCZ, 10, "star"), ("Hybrid2", _HYBRID2, 12, "star"),
+                                                   ("Cubic", _CUBIC, 8, "direct"), ("Kelvin", _KELVIN, 24, "direct")])
+def test_more_reference_geometries_take_the_fast_schur_kernels(ctx, name, table, n_bnd, kind):
+    """Star cells beyond BCC and cells without an interior joint beyond Octet (Kelvin: 24 boundary joints, 144 DOF):
+    the strut path (k_schur_star / k_schur_direct) equals the dense condensation of every interior node."""
+    from pylatticedso_b200.schur import synthetic_cell_batch
+    rng = np.random.default_rng(len(table))
+    batch, bnd = synthetic_cell_batch(ctx, np.asarray(table, dtype=float), rng.uniform(0.02, 0.05, 24), 2, E_MOD, NU)
+    assert len(bnd) == n_bnd and batch.chains is not None
+    assert batch.star == (kind == "star") and (batch.chains["n_joints"] == n_bnd) == (kind == "direct")
+    S = batch.schur().cpu().numpy()
+    Sd = batch.schur(use_chains=False).cpu().numpy()
+    assert S.shape == (24, 6 * n_bnd, 6 * n_bnd)
+    assert np.abs(S - Sd).max() < 1e-12 * np.abs(Sd).max()
