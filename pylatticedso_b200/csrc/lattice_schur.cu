@@ -1047,7 +1047,8 @@ __global__ void __launch_bounds__(16 * star_cells_per_cta(GRAD), 3) k_schur_star
 static constexpr int DIRECT_WARPS = 8;    // 8 warps (1.84 ms) against 4 (2.11 ms) and 2 (2.12 ms) for 64 000 Octet cells
 __global__ void __launch_bounds__(32 * DIRECT_WARPS) k_schur_direct(
     const SupCoef* __restrict__ sup, const int32_t* __restrict__ inc_ptr, const int16_t* __restrict__ inc,
-    const int16_t* __restrict__ pair, int64_t n_cells, int ns, int nj, double* __restrict__ S) {
+    const int16_t* __restrict__ pair, int64_t n_cells, int ns, int nj, double* __restrict__ S, int64_t cell_stride,
+    const int32_t* __restrict__ group, int gsel) {
   extern __shared__ __align__(16) double direct_smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int per_cell = (ns + nj) * 36;
@@ -1059,7 +1060,13 @@ __global__ void __launch_bounds__(32 * DIRECT_WARPS) k_schur_direct(
   const int nB = 6 * nj;
   for (int64_t cell = (int64_t)blockIdx.x * DIRECT_WARPS + wid; cell < n_cells; cell += (int64_t)gridDim.x * DIRECT_WARPS) {
     __syncwarp();
-    for (int k = lane; k < ns; k += 32) sup_block(sup[cell * ns + k], 0, 1, sB + k * 36);
+    // sensitivities: S is linear in the super-elements, so dS/dr_g is the SAME assembly applied to the derivative
+    // super-elements of the struts of radius group g (group != nullptr: all other struts contribute nothing)
+    for (int k = lane; k < ns; k += 32) {
+      if (group && group[k] != gsel) {
+        for (int e = 0; e < 36; ++e) sB[k * 36 + e] = 0.0;
+      } else sup_block(sup[cell * ns + k], 0, 1, sB + k * 36);
+    }
     for (int j = lane; j < nj; j += 32) {
       double q[36];
 #pragma unroll
@@ -1067,8 +1074,9 @@ __global__ void __launch_bounds__(32 * DIRECT_WARPS) k_schur_direct(
       // the struts of joint j in ascending strut order (fixed summation order); inc = +(k+1): end a, -(k+1): end b
       for (int t = inc_ptr[j]; t < inc_ptr[j + 1]; ++t) {
         const int p = inc[t];
-        const int e = p > 0 ? 0 : 1;
-        sup_block_accum(sup[cell * ns + (p > 0 ? p - 1 : -p - 1)], e, e, q);
+        const int e = p > 0 ? 0 : 1, k = p > 0 ? p - 1 : -p - 1;
+        if (group && group[k] != gsel) continue;
+        sup_block_accum(sup[cell * ns + k], e, e, q);
       }
 #pragma unroll
       for (int e = 0; e < 36; ++e) sD[j * 36 + e] = q[e];
@@ -1083,7 +1091,7 @@ __global__ void __launch_bounds__(32 * DIRECT_WARPS) k_schur_direct(
         bq[q] = col - 6 * jq[q];
       }
       const int ncol = nB - c0 < 4 ? nB - c0 : 4;
-      double* out = S + cell * (int64_t)nB * nB + c0;
+      double* out = S + cell * cell_stride + c0;
       // rows are multiples of 32 bytes when nB % 4 == 0: then every full piece of this lane is a 256-bit store
       const bool fast = ncol == 4 && (nB & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 31) == 0;
       for (int i = 0; i < nj; ++i) {
@@ -1149,7 +1157,7 @@ extern "C" int lat_schur_batch_struts(lat_ctx* ctx, const double* xyz, const int
   LAT_CUDA(ctx, cudaMemcpyAsync(ca.data(), chain_a, n_chains * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   LAT_CUDA(ctx, cudaMemcpyAsync(cb.data(), chain_b, n_chains * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  if (!dS && n_joints == n_bnd_nodes && n_chains <= 4096) {
+  if (n_joints == n_bnd_nodes && n_chains <= 4096) {
     // no interior joint: S is the assembled joint-only matrix (k_schur_direct); two struts between the same pair of
     // joints are left to the general path
     std::vector<int16_t> pair((size_t)n_joints * n_joints, 0);
@@ -1163,6 +1171,8 @@ extern "C" int lat_schur_batch_struts(lat_ctx* ctx, const double* xyz, const int
     if (simple) {
       const int ns = n_chains;
       SupCoef* sup = lat_buf<SupCoef>(ctx, "schur_sup", (size_t)n_cells * ns);
+      SupCoef* dsup = dS ? lat_buf<SupCoef>(ctx, "schur_dsup", (size_t)n_cells * ns) : nullptr;
+      if (dS && !dsup) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
       int16_t* dpair = lat_buf<int16_t>(ctx, "schur_pair", pair.size());
       int32_t* dincp = lat_buf<int32_t>(ctx, "schur_incp", (size_t)n_joints + 1);
       int16_t* dinc = lat_buf<int16_t>(ctx, "schur_inc", (size_t)2 * ns);
@@ -1179,15 +1189,25 @@ extern "C" int lat_schur_batch_struts(lat_ctx* ctx, const double* xyz, const int
       LAT_CUDA(ctx, cudaMemcpyAsync(dincp, incp.data(), incp.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
       LAT_CUDA(ctx, cudaMemcpyAsync(dinc, incv.data(), incv.size() * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
       LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the host tables go out of scope
-      LAT_LAUNCH(ctx, k_chain_condense, (unsigned)ceil_div(n_cells * ns, 128), 128, 0, xyz, len0, len1, rad, n_cells, n_loc_nodes,
-                 n_loc_elem, chain_ptr, chain_elem, chain_flip, ns, young, nu, kappa, sup);
       const size_t smem = (size_t)DIRECT_WARPS * (ns + n_joints) * 36 * sizeof(double);
       if (smem <= 200 * 1024) {
+        const unsigned cgrid = (unsigned)ceil_div(n_cells * ns, 128);
+        if (dS)
+          LAT_LAUNCH(ctx, k_chain_condense_dual, cgrid, 128, 0, xyz, len0, len1, rad, drad_chain, n_cells, n_loc_nodes, n_loc_elem,
+                     chain_ptr, chain_elem, chain_flip, ns, young, nu, kappa, sup, dsup);
+        else
+          LAT_LAUNCH(ctx, k_chain_condense, cgrid, 128, 0, xyz, len0, len1, rad, n_cells, n_loc_nodes, n_loc_elem, chain_ptr,
+                     chain_elem, chain_flip, ns, young, nu, kappa, sup);
         LAT_CUDA(ctx, cudaFuncSetAttribute(k_schur_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int64_t grid = ceil_div(n_cells, DIRECT_WARPS);
         const int64_t cap = (int64_t)ctx->sm_count * 16;
         if (grid > cap) grid = cap;
-        LAT_LAUNCH(ctx, k_schur_direct, (unsigned)grid, 32 * DIRECT_WARPS, smem, sup, dincp, dinc, dpair, n_cells, ns, n_joints, S);
+        const int64_t nB2 = (int64_t)36 * n_joints * n_joints;
+        LAT_LAUNCH(ctx, k_schur_direct, (unsigned)grid, 32 * DIRECT_WARPS, smem, sup, dincp, dinc, dpair, n_cells, ns, n_joints, S, nB2,
+                   nullptr, 0);
+        for (int g = 0; dS && g < n_grad; ++g)
+          LAT_LAUNCH(ctx, k_schur_direct, (unsigned)grid, 32 * DIRECT_WARPS, smem, dsup, dincp, dinc, dpair, n_cells, ns, n_joints,
+                     dS + g * nB2, (int64_t)n_grad * nB2, chain_group, g);
         return LAT_OK;
       }
     }

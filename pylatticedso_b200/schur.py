@@ -165,8 +165,9 @@ def schur_gradients(lattice, cell, radii_params, elements_per_strut="gmsh", ctx=
     dev = ctx.device
     t = lambda a, d: torch.from_numpy(np.ascontiguousarray(a, dtype=d)).to(dev)
     chains = strut_chains(xyz, l0, l1, len(bnd), allow_trivial=True)
-    cg = chain_groups(chains, types) if is_star(chains, len(bnd)) else None
-    if cg is not None:          # star cell: sensitivities through the differentiated strut pre-pass
+    fast = chains is not None and (is_star(chains, len(bnd)) or chains["n_joints"] == len(bnd))
+    cg = chain_groups(chains, types) if fast else None
+    if cg is not None:          # star cell / no interior joint: sensitivities through the differentiated strut pre-pass
         S, dS = ctx.schur_batch_struts(t(xyz[None], np.float64), t(l0, np.int32), t(l1, np.int32), t(rad[None], np.float64),
                                        _chains_to_device(chains, dev), len(bnd), E, nu, KAPPA, chain_group=t(cg, np.int32),
                                        drad_chain=t(mesh.chain, np.float64), n_grad=len(radii_params))
@@ -204,9 +205,10 @@ class CellBatch:
             tr = strut_chains(np.asarray(xyz)[0], len0, len1, self.n_bnd_nodes, allow_trivial=True)
             ch = tr if (tr is not None and (is_star(tr, self.n_bnd_nodes) or tr["n_joints"] == self.n_bnd_nodes)) else None
         self.star = is_star(ch, self.n_bnd_nodes)
+        self.direct = ch is not None and ch["n_joints"] == self.n_bnd_nodes      # no interior joint: S is assembled directly
         self.chains = None if ch is None else _chains_to_device(ch, dev)
         self.chain_group = None
-        if self.star and elem_group is not None:
+        if (self.star or self.direct) and elem_group is not None:
             cg = chain_groups(ch, elem_group)
             self.chain_group = None if cg is None else t(cg, np.int32)
 
@@ -214,7 +216,7 @@ class CellBatch:
         if use_chains and self.chains is not None and not with_gradients:
             return self.ctx.schur_batch_struts(self.xyz, self.len0, self.len1, self.rad, self.chains, self.n_bnd_nodes,
                                                self.young, self.nu, self.kappa)
-        if use_chains and with_gradients and self.star and self.chain_group is not None:
+        if use_chains and with_gradients and (self.star or self.direct) and self.chain_group is not None:
             return self.ctx.schur_batch_struts(self.xyz, self.len0, self.len1, self.rad, self.chains, self.n_bnd_nodes,
                                                self.young, self.nu, self.kappa, chain_group=self.chain_group,
                                                drad_chain=self.chain, n_grad=self.n_grad)

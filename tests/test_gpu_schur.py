@@ -245,3 +245,24 @@ def test_more_reference_geometries_take_the_fast_schur_kernels(ctx, name, table,
     Sd = batch.schur(use_chains=False).cpu().numpy()
     assert S.shape == (24, 6 * n_bnd, 6 * n_bnd)
     assert np.abs(S - Sd).max() < 1e-12 * np.abs(Sd).max()
+
+
+def test_octet_sensitivities_through_the_direct_kernel(ctx):
+    """dS/dr of cells without an interior joint: S is linear in the super-elements, so the direct assembly applied to
+    the forward-mode derivative of the strut pre-pass is the analytic sensitivity.  Against the dense route (analytic,
+    all interior nodes) and a central difference of the values."""
+    from pylatticedso_b200.schur import synthetic_cell_batch
+    rng = np.random.default_rng(8)
+    radii = rng.uniform(0.02, 0.05, 20)
+    batch, bnd = synthetic_cell_batch(ctx, "Octet", radii, 2, E_MOD, NU, with_gradients=True)
+    assert batch.direct and batch.chain_group is not None
+    S, dS = batch.schur(with_gradients=True)
+    Sd, dSd = batch.schur(with_gradients=True, use_chains=False)
+    assert tuple(dS.shape) == (20, 1, 84, 84)
+    assert float((S - Sd).abs().max()) < 1e-12 * float(Sd.abs().max())
+    assert float((dS - dSd).abs().max()) < 1e-11 * float(dSd.abs().max())
+    h = 1e-6
+    Sp = synthetic_cell_batch(ctx, "Octet", radii + h, 2, E_MOD, NU)[0].schur()
+    Sm = synthetic_cell_batch(ctx, "Octet", radii - h, 2, E_MOD, NU)[0].schur()
+    fd = (Sp - Sm) / (2 * h)
+    assert float((dS[:, 0] - fd).abs().max()) < 1e-6 * float(fd.abs().max())
