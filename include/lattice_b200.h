@@ -296,6 +296,9 @@ int lat_schur_batch_chains(lat_ctx* ctx, const double* xyz, const int32_t* len0,
  *   d rad_e / d r_group (NULL -> 1); dS: [n_cells][n_grad][6 n_bnd][6 n_bnd] or NULL.  The strut pre-pass is differentiated
  *   in forward mode, so the sensitivities no longer need lat_schur_batch's dense route over all strut-interior DOFs
  *   (replaces the central finite differences of lattice_sim.py:1020-1054).
+ * Cells WITHOUT an interior joint (n_joints == n_bnd_nodes: Octet, Kelvin, Cubic, ...): nothing is left to eliminate after
+ * the pre-pass, S is the assembled joint-only cell matrix and dS/dr_g the same assembly applied to the differentiated
+ * pre-pass of group g's struts (k_schur_direct, one warp per cell).
  * Other topologies: S falls through to lat_schur_batch_chains; with dS != NULL the call returns LAT_ERR_UNSUPPORTED
  * (use lat_schur_batch).  [syncs: two small D2H copies of the chain ends] */
 int lat_schur_batch_struts(lat_ctx* ctx, const double* xyz, const int32_t* len0, const int32_t* len1,
