@@ -407,6 +407,28 @@ int lat_basis_prepare(lat_ctx* ctx, const double* basis, int64_t len, int32_t k,
 int lat_basis_expand(lat_ctx* ctx, const double* basisP, int32_t k, int64_t len, const double* alphas, int64_t M,
                      int32_t lda, double* out);
 
+/* ---- two-level preconditioner: 6x6 block-Jacobi + rigid-body-mode coarse space (csrc/coarse.cuh) ----
+ * Stands where the reference passes SuperLU's factorisation of the global interface matrix to its PCG as the
+ * preconditioner M (lattice_sim.py:1333-1415, used by solve_DDM :1148-1160 and LatticeOpti._solve_adjoint_vector,
+ * lattice_opti.py:1636-1645): M^-1 = D^-1 + Z E^+ Z^T with E = Z^T A Z, Z = the six rigid-body modes of every
+ * aggregate of nodes about its centroid, constrained DOFs masked.  The coarse space is resident in the context:
+ *   lat_coarse_setup       nodes -> aggregates (agg_ptr [n_agg+1], agg_nodes [n_nodes]: node indices grouped by
+ *                          aggregate, every node exactly once); fixed [6 n_nodes] or NULL.  Deactivates any inverse. [syncs]
+ *   lat_coarse_galerkin    E [6 n_agg][6 n_agg] = Z^T A Z of a BSR matrix with or without the Dirichlet elimination
+ *                          (the masked rows / columns do not take part)
+ *   lat_coarse_set_inverse registers Einv (device, [6 n_agg]^2 row-major, symmetric, borrowed until replaced; the
+ *                          host forms it from E with a dense library factorisation) -- from then on lat_pcg_bsr and
+ *                          lat_pcg_matfree on this context (same n_nodes, precond as given, textbook mode) add the
+ *                          coarse correction in every iteration and report bit 10 in result.reserved; NULL switches
+ *                          it off.  LAT_ERR_UNSUPPORTED with reference_semantics and in the multi-GPU solvers.
+ *   lat_coarse_apply       u += Z Einv Z^T r (one application of the coarse correction; r, u 16-byte aligned) */
+int lat_coarse_setup(lat_ctx* ctx, const double* x, const double* y, const double* z, int64_t n_nodes,
+                     const int32_t* agg_ptr, const int32_t* agg_nodes, int32_t n_agg, const uint8_t* fixed);
+int lat_coarse_galerkin(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, const double* vals,
+                        int64_t n_nodes, double* E);
+int lat_coarse_set_inverse(lat_ctx* ctx, const double* einv);
+int lat_coarse_apply(lat_ctx* ctx, const double* r, double* u);
+
 #ifdef __cplusplus
 }
 #endif

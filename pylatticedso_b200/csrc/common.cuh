@@ -26,6 +26,17 @@ struct PcgScalars {
   int32_t restarts, pad2;
 };
 
+// Rigid-body-mode coarse space of the two-level preconditioner (coarse.cuh), registered by lat_coarse_setup.
+struct CoarseSpace {
+  int64_t n_nodes = -1;
+  int32_t n_agg = 0, n_pieces = 0;
+  bool active = false;            // an inverse is registered: the PCG drivers add the coarse correction
+  const double* einv = nullptr;   // [6 n_agg][6 n_agg] row-major (borrowed)
+  // ctx-owned buffers: "coarse_nodes" [n_nodes] CoarseNode in aggregate order, "coarse_bynode" [n_nodes] (agg, d, mask)
+  // by node, "coarse_ptr" [n_agg+1], "coarse_piece_ptr" [n_pieces+1], "coarse_piece_agg" [n_pieces],
+  // "coarse_agg_piece" [n_agg+1], "coarse_part" [6 n_pieces], "coarse_rc" / "coarse_yc" [6 n_agg]
+};
+
 struct lat_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -51,6 +62,7 @@ struct lat_ctx {
   int nranks = 1, rank = 0;
   // NVLink peer-memory path (lat_p2p_*): one arena per rank, mapped into every rank
   struct P2P* p2p = nullptr;
+  CoarseSpace coarse;
 };
 
 int lat_fail(lat_ctx* ctx, int code, const char* what, const char* file, int line);

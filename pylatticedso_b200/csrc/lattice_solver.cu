@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 
 #include <stddef.h>
@@ -959,6 +960,25 @@ static int spmv_plan(lat_ctx* ctx, const int32_t* rowptr, int64_t n_nodes, SpmvP
 // ---------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------
+#include "coarse.cuh"
+
+static CoarseLaunch coarse_launch(lat_ctx* ctx) {
+  CoarseLaunch cl;
+  const CoarseSpace& cs = ctx->coarse;
+  cl.n_agg = cs.n_agg;
+  cl.n_pieces = cs.n_pieces;
+  cl.agg_ptr = (const int32_t*)ctx->bufs["coarse_ptr"].p;
+  cl.piece_ptr = (const int32_t*)ctx->bufs["coarse_piece_ptr"].p;
+  cl.piece_agg = (const int32_t*)ctx->bufs["coarse_piece_agg"].p;
+  cl.agg_piece = (const int32_t*)ctx->bufs["coarse_agg_piece"].p;
+  cl.nodes = (const CoarseNode*)ctx->bufs["coarse_nodes"].p;
+  cl.einv = cs.einv;
+  cl.part = (double*)ctx->bufs["coarse_part"].p;
+  cl.rc = (double*)ctx->bufs["coarse_rc"].p;
+  cl.yc = (double*)ctx->bufs["coarse_yc"].p;
+  return cl;
+}
+
 template <int PC>
 static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, const double* vals,
                    int64_t n_nodes, const double* b, double* x, const lat_pcg_opts* o, lat_pcg_result* res,
@@ -1015,6 +1035,20 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
 
   // bit 3 of `reserved` forces the classic two-reduction recurrences in the textbook mode
   const bool cgv = mf || (!o->reference_semantics && !(o->reserved & 8) && !plan.tma);
+  // two-level preconditioner (coarse.cuh): registered on the context by lat_coarse_setup / lat_coarse_set_inverse
+  const CoarseSpace& cs = ctx->coarse;
+  const bool coarse = cs.active;
+  if (coarse && cs.n_nodes != n_nodes)
+    return lat_fail(ctx, LAT_ERR_STATE, "the registered coarse space belongs to another system: call lat_coarse_setup / lat_coarse_set_inverse(NULL)", __FILE__, __LINE__);
+  if (coarse && !cgv)
+    return lat_fail(ctx, LAT_ERR_UNSUPPORTED, "the coarse correction runs in the Chronopoulos-Gear iteration only (no reference_semantics / classic / TMA variant)", __FILE__, __LINE__);
+  const CoarseLaunch cl = coarse ? coarse_launch(ctx) : CoarseLaunch();
+  const int coarse_launches = coarse ? cl.launches() : 0;
+  // u (= z here) += Z Einv Z^T r, between the kernel that produced u = D^-1 r and the product that consumes it
+  auto launch_coarse = [&](cudaStream_t st) {
+    if (coarse) cl.run(st, r, z, sc, prm.maxiter);
+  };
+  const int per_iter = (cgv ? 3 : 2) + coarse_launches;
   auto launch_spmv = [&](cudaStream_t st) {
     if (mf)
       k_cg_spmv_mf<false><<<mf_grid, MF_BLOCK, 0, st>>>(*mf, n_nodes, z, r, Ap, sc, partials, prm, RowSet());
@@ -1039,7 +1073,7 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
     if (cgv) k_cg_reduce<<<1, CG_REDUCE_BLOCK, 0, st>>>(partials, (int)(mf ? mf_grid : grid), sc, prm);
   };
   auto launch_iteration = [&](cudaStream_t st) {
-    if (cgv) { launch_update(st); launch_spmv(st); launch_reduce(st); }
+    if (cgv) { launch_update(st); launch_coarse(st); launch_spmv(st); launch_reduce(st); }
     else { launch_spmv(st); launch_update(st); }
   };
   LAT_CUDA(ctx, cudaMemsetAsync(sc, 0, sizeof(PcgScalars), ctx->stream));
@@ -1052,9 +1086,10 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
     const int32_t one = 1;
     LAT_CUDA(ctx, cudaMemcpyAsync(&sc->first, &one, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     LAT_LAUNCH(ctx, k_cg_init<PC>, grid, SPMV_BLOCK, 0, n_nodes, b, dinv, x, r, z, pa, pb);
+    launch_coarse(ctx->stream);
     launch_spmv(ctx->stream);  // set-up pass: w0 = A u0, gamma0, delta0, |b|^2
     launch_reduce(ctx->stream);
-    ctx->launches += 2;
+    ctx->launches += 2 + coarse_launches;
   } else {
     LAT_LAUNCH(ctx, k_pcg_init<PC>, grid, SPMV_BLOCK, 0, n_nodes, b, dinv, x, r, z, pa, pb, sc, partials, 0);
   }
@@ -1091,6 +1126,8 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
       if (cgv) {
         cudaEventRecord(evs[3 * it + 1], ctx->stream);
         launch_update(ctx->stream);
+        launch_coarse(ctx->stream);                    // timed with the update kernel
+        ctx->launches += coarse_launches;
         cudaEventRecord(evs[3 * it + 2], ctx->stream);
         cudaEventRecord(evs[3 * it], ctx->stream);
         launch_spmv(ctx->stream);
@@ -1141,7 +1178,7 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
       while (launched < nb && launched - checked < 2) {
         ce = cudaGraphLaunch(gexec, ctx->stream);
         if (ce != cudaSuccess) return lat_cuda_fail(ctx, ce, "cudaGraphLaunch", __FILE__, __LINE__);
-        ctx->launches += (cgv ? 3 : 2) * check;
+        ctx->launches += per_iter * check;
         cudaMemcpyAsync(&hs[launched & 1], sc, sizeof(PcgScalars), cudaMemcpyDeviceToHost, ctx->stream);
         cudaEventRecord(ctx->ev[2 + (launched & 1)], ctx->stream);
         ++launched;
@@ -1173,9 +1210,10 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
     true_rr = hs[0].true_rr;
     if (hs[0].done) break;       // accepted
     // restart from x: set-up pass, then iterate on the remaining budget
+    launch_coarse(ctx->stream);
     launch_spmv(ctx->stream);
     launch_reduce(ctx->stream);
-    ctx->launches += 2;
+    ctx->launches += 2 + coarse_launches;
     rc = run_batches((int64_t)o->maxiter - hs[0].iters);
   }
   if (rc == LAT_OK) {
@@ -1198,7 +1236,7 @@ static int pcg_run(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, c
   res->spmv_ms = spmv_ms;
   res->update_ms = update_ms;
   res->profiled = nprof;
-  res->reserved = hs[0].restarts | 0x100;   // bit 8: the iteration batches ran as CUDA graphs
+  res->reserved = hs[0].restarts | 0x100 | (coarse ? 0x400 : 0);   // bit 8: the iteration batches ran as CUDA graphs; bit 10: two-level
   res->true_relres = (true_rr >= 0.0 && hs[0].bb > 0.0) ? sqrt(true_rr / hs[0].bb) : -1.0;
   return LAT_OK;
 }
@@ -1440,7 +1478,8 @@ extern "C" int lat_pcg_bsr(lat_ctx* ctx, const int32_t* rowptr, const int32_t* c
   LAT_CUDA(ctx, cudaSetDevice(ctx->device));
   // Textbook mode, nothing experimental requested: try the persistent on-chip kernel first (bit 7 of `reserved`
   // opts out; profile_iters > 0 asks for per-kernel timings, which only the three-kernel iteration has).
-  const bool want_persist = !opts->reference_semantics && !(opts->reserved & (2 | 8 | 128)) && opts->profile_iters <= 0;
+  const bool want_persist = !opts->reference_semantics && !(opts->reserved & (2 | 8 | 128)) && opts->profile_iters <= 0 &&
+                            !ctx->coarse.active;   // the coarse correction lives in the three-kernel iteration
   if (want_persist) {
     bool used = false;
     int rc = LAT_OK;
@@ -1543,6 +1582,91 @@ extern "C" int lat_pcg_matfree(lat_ctx* ctx, const double* b, double* x, const l
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// two-level preconditioner (coarse.cuh): set-up entry points
+// ---------------------------------------------------------------------------
+extern "C" int lat_coarse_setup(lat_ctx* ctx, const double* x, const double* y, const double* z, int64_t n_nodes,
+                                const int32_t* agg_ptr, const int32_t* agg_nodes, int32_t n_agg, const uint8_t* fixed) {
+  if (!ctx) return LAT_ERR_ARG;
+  LAT_CHECK_ARG(ctx, x && y && z && agg_ptr && agg_nodes && n_nodes > 0 && n_agg > 0 && n_nodes < ((int64_t)1 << COARSE_NODE_BITS));
+  LAT_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->coarse = CoarseSpace();
+  CoarseNode* by_agg = lat_buf<CoarseNode>(ctx, "coarse_nodes", (size_t)n_nodes);
+  CoarseNode* by_node = lat_buf<CoarseNode>(ctx, "coarse_bynode", (size_t)n_nodes);
+  int32_t* ptr = lat_buf<int32_t>(ctx, "coarse_ptr", (size_t)n_agg + 1);
+  double* rc = lat_buf<double>(ctx, "coarse_rc", (size_t)6 * n_agg);
+  double* yc = lat_buf<double>(ctx, "coarse_yc", (size_t)6 * n_agg);
+  if (!by_agg || !by_node || !ptr || !rc || !yc) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+  std::vector<int32_t> h_ptr((size_t)n_agg + 1);
+  LAT_CUDA(ctx, cudaMemcpyAsync(ptr, agg_ptr, ((size_t)n_agg + 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  LAT_CUDA(ctx, cudaMemcpyAsync(h_ptr.data(), agg_ptr, ((size_t)n_agg + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h_ptr[0] != 0 || h_ptr[n_agg] != n_nodes)
+    return lat_fail(ctx, LAT_ERR_ARG, "agg_ptr must run from 0 to n_nodes: every node belongs to exactly one aggregate", __FILE__, __LINE__);
+  // pieces: every aggregate cut into chunks of at most COARSE_PIECE entries
+  std::vector<int32_t> piece_ptr(1, 0), piece_agg, agg_piece((size_t)n_agg + 1, 0);
+  for (int32_t a = 0; a < n_agg; ++a) {
+    if (h_ptr[a + 1] < h_ptr[a]) return lat_fail(ctx, LAT_ERR_ARG, "agg_ptr must be non-decreasing", __FILE__, __LINE__);
+    for (int32_t k = h_ptr[a]; k < h_ptr[a + 1]; k += COARSE_PIECE) {
+      piece_ptr.push_back(std::min(k + COARSE_PIECE, h_ptr[a + 1]));
+      piece_agg.push_back(a);
+    }
+    agg_piece[a + 1] = (int32_t)piece_agg.size();
+  }
+  const int32_t n_pieces = (int32_t)piece_agg.size();
+  int32_t* d_pp = lat_buf<int32_t>(ctx, "coarse_piece_ptr", (size_t)n_pieces + 1);
+  int32_t* d_pa = lat_buf<int32_t>(ctx, "coarse_piece_agg", (size_t)std::max(n_pieces, 1));
+  int32_t* d_ap = lat_buf<int32_t>(ctx, "coarse_agg_piece", (size_t)n_agg + 1);
+  double* part = lat_buf<double>(ctx, "coarse_part", (size_t)6 * std::max(n_pieces, 1));
+  if (!d_pp || !d_pa || !d_ap || !part) return lat_fail(ctx, 2, "workspace allocation failed", __FILE__, __LINE__);
+  LAT_CUDA(ctx, cudaMemcpyAsync(d_pp, piece_ptr.data(), ((size_t)n_pieces + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  LAT_CUDA(ctx, cudaMemcpyAsync(d_pa, piece_agg.data(), (size_t)n_pieces * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  LAT_CUDA(ctx, cudaMemcpyAsync(d_ap, agg_piece.data(), ((size_t)n_agg + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  LAT_LAUNCH(ctx, k_coarse_setup, (unsigned)n_agg, COARSE_BLOCK, 0, ptr, agg_nodes, x, y, z, fixed, by_agg, by_node);
+  LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the host vectors above are read by the async copies
+  ctx->coarse.n_pieces = n_pieces;
+  ctx->coarse.n_nodes = n_nodes;
+  ctx->coarse.n_agg = n_agg;
+  return LAT_OK;
+}
+
+extern "C" int lat_coarse_galerkin(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, const double* vals,
+                                   int64_t n_nodes, double* E) {
+  if (!ctx) return LAT_ERR_ARG;
+  LAT_CHECK_ARG(ctx, rowptr && colidx && vals && E);
+  if (ctx->coarse.n_nodes != n_nodes)
+    return lat_fail(ctx, LAT_ERR_STATE, "no coarse space for this system: call lat_coarse_setup", __FILE__, __LINE__);
+  LAT_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t n_c = 6 * (int64_t)ctx->coarse.n_agg;
+  LAT_CUDA(ctx, cudaMemsetAsync(E, 0, (size_t)n_c * n_c * sizeof(double), ctx->stream));
+  LAT_LAUNCH(ctx, k_coarse_galerkin, (unsigned)ceil_div(n_nodes, 128), 128, 0, rowptr, colidx, vals, n_nodes,
+             (const CoarseNode*)ctx->bufs["coarse_bynode"].p, n_c, E);
+  return LAT_OK;
+}
+
+extern "C" int lat_coarse_set_inverse(lat_ctx* ctx, const double* einv) {
+  if (!ctx) return LAT_ERR_ARG;
+  if (einv && ctx->coarse.n_nodes < 0)
+    return lat_fail(ctx, LAT_ERR_STATE, "no coarse space: call lat_coarse_setup", __FILE__, __LINE__);
+  ctx->coarse.einv = einv;
+  ctx->coarse.active = einv != nullptr;
+  return LAT_OK;
+}
+
+extern "C" int lat_coarse_apply(lat_ctx* ctx, const double* r, double* u) {
+  if (!ctx) return LAT_ERR_ARG;
+  LAT_CHECK_ARG(ctx, r && u && r != u);
+  LAT_CHECK_ARG(ctx, ((reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(u)) & 15) == 0);
+  const CoarseSpace& cs = ctx->coarse;
+  if (!cs.active) return lat_fail(ctx, LAT_ERR_STATE, "no coarse inverse registered: call lat_coarse_set_inverse", __FILE__, __LINE__);
+  LAT_CUDA(ctx, cudaSetDevice(ctx->device));
+  const CoarseLaunch cl = coarse_launch(ctx);
+  cl.run(ctx->stream, r, u, nullptr, 0);
+  ctx->launches += cl.launches();
+  LAT_CUDA(ctx, cudaPeekAtLastError());
+  return LAT_OK;
+}
 
 // ===========================================================================
 // multi-GPU: NCCL (dlopen'ed -- the library torch already loaded), halo exchange, distributed PCG
@@ -2481,6 +2605,8 @@ extern "C" int lat_pcg_bsr_dist(lat_ctx* ctx, const int32_t* rowptr, const int32
   LAT_CHECK_ARG(ctx, rowptr && colidx && vals && halo && b && x && opts && result);
   LAT_CHECK_ARG(ctx, halo->n_owned > 0 && halo->n_local >= halo->n_owned && opts->maxiter >= 0);
   LAT_CHECK_ARG(ctx, ctx->nranks == 1 || ctx->nccl_comm != nullptr);
+  if (ctx->coarse.active)
+    return lat_fail(ctx, LAT_ERR_UNSUPPORTED, "the two-level preconditioner is single-GPU: lat_coarse_set_inverse(NULL) first", __FILE__, __LINE__);
   LAT_CUDA(ctx, cudaSetDevice(ctx->device));
   switch (opts->precond) {
     case LAT_PC_NONE: return pcg_run_dist<LAT_PC_NONE>(ctx, rowptr, colidx, vals, halo, b, x, opts, result);
@@ -2501,6 +2627,8 @@ extern "C" int lat_pcg_matfree_dist(lat_ctx* ctx, const lat_halo* halo, const do
   if (int rc = mf_get(ctx, &op)) return rc;
   if (ctx->mf_nnodes != halo->n_local)
     return lat_fail(ctx, LAT_ERR_STATE, "resident matrix-free operator was set up for a different local mesh", __FILE__, __LINE__);
+  if (ctx->coarse.active)
+    return lat_fail(ctx, LAT_ERR_UNSUPPORTED, "the two-level preconditioner is single-GPU: lat_coarse_set_inverse(NULL) first", __FILE__, __LINE__);
   LAT_CUDA(ctx, cudaSetDevice(ctx->device));
   switch (opts->precond) {
     case LAT_PC_NONE: return pcg_run_dist<LAT_PC_NONE>(ctx, nullptr, nullptr, nullptr, halo, b, x, opts, result, &op);

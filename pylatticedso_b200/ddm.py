@@ -57,13 +57,26 @@ class InterfaceProblem:
         self.S = S
         self.vals = ctx.assemble_cells_bsr(S, self.cell_nodes, self.rowptr, self.colidx)
 
-    def solve(self, fixed, g, f, tol=1e-10, maxiter=200000, precond=L.PC_BLOCK6):
+    def solve(self, fixed, g, f, tol=1e-10, maxiter=200000, precond=L.PC_BLOCK6, two_level=None, xyz=None):
+        """``two_level`` (True or a number of aggregates) with ``xyz`` [n_interface_nodes, 3]: block-Jacobi + rigid-body-mode
+        coarse space (coarse.TwoLevel) -- the role SuperLU's factorisation of this matrix plays in the reference
+        (lattice_sim.py:1333-1415)."""
+        import contextlib
         torch, ctx = self.torch, self.ctx
         dev = ctx.device
         t = lambda a, d: torch.from_numpy(np.ascontiguousarray(a, dtype=d)).to(dev)
         fd, gd, fv = t(fixed, np.uint8), t(g, np.float64), t(f, np.float64)
         vbc, b = ctx.apply_dirichlet(self.rowptr, self.colidx, self.vals, fd, gd, fv)
-        u, info = ctx.pcg(self.rowptr, self.colidx, vbc, b, tol=tol, maxiter=maxiter, precond=precond)
+        scope = contextlib.nullcontext()
+        if two_level:
+            from . import coarse
+            if xyz is None:
+                raise ValueError("two_level needs the interface node coordinates (xyz)")
+            c = t(np.asarray(xyz, dtype=np.float64).T, np.float64)
+            n_agg = coarse.default_aggregates(self.n_nodes) if two_level is True else int(two_level)
+            scope = coarse.TwoLevel(ctx, c[0], c[1], c[2], fd, self.rowptr, self.colidx, vbc, n_agg)
+        with scope:
+            u, info = ctx.pcg(self.rowptr, self.colidx, vbc, b, tol=tol, maxiter=maxiter, precond=precond)
         ctx.set_dirichlet_values(fd, gd, u)
         R = ctx.spmv(self.rowptr, self.colidx, self.vals, u)
         return u, R, info, b
@@ -125,7 +138,7 @@ def free_dof_map(lattice, pts, n_free=None):
     return out
 
 
-def solve_DDM_B200(lattice, tol=1e-10, maxiter=200000, ctx=None):
+def solve_DDM_B200(lattice, tol=1e-10, maxiter=200000, ctx=None, two_level=None):
     """Drop-in for ``LatticeSim.solve_DDM()`` -> (xsol, info, global_displacement_index, b)
     (lattice_sim.py:1111-1176).
 
@@ -138,7 +151,12 @@ def solve_DDM_B200(lattice, tol=1e-10, maxiter=200000, ctx=None):
         if callable(fn):
             fn()
     prob, pts, fixed, g, f = interface_from_lattice(lattice, ctx)
-    u, R, info, b = prob.solve(fixed, g, f, tol=tol, maxiter=maxiter)
+    xyz = None
+    if two_level:
+        xyz = np.zeros((prob.n_nodes, 3))
+        for ib, p in pts.items():
+            xyz[ib] = (float(p.x), float(p.y), float(p.z))
+    u, R, info, b = prob.solve(fixed, g, f, tol=tol, maxiter=maxiter, two_level=two_level, xyz=xyz)
     if info["info"] not in (0, 5):
         import warnings
         warnings.warn(f"solve_DDM_B200: interface PCG stopped with info={info['info']} (relres {info['relres']:.2e}, "

@@ -85,13 +85,39 @@ class BeamFEM:
         self.rad.copy_(t)
         self.vals = None
 
+    # -- two-level preconditioner ---------------------------------------------------
+    def two_level(self, fixed, n_aggregates=None):
+        """Rigid-body-mode coarse space of this operator under the constraints ``fixed`` (coarse.TwoLevel; resident in
+        the context until the next call).  A matrix-free user pays one temporary assembly for the Galerkin product."""
+        from . import coarse
+        torch = self.torch
+        if self.rowptr is None:
+            self.build_pattern()
+        dev = self.ctx.device
+        fixed_d = torch.as_tensor(np.ascontiguousarray(fixed, dtype=np.uint8)).to(dev) if not torch.is_tensor(fixed) else fixed
+        vals = self.vals
+        if vals is None:
+            vals = self.ctx.assemble_bsr(self.x, self.y, self.z, self.en0, self.en1, self.rad, self.n_nodes, self.nnzb,
+                                         self.young, self.nu, self.kappa)
+        return coarse.TwoLevel(self.ctx, self.x, self.y, self.z, fixed_d, self.rowptr, self.colidx, vals, n_aggregates)
+
+    def _two_level_scope(self, two_level, fixed):
+        import contextlib
+        if two_level is None or two_level is False:
+            return contextlib.nullcontext()
+        from . import coarse
+        if isinstance(two_level, coarse.TwoLevel):
+            return two_level
+        return self.two_level(fixed, None if two_level is True else int(two_level))
+
     # -- solve ------------------------------------------------------------------
     def solve(self, fixed, g, f, tol=1e-8, maxiter=200000, precond=L.PC_BLOCK6, keep_unconstrained=True,
-              want_reactions=True, **pcg_kw):
+              want_reactions=True, two_level=None, **pcg_kw):
         """Static solve K u = f with u[c] = g.  Returns (u, reactions, info) as device tensors/dict.
 
         BC algebra of simulation_base.py:480-499; the sparse LU of :502-511 is replaced
-        by PCG to ``tol`` relative residual."""
+        by PCG to ``tol`` relative residual.  ``two_level``: True / a number of aggregates / a coarse.TwoLevel adds the
+        rigid-body-mode coarse correction to the preconditioner (csrc/coarse.cuh)."""
         torch = self.torch
         if self.vals is None:
             self.assemble()
@@ -102,8 +128,9 @@ class BeamFEM:
         keep = keep_unconstrained or want_reactions
         self.vals_bc, b = self.ctx.apply_dirichlet(self.rowptr, self.colidx, self.vals, fixed_d, g_d, f_d,
                                                    inplace=not keep)
-        u, info = self.ctx.pcg(self.rowptr, self.colidx, self.vals_bc, b, tol=tol, maxiter=maxiter,
-                               precond=precond, **pcg_kw)
+        with self._two_level_scope(two_level, fixed_d):
+            u, info = self.ctx.pcg(self.rowptr, self.colidx, self.vals_bc, b, tol=tol, maxiter=maxiter,
+                                   precond=precond, **pcg_kw)
         self.ctx.set_dirichlet_values(fixed_d, g_d, u)
         R = None
         if want_reactions:
@@ -113,7 +140,7 @@ class BeamFEM:
         return u, R, info
 
     def solve_matrix_free(self, fixed, g, f, tol=1e-8, maxiter=200000, precond=L.PC_BLOCK6, want_reactions=True,
-                          **pcg_kw):
+                          two_level=None, **pcg_kw):
         """Same system and BC algebra as :meth:`solve`, but K is never assembled: every product regenerates the
         element action from the geometry (csrc/matfree.cuh).  No 288 B/block matrix in HBM, ~10x fewer bytes per
         PCG iteration.  Returns (u, reactions, info) like :meth:`solve`."""
@@ -127,7 +154,8 @@ class BeamFEM:
         self.ctx.matfree_setup(self.x, self.y, self.z, self.en0, self.en1, self.rad, self.n_nodes, self.young,
                                self.nu, self.kappa, fixed=fixed_d)
         b = self.ctx.matfree_rhs(g_d, f_d)
-        u, info = self.ctx.pcg_matfree(b, tol=tol, maxiter=maxiter, precond=precond, **pcg_kw)
+        with self._two_level_scope(two_level, fixed_d):
+            u, info = self.ctx.pcg_matfree(b, tol=tol, maxiter=maxiter, precond=precond, **pcg_kw)
         self.ctx.set_dirichlet_values(fixed_d, g_d, u)
         R = self.ctx.matfree_apply(u, eliminated=False) if want_reactions else None   # R = K_unconstrained u
         return u, R, info

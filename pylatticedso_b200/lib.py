@@ -17,7 +17,7 @@ _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "liblattice_b200.so")
 SOURCES = ["lattice_core.cu", "lattice_solver.cu", "lattice_schur.cu", "lattice_surrogate.cu"]
 HEADERS = [os.path.join(_HERE, "csrc", "common.cuh"), os.path.join(_HERE, "csrc", "matfree.cuh"),
-           os.path.join(_HERE, "csrc", "pcg_persist.cuh"),
+           os.path.join(_HERE, "csrc", "pcg_persist.cuh"), os.path.join(_HERE, "csrc", "coarse.cuh"),
            os.path.join(_ROOT, "include", "lattice_b200.h")]
 
 ASM_GATHER, ASM_ATOMIC, ASM_ROWS = 0, 1, 2
@@ -34,6 +34,7 @@ EXPORTS = [
     "lat_cell_quadform", "lat_schur_batch_struts",
     "lat_greedy_basis", "lat_upper_solve", "lat_basis_project", "lat_rbf_fit", "lat_rbf_eval", "lat_alpha_lookup",
     "lat_basis_prepare", "lat_basis_expand", "lat_alpha_simplex",
+    "lat_coarse_setup", "lat_coarse_galerkin", "lat_coarse_set_inverse", "lat_coarse_apply",
 ]
 
 
@@ -148,6 +149,10 @@ def load():
     lib.lat_alpha_simplex.argtypes = [vp, vp, vp, i32, i32, vp, i32, vp, i32, vp, i64, vp]
     lib.lat_basis_prepare.argtypes = [vp, vp, i64, i32, i32, vp]
     lib.lat_basis_expand.argtypes = [vp, vp, i32, i64, vp, i64, i32, vp]
+    lib.lat_coarse_setup.argtypes = [vp, vp, vp, vp, i64, vp, vp, i32, vp]
+    lib.lat_coarse_galerkin.argtypes = [vp, vp, vp, vp, i64, vp]
+    lib.lat_coarse_set_inverse.argtypes = [vp, vp]
+    lib.lat_coarse_apply.argtypes = [vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("lat_last_error", "lat_launch_count"):
@@ -299,7 +304,7 @@ class Context:
         return x, dict(iters=r.iters, info=r.info, relres=r.relres, norm_b=r.norm_b, solve_ms=r.solve_ms,
                        launches=r.launches, spmv_ms=r.spmv_ms, update_ms=r.update_ms, profiled=r.profiled,
                        true_relres=r.true_relres, restarts=r.reserved & 0xff, graph=bool(r.reserved & 0x100),
-                       persistent=bool(r.reserved & 0x200))
+                       persistent=bool(r.reserved & 0x200), two_level=bool(r.reserved & 0x400))
 
     # ---- matrix-free operator (resident in the context; needs bsr_pattern() of the same mesh) ----
     def matfree_setup(self, x, y, z, en0, en1, rad, n_nodes, young, nu, kappa=0.9, fixed=None):
@@ -329,7 +334,29 @@ class Context:
         self.check(self.lib.lat_pcg_matfree(self.h, _ptr(b), _ptr(x), C.byref(o), C.byref(r)))
         return x, dict(iters=r.iters, info=r.info, relres=r.relres, norm_b=r.norm_b, solve_ms=r.solve_ms,
                        launches=r.launches, spmv_ms=r.spmv_ms, update_ms=r.update_ms, profiled=r.profiled,
-                       true_relres=r.true_relres, restarts=r.reserved & 0xff, graph=bool(r.reserved & 0x100))
+                       true_relres=r.true_relres, restarts=r.reserved & 0xff, graph=bool(r.reserved & 0x100),
+                       two_level=bool(r.reserved & 0x400))
+
+    # ---- two-level preconditioner (csrc/coarse.cuh; host policy in coarse.py) ----
+    def coarse_setup(self, x, y, z, agg_ptr, agg_nodes, fixed=None):
+        self._coarse_keep = None
+        self.check(self.lib.lat_coarse_setup(self.h, _ptr(x), _ptr(y), _ptr(z), x.numel(), _ptr(agg_ptr), _ptr(agg_nodes),
+                                             agg_ptr.numel() - 1, _ptr(fixed)))
+
+    def coarse_galerkin(self, rowptr, colidx, vals, n_agg):
+        import torch
+        E = torch.empty((6 * n_agg, 6 * n_agg), dtype=torch.float64, device=self.device)
+        self.check(self.lib.lat_coarse_galerkin(self.h, _ptr(rowptr), _ptr(colidx), _ptr(vals), rowptr.numel() - 1, _ptr(E)))
+        return E
+
+    def coarse_set_inverse(self, einv):
+        """Registers (and keeps alive) the dense coarse inverse; ``None`` switches the coarse correction off."""
+        self._coarse_keep = einv
+        self.check(self.lib.lat_coarse_set_inverse(self.h, _ptr(einv)))
+
+    def coarse_apply(self, r, u):
+        self.check(self.lib.lat_coarse_apply(self.h, _ptr(r), _ptr(u)))
+        return u
 
     def compliance_grad(self, x, y, z, en0, en1, rad, group, n_groups, u, young, nu, kappa=0.9, chain=None,
                         lam=None, want_elem=False):

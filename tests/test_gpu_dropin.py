@@ -241,6 +241,17 @@ def test_solve_ddm_b200_equals_the_reference_solve_ddm(ctx):
     assert np.abs(ub - G["u_boundary_reference"]).max() <= 1e-7 * np.abs(G["u_boundary_reference"]).max()
 
 
+def test_solve_ddm_b200_two_level_preconditioner(ctx):
+    """The same reference solve_DDM dump with the two-level preconditioner standing in for the reference's SuperLU
+    preconditioner (lattice_sim.py:1333-1415): the solution does not depend on the preconditioner."""
+    from pylatticedso_b200.ddm import solve_DDM_B200
+    G, lat = _ddm_dump()
+    xsol, info, gdi, b = solve_DDM_B200(lat, tol=1e-12, ctx=ctx, two_level=4)
+    assert info == 0 and lat.python_loop_calls == 0
+    assert np.abs(xsol - G["xsol_reference"]).max() <= 1e-7 * np.abs(G["xsol_reference"]).max()
+    assert np.array_equal(np.asarray(gdi), G["global_displacement_index"])
+
+
 def test_schur_gradients_dropin_on_dumped_reference_cell(ctx):
     """schur.schur_gradients (the rebinding of LatticeSim._compute_schur_gradients, lattice_sim.py:1020-1054) on a
     penalised BCC cell rebuilt from the reference dump: analytic dS/dr against the reference's recipe -- a central

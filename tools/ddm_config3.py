@@ -26,6 +26,12 @@ def run(ctx, n, m, tol=1e-12, verbose=True):
     u, R, info, _ = prob.solve(fixed.ravel(), g.ravel(), f.ravel(), tol=tol)
     torch.cuda.synchronize()
     t_ddm = time.perf_counter() - t0
+    # the same interface system with the two-level preconditioner (block-Jacobi + rigid-body-mode coarse space)
+    t2 = time.perf_counter()
+    u2, _, info2, _ = prob.solve(fixed.ravel(), g.ravel(), f.ravel(), tol=tol, two_level=True, xyz=cxyz)
+    torch.cuda.synchronize()
+    t_2l = time.perf_counter() - t2
+    du2 = float((u2 - u).abs().max() / u.abs().max())
     # the same lattice through the full FEM (all nodes, same subdivision)
     lat = M.synthetic_lattice("BCC", (n, n, n), [1.0], cell_radii=radii[:, None])
     mesh = M.mesh_from_synthetic(lat, m)
@@ -54,6 +60,8 @@ def run(ctx, n, m, tol=1e-12, verbose=True):
         print(f"BCC {n}^3, {n**3} cells, per-cell radii, {m} element(s) per strut, tol {tol:g}")
         print(f"  DDM : condense {tm['condense_ms']:.2f} ms (+ batch set-up {tm['setup_ms']:.1f} ms), interface pattern + assembly "
               f"{tm['interface_assembly_ms']:.1f} ms, PCG on {6*nc} interface DOF: {info['iters']} it, {info['solve_ms']:.1f} ms (info {info['info']})")
+        print(f"  DDM, two-level preconditioner: {info2['iters']} it, {info2['solve_ms']:.1f} ms PCG, {1e3 * t_2l:.1f} ms with the coarse "
+              f"set-up (info {info2['info']}); |u - u_blockjacobi|/|u| {du2:.1e}")
         print(f"  FEM : {mesh.n_dof} DOF matrix-free PCG: {inf['iters']} it, {inf['solve_ms']:.1f} ms (info {inf['info']})")
         print(f"  corner displacements DDM vs FEM: {eu:.2e}; reactions on constrained corners: {er:.2e}", flush=True)
     return out
