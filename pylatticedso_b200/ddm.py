@@ -138,7 +138,10 @@ def free_dof_map(lattice, pts, n_free=None):
     return out
 
 
-def solve_DDM_B200(lattice, tol=1e-10, maxiter=200000, ctx=None, two_level=None):
+TWO_LEVEL_AUTO_NODES = 20000     # interface systems from this size on get the coarse space by default
+
+
+def solve_DDM_B200(lattice, tol=1e-10, maxiter=200000, ctx=None, two_level="auto"):
     """Drop-in for ``LatticeSim.solve_DDM()`` -> (xsol, info, global_displacement_index, b)
     (lattice_sim.py:1111-1176).
 
@@ -151,6 +154,10 @@ def solve_DDM_B200(lattice, tol=1e-10, maxiter=200000, ctx=None, two_level=None)
         if callable(fn):
             fn()
     prob, pts, fixed, g, f = interface_from_lattice(lattice, ctx)
+    if two_level == "auto":
+        # the reference always preconditions this solve with a factorisation of the interface matrix (lattice_sim.py:
+        # 1333-1415); the coarse space plays that role from the size on where its set-up pays (config 3: 797 -> 116 it)
+        two_level = prob.n_nodes >= TWO_LEVEL_AUTO_NODES
     xyz = None
     if two_level:
         xyz = np.zeros((prob.n_nodes, 3))

@@ -27,10 +27,11 @@ def run(ctx, n, m, tol=1e-12, verbose=True):
     torch.cuda.synchronize()
     t_ddm = time.perf_counter() - t0
     # the same interface system with the two-level preconditioner (block-Jacobi + rigid-body-mode coarse space)
-    t2 = time.perf_counter()
-    u2, _, info2, _ = prob.solve(fixed.ravel(), g.ravel(), f.ravel(), tol=tol, two_level=True, xyz=cxyz)
-    torch.cuda.synchronize()
-    t_2l = time.perf_counter() - t2
+    for _ in range(2):          # second pass: warm library handles / workspaces (the first dense factorisation pays ~0.3 s of cuSOLVER start-up)
+        t2 = time.perf_counter()
+        u2, _, info2, _ = prob.solve(fixed.ravel(), g.ravel(), f.ravel(), tol=tol, two_level=True, xyz=cxyz)
+        torch.cuda.synchronize()
+        t_2l = time.perf_counter() - t2
     du2 = float((u2 - u).abs().max() / u.abs().max())
     # the same lattice through the full FEM (all nodes, same subdivision)
     lat = M.synthetic_lattice("BCC", (n, n, n), [1.0], cell_radii=radii[:, None])
@@ -55,12 +56,13 @@ def run(ctx, n, m, tol=1e-12, verbose=True):
     er = np.abs(Rd[fxm] - Rf_c[fxm]).max() / np.abs(Rf_c[fxm]).max()
     out = dict(n=n, m=m, cells=n ** 3, interface_dof=6 * nc, fem_dof=mesh.n_dof, ddm_iters=info["iters"], ddm_info=info["info"],
                ddm_pcg_ms=info["solve_ms"], fem_iters=inf["iters"], fem_pcg_ms=inf["solve_ms"], u_rel=float(eu), R_rel=float(er),
-               ddm_wall_s=t_ddm, fem_wall_s=t_fem, **tm)
+               ddm_wall_s=t_ddm, fem_wall_s=t_fem, two_level_iters=info2["iters"], two_level_info=info2["info"],
+               two_level_pcg_ms=info2["solve_ms"], two_level_wall_ms=1e3 * t_2l, two_level_u_rel=du2, **tm)
     if verbose:
         print(f"BCC {n}^3, {n**3} cells, per-cell radii, {m} element(s) per strut, tol {tol:g}")
         print(f"  DDM : condense {tm['condense_ms']:.2f} ms (+ batch set-up {tm['setup_ms']:.1f} ms), interface pattern + assembly "
               f"{tm['interface_assembly_ms']:.1f} ms, PCG on {6*nc} interface DOF: {info['iters']} it, {info['solve_ms']:.1f} ms (info {info['info']})")
-        print(f"  DDM, two-level preconditioner: {info2['iters']} it, {info2['solve_ms']:.1f} ms PCG, {1e3 * t_2l:.1f} ms with the coarse "
+        print(f"  DDM, two-level preconditioner: {info2['iters']} it, {info2['solve_ms']:.1f} ms PCG, {1e3 * t_2l:.1f} ms wall with uploads, elimination and the coarse "
               f"set-up (info {info2['info']}); |u - u_blockjacobi|/|u| {du2:.1e}")
         print(f"  FEM : {mesh.n_dof} DOF matrix-free PCG: {inf['iters']} it, {inf['solve_ms']:.1f} ms (info {inf['info']})")
         print(f"  corner displacements DDM vs FEM: {eu:.2e}; reactions on constrained corners: {er:.2e}", flush=True)
