@@ -19,9 +19,10 @@
 #pragma once
 #include "common.cuh"
 
-static constexpr int COARSE_BLOCK = 128;         // node passes
+static constexpr int COARSE_BLOCK = 256;         // node passes
 static constexpr int COARSE_SOLVE_BLOCK = 512;   // dense coarse product: 6 rows of Einv per CTA
-static constexpr int COARSE_PIECE = 512;         // nodes per piece of an aggregate
+static constexpr int COARSE_PIECE = 1024;        // nodes per piece of an aggregate
+static constexpr int COARSE_NPT = COARSE_PIECE / COARSE_BLOCK;   // nodes per thread of a node pass, all in flight together
 
 // One node of an aggregate: 16 bytes, so that a pass over the nodes adds 16 B to the 48 B of the node's vector entries.
 // The lever arm d = x_i - c_a is kept in FP32 -- Z is DEFINED with the rounded d (Galerkin product, restriction and
@@ -203,12 +204,25 @@ __global__ void __launch_bounds__(COARSE_BLOCK) k_coarse_restrict(const int32_t*
   if (sc && (sc->done || sc->iters >= maxiter)) return;
   const int lo = piece_ptr[blockIdx.x], hi = piece_ptr[blockIdx.x + 1];
   double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  for (int k = lo + threadIdx.x; k < hi; k += COARSE_BLOCK) {
-    const CoarseNodeD c = coarse_load(by_agg + k);
-    const double2* rp = reinterpret_cast<const double2*>(r + (int64_t)c.node * 6);
-    const double2 r0 = rp[0], r1 = rp[1], r2 = rp[2];
-    const double v[6] = {r0.x, r0.y, r1.x, r1.y, r2.x, r2.y};
-    coarse_restrict_node(c, v, acc);
+  // a piece has at most COARSE_PIECE entries: the table words of all of this thread's nodes are requested first, then
+  // all their vector entries (two memory round trips per CTA instead of two per node)
+  CoarseNodeD c[COARSE_NPT];
+#pragma unroll
+  for (int j = 0; j < COARSE_NPT; ++j) {
+    const int k = lo + threadIdx.x + j * COARSE_BLOCK;
+    c[j] = coarse_load(by_agg + (k < hi ? k : lo));
+    if (k >= hi) c[j].mask = 0u;                      // masked out: contributes nothing
+  }
+  double2 rv[COARSE_NPT][3];
+#pragma unroll
+  for (int j = 0; j < COARSE_NPT; ++j) {
+    const double2* rp = reinterpret_cast<const double2*>(r + (int64_t)c[j].node * 6);
+    rv[j][0] = rp[0]; rv[j][1] = rp[1]; rv[j][2] = rp[2];
+  }
+#pragma unroll
+  for (int j = 0; j < COARSE_NPT; ++j) {
+    const double v[6] = {rv[j][0].x, rv[j][0].y, rv[j][1].x, rv[j][1].y, rv[j][2].x, rv[j][2].y};
+    coarse_restrict_node(c[j], v, acc);
   }
   coarse_block_sum6<COARSE_BLOCK>(acc, s_part, s_tot);
   if (threadIdx.x < 6) part[(int64_t)blockIdx.x * 6 + threadIdx.x] = s_tot[threadIdx.x];
@@ -278,28 +292,43 @@ __global__ void __launch_bounds__(COARSE_BLOCK) k_coarse_prolong(const int32_t* 
   const int lo = piece_ptr[blockIdx.x], hi = piece_ptr[blockIdx.x + 1];
   const double* yp = yc + (int64_t)piece_agg[blockIdx.x] * 6;
   const double y[6] = {yp[0], yp[1], yp[2], yp[3], yp[4], yp[5]};
-  for (int k = lo + threadIdx.x; k < hi; k += COARSE_BLOCK) {
-    const CoarseNodeD c = coarse_load(by_agg + k);
+  CoarseNodeD c[COARSE_NPT];
+#pragma unroll
+  for (int j = 0; j < COARSE_NPT; ++j) {
+    const int k = lo + threadIdx.x + j * COARSE_BLOCK;
+    c[j] = coarse_load(by_agg + (k < hi ? k : lo));
+    if (k >= hi) c[j].node = -1;
+  }
+  double2 uv[COARSE_NPT][3];
+#pragma unroll
+  for (int j = 0; j < COARSE_NPT; ++j) {
+    if (c[j].node < 0) continue;
+    const double2* up = reinterpret_cast<const double2*>(u + (int64_t)c[j].node * 6);
+    uv[j][0] = up[0]; uv[j][1] = up[1]; uv[j][2] = up[2];
+  }
+#pragma unroll
+  for (int j = 0; j < COARSE_NPT; ++j) {
+    if (c[j].node < 0) continue;
     double d[6];
-    coarse_prolong_node(c, y, d);
-    double2* up = reinterpret_cast<double2*>(u + (int64_t)c.node * 6);
-    double2 u0 = up[0], u1 = up[1], u2 = up[2];
-    u0.x += d[0]; u0.y += d[1]; u1.x += d[2]; u1.y += d[3]; u2.x += d[4]; u2.y += d[5];
-    up[0] = u0; up[1] = u1; up[2] = u2;
+    coarse_prolong_node(c[j], y, d);
+    double2* up = reinterpret_cast<double2*>(u + (int64_t)c[j].node * 6);
+    uv[j][0].x += d[0]; uv[j][0].y += d[1]; uv[j][1].x += d[2]; uv[j][1].y += d[3]; uv[j][2].x += d[4]; uv[j][2].y += d[5];
+    up[0] = uv[j][0]; up[1] = uv[j][1]; up[2] = uv[j][2];
   }
 }
 
 // The launches of one coarse correction u += Z Einv Z^T r on stream st; returns their number.
 struct CoarseLaunch {
   int n_agg = 0, n_pieces = 0;
+  bool fused = false;   // every aggregate is exactly one piece
   const int32_t *agg_ptr = nullptr, *piece_ptr = nullptr, *piece_agg = nullptr, *agg_piece = nullptr;
   const CoarseNode* nodes = nullptr;
   const double* einv = nullptr;
   double *part = nullptr, *rc = nullptr, *yc = nullptr;
-  int launches() const { return n_pieces == n_agg ? 2 : 4; }
+  int launches() const { return fused ? 2 : 4; }
   void run(cudaStream_t st, const double* r, double* u, const PcgScalars* sc, int maxiter) const {
     const int64_t n_c = 6 * (int64_t)n_agg;
-    if (n_pieces == n_agg) {
+    if (fused) {
       k_coarse_restrict<<<n_agg, COARSE_BLOCK, 0, st>>>(agg_ptr, nodes, r, rc, sc, maxiter);
       k_coarse_solve<true><<<n_agg, COARSE_SOLVE_BLOCK, 0, st>>>(agg_ptr, nodes, einv, rc, n_c, yc, u, sc, maxiter);
     } else {

@@ -31,6 +31,7 @@ struct CoarseSpace {
   int64_t n_nodes = -1;
   int32_t n_agg = 0, n_pieces = 0;
   bool active = false;            // an inverse is registered: the PCG drivers add the coarse correction
+  bool fused = false;             // every aggregate is exactly one piece: 2 launches per correction instead of 4
   const double* einv = nullptr;   // [6 n_agg][6 n_agg] row-major (borrowed)
   // ctx-owned buffers: "coarse_nodes" [n_nodes] CoarseNode in aggregate order, "coarse_bynode" [n_nodes] (agg, d, mask)
   // by node, "coarse_ptr" [n_agg+1], "coarse_piece_ptr" [n_pieces+1], "coarse_piece_agg" [n_pieces],

@@ -967,6 +967,7 @@ static CoarseLaunch coarse_launch(lat_ctx* ctx) {
   const CoarseSpace& cs = ctx->coarse;
   cl.n_agg = cs.n_agg;
   cl.n_pieces = cs.n_pieces;
+  cl.fused = cs.fused;
   cl.agg_ptr = (const int32_t*)ctx->bufs["coarse_ptr"].p;
   cl.piece_ptr = (const int32_t*)ctx->bufs["coarse_piece_ptr"].p;
   cl.piece_agg = (const int32_t*)ctx->bufs["coarse_piece_agg"].p;
@@ -1626,6 +1627,9 @@ extern "C" int lat_coarse_setup(lat_ctx* ctx, const double* x, const double* y, 
   LAT_LAUNCH(ctx, k_coarse_setup, (unsigned)n_agg, COARSE_BLOCK, 0, ptr, agg_nodes, x, y, z, fixed, by_agg, by_node);
   LAT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the host vectors above are read by the async copies
   ctx->coarse.n_pieces = n_pieces;
+  bool one_each = n_pieces == n_agg;
+  for (int32_t a = 0; a < n_agg && one_each; ++a) one_each = agg_piece[a + 1] - agg_piece[a] == 1;
+  ctx->coarse.fused = one_each;
   ctx->coarse.n_nodes = n_nodes;
   ctx->coarse.n_agg = n_agg;
   return LAT_OK;

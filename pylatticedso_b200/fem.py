@@ -171,14 +171,16 @@ class BeamFEM:
             raise ValueError("mesh is not beam-major between lattice points")
         return np.r_[starts, m.n_elems].astype(np.int32), sa, sb
 
-    def solve_condensed(self, fixed, g, f, tol=1e-8, maxiter=200000, precond=L.PC_BLOCK6, full_field=False, **pcg_kw):
+    def solve_condensed(self, fixed, g, f, tol=1e-8, maxiter=200000, precond=L.PC_BLOCK6, full_field=False,
+                        two_level=None, **pcg_kw):
         """Joint-only solve: every strut (all its elements) is condensed exactly onto its two lattice points
         (``lat_assemble_bsr_struts``), the BSR system over the ``n_points`` joints is solved by the same PCG.  Needs
         loads and constraints on lattice points only -- what the reference applies -- and returns
         (u_joints [6 n_points], reactions on the joints, info): identical to the joint entries of :meth:`solve`
         with 5x (2 elements per strut) to ~70x (the reference's 18) fewer DOFs and far fewer iterations.
         ``full_field=True`` additionally back-substitutes the strut-interior nodes (``lat_strut_recover``) and returns
-        u and R over ALL nodes of the mesh (R is zero on interior nodes), e.g. for the element-form gradient."""
+        u and R over ALL nodes of the mesh (R is zero on interior nodes), e.g. for the element-form gradient.
+        ``two_level`` (True / number of aggregates): coarse space over the joints (coarse.TwoLevel)."""
         torch = self.torch
         m, ctx, dev = self.mesh, self.ctx, self.ctx.device
         nj = 6 * m.n_points
@@ -198,7 +200,15 @@ class BeamFEM:
                                        self.young, self.nu, self.kappa)
         fd, gd, fv = t(fixed[:nj], np.uint8), t(g[:nj], np.float64), t(f[:nj], np.float64)
         vbc, b = ctx.apply_dirichlet(rowptr, colidx, vals, fd, gd, fv, inplace=False)
-        u, info = ctx.pcg(rowptr, colidx, vbc, b, tol=tol, maxiter=maxiter, precond=precond, **pcg_kw)
+        import contextlib
+        scope = contextlib.nullcontext()
+        if two_level:
+            from . import coarse
+            npts = m.n_points
+            scope = coarse.TwoLevel(ctx, self.x[:npts].contiguous(), self.y[:npts].contiguous(), self.z[:npts].contiguous(),
+                                    fd, rowptr, colidx, vbc, None if two_level is True else int(two_level))
+        with scope:
+            u, info = ctx.pcg(rowptr, colidx, vbc, b, tol=tol, maxiter=maxiter, precond=precond, **pcg_kw)
         ctx.set_dirichlet_values(fd, gd, u)
         R = ctx.spmv(rowptr, colidx, vals, u)
         info = dict(info, n_dof_condensed=nj, n_dof_full=m.n_dof)
@@ -276,7 +286,8 @@ def solve_FEM_B200(lattice, elements_per_strut="gmsh", tol=1e-10, maxiter=500000
     fixed, g, f = bc_arrays_from_lattice(lattice, mesh, dedup_point_loads=dedup_point_loads)
     fem = BeamFEM(mesh, E, nu, ctx=ctx or L.default_context())     # one shared workspace across drop-in calls
     if condense_struts:      # joint-only solve + back-substitution: model.u / model.R cover all nodes like the other paths
-        u, R, info = fem.solve_condensed(fixed, g, f, tol=tol, maxiter=maxiter, precond=precond, full_field=True)
+        u, R, info = fem.solve_condensed(fixed, g, f, tol=tol, maxiter=maxiter, precond=precond, full_field=True,
+                                         two_level=two_level)
     else:
         solve = fem.solve_matrix_free if matrix_free else fem.solve
         u, R, info = solve(fixed, g, f, tol=tol, maxiter=maxiter, precond=precond, two_level=two_level)
