@@ -363,25 +363,43 @@ def config5_section(ctx, rank, world, hbm_peak, n=100):
     torch.cuda.empty_cache()
     um, Rm, im = dfem.solve_matrix_free(tol=1e-8, maxiter=100000, precond=L.PC_BLOCK6, want_reactions=False)
     diff = torch.stack([(um[:no] - ua[:no]).abs().max(), ua[:no].abs().max()])
+    # the same matrix-free solve with the two-level preconditioner (block-Jacobi + rigid-body-mode coarse space,
+    # csrc/coarse.cuh); set-up = temporary assembly + Galerkin product (+ all-reduce of the coarse matrix) + dense
+    # factorisation, timed warm (second build).  A failure here must not take the headline down: it is reported instead.
     two = None
-    if world == 1:
-        # the same matrix-free solve with the two-level preconditioner (block-Jacobi + rigid-body-mode coarse space,
-        # csrc/coarse.cuh); set-up = temporary assembly + Galerkin product + dense factorisation, timed warm (second build)
+    try:
         for _ in range(2):
             torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
             t1 = time.perf_counter()
-            tl = dfem.fem.two_level(dfem.bc[0])
+            tl = dfem.fem.two_level(dfem.bc[0]) if world == 1 else dfem.two_level()
             torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
             tl_setup_ms = 1e3 * (time.perf_counter() - t1)
-        u2, _, i2 = dfem.fem.solve_matrix_free(*dfem.bc, tol=1e-8, maxiter=100000, precond=L.PC_BLOCK6, want_reactions=False,
-                                               two_level=tl)
-        two = {"solve_ms": i2["solve_ms"], "iters": i2["iters"], "info": i2["info"], "true_relres": i2["true_relres"],
-               "setup_ms": tl_setup_ms, "n_aggregates": tl.n_agg, "coarse_dof": 6 * tl.n_agg,
-               "u_rel_vs_block_jacobi": float((u2[:no] - um[:no]).abs().max() / um[:no].abs().max()),
-               "speedup_vs_block_jacobi": im["solve_ms"] / i2["solve_ms"],
-               "note": "matrix-free PCG, M^-1 = D^-1 + Z E^+ Z^T (single GPU only); the solution is the same to the solver tolerance"}
+        if world == 1:
+            u2, _, i2 = dfem.fem.solve_matrix_free(*dfem.bc, tol=1e-8, maxiter=100000, precond=L.PC_BLOCK6, want_reactions=False,
+                                                   two_level=tl)
+        else:
+            u2, _, i2 = dfem.solve_matrix_free(tol=1e-8, maxiter=100000, precond=L.PC_BLOCK6, want_reactions=False, two_level=tl)
+        d2 = torch.stack([(u2[:no] - um[:no]).abs().max(), um[:no].abs().max()])
+        t2 = torch.tensor([i2["solve_ms"], tl_setup_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(d2, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        two = {"solve_ms": float(t2[0]), "iters": i2["iters"], "info": i2["info"], "true_relres": i2["true_relres"],
+               "setup_ms": float(t2[1]), "n_aggregates": tl.n_agg, "coarse_dof": 6 * tl.n_agg,
+               "u_rel_vs_block_jacobi": float(d2[0] / d2[1]),
+               "speedup_vs_block_jacobi": im["solve_ms"] / float(t2[0]),
+               "note": "matrix-free PCG, M^-1 = D^-1 + Z E^+ Z^T; N > 1: coarse residual all-reduced once per iteration, separate "
+                       "halo kernel; the solution is the same to the solver tolerance"}
         del tl, u2
         torch.cuda.empty_cache()
+    except Exception as e_:      # noqa: BLE001
+        two = {"error": f"{type(e_).__name__}: {e_}"[:300]}
+        if rank == 0:
+            print(f"bench.py: config5 two-level section failed: {e_}", file=sys.stderr)
     tt = torch.tensor([asm_ms, info["solve_ms"], im["solve_ms"], t_gen_upload, t_first,
                        resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1e6], dtype=torch.float64, device=dev)
     cnt = torch.tensor([dfem.n_owned, dfem.nnzb_owned], dtype=torch.float64, device=dev)

@@ -412,18 +412,27 @@ int lat_basis_expand(lat_ctx* ctx, const double* basisP, int32_t k, int64_t len,
  * preconditioner M (lattice_sim.py:1333-1415, used by solve_DDM :1148-1160 and LatticeOpti._solve_adjoint_vector,
  * lattice_opti.py:1636-1645): M^-1 = D^-1 + Z E^+ Z^T with E = Z^T A Z, Z = the six rigid-body modes of every
  * aggregate of nodes about its centroid, constrained DOFs masked.  The coarse space is resident in the context:
- *   lat_coarse_setup       nodes -> aggregates (agg_ptr [n_agg+1], agg_nodes [n_nodes]: node indices grouped by
- *                          aggregate, every node exactly once); fixed [6 n_nodes] or NULL.  Deactivates any inverse. [syncs]
- *   lat_coarse_galerkin    E [6 n_agg][6 n_agg] = Z^T A Z of a BSR matrix with or without the Dirichlet elimination
- *                          (the masked rows / columns do not take part)
+ *   lat_coarse_setup       node_agg [n_nodes]: aggregate of every local node; agg_ptr [n_agg+1] / agg_nodes: the nodes
+ *                          whose residual is restricted and whose u is corrected, grouped by aggregate (single GPU: every
+ *                          node once; sharded: the OWNED nodes, ghosts only appear in node_agg); fixed [6 n_nodes] or
+ *                          NULL; centers [3 n_agg] or NULL (NULL: centroid of the listed nodes; ranks of a sharded solve
+ *                          pass common points, e.g. the box centres -- the coarse space does not depend on them).
+ *                          Deactivates any inverse. [syncs]
+ *   lat_coarse_galerkin    E [6 n_agg][6 n_agg] = Z^T A Z over the n_nodes block rows given (all rows; sharded: the owned
+ *                          rows, E is then summed over the ranks by the caller), with or without the Dirichlet
+ *                          elimination (the masked rows / columns do not take part)
  *   lat_coarse_set_inverse registers Einv (device, [6 n_agg]^2 row-major, symmetric, borrowed until replaced; the
- *                          host forms it from E with a dense library factorisation) -- from then on lat_pcg_bsr and
- *                          lat_pcg_matfree on this context (same n_nodes, precond as given, textbook mode) add the
- *                          coarse correction in every iteration and report bit 10 in result.reserved; NULL switches
- *                          it off.  LAT_ERR_UNSUPPORTED with reference_semantics and in the multi-GPU solvers.
- *   lat_coarse_apply       u += Z Einv Z^T r (one application of the coarse correction; r, u 16-byte aligned) */
+ *                          host forms it from E with a dense library factorisation) -- from then on lat_pcg_bsr,
+ *                          lat_pcg_matfree and their _dist forms on this context (same local n_nodes, precond as given,
+ *                          textbook mode) add the coarse correction in every iteration and report bit 10 in
+ *                          result.reserved; NULL switches it off.  The sharded solvers all-reduce the coarse residual
+ *                          (6 n_agg doubles) once per iteration and use the separate halo kernel / NCCL exchange.
+ *                          LAT_ERR_UNSUPPORTED with reference_semantics.
+ *   lat_coarse_apply       u += Z Einv Z^T r (one application of the coarse correction on this rank's listed nodes, no
+ *                          all-reduce; r, u 16-byte aligned) */
 int lat_coarse_setup(lat_ctx* ctx, const double* x, const double* y, const double* z, int64_t n_nodes,
-                     const int32_t* agg_ptr, const int32_t* agg_nodes, int32_t n_agg, const uint8_t* fixed);
+                     const int32_t* node_agg, const int32_t* agg_ptr, const int32_t* agg_nodes, int32_t n_agg,
+                     const uint8_t* fixed, const double* centers);
 int lat_coarse_galerkin(lat_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, const double* vals,
                         int64_t n_nodes, double* E);
 int lat_coarse_set_inverse(lat_ctx* ctx, const double* einv);

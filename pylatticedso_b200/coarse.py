@@ -87,22 +87,33 @@ class TwoLevel:
     ``rowptr/colidx/vals``: the BSR matrix the coarse operator is the Galerkin projection of (eliminated or not: the
     constrained DOFs are masked out of the coarse space)."""
 
-    def __init__(self, ctx: L.Context, x, y, z, fixed, rowptr, colidx, vals, n_aggregates=None, agg=None):
+    def __init__(self, ctx: L.Context, x, y, z, fixed, rowptr, colidx, vals, n_aggregates=None, agg=None, n_agg=None,
+                 n_owned=None, centers=None, allreduce=None):
+        """Sharded systems (distributed.DistributedFEM.two_level): ``agg`` / ``n_agg`` = the GLOBAL aggregate of every
+        local node, ``n_owned`` = the leading nodes this rank owns (the rest are ghosts), ``centers`` [n_agg, 3] common
+        reference points, ``allreduce(E)`` sums the rank contributions of the coarse matrix in place."""
         import torch
         self.ctx = ctx
         if agg is None:
             agg, n_agg = box_aggregates(x, y, z, n_aggregates or default_aggregates(int(x.numel())))
-        else:
+        elif n_agg is None:
             n_agg = int(agg.max()) + 1
-        order = torch.argsort(agg, stable=True)
-        counts = torch.bincount(agg, minlength=n_agg)
+        n_nodes = int(x.numel())
+        n_owned = n_nodes if n_owned is None else int(n_owned)
+        own = agg[:n_owned]
+        order = torch.argsort(own, stable=True)
+        counts = torch.bincount(own, minlength=n_agg)
         ptr = torch.zeros(n_agg + 1, dtype=torch.int32, device=x.device)
         ptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
         self.n_agg, self.agg = n_agg, agg
+        self.node_agg = agg.to(torch.int32).contiguous()
         self.agg_ptr, self.agg_nodes = ptr, order.to(torch.int32).contiguous()
         fx = None if fixed is None else fixed.to(torch.uint8).contiguous()
-        ctx.coarse_setup(x, y, z, self.agg_ptr, self.agg_nodes, fx)
-        self.E = ctx.coarse_galerkin(rowptr, colidx, vals, n_agg)
+        cen = None if centers is None else centers.to(torch.float64).contiguous()
+        ctx.coarse_setup(x, y, z, self.node_agg, self.agg_ptr, self.agg_nodes, fx, cen)
+        self.E = ctx.coarse_galerkin(rowptr, colidx, vals, n_agg, n_rows=n_owned)
+        if allreduce is not None:
+            allreduce(self.E)
         self.Einv = invert_coarse(self.E)
         self.active = False
 

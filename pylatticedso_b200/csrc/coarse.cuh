@@ -99,23 +99,32 @@ __device__ __forceinline__ void coarse_block_sum6(double (&v)[6], double* s_part
   for (int i = 0; i < 6; ++i) v[i] = s_tot[i];
 }
 
-// centroids of the aggregates and the per-node tables
+// Reference points of the aggregates (given, or the centroid of the listed nodes) and the aggregate-ordered node table.
+// Any reference point spans the same coarse space (translations + rotations about ANY point); ranks of a sharded solve
+// must agree on it, so they pass the box centres.
 __global__ void __launch_bounds__(COARSE_BLOCK) k_coarse_setup(const int32_t* __restrict__ agg_ptr,
                                                               const int32_t* __restrict__ agg_nodes,
                                                               const double* __restrict__ x, const double* __restrict__ y,
                                                               const double* __restrict__ z, const uint8_t* __restrict__ fixed,
-                                                              CoarseNode* __restrict__ by_agg, CoarseNode* __restrict__ by_node) {
+                                                              const double* __restrict__ centers_in, double* __restrict__ centers,
+                                                              CoarseNode* __restrict__ by_agg) {
   __shared__ double s_part[6 * (COARSE_BLOCK / 32)], s_tot[6];
   const int a = blockIdx.x;
   const int lo = agg_ptr[a], hi = agg_ptr[a + 1];
-  double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  for (int k = lo + threadIdx.x; k < hi; k += COARSE_BLOCK) {
-    const int n = agg_nodes[k];
-    v[0] += x[n]; v[1] += y[n]; v[2] += z[n];
+  double cx, cy, cz;
+  if (centers_in) {
+    cx = centers_in[3 * a]; cy = centers_in[3 * a + 1]; cz = centers_in[3 * a + 2];
+  } else {
+    double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int k = lo + threadIdx.x; k < hi; k += COARSE_BLOCK) {
+      const int n = agg_nodes[k];
+      v[0] += x[n]; v[1] += y[n]; v[2] += z[n];
+    }
+    coarse_block_sum6<COARSE_BLOCK>(v, s_part, s_tot);
+    const double inv = hi > lo ? 1.0 / (double)(hi - lo) : 0.0;
+    cx = v[0] * inv; cy = v[1] * inv; cz = v[2] * inv;
   }
-  coarse_block_sum6<COARSE_BLOCK>(v, s_part, s_tot);
-  const double inv = hi > lo ? 1.0 / (double)(hi - lo) : 0.0;
-  const double cx = v[0] * inv, cy = v[1] * inv, cz = v[2] * inv;
+  if (threadIdx.x == 0) { centers[3 * a] = cx; centers[3 * a + 1] = cy; centers[3 * a + 2] = cz; }
   for (int k = lo + threadIdx.x; k < hi; k += COARSE_BLOCK) {
     const int n = agg_nodes[k];
     CoarseNode c;
@@ -125,9 +134,25 @@ __global__ void __launch_bounds__(COARSE_BLOCK) k_coarse_setup(const int32_t* __
       if (!fixed || !fixed[(int64_t)n * 6 + d]) m |= 1u << d;
     c.node_mask = (m << COARSE_NODE_BITS) | (uint32_t)n;
     by_agg[k] = c;
-    c.node_mask = (m << COARSE_NODE_BITS) | (uint32_t)a;   // the by-node copy stores the aggregate instead
-    by_node[n] = c;
   }
+}
+
+// node-ordered table over ALL local nodes (ghosts of a sharded solve included: the Galerkin product needs the columns):
+// lever arm, free-DOF mask and, in the index field, the aggregate
+__global__ void __launch_bounds__(256) k_coarse_bynode(const int32_t* __restrict__ node_agg, const double* __restrict__ x,
+                                                      const double* __restrict__ y, const double* __restrict__ z,
+                                                      const uint8_t* __restrict__ fixed, const double* __restrict__ centers,
+                                                      int64_t n_nodes, CoarseNode* __restrict__ by_node) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_nodes) return;
+  const int a = node_agg[n];
+  CoarseNode c;
+  c.dx = (float)(x[n] - centers[3 * a]); c.dy = (float)(y[n] - centers[3 * a + 1]); c.dz = (float)(z[n] - centers[3 * a + 2]);
+  uint32_t m = 0;
+  for (int d = 0; d < 6; ++d)
+    if (!fixed || !fixed[n * 6 + d]) m |= 1u << d;
+  c.node_mask = (m << COARSE_NODE_BITS) | (uint32_t)a;
+  by_node[n] = c;
 }
 
 // E += Z^T A Z: one thread per BSR block (i, j):  T_i^T A_ij T_j  added to the 6x6 block (agg_i, agg_j) of the
@@ -251,6 +276,7 @@ __global__ void __launch_bounds__(COARSE_SOLVE_BLOCK) k_coarse_solve(const int32
   __shared__ double s_part[6 * (COARSE_SOLVE_BLOCK / 32)], s_tot[6];
   if (sc && (sc->done || sc->iters >= maxiter)) return;
   const int a = blockIdx.x;
+  if (agg_ptr[a + 1] == agg_ptr[a]) return;      // no node of this aggregate is prolonged here (sharded solve): y is not needed
   double y[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   const double* row = einv + (int64_t)a * 6 * n_c;
   // n_c = 6 n_agg is even and the rows start 16-byte aligned: 128-bit loads, two column pairs in flight per thread
@@ -326,17 +352,30 @@ struct CoarseLaunch {
   const double* einv = nullptr;
   double *part = nullptr, *rc = nullptr, *yc = nullptr;
   int launches() const { return fused ? 2 : 4; }
-  void run(cudaStream_t st, const double* r, double* u, const PcgScalars* sc, int maxiter) const {
+  // rc = Z^T r over the listed nodes (a sharded solve all-reduces rc between the two halves).  gather = false (non-fused
+  // layout only): stop after the per-piece sums; the caller's own gather kernel adds them up across ranks.
+  void restrict_to_coarse(cudaStream_t st, const double* r, const PcgScalars* sc, int maxiter, bool gather = true) const {
     const int64_t n_c = 6 * (int64_t)n_agg;
     if (fused) {
       k_coarse_restrict<<<n_agg, COARSE_BLOCK, 0, st>>>(agg_ptr, nodes, r, rc, sc, maxiter);
-      k_coarse_solve<true><<<n_agg, COARSE_SOLVE_BLOCK, 0, st>>>(agg_ptr, nodes, einv, rc, n_c, yc, u, sc, maxiter);
     } else {
       k_coarse_restrict<<<n_pieces, COARSE_BLOCK, 0, st>>>(piece_ptr, nodes, r, part, sc, maxiter);
-      k_coarse_gather<<<(unsigned)((n_c + 255) / 256), 256, 0, st>>>(agg_piece, part, rc, (int)n_c, sc, maxiter);
+      if (gather) k_coarse_gather<<<(unsigned)((n_c + 255) / 256), 256, 0, st>>>(agg_piece, part, rc, (int)n_c, sc, maxiter);
+    }
+  }
+  // u += Z (Einv rc) on the listed nodes
+  void correct(cudaStream_t st, double* u, const PcgScalars* sc, int maxiter) const {
+    const int64_t n_c = 6 * (int64_t)n_agg;
+    if (fused) {
+      k_coarse_solve<true><<<n_agg, COARSE_SOLVE_BLOCK, 0, st>>>(agg_ptr, nodes, einv, rc, n_c, yc, u, sc, maxiter);
+    } else {
       k_coarse_solve<false><<<n_agg, COARSE_SOLVE_BLOCK, 0, st>>>(agg_ptr, nodes, einv, rc, n_c, yc, u, sc, maxiter);
       k_coarse_prolong<<<n_pieces, COARSE_BLOCK, 0, st>>>(piece_ptr, piece_agg, nodes, yc, u, sc, maxiter);
     }
+  }
+  void run(cudaStream_t st, const double* r, double* u, const PcgScalars* sc, int maxiter) const {
+    restrict_to_coarse(st, r, sc, maxiter);
+    correct(st, u, sc, maxiter);
   }
 };
 

@@ -293,8 +293,54 @@ class DistributedFEM:
         self.ctx.p2p_setup(self.n_local, self.part.peers, dst0)
         self.p2p = True
 
+    def two_level(self, n_aggregates=None):
+        """Rigid-body-mode coarse space of the sharded system (coarse.TwoLevel): boxes over the GLOBAL bounding box, so
+        every rank numbers the aggregates alike; each rank forms the Galerkin product of its owned rows (the ghost
+        columns included), the coarse matrix is summed over the ranks and every rank inverts it.  Needs
+        ``set_bc_local`` first; a matrix-free user pays one temporary assembly."""
+        import torch.distributed as dist
+        from . import coarse
+        torch, ctx = self.torch, self.ctx
+        dev = ctx.device
+        lo = torch.stack([self.x.min(), self.y.min(), self.z.min()])
+        hi = torch.stack([self.x.max(), self.y.max(), self.z.max()])
+        n_glob = torch.tensor([float(self.n_owned)], dtype=torch.float64, device=dev)
+        if self.world > 1:
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            dist.all_reduce(n_glob)
+        target = int(n_aggregates or coarse.default_aggregates(int(n_glob.item())))
+        ext = (hi - lo).clamp_min(1e-300).cpu().numpy()
+        lo_h = lo.cpu().numpy()
+        live = ext > 1e-9 * ext.max()
+        h = (np.prod(ext[live]) / target) ** (1.0 / max(1, int(live.sum())))
+        nb = np.where(live, np.maximum(1, np.round(ext / h)), 1).astype(np.int64)
+        ijk = []
+        for k, c in enumerate((self.x, self.y, self.z)):
+            ijk.append(((c - float(lo_h[k])) / float(ext[k]) * float(nb[k])).floor().long().clamp_(0, int(nb[k]) - 1))
+        agg = (ijk[0] * int(nb[1]) + ijk[1]) * int(nb[2]) + ijk[2]         # global box index, empty boxes kept
+        n_agg = int(nb.prod())
+        gi, gj, gk = np.meshgrid(np.arange(nb[0]), np.arange(nb[1]), np.arange(nb[2]), indexing="ij")
+        cen = lo_h[None, :] + (np.stack([gi.ravel(), gj.ravel(), gk.ravel()], 1) + 0.5) * (ext / nb)[None, :]
+        vals = self.vals
+        if vals is None:
+            vals = self.ctx.assemble_bsr(self.x, self.y, self.z, self.en0, self.en1, self.rad, self.n_local, self.nnzb,
+                                         self.young, self.nu, self.kappa)
+        allred = (lambda E: dist.all_reduce(E)) if self.world > 1 else None
+        return coarse.TwoLevel(ctx, self.x, self.y, self.z, self.fixed_d, self.rowptr, self.colidx, vals, agg=agg, n_agg=n_agg,
+                               n_owned=self.n_owned, centers=torch.from_numpy(cen).to(dev), allreduce=allred)
+
+    def _two_level_scope(self, two_level):
+        import contextlib
+        if two_level is None or two_level is False:
+            return contextlib.nullcontext()
+        from . import coarse
+        if isinstance(two_level, coarse.TwoLevel):
+            return two_level
+        return self.two_level(None if two_level is True else int(two_level))
+
     def solve(self, tol=1e-8, maxiter=200000, precond=2, vals_bc=None, b=None, u=None, check_every=0, profile_iters=0,
-              overlap=False, fused_halo=True, persistent=True):
+              overlap=False, fused_halo=True, persistent=True, two_level=None):
         """Returns (u_local [6 n_local] incl. ghosts, reactions on owned rows, info)."""
         torch, ctx = self.torch, self.ctx
         if self.vals is None:
@@ -309,16 +355,17 @@ class DistributedFEM:
         ctx.check(ctx.lib.lat_apply_dirichlet(ctx.h, L._ptr(self.rowptr), L._ptr(self.colidx), self.n_local,
                                               L._ptr(self.vals), L._ptr(self.fixed_d), L._ptr(self.g_d),
                                               L._ptr(self.f_d), L._ptr(vals_bc), L._ptr(b)))
-        u, info = ctx.pcg_dist(self.rowptr, self.colidx, vals_bc, self.halo, b, u, tol=tol, maxiter=maxiter,
-                               precond=precond, check_every=check_every, p2p=getattr(self, "p2p", False),
-                               profile_iters=profile_iters, overlap=overlap, fused_halo=fused_halo, persistent=persistent)
+        with self._two_level_scope(two_level):
+            u, info = ctx.pcg_dist(self.rowptr, self.colidx, vals_bc, self.halo, b, u, tol=tol, maxiter=maxiter,
+                                   precond=precond, check_every=check_every, p2p=getattr(self, "p2p", False),
+                                   profile_iters=profile_iters, overlap=overlap, fused_halo=fused_halo, persistent=persistent)
         ctx.set_dirichlet_values(self.fixed_d, self.g_d, u)
         ctx.halo_exchange(self.halo, u)
         R = ctx.spmv(self.rowptr, self.colidx, self.vals, u)     # rows >= n_owned are partial: ignore
         return u, R, info
 
     def solve_matrix_free(self, tol=1e-8, maxiter=200000, precond=2, b=None, u=None, check_every=0, profile_iters=0,
-                          want_reactions=True, overlap=False, fused_halo=True):
+                          want_reactions=True, overlap=False, fused_halo=True, two_level=None):
         """:meth:`solve` without an assembled matrix (csrc/matfree.cuh): the operator is regenerated from the
         local mesh in every product; halo exchange and all-reduce are unchanged."""
         torch, ctx = self.torch, self.ctx
@@ -329,9 +376,10 @@ class DistributedFEM:
         ctx.matfree_setup(self.x, self.y, self.z, self.en0, self.en1, self.rad, self.n_local, self.young, self.nu,
                           self.kappa, fixed=self.fixed_d)
         ctx.matfree_rhs(self.g_d, self.f_d, out=b)        # rows >= n_owned are partial: never read
-        u, info = ctx.pcg_matfree_dist(self.halo, b, u, tol=tol, maxiter=maxiter, precond=precond,
-                                       check_every=check_every, p2p=getattr(self, "p2p", False),
-                                       profile_iters=profile_iters, overlap=overlap, fused_halo=fused_halo)
+        with self._two_level_scope(two_level):
+            u, info = ctx.pcg_matfree_dist(self.halo, b, u, tol=tol, maxiter=maxiter, precond=precond,
+                                           check_every=check_every, p2p=getattr(self, "p2p", False),
+                                           profile_iters=profile_iters, overlap=overlap, fused_halo=fused_halo)
         ctx.set_dirichlet_values(self.fixed_d, self.g_d, u)
         ctx.halo_exchange(self.halo, u)
         R = ctx.matfree_apply(u, eliminated=False) if want_reactions else None

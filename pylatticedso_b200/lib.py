@@ -149,7 +149,7 @@ def load():
     lib.lat_alpha_simplex.argtypes = [vp, vp, vp, i32, i32, vp, i32, vp, i32, vp, i64, vp]
     lib.lat_basis_prepare.argtypes = [vp, vp, i64, i32, i32, vp]
     lib.lat_basis_expand.argtypes = [vp, vp, i32, i64, vp, i64, i32, vp]
-    lib.lat_coarse_setup.argtypes = [vp, vp, vp, vp, i64, vp, vp, i32, vp]
+    lib.lat_coarse_setup.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, i32, vp, vp]
     lib.lat_coarse_galerkin.argtypes = [vp, vp, vp, vp, i64, vp]
     lib.lat_coarse_set_inverse.argtypes = [vp, vp]
     lib.lat_coarse_apply.argtypes = [vp, vp, vp]
@@ -338,15 +338,16 @@ class Context:
                        two_level=bool(r.reserved & 0x400))
 
     # ---- two-level preconditioner (csrc/coarse.cuh; host policy in coarse.py) ----
-    def coarse_setup(self, x, y, z, agg_ptr, agg_nodes, fixed=None):
+    def coarse_setup(self, x, y, z, node_agg, agg_ptr, agg_nodes, fixed=None, centers=None):
         self._coarse_keep = None
-        self.check(self.lib.lat_coarse_setup(self.h, _ptr(x), _ptr(y), _ptr(z), x.numel(), _ptr(agg_ptr), _ptr(agg_nodes),
-                                             agg_ptr.numel() - 1, _ptr(fixed)))
+        self.check(self.lib.lat_coarse_setup(self.h, _ptr(x), _ptr(y), _ptr(z), x.numel(), _ptr(node_agg), _ptr(agg_ptr),
+                                             _ptr(agg_nodes), agg_ptr.numel() - 1, _ptr(fixed), _ptr(centers)))
 
-    def coarse_galerkin(self, rowptr, colidx, vals, n_agg):
+    def coarse_galerkin(self, rowptr, colidx, vals, n_agg, n_rows=None):
         import torch
         E = torch.empty((6 * n_agg, 6 * n_agg), dtype=torch.float64, device=self.device)
-        self.check(self.lib.lat_coarse_galerkin(self.h, _ptr(rowptr), _ptr(colidx), _ptr(vals), rowptr.numel() - 1, _ptr(E)))
+        n_rows = rowptr.numel() - 1 if n_rows is None else int(n_rows)
+        self.check(self.lib.lat_coarse_galerkin(self.h, _ptr(rowptr), _ptr(colidx), _ptr(vals), n_rows, _ptr(E)))
         return E
 
     def coarse_set_inverse(self, einv):
@@ -532,7 +533,7 @@ class Context:
         self.check(self.lib.lat_pcg_matfree_dist(self.h, C.byref(halo), _ptr(b), _ptr(x), C.byref(o), C.byref(r)))
         return x, dict(iters=r.iters, info=r.info, relres=r.relres, norm_b=r.norm_b, solve_ms=r.solve_ms,
                        launches=r.launches, true_relres=r.true_relres, restarts=r.reserved & 0xff, graph=bool(r.reserved & 0x100), spmv_ms=r.spmv_ms,
-                       update_ms=r.update_ms, profiled=r.profiled)
+                       update_ms=r.update_ms, profiled=r.profiled, two_level=bool(r.reserved & 0x400))
 
     def pcg_dist(self, rowptr, colidx, vals, halo, b, x, tol=1e-8, maxiter=10000, precond=PC_JACOBI,
                  reference_semantics=False, mintol=0.0, alpha_max=0.0, restart_every=0, check_every=0, p2p=False,
@@ -549,4 +550,5 @@ class Context:
                                              _ptr(x), C.byref(o), C.byref(r)))
         return x, dict(iters=r.iters, info=r.info, relres=r.relres, norm_b=r.norm_b, solve_ms=r.solve_ms,
                        launches=r.launches, true_relres=r.true_relres, restarts=r.reserved & 0xff, graph=bool(r.reserved & 0x100), spmv_ms=r.spmv_ms,
-                       update_ms=r.update_ms, profiled=r.profiled, persistent=bool(r.reserved & 0x200))
+                       update_ms=r.update_ms, profiled=r.profiled, persistent=bool(r.reserved & 0x200),
+                       two_level=bool(r.reserved & 0x400))
