@@ -34,6 +34,14 @@ def material_constants(lattice):
         raise KeyError(f"unknown material {name!r}") from e
 
 
+def stretch_dominated(mesh: BeamMesh) -> bool:
+    """Maxwell's rigidity count for pin-jointed frames: a 3-D lattice whose joints connect >= 12 struts on average in the
+    bulk (Octet: 12, BCC: 8) carries load by strut tension / compression; its stiffness matrix is then governed by
+    long-wavelength modes -- the ones the rigid-body-mode coarse space removes (two-level table)."""
+    n_struts = int(np.count_nonzero(mesh.en0 < mesh.n_points))      # every strut starts at a lattice point (mesh.py numbering)
+    return 2.0 * n_struts / max(1, mesh.n_points) >= 10.5           # surface joints pull the mean below the bulk value
+
+
 class BeamFEM:
     """Assembled beam-FEM operator resident on one GPU."""
 
@@ -101,8 +109,17 @@ class BeamFEM:
                                          self.young, self.nu, self.kappa)
         return coarse.TwoLevel(self.ctx, self.x, self.y, self.z, fixed_d, self.rowptr, self.colidx, vals, n_aggregates)
 
+    def stretch_dominated(self):
+        return stretch_dominated(self.mesh)
+
+    TWO_LEVEL_AUTO_NODES = 20000
+
     def _two_level_scope(self, two_level, fixed):
         import contextlib
+        if isinstance(two_level, str):
+            if two_level != "auto":
+                raise ValueError("two_level: None / True / number of aggregates / coarse.TwoLevel / 'auto'")
+            two_level = self.n_nodes >= self.TWO_LEVEL_AUTO_NODES and self.stretch_dominated()
         if two_level is None or two_level is False:
             return contextlib.nullcontext()
         from . import coarse
@@ -202,6 +219,8 @@ class BeamFEM:
         vbc, b = ctx.apply_dirichlet(rowptr, colidx, vals, fd, gd, fv, inplace=False)
         import contextlib
         scope = contextlib.nullcontext()
+        if two_level == "auto":
+            two_level = m.n_points >= self.TWO_LEVEL_AUTO_NODES and self.stretch_dominated()
         if two_level:
             from . import coarse
             npts = m.n_points
@@ -264,7 +283,7 @@ class FEMResult:
 
 
 def solve_FEM_B200(lattice, elements_per_strut="gmsh", tol=1e-10, maxiter=500000, precond=L.PC_BLOCK6,
-                   dedup_point_loads=False, ctx=None, matrix_free=False, condense_struts=False, two_level=None):
+                   dedup_point_loads=False, ctx=None, matrix_free=False, condense_struts=False, two_level="auto"):
     """Drop-in for ``solve_FEM_FenicsX(lattice) -> (xsol, simulationModel)``
     (utils_simulation.py:21-56).
 
@@ -273,8 +292,9 @@ def solve_FEM_B200(lattice, elements_per_strut="gmsh", tol=1e-10, maxiter=500000
     ``condense_struts=True`` solves the exact joint-only system (:meth:`BeamFEM.solve_condensed`) and
     back-substitutes the strut-interior nodes, so ``model.u`` / ``model.R`` are the same full fields as on the other
     paths (the write-back below only touches lattice points anyway).
-    ``two_level`` (True / number of aggregates; assembled and matrix-free paths): block-Jacobi + rigid-body-mode coarse
-    space (coarse.TwoLevel) -- 4-6x fewer iterations on stretch-dominated lattices (Octet), no gain on BCC.
+    ``two_level`` (True / number of aggregates / "auto"): block-Jacobi + rigid-body-mode coarse space (coarse.TwoLevel) --
+    4-6x fewer iterations on stretch-dominated lattices (Octet), no gain on BCC.  "auto" (default) switches it on for
+    lattices of at least 20 000 nodes whose mean joint valence says stretch-dominated (``BeamFEM.stretch_dominated``).
 
     Leaves ``Point.displacement_vector`` on every lattice node and
     ``Point.reaction_force_vector`` on nodes with a fixed DOF

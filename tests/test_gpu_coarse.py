@@ -100,3 +100,20 @@ def test_two_level_error_paths(ctx):
     with tl:
         with pytest.raises(L.LatticeB200Error, match="another system"):
             P2["fem"].solve(P2["fixed"], P2["g"], P2["f"], persistent=False)
+
+
+def test_two_level_auto_choice(ctx):
+    """two_level="auto" (the default of solve_FEM_B200): on for a stretch-dominated lattice of >= 20 000 nodes, off otherwise;
+    the solution does not depend on the choice."""
+    from pylatticedso_b200 import mesh as M
+    from pylatticedso_b200.fem import BeamFEM
+    for geom, n, m_el, want in (("Octet", 18, 1, True), ("BCC", 14, 2, False), ("Octet", 6, 1, False)):
+        m = M.mesh_from_synthetic(M.synthetic_lattice(geom, (n, n, n), [0.04]), m_el)
+        fixed, g, f = M.compression_bc(m)
+        fem = BeamFEM(m, E_MOD, NU, ctx=ctx)
+        u, _, info = fem.solve(fixed, g, f, tol=1e-10, two_level="auto", want_reactions=False)
+        assert info["info"] == 0 and info["two_level"] == want, (geom, n, m.n_nodes)
+        if want:
+            u0, _, i0 = fem.solve(fixed, g, f, tol=1e-10, want_reactions=False)
+            assert not i0["two_level"] and info["iters"] < 0.5 * i0["iters"]
+            assert float((u - u0).abs().max() / u0.abs().max()) < 1e-6
