@@ -350,6 +350,12 @@ int lat_ddm_matvec(lat_ctx* ctx, const double* S, int64_t s_stride, const int32_
 int lat_assemble_cells_bsr(lat_ctx* ctx, const double* S, int64_t s_stride, const int32_t* cell_nodes,
                            int64_t n_cells, int32_t n_bnd_nodes, const int32_t* rowptr, const int32_t* colidx,
                            int64_t nnzb, double* vals);
+/* The same matrix by a gather over a PLAN, for repeated assemblies on one interface pattern (a design iteration changes S,
+ * not the pattern): blk_ptr int32[nnzb+1] / contrib int64[blk_ptr[nnzb]] list for every BSR block its contributions
+ * (cell * n_bnd_nodes + a) * n_bnd_nodes + b, sorted by block (the host builds it once: ddm.InterfaceProblem).  No
+ * atomics: fixed summation order, bit-reproducible matrix, every entry of S read once.  vals[nnzb*36] is overwritten. */
+int lat_assemble_cells_bsr_plan(lat_ctx* ctx, const double* S, int64_t s_stride, int32_t n_bnd_nodes,
+                                const int32_t* blk_ptr, const int64_t* contrib, int64_t nnzb, double* vals);
 
 /* ---- A11, cell form: q[c][j] = v_c^T dS_{m(c,j)} u_c ------------------------------------------
  * The per-(cell, geometry) term of LatticeOpti.calculate_gradient (lattice_opti.py:752-761,

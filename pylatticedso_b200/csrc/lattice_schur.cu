@@ -1407,6 +1407,51 @@ extern "C" int lat_assemble_cells_bsr(lat_ctx* ctx, const double* S, int64_t s_s
 }
 
 
+// Gather form of the same assembly: a PLAN (built once per interface pattern by the host: ddm.InterfaceProblem) lists for
+// every BSR block the (cell, row node, column node) contributions, sorted by block.  One warp per block adds its
+// contributions in plan order -- fixed summation order (bit-reproducible matrix, unlike the FP64 reductions above), no
+// atomics, every S entry read once and every block written once: the assembly of a design iteration (new radii -> new
+// S, same plan) moves 8 nB^2 per cell + 288 B per block.
+// contrib[k] = (cell * nbn + a) * nbn + b.
+__global__ void __launch_bounds__(256) k_assemble_cells_gather(const double* __restrict__ S, int64_t s_stride, int nbn,
+                                                               const int32_t* __restrict__ blk_ptr, const int64_t* __restrict__ contrib,
+                                                               int64_t nnzb, double* __restrict__ vals) {
+  const int lane = threadIdx.x & 31;
+  const int64_t l = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (l >= nnzb) return;
+  const int nb = 6 * nbn;
+  const int lo = blk_ptr[l], hi = blk_ptr[l + 1];
+  // lane -> entries (i0, j0) = lane / 6, lane % 6 and, for lanes 0..3, entry 32 + lane
+  const int i0 = lane / 6, j0 = lane - i0 * 6;
+  const int k1 = 32 + lane, i1 = k1 / 6, j1 = k1 - i1 * 6;
+  double acc0 = 0.0, acc1 = 0.0;
+  for (int k = lo; k < hi; ++k) {
+    const int64_t d = __ldg(contrib + k);
+    const int64_t ca = d / nbn;
+    const int b = (int)(d - ca * nbn);
+    const int64_t c = ca / nbn;
+    const int a = (int)(ca - c * nbn);
+    const double* Sc = S + c * s_stride + (int64_t)(a * 6) * nb + b * 6;
+    acc0 += __ldg(Sc + (int64_t)i0 * nb + j0);
+    if (lane < 4) acc1 += __ldg(Sc + (int64_t)i1 * nb + j1);
+  }
+  double* dst = vals + l * 36;
+  dst[lane] = acc0;
+  if (lane < 4) dst[32 + lane] = acc1;
+}
+
+extern "C" int lat_assemble_cells_bsr_plan(lat_ctx* ctx, const double* S, int64_t s_stride, int32_t n_bnd_nodes,
+                                           const int32_t* blk_ptr, const int64_t* contrib, int64_t nnzb, double* vals) {
+  if (!ctx) return LAT_ERR_ARG;
+  LAT_CHECK_ARG(ctx, S && blk_ptr && contrib && vals && n_bnd_nodes > 0 && nnzb > 0);
+  LAT_CHECK_ARG(ctx, 6 * n_bnd_nodes <= SCHUR_MAX_NB);
+  LAT_CHECK_ARG(ctx, s_stride == 0 || s_stride >= (int64_t)36 * n_bnd_nodes * n_bnd_nodes);
+  LAT_CUDA(ctx, cudaSetDevice(ctx->device));
+  LAT_LAUNCH(ctx, k_assemble_cells_gather, (unsigned)ceil_div(nnzb, 8), 256, 0, S, s_stride, (int)n_bnd_nodes, blk_ptr, contrib, nnzb, vals);
+  return LAT_OK;
+}
+
+
 // ===========================================================================
 // A11 (cell form): q[c][j] = v_c^T dS_{m(c,j)} u_c
 // ===========================================================================

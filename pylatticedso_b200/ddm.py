@@ -52,10 +52,53 @@ class InterfaceProblem:
         dev = ctx.device
         self.n_nodes = int(n_interface_nodes)
         self.cell_nodes = torch.from_numpy(np.ascontiguousarray(cell_nodes, dtype=np.int32)).to(dev)
-        e0, e1 = cell_pair_elements(cell_nodes)
-        self.rowptr, self.colidx = ctx.bsr_pattern(torch.from_numpy(e0).to(dev), torch.from_numpy(e1).to(dev), self.n_nodes)
+        cn = self.cell_nodes
+        nc, nbn = int(cn.shape[0]), int(cn.shape[1])
+        # pattern input: all unordered node pairs of every cell as virtual 2-node elements, generated on the device
+        # (pair-major like cell_pair_elements; 6 M pairs at BASELINE config 3: 35 ms of host work + upload gone)
+        ia, ib = np.triu_indices(nbn, k=1)
+        a = cn[:, torch.from_numpy(ia).to(dev)].t().reshape(-1)
+        b = cn[:, torch.from_numpy(ib).to(dev)].t().reshape(-1)
+        ok = (a != b) & (a >= 0) & (b >= 0)
+        if not bool(ok.all()):
+            a, b = a[ok], b[ok]
+        self.rowptr, self.colidx = ctx.bsr_pattern(a.contiguous(), b.contiguous(), self.n_nodes)
+        del a, b, ok
+        self._build_plan()
         self.S = S
-        self.vals = ctx.assemble_cells_bsr(S, self.cell_nodes, self.rowptr, self.colidx)
+        self.vals = self.assemble(S)
+
+    def _build_plan(self):
+        """Assembly plan of ``lat_assemble_cells_bsr_plan``: the contributions (cell, a, b) of every BSR block, sorted by
+        block (cell-major inside a block, so the summation order is fixed).  Depends on the pattern only."""
+        torch = self.torch
+        cn, nn = self.cell_nodes.long(), self.n_nodes
+        nc, nbn = int(cn.shape[0]), int(cn.shape[1])
+        nnzb = int(self.colidx.numel())
+        row = torch.repeat_interleave(torch.arange(nn, device=cn.device), (self.rowptr[1:] - self.rowptr[:-1]).long())
+        bkey = row * nn + self.colidx.long()                       # ascending: rows ascending, columns sorted inside a row
+        ckey = (cn[:, :, None] * nn + cn[:, None, :]).reshape(-1)  # flat index = (c * nbn + a) * nbn + b
+        valid = ((cn[:, :, None] >= 0) & (cn[:, None, :] >= 0)).reshape(-1)
+        d = torch.arange(nc * nbn * nbn, device=cn.device)
+        if not bool(valid.all()):
+            d, ckey = d[valid], ckey[valid]
+        blk = torch.searchsorted(bkey, ckey)
+        if bool((blk >= nnzb).any()) or not bool((bkey[blk.clamp_max(nnzb - 1)] == ckey).all()):
+            raise L.LatticeB200Error("interface pattern does not contain every (node, node) pair of the cells")
+        order = torch.argsort(blk, stable=True)
+        self.plan_contrib = d[order].contiguous()
+        ptr = torch.zeros(nnzb + 1, dtype=torch.int64, device=cn.device)
+        ptr[1:] = torch.cumsum(torch.bincount(blk, minlength=nnzb), 0)
+        if int(ptr[-1]) >= 2 ** 31:
+            raise L.LatticeB200Error("assembly plan exceeds int32 offsets")
+        self.plan_ptr = ptr.to(torch.int32).contiguous()
+
+    def assemble(self, S, out=None):
+        """K_G = sum_c P_c^T S_c P_c for new Schur matrices on the same pattern (a design iteration): plan-driven gather,
+        no atomics, bit-reproducible.  S: [n_cells, nb, nb] or [nb, nb] (shared)."""
+        self.S = S
+        self.vals = self.ctx.assemble_cells_plan(S, int(self.cell_nodes.shape[1]), self.plan_ptr, self.plan_contrib, out=out)
+        return self.vals
 
     def solve(self, fixed, g, f, tol=1e-10, maxiter=200000, precond=L.PC_BLOCK6, two_level=None, xyz=None):
         """``two_level`` (True or a number of aggregates) with ``xyz`` [n_interface_nodes, 3]: block-Jacobi + rigid-body-mode

@@ -35,6 +35,7 @@ EXPORTS = [
     "lat_greedy_basis", "lat_upper_solve", "lat_basis_project", "lat_rbf_fit", "lat_rbf_eval", "lat_alpha_lookup",
     "lat_basis_prepare", "lat_basis_expand", "lat_alpha_simplex",
     "lat_coarse_setup", "lat_coarse_galerkin", "lat_coarse_set_inverse", "lat_coarse_apply",
+    "lat_assemble_cells_bsr_plan",
 ]
 
 
@@ -130,6 +131,7 @@ def load():
                                            vp, vp, i32, vp]
     lib.lat_ddm_matvec.argtypes = [vp, vp, i64, vp, vp, i64, i32, i64, vp, vp]
     lib.lat_assemble_cells_bsr.argtypes = [vp, vp, i64, vp, i64, i32, vp, vp, i64, vp]
+    lib.lat_assemble_cells_bsr_plan.argtypes = [vp, vp, i64, i32, vp, vp, i64, vp]
     lib.lat_cell_quadform.argtypes = [vp, vp, i64, vp, vp, vp, i64, i32, i32, vp]
     lib.lat_nccl_unique_id.argtypes = [vp]
     lib.lat_comm_create.argtypes = [vp, vp, C.c_int, C.c_int]
@@ -451,6 +453,16 @@ class Context:
         vals = torch.empty(colidx.numel() * 36, dtype=torch.float64, device=self.device)
         self.check(self.lib.lat_assemble_cells_bsr(self.h, _ptr(S), stride, _ptr(cell_nodes), n_cells, nbn, _ptr(rowptr),
                                                    _ptr(colidx), colidx.numel(), _ptr(vals)))
+        return vals
+
+    def assemble_cells_plan(self, S, n_bnd_nodes, blk_ptr, contrib, out=None):
+        """The same matrix by the plan-driven gather (``lat_assemble_cells_bsr_plan``): fixed summation order."""
+        import torch
+        nnzb = int(blk_ptr.numel()) - 1
+        stride = 0 if S.dim() == 2 else 36 * n_bnd_nodes * n_bnd_nodes
+        vals = out if out is not None else torch.empty(nnzb * 36, dtype=torch.float64, device=self.device)
+        self.check(self.lib.lat_assemble_cells_bsr_plan(self.h, _ptr(S), stride, n_bnd_nodes, _ptr(blk_ptr), _ptr(contrib),
+                                                        nnzb, _ptr(vals)))
         return vals
 
     def cell_quadform(self, mats, mat_index, U, V=None):

@@ -156,6 +156,20 @@ def test_ddm_interface_solve_equals_full_fem(ctx):
     y1 = ctx.ddm_matvec(S, gidx, x)
     y2 = ctx.spmv(prob.rowptr, prob.colidx, prob.vals, x)
     assert float((y1 - y2).abs().max()) < 1e-11 * float(y2.abs().max())
+    # the plan-driven gather assembly (InterfaceProblem.assemble) == the atomic scatter assembly, is bit-reproducible, and
+    # follows new Schur matrices on the same pattern (per-cell S, one cell with an absent node)
+    va = ctx.assemble_cells_bsr(S, prob.cell_nodes, prob.rowptr, prob.colidx)
+    assert float((va - prob.vals).abs().max()) < 1e-13 * float(va.abs().max())
+    Sc = S[None] * torch.from_numpy(1.0 + 0.1 * rng.random(len(cells))).to(ctx.device)[:, None, None]
+    v1 = prob.assemble(Sc).clone()
+    v2 = prob.assemble(Sc)
+    assert torch.equal(v1, v2)
+    va = ctx.assemble_cells_bsr(Sc, prob.cell_nodes, prob.rowptr, prob.colidx)
+    assert float((va - v1).abs().max()) < 1e-13 * float(va.abs().max())
+    cn2 = cell_nodes.copy(); cn2[1, 3] = -1
+    prob2 = InterfaceProblem(ctx, cn2, corner.size, Sc)
+    va = ctx.assemble_cells_bsr(Sc, prob2.cell_nodes, prob2.rowptr, prob2.colidx)
+    assert float((va - prob2.vals).abs().max()) < 1e-13 * float(va.abs().max())
 
 
 def test_schur_dataset_roundtrip_in_reference_schema(ctx, tmp_path):
