@@ -1,3 +1,8 @@
+"""Interface assembly (A9) at BASELINE config 3 (BCC 60^3, 216 000 cells): InterfaceProblem set-up (device pair generation +
+pattern + plan) and the plan-driven gather assembly against the FP64-RED scatter assembly.
+
+    python tools/ab_interface_assembly.py
+"""
 import sys, time
 import numpy as np, torch
 sys.path.insert(0, '.')
