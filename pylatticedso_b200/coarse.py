@@ -110,14 +110,23 @@ class TwoLevel:
         self.agg_ptr, self.agg_nodes = ptr, order.to(torch.int32).contiguous()
         fx = None if fixed is None else fixed.to(torch.uint8).contiguous()
         cen = None if centers is None else centers.to(torch.float64).contiguous()
-        ctx.coarse_setup(x, y, z, self.node_agg, self.agg_ptr, self.agg_nodes, fx, cen)
+        self._setup_args = (x, y, z, self.node_agg, self.agg_ptr, self.agg_nodes, fx, cen)
+        self._make_resident()
         self.E = ctx.coarse_galerkin(rowptr, colidx, vals, n_agg, n_rows=n_owned)
         if allreduce is not None:
             allreduce(self.E)
         self.Einv = invert_coarse(self.E)
         self.active = False
 
+    def _make_resident(self):
+        """A context holds ONE coarse space (node tables); building another TwoLevel on the same context replaces them, so
+        the tables are re-built before this one is used again."""
+        if getattr(self.ctx, "_coarse_owner", None) is not self:
+            self.ctx.coarse_setup(*self._setup_args)
+            self.ctx._coarse_owner = self
+
     def __enter__(self):
+        self._make_resident()
         self.ctx.coarse_set_inverse(self.Einv)
         self.active = True
         return self
@@ -131,6 +140,7 @@ class TwoLevel:
         """u += Z Einv Z^T r (one coarse correction; for tests)."""
         was = self.active
         if not was:
+            self._make_resident()
             self.ctx.coarse_set_inverse(self.Einv)
         try:
             return self.ctx.coarse_apply(r, u)

@@ -3,19 +3,24 @@
 //   M^-1 = D^-1 + Z E^+ Z^T,      E = Z^T A Z
 //
 // The nodes are grouped into aggregates (boxes of cells, chosen by the host).  Each aggregate carries the six
-// rigid-body modes of its nodes about its centroid c_a:   u_i = t + w x (x_i - c_a),  theta_i = w,  with the
-// constrained DOFs masked out, so Z has 6 columns per aggregate and one 6x6 block T_i per node,
+// rigid-body modes of its nodes about a reference point c_a (its centroid, or the box centre in a sharded solve -- the
+// coarse space is the same for any point):   u_i = t + w x (x_i - c_a),  theta_i = w,  with the constrained DOFs masked
+// out, so Z has 6 columns per aggregate and one 6x6 block T_i per node,
 //     T_i = M_i [ I  -[d_i]x ; 0  I ],   d_i = x_i - c_a,  M_i = diag(free DOF mask).
 // The reference hands SuperLU's factorisation of the whole interface matrix to its PCG as the preconditioner
 // (lattice_sim.py:1333-1415) and converges in a few iterations; a host factorisation cannot run inside the device
 // loop, and block-Jacobi alone leaves the long-wavelength modes of a stretch-dominated lattice to the Krylov space
-// (888 iterations on the 100^3 octet lattice).  The coarse space removes them: E is small (6 n_agg, dense), its
-// inverse is formed once by the host through a library factorisation, and every iteration adds
+// (888 iterations on the 100^3 octet lattice; 139 with the coarse space).  E is small (6 n_agg, dense), its inverse is
+// formed once by the host through a library factorisation, and every iteration adds, between the update kernel (which
+// produces r and u = D^-1 r) and the product kernel (which needs the final u),
 //     k_coarse_restrict : rc = Z^T r          one CTA per aggregate (piece), fixed-order reduction
 //     k_coarse_solve    : u += Z (Einv rc)    one CTA per aggregate: 6 rows of the dense inverse, then its nodes
-// (large aggregates: + k_coarse_gather / k_coarse_prolong, see below) between the update kernel (which produces r and u = D^-1 r) and the product kernel (which needs the final u).
-// Both kernels stream r / u once (16 B per DOF) and Einv once (8 n_c^2 B); the additive form keeps M^-1 symmetric
-// positive definite whatever the aggregates are, so the Chronopoulos-Gear recurrences are unchanged.
+// (aggregates of more than COARSE_PIECE nodes: + k_coarse_gather / k_coarse_prolong, see "per-iteration kernels").
+// The node passes stream r once and u twice (48 B per node each) plus a 16-byte table entry per node, the coarse product
+// streams Einv once (8 n_c^2 B).  The additive form keeps M^-1 symmetric positive definite whatever the aggregates are,
+// so the Chronopoulos-Gear recurrences, the stop test and the true-residual safeguard are unchanged.
+// Sharded solves (lattice_solver.cu, pcg_run_dist_impl): the listed nodes are the rank's OWNED nodes, the coarse residual
+// is all-reduced by k_coarse_gather_p2p (LL words into every rank's peer-memory inbox) or NCCL.
 #pragma once
 #include "common.cuh"
 

@@ -342,6 +342,7 @@ class Context:
     # ---- two-level preconditioner (csrc/coarse.cuh; host policy in coarse.py) ----
     def coarse_setup(self, x, y, z, node_agg, agg_ptr, agg_nodes, fixed=None, centers=None):
         self._coarse_keep = None
+        self._coarse_owner = None
         self.check(self.lib.lat_coarse_setup(self.h, _ptr(x), _ptr(y), _ptr(z), x.numel(), _ptr(node_agg), _ptr(agg_ptr),
                                              _ptr(agg_nodes), agg_ptr.numel() - 1, _ptr(fixed), _ptr(centers)))
 

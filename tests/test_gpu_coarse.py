@@ -95,6 +95,12 @@ def test_two_level_error_paths(ctx):
     with tl:
         with pytest.raises(L.LatticeB200Error, match="Chronopoulos-Gear"):
             fem.solve(P["fixed"], P["g"], P["f"], reference_semantics=True, mintol=0.0, alpha_max=0.0)
+    # two coarse spaces on one context: the tables are re-built when the first one is used again
+    tl_b = fem.two_level(P["fixed"], 27)
+    u_a, _, i_a = fem.solve(P["fixed"], P["g"], P["f"], tol=1e-10, two_level=tl)
+    u_b, _, i_b = fem.solve(P["fixed"], P["g"], P["f"], tol=1e-10, two_level=tl_b)
+    assert i_a["info"] == 0 and i_b["info"] == 0 and i_a["two_level"] and i_b["two_level"]
+    assert float((u_a - u_b).abs().max()) < 1e-7 * float(u_a.abs().max())
     # a coarse space of another system is refused, not silently applied
     P2 = _problem(ctx, "BCC", 2, 1, 8)
     with tl:
