@@ -323,9 +323,9 @@ class DistributedFEM:
         gi, gj, gk = np.meshgrid(np.arange(nb[0]), np.arange(nb[1]), np.arange(nb[2]), indexing="ij")
         cen = lo_h[None, :] + (np.stack([gi.ravel(), gj.ravel(), gk.ravel()], 1) + 0.5) * (ext / nb)[None, :]
         vals = self.vals
-        if vals is None:
-            vals = self.ctx.assemble_bsr(self.x, self.y, self.z, self.en0, self.en1, self.rad, self.n_local, self.nnzb,
-                                         self.young, self.nu, self.kappa)
+        if vals is None:            # temporary assembly (the subclass' operator for the joint-only system)
+            vals = self.assemble()
+            self.vals = None
         allred = (lambda E: dist.all_reduce(E)) if self.world > 1 else None
         return coarse.TwoLevel(ctx, self.x, self.y, self.z, self.fixed_d, self.rowptr, self.colidx, vals, agg=agg, n_agg=n_agg,
                                n_owned=self.n_owned, centers=torch.from_numpy(cen).to(dev), allreduce=allred)

@@ -65,6 +65,22 @@ def main():
                     ok = ok and info["info"] == 0 and info["two_level"] and eu < 1e-8 and er < 1e-8 and abs(info["iters"] - it1[0]) <= 3
         ctx.p2p_destroy()
         del dfem
+        # the joint-only (strut-condensed) system, sharded, with the coarse space over the joints
+        if m_ > 1:
+            jf = D.DistributedJointFEM(ctx, mesh, E, NU, rank, world)
+            nj = 6 * mesh.n_points
+            jf.set_bc(fixed[:nj], g[:nj], f[:nj])
+            jf.enable_p2p()
+            uj, Rj, info = jf.solve(tol=1e-12, maxiter=100000, precond=L.PC_BLOCK6, two_level=n_agg)
+            uj0, _, info0 = jf.solve(tol=1e-12, maxiter=100000, precond=L.PC_BLOCK6, persistent=False)
+            ujg = jf.gather_owned(uj)
+            if rank == 0:
+                eu = np.abs(ujg - uo[:nj]).max() / np.abs(uo).max()
+                print(f"[dist_two_level] joint-only {geom}{n} m={m_} world={world} n_dof={nj} iters={info['iters']} (block-Jacobi {info0['iters']}) "
+                      f"info={info['info']} two_level={info['two_level']} |u-uo|/|uo|={eu:.2e}", flush=True)
+                ok = ok and info["info"] == 0 and info["two_level"] and eu < 1e-8
+            ctx.p2p_destroy()
+            del jf
     if n_big > 0:
         t0 = time.perf_counter()
         dfem = D.DistributedFEM.from_generator(ctx, "Octet", (n_big,) * 3, [0.03], 1, E, NU, rank, world)
