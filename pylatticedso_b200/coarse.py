@@ -24,25 +24,39 @@ def default_aggregates(n_nodes):
     return int(max(8, min(1000, round(n_nodes / 500.0))))
 
 
+def box_grid(lo, hi, target):
+    """Boxes per axis (numpy int64 [3]) of a regular grid over [lo, hi] with about ``target`` boxes, as cubic as the
+    extents allow; flat axes get one box.  Pure host arithmetic: the ranks of a sharded solve call it with the GLOBAL
+    bounds and get the same grid."""
+    ext = np.maximum(np.asarray(hi, dtype=np.float64) - np.asarray(lo, dtype=np.float64), 1e-300)
+    live = ext > 1e-9 * ext.max()
+    h = (np.prod(ext[live]) / max(1, int(target))) ** (1.0 / max(1, int(live.sum())))
+    return np.where(live, np.maximum(1, np.round(ext / h)), 1).astype(np.int64), ext
+
+
+def box_index(x, y, z, lo, ext, nb):
+    """Flat box index (torch int64) of every node: (i * nb_y + j) * nb_z + k, nodes on the upper faces in the last box."""
+    ijk = []
+    for k, c in enumerate((x, y, z)):
+        ijk.append(((c - float(lo[k])) / float(ext[k]) * float(nb[k])).floor().long().clamp_(0, int(nb[k]) - 1))
+    return (ijk[0] * int(nb[1]) + ijk[1]) * int(nb[2]) + ijk[2]
+
+
+def box_centers(lo, ext, nb):
+    """Centres of all boxes in flat-index order (numpy [prod(nb), 3])."""
+    gi, gj, gk = np.meshgrid(np.arange(nb[0]), np.arange(nb[1]), np.arange(nb[2]), indexing="ij")
+    return np.asarray(lo, dtype=np.float64)[None, :] + (np.stack([gi.ravel(), gj.ravel(), gk.ravel()], 1) + 0.5) * (ext / nb)[None, :]
+
+
 def box_aggregates(x, y, z, target):
     """Aggregate index per node (torch int64 on the nodes' device) and the number of aggregates: a regular grid of
     boxes over the bounding box, box counts per axis proportional to the extents, empty boxes dropped."""
     import torch
     target = int(max(1, min(target, MAX_AGGREGATES)))
-    lo = torch.stack([x.min(), y.min(), z.min()])
-    hi = torch.stack([x.max(), y.max(), z.max()])
-    ext = (hi - lo).clamp_min(1e-300).cpu().numpy()
-    live = ext > 1e-9 * ext.max()
-    # boxes as cubic as the target allows: n_k ~ ext_k / h with prod(n_k) ~ target
-    h = (np.prod(ext[live]) / target) ** (1.0 / max(1, int(live.sum())))
-    nb = np.where(live, np.maximum(1, np.round(ext / h)), 1).astype(np.int64)
-    nbt = torch.from_numpy(nb).to(x.device)
-    ijk = []
-    for k, c in enumerate((x, y, z)):
-        t = ((c - lo[k]) / float(ext[k]) * float(nb[k])).floor().long().clamp_(0, int(nb[k]) - 1)
-        ijk.append(t)
-    flat = (ijk[0] * nbt[1] + ijk[1]) * nbt[2] + ijk[2]
-    uniq, inv = torch.unique(flat, return_inverse=True)
+    lo = torch.stack([x.min(), y.min(), z.min()]).cpu().numpy()
+    hi = torch.stack([x.max(), y.max(), z.max()]).cpu().numpy()
+    nb, ext = box_grid(lo, hi, target)
+    uniq, inv = torch.unique(box_index(x, y, z, lo, ext, nb), return_inverse=True)
     return inv, int(uniq.numel())
 
 

@@ -310,18 +310,11 @@ class DistributedFEM:
             dist.all_reduce(hi, op=dist.ReduceOp.MAX)
             dist.all_reduce(n_glob)
         target = int(n_aggregates or coarse.default_aggregates(int(n_glob.item())))
-        ext = (hi - lo).clamp_min(1e-300).cpu().numpy()
         lo_h = lo.cpu().numpy()
-        live = ext > 1e-9 * ext.max()
-        h = (np.prod(ext[live]) / target) ** (1.0 / max(1, int(live.sum())))
-        nb = np.where(live, np.maximum(1, np.round(ext / h)), 1).astype(np.int64)
-        ijk = []
-        for k, c in enumerate((self.x, self.y, self.z)):
-            ijk.append(((c - float(lo_h[k])) / float(ext[k]) * float(nb[k])).floor().long().clamp_(0, int(nb[k]) - 1))
-        agg = (ijk[0] * int(nb[1]) + ijk[1]) * int(nb[2]) + ijk[2]         # global box index, empty boxes kept
+        nb, ext = coarse.box_grid(lo_h, hi.cpu().numpy(), min(target, coarse.MAX_AGGREGATES))
+        agg = coarse.box_index(self.x, self.y, self.z, lo_h, ext, nb)       # global box index, empty boxes kept
         n_agg = int(nb.prod())
-        gi, gj, gk = np.meshgrid(np.arange(nb[0]), np.arange(nb[1]), np.arange(nb[2]), indexing="ij")
-        cen = lo_h[None, :] + (np.stack([gi.ravel(), gj.ravel(), gk.ravel()], 1) + 0.5) * (ext / nb)[None, :]
+        cen = coarse.box_centers(lo_h, ext, nb)
         vals = self.vals
         if vals is None:            # temporary assembly (the subclass' operator for the joint-only system)
             vals = self.assemble()

@@ -44,3 +44,34 @@ def test_stretch_dominated_rule():
     assert stretch_dominated(M.mesh_from_synthetic(M.synthetic_lattice("Octet", (12, 12, 12), [0.03]), 1))
     assert stretch_dominated(M.mesh_from_synthetic(M.synthetic_lattice("Octet", (12, 12, 12), [0.03]), 3))   # subdivision does not matter
     assert not stretch_dominated(M.mesh_from_synthetic(M.synthetic_lattice("BCC", (12, 12, 12), [0.05]), 2))
+
+
+def test_sharded_aggregates_agree_across_slabs():
+    """What DistributedFEM.two_level does on the host: every rank cuts the boxes over the GLOBAL bounding box, so a node
+    gets the same aggregate on the rank that owns it and on the ranks that see it as a ghost; compacting the global
+    numbering gives the single-GPU (and oracle) aggregates."""
+    from pylatticedso_b200 import distributed as D
+    lat = M.synthetic_lattice("Octet", (6, 3, 3), [0.03])
+    m = M.mesh_from_synthetic(lat, 1)
+    lo, hi = m.xyz.min(0), m.xyz.max(0)
+    nb, ext = coarse.box_grid(lo, hi, 12)
+    t = torch.from_numpy
+    g_idx = coarse.box_index(t(m.x), t(m.y), t(m.z), lo, ext, nb).numpy()
+    assert g_idx.min() >= 0 and g_idx.max() < nb.prod()
+    cen = coarse.box_centers(lo, ext, nb)
+    assert cen.shape == (nb.prod(), 3) and np.all(cen >= lo) and np.all(cen <= hi)
+    # every node lies in the box it is assigned to
+    half = 0.5 * ext / nb
+    assert np.all(np.abs(m.xyz - cen[g_idx]) <= half + 1e-12)
+    world = 3
+    owned_total = 0
+    for rank in range(world):
+        part = D.partition_slab(m, rank, world)
+        lm = D.local_mesh(m, part)
+        l_idx = coarse.box_index(t(lm.x), t(lm.y), t(lm.z), lo, ext, nb).numpy()      # local numbering [owned | ghosts]
+        assert (l_idx == g_idx[part.local_nodes]).all()
+        owned_total += part.n_owned
+    assert owned_total == m.n_nodes                                                    # every node restricted exactly once
+    a_o, n_o = co.box_aggregates(m.xyz, 12)
+    uniq, inv = np.unique(g_idx, return_inverse=True)
+    assert n_o == len(uniq) and (inv == a_o).all()
