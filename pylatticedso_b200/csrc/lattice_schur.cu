@@ -1408,36 +1408,61 @@ extern "C" int lat_assemble_cells_bsr(lat_ctx* ctx, const double* S, int64_t s_s
 
 
 // Gather form of the same assembly: a PLAN (built once per interface pattern by the host: ddm.InterfaceProblem) lists for
-// every BSR block the (cell, row node, column node) contributions, sorted by block.  One warp per block adds its
+// every BSR block the (cell, row node, column node) contributions, sorted by block.  Eight lanes per block add its
 // contributions in plan order -- fixed summation order (bit-reproducible matrix, unlike the FP64 reductions above), no
 // atomics, every S entry read once and every block written once: the assembly of a design iteration (new radii -> new
 // S, same plan) moves 8 nB^2 per cell + 288 B per block.
-// contrib[k] = (cell * nbn + a) * nbn + b.
+// contrib[k] = (cell * nbn + a) * nbn + b.  A group of lanes per block adds its contributions in plan order.
+// Eight lanes per block (four blocks per warp, so four independent chains blk_ptr -> contrib -> S per warp are in flight):
+// lane sl of a group owns entries sl, sl + 8, ..., sl + 32 (< 36) of the 6x6 block; two contributions are fetched per trip.
 __global__ void __launch_bounds__(256) k_assemble_cells_gather(const double* __restrict__ S, int64_t s_stride, int nbn,
                                                                const int32_t* __restrict__ blk_ptr, const int64_t* __restrict__ contrib,
                                                                int64_t nnzb, double* __restrict__ vals) {
-  const int lane = threadIdx.x & 31;
-  const int64_t l = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int sl = threadIdx.x & 7;
+  const int64_t l = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
   if (l >= nnzb) return;
   const int nb = 6 * nbn;
-  const int lo = blk_ptr[l], hi = blk_ptr[l + 1];
-  // lane -> entries (i0, j0) = lane / 6, lane % 6 and, for lanes 0..3, entry 32 + lane
-  const int i0 = lane / 6, j0 = lane - i0 * 6;
-  const int k1 = 32 + lane, i1 = k1 / 6, j1 = k1 - i1 * 6;
-  double acc0 = 0.0, acc1 = 0.0;
-  for (int k = lo; k < hi; ++k) {
-    const int64_t d = __ldg(contrib + k);
+  const int lo = __ldg(blk_ptr + l), hi = __ldg(blk_ptr + l + 1);
+  int off[5];
+#pragma unroll
+  for (int m = 0; m < 5; ++m) {
+    const int e = sl + 8 * m;
+    off[m] = e < 36 ? (e / 6) * nb + (e % 6) : 0;
+  }
+  const bool last = sl < 4;                    // entries 32..35
+  double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  auto base_of = [&](int64_t d) -> const double* {
     const int64_t ca = d / nbn;
     const int b = (int)(d - ca * nbn);
     const int64_t c = ca / nbn;
     const int a = (int)(ca - c * nbn);
-    const double* Sc = S + c * s_stride + (int64_t)(a * 6) * nb + b * 6;
-    acc0 += __ldg(Sc + (int64_t)i0 * nb + j0);
-    if (lane < 4) acc1 += __ldg(Sc + (int64_t)i1 * nb + j1);
+    return S + c * s_stride + (int64_t)(a * 6) * nb + b * 6;
+  };
+  int k = lo;
+  for (; k + 1 < hi; k += 2) {
+    const int64_t d0 = __ldg(contrib + k), d1 = __ldg(contrib + k + 1);
+    const double* s0 = base_of(d0);
+    const double* s1 = base_of(d1);
+    double v0[5], v1[5];
+#pragma unroll
+    for (int m = 0; m < 5; ++m) {
+      const bool on = m < 4 || last;
+      v0[m] = on ? __ldg(s0 + off[m]) : 0.0;
+      v1[m] = on ? __ldg(s1 + off[m]) : 0.0;
+    }
+#pragma unroll
+    for (int m = 0; m < 5; ++m) { acc[m] += v0[m]; acc[m] += v1[m]; }      // plan order
+  }
+  if (k < hi) {
+    const double* s0 = base_of(__ldg(contrib + k));
+#pragma unroll
+    for (int m = 0; m < 5; ++m)
+      if (m < 4 || last) acc[m] += __ldg(s0 + off[m]);
   }
   double* dst = vals + l * 36;
-  dst[lane] = acc0;
-  if (lane < 4) dst[32 + lane] = acc1;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) dst[sl + 8 * m] = acc[m];
+  if (last) dst[32 + sl] = acc[4];
 }
 
 extern "C" int lat_assemble_cells_bsr_plan(lat_ctx* ctx, const double* S, int64_t s_stride, int32_t n_bnd_nodes,
@@ -1447,7 +1472,7 @@ extern "C" int lat_assemble_cells_bsr_plan(lat_ctx* ctx, const double* S, int64_
   LAT_CHECK_ARG(ctx, 6 * n_bnd_nodes <= SCHUR_MAX_NB);
   LAT_CHECK_ARG(ctx, s_stride == 0 || s_stride >= (int64_t)36 * n_bnd_nodes * n_bnd_nodes);
   LAT_CUDA(ctx, cudaSetDevice(ctx->device));
-  LAT_LAUNCH(ctx, k_assemble_cells_gather, (unsigned)ceil_div(nnzb, 8), 256, 0, S, s_stride, (int)n_bnd_nodes, blk_ptr, contrib, nnzb, vals);
+  LAT_LAUNCH(ctx, k_assemble_cells_gather, (unsigned)ceil_div(nnzb, 32), 256, 0, S, s_stride, (int)n_bnd_nodes, blk_ptr, contrib, nnzb, vals);
   return LAT_OK;
 }
 
