@@ -25,7 +25,9 @@ Every line also carries
            matrix-free at full size + the CUDA path against the CPU oracle's direct solve on a BCC 6^3 case.
            The process exits non-zero when a figure is above 1e-8 (u, R) / 1e-6 (gradient).
   config5  BASELINE configs[4]: Octet 100^3 (24.4 M DOF), r = 0.03, strong scaling over the N GPUs, generated
-           per slab on each rank; assembled and matrix-free solve to 1e-8, time to first iteration, host RSS.
+           per slab on each rank; assembled and matrix-free solve to 1e-8, time to first iteration, host RSS;
+           matrix_free_two_level: the same matrix-free solve with the two-level preconditioner (csrc/coarse.cuh).
+  ddm_config3 (N = 1)  BASELINE configs[3] through the DDM path, block-Jacobi and two-level interface solve.
 The reference arm (--impl reference) runs the SAME (20 N) x 20 x 20 workload with Jacobi-PCG (C/OpenMP oracle
 port) on all host threads of the box (the thread count is set explicitly: torchrun exports OMP_NUM_THREADS=1).
 """
