@@ -125,12 +125,21 @@ class TwoLevel:
         fx = None if fixed is None else fixed.to(torch.uint8).contiguous()
         cen = None if centers is None else centers.to(torch.float64).contiguous()
         self._setup_args = (x, y, z, self.node_agg, self.agg_ptr, self.agg_nodes, fx, cen)
-        self._make_resident()
-        self.E = ctx.coarse_galerkin(rowptr, colidx, vals, n_agg, n_rows=n_owned)
-        if allreduce is not None:
-            allreduce(self.E)
-        self.Einv = invert_coarse(self.E)
+        self._pattern, self._n_owned, self._allreduce = (rowptr, colidx), n_owned, allreduce
         self.active = False
+        self.update(vals)
+
+    def update(self, vals):
+        """New matrix values on the same mesh, constraints and aggregates (a design iteration changes the radii, not the
+        lattice): only the Galerkin product and the dense factorisation are redone."""
+        self._make_resident()
+        self.E = self.ctx.coarse_galerkin(self._pattern[0], self._pattern[1], vals, self.n_agg, n_rows=self._n_owned)
+        if self._allreduce is not None:
+            self._allreduce(self.E)
+        self.Einv = invert_coarse(self.E)
+        if self.active:
+            self.ctx.coarse_set_inverse(self.Einv)
+        return self
 
     def _make_resident(self):
         """A context holds ONE coarse space (node tables); building another TwoLevel on the same context replaces them, so

@@ -101,6 +101,17 @@ def test_two_level_error_paths(ctx):
     u_b, _, i_b = fem.solve(P["fixed"], P["g"], P["f"], tol=1e-10, two_level=tl_b)
     assert i_a["info"] == 0 and i_b["info"] == 0 and i_a["two_level"] and i_b["two_level"]
     assert float((u_a - u_b).abs().max()) < 1e-7 * float(u_a.abs().max())
+    # a design iteration: new radii on the same lattice -> TwoLevel.update(new matrix) == a freshly built coarse space
+    E_old = tl.E.clone()
+    fem.set_radii(P["m"].rad * 1.3)
+    fem.assemble()
+    tl.update(fem.vals)
+    E_new = fem.two_level(P["fixed"], 8).E
+    assert float((tl.E - E_new).abs().max()) < 1e-12 * float(E_new.abs().max())
+    assert float((tl.E - E_old).abs().max()) > 0.1 * float(E_old.abs().max())        # the matrix did change
+    u_c, _, i_c = fem.solve(P["fixed"], P["g"], P["f"], tol=1e-10, two_level=tl)
+    u_d, _, i_d = fem.solve(P["fixed"], P["g"], P["f"], tol=1e-10)
+    assert i_c["info"] == 0 and i_c["two_level"] and float((u_c - u_d).abs().max()) < 1e-7 * float(u_d.abs().max())
     # a coarse space of another system is refused, not silently applied
     P2 = _problem(ctx, "BCC", 2, 1, 8)
     with tl:
