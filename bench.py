@@ -307,7 +307,7 @@ def config5_section(ctx, rank, world, hbm_peak, n=100):
     t0 = time.perf_counter()
     if world == 1:
         from pylatticedso_b200.fem import BeamFEM
-        lm, part = D.generate_slab("Octet", (n, n, n), [0.03], 1, 0, 1)
+        lm, part = D.generate_slab("Octet", (n, n, n), [0.03], 1, 0, 1, device=dev)
         fixed, g, f = D.compression_bc_local(lm)
 
         class _Single:          # the single-GPU path behind the same few calls the sharded one offers

@@ -171,18 +171,19 @@ def slab_layers(n_layers, world):
 
 
 def generate_slab(geom_types, n_cells, radii, elements_per_strut, rank, world, cell_size=(1.0, 1.0, 1.0),
-                  grad_radius=None, cell_radii=None):
+                  grad_radius=None, cell_radii=None, device=None):
     """Per-slab lattice generation: the rank builds ONLY its own cell layers plus one overlap layer on each side
     (host time and memory ~ 1/world of the full lattice) and returns (local BeamMesh in [owned | ghosts] numbering,
     SlabPartition).  No global numbering exists on this path: both sides of an exchange order the shared nodes by
     their rank in the generator's numbering, which is monotone in the reference's global numbering
     (lattice points by (x, y, z), strut-interior nodes beam-major), so send and receive lists agree without
-    communication -- the same contract as :func:`partition_slab`."""
+    communication -- the same contract as :func:`partition_slab`.  ``device``: torch device for the numbering of the
+    lattice points (``mesh._grid_lattice_torch``; bit-identical to the host path)."""
     from .mesh import synthetic_lattice, mesh_from_synthetic
     nx = int(n_cells[0])
     i0, i1 = slab_layers(nx, world)[rank]
     lat = synthetic_lattice(geom_types, n_cells, radii, cell_size=cell_size, grad_radius=grad_radius,
-                            cell_radii=cell_radii, i_range=(i0 - 1, i1 + 1))
+                            cell_radii=cell_radii, i_range=(i0 - 1, i1 + 1), device=device)
     mesh = mesh_from_synthetic(lat, elements_per_strut)
     cs = float(cell_size[0])
     # cell-plane coordinates exactly as the generator accumulates them (lattice.py:433-442)
@@ -226,7 +227,7 @@ class DistributedFEM:
         import torch
         import torch.distributed as dist
         lm, part = generate_slab(geom_types, n_cells, radii, elements_per_strut, rank, world, cell_size, grad_radius,
-                                 cell_radii)
+                                 cell_radii, device=ctx.device)
         self = cls(ctx, None, young, nu, rank, world, kappa, part=part, lmesh=lm)
         # global sizes: owned nodes, and elements counted once (by the owner of their first node)
         cnt = torch.tensor([part.n_owned, int((lm.en0 < part.n_owned).sum())], dtype=torch.int64)

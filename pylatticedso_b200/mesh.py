@@ -314,8 +314,68 @@ def _grid_lattice(tables, ci, cj, ck, gcell, org, size, cr, dims, i_lo, i_hi):
     return (pxyz, n1[binst], n2[binst], cr[bcell_l, geom_of_row[brow]], gcell[bcell_l], geom_of_row[brow])
 
 
+def _grid_lattice_torch(tables, ci, cj, ck, gcell, org, size, cr, dims, i_lo, i_hi, device):
+    """:func:`_grid_lattice` with the large scatters, prefix sums and gathers as torch ops on ``device`` (the GPU of the
+    rank that generates its slab): "first creation wins" = the LOWEST creating instance = ``scatter_reduce(amin)``, which
+    is deterministic; every floating-point expression is the same elementwise one.  Bit-identical outputs
+    (tests/test_mesh.py compares the two on CPU tensors); returns numpy arrays like the numpy path."""
+    import torch
+    nx, ny, nz = dims
+    T = np.concatenate(tables, axis=0)
+    geom_of_row = np.concatenate([np.full(t.shape[0], g, dtype=np.int64) for g, t in enumerate(tables)])
+    T2 = np.rint(T * 2.0).astype(np.int64)
+    nbt, ncl = T2.shape[0], ci.shape[0]
+    Gy, Gz = 2 * ny + 1, 2 * nz + 1
+    n_slots = (2 * (i_hi - i_lo) + 1) * Gy * Gz
+    dev = torch.device(device)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    cbase = t(((2 * (ci - i_lo)) * Gy + 2 * cj) * Gz + 2 * ck)
+    off1 = (T2[:, 0] * Gy + T2[:, 1]) * Gz + T2[:, 2]
+    off2 = (T2[:, 3] * Gy + T2[:, 4]) * Gz + T2[:, 5]
+    key1 = (cbase[:, None] + t(off1)[None, :]).reshape(-1)
+    key2 = (cbase[:, None] + t(off2)[None, :]).reshape(-1)
+    n_inst = int(key1.shape[0])
+    BIG = 2 ** 62
+    # creation index: ends 1 of all instances (0 .. n_inst-1) come before ends 2 (n_inst ..): the first creation of a
+    # grid point is the minimum over everything that lands on it
+    first = torch.full((n_slots,), BIG, dtype=torch.int64, device=dev)
+    first.scatter_reduce_(0, torch.cat([key1, key2]), torch.arange(2 * n_inst, dtype=torch.int64, device=dev), "amin")
+    occ = first < BIG
+    node_of_slot = torch.cumsum(occ, 0) - 1
+    fidx = first[occ]
+    npnt = int(fidx.shape[0])
+    del first, occ
+    end2 = fidx >= n_inst
+    inst = torch.where(end2, fidx - n_inst, fidx)
+    cell_l, row = inst // nbt, inst % nbt
+    Tt = t(T)
+    frac = torch.where(end2[:, None], Tt[row, 3:6], Tt[row, 0:3])
+    pxyz = frac * t(size)[None, :] + t(org)[cell_l]
+    n1 = node_of_slot[key1]
+    n2 = node_of_slot[key2]
+    del node_of_slot, key1, key2
+    swap = off2 < off1
+    d = np.where(swap[:, None], T2[:, 0:3] - T2[:, 3:6], T2[:, 3:6] - T2[:, 0:3])
+    dkey = (d[:, 0] * (4 * Gy) + d[:, 1]) * (4 * Gz) + d[:, 2]
+    codes_u, code = np.unique(dkey, return_inverse=True)
+    nd = int(codes_u.shape[0])
+    code = code.ravel().astype(np.int64)
+    lo = torch.where(t(swap).repeat(ncl), n2, n1)
+    bkey = lo * nd + t(code).repeat(ncl)
+    del lo
+    bfirst = torch.full((npnt * nd,), BIG, dtype=torch.int64, device=dev)
+    bfirst.scatter_reduce_(0, bkey, torch.arange(n_inst, dtype=torch.int64, device=dev), "amin")
+    del bkey
+    binst = bfirst[bfirst < BIG]                                   # already in (lower end, upper end) order
+    del bfirst
+    bcell_l, brow = binst // nbt, binst % nbt
+    g_row = t(geom_of_row)[brow]
+    out = (pxyz, n1[binst], n2[binst], t(cr)[bcell_l, g_row], t(gcell)[bcell_l], g_row)
+    return tuple(o.cpu().numpy() for o in out)
+
+
 def synthetic_lattice(geom_types, n_cells, radii, cell_size=(1.0, 1.0, 1.0),
-                      grad_radius=None, cell_radii=None, i_range=None, _force_generic=False) -> SyntheticLattice:
+                      grad_radius=None, cell_radii=None, i_range=None, _force_generic=False, device=None) -> SyntheticLattice:
     """Regular lattice arrays in the reference numbering.
 
     ``i_range = (i_lo, i_hi)`` generates only the cell layers ``i_lo <= i < i_hi`` of the
@@ -329,6 +389,8 @@ def synthetic_lattice(geom_types, n_cells, radii, cell_size=(1.0, 1.0, 1.0),
     in the JSON ``gradient.radii`` block -- only ``"linear"``/``"constant"`` are
     evaluated here (``gradient_properties.py:104``); ``cell_radii``: optional
     ``[Nc, n_geom]`` explicit per-cell radii (cell-index order), overriding both.
+    ``device``: a torch device (e.g. the rank's GPU) on which the half-cell-grid numbering runs
+    (:func:`_grid_lattice_torch`, same result bit for bit); None = numpy on the host.
     """
     if isinstance(geom_types, str) or isinstance(geom_types, np.ndarray):
         geom_types = [geom_types]
@@ -367,7 +429,11 @@ def synthetic_lattice(geom_types, n_cells, radii, cell_size=(1.0, 1.0, 1.0),
     size = np.array(cs)
     if not _force_generic and all(np.abs(t * 2.0 - np.rint(t * 2.0)).max() < 1e-12 and t.min() >= 0.0 and t.max() <= 1.0
                                   for t in tables):
-        pxyz, p1, p2, brad, bcell, btype = _grid_lattice(tables, ci, cj, ck, gcell, org, size, cr, (nx, ny, nz), i_lo, i_hi)
+        if device is None:
+            pxyz, p1, p2, brad, bcell, btype = _grid_lattice(tables, ci, cj, ck, gcell, org, size, cr, (nx, ny, nz), i_lo, i_hi)
+        else:
+            pxyz, p1, p2, brad, bcell, btype = _grid_lattice_torch(tables, ci, cj, ck, gcell, org, size, cr, (nx, ny, nz),
+                                                                   i_lo, i_hi, device)
         return SyntheticLattice(pxyz=pxyz, b_p1=p1.astype(np.int64), b_p2=p2.astype(np.int64), b_rad=brad,
                                 b_cell=bcell.astype(np.int64), b_type=btype.astype(np.int64), n_cells=(nx, ny, nz),
                                 cell_size=cs, cell_radii=cr,
