@@ -171,7 +171,7 @@ def slab_layers(n_layers, world):
 
 
 def generate_slab(geom_types, n_cells, radii, elements_per_strut, rank, world, cell_size=(1.0, 1.0, 1.0),
-                  grad_radius=None, cell_radii=None, device=None):
+                  grad_radius=None, cell_radii=None, device=None, _general=False):
     """Per-slab lattice generation: the rank builds ONLY its own cell layers plus one overlap layer on each side
     (host time and memory ~ 1/world of the full lattice) and returns (local BeamMesh in [owned | ghosts] numbering,
     SlabPartition).  No global numbering exists on this path: both sides of an exchange order the shared nodes by
@@ -185,6 +185,18 @@ def generate_slab(geom_types, n_cells, radii, elements_per_strut, rank, world, c
     lat = synthetic_lattice(geom_types, n_cells, radii, cell_size=cell_size, grad_radius=grad_radius,
                             cell_radii=cell_radii, i_range=(i0 - 1, i1 + 1), device=device)
     mesh = mesh_from_synthetic(lat, elements_per_strut)
+    if world == 1 and not _general:
+        # one rank owns everything: the partition and the local numbering are the identity (no gathers, no copies)
+        nodes = np.arange(mesh.n_nodes, dtype=np.int64)
+        empty = np.zeros(0, dtype=np.int64)
+        part = SlabPartition(0, 1, nodes, empty, empty, np.arange(mesh.n_elems, dtype=np.int64), [], [], [])
+        lm = BeamMesh(x=mesh.x, y=mesh.y, z=mesh.z, en0=mesh.en0.astype(np.int32, copy=False), en1=mesh.en1.astype(np.int32, copy=False),
+                      rad=mesh.rad, beam_of_elem=mesh.beam_of_elem, chain=mesh.chain, n_points=mesh.n_points,
+                      point_index=nodes[: mesh.n_points], cell_of_elem=mesh.cell_of_elem,
+                      meta={"global_nodes": nodes, "is_point": nodes < mesh.n_points})
+        lm.meta["lattice"] = lat
+        lm.meta["layers"] = (i0, i1)
+        return lm, part
     cs = float(cell_size[0])
     # cell-plane coordinates exactly as the generator accumulates them (lattice.py:433-442)
     xs = np.concatenate([[0.0], np.cumsum(np.full(max(nx - 1, 0), cs))])[:nx]

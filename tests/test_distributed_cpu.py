@@ -186,3 +186,19 @@ def test_joint_only_partition_covers_every_strut_and_keeps_the_geometry():
         np.testing.assert_array_equal(lm.en1, f["len1"][f["chain_ptr"][1:] - 1])
     assert owned_total == mesh.n_points
     assert seen.min() == 1 and seen.max() == 2                       # struts across a cut are condensed on both sides
+
+
+def test_generate_slab_single_rank_fast_path_equals_the_general_path():
+    """world = 1: the identity partition is built directly; same mesh, same partition as the general code."""
+    from pylatticedso_b200 import distributed as D
+    for geom, n, m_ in (("Octet", (5, 4, 3), 1), ("BCC", (4, 3, 3), 3)):
+        a, pa = D.generate_slab(geom, n, [0.04], m_, 0, 1)
+        b, pb = D.generate_slab(geom, n, [0.04], m_, 0, 1, _general=True)
+        for k in ("x", "y", "z", "en0", "en1", "rad", "beam_of_elem", "chain", "point_index", "cell_of_elem"):
+            va, vb = getattr(a, k), getattr(b, k)
+            assert np.array_equal(va, vb) and va.dtype == vb.dtype, k
+        assert a.n_points == b.n_points and np.array_equal(a.meta["is_point"], b.meta["is_point"])
+        assert np.array_equal(a.meta["global_nodes"], b.meta["global_nodes"])
+        assert pa.n_owned == pb.n_owned and pa.n_local == pb.n_local and pa.peers == pb.peers == []
+        assert np.array_equal(pa.local_elems, pb.local_elems) and np.array_equal(pa.local_nodes, pb.local_nodes)
+        assert pa.send_lists == pb.send_lists == [] and pa.recv_counts == pb.recv_counts == []
